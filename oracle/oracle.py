@@ -1,0 +1,287 @@
+"""ctypes binding of the CPU oracle (oracle/shodh_oracle.c).
+
+TEST INFRASTRUCTURE ONLY.  Imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs; never by shodh_memory_b200/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liboracle.so")
+_SRC = os.path.join(_HERE, "shodh_oracle.c")
+
+DEFAULT_WEIGHTS = np.array([0.18, 0.17, 0.05, 0.05, 0.28, 0.14, 0.13], dtype=np.float32)
+
+METRIC_NEG_DOT, METRIC_EUCLIDEAN, METRIC_COSINE = 0, 1, 2
+VARIANT_SCALAR, VARIANT_AVX2 = 0, 1
+
+
+def build(force: bool = False) -> str:
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
+        subprocess.check_call(["sh", os.path.join(_HERE, "build.sh")])
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        f32p, u32p, u64p, i64p = (C.POINTER(C.c_float), C.POINTER(C.c_uint32),
+                                  C.POINTER(C.c_uint64), C.POINTER(C.c_int64))
+        L.so_dot.restype = C.c_float
+        L.so_dot.argtypes = [f32p, f32p, C.c_uint32, C.c_int]
+        L.so_euclidean_squared.restype = C.c_float
+        L.so_euclidean_squared.argtypes = [f32p, f32p, C.c_uint32]
+        L.so_l2_norm.restype = C.c_float
+        L.so_l2_norm.argtypes = [f32p, C.c_uint32]
+        L.so_l2_norm_squared.restype = C.c_float
+        L.so_l2_norm_squared.argtypes = [f32p, C.c_uint32]
+        L.so_normalized_distance.restype = C.c_float
+        L.so_normalized_distance.argtypes = [f32p, f32p, C.c_uint32, C.c_int]
+        L.so_cosine_similarity.restype = C.c_float
+        L.so_cosine_similarity.argtypes = [f32p, C.c_uint32, f32p, C.c_uint32, C.c_int]
+        L.so_cosine_similarity_inline.restype = C.c_float
+        L.so_cosine_similarity_inline.argtypes = [f32p, f32p, C.c_uint32]
+        L.so_normalize_inplace.restype = None
+        L.so_normalize_inplace.argtypes = [f32p, C.c_uint32]
+        L.so_total_order_key.restype = C.c_uint32
+        L.so_total_order_key.argtypes = [C.c_float]
+        L.so_brute_force_search.restype = C.c_uint32
+        L.so_brute_force_search.argtypes = [f32p, C.c_uint64, C.c_uint32, u32p, f32p, C.c_uint32,
+                                            C.c_int, C.c_int, C.c_int, u32p, f32p]
+        L.so_brute_force_search_batch.restype = C.c_int
+        L.so_brute_force_search_batch.argtypes = [f32p, C.c_uint64, C.c_uint32, u32p, f32p,
+                                                  C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int,
+                                                  C.c_int, u32p, f32p, u32p]
+        L.so_score_rows.restype = None
+        L.so_score_rows.argtypes = [f32p, C.c_uint32, f32p, u32p, C.c_uint32, C.c_int, C.c_int, f32p]
+        L.so_top_k_similar.restype = C.c_uint32
+        L.so_top_k_similar.argtypes = [f32p, C.c_uint32, f32p, C.c_uint64, C.c_uint32, C.c_uint32,
+                                       C.c_int, u32p, f32p]
+        L.so_search_ids_post.restype = C.c_uint32
+        L.so_search_ids_post.argtypes = [u32p, f32p, C.c_uint32, u64p, C.c_uint64, C.c_uint32,
+                                         u64p, f32p]
+        L.so_calibrate_score.restype = C.c_float
+        L.so_calibrate_score.argtypes = [C.c_float]
+        L.so_fuse_scores_full.restype = C.c_float
+        L.so_fuse_scores_full.argtypes = [f32p] + [C.c_float] * 5 + [C.c_uint32, C.c_float]
+        L.so_apply_recency_boost.restype = C.c_float
+        L.so_apply_recency_boost.argtypes = [C.c_float, C.c_int64, C.c_int64, C.c_uint64, C.c_float]
+        L.so_fuse_rank.restype = C.c_uint32
+        L.so_fuse_rank.argtypes = [f32p] * 6 + [u32p, f32p, i64p, C.c_uint32, C.c_int64, C.c_uint64,
+                                                C.c_float, C.c_float, C.c_float, C.c_uint32, u32p,
+                                                f32p, f32p]
+        L.so_pool_finalize.restype = None
+        L.so_pool_finalize.argtypes = [f32p, i64p, C.c_uint32, C.c_uint32, f32p]
+        L.so_synth_corpus.restype = None
+        L.so_synth_corpus.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, f32p]
+        L.so_synth_queries.restype = None
+        L.so_synth_queries.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, f32p, u64p]
+        L.so_round_f16.restype = None
+        L.so_round_f16.argtypes = [f32p, f32p, C.c_uint64]
+        L.so_max_threads.restype = C.c_int
+        L.so_max_threads.argtypes = []
+        _lib = L
+    return _lib
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a: np.ndarray, ty):
+    return a.ctypes.data_as(C.POINTER(ty))
+
+
+def dot(a, b, variant=VARIANT_SCALAR) -> float:
+    a, b = _f32(a), _f32(b)
+    assert a.shape == b.shape
+    return float(lib().so_dot(_p(a, C.c_float), _p(b, C.c_float), a.size, variant))
+
+
+def euclidean_squared(a, b) -> float:
+    a, b = _f32(a), _f32(b)
+    return float(lib().so_euclidean_squared(_p(a, C.c_float), _p(b, C.c_float), a.size))
+
+
+def l2_norm(a) -> float:
+    a = _f32(a)
+    return float(lib().so_l2_norm(_p(a, C.c_float), a.size))
+
+
+def normalized_distance(a, b, variant=VARIANT_SCALAR) -> float:
+    a, b = _f32(a), _f32(b)
+    return float(lib().so_normalized_distance(_p(a, C.c_float), _p(b, C.c_float), a.size, variant))
+
+
+def cosine_similarity(a, b, variant=VARIANT_SCALAR) -> float:
+    a, b = _f32(a), _f32(b)
+    return float(lib().so_cosine_similarity(_p(a, C.c_float), a.size, _p(b, C.c_float), b.size, variant))
+
+
+def cosine_similarity_inline(a, b) -> float:
+    a, b = _f32(a), _f32(b)
+    return float(lib().so_cosine_similarity_inline(_p(a, C.c_float), _p(b, C.c_float), a.size))
+
+
+def normalize(a) -> np.ndarray:
+    a = _f32(a).copy()
+    lib().so_normalize_inplace(_p(a, C.c_float), a.size)
+    return a
+
+
+def total_order_key(x: float) -> int:
+    return int(lib().so_total_order_key(C.c_float(x)))
+
+
+def deleted_bitmap(n: int, deleted_ids) -> np.ndarray:
+    bm = np.zeros((n + 31) // 32 + 1, dtype=np.uint32)
+    for i in deleted_ids:
+        bm[i >> 5] |= np.uint32(1 << (i & 31))
+    return bm
+
+
+def brute_force_search(corpus, query, k, deleted=None, metric=METRIC_NEG_DOT,
+                       variant=VARIANT_SCALAR, as_written=False):
+    """VamanaIndex::brute_force_search (vamana.rs:1167-1188) -> (ids u32[r], dist f32[r])."""
+    corpus = _f32(corpus)
+    n, dim = (corpus.shape if corpus.ndim == 2 else (0, 0))
+    query = _f32(query)
+    ids = np.zeros(max(k, 1), dtype=np.uint32)
+    dist = np.zeros(max(k, 1), dtype=np.float32)
+    bm = None if deleted is None else deleted_bitmap(n, deleted)
+    r = lib().so_brute_force_search(_p(corpus, C.c_float), n, dim,
+                                    None if bm is None else _p(bm, C.c_uint32),
+                                    _p(query, C.c_float), k, metric, variant, int(as_written),
+                                    _p(ids, C.c_uint32), _p(dist, C.c_float))
+    return ids[:r].copy(), dist[:r].copy()
+
+
+def brute_force_search_batch(corpus, queries, k, deleted=None, metric=METRIC_NEG_DOT,
+                             variant=VARIANT_SCALAR, as_written=False, threads=0):
+    """Batch of queries, one per host thread -> (ids [b,k], dist [b,k], counts [b], threads_used)."""
+    corpus, queries = _f32(corpus), _f32(queries)
+    n, dim = corpus.shape
+    b = queries.shape[0]
+    ids = np.zeros((b, max(k, 1)), dtype=np.uint32)
+    dist = np.zeros((b, max(k, 1)), dtype=np.float32)
+    counts = np.zeros(b, dtype=np.uint32)
+    bm = None if deleted is None else deleted_bitmap(n, deleted)
+    used = lib().so_brute_force_search_batch(_p(corpus, C.c_float), n, dim,
+                                             None if bm is None else _p(bm, C.c_uint32),
+                                             _p(queries, C.c_float), b, k, metric, variant,
+                                             int(as_written), threads, _p(ids, C.c_uint32),
+                                             _p(dist, C.c_float), _p(counts, C.c_uint32))
+    return ids, dist, counts, used
+
+
+def score_rows(corpus, query, ids, metric=METRIC_NEG_DOT, variant=VARIANT_SCALAR) -> np.ndarray:
+    corpus, query = _f32(corpus), _f32(query)
+    ids = np.ascontiguousarray(ids, dtype=np.uint32)
+    out = np.zeros(ids.size, dtype=np.float32)
+    lib().so_score_rows(_p(corpus, C.c_float), corpus.shape[1], _p(query, C.c_float),
+                        _p(ids, C.c_uint32), ids.size, metric, variant, _p(out, C.c_float))
+    return out
+
+
+def top_k_similar(query, candidates, k, variant=VARIANT_SCALAR):
+    """similarity.rs::top_k_similar -> (positions, scores)."""
+    query = _f32(query)
+    candidates = _f32(candidates)
+    if candidates.size == 0:
+        return np.zeros(0, np.uint32), np.zeros(0, np.float32)
+    n, dim = candidates.shape
+    pos = np.zeros(max(k, 1), np.uint32)
+    sc = np.zeros(max(k, 1), np.float32)
+    r = lib().so_top_k_similar(_p(query, C.c_float), query.size, _p(candidates, C.c_float), n, dim,
+                               k, variant, _p(pos, C.c_uint32), _p(sc, C.c_float))
+    return pos[:r].copy(), sc[:r].copy()
+
+
+def search_ids_post(vec_ids, dists, vec2mem, limit):
+    """retrieval.rs:927-961 -> (mem ids [r,2] u64, similarities [r])."""
+    vec_ids = np.ascontiguousarray(vec_ids, np.uint32)
+    dists = _f32(dists)
+    vec2mem = np.ascontiguousarray(vec2mem, np.uint64)
+    mem = np.zeros((max(limit, 1), 2), np.uint64)
+    sim = np.zeros(max(limit, 1), np.float32)
+    r = lib().so_search_ids_post(_p(vec_ids, C.c_uint32), _p(dists, C.c_float), vec_ids.size,
+                                 _p(vec2mem, C.c_uint64), vec2mem.shape[0], limit,
+                                 _p(mem, C.c_uint64), _p(sim, C.c_float))
+    return mem[:r].copy(), sim[:r].copy()
+
+
+def calibrate_score(x: float) -> float:
+    return float(lib().so_calibrate_score(C.c_float(x)))
+
+
+def fuse_scores_full(sem, ent, tag, imp, mom, access, graph, weights=DEFAULT_WEIGHTS) -> float:
+    w = _f32(weights)
+    return float(lib().so_fuse_scores_full(_p(w, C.c_float), sem, ent, tag, imp, mom, int(access), graph))
+
+
+def apply_recency_boost(score, now_s, created_s, boost_hours=24, multiplier=1.2) -> float:
+    return float(lib().so_apply_recency_boost(score, int(now_s), int(created_s), boost_hours, multiplier))
+
+
+def fuse_rank(feats: dict, now_s: int, max_results=5, min_score=0.25, weights=DEFAULT_WEIGHTS,
+              recency_hours=24, recency_mult=1.2, graph_boost=1.15):
+    """relevance.rs:805-918 ranking -> (order, scores, all_scores)."""
+    w = _f32(weights)
+    sem, ent, tag, imp, mom, gr = (_f32(feats[k]) for k in
+                                   ("semantic", "entity", "tag", "importance", "momentum", "graph"))
+    acc = np.ascontiguousarray(feats["access_count"], np.uint32)
+    created = np.ascontiguousarray(feats["created_at"], np.int64)
+    n = sem.size
+    order = np.zeros(max(max_results, 1), np.uint32)
+    score = np.zeros(max(max_results, 1), np.float32)
+    allsc = np.zeros(max(n, 1), np.float32)
+    r = lib().so_fuse_rank(_p(w, C.c_float), _p(sem, C.c_float), _p(ent, C.c_float),
+                           _p(tag, C.c_float), _p(imp, C.c_float), _p(mom, C.c_float),
+                           _p(acc, C.c_uint32), _p(gr, C.c_float), _p(created, C.c_int64), n,
+                           int(now_s), recency_hours, recency_mult, graph_boost, min_score,
+                           max_results, _p(order, C.c_uint32), _p(score, C.c_float),
+                           _p(allsc, C.c_float))
+    return order[:r].copy(), score[:r].copy(), allsc[:n].copy()
+
+
+def pool_finalize(hidden_states, attention) -> np.ndarray:
+    h = _f32(hidden_states)
+    att = np.ascontiguousarray(attention, np.int64)
+    seq, hidden = h.shape
+    out = np.zeros(hidden, np.float32)
+    lib().so_pool_finalize(_p(h, C.c_float), _p(att, C.c_int64), seq, hidden, _p(out, C.c_float))
+    return out
+
+
+def synth_corpus(seed: int, first_row: int, n: int, dim: int = 384, f16_round: bool = False) -> np.ndarray:
+    out = np.empty((n, dim), np.float32)
+    lib().so_synth_corpus(seed, first_row, n, dim, int(f16_round), _p(out, C.c_float))
+    return out
+
+
+def synth_queries(seed: int, n_rows: int, b: int, dim: int = 384):
+    out = np.empty((b, dim), np.float32)
+    near = np.empty(b, np.uint64)
+    lib().so_synth_queries(seed, n_rows, b, dim, _p(out, C.c_float), _p(near, C.c_uint64))
+    return out, near
+
+
+def round_f16(a) -> np.ndarray:
+    a = _f32(a)
+    out = np.empty_like(a)
+    lib().so_round_f16(_p(a, C.c_float), _p(out, C.c_float), a.size)
+    return out
+
+
+def max_threads() -> int:
+    return int(lib().so_max_threads())
