@@ -1,0 +1,179 @@
+/*
+ * shodh_gpu.h -- C ABI of libshodh_gpu.so: the B200-native (sm_100a) drop-in for
+ * the semantic-recall hot path of shodh-memory (query embedding -> exact
+ * cosine/dot top-k scan over the in-process vector store -> relevance fusion).
+ *
+ * The reference has no FFI for this path; its seams are Rust-level (SURVEY.md
+ * section 8b).  Each entry point below names the reference interface it
+ * replaces (paths relative to the reference repo).  INTEGRATION.md shows the
+ * Rust `extern "C"` block and the `GpuVectorStore` / `GpuMiniLM` wrappers a
+ * maintainer would add behind `VamanaIndex` / `Embedder`.
+ *
+ * Conventions (all functions):
+ *   - return SG_OK (0) or a negative sg_status; never throw, never abort;
+ *   - NO CPU fallback: if there is no usable sm_100 device the call fails;
+ *   - caller owns every host buffer; handles own all device memory;
+ *   - a handle may be used from many threads; calls on one handle serialise;
+ *   - sg_last_error() returns a thread-local, human-readable message.
+ */
+#ifndef SHODH_GPU_H
+#define SHODH_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SG_API __attribute__((visibility("default")))
+#else
+#define SG_API
+#endif
+
+typedef enum sg_status {
+    SG_OK = 0,
+    SG_ERR_INVALID = -1,      /* bad argument (null pointer, k == 0, id out of range ...) */
+    SG_ERR_CUDA = -2,         /* a CUDA runtime/driver call failed; see sg_last_error() */
+    SG_ERR_OOM = -3,          /* device or pinned-host allocation failed */
+    SG_ERR_DIM = -4,          /* dimension mismatch (spann.rs:586-592 sets the precedent: error, not UB) */
+    SG_ERR_UNSUPPORTED = -5,  /* valid request outside what the kernels cover (documented limits) */
+    SG_ERR_NO_DEVICE = -6,    /* no sm_100 device / extension cannot run: fail loudly, never fall back */
+    SG_ERR_NOT_BUILT = -7     /* store holds no vectors where the reference would say "graph not built" */
+} sg_status;
+
+/* element type the corpus is held in on the device (queries are always f32) */
+typedef enum sg_dtype { SG_DTYPE_F32 = 0, SG_DTYPE_F16 = 1 } sg_dtype;
+
+/* src/vector_db/vamana.rs:44-60 DistanceMetric.  RetrievalEngine only permits
+ * NormalizedDotProduct (src/memory/retrieval.rs:188-193): distance = -dot. */
+typedef enum sg_metric { SG_METRIC_NEG_DOT = 0 } sg_metric;
+
+/* which summation order the exact scores reproduce */
+typedef enum sg_order {
+    SG_ORDER_SCALAR = 0, /* distance_inline.rs:157-173, what a default x86-64 build runs */
+    SG_ORDER_AVX2 = 1    /* distance_inline.rs:67-111, `-C target-cpu=native` builds */
+} sg_order;
+
+typedef struct sg_store sg_store;
+typedef struct sg_encoder sg_encoder;
+
+/* ---- library ------------------------------------------------------------------------- */
+SG_API const char *sg_version(void);
+SG_API const char *sg_last_error(void);
+SG_API int sg_device_count(int *count_out);
+/* number of this library's kernels launched since load (bench.py: gpu_launches) */
+SG_API uint64_t sg_kernel_launch_count(void);
+
+/* ---- vector store: replaces VamanaIndex as held by RetrievalEngine ---------------------
+ * (src/memory/retrieval.rs:53 `vector_index: Arc<RwLock<VamanaIndex>>`).
+ * ids are dense and sequential from 0 in insertion order (vamana.rs:854-855). */
+
+/* VamanaIndex::new (vamana.rs:163-198).  dim must be a multiple of 64 (F16) / 32 (F32),
+ * <= 2048.  device = CUDA ordinal. */
+SG_API int sg_store_create(sg_store **out, int device, uint32_t dim, int dtype, int metric);
+SG_API void sg_store_destroy(sg_store *s);
+
+/* pre-size device memory for n_rows (amortises add_vector growth) */
+SG_API int sg_store_reserve(sg_store *s, uint64_t n_rows);
+
+/* VamanaIndex::add_vector (vamana.rs:853-974) / build (:200-284) /
+ * rebuild_from_vectors: append n row-major f32 rows (rounded to the store dtype
+ * on the device, round-to-nearest-even).  first_id_out receives the id of row 0. */
+SG_API int sg_store_append(sg_store *s, const float *rows_f32, uint64_t n, uint32_t *first_id_out);
+
+/* VamanaIndex::mark_deleted (vamana.rs:813-820): soft delete.  *ok_out = 1 if id < len
+ * (the reference returns true, also for an id that was already deleted), 0 otherwise. */
+SG_API int sg_store_mark_deleted(sg_store *s, uint32_t id, int *ok_out);
+/* VamanaIndex::is_deleted (:823-825) / clear_deleted (:850-852) */
+SG_API int sg_store_is_deleted(sg_store *s, uint32_t id, int *deleted_out);
+SG_API int sg_store_clear_deleted(sg_store *s);
+
+/* VamanaIndex::len (vamana.rs:976-979): rows ever appended (deleted included). */
+SG_API int sg_store_len(const sg_store *s, uint64_t *n_out);
+SG_API int sg_store_deleted_count(const sg_store *s, uint64_t *n_out);
+
+/* VamanaIndex::get_vector / extract_all_vectors: rows [first, first+n) upcast to f32. */
+SG_API int sg_store_get_vectors(sg_store *s, uint64_t first, uint64_t n, float *rows_f32_out);
+
+/* summation order of the exact scores (default SG_ORDER_SCALAR) */
+SG_API int sg_store_set_order(sg_store *s, int order);
+
+/* row-sharding: ids reported by search are id_base + local id */
+SG_API int sg_store_set_id_base(sg_store *s, uint32_t id_base);
+
+/* VamanaIndex::search (vamana.rs:764-808) on its exact path (`SHODH_VECTOR_EXACT`,
+ * :775-777 -> brute_force_search :1167-1188), batched over b queries:
+ * for every live row dist = -dot(query,row) in the reference's summation order,
+ * results sorted by (dist total_cmp ascending, id ascending), truncated to k.
+ * queries_f32 [b,dim]; ids_out/dist_out [b,k]; counts_out [b] = min(k, live rows).
+ * Unused tail slots hold id 0xFFFFFFFF / dist +inf.  Empty store -> counts 0 (Ok(vec![])).
+ * Limit: k <= 1024. */
+SG_API int sg_store_search(sg_store *s, const float *queries_f32, uint32_t b, uint32_t k,
+                           uint32_t *ids_out, float *dist_out, uint32_t *counts_out);
+
+/* same, with queries and results resident in device memory and asynchronous on
+ * `cuda_stream` (a cudaStream_t; NULL = the store's own stream).  This is the
+ * form the GPU encoder feeds and the multi-GPU exchange consumes. */
+SG_API int sg_store_search_device(sg_store *s, const float *d_queries_f32, uint32_t b, uint32_t k,
+                                  uint32_t *d_ids_out, float *d_dist_out, uint32_t *d_counts_out,
+                                  void *cuda_stream);
+
+/* k-way merge of per-shard results: lists [b, n_lists, k] of (id, dist)
+ * already sorted by (dist, id) -> the global top-k per query, same order rule.
+ * All pointers are device pointers; asynchronous on cuda_stream. */
+SG_API int sg_merge_topk_device(int device, const uint32_t *d_ids, const float *d_dist,
+                                uint32_t b, uint32_t n_lists, uint32_t k, uint32_t *d_ids_out,
+                                float *d_dist_out, uint32_t *d_counts_out, void *cuda_stream);
+
+/* CUDA-event time of the scan kernel(s) of the most recent search, in ms
+ * (bench.py roofline).  Enable with sg_store_set_profiling(s, 1). */
+SG_API int sg_store_set_profiling(sg_store *s, int on);
+SG_API int sg_store_last_scan_ms(sg_store *s, float *ms_out, uint32_t *launches_out);
+
+/* TEST/BENCH ONLY: fill rows [first_row, first_row+n) of the deterministic synthetic
+ * corpus (oracle/shodh_oracle.c so_synth_corpus, bit-identical) directly on the device. */
+SG_API int sg_store_append_synthetic(sg_store *s, uint64_t seed, uint64_t first_row, uint64_t n);
+
+/* ---- relevance fusion: replaces the ranking phase of
+ * RelevanceEngine::surface_relevant_inner (src/relevance.rs:805-918) -------------------- */
+typedef struct sg_fuse_weights { /* LearnedWeights, relevance.rs:343-369; defaults :64-88 */
+    float semantic, entity, tag, importance, momentum, access_count, graph_strength;
+} sg_fuse_weights;
+
+typedef struct sg_fuse_config { /* RelevanceConfig, relevance.rs:120-195 */
+    uint64_t recency_boost_hours;   /* 24   */
+    float recency_boost_multiplier; /* 1.2  */
+    float graph_boost_multiplier;   /* 1.15 */
+    float min_score;                /* 0.25 (MIN_RELEVANCE_SCORE, relevance.rs:914) */
+    uint32_t max_results;           /* 5    */
+} sg_fuse_config;
+
+typedef struct sg_candidate_feats { /* SoA over n candidates, host pointers */
+    const float *semantic;        /* similarity = -distance from the scan */
+    const float *entity;
+    const float *tag;
+    const float *importance;
+    const float *momentum;        /* feedback EMA in [-1,1] */
+    const uint32_t *access_count;
+    const float *graph_strength;
+    const int64_t *created_at_unix_s;
+} sg_candidate_feats;
+
+SG_API void sg_fuse_default_weights(sg_fuse_weights *w);
+SG_API void sg_fuse_default_config(sg_fuse_config *c);
+
+/* fuse_scores_full (:529-594) + apply_recency_boost (:1524-1547) + graph boost
+ * (:877-881) + sort (score desc, created_at desc, candidate position asc) (:905-910)
+ * + `>= min_score` (:914-915) + truncate (:918).  order_out/score_out [max_results];
+ * all_scores_out [n] optional (may be NULL). */
+SG_API int sg_fuse_topk(int device, const sg_fuse_weights *w, const sg_fuse_config *cfg,
+                        const sg_candidate_feats *feats, uint32_t n, int64_t now_unix_s,
+                        uint32_t *order_out, float *score_out, uint32_t *n_out,
+                        float *all_scores_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHODH_GPU_H */

@@ -1,0 +1,103 @@
+"""ctypes binding of libshodh_gpu.so (the C ABI declared in include/shodh_gpu.h).
+
+Loading fails loudly if the CUDA library is missing -- there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libshodh_gpu.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "shodh_gpu.h")
+
+SG_OK = 0
+SG_ERR_INVALID, SG_ERR_CUDA, SG_ERR_OOM, SG_ERR_DIM = -1, -2, -3, -4
+SG_ERR_UNSUPPORTED, SG_ERR_NO_DEVICE, SG_ERR_NOT_BUILT = -5, -6, -7
+SG_DTYPE_F32, SG_DTYPE_F16 = 0, 1
+SG_METRIC_NEG_DOT = 0
+SG_ORDER_SCALAR, SG_ORDER_AVX2 = 0, 1
+
+
+class SgError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libshodh_gpu error {code}: {msg}")
+        self.code = code
+
+
+class FuseWeights(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("semantic", "entity", "tag", "importance", "momentum",
+                                         "access_count", "graph_strength")]
+
+
+class FuseConfig(C.Structure):
+    _fields_ = [("recency_boost_hours", C.c_uint64), ("recency_boost_multiplier", C.c_float),
+                ("graph_boost_multiplier", C.c_float), ("min_score", C.c_float),
+                ("max_results", C.c_uint32)]
+
+
+class CandidateFeats(C.Structure):
+    _fields_ = [("semantic", C.POINTER(C.c_float)), ("entity", C.POINTER(C.c_float)),
+                ("tag", C.POINTER(C.c_float)), ("importance", C.POINTER(C.c_float)),
+                ("momentum", C.POINTER(C.c_float)), ("access_count", C.POINTER(C.c_uint32)),
+                ("graph_strength", C.POINTER(C.c_float)), ("created_at_unix_s", C.POINTER(C.c_int64))]
+
+
+def declared_symbols() -> list[str]:
+    """Every function include/shodh_gpu.h declares with SG_API."""
+    src = open(HEADER_PATH).read()
+    return sorted(set(re.findall(r"SG_API\s+[\w\s\*]+?\b(sg_\w+)\s*\(", src)))
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "shodh_memory_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    missing = [s for s in declared_symbols() if not hasattr(L, s)]
+    if missing:
+        raise ImportError(f"libshodh_gpu.so does not export: {missing}")
+    vp, u32p, f32p, u64p = C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_float), C.POINTER(C.c_uint64)
+    L.sg_version.restype = C.c_char_p
+    L.sg_last_error.restype = C.c_char_p
+    L.sg_kernel_launch_count.restype = C.c_uint64
+    L.sg_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.sg_store_create.argtypes = [C.POINTER(vp), C.c_int, C.c_uint32, C.c_int, C.c_int]
+    L.sg_store_destroy.argtypes = [vp]
+    L.sg_store_destroy.restype = None
+    L.sg_store_reserve.argtypes = [vp, C.c_uint64]
+    L.sg_store_append.argtypes = [vp, f32p, C.c_uint64, u32p]
+    L.sg_store_append_synthetic.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64]
+    L.sg_store_mark_deleted.argtypes = [vp, C.c_uint32, C.POINTER(C.c_int)]
+    L.sg_store_is_deleted.argtypes = [vp, C.c_uint32, C.POINTER(C.c_int)]
+    L.sg_store_clear_deleted.argtypes = [vp]
+    L.sg_store_len.argtypes = [vp, u64p]
+    L.sg_store_deleted_count.argtypes = [vp, u64p]
+    L.sg_store_get_vectors.argtypes = [vp, C.c_uint64, C.c_uint64, f32p]
+    L.sg_store_set_order.argtypes = [vp, C.c_int]
+    L.sg_store_set_id_base.argtypes = [vp, C.c_uint32]
+    L.sg_store_set_profiling.argtypes = [vp, C.c_int]
+    L.sg_store_last_scan_ms.argtypes = [vp, f32p, u32p]
+    L.sg_store_search.argtypes = [vp, f32p, C.c_uint32, C.c_uint32, u32p, f32p, u32p]
+    L.sg_store_search_device.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
+    L.sg_merge_topk_device.argtypes = [C.c_int, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
+    L.sg_fuse_default_weights.argtypes = [C.POINTER(FuseWeights)]
+    L.sg_fuse_default_weights.restype = None
+    L.sg_fuse_default_config.argtypes = [C.POINTER(FuseConfig)]
+    L.sg_fuse_default_config.restype = None
+    L.sg_fuse_topk.argtypes = [C.c_int, C.POINTER(FuseWeights), C.POINTER(FuseConfig),
+                               C.POINTER(CandidateFeats), C.c_uint32, C.c_int64, u32p, f32p, u32p, f32p]
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != SG_OK:
+        raise SgError(rc, lib().sg_last_error().decode(errors="replace"))

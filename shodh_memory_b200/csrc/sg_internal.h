@@ -1,0 +1,55 @@
+// sg_internal.h -- declarations shared between the translation units of libshodh_gpu.
+#pragma once
+#include "sg_common.cuh"
+
+namespace sg {
+
+// ---- scan_exact.cu ----
+struct ScanArgs {
+    const float *queries;     // device [nq][dim] f32
+    uint32_t nq;              // queries in this sweep (<= QB of the instantiation)
+    uint32_t dim;
+    uint64_t n_rows;
+    const uint32_t *deleted;  // device bitmap (bit i = row i soft-deleted) or nullptr
+    uint32_t k;
+    uint32_t cap;             // per-(warp,query) candidate buffer capacity (pow2, >= k + 32)
+    uint32_t nbox;            // 128-byte boxes per row (dim * esize / 128)
+    uint32_t ring;            // box slots per warp
+    uint64_t *out_lists;      // [nq][gridDim.x][k] sorted keys, KEY_SENTINEL padded
+};
+size_t scan_smem_bytes(uint32_t W, uint32_t ring, uint32_t qb, uint32_t dim, uint32_t cap);
+cudaError_t launch_scan_exact(const CUtensorMap &tmap, const ScanArgs &a, int qb, bool f16, int order,
+                              uint32_t grid, uint32_t W, size_t smem, cudaStream_t st);
+
+// ---- select.cu ----
+// lists [b][n_per_query] u64 keys (any order, sentinel padded) -> top-k per query
+cudaError_t launch_merge_keys(const uint64_t *d_lists, uint32_t b, uint32_t n_per_query, uint32_t k,
+                              uint32_t id_base, uint32_t *d_ids, float *d_dist, uint32_t *d_counts,
+                              cudaStream_t st);
+// lists as (ids, dist) pairs [b][n_per_query]; id 0xFFFFFFFF marks an empty slot
+cudaError_t launch_merge_pairs(const uint32_t *d_ids_in, const float *d_dist_in, uint32_t b,
+                               uint32_t n_per_query, uint32_t k, uint32_t *d_ids, float *d_dist,
+                               uint32_t *d_counts, cudaStream_t st);
+
+// ---- convert / synth (store_kernels.cu) ----
+cudaError_t launch_f32_to_f16(const float *d_src, __half *d_dst, uint64_t n_elems, cudaStream_t st);
+cudaError_t launch_f16_to_f32(const __half *d_src, float *d_dst, uint64_t n_elems, cudaStream_t st);
+cudaError_t launch_synth_rows(void *d_rows, bool f16, uint64_t seed, uint64_t first_row, uint64_t n,
+                              uint32_t dim, cudaStream_t st);
+cudaError_t launch_set_bit(uint32_t *d_bitmap, uint32_t id, uint32_t *d_was_set, cudaStream_t st);
+
+// ---- fuse.cu ----
+struct FuseDev {
+    const float *semantic, *entity, *tag, *importance, *momentum, *graph;
+    const uint32_t *access;
+    const int64_t *created;
+};
+cudaError_t launch_fuse_rank(const FuseDev &f, uint32_t n, sg_fuse_weights w, sg_fuse_config c,
+                             int64_t now_s, uint32_t *d_order, float *d_score, uint32_t *d_n_out,
+                             float *d_all, cudaStream_t st);
+
+// ---- tensor map (store.cu) ----
+int encode_corpus_tmap(CUtensorMap *out, const void *d_rows, bool f16, uint32_t dim, uint64_t n_rows,
+                       uint32_t box_rows);
+
+}  // namespace sg

@@ -1,0 +1,770 @@
+// store.cu -- the C ABI of libshodh_gpu: device-resident vector store + exact search.
+//
+// Host-side mirror of the reference's VamanaIndex surface as RetrievalEngine uses it
+// (reference src/vector_db/vamana.rs: search :764, add_vector :853, mark_deleted :813,
+// len :976, build :200, extract_all_vectors; src/memory/retrieval.rs:53,912-918).
+// Data layout in HBM: one dense row-major matrix [n_rows, dim] in the store dtype
+// (fp16 by default: 768 B per 384-d row), 256-byte aligned, plus a soft-delete bitmap of
+// one bit per row.  Ids are row numbers.  There is deliberately no CPU fallback.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "sg_internal.h"
+
+namespace sg {
+
+// ---------------------------------------------------------------------------------------
+// error string + launch counter
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---------------------------------------------------------------------------------------
+// driver entry point for cuTensorMapEncodeTiled (no -lcuda link dependency)
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode_fn()
+{
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    return fn;
+}
+
+int encode_corpus_tmap(CUtensorMap *out, const void *d_rows, bool f16, uint32_t dim, uint64_t n_rows,
+                       uint32_t box_rows)
+{
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+        return SG_ERR_NO_DEVICE;
+    }
+    const uint32_t esize = f16 ? 2 : 4;
+    cuuint64_t gdim[2] = {dim, n_rows ? n_rows : 1};
+    cuuint64_t gstride[1] = {(cuuint64_t)dim * esize};
+    cuuint32_t box[2] = {128u / esize, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                     const_cast<void *>(d_rows), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (dim=%u rows=%llu)", (int)r, dim,
+                  (unsigned long long)n_rows);
+        return SG_ERR_CUDA;
+    }
+    return SG_OK;
+}
+
+static int env_u32(const char *name, uint32_t dflt)
+{
+    const char *v = getenv(name);
+    if (!v || !*v) return (int)dflt;
+    return atoi(v);
+}
+
+}  // namespace sg
+
+using namespace sg;
+
+// ---------------------------------------------------------------------------------------
+// the store
+// ---------------------------------------------------------------------------------------
+struct sg_store {
+    int device = 0;
+    int sm_count = 148;
+    uint32_t dim = 0;
+    int dtype = SG_DTYPE_F16;
+    int metric = SG_METRIC_NEG_DOT;
+    int order = SG_ORDER_SCALAR;
+    uint32_t id_base = 0;
+    uint32_t esize = 2;
+
+    void *d_rows = nullptr;
+    uint64_t n = 0, cap = 0;
+    uint32_t *d_deleted = nullptr;       // bitmap, cap/32 (+pad) words
+    std::vector<uint32_t> h_deleted;     // host mirror
+    uint64_t n_deleted = 0;
+
+    cudaStream_t stream = nullptr;
+    mutable std::mutex mu;
+
+    // scratch
+    float *d_queries = nullptr;  size_t q_cap = 0;      // floats
+    uint64_t *d_lists = nullptr; size_t lists_cap = 0;  // keys
+    uint32_t *d_ids = nullptr; float *d_dist = nullptr; uint32_t *d_counts = nullptr; size_t res_cap = 0, cnt_cap = 0;
+    void *h_pinned = nullptr; size_t pinned_cap = 0;
+    float *d_stage = nullptr; size_t stage_cap = 0;     // floats, append staging
+
+    bool profiling = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    uint32_t last_scan_launches = 0;
+};
+
+namespace {
+
+int check_device(int device, int *sm_count)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("no CUDA device available (%s); libshodh_gpu has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return SG_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) {
+        set_error("device ordinal %d out of range (0..%d)", device, n - 1);
+        return SG_ERR_INVALID;
+    }
+    cudaDeviceProp p;
+    SG_CUDA_TRY(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10) {
+        set_error("device %d is sm_%d%d; libshodh_gpu is built for sm_100a (B200) only", device, p.major, p.minor);
+        return SG_ERR_NO_DEVICE;
+    }
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    return SG_OK;
+}
+
+template <typename T>
+int grow(T *&ptr, size_t &cap, size_t need, bool keep = false, cudaStream_t st = nullptr)
+{
+    if (need <= cap) return SG_OK;
+    size_t ncap = need + need / 2;
+    T *np = nullptr;
+    SG_CUDA_TRY(cudaMalloc(&np, ncap * sizeof(T)));
+    if (keep && ptr && cap) {
+        cudaError_t e = cudaMemcpyAsync(np, ptr, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            cudaFree(np);
+            set_error("device copy during growth failed: %s", cudaGetErrorString(e));
+            return SG_ERR_CUDA;
+        }
+    }
+    if (ptr) cudaFree(ptr);
+    ptr = np;
+    cap = ncap;
+    return SG_OK;
+}
+
+int grow_pinned(sg_store *s, size_t bytes)
+{
+    if (bytes <= s->pinned_cap) return SG_OK;
+    if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    s->h_pinned = nullptr;
+    s->pinned_cap = 0;
+    size_t ncap = bytes + bytes / 2;
+    SG_CUDA_TRY(cudaHostAlloc(&s->h_pinned, ncap, cudaHostAllocDefault));
+    s->pinned_cap = ncap;
+    return SG_OK;
+}
+
+int ensure_rows(sg_store *s, uint64_t need_rows)
+{
+    if (need_rows <= s->cap) return SG_OK;
+    if (need_rows >= 0xFFFFFFFFull) {
+        set_error("store is limited to 2^32-2 rows (ids are u32)");
+        return SG_ERR_UNSUPPORTED;
+    }
+    uint64_t ncap = s->cap + s->cap / 2;
+    if (ncap < need_rows) ncap = need_rows;
+    ncap = (ncap + 1023) & ~1023ull;
+    void *nrows = nullptr;
+    const size_t row_bytes = (size_t)s->dim * s->esize;
+    SG_CUDA_TRY(cudaMalloc(&nrows, ncap * row_bytes));
+    uint32_t *nbm = nullptr;
+    const size_t words = ncap / 32 + 1;
+    cudaError_t e = cudaMalloc(&nbm, words * 4);
+    if (e != cudaSuccess) {
+        cudaFree(nrows);
+        set_error("cudaMalloc(bitmap) failed: %s", cudaGetErrorString(e));
+        return SG_ERR_OOM;
+    }
+    e = cudaMemsetAsync(nbm, 0, words * 4, s->stream);
+    if (e == cudaSuccess && s->n) {
+        e = cudaMemcpyAsync(nrows, s->d_rows, s->n * row_bytes, cudaMemcpyDeviceToDevice, s->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(nbm, s->d_deleted, (s->n / 32 + 1) * 4, cudaMemcpyDeviceToDevice, s->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) {
+        cudaFree(nrows);
+        cudaFree(nbm);
+        set_error("growing the store failed: %s", cudaGetErrorString(e));
+        return SG_ERR_CUDA;
+    }
+    if (s->d_rows) cudaFree(s->d_rows);
+    if (s->d_deleted) cudaFree(s->d_deleted);
+    s->d_rows = nrows;
+    s->d_deleted = nbm;
+    s->cap = ncap;
+    s->h_deleted.resize(words, 0u);
+    return SG_OK;
+}
+
+struct ScanPlan {
+    uint32_t W, ring, cap, grid;
+    size_t smem[5];  // indexed by qb (1,2,4)
+};
+
+// choose warps-per-CTA / ring depth / buffer capacity so the CTA fits in 227 KB
+int plan_scan(const sg_store *s, uint32_t k, uint32_t qb, ScanPlan *p)
+{
+    const uint32_t nbox = s->dim * s->esize / 128;
+    uint32_t kp = 32;
+    while (kp < k) kp <<= 1;
+    p->cap = 2 * kp;
+    uint32_t ring = (uint32_t)env_u32("SG_SCAN_RING", nbox < 6 ? (nbox < 3 ? 3 : nbox) : 6);
+    if (ring < 2) ring = 2;
+    uint32_t Wmax = (uint32_t)env_u32("SG_SCAN_WARPS", 8);
+    if (Wmax > 16) Wmax = 16;
+    const size_t limit = 227 * 1024;
+    for (uint32_t W = Wmax; W >= 1; --W) {
+        size_t sm = scan_smem_bytes(W, ring, qb, s->dim, p->cap);
+        uint32_t M = 2;
+        while (M < W * k) M <<= 1;
+        if (sm <= limit && (size_t)M * 8 <= (size_t)W * ring * 4096) {
+            p->W = W;
+            p->ring = ring;
+            p->smem[qb] = sm;
+            const uint64_t n_tiles = (s->n + 31) / 32;
+            uint64_t g = (n_tiles + W - 1) / W;
+            p->grid = (uint32_t)(g < (uint64_t)s->sm_count ? (g ? g : 1) : s->sm_count);
+            return SG_OK;
+        }
+    }
+    set_error("no scan configuration fits shared memory (dim=%u k=%u qb=%u)", s->dim, k, qb);
+    return SG_ERR_UNSUPPORTED;
+}
+
+// all pointers are device pointers; runs asynchronously on st
+int search_device_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint32_t *d_ids, float *d_dist,
+                         uint32_t *d_counts, cudaStream_t st)
+{
+    if (b == 0) return SG_OK;
+    if (k == 0 || k > 1024) {
+        set_error("k=%u outside the supported range 1..1024", k);
+        return k == 0 ? SG_ERR_INVALID : SG_ERR_UNSUPPORTED;
+    }
+    s->last_scan_launches = 0;
+    s->ev_valid = false;
+    if (s->n == 0) {  // VamanaIndex::search on an empty index: Ok(vec![]) (vamana.rs:766-768)
+        SG_CUDA_TRY(launch_merge_keys(nullptr, b, 0, k, s->id_base, d_ids, d_dist, d_counts, st));
+        return SG_OK;
+    }
+    // one plan for the widest sweep; narrower sweeps reuse W/ring/grid (their smem is smaller)
+    const uint32_t qb_max = b >= 3 ? 4 : b;
+    ScanPlan plan;
+    int rc = plan_scan(s, k, qb_max, &plan);
+    if (rc != SG_OK) return rc;
+    const uint32_t L = plan.grid;
+    rc = grow(s->d_lists, s->lists_cap, (size_t)b * L * k);
+    if (rc != SG_OK) return rc;
+
+    CUtensorMap tmap;
+    rc = encode_corpus_tmap(&tmap, s->d_rows, s->dtype == SG_DTYPE_F16, s->dim, s->n, 32);
+    if (rc != SG_OK) return rc;
+
+    if (s->profiling) SG_CUDA_TRY(cudaEventRecord(s->ev0, st));
+    uint32_t done = 0;
+    while (done < b) {
+        const uint32_t rem = b - done;
+        const uint32_t qb = rem >= 3 ? 4 : rem;
+        const uint32_t nq = rem < qb ? rem : qb;
+        ScanArgs a;
+        a.queries = d_q + (size_t)done * s->dim;
+        a.nq = nq;
+        a.dim = s->dim;
+        a.n_rows = s->n;
+        a.deleted = s->n_deleted ? s->d_deleted : nullptr;
+        a.k = k;
+        a.cap = plan.cap;
+        a.nbox = s->dim * s->esize / 128;
+        a.ring = plan.ring;
+        a.out_lists = s->d_lists + (size_t)done * L * k;
+        size_t smem = scan_smem_bytes(plan.W, plan.ring, qb, s->dim, plan.cap);
+        cudaError_t e = launch_scan_exact(tmap, a, (int)qb, s->dtype == SG_DTYPE_F16, s->order, L, plan.W, smem, st);
+        if (e != cudaSuccess) {
+            set_error("scan kernel launch failed: %s", cudaGetErrorString(e));
+            return SG_ERR_CUDA;
+        }
+        ++s->last_scan_launches;
+        done += nq;
+    }
+    if (s->profiling) {
+        SG_CUDA_TRY(cudaEventRecord(s->ev1, st));
+        s->ev_valid = true;
+    }
+    SG_CUDA_TRY(launch_merge_keys(s->d_lists, b, L * k, k, s->id_base, d_ids, d_dist, d_counts, st));
+    return SG_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+const char *sg_version(void) { return "shodh_gpu 0.1.0 (sm_100a)"; }
+const char *sg_last_error(void) { return g_err; }
+uint64_t sg_kernel_launch_count(void) { return g_launches.load(); }
+
+int sg_device_count(int *count_out)
+{
+    if (!count_out) return SG_ERR_INVALID;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count_out = 0;
+        set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        return SG_ERR_NO_DEVICE;
+    }
+    *count_out = n;
+    return SG_OK;
+}
+
+int sg_store_create(sg_store **out, int device, uint32_t dim, int dtype, int metric)
+{
+    if (!out) return SG_ERR_INVALID;
+    *out = nullptr;
+    if (dtype != SG_DTYPE_F16 && dtype != SG_DTYPE_F32) {
+        set_error("unknown dtype %d", dtype);
+        return SG_ERR_INVALID;
+    }
+    if (metric != SG_METRIC_NEG_DOT) {
+        set_error("only NormalizedDotProduct is supported (RetrievalEngine refuses the others, retrieval.rs:188-193)");
+        return SG_ERR_UNSUPPORTED;
+    }
+    const uint32_t mult = dtype == SG_DTYPE_F16 ? 64 : 32;
+    if (dim == 0 || dim % mult != 0 || dim > 2048) {
+        set_error("dim=%u unsupported: must be a non-zero multiple of %u and <= 2048", dim, mult);
+        return SG_ERR_UNSUPPORTED;
+    }
+    int sms = 0;
+    int rc = check_device(device, &sms);
+    if (rc != SG_OK) return rc;
+    SG_CUDA_TRY(cudaSetDevice(device));
+    sg_store *s = new (std::nothrow) sg_store();
+    if (!s) return SG_ERR_OOM;
+    s->device = device;
+    s->sm_count = sms;
+    s->dim = dim;
+    s->dtype = dtype;
+    s->esize = dtype == SG_DTYPE_F16 ? 2 : 4;
+    s->metric = metric;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+    if (e != cudaSuccess) {
+        set_error("stream/event creation failed: %s", cudaGetErrorString(e));
+        delete s;
+        return SG_ERR_CUDA;
+    }
+    *out = s;
+    return SG_OK;
+}
+
+void sg_store_destroy(sg_store *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->d_rows);
+    cudaFree(s->d_deleted);
+    cudaFree(s->d_queries);
+    cudaFree(s->d_lists);
+    cudaFree(s->d_ids);
+    cudaFree(s->d_dist);
+    cudaFree(s->d_counts);
+    cudaFree(s->d_stage);
+    if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int sg_store_reserve(sg_store *s, uint64_t n_rows)
+{
+    if (!s) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    SG_CUDA_TRY(cudaSetDevice(s->device));
+    return ensure_rows(s, n_rows);
+}
+
+int sg_store_append(sg_store *s, const float *rows, uint64_t n, uint32_t *first_id_out)
+{
+    if (!s || (!rows && n)) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    SG_CUDA_TRY(cudaSetDevice(s->device));
+    if (first_id_out) *first_id_out = (uint32_t)s->n;
+    if (n == 0) return SG_OK;
+    int rc = ensure_rows(s, s->n + n);
+    if (rc != SG_OK) return rc;
+    const size_t chunk_rows = (size_t)(16u << 20) / ((size_t)s->dim * 4) ? (size_t)(16u << 20) / ((size_t)s->dim * 4) : 1;
+    rc = grow_pinned(s, chunk_rows * s->dim * 4);
+    if (rc != SG_OK) return rc;
+    if (s->dtype == SG_DTYPE_F16) {
+        rc = grow(s->d_stage, s->stage_cap, chunk_rows * s->dim);
+        if (rc != SG_OK) return rc;
+    }
+    uint64_t done = 0;
+    while (done < n) {
+        const uint64_t cnt = (n - done) < chunk_rows ? (n - done) : chunk_rows;
+        const size_t elems = (size_t)cnt * s->dim;
+        memcpy(s->h_pinned, rows + done * s->dim, elems * 4);
+        uint8_t *dst = static_cast<uint8_t *>(s->d_rows) + (s->n + done) * (size_t)s->dim * s->esize;
+        if (s->dtype == SG_DTYPE_F16) {
+            SG_CUDA_TRY(cudaMemcpyAsync(s->d_stage, s->h_pinned, elems * 4, cudaMemcpyHostToDevice, s->stream));
+            SG_CUDA_TRY(launch_f32_to_f16(s->d_stage, reinterpret_cast<__half *>(dst), elems, s->stream));
+        } else {
+            SG_CUDA_TRY(cudaMemcpyAsync(dst, s->h_pinned, elems * 4, cudaMemcpyHostToDevice, s->stream));
+        }
+        SG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+        done += cnt;
+    }
+    s->n += n;
+    return SG_OK;
+}
+
+int sg_store_append_synthetic(sg_store *s, uint64_t seed, uint64_t first_row, uint64_t n)
+{
+    if (!s) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    SG_CUDA_TRY(cudaSetDevice(s->device));
+    int rc = ensure_rows(s, s->n + n);
+    if (rc != SG_OK) return rc;
+    uint8_t *dst = static_cast<uint8_t *>(s->d_rows) + s->n * (size_t)s->dim * s->esize;
+    SG_CUDA_TRY(launch_synth_rows(dst, s->dtype == SG_DTYPE_F16, seed, first_row, n, s->dim, s->stream));
+    SG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->n += n;
+    return SG_OK;
+}
+
+int sg_store_mark_deleted(sg_store *s, uint32_t id, int *ok_out)
+{
+    if (!s) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    if (id >= s->n) {  // mark_deleted returns false for unknown ids (vamana.rs:814-819)
+        if (ok_out) *ok_out = 0;
+        return SG_OK;
+    }
+    SG_CUDA_TRY(cudaSetDevice(s->device));
+    uint32_t &w = s->h_deleted[id >> 5];
+    const uint32_t bit = 1u << (id & 31);
+    if (!(w & bit)) {
+        w |= bit;
+        ++s->n_deleted;
+        SG_CUDA_TRY(cudaMemcpyAsync(s->d_deleted + (id >> 5), &w, 4, cudaMemcpyHostToDevice, s->stream));
+        SG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    }
+    if (ok_out) *ok_out = 1;
+    return SG_OK;
+}
+
+int sg_store_is_deleted(sg_store *s, uint32_t id, int *deleted_out)
+{
+    if (!s || !deleted_out) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    *deleted_out = (id < s->n) ? (int)((s->h_deleted[id >> 5] >> (id & 31)) & 1u) : 0;
+    return SG_OK;
+}
+
+int sg_store_clear_deleted(sg_store *s)
+{
+    if (!s) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    if (!s->d_deleted) return SG_OK;
+    SG_CUDA_TRY(cudaSetDevice(s->device));
+    std::fill(s->h_deleted.begin(), s->h_deleted.end(), 0u);
+    s->n_deleted = 0;
+    SG_CUDA_TRY(cudaMemsetAsync(s->d_deleted, 0, s->h_deleted.size() * 4, s->stream));
+    SG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return SG_OK;
+}
+
+int sg_store_len(const sg_store *s, uint64_t *n_out)
+{
+    if (!s || !n_out) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    *n_out = s->n;
+    return SG_OK;
+}
+
+int sg_store_deleted_count(const sg_store *s, uint64_t *n_out)
+{
+    if (!s || !n_out) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    *n_out = s->n_deleted;
+    return SG_OK;
+}
+
+int sg_store_get_vectors(sg_store *s, uint64_t first, uint64_t n, float *out)
+{
+    if (!s || (!out && n)) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    if (first + n > s->n) {
+        set_error("rows [%llu,%llu) out of range (len %llu)", (unsigned long long)first,
+                  (unsigned long long)(first + n), (unsigned long long)s->n);
+        return SG_ERR_INVALID;
+    }
+    if (n == 0) return SG_OK;
+    SG_CUDA_TRY(cudaSetDevice(s->device));
+    const size_t chunk_rows = (size_t)(16u << 20) / ((size_t)s->dim * 4) ? (size_t)(16u << 20) / ((size_t)s->dim * 4) : 1;
+    int rc = grow_pinned(s, chunk_rows * s->dim * 4);
+    if (rc != SG_OK) return rc;
+    if (s->dtype == SG_DTYPE_F16) {
+        rc = grow(s->d_stage, s->stage_cap, chunk_rows * s->dim);
+        if (rc != SG_OK) return rc;
+    }
+    uint64_t done = 0;
+    while (done < n) {
+        const uint64_t cnt = (n - done) < chunk_rows ? (n - done) : chunk_rows;
+        const size_t elems = (size_t)cnt * s->dim;
+        const uint8_t *src = static_cast<const uint8_t *>(s->d_rows) + (first + done) * (size_t)s->dim * s->esize;
+        if (s->dtype == SG_DTYPE_F16) {
+            SG_CUDA_TRY(launch_f16_to_f32(reinterpret_cast<const __half *>(src), s->d_stage, elems, s->stream));
+            SG_CUDA_TRY(cudaMemcpyAsync(s->h_pinned, s->d_stage, elems * 4, cudaMemcpyDeviceToHost, s->stream));
+        } else {
+            SG_CUDA_TRY(cudaMemcpyAsync(s->h_pinned, src, elems * 4, cudaMemcpyDeviceToHost, s->stream));
+        }
+        SG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+        memcpy(out + done * s->dim, s->h_pinned, elems * 4);
+        done += cnt;
+    }
+    return SG_OK;
+}
+
+int sg_store_set_order(sg_store *s, int order)
+{
+    if (!s || (order != SG_ORDER_SCALAR && order != SG_ORDER_AVX2)) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    s->order = order;
+    return SG_OK;
+}
+
+int sg_store_set_id_base(sg_store *s, uint32_t id_base)
+{
+    if (!s) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    s->id_base = id_base;
+    return SG_OK;
+}
+
+int sg_store_set_profiling(sg_store *s, int on)
+{
+    if (!s) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    s->profiling = on != 0;
+    s->ev_valid = false;
+    return SG_OK;
+}
+
+int sg_store_last_scan_ms(sg_store *s, float *ms_out, uint32_t *launches_out)
+{
+    if (!s || !ms_out) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    if (!s->ev_valid) {
+        set_error("no profiled search yet (sg_store_set_profiling(s,1), then search)");
+        return SG_ERR_INVALID;
+    }
+    SG_CUDA_TRY(cudaSetDevice(s->device));
+    SG_CUDA_TRY(cudaEventSynchronize(s->ev1));
+    SG_CUDA_TRY(cudaEventElapsedTime(ms_out, s->ev0, s->ev1));
+    if (launches_out) *launches_out = s->last_scan_launches;
+    return SG_OK;
+}
+
+int sg_store_search_device(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint32_t *d_ids, float *d_dist,
+                           uint32_t *d_counts, void *cuda_stream)
+{
+    if (!s || (b && (!d_q || !d_ids || !d_dist || !d_counts))) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    SG_CUDA_TRY(cudaSetDevice(s->device));
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s->stream;
+    return search_device_locked(s, d_q, b, k, d_ids, d_dist, d_counts, st);
+}
+
+int sg_store_search(sg_store *s, const float *queries, uint32_t b, uint32_t k, uint32_t *ids_out, float *dist_out,
+                    uint32_t *counts_out)
+{
+    if (!s || (b && (!queries || !ids_out || !dist_out || !counts_out))) return SG_ERR_INVALID;
+    if (b == 0) return SG_OK;
+    if (k == 0) {
+        set_error("k must be >= 1");
+        return SG_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> g(s->mu);
+    SG_CUDA_TRY(cudaSetDevice(s->device));
+    const size_t qbytes = (size_t)b * s->dim * 4, rbytes = (size_t)b * k * 4, cbytes = (size_t)b * 4;
+    int rc = grow_pinned(s, qbytes + 2 * rbytes + cbytes);
+    if (rc != SG_OK) return rc;
+    if ((rc = grow(s->d_queries, s->q_cap, (size_t)b * s->dim)) != SG_OK) return rc;
+    if ((size_t)b * k > s->res_cap) {
+        size_t c1 = s->res_cap, c2 = s->res_cap;
+        if ((rc = grow(s->d_ids, c1, (size_t)b * k)) != SG_OK) return rc;
+        if ((rc = grow(s->d_dist, c2, (size_t)b * k)) != SG_OK) return rc;
+        s->res_cap = c1 < c2 ? c1 : c2;
+    }
+    if ((rc = grow(s->d_counts, s->cnt_cap, (size_t)b)) != SG_OK) return rc;
+
+    uint8_t *hp = static_cast<uint8_t *>(s->h_pinned);
+    memcpy(hp, queries, qbytes);
+    SG_CUDA_TRY(cudaMemcpyAsync(s->d_queries, hp, qbytes, cudaMemcpyHostToDevice, s->stream));
+    rc = search_device_locked(s, s->d_queries, b, k, s->d_ids, s->d_dist, s->d_counts, s->stream);
+    if (rc != SG_OK) return rc;
+    SG_CUDA_TRY(cudaMemcpyAsync(hp + qbytes, s->d_ids, rbytes, cudaMemcpyDeviceToHost, s->stream));
+    SG_CUDA_TRY(cudaMemcpyAsync(hp + qbytes + rbytes, s->d_dist, rbytes, cudaMemcpyDeviceToHost, s->stream));
+    SG_CUDA_TRY(cudaMemcpyAsync(hp + qbytes + 2 * rbytes, s->d_counts, cbytes, cudaMemcpyDeviceToHost, s->stream));
+    SG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    memcpy(ids_out, hp + qbytes, rbytes);
+    memcpy(dist_out, hp + qbytes + rbytes, rbytes);
+    memcpy(counts_out, hp + qbytes + 2 * rbytes, cbytes);
+    return SG_OK;
+}
+
+int sg_merge_topk_device(int device, const uint32_t *d_ids, const float *d_dist, uint32_t b, uint32_t n_lists,
+                         uint32_t k, uint32_t *d_ids_out, float *d_dist_out, uint32_t *d_counts_out, void *cuda_stream)
+{
+    if (b && (!d_ids || !d_dist || !d_ids_out || !d_dist_out || !d_counts_out)) return SG_ERR_INVALID;
+    if (k == 0 || k > 1024) {
+        set_error("k=%u outside the supported range 1..1024", k);
+        return SG_ERR_UNSUPPORTED;
+    }
+    int rc = check_device(device, nullptr);
+    if (rc != SG_OK) return rc;
+    SG_CUDA_TRY(cudaSetDevice(device));
+    SG_CUDA_TRY(launch_merge_pairs(d_ids, d_dist, b, n_lists * k, k, d_ids_out, d_dist_out, d_counts_out,
+                                   static_cast<cudaStream_t>(cuda_stream)));
+    return SG_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// relevance fusion
+// ---------------------------------------------------------------------------------------
+void sg_fuse_default_weights(sg_fuse_weights *w)
+{
+    if (!w) return;  // relevance.rs:64-88
+    w->semantic = 0.18f;
+    w->entity = 0.17f;
+    w->tag = 0.05f;
+    w->importance = 0.05f;
+    w->momentum = 0.28f;
+    w->access_count = 0.14f;
+    w->graph_strength = 0.13f;
+}
+
+void sg_fuse_default_config(sg_fuse_config *c)
+{
+    if (!c) return;  // relevance.rs:147-177, :914
+    c->recency_boost_hours = 24;
+    c->recency_boost_multiplier = 1.2f;
+    c->graph_boost_multiplier = 1.15f;
+    c->min_score = 0.25f;
+    c->max_results = 5;
+}
+
+int sg_fuse_topk(int device, const sg_fuse_weights *w, const sg_fuse_config *cfg, const sg_candidate_feats *f,
+                 uint32_t n, int64_t now_unix_s, uint32_t *order_out, float *score_out, uint32_t *n_out,
+                 float *all_scores_out)
+{
+    if (!w || !cfg || !f || !n_out || (cfg->max_results && (!order_out || !score_out))) return SG_ERR_INVALID;
+    *n_out = 0;
+    if (n == 0 || cfg->max_results == 0) return SG_OK;
+    if (n > 8192) {
+        set_error("sg_fuse_topk supports up to 8192 candidates per call (got %u)", n);
+        return SG_ERR_UNSUPPORTED;
+    }
+    int rc = check_device(device, nullptr);
+    if (rc != SG_OK) return rc;
+    SG_CUDA_TRY(cudaSetDevice(device));
+    // one transient arena: 6 f32 + 1 u32 + 1 i64 per candidate in, order/score/all/n out
+    const size_t in_bytes = (size_t)n * (7 * 4 + 8);
+    const size_t out_bytes = (size_t)cfg->max_results * 8 + (size_t)n * 4 + 16;
+    uint8_t *d = nullptr, *h = nullptr;
+    SG_CUDA_TRY(cudaMalloc(&d, in_bytes + out_bytes + 32));
+    cudaError_t e = cudaHostAlloc(&h, in_bytes + out_bytes + 32, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        set_error("cudaHostAlloc: %s", cudaGetErrorString(e));
+        return SG_ERR_OOM;
+    }
+    cudaStream_t st = nullptr;
+    e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    int ret = SG_OK;
+    if (e == cudaSuccess) {
+        // created_at first (8-byte aligned), then the 4-byte arrays
+        size_t off = 0;
+        memcpy(h + off, f->created_at_unix_s, (size_t)n * 8); const size_t o_created = off; off += (size_t)n * 8;
+        const void *srcs[7] = {f->semantic, f->entity, f->tag, f->importance, f->momentum, f->graph_strength, f->access_count};
+        size_t offs[7];
+        for (int i = 0; i < 7; ++i) {
+            memcpy(h + off, srcs[i], (size_t)n * 4);
+            offs[i] = off;
+            off += (size_t)n * 4;
+        }
+        const size_t o_n = (off + 15) & ~(size_t)15;
+        const size_t o_order = o_n + 16, o_score = o_order + (size_t)cfg->max_results * 4;
+        const size_t o_all = o_score + (size_t)cfg->max_results * 4;
+        e = cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) {
+            FuseDev fd;
+            fd.created = reinterpret_cast<const int64_t *>(d + o_created);
+            fd.semantic = reinterpret_cast<const float *>(d + offs[0]);
+            fd.entity = reinterpret_cast<const float *>(d + offs[1]);
+            fd.tag = reinterpret_cast<const float *>(d + offs[2]);
+            fd.importance = reinterpret_cast<const float *>(d + offs[3]);
+            fd.momentum = reinterpret_cast<const float *>(d + offs[4]);
+            fd.graph = reinterpret_cast<const float *>(d + offs[5]);
+            fd.access = reinterpret_cast<const uint32_t *>(d + offs[6]);
+            e = launch_fuse_rank(fd, n, *w, *cfg, now_unix_s, reinterpret_cast<uint32_t *>(d + o_order),
+                                 reinterpret_cast<float *>(d + o_score), reinterpret_cast<uint32_t *>(d + o_n),
+                                 reinterpret_cast<float *>(d + o_all), st);
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h + o_n, d + o_n, o_all + (size_t)n * 4 - o_n, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) {
+            uint32_t m = *reinterpret_cast<uint32_t *>(h + o_n);
+            *n_out = m;
+            memcpy(order_out, h + o_order, (size_t)m * 4);
+            memcpy(score_out, h + o_score, (size_t)m * 4);
+            if (all_scores_out) memcpy(all_scores_out, h + o_all, (size_t)n * 4);
+        }
+    }
+    if (e != cudaSuccess) {
+        set_error("sg_fuse_topk: %s", cudaGetErrorString(e));
+        ret = SG_ERR_CUDA;
+    }
+    if (st) cudaStreamDestroy(st);
+    cudaFreeHost(h);
+    cudaFree(d);
+    return ret;
+}
+
+}  // extern "C"

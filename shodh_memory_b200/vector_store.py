@@ -1,0 +1,144 @@
+"""Host-side mirror of the reference's vector-store surface over the C ABI.
+
+`GpuVectorStore` exposes the method set `RetrievalEngine` uses on `VamanaIndex`
+(reference src/vector_db/vamana.rs: search :764, add_vector :853, build :200,
+mark_deleted :813, is_deleted :823, deleted_count :828, len :976,
+extract_all_vectors) with the same argument meaning and error behaviour, so the parity
+tests read like the reference's own.  All compute happens in libshodh_gpu.so."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+_DT = {"f16": capi.SG_DTYPE_F16, "f32": capi.SG_DTYPE_F32}
+
+
+def _ptr(a: np.ndarray, ty):
+    return a.ctypes.data_as(C.POINTER(ty))
+
+
+class GpuVectorStore:
+    def __init__(self, dim: int = 384, dtype: str = "f16", device: int = 0):
+        self._h = C.c_void_p()
+        self.dim = dim
+        self.dtype = dtype
+        self.device = device
+        capi.check(capi.lib().sg_store_create(C.byref(self._h), device, dim, _DT[dtype], capi.SG_METRIC_NEG_DOT))
+
+    # -- lifecycle --------------------------------------------------------------------
+    def close(self) -> None:
+        if self._h:
+            capi.lib().sg_store_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    # -- VamanaIndex surface ------------------------------------------------------------
+    def __len__(self) -> int:
+        n = C.c_uint64()
+        capi.check(capi.lib().sg_store_len(self._h, C.byref(n)))
+        return n.value
+
+    def reserve(self, n_rows: int) -> None:
+        capi.check(capi.lib().sg_store_reserve(self._h, n_rows))
+
+    def add_vector(self, vector) -> int:
+        """VamanaIndex::add_vector -> the new id."""
+        return self.add_vectors(np.asarray(vector, np.float32)[None, :])
+
+    def add_vectors(self, rows) -> int:
+        """VamanaIndex::build / rebuild_from_vectors (bulk) -> id of the first appended row."""
+        rows = np.ascontiguousarray(rows, np.float32)
+        if rows.ndim != 2 or rows.shape[1] != self.dim:
+            raise capi.SgError(capi.SG_ERR_DIM, f"expected [n,{self.dim}] rows, got {rows.shape}")
+        first = C.c_uint32()
+        capi.check(capi.lib().sg_store_append(self._h, _ptr(rows, C.c_float), rows.shape[0], C.byref(first)))
+        return first.value
+
+    build = add_vectors
+
+    def append_synthetic(self, seed: int, first_row: int, n: int) -> None:
+        capi.check(capi.lib().sg_store_append_synthetic(self._h, seed, first_row, n))
+
+    def mark_deleted(self, vector_id: int) -> bool:
+        ok = C.c_int()
+        capi.check(capi.lib().sg_store_mark_deleted(self._h, vector_id, C.byref(ok)))
+        return bool(ok.value)
+
+    def is_deleted(self, vector_id: int) -> bool:
+        d = C.c_int()
+        capi.check(capi.lib().sg_store_is_deleted(self._h, vector_id, C.byref(d)))
+        return bool(d.value)
+
+    def clear_deleted(self) -> None:
+        capi.check(capi.lib().sg_store_clear_deleted(self._h))
+
+    def deleted_count(self) -> int:
+        n = C.c_uint64()
+        capi.check(capi.lib().sg_store_deleted_count(self._h, C.byref(n)))
+        return n.value
+
+    def get_vectors(self, first: int, n: int) -> np.ndarray:
+        out = np.empty((n, self.dim), np.float32)
+        capi.check(capi.lib().sg_store_get_vectors(self._h, first, n, _ptr(out, C.c_float)))
+        return out
+
+    def extract_all_vectors(self) -> np.ndarray:
+        return self.get_vectors(0, len(self))
+
+    def set_order(self, order: str) -> None:
+        capi.check(capi.lib().sg_store_set_order(
+            self._h, capi.SG_ORDER_AVX2 if order == "avx2" else capi.SG_ORDER_SCALAR))
+
+    def set_id_base(self, base: int) -> None:
+        capi.check(capi.lib().sg_store_set_id_base(self._h, base))
+
+    def search(self, query, k: int):
+        """VamanaIndex::search(query, k) -> list[(id, distance)], distance = -dot, ascending."""
+        ids, dist, counts = self.search_batch(np.asarray(query, np.float32)[None, :], k)
+        c = int(counts[0])
+        return [(int(i), float(d)) for i, d in zip(ids[0, :c], dist[0, :c])]
+
+    def search_batch(self, queries, k: int):
+        """b queries at once -> (ids [b,k] u32, dist [b,k] f32, counts [b] u32)."""
+        q = np.ascontiguousarray(queries, np.float32)
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise capi.SgError(capi.SG_ERR_DIM, f"expected [b,{self.dim}] queries, got {q.shape}")
+        b = q.shape[0]
+        ids = np.empty((b, k), np.uint32)
+        dist = np.empty((b, k), np.float32)
+        counts = np.zeros(b, np.uint32)
+        capi.check(capi.lib().sg_store_search(self._h, _ptr(q, C.c_float), b, k, _ptr(ids, C.c_uint32),
+                                              _ptr(dist, C.c_float), _ptr(counts, C.c_uint32)))
+        return ids, dist, counts
+
+    def search_device(self, d_queries: int, b: int, k: int, d_ids: int, d_dist: int, d_counts: int,
+                      stream: int = 0) -> None:
+        """Raw device pointers (ints), asynchronous on `stream` (a cudaStream_t value)."""
+        capi.check(capi.lib().sg_store_search_device(self._h, d_queries, b, k, d_ids, d_dist, d_counts, stream))
+
+    # -- profiling hooks for bench.py -----------------------------------------------------
+    def set_profiling(self, on: bool) -> None:
+        capi.check(capi.lib().sg_store_set_profiling(self._h, int(on)))
+
+    def last_scan_ms(self):
+        ms, n = C.c_float(), C.c_uint32()
+        capi.check(capi.lib().sg_store_last_scan_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+def merge_topk_device(device: int, d_ids: int, d_dist: int, b: int, n_lists: int, k: int, d_ids_out: int,
+                      d_dist_out: int, d_counts_out: int, stream: int = 0) -> None:
+    capi.check(capi.lib().sg_merge_topk_device(device, d_ids, d_dist, b, n_lists, k, d_ids_out, d_dist_out,
+                                               d_counts_out, stream))
