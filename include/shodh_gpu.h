@@ -127,9 +127,21 @@ SG_API int sg_merge_topk_device(int device, const uint32_t *d_ids, const float *
                                 uint32_t b, uint32_t n_lists, uint32_t k, uint32_t *d_ids_out,
                                 float *d_dist_out, uint32_t *d_counts_out, void *cuda_stream);
 
-/* CUDA-event time of the scan kernel(s) of the most recent search, in ms
- * (bench.py roofline).  Enable with sg_store_set_profiling(s, 1). */
+/* general layout: element (query q, list l, slot j) lives at l*list_stride + q*query_stride + j
+ * in both d_ids and d_dist (e.g. the receive buffer of an all-gather: list_stride = per-rank block). */
+SG_API int sg_merge_topk_device_strided(int device, const uint32_t *d_ids, const float *d_dist,
+                                        uint32_t b, uint32_t n_lists, uint32_t k, uint64_t list_stride,
+                                        uint64_t query_stride, uint32_t *d_ids_out, float *d_dist_out,
+                                        uint32_t *d_counts_out, void *cuda_stream);
+
+/* CUDA-event timing of the scan kernel(s) inside each search (bench.py roofline): with
+ * profiling on, every search records an event pair around its sweep launches on the stream
+ * it runs on (no synchronisation).  sg_store_profile_read waits for the last recorded
+ * search, writes up to cap per-search durations (ms) in call order, returns how many
+ * searches were recorded since the last read/reset and the sweep launches per search. */
 SG_API int sg_store_set_profiling(sg_store *s, int on);
+SG_API int sg_store_profile_read(sg_store *s, float *ms_out, uint32_t cap, uint32_t *n_out,
+                                 uint32_t *launches_per_search_out);
 SG_API int sg_store_last_scan_ms(sg_store *s, float *ms_out, uint32_t *launches_out);
 
 /* TEST/BENCH ONLY: fill rows [first_row, first_row+n) of the deterministic synthetic

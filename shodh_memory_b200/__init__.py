@@ -26,5 +26,12 @@ def device_count() -> int:
     return n.value if rc == 0 else 0
 
 
-__all__ = ["GpuVectorStore", "merge_topk_device", "fuse_topk", "SgError", "version", "kernel_launch_count",
+def __getattr__(name):  # torch-dependent helpers load lazily (the C ABI itself needs no torch)
+    if name in ("ShardedGpuStore", "shard_range", "gathered_strides", "exchange"):
+        from . import sharded
+        return getattr(sharded, name)
+    raise AttributeError(name)
+
+
+__all__ = ["GpuVectorStore", "ShardedGpuStore", "merge_topk_device", "fuse_topk", "SgError", "version", "kernel_launch_count",
            "device_count", "capi"]

@@ -16,6 +16,7 @@ template <bool PAIRS>
 __global__ void __launch_bounds__(1024, 1)
 merge_kernel(const uint64_t *__restrict__ lists, const uint32_t *__restrict__ ids_in,
              const float *__restrict__ dist_in, uint32_t n_per_query, uint32_t k, uint32_t id_base,
+             uint64_t list_stride, uint64_t query_stride,
              uint32_t *__restrict__ ids_out, float *__restrict__ dist_out, uint32_t *__restrict__ counts)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -30,8 +31,10 @@ merge_kernel(const uint64_t *__restrict__ lists, const uint32_t *__restrict__ id
         for (uint32_t i = threadIdx.x; i < take; i += blockDim.x) {
             uint64_t key;
             if constexpr (PAIRS) {
-                uint32_t id = ids_in[base + pos + i];
-                key = (id == 0xFFFFFFFFu) ? KEY_SENTINEL : make_key(order_key32(dist_in[base + pos + i]), id);
+                const uint32_t e = pos + i, l = e / k, j = e - l * k;
+                const size_t at = (size_t)l * list_stride + (size_t)q * query_stride + j;
+                uint32_t id = ids_in[at];
+                key = (id == 0xFFFFFFFFu) ? KEY_SENTINEL : make_key(order_key32(dist_in[at]), id);
             } else {
                 key = lists[base + pos + i];
             }
@@ -69,8 +72,8 @@ merge_kernel(const uint64_t *__restrict__ lists, const uint32_t *__restrict__ id
 
 template <bool PAIRS>
 cudaError_t launch(const uint64_t *lists, const uint32_t *ids_in, const float *dist_in, uint32_t b,
-                   uint32_t n_per_query, uint32_t k, uint32_t id_base, uint32_t *ids, float *dist,
-                   uint32_t *counts, cudaStream_t st)
+                   uint32_t n_per_query, uint32_t k, uint32_t id_base, uint64_t list_stride, uint64_t query_stride,
+                   uint32_t *ids, float *dist, uint32_t *counts, cudaStream_t st)
 {
     if (b == 0) return cudaSuccess;
     uint32_t need = n_per_query < SORT_MAX ? next_pow2(n_per_query < 2 ? 2 : n_per_query) : SORT_MAX;
@@ -80,7 +83,8 @@ cudaError_t launch(const uint64_t *lists, const uint32_t *ids_in, const float *d
     auto kern = merge_kernel<PAIRS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SORT_MAX * 8));
     if (e != cudaSuccess) return e;
-    kern<<<b, threads, smem, st>>>(lists, ids_in, dist_in, n_per_query, k, id_base, ids, dist, counts);
+    kern<<<b, threads, smem, st>>>(lists, ids_in, dist_in, n_per_query, k, id_base, list_stride, query_stride, ids,
+                                   dist, counts);
     count_launch();
     return cudaGetLastError();
 }
@@ -91,14 +95,15 @@ cudaError_t launch_merge_keys(const uint64_t *d_lists, uint32_t b, uint32_t n_pe
                               uint32_t id_base, uint32_t *d_ids, float *d_dist, uint32_t *d_counts,
                               cudaStream_t st)
 {
-    return launch<false>(d_lists, nullptr, nullptr, b, n_per_query, k, id_base, d_ids, d_dist, d_counts, st);
+    return launch<false>(d_lists, nullptr, nullptr, b, n_per_query, k, id_base, 0, 0, d_ids, d_dist, d_counts, st);
 }
 
-cudaError_t launch_merge_pairs(const uint32_t *d_ids_in, const float *d_dist_in, uint32_t b,
-                               uint32_t n_per_query, uint32_t k, uint32_t *d_ids, float *d_dist,
-                               uint32_t *d_counts, cudaStream_t st)
+cudaError_t launch_merge_pairs(const uint32_t *d_ids_in, const float *d_dist_in, uint32_t b, uint32_t n_lists,
+                               uint32_t k, uint64_t list_stride, uint64_t query_stride, uint32_t *d_ids,
+                               float *d_dist, uint32_t *d_counts, cudaStream_t st)
 {
-    return launch<true>(nullptr, d_ids_in, d_dist_in, b, n_per_query, k, 0, d_ids, d_dist, d_counts, st);
+    return launch<true>(nullptr, d_ids_in, d_dist_in, b, n_lists * k, k, 0, list_stride, query_stride, d_ids, d_dist,
+                        d_counts, st);
 }
 
 }  // namespace sg

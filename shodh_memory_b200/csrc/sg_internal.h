@@ -27,9 +27,9 @@ cudaError_t launch_merge_keys(const uint64_t *d_lists, uint32_t b, uint32_t n_pe
                               uint32_t id_base, uint32_t *d_ids, float *d_dist, uint32_t *d_counts,
                               cudaStream_t st);
 // lists as (ids, dist) pairs [b][n_per_query]; id 0xFFFFFFFF marks an empty slot
-cudaError_t launch_merge_pairs(const uint32_t *d_ids_in, const float *d_dist_in, uint32_t b,
-                               uint32_t n_per_query, uint32_t k, uint32_t *d_ids, float *d_dist,
-                               uint32_t *d_counts, cudaStream_t st);
+cudaError_t launch_merge_pairs(const uint32_t *d_ids_in, const float *d_dist_in, uint32_t b, uint32_t n_lists,
+                               uint32_t k, uint64_t list_stride, uint64_t query_stride, uint32_t *d_ids,
+                               float *d_dist, uint32_t *d_counts, cudaStream_t st);
 
 // ---- convert / synth (store_kernels.cu) ----
 cudaError_t launch_f32_to_f16(const float *d_src, __half *d_dst, uint64_t n_elems, cudaStream_t st);

@@ -120,8 +120,8 @@ struct sg_store {
     float *d_stage = nullptr; size_t stage_cap = 0;     // floats, append staging
 
     bool profiling = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool ev_valid = false;
+    std::vector<cudaEvent_t> ev;  // pairs: ev[2i] before, ev[2i+1] after the sweep launches of search i
+    uint32_t ev_count = 0;        // searches recorded since the last read/reset
     uint32_t last_scan_launches = 0;
 };
 
@@ -272,7 +272,6 @@ int search_device_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, 
         return k == 0 ? SG_ERR_INVALID : SG_ERR_UNSUPPORTED;
     }
     s->last_scan_launches = 0;
-    s->ev_valid = false;
     if (s->n == 0) {  // VamanaIndex::search on an empty index: Ok(vec![]) (vamana.rs:766-768)
         SG_CUDA_TRY(launch_merge_keys(nullptr, b, 0, k, s->id_base, d_ids, d_dist, d_counts, st));
         return SG_OK;
@@ -290,7 +289,8 @@ int search_device_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, 
     rc = encode_corpus_tmap(&tmap, s->d_rows, s->dtype == SG_DTYPE_F16, s->dim, s->n, 32);
     if (rc != SG_OK) return rc;
 
-    if (s->profiling) SG_CUDA_TRY(cudaEventRecord(s->ev0, st));
+    const bool prof = s->profiling && 2 * (size_t)(s->ev_count + 1) <= s->ev.size();
+    if (prof) SG_CUDA_TRY(cudaEventRecord(s->ev[2 * s->ev_count], st));
     uint32_t done = 0;
     while (done < b) {
         const uint32_t rem = b - done;
@@ -316,9 +316,9 @@ int search_device_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, 
         ++s->last_scan_launches;
         done += nq;
     }
-    if (s->profiling) {
-        SG_CUDA_TRY(cudaEventRecord(s->ev1, st));
-        s->ev_valid = true;
+    if (prof) {
+        SG_CUDA_TRY(cudaEventRecord(s->ev[2 * s->ev_count + 1], st));
+        ++s->ev_count;
     }
     SG_CUDA_TRY(launch_merge_keys(s->d_lists, b, L * k, k, s->id_base, d_ids, d_dist, d_counts, st));
     return SG_OK;
@@ -379,8 +379,6 @@ int sg_store_create(sg_store **out, int device, uint32_t dim, int dtype, int met
     s->esize = dtype == SG_DTYPE_F16 ? 2 : 4;
     s->metric = metric;
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
-    if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
     if (e != cudaSuccess) {
         set_error("stream/event creation failed: %s", cudaGetErrorString(e));
         delete s;
@@ -404,8 +402,7 @@ void sg_store_destroy(sg_store *s)
     cudaFree(s->d_counts);
     cudaFree(s->d_stage);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
-    if (s->ev0) cudaEventDestroy(s->ev0);
-    if (s->ev1) cudaEventDestroy(s->ev1);
+    for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -581,8 +578,30 @@ int sg_store_set_profiling(sg_store *s, int on)
 {
     if (!s) return SG_ERR_INVALID;
     std::lock_guard<std::mutex> g(s->mu);
+    SG_CUDA_TRY(cudaSetDevice(s->device));
     s->profiling = on != 0;
-    s->ev_valid = false;
+    s->ev_count = 0;
+    const size_t want = 2 * 4096;
+    while (s->profiling && s->ev.size() < want) {
+        cudaEvent_t e;
+        SG_CUDA_TRY(cudaEventCreate(&e));
+        s->ev.push_back(e);
+    }
+    return SG_OK;
+}
+
+int sg_store_profile_read(sg_store *s, float *ms_out, uint32_t cap, uint32_t *n_out, uint32_t *launches_out)
+{
+    if (!s || !n_out || (cap && !ms_out)) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    SG_CUDA_TRY(cudaSetDevice(s->device));
+    const uint32_t n = s->ev_count;
+    *n_out = n;
+    if (launches_out) *launches_out = s->last_scan_launches;
+    if (n) SG_CUDA_TRY(cudaEventSynchronize(s->ev[2 * (n - 1) + 1]));
+    for (uint32_t i = 0; i < n && i < cap; ++i)
+        SG_CUDA_TRY(cudaEventElapsedTime(ms_out + i, s->ev[2 * i], s->ev[2 * i + 1]));
+    s->ev_count = 0;
     return SG_OK;
 }
 
@@ -590,14 +609,16 @@ int sg_store_last_scan_ms(sg_store *s, float *ms_out, uint32_t *launches_out)
 {
     if (!s || !ms_out) return SG_ERR_INVALID;
     std::lock_guard<std::mutex> g(s->mu);
-    if (!s->ev_valid) {
-        set_error("no profiled search yet (sg_store_set_profiling(s,1), then search)");
+    if (!s->ev_count) {
+        set_error("no profiled search recorded (sg_store_set_profiling(s,1), then search)");
         return SG_ERR_INVALID;
     }
     SG_CUDA_TRY(cudaSetDevice(s->device));
-    SG_CUDA_TRY(cudaEventSynchronize(s->ev1));
-    SG_CUDA_TRY(cudaEventElapsedTime(ms_out, s->ev0, s->ev1));
+    const uint32_t i = s->ev_count - 1;
+    SG_CUDA_TRY(cudaEventSynchronize(s->ev[2 * i + 1]));
+    SG_CUDA_TRY(cudaEventElapsedTime(ms_out, s->ev[2 * i], s->ev[2 * i + 1]));
     if (launches_out) *launches_out = s->last_scan_launches;
+    s->ev_count = 0;
     return SG_OK;
 }
 
@@ -649,8 +670,9 @@ int sg_store_search(sg_store *s, const float *queries, uint32_t b, uint32_t k, u
     return SG_OK;
 }
 
-int sg_merge_topk_device(int device, const uint32_t *d_ids, const float *d_dist, uint32_t b, uint32_t n_lists,
-                         uint32_t k, uint32_t *d_ids_out, float *d_dist_out, uint32_t *d_counts_out, void *cuda_stream)
+int sg_merge_topk_device_strided(int device, const uint32_t *d_ids, const float *d_dist, uint32_t b, uint32_t n_lists,
+                                 uint32_t k, uint64_t list_stride, uint64_t query_stride, uint32_t *d_ids_out,
+                                 float *d_dist_out, uint32_t *d_counts_out, void *cuda_stream)
 {
     if (b && (!d_ids || !d_dist || !d_ids_out || !d_dist_out || !d_counts_out)) return SG_ERR_INVALID;
     if (k == 0 || k > 1024) {
@@ -660,9 +682,16 @@ int sg_merge_topk_device(int device, const uint32_t *d_ids, const float *d_dist,
     int rc = check_device(device, nullptr);
     if (rc != SG_OK) return rc;
     SG_CUDA_TRY(cudaSetDevice(device));
-    SG_CUDA_TRY(launch_merge_pairs(d_ids, d_dist, b, n_lists * k, k, d_ids_out, d_dist_out, d_counts_out,
-                                   static_cast<cudaStream_t>(cuda_stream)));
+    SG_CUDA_TRY(launch_merge_pairs(d_ids, d_dist, b, n_lists, k, list_stride, query_stride, d_ids_out, d_dist_out,
+                                   d_counts_out, static_cast<cudaStream_t>(cuda_stream)));
     return SG_OK;
+}
+
+int sg_merge_topk_device(int device, const uint32_t *d_ids, const float *d_dist, uint32_t b, uint32_t n_lists,
+                         uint32_t k, uint32_t *d_ids_out, float *d_dist_out, uint32_t *d_counts_out, void *cuda_stream)
+{
+    return sg_merge_topk_device_strided(device, d_ids, d_dist, b, n_lists, k, k, (uint64_t)n_lists * k, d_ids_out,
+                                        d_dist_out, d_counts_out, cuda_stream);
 }
 
 // ---------------------------------------------------------------------------------------

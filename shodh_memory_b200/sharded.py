@@ -1,0 +1,109 @@
+"""Row-sharded store across the GPUs of one box (BASELINE.json config 4).
+
+One process per GPU (torch.distributed).  GPU g holds the contiguous row block
+[g*N/W, (g+1)*N/W) and reports global ids (id_base).  A search is: local exact sweep ->
+ONE all-gather of the per-shard (id, dist)[b,k] lists (b*k*8 bytes per rank, pure latency on
+NVLink/NVSwitch) -> k-way merge on every rank with the same (dist, id) rule, straight out of
+the all-gather receive buffer (strided merge, no repack).
+
+torch is plumbing here (device buffers, streams, the process group); the sweep and the
+merge are this package's CUDA kernels.  The packing / layout logic is backend-agnostic so the
+gloo CPU tests can exercise it (tests/test_sharded_cpu.py)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .vector_store import GpuVectorStore, merge_topk_device
+
+
+def shard_range(n_total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous row block of `rank`: [rank*N/W, (rank+1)*N/W) (integer division, no gaps)."""
+    return (n_total * rank) // world, (n_total * (rank + 1)) // world
+
+
+def gathered_strides(b: int, k: int) -> tuple[int, int, int]:
+    """Layout of the all-gather receive buffer [world][2][b][k] (int32 words): returns
+    (list_stride, query_stride, dist_offset) for the strided merge."""
+    return 2 * b * k, k, b * k
+
+
+def exchange(local_pack: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """local_pack: int32 [2,b,k] (ids, dist bit patterns) -> gathered int32 [world,2,b,k]."""
+    if world == 1:
+        return local_pack.unsqueeze(0)
+    out = torch.empty(world * local_pack.numel(), dtype=local_pack.dtype, device=local_pack.device)
+    dist.all_gather_into_tensor(out, local_pack.reshape(-1), group=group)
+    return out.view((world,) + tuple(local_pack.shape))
+
+
+class ShardedGpuStore:
+    def __init__(self, n_total: int, dim: int = 384, dtype: str = "f16", rank: int = 0, world: int = 1,
+                 device: int = 0, group=None):
+        self.n_total, self.dim, self.rank, self.world, self.device, self.group = n_total, dim, rank, world, device, group
+        self.lo, self.hi = shard_range(n_total, rank, world)
+        self.local = GpuVectorStore(dim, dtype, device)
+        self.local.set_id_base(self.lo)
+        self._bufs = {}
+
+    def fill_synthetic(self, seed: int) -> None:
+        self.local.reserve(self.hi - self.lo)
+        self.local.append_synthetic(seed, self.lo, self.hi - self.lo)
+
+    def add_rows(self, rows_global: np.ndarray) -> None:
+        """rows_global: the FULL [n_total, dim] matrix (every rank passes the same); keeps its block."""
+        self.local.add_vectors(rows_global[self.lo:self.hi])
+
+    def _buffers(self, b: int, k: int):
+        key = (b, k)
+        if key not in self._bufs:
+            dev = torch.device("cuda", self.device)
+            self._bufs[key] = dict(
+                pack=torch.empty((2, b, k), dtype=torch.int32, device=dev),
+                cnt=torch.empty(b, dtype=torch.int32, device=dev),
+                out_ids=torch.empty((b, k), dtype=torch.int32, device=dev),
+                out_dist=torch.empty((b, k), dtype=torch.float32, device=dev),
+                out_cnt=torch.empty(b, dtype=torch.int32, device=dev))
+        return self._bufs[key]
+
+    def search_device(self, d_queries: torch.Tensor, k: int):
+        """d_queries: f32 [b,dim] on this rank's GPU (same on every rank).  Asynchronous on the
+        current torch stream.  Returns (ids int32 [b,k] (bit pattern of u32), dist f32 [b,k], counts)."""
+        b = d_queries.shape[0]
+        bufs = self._buffers(b, k)
+        stream = torch.cuda.current_stream().cuda_stream
+        pack = bufs["pack"]
+        self.local.search_device(d_queries.data_ptr(), b, k, pack[0].data_ptr(), pack[1].data_ptr(),
+                                 bufs["cnt"].data_ptr(), stream)
+        if self.world == 1:
+            return pack[0], pack[1].view(torch.float32), bufs["cnt"]
+        gathered = exchange(pack, self.world, self.group)
+        ls, qs, doff = gathered_strides(b, k)
+        base = gathered.data_ptr()
+        merge_topk_device(self.device, base, base + 4 * doff, b, self.world, k, bufs["out_ids"].data_ptr(),
+                          bufs["out_dist"].data_ptr(), bufs["out_cnt"].data_ptr(), stream,
+                          list_stride=ls, query_stride=qs)
+        return bufs["out_ids"], bufs["out_dist"], bufs["out_cnt"]
+
+    def search(self, queries_host: torch.Tensor, k: int):
+        """End-to-end form: pinned host queries in, pinned host results out (H2D + D2H inside)."""
+        b = queries_host.shape[0]
+        key = ("h", b, k)
+        if key not in self._bufs:
+            dev = torch.device("cuda", self.device)
+            self._bufs[key] = dict(dq=torch.empty((b, self.dim), dtype=torch.float32, device=dev),
+                                   h_ids=torch.empty((b, k), dtype=torch.int32).pin_memory(),
+                                   h_dist=torch.empty((b, k), dtype=torch.float32).pin_memory(),
+                                   h_cnt=torch.empty(b, dtype=torch.int32).pin_memory())
+        hb = self._bufs[key]
+        hb["dq"].copy_(queries_host, non_blocking=True)
+        ids, dst, cnt = self.search_device(hb["dq"], k)
+        hb["h_ids"].copy_(ids, non_blocking=True)
+        hb["h_dist"].copy_(dst, non_blocking=True)
+        hb["h_cnt"].copy_(cnt, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return hb["h_ids"], hb["h_dist"], hb["h_cnt"]
+
+    def close(self) -> None:
+        self.local.close()

@@ -132,6 +132,13 @@ class GpuVectorStore:
     def set_profiling(self, on: bool) -> None:
         capi.check(capi.lib().sg_store_set_profiling(self._h, int(on)))
 
+    def profile_read(self, cap: int = 4096):
+        """-> (per-search scan ms array, sweep launches per search)"""
+        ms = np.zeros(cap, np.float32)
+        n, l = C.c_uint32(), C.c_uint32()
+        capi.check(capi.lib().sg_store_profile_read(self._h, _ptr(ms, C.c_float), cap, C.byref(n), C.byref(l)))
+        return ms[:min(n.value, cap)].copy(), l.value
+
     def last_scan_ms(self):
         ms, n = C.c_float(), C.c_uint32()
         capi.check(capi.lib().sg_store_last_scan_ms(self._h, C.byref(ms), C.byref(n)))
@@ -139,6 +146,10 @@ class GpuVectorStore:
 
 
 def merge_topk_device(device: int, d_ids: int, d_dist: int, b: int, n_lists: int, k: int, d_ids_out: int,
-                      d_dist_out: int, d_counts_out: int, stream: int = 0) -> None:
-    capi.check(capi.lib().sg_merge_topk_device(device, d_ids, d_dist, b, n_lists, k, d_ids_out, d_dist_out,
-                                               d_counts_out, stream))
+                      d_dist_out: int, d_counts_out: int, stream: int = 0, list_stride: int | None = None,
+                      query_stride: int | None = None) -> None:
+    """Element (q, list l, slot j) at l*list_stride + q*query_stride + j; default layout [b, n_lists, k]."""
+    if list_stride is None:
+        list_stride, query_stride = k, n_lists * k
+    capi.check(capi.lib().sg_merge_topk_device_strided(device, d_ids, d_dist, b, n_lists, k, list_stride,
+                                                       query_stride, d_ids_out, d_dist_out, d_counts_out, stream))

@@ -224,15 +224,7 @@ def test_neg_zero_sorts_before_pos_zero(oracle):
 
 
 # ---- retrieval.rs:2430-2438 test_vector family ----
-def ref_test_vector(i, dim):
-    """retrieval.rs:2430-2438 (iterator sum is sequential left-to-right in f32)."""
-    v = np.ones(dim, F)
-    v[i % dim] = F(v[i % dim] + F(F(0.5) * F(np.sqrt(F(dim)))))
-    s = F(0)
-    for x in v:
-        s = F(s + F(x * x))
-    norm = F(np.sqrt(s))
-    return (v / norm).astype(F)
+from helpers import ref_test_vector  # retrieval.rs:2430-2438
 
 
 @pytest.mark.parametrize("variant", [0, 1])

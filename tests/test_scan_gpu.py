@@ -162,7 +162,7 @@ def test_vamana_unit_test_five_vectors(sg, oracle):
 
 def test_retrieval_test_vector_self_query(sg, oracle):
     """retrieval.rs:2430-2438 / :2482-2529: test_vector(i) retrieves its own id first."""
-    from tests.test_oracle_pins import ref_test_vector
+    from helpers import ref_test_vector
     corpus = np.stack([ref_test_vector(i, 384) for i in range(300)])
     st = sg.GpuVectorStore(384, "f32")
     st.add_vectors(corpus)
