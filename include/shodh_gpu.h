@@ -114,7 +114,7 @@ SG_API int sg_store_search(sg_store *s, const float *queries_f32, uint32_t b, ui
                            uint32_t *ids_out, float *dist_out, uint32_t *counts_out);
 
 /* same, with queries and results resident in device memory and asynchronous on
- * `cuda_stream` (a cudaStream_t; NULL = the store's own stream).  This is the
+ * `cuda_stream` (a cudaStream_t; NULL = the CUDA default stream).  This is the
  * form the GPU encoder feeds and the multi-GPU exchange consumes. */
 SG_API int sg_store_search_device(sg_store *s, const float *d_queries_f32, uint32_t b, uint32_t k,
                                   uint32_t *d_ids_out, float *d_dist_out, uint32_t *d_counts_out,

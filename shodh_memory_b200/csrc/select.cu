@@ -12,17 +12,24 @@ namespace {
 
 constexpr uint32_t SORT_MAX = 8192;  // keys per in-smem sort (64 KB)
 
+// One CTA per (query, group).  With n_groups == 1 the CTA reduces all of the query's keys and
+// writes decoded (id, dist) results; with n_groups > 1 (first level of a two-level merge) it
+// reduces keys [grp*group_keys, ...) of the query and writes its k best RAW keys to keys_out.
 template <bool PAIRS>
 __global__ void __launch_bounds__(1024, 1)
 merge_kernel(const uint64_t *__restrict__ lists, const uint32_t *__restrict__ ids_in,
-             const float *__restrict__ dist_in, uint32_t n_per_query, uint32_t k, uint32_t id_base,
-             uint64_t list_stride, uint64_t query_stride,
-             uint32_t *__restrict__ ids_out, float *__restrict__ dist_out, uint32_t *__restrict__ counts)
+             const float *__restrict__ dist_in, uint32_t n_per_query_total, uint32_t group_keys, uint32_t n_groups,
+             uint32_t k, uint32_t id_base, uint64_t list_stride, uint64_t query_stride,
+             uint64_t *__restrict__ keys_out, uint32_t *__restrict__ ids_out, float *__restrict__ dist_out,
+             uint32_t *__restrict__ counts)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint64_t *buf = reinterpret_cast<uint64_t *>(smem_raw);
-    const uint32_t q = blockIdx.x;
-    const size_t base = (size_t)q * n_per_query;
+    const uint32_t q = blockIdx.x / n_groups, grp = blockIdx.x - q * n_groups;
+    const uint32_t first = grp * group_keys;
+    const uint32_t n_per_query = first >= n_per_query_total ? 0
+                                 : (n_per_query_total - first < group_keys ? n_per_query_total - first : group_keys);
+    const size_t base = (size_t)q * n_per_query_total + first;
 
     uint32_t kept = 0, pos = 0;
     while (pos < n_per_query) {
@@ -31,7 +38,7 @@ merge_kernel(const uint64_t *__restrict__ lists, const uint32_t *__restrict__ id
         for (uint32_t i = threadIdx.x; i < take; i += blockDim.x) {
             uint64_t key;
             if constexpr (PAIRS) {
-                const uint32_t e = pos + i, l = e / k, j = e - l * k;
+                const uint32_t e = first + pos + i, l = e / k, j = e - l * k;
                 const size_t at = (size_t)l * list_stride + (size_t)q * query_stride + j;
                 uint32_t id = ids_in[at];
                 key = (id == 0xFFFFFFFFu) ? KEY_SENTINEL : make_key(order_key32(dist_in[at]), id);
@@ -51,6 +58,11 @@ merge_kernel(const uint64_t *__restrict__ lists, const uint32_t *__restrict__ id
     if (n_per_query == 0) {
         for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) buf[i] = KEY_SENTINEL;
         __syncthreads();
+    }
+    if (n_groups > 1) {
+        uint64_t *out = keys_out + ((size_t)q * n_groups + grp) * k;
+        for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) out[i] = i < kept ? buf[i] : KEY_SENTINEL;
+        return;
     }
     uint32_t local = 0;
     for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
@@ -72,38 +84,59 @@ merge_kernel(const uint64_t *__restrict__ lists, const uint32_t *__restrict__ id
 
 template <bool PAIRS>
 cudaError_t launch(const uint64_t *lists, const uint32_t *ids_in, const float *dist_in, uint32_t b,
-                   uint32_t n_per_query, uint32_t k, uint32_t id_base, uint64_t list_stride, uint64_t query_stride,
-                   uint32_t *ids, float *dist, uint32_t *counts, cudaStream_t st)
+                   uint32_t n_per_query, uint32_t group_keys, uint32_t n_groups, uint32_t k, uint32_t id_base,
+                   uint64_t list_stride, uint64_t query_stride, uint64_t *keys_out, uint32_t *ids, float *dist,
+                   uint32_t *counts, cudaStream_t st)
 {
     if (b == 0) return cudaSuccess;
-    uint32_t need = n_per_query < SORT_MAX ? next_pow2(n_per_query < 2 ? 2 : n_per_query) : SORT_MAX;
+    const uint32_t per_cta = n_groups > 1 ? group_keys : n_per_query;
+    uint32_t need = per_cta < SORT_MAX ? next_pow2(per_cta < 2 ? 2 : per_cta) : SORT_MAX;
     if (need < k) need = next_pow2(k);
     size_t smem = (size_t)need * 8;
     uint32_t threads = need / 2 < 1024 ? (need / 2 < 32 ? 32 : need / 2) : 1024;
     auto kern = merge_kernel<PAIRS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SORT_MAX * 8));
     if (e != cudaSuccess) return e;
-    kern<<<b, threads, smem, st>>>(lists, ids_in, dist_in, n_per_query, k, id_base, list_stride, query_stride, ids,
-                                   dist, counts);
+    kern<<<b * n_groups, threads, smem, st>>>(lists, ids_in, dist_in, n_per_query, group_keys, n_groups, k, id_base,
+                                              list_stride, query_stride, keys_out, ids, dist, counts);
     count_launch();
     return cudaGetLastError();
 }
 
 }  // namespace
 
-cudaError_t launch_merge_keys(const uint64_t *d_lists, uint32_t b, uint32_t n_per_query, uint32_t k,
-                              uint32_t id_base, uint32_t *d_ids, float *d_dist, uint32_t *d_counts,
+// how many first-level groups a (n_lists x k)-key merge is split into (1 = single level)
+uint32_t merge_groups(uint32_t n_lists, uint32_t k)
+{
+    if ((uint64_t)n_lists * k <= 4096) return 1;
+    uint32_t lists_per_group = 2048 / k ? 2048 / k : 1;
+    if (lists_per_group < 2) lists_per_group = 2;
+    return (n_lists + lists_per_group - 1) / lists_per_group;
+}
+
+cudaError_t launch_merge_keys(const uint64_t *d_lists, uint32_t b, uint32_t n_lists, uint32_t k, uint32_t id_base,
+                              uint64_t *d_scratch, uint32_t *d_ids, float *d_dist, uint32_t *d_counts,
                               cudaStream_t st)
 {
-    return launch<false>(d_lists, nullptr, nullptr, b, n_per_query, k, id_base, 0, 0, d_ids, d_dist, d_counts, st);
+    const uint32_t groups = d_scratch ? merge_groups(n_lists, k) : 1;
+    if (groups > 1) {
+        const uint32_t lists_per_group = (n_lists + groups - 1) / groups;
+        cudaError_t e = launch<false>(d_lists, nullptr, nullptr, b, n_lists * k, lists_per_group * k, groups, k, 0, 0, 0,
+                                      d_scratch, nullptr, nullptr, nullptr, st);
+        if (e != cudaSuccess) return e;
+        return launch<false>(d_scratch, nullptr, nullptr, b, groups * k, groups * k, 1, k, id_base, 0, 0, nullptr,
+                             d_ids, d_dist, d_counts, st);
+    }
+    return launch<false>(d_lists, nullptr, nullptr, b, n_lists * k, n_lists * k, 1, k, id_base, 0, 0, nullptr, d_ids,
+                         d_dist, d_counts, st);
 }
 
 cudaError_t launch_merge_pairs(const uint32_t *d_ids_in, const float *d_dist_in, uint32_t b, uint32_t n_lists,
                                uint32_t k, uint64_t list_stride, uint64_t query_stride, uint32_t *d_ids,
                                float *d_dist, uint32_t *d_counts, cudaStream_t st)
 {
-    return launch<true>(nullptr, d_ids_in, d_dist_in, b, n_lists * k, k, 0, list_stride, query_stride, d_ids, d_dist,
-                        d_counts, st);
+    return launch<true>(nullptr, d_ids_in, d_dist_in, b, n_lists * k, n_lists * k, 1, k, 0, list_stride, query_stride,
+                        nullptr, d_ids, d_dist, d_counts, st);
 }
 
 }  // namespace sg

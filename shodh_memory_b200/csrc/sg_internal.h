@@ -22,9 +22,11 @@ cudaError_t launch_scan_exact(const CUtensorMap &tmap, const ScanArgs &a, int qb
                               uint32_t grid, uint32_t W, size_t smem, cudaStream_t st);
 
 // ---- select.cu ----
-// lists [b][n_per_query] u64 keys (any order, sentinel padded) -> top-k per query
-cudaError_t launch_merge_keys(const uint64_t *d_lists, uint32_t b, uint32_t n_per_query, uint32_t k,
-                              uint32_t id_base, uint32_t *d_ids, float *d_dist, uint32_t *d_counts,
+// lists [b][n_lists][k] u64 keys (sentinel padded) -> top-k per query.  d_scratch (may be null) holds
+// [b][merge_groups(n_lists,k)][k] keys and enables the two-level merge for large n_lists*k.
+uint32_t merge_groups(uint32_t n_lists, uint32_t k);
+cudaError_t launch_merge_keys(const uint64_t *d_lists, uint32_t b, uint32_t n_lists, uint32_t k, uint32_t id_base,
+                              uint64_t *d_scratch, uint32_t *d_ids, float *d_dist, uint32_t *d_counts,
                               cudaStream_t st);
 // lists as (ids, dist) pairs [b][n_per_query]; id 0xFFFFFFFF marks an empty slot
 cudaError_t launch_merge_pairs(const uint32_t *d_ids_in, const float *d_dist_in, uint32_t b, uint32_t n_lists,

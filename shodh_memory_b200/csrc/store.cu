@@ -115,6 +115,7 @@ struct sg_store {
     // scratch
     float *d_queries = nullptr;  size_t q_cap = 0;      // floats
     uint64_t *d_lists = nullptr; size_t lists_cap = 0;  // keys
+    uint64_t *d_lists2 = nullptr; size_t lists2_cap = 0; // first-level merge output
     uint32_t *d_ids = nullptr; float *d_dist = nullptr; uint32_t *d_counts = nullptr; size_t res_cap = 0, cnt_cap = 0;
     void *h_pinned = nullptr; size_t pinned_cap = 0;
     float *d_stage = nullptr; size_t stage_cap = 0;     // floats, append staging
@@ -273,7 +274,7 @@ int search_device_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, 
     }
     s->last_scan_launches = 0;
     if (s->n == 0) {  // VamanaIndex::search on an empty index: Ok(vec![]) (vamana.rs:766-768)
-        SG_CUDA_TRY(launch_merge_keys(nullptr, b, 0, k, s->id_base, d_ids, d_dist, d_counts, st));
+        SG_CUDA_TRY(launch_merge_keys(nullptr, b, 0, k, s->id_base, nullptr, d_ids, d_dist, d_counts, st));
         return SG_OK;
     }
     // one plan for the widest sweep; narrower sweeps reuse W/ring/grid (their smem is smaller)
@@ -284,6 +285,8 @@ int search_device_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, 
     const uint32_t L = plan.grid;
     rc = grow(s->d_lists, s->lists_cap, (size_t)b * L * k);
     if (rc != SG_OK) return rc;
+    const uint32_t groups = merge_groups(L, k);
+    if (groups > 1 && (rc = grow(s->d_lists2, s->lists2_cap, (size_t)b * groups * k)) != SG_OK) return rc;
 
     CUtensorMap tmap;
     rc = encode_corpus_tmap(&tmap, s->d_rows, s->dtype == SG_DTYPE_F16, s->dim, s->n, 32);
@@ -320,7 +323,8 @@ int search_device_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, 
         SG_CUDA_TRY(cudaEventRecord(s->ev[2 * s->ev_count + 1], st));
         ++s->ev_count;
     }
-    SG_CUDA_TRY(launch_merge_keys(s->d_lists, b, L * k, k, s->id_base, d_ids, d_dist, d_counts, st));
+    SG_CUDA_TRY(launch_merge_keys(s->d_lists, b, L, k, s->id_base, groups > 1 ? s->d_lists2 : nullptr, d_ids, d_dist,
+                                  d_counts, st));
     return SG_OK;
 }
 
@@ -397,6 +401,7 @@ void sg_store_destroy(sg_store *s)
     cudaFree(s->d_deleted);
     cudaFree(s->d_queries);
     cudaFree(s->d_lists);
+    cudaFree(s->d_lists2);
     cudaFree(s->d_ids);
     cudaFree(s->d_dist);
     cudaFree(s->d_counts);
@@ -628,7 +633,7 @@ int sg_store_search_device(sg_store *s, const float *d_q, uint32_t b, uint32_t k
     if (!s || (b && (!d_q || !d_ids || !d_dist || !d_counts))) return SG_ERR_INVALID;
     std::lock_guard<std::mutex> g(s->mu);
     SG_CUDA_TRY(cudaSetDevice(s->device));
-    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s->stream;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);  // NULL = the CUDA (legacy) default stream
     return search_device_locked(s, d_q, b, k, d_ids, d_dist, d_counts, st);
 }
 
