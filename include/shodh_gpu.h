@@ -120,6 +120,12 @@ SG_API int sg_store_search_device(sg_store *s, const float *d_queries_f32, uint3
                                   uint32_t *d_ids_out, float *d_dist_out, uint32_t *d_counts_out,
                                   void *cuda_stream);
 
+/* Batched searches (b >= 5, k <= 24, F16 store) run the tensor-core sweep: approximate scores
+ * select k+slack candidates, which are re-scored exactly and certified with a rigorous error
+ * bound; queries that cannot be certified are re-run on the exact sweep, so results are always
+ * the exact ones.  Statistics: queries that took the tensor path / that needed the re-run. */
+SG_API int sg_store_tc_stats(sg_store *s, uint64_t *queries_out, uint64_t *flagged_out);
+
 /* k-way merge of per-shard results: lists [b, n_lists, k] of (id, dist)
  * already sorted by (dist, id) -> the global top-k per query, same order rule.
  * All pointers are device pointers; asynchronous on cuda_stream. */

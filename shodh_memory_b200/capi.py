@@ -90,6 +90,7 @@ def lib() -> C.CDLL:
     L.sg_merge_topk_device.argtypes = [C.c_int, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
     L.sg_merge_topk_device_strided.argtypes = [C.c_int, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
                                                C.c_uint64, vp, vp, vp, vp]
+    L.sg_store_tc_stats.argtypes = [vp, u64p, u64p]
     L.sg_store_profile_read.argtypes = [vp, f32p, C.c_uint32, u32p, u32p]
     L.sg_fuse_default_weights.argtypes = [C.POINTER(FuseWeights)]
     L.sg_fuse_default_weights.restype = None

@@ -1,0 +1,455 @@
+// scan_tc.cu -- the tensor-core corpus sweep ("path B") for batched queries.
+//
+// For b >= 5 queries the row loop of VamanaIndex::brute_force_search (reference
+// src/vector_db/vamana.rs:1167-1188) is a [b x dim] . [dim x n_rows] contraction: at b = 256
+// it needs ~2 PFLOP/s to keep up with HBM, which only tcgen05 can deliver.  The tensor cores
+// see fp16(query) x fp16(row) with f32 accumulation, i.e. APPROXIMATE scores; exactness is
+// restored by over-selection + exact re-scoring:
+//   K1 (this file, scan_tc_kernel): one sweep; per query keep the KK = k + slack best
+//       approximate scores (a GPU-wide shared threshold keeps the candidate traffic tiny);
+//   K2 (finalize_tc_kernel): per query take the global top-KK approximate candidates,
+//       re-score them in EXACTLY the reference's summation order (distance_inline.rs:157-173 /
+//       :67-111), sort by (dist, id), and certify with a rigorous error bound E that no row
+//       outside the candidate set can reach the top k:  kth_exact_sim > weakest_kept_approx + E.
+//       Queries that cannot be certified are flagged and re-run on the exact path A.
+// So the result is bit-identical to path A / the CPU oracle, or the query is flagged.
+//
+// B200 mapping (one CTA per SM, 256 threads, persistent over 128-row corpus tiles):
+//   warp 0   TMA producer: the fp16 query block (A operand, 128 x dim, resident for the whole
+//            sweep) and a ring of K-blocks of corpus tiles (B operand, 128 rows x 64 elems,
+//            SWIZZLE_128B, K-major -- the same boxes path A streams);
+//   warp 1   MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128 (queries) x N=128 (rows),
+//            K=16 per instruction, accumulators in TMEM (4 stages x 128 columns);
+//   warp 2   TMEM allocator;
+//   warps 4-7 epilogue: thread t owns query t = TMEM lane t; tcgen05.ld 32 columns at a time,
+//            compares against its threshold, inserts the (rare) hits into its sorted list in
+//            shared memory.
+// HBM-bound: algorithmic bytes per sweep = n_rows * dim * 2; the MMA work per row is
+// 12 cycles against ~33 cycles of HBM time per row per SM.
+#include "sg_internal.h"
+
+namespace sg {
+namespace {
+
+constexpr uint32_t TC_M = 128;          // queries per sweep (TMEM lanes)
+constexpr uint32_t TC_N = 128;          // corpus rows per tile (TMEM columns per accumulator)
+constexpr uint32_t TC_KB = 64;          // fp16 elements per K-block (one 128B swizzle row)
+constexpr uint32_t TC_STAGE_BYTES = TC_N * 128;   // 16 KB
+constexpr uint32_t TC_ACC_STAGES = 4;   // 4 x 128 = 512 TMEM columns
+constexpr uint32_t TC_THREADS = 256;
+
+// ---- tcgen05 wrappers ---------------------------------------------------------------------
+SG_DEVICE_INLINE void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+SG_DEVICE_INLINE void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+SG_DEVICE_INLINE void tmem_alloc(uint32_t smem_dst, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+SG_DEVICE_INLINE void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, f32 accumulate
+SG_DEVICE_INLINE void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs have completed
+SG_DEVICE_INLINE void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+SG_DEVICE_INLINE void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+SG_DEVICE_INLINE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4 in
+// bits [0,14), stride byte offset (8 rows x 128 B = 1024) >> 4 in [32,46), version 1 at bit 46,
+// layout type 2 (SWIZZLE_128B) in [61,64).  The leading byte offset is unused for this layout.
+SG_DEVICE_INLINE uint64_t make_sw128_desc(uint32_t smem_addr)
+{
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D=f32 (bits 4-5 = 1), A=B=f16 (0), both K-major, N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) { return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24); }
+
+SG_DEVICE_INLINE uint32_t ld_relaxed_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// sorted insert of `key` into the thread's ascending list (entry j at my[j*128]); returns
+// (new_count << 32) | new_threshold.  Out of line: hits are rare, the compare loop stays small.
+__device__ __noinline__ uint64_t list_insert(uint64_t *my, uint32_t cnt, uint32_t tau, uint32_t KK, uint64_t key)
+{
+    uint32_t p = cnt < KK ? cnt : KK - 1;
+    if (cnt < KK || key < my[(size_t)p * TC_M]) {
+        while (p > 0 && my[(size_t)(p - 1) * TC_M] > key) {
+            my[(size_t)p * TC_M] = my[(size_t)(p - 1) * TC_M];
+            --p;
+        }
+        my[(size_t)p * TC_M] = key;
+        if (cnt < KK) ++cnt;
+        if (cnt == KK) tau = (uint32_t)(my[(size_t)(KK - 1) * TC_M] >> 32);
+    }
+    return ((uint64_t)cnt << 32) | tau;
+}
+
+// ---- K1: the sweep -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
+               const TcArgs a)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t nkb = a.dim / TC_KB;          // K-blocks per row
+    const uint32_t S = a.stages;
+    const uint32_t KK = a.kk;
+
+    // carve-up: A block | B ring | per-query lists | barriers | tmem ptr
+    uint8_t *a_base = smem;                                         // nkb x (128 x 128 B)
+    uint8_t *b_base = a_base + (size_t)nkb * TC_M * 128;            // S x 16 KB
+    uint64_t *lists = reinterpret_cast<uint64_t *>(b_base + (size_t)S * TC_STAGE_BYTES);  // [KK][128]
+    uint64_t *bars = lists + (size_t)KK * TC_M;
+    uint64_t *full_bar = bars;                       // [S]
+    uint64_t *empty_bar = bars + S;                  // [S]
+    uint64_t *tfull_bar = bars + 2 * S;              // [TC_ACC_STAGES]
+    uint64_t *tempty_bar = tfull_bar + TC_ACC_STAGES;  // [TC_ACC_STAGES]
+    uint64_t *a_bar = tempty_bar + TC_ACC_STAGES;    // [1]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_bar + 1);
+
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < S; ++i) {
+            mbar_init(smem_u32(full_bar + i), 1);
+            mbar_init(smem_u32(empty_bar + i), 1);
+        }
+        for (uint32_t i = 0; i < TC_ACC_STAGES; ++i) {
+            mbar_init(smem_u32(tfull_bar + i), 1);
+            mbar_init(smem_u32(tempty_bar + i), 128);
+        }
+        mbar_init(smem_u32(a_bar), 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&tmap_rows);
+        tma_prefetch_desc(&tmap_q);
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const uint64_t n_tiles = (a.n_rows + TC_N - 1) / TC_N;
+    const uint64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            mbar_arrive_expect_tx(smem_u32(a_bar), nkb * TC_M * 128);
+            for (uint32_t kb = 0; kb < nkb; ++kb)
+                tma_load_2d(smem_u32(a_base + (size_t)kb * TC_M * 128), &tmap_q, smem_u32(a_bar), (int32_t)(kb * TC_KB),
+                            (int32_t)(a.q_tile * TC_M));
+            uint32_t st = 0, ph = 0;
+            for (uint64_t it = 0; it < my_tiles; ++it) {
+                const uint64_t tile = blockIdx.x + it * gridDim.x;
+                for (uint32_t kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(smem_u32(empty_bar + st), ph ^ 1);
+                    mbar_arrive_expect_tx(smem_u32(full_bar + st), TC_STAGE_BYTES);
+                    tma_load_2d(smem_u32(b_base + (size_t)st * TC_STAGE_BYTES), &tmap_rows, smem_u32(full_bar + st),
+                                (int32_t)(kb * TC_KB), (int32_t)(tile * TC_N));
+                    if (++st == S) { st = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(TC_M, TC_N);
+            mbar_wait(smem_u32(a_bar), 0);
+            tc_fence_after();
+            uint32_t st = 0, ph = 0;
+            for (uint64_t it = 0; it < my_tiles; ++it) {
+                const uint32_t acc = (uint32_t)(it % TC_ACC_STAGES);
+                const uint32_t acc_ph = (uint32_t)((it / TC_ACC_STAGES) & 1);
+                mbar_wait(smem_u32(tempty_bar + acc), acc_ph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * TC_N;
+                for (uint32_t kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(smem_u32(full_bar + st), ph);
+                    tc_fence_after();
+                    const uint64_t da = make_sw128_desc(smem_u32(a_base + (size_t)kb * TC_M * 128));
+                    const uint64_t db = make_sw128_desc(smem_u32(b_base + (size_t)st * TC_STAGE_BYTES));
+#pragma unroll
+                    for (uint32_t k = 0; k < TC_KB / 16; ++k)   // advance 32 B (= 16 fp16) inside the swizzle row
+                        umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(smem_u32(empty_bar + st));     // frees the B slot when these MMAs retire
+                    if (++st == S) { st = 0; ph ^= 1; }
+                }
+                umma_commit(smem_u32(tfull_bar + acc));        // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: thread t <-> query t <-> TMEM lane t =====
+        const uint32_t t = threadIdx.x - 128;
+        const bool active = t < a.nq;
+        uint64_t *my = lists + t;                      // entry j at my[j * 128]
+        for (uint32_t j = 0; j < KK; ++j) my[(size_t)j * TC_M] = KEY_SENTINEL;
+        uint32_t cnt = 0;
+        uint32_t tau = 0xFFFFFFFFu;                    // accept key32 <= tau
+        uint32_t *gtau = a.gtau + (size_t)a.q_tile * TC_M + t;
+        const uint32_t lane_base = ((warp & 3) * 32) << 16;
+
+        for (uint64_t it = 0; it < my_tiles; ++it) {
+            const uint64_t tile = blockIdx.x + it * gridDim.x;
+            const uint32_t acc = (uint32_t)(it % TC_ACC_STAGES);
+            const uint32_t acc_ph = (uint32_t)((it / TC_ACC_STAGES) & 1);
+            if (active) {
+                uint32_t g = ld_relaxed_u32(gtau);
+                if (g < tau) tau = g;
+            }
+            mbar_wait(smem_u32(tfull_bar + acc), acc_ph);
+            tc_fence_after();
+            bool changed = false;
+#pragma unroll 1
+            for (uint32_t c = 0; c < TC_N / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + lane_base + acc * TC_N + c * 32, r);
+                tmem_ld_wait();
+                if (active) {
+#pragma unroll
+                    for (uint32_t j = 0; j < 32; ++j) {
+                        const uint32_t key32 = order_key32(neg_dot_to_dist(__uint_as_float(r[j])));
+                        if (key32 <= tau) {
+                            const uint64_t row = tile * TC_N + c * 32 + j;
+                            bool ok = row < a.n_rows;
+                            if (ok && a.deleted) ok = !((__ldg(a.deleted + (row >> 5)) >> (row & 31)) & 1u);
+                            if (ok) {
+                                const uint32_t tau_old = tau;
+                                const uint64_t r2 = list_insert(my, cnt, tau, KK, make_key(key32, (uint32_t)row));
+                                cnt = (uint32_t)(r2 >> 32);
+                                tau = (uint32_t)r2;
+                                changed |= tau != tau_old;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(smem_u32(tempty_bar + acc));       // 128 arrivals release the accumulator
+            if (active && changed) atomicMin(gtau, tau);    // share the threshold GPU-wide
+        }
+
+        // publish the survivors: everything at or above the best threshold known GPU-wide
+        if (active) {
+            uint32_t g = ld_relaxed_u32(gtau);
+            if (g < tau) tau = g;
+            const uint32_t qg = a.q_tile * TC_M + t;
+            for (uint32_t j = 0; j < cnt; ++j) {
+                const uint64_t key = my[(size_t)j * TC_M];
+                if ((uint32_t)(key >> 32) > tau) break;
+                const uint32_t slot = atomicAdd(a.cand_count + qg, 1u);
+                if (slot < a.cand_cap) a.cand[(size_t)qg * a.cand_cap + slot] = key;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---- query preparation: fp16 rounding + the rigorous error bound -------------------------------
+// qh[q] = fp16(q) (zero rows for q >= b up to the 128-padded count); err[q] = |q - fp16(q)|_2,
+// qnorm[q] = |q|_2 (both rounded up a little by computing in f64).
+__global__ void prep_queries_kernel(const float *__restrict__ q, uint32_t b, uint32_t b_pad, uint32_t dim,
+                                    __half *__restrict__ qh, float *__restrict__ err, float *__restrict__ qnorm,
+                                    uint32_t *__restrict__ gtau, uint32_t *__restrict__ cand_count,
+                                    uint32_t *__restrict__ flags)
+{
+    const uint32_t row = blockIdx.x;
+    __shared__ double s_e[32], s_n[32];
+    double e = 0.0, n2 = 0.0;
+    for (uint32_t j = threadIdx.x; j < dim; j += blockDim.x) {
+        float v = row < b ? q[(size_t)row * dim + j] : 0.0f;
+        __half h = __float2half_rn(v);
+        qh[(size_t)row * dim + j] = h;
+        double d = (double)v - (double)__half2float(h);
+        e += d * d;
+        n2 += (double)v * (double)v;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        e += __shfl_down_sync(0xFFFFFFFFu, e, o);
+        n2 += __shfl_down_sync(0xFFFFFFFFu, n2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_e[threadIdx.x >> 5] = e;
+        s_n[threadIdx.x >> 5] = n2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double te = 0, tn = 0;
+        for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) {
+            te += s_e[w];
+            tn += s_n[w];
+        }
+        if (row < b) {
+            err[row] = (float)(sqrt(te) * 1.000001);
+            qnorm[row] = (float)(sqrt(tn) * 1.000001);
+        }
+        gtau[row] = 0xFFFFFFFFu;
+        cand_count[row] = 0;
+        if (row < b) flags[row] = 0;
+        (void)b_pad;
+    }
+}
+
+// ---- K2: exact re-score + certification ---------------------------------------------------------
+// exact -dot in the reference's order for one (query,row): one thread, sequential chain
+template <int ORDER>
+SG_DEVICE_INLINE float exact_dot(const float *__restrict__ q, const __half *__restrict__ row, uint32_t dim)
+{
+    if constexpr (ORDER == SG_ORDER_SCALAR) {
+        float sum = 0.0f;
+        for (uint32_t i = 0; i < dim; i += 4) {
+            float p0 = __fmul_rn(q[i], __half2float(row[i])), p1 = __fmul_rn(q[i + 1], __half2float(row[i + 1]));
+            float p2 = __fmul_rn(q[i + 2], __half2float(row[i + 2])), p3 = __fmul_rn(q[i + 3], __half2float(row[i + 3]));
+            sum = __fadd_rn(sum, __fadd_rn(__fadd_rn(__fadd_rn(p0, p1), p2), p3));
+        }
+        return sum;
+    } else {
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (uint32_t i = 0; i < dim; i += 8)
+#pragma unroll
+            for (int t = 0; t < 8; ++t) acc[t] = __fmaf_rn(q[i + t], __half2float(row[i + t]), acc[t]);
+        float r = __fadd_rn(acc[0], acc[1]);
+#pragma unroll
+        for (int t = 2; t < 8; ++t) r = __fadd_rn(r, acc[t]);
+        return r;
+    }
+}
+
+// one CTA (256 threads) per query
+__global__ void __launch_bounds__(256)
+finalize_tc_kernel(const FinalizeArgs f)
+{
+    __shared__ uint64_t keys[TC_CAND_CAP];      // approx keys, then exact keys
+    __shared__ float q_s[2048];
+    __shared__ uint32_t s_flag;
+    const uint32_t q = blockIdx.x;
+    uint32_t n = f.cand_count[q];
+    const bool overflow = n > f.cand_cap;
+    if (overflow) n = f.cand_cap;
+    for (uint32_t i = threadIdx.x; i < f.dim; i += blockDim.x) q_s[i] = f.queries[(size_t)q * f.dim + i];
+    const uint32_t M = next_pow2(n < 2 ? 2 : n);
+    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x)
+        keys[i] = i < n ? f.cand[(size_t)q * f.cand_cap + i] : KEY_SENTINEL;
+    if (threadIdx.x == 0) s_flag = overflow ? 1u : 0u;
+    __syncthreads();
+    block_bitonic_sort(keys, M);                 // ascending approx key: best approximate first
+    const uint32_t kk = n < f.kk ? n : f.kk;     // the global top-KK by approximate score
+    // weakest approximate similarity that was kept == bound on everything that was dropped
+    const bool dropped_any = (f.n_live > kk);
+    const float weakest_approx_sim = kk ? -key32_to_dist((uint32_t)(keys[kk - 1] >> 32)) : 0.0f;
+    __syncthreads();
+    // exact re-score: one thread per candidate (sequential chain, like the reference)
+    uint64_t exact_key = KEY_SENTINEL;
+    if (threadIdx.x < kk) {
+        const uint32_t row = (uint32_t)(keys[threadIdx.x] & 0xFFFFFFFFu);
+        const __half *rp = reinterpret_cast<const __half *>(f.rows) + (size_t)row * f.dim;
+        float dot = f.order == SG_ORDER_AVX2 ? exact_dot<SG_ORDER_AVX2>(q_s, rp, f.dim)
+                                             : exact_dot<SG_ORDER_SCALAR>(q_s, rp, f.dim);
+        exact_key = make_key(order_key32(neg_dot_to_dist(dot)), row);
+    }
+    __syncthreads();
+    const uint32_t M2 = next_pow2(kk < 2 ? 2 : kk);
+    if (threadIdx.x < M2) keys[threadIdx.x] = exact_key;
+    __syncthreads();
+    block_bitonic_sort(keys, M2);
+    const uint32_t out_n = kk < f.k ? kk : f.k;
+    // certification: every dropped row has approx sim <= weakest_approx_sim, hence exact sim <=
+    // weakest_approx_sim + E; it cannot enter (or tie into) the top k if kth_exact_sim is larger.
+    if (threadIdx.x == 0 && dropped_any) {
+        bool ok = false;
+        if (out_n == f.k) {
+            const float kth_exact_sim = -key32_to_dist((uint32_t)(keys[f.k - 1] >> 32));
+            const float R = *f.max_row_norm;
+            const float E = f.err[q] * R + f.c_acc * f.qnorm[q] * R;
+            ok = kth_exact_sim > weakest_approx_sim + E;     // NaN compares false -> flagged
+        }
+        if (!ok) s_flag = 1u;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < f.k; i += blockDim.x) {
+        const bool valid = i < out_n;
+        const uint64_t key = valid ? keys[i] : KEY_SENTINEL;
+        f.ids_out[(size_t)q * f.k + i] = valid ? (uint32_t)(key & 0xFFFFFFFFu) + f.id_base : 0xFFFFFFFFu;
+        f.dist_out[(size_t)q * f.k + i] = valid ? key32_to_dist((uint32_t)(key >> 32)) : __uint_as_float(0x7F800000u);
+    }
+    if (threadIdx.x == 0) {
+        f.counts_out[q] = out_n;
+        f.flags[q] = s_flag;
+        if (s_flag) atomicAdd(f.n_flagged, 1u);
+    }
+}
+
+}  // namespace
+
+size_t tc_smem_bytes(uint32_t dim, uint32_t stages, uint32_t kk)
+{
+    size_t s = (size_t)(dim / TC_KB) * TC_M * 128;          // A
+    s += (size_t)stages * TC_STAGE_BYTES;                    // B ring
+    s += (size_t)kk * TC_M * 8;                              // lists
+    s += (size_t)(2 * stages + 2 * TC_ACC_STAGES + 1) * 8 + 16;
+    return s;
+}
+
+cudaError_t launch_prep_queries(const float *d_q, uint32_t b, uint32_t b_pad, uint32_t dim, __half *d_qh, float *d_err,
+                                float *d_qnorm, uint32_t *d_gtau, uint32_t *d_cand_count, uint32_t *d_flags,
+                                cudaStream_t st)
+{
+    prep_queries_kernel<<<b_pad, 128, 0, st>>>(d_q, b, b_pad, dim, d_qh, d_err, d_qnorm, d_gtau, d_cand_count, d_flags);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan_tc(const CUtensorMap &tmap_rows, const CUtensorMap &tmap_q, const TcArgs &a, uint32_t grid,
+                           size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    scan_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmap_rows, tmap_q, a);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_finalize_tc(const FinalizeArgs &f, uint32_t b, cudaStream_t st)
+{
+    finalize_tc_kernel<<<b, 256, 0, st>>>(f);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace sg

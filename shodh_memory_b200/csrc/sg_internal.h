@@ -21,6 +21,44 @@ size_t scan_smem_bytes(uint32_t W, uint32_t ring, uint32_t qb, uint32_t dim, uin
 cudaError_t launch_scan_exact(const CUtensorMap &tmap, const ScanArgs &a, int qb, bool f16, int order,
                               uint32_t grid, uint32_t W, size_t smem, cudaStream_t st);
 
+// ---- scan_tc.cu (tensor-core sweep) ----
+constexpr uint32_t TC_CAND_CAP = 512;  // published candidates per query (overflow -> exact fallback)
+struct TcArgs {
+    uint64_t n_rows;
+    uint32_t dim;
+    uint32_t nq;              // live queries in this 128-query tile
+    uint32_t q_tile;          // which 128-query tile
+    uint32_t stages;          // B ring depth
+    uint32_t kk;              // candidates kept per query (k + slack)
+    const uint32_t *deleted;
+    uint32_t *gtau;           // [b_pad] GPU-wide threshold per query (order key of the kk-th best distance)
+    uint64_t *cand;           // [b_pad][cand_cap] published candidate keys
+    uint32_t *cand_count;     // [b_pad]
+    uint32_t cand_cap;
+};
+struct FinalizeArgs {
+    const float *queries;     // [b][dim] f32 (the exact operands)
+    const void *rows;         // fp16 corpus
+    uint32_t dim, k, kk, order, id_base;
+    uint64_t n_live;
+    const uint64_t *cand;
+    const uint32_t *cand_count;
+    uint32_t cand_cap;
+    const float *err, *qnorm; // per-query |q - fp16(q)|, |q|
+    const float *max_row_norm; // device scalar: upper bound on |row|_2 over the store
+    float c_acc;              // accumulation-error coefficient of the bound
+    uint32_t *ids_out; float *dist_out; uint32_t *counts_out;
+    uint32_t *flags;          // [b] 1 = could not be certified
+    uint32_t *n_flagged;      // device counter
+};
+size_t tc_smem_bytes(uint32_t dim, uint32_t stages, uint32_t kk);
+cudaError_t launch_prep_queries(const float *d_q, uint32_t b, uint32_t b_pad, uint32_t dim, __half *d_qh, float *d_err,
+                                float *d_qnorm, uint32_t *d_gtau, uint32_t *d_cand_count, uint32_t *d_flags,
+                                cudaStream_t st);
+cudaError_t launch_scan_tc(const CUtensorMap &tmap_rows, const CUtensorMap &tmap_q, const TcArgs &a, uint32_t grid,
+                           size_t smem, cudaStream_t st);
+cudaError_t launch_finalize_tc(const FinalizeArgs &f, uint32_t b, cudaStream_t st);
+
 // ---- select.cu ----
 // lists [b][n_lists][k] u64 keys (sentinel padded) -> top-k per query.  d_scratch (may be null) holds
 // [b][merge_groups(n_lists,k)][k] keys and enables the two-level merge for large n_lists*k.
@@ -39,6 +77,9 @@ cudaError_t launch_f16_to_f32(const __half *d_src, float *d_dst, uint64_t n_elem
 cudaError_t launch_synth_rows(void *d_rows, bool f16, uint64_t seed, uint64_t first_row, uint64_t n,
                               uint32_t dim, cudaStream_t st);
 cudaError_t launch_set_bit(uint32_t *d_bitmap, uint32_t id, uint32_t *d_was_set, cudaStream_t st);
+// max over rows of |row|_2 (rounded up), folded into *d_max_norm (a float, initialised to 0)
+cudaError_t launch_max_row_norm(const void *d_rows, bool f16, uint64_t n, uint32_t dim, float *d_max_norm,
+                                cudaStream_t st);
 
 // ---- fuse.cu ----
 struct FuseDev {

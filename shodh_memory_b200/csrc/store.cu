@@ -120,6 +120,16 @@ struct sg_store {
     void *h_pinned = nullptr; size_t pinned_cap = 0;
     float *d_stage = nullptr; size_t stage_cap = 0;     // floats, append staging
 
+    // tensor-core path scratch
+    float *d_max_norm = nullptr;                           // device scalar: bound on |row|_2 over the store
+    __half *d_qh = nullptr; size_t qh_cap = 0;             // fp16 queries, 128-row padded
+    float *d_qerr = nullptr; size_t qmeta_cap = 0;         // [b_pad] |q - fp16(q)|
+    float *d_qnorm = nullptr;                              // [b_pad]
+    uint32_t *d_gtau = nullptr, *d_cand_count = nullptr, *d_flags = nullptr, *d_nflag = nullptr;
+    uint64_t *d_cand = nullptr; size_t cand_cap_q = 0;     // [b_pad][TC_CAND_CAP]
+    uint32_t *h_flags = nullptr; size_t hflags_cap = 0;    // pinned: [0] = n_flagged, [1..] flags
+    uint64_t tc_searches = 0, tc_flagged = 0;              // statistics (sg_store_tc_stats)
+
     bool profiling = false;
     std::vector<cudaEvent_t> ev;  // pairs: ev[2i] before, ev[2i+1] after the sweep launches of search i
     uint32_t ev_count = 0;        // searches recorded since the last read/reset
@@ -263,16 +273,10 @@ int plan_scan(const sg_store *s, uint32_t k, uint32_t qb, ScanPlan *p)
     return SG_ERR_UNSUPPORTED;
 }
 
-// all pointers are device pointers; runs asynchronously on st
-int search_device_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint32_t *d_ids, float *d_dist,
-                         uint32_t *d_counts, cudaStream_t st)
+// exact path A.  all pointers are device pointers; runs asynchronously on st
+int search_exact_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint32_t *d_ids, float *d_dist,
+                        uint32_t *d_counts, cudaStream_t st, bool record)
 {
-    if (b == 0) return SG_OK;
-    if (k == 0 || k > 1024) {
-        set_error("k=%u outside the supported range 1..1024", k);
-        return k == 0 ? SG_ERR_INVALID : SG_ERR_UNSUPPORTED;
-    }
-    s->last_scan_launches = 0;
     if (s->n == 0) {  // VamanaIndex::search on an empty index: Ok(vec![]) (vamana.rs:766-768)
         SG_CUDA_TRY(launch_merge_keys(nullptr, b, 0, k, s->id_base, nullptr, d_ids, d_dist, d_counts, st));
         return SG_OK;
@@ -292,7 +296,7 @@ int search_device_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, 
     rc = encode_corpus_tmap(&tmap, s->d_rows, s->dtype == SG_DTYPE_F16, s->dim, s->n, 32);
     if (rc != SG_OK) return rc;
 
-    const bool prof = s->profiling && 2 * (size_t)(s->ev_count + 1) <= s->ev.size();
+    const bool prof = record && s->profiling && 2 * (size_t)(s->ev_count + 1) <= s->ev.size();
     if (prof) SG_CUDA_TRY(cudaEventRecord(s->ev[2 * s->ev_count], st));
     uint32_t done = 0;
     while (done < b) {
@@ -326,6 +330,147 @@ int search_device_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, 
     SG_CUDA_TRY(launch_merge_keys(s->d_lists, b, L, k, s->id_base, groups > 1 ? s->d_lists2 : nullptr, d_ids, d_dist,
                                   d_counts, st));
     return SG_OK;
+}
+
+
+// tensor-core path B: approximate sweep + exact re-score + certification; uncertified queries are
+// re-run on path A.  Returns SG_ERR_UNSUPPORTED (without side effects) if the shape does not fit.
+bool tc_eligible(const sg_store *s, uint32_t b, uint32_t k, uint32_t *kk_out, uint32_t *stages_out)
+{
+    if (s->dtype != SG_DTYPE_F16 || s->dim % 64 != 0) return false;
+    if (env_u32("SG_TC_DISABLE", 0)) return false;
+    if (b < (uint32_t)env_u32("SG_TC_MIN_B", 5)) return false;
+    if (k > 24 || s->n < 4096) return false;
+    const uint32_t kk = 32;                       // k + slack (>= 8 spare candidates)
+    for (uint32_t stages = 8; stages >= 3; --stages) {
+        if (tc_smem_bytes(s->dim, stages, kk) <= 227 * 1024) {
+            *kk_out = kk;
+            *stages_out = stages;
+            return true;
+        }
+    }
+    return false;
+}
+
+int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint32_t kk, uint32_t stages,
+                     uint32_t *d_ids, float *d_dist, uint32_t *d_counts, cudaStream_t st)
+{
+    const uint32_t b_pad = (b + 127) / 128 * 128;
+    int rc;
+    if ((rc = grow(s->d_qh, s->qh_cap, (size_t)b_pad * s->dim)) != SG_OK) return rc;
+    if (b_pad > s->qmeta_cap) {
+        size_t c[5] = {s->qmeta_cap, s->qmeta_cap, s->qmeta_cap, s->qmeta_cap, s->qmeta_cap};
+        if ((rc = grow(s->d_qerr, c[0], b_pad)) != SG_OK) return rc;
+        if ((rc = grow(s->d_qnorm, c[1], b_pad)) != SG_OK) return rc;
+        if ((rc = grow(s->d_gtau, c[2], b_pad)) != SG_OK) return rc;
+        if ((rc = grow(s->d_cand_count, c[3], b_pad)) != SG_OK) return rc;
+        if ((rc = grow(s->d_flags, c[4], b_pad)) != SG_OK) return rc;
+        s->qmeta_cap = c[0];
+    }
+    if ((rc = grow(s->d_cand, s->cand_cap_q, (size_t)b_pad * TC_CAND_CAP)) != SG_OK) return rc;
+    if ((size_t)b + 1 > s->hflags_cap) {
+        if (s->h_flags) cudaFreeHost(s->h_flags);
+        s->h_flags = nullptr;
+        s->hflags_cap = 0;
+        SG_CUDA_TRY(cudaHostAlloc(&s->h_flags, ((size_t)b_pad + 1) * 4, cudaHostAllocDefault));
+        s->hflags_cap = (size_t)b_pad + 1;
+    }
+    CUtensorMap tmap_rows, tmap_q;
+    if ((rc = encode_corpus_tmap(&tmap_rows, s->d_rows, true, s->dim, s->n, 128)) != SG_OK) return rc;
+    if ((rc = encode_corpus_tmap(&tmap_q, s->d_qh, true, s->dim, b_pad, 128)) != SG_OK) return rc;
+
+    SG_CUDA_TRY(cudaMemsetAsync(s->d_nflag, 0, 4, st));
+    SG_CUDA_TRY(launch_prep_queries(d_q, b, b_pad, s->dim, s->d_qh, s->d_qerr, s->d_qnorm, s->d_gtau, s->d_cand_count,
+                                    s->d_flags, st));
+    const uint64_t n_tiles = (s->n + 127) / 128;
+    const uint32_t grid = (uint32_t)(n_tiles < (uint64_t)s->sm_count ? n_tiles : s->sm_count);
+    const size_t smem = tc_smem_bytes(s->dim, stages, kk);
+    const bool prof = s->profiling && 2 * (size_t)(s->ev_count + 1) <= s->ev.size();
+    if (prof) SG_CUDA_TRY(cudaEventRecord(s->ev[2 * s->ev_count], st));
+    for (uint32_t qt = 0; qt < b_pad / 128; ++qt) {
+        TcArgs a;
+        a.n_rows = s->n;
+        a.dim = s->dim;
+        a.nq = b - qt * 128 < 128 ? b - qt * 128 : 128;
+        a.q_tile = qt;
+        a.stages = stages;
+        a.kk = kk;
+        a.deleted = s->n_deleted ? s->d_deleted : nullptr;
+        a.gtau = s->d_gtau;
+        a.cand = s->d_cand;
+        a.cand_count = s->d_cand_count;
+        a.cand_cap = TC_CAND_CAP;
+        cudaError_t e = launch_scan_tc(tmap_rows, tmap_q, a, grid, smem, st);
+        if (e != cudaSuccess) {
+            set_error("tensor-core scan launch failed: %s", cudaGetErrorString(e));
+            return SG_ERR_CUDA;
+        }
+        ++s->last_scan_launches;
+    }
+    if (prof) {
+        SG_CUDA_TRY(cudaEventRecord(s->ev[2 * s->ev_count + 1], st));
+        ++s->ev_count;
+    }
+    FinalizeArgs f;
+    f.queries = d_q;
+    f.rows = s->d_rows;
+    f.dim = s->dim;
+    f.k = k;
+    f.kk = kk;
+    f.order = (uint32_t)s->order;
+    f.id_base = s->id_base;
+    f.n_live = s->n - s->n_deleted;
+    f.cand = s->d_cand;
+    f.cand_count = s->d_cand_count;
+    f.cand_cap = TC_CAND_CAP;
+    f.err = s->d_qerr;
+    f.qnorm = s->d_qnorm;
+    f.max_row_norm = s->d_max_norm;
+    f.c_acc = 1.0e-4f;
+    f.ids_out = d_ids;
+    f.dist_out = d_dist;
+    f.counts_out = d_counts;
+    f.flags = s->d_flags;
+    f.n_flagged = s->d_nflag;
+    SG_CUDA_TRY(launch_finalize_tc(f, b, st));
+
+    // certification outcome: the (rare) flagged queries are re-run on the exact path.  This is the
+    // one host round trip of the batched path (4 bytes).
+    SG_CUDA_TRY(cudaMemcpyAsync(s->h_flags, s->d_nflag, 4, cudaMemcpyDeviceToHost, st));
+    SG_CUDA_TRY(cudaStreamSynchronize(st));
+    s->tc_searches += b;
+    const uint32_t n_flagged = s->h_flags[0];
+    if (n_flagged) {
+        s->tc_flagged += n_flagged;
+        SG_CUDA_TRY(cudaMemcpyAsync(s->h_flags + 1, s->d_flags, (size_t)b * 4, cudaMemcpyDeviceToHost, st));
+        SG_CUDA_TRY(cudaStreamSynchronize(st));
+        uint32_t i = 0;
+        while (i < b) {
+            if (!s->h_flags[1 + i]) { ++i; continue; }
+            uint32_t j = i;
+            while (j < b && j - i < 4 && s->h_flags[1 + j]) ++j;   // a run of up to 4 flagged neighbours: one sweep
+            rc = search_exact_locked(s, d_q + (size_t)i * s->dim, j - i, k, d_ids + (size_t)i * k,
+                                     d_dist + (size_t)i * k, d_counts + i, st, false);
+            if (rc != SG_OK) return rc;
+            i = j;
+        }
+    }
+    return SG_OK;
+}
+
+// all pointers are device pointers
+int search_device_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint32_t *d_ids, float *d_dist,
+                         uint32_t *d_counts, cudaStream_t st)
+{
+    if (b == 0) return SG_OK;
+    if (k == 0 || k > 1024) {
+        set_error("k=%u outside the supported range 1..1024", k);
+        return k == 0 ? SG_ERR_INVALID : SG_ERR_UNSUPPORTED;
+    }
+    s->last_scan_launches = 0;
+    uint32_t kk = 0, stages = 0;
+    if (tc_eligible(s, b, k, &kk, &stages)) return search_tc_locked(s, d_q, b, k, kk, stages, d_ids, d_dist, d_counts, st);
+    return search_exact_locked(s, d_q, b, k, d_ids, d_dist, d_counts, st, true);
 }
 
 }  // namespace
@@ -383,6 +528,9 @@ int sg_store_create(sg_store **out, int device, uint32_t dim, int dtype, int met
     s->esize = dtype == SG_DTYPE_F16 ? 2 : 4;
     s->metric = metric;
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_max_norm, sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_nflag, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(s->d_max_norm, 0, sizeof(float));
     if (e != cudaSuccess) {
         set_error("stream/event creation failed: %s", cudaGetErrorString(e));
         delete s;
@@ -406,6 +554,16 @@ void sg_store_destroy(sg_store *s)
     cudaFree(s->d_dist);
     cudaFree(s->d_counts);
     cudaFree(s->d_stage);
+    cudaFree(s->d_max_norm);
+    cudaFree(s->d_qh);
+    cudaFree(s->d_qerr);
+    cudaFree(s->d_qnorm);
+    cudaFree(s->d_gtau);
+    cudaFree(s->d_cand_count);
+    cudaFree(s->d_flags);
+    cudaFree(s->d_nflag);
+    cudaFree(s->d_cand);
+    if (s->h_flags) cudaFreeHost(s->h_flags);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -448,6 +606,7 @@ int sg_store_append(sg_store *s, const float *rows, uint64_t n, uint32_t *first_
         } else {
             SG_CUDA_TRY(cudaMemcpyAsync(dst, s->h_pinned, elems * 4, cudaMemcpyHostToDevice, s->stream));
         }
+        SG_CUDA_TRY(launch_max_row_norm(dst, s->dtype == SG_DTYPE_F16, cnt, s->dim, s->d_max_norm, s->stream));
         SG_CUDA_TRY(cudaStreamSynchronize(s->stream));
         done += cnt;
     }
@@ -464,6 +623,7 @@ int sg_store_append_synthetic(sg_store *s, uint64_t seed, uint64_t first_row, ui
     if (rc != SG_OK) return rc;
     uint8_t *dst = static_cast<uint8_t *>(s->d_rows) + s->n * (size_t)s->dim * s->esize;
     SG_CUDA_TRY(launch_synth_rows(dst, s->dtype == SG_DTYPE_F16, seed, first_row, n, s->dim, s->stream));
+    SG_CUDA_TRY(launch_max_row_norm(dst, s->dtype == SG_DTYPE_F16, n, s->dim, s->d_max_norm, s->stream));
     SG_CUDA_TRY(cudaStreamSynchronize(s->stream));
     s->n += n;
     return SG_OK;
@@ -624,6 +784,15 @@ int sg_store_last_scan_ms(sg_store *s, float *ms_out, uint32_t *launches_out)
     SG_CUDA_TRY(cudaEventElapsedTime(ms_out, s->ev[2 * i], s->ev[2 * i + 1]));
     if (launches_out) *launches_out = s->last_scan_launches;
     s->ev_count = 0;
+    return SG_OK;
+}
+
+int sg_store_tc_stats(sg_store *s, uint64_t *queries_out, uint64_t *flagged_out)
+{
+    if (!s) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    if (queries_out) *queries_out = s->tc_searches;
+    if (flagged_out) *flagged_out = s->tc_flagged;
     return SG_OK;
 }
 

@@ -92,7 +92,37 @@ synth_rows_kernel(void *rows, uint64_t seed, uint64_t first_row, uint64_t n, uin
     }
 }
 
+// one warp per row; the result only feeds an error BOUND, so it is rounded up, never down
+__global__ void max_row_norm_kernel(const void *rows, bool f16, uint64_t n, uint32_t dim, float *out)
+{
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    float ss = 0.0f;
+    for (uint32_t j = lane; j < dim; j += 32) {
+        float x = f16 ? __half2float(reinterpret_cast<const __half *>(rows)[warp * dim + j])
+                      : reinterpret_cast<const float *>(rows)[warp * dim + j];
+        ss = fmaf(x, x, ss);
+    }
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_down_sync(0xFFFFFFFFu, ss, o);
+    if (lane == 0) {
+        float nrm = sqrtf(ss) * 1.0001f;
+        if (!(nrm == nrm)) nrm = __uint_as_float(0x7F800000u);   // NaN rows poison the bound -> +inf
+        atomicMax(reinterpret_cast<unsigned int *>(out), __float_as_uint(nrm));  // non-negative floats order as uints
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_max_row_norm(const void *d_rows, bool f16, uint64_t n, uint32_t dim, float *d_max_norm,
+                                cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    const uint64_t threads = n * 32;
+    max_row_norm_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, st>>>(d_rows, f16, n, dim, d_max_norm);
+    count_launch();
+    return cudaGetLastError();
+}
 
 cudaError_t launch_f32_to_f16(const float *d_src, __half *d_dst, uint64_t n_elems, cudaStream_t st)
 {

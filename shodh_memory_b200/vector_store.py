@@ -132,6 +132,12 @@ class GpuVectorStore:
     def set_profiling(self, on: bool) -> None:
         capi.check(capi.lib().sg_store_set_profiling(self._h, int(on)))
 
+    def tc_stats(self):
+        """-> (queries served by the tensor-core path, queries that needed the exact re-run)"""
+        a, b = C.c_uint64(), C.c_uint64()
+        capi.check(capi.lib().sg_store_tc_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def profile_read(self, cap: int = 4096):
         """-> (per-search scan ms array, sweep launches per search)"""
         ms = np.zeros(cap, np.float32)
