@@ -259,17 +259,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
             if (active && changed) atomicMin(gtau, tau);    // share the threshold GPU-wide
         }
 
-        // publish the survivors: everything at or above the best threshold known GPU-wide
+        // publish this CTA's sorted list for the query (KEY_SENTINEL padded); K2 merges the lists
         if (active) {
-            uint32_t g = ld_relaxed_u32(gtau);
-            if (g < tau) tau = g;
             const uint32_t qg = a.q_tile * TC_M + t;
-            for (uint32_t j = 0; j < cnt; ++j) {
-                const uint64_t key = my[(size_t)j * TC_M];
-                if ((uint32_t)(key >> 32) > tau) break;
-                const uint32_t slot = atomicAdd(a.cand_count + qg, 1u);
-                if (slot < a.cand_cap) a.cand[(size_t)qg * a.cand_cap + slot] = key;
-            }
+            uint64_t *out = a.lists + ((size_t)qg * gridDim.x + blockIdx.x) * KK;
+            for (uint32_t j = 0; j < KK; ++j) out[j] = my[(size_t)j * TC_M];
         }
     }
 
@@ -286,8 +280,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
 // qnorm[q] = |q|_2 (both rounded up a little by computing in f64).
 __global__ void prep_queries_kernel(const float *__restrict__ q, uint32_t b, uint32_t b_pad, uint32_t dim,
                                     __half *__restrict__ qh, float *__restrict__ err, float *__restrict__ qnorm,
-                                    uint32_t *__restrict__ gtau, uint32_t *__restrict__ cand_count,
-                                    uint32_t *__restrict__ flags)
+                                    uint32_t *__restrict__ gtau, uint32_t *__restrict__ flags)
 {
     const uint32_t row = blockIdx.x;
     __shared__ double s_e[32], s_n[32];
@@ -320,7 +313,6 @@ __global__ void prep_queries_kernel(const float *__restrict__ q, uint32_t b, uin
             qnorm[row] = (float)(sqrt(tn) * 1.000001);
         }
         gtau[row] = 0xFFFFFFFFu;
-        cand_count[row] = 0;
         if (row < b) flags[row] = 0;
         (void)b_pad;
     }
@@ -355,18 +347,41 @@ SG_DEVICE_INLINE float exact_dot(const float *__restrict__ q, const __half *__re
 __global__ void __launch_bounds__(256)
 finalize_tc_kernel(const FinalizeArgs f)
 {
-    __shared__ uint64_t keys[TC_CAND_CAP];      // approx keys, then exact keys
+    __shared__ uint64_t keys[TC_CAND_CAP];      // heads, then surviving approx keys, then exact keys
     __shared__ float q_s[2048];
-    __shared__ uint32_t s_flag;
+    __shared__ uint32_t s_flag, s_n;
     const uint32_t q = blockIdx.x;
-    uint32_t n = f.cand_count[q];
-    const bool overflow = n > f.cand_cap;
-    if (overflow) n = f.cand_cap;
+    const uint32_t L = f.n_lists;
+    const uint64_t *ql = f.lists + (size_t)q * L * f.kk;
     for (uint32_t i = threadIdx.x; i < f.dim; i += blockDim.x) q_s[i] = f.queries[(size_t)q * f.dim + i];
+    // (1) threshold from the list heads: at least kk candidates (kk distinct heads) have key <= T0,
+    //     so every member of the global top-kk has key <= T0.
+    const uint32_t MH = next_pow2(L < 2 ? 2 : L);
+    for (uint32_t i = threadIdx.x; i < MH; i += blockDim.x) keys[i] = i < L ? ql[(size_t)i * f.kk] : KEY_SENTINEL;
+    if (threadIdx.x == 0) {
+        s_flag = 0;
+        s_n = 0;
+    }
+    __syncthreads();
+    block_bitonic_sort(keys, MH);
+    const uint64_t T0 = L >= f.kk ? keys[f.kk - 1] : KEY_SENTINEL;
+    __syncthreads();
+    // (2) gather every entry with key <= T0 (lists are sorted: a prefix of each)
+    for (uint32_t i = threadIdx.x; i < L; i += blockDim.x) {
+        for (uint32_t j = 0; j < f.kk; ++j) {
+            const uint64_t key = ql[(size_t)i * f.kk + j];
+            if (key == KEY_SENTINEL || key > T0) break;
+            const uint32_t slot = atomicAdd(&s_n, 1u);
+            if (slot < TC_CAND_CAP) keys[slot] = key;
+        }
+    }
+    __syncthreads();
+    uint32_t n = s_n;
+    const bool overflow = n > TC_CAND_CAP;
+    if (overflow) n = TC_CAND_CAP;
     const uint32_t M = next_pow2(n < 2 ? 2 : n);
-    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x)
-        keys[i] = i < n ? f.cand[(size_t)q * f.cand_cap + i] : KEY_SENTINEL;
-    if (threadIdx.x == 0) s_flag = overflow ? 1u : 0u;
+    for (uint32_t i = n + threadIdx.x; i < M; i += blockDim.x) keys[i] = KEY_SENTINEL;
+    if (threadIdx.x == 0 && overflow) s_flag = 1u;
     __syncthreads();
     block_bitonic_sort(keys, M);                 // ascending approx key: best approximate first
     const uint32_t kk = n < f.kk ? n : f.kk;     // the global top-KK by approximate score
@@ -427,10 +442,9 @@ size_t tc_smem_bytes(uint32_t dim, uint32_t stages, uint32_t kk)
 }
 
 cudaError_t launch_prep_queries(const float *d_q, uint32_t b, uint32_t b_pad, uint32_t dim, __half *d_qh, float *d_err,
-                                float *d_qnorm, uint32_t *d_gtau, uint32_t *d_cand_count, uint32_t *d_flags,
-                                cudaStream_t st)
+                                float *d_qnorm, uint32_t *d_gtau, uint32_t *d_flags, cudaStream_t st)
 {
-    prep_queries_kernel<<<b_pad, 128, 0, st>>>(d_q, b, b_pad, dim, d_qh, d_err, d_qnorm, d_gtau, d_cand_count, d_flags);
+    prep_queries_kernel<<<b_pad, 128, 0, st>>>(d_q, b, b_pad, dim, d_qh, d_err, d_qnorm, d_gtau, d_flags);
     count_launch();
     return cudaGetLastError();
 }

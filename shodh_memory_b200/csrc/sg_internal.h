@@ -22,7 +22,7 @@ cudaError_t launch_scan_exact(const CUtensorMap &tmap, const ScanArgs &a, int qb
                               uint32_t grid, uint32_t W, size_t smem, cudaStream_t st);
 
 // ---- scan_tc.cu (tensor-core sweep) ----
-constexpr uint32_t TC_CAND_CAP = 512;  // published candidates per query (overflow -> exact fallback)
+constexpr uint32_t TC_CAND_CAP = 1024;  // candidates at or above the heads threshold (overflow -> exact re-run)
 struct TcArgs {
     uint64_t n_rows;
     uint32_t dim;
@@ -31,19 +31,16 @@ struct TcArgs {
     uint32_t stages;          // B ring depth
     uint32_t kk;              // candidates kept per query (k + slack)
     const uint32_t *deleted;
-    uint32_t *gtau;           // [b_pad] GPU-wide threshold per query (order key of the kk-th best distance)
-    uint64_t *cand;           // [b_pad][cand_cap] published candidate keys
-    uint32_t *cand_count;     // [b_pad]
-    uint32_t cand_cap;
+    uint32_t *gtau;           // [b_pad] shared threshold per query (best CTA-local kk-th distance key so far)
+    uint64_t *lists;          // [b_pad][gridDim.x][kk] each CTA's sorted approximate candidates
 };
 struct FinalizeArgs {
     const float *queries;     // [b][dim] f32 (the exact operands)
     const void *rows;         // fp16 corpus
     uint32_t dim, k, kk, order, id_base;
     uint64_t n_live;
-    const uint64_t *cand;
-    const uint32_t *cand_count;
-    uint32_t cand_cap;
+    const uint64_t *lists;    // [b][n_lists][kk]
+    uint32_t n_lists;
     const float *err, *qnorm; // per-query |q - fp16(q)|, |q|
     const float *max_row_norm; // device scalar: upper bound on |row|_2 over the store
     float c_acc;              // accumulation-error coefficient of the bound
@@ -53,8 +50,7 @@ struct FinalizeArgs {
 };
 size_t tc_smem_bytes(uint32_t dim, uint32_t stages, uint32_t kk);
 cudaError_t launch_prep_queries(const float *d_q, uint32_t b, uint32_t b_pad, uint32_t dim, __half *d_qh, float *d_err,
-                                float *d_qnorm, uint32_t *d_gtau, uint32_t *d_cand_count, uint32_t *d_flags,
-                                cudaStream_t st);
+                                float *d_qnorm, uint32_t *d_gtau, uint32_t *d_flags, cudaStream_t st);
 cudaError_t launch_scan_tc(const CUtensorMap &tmap_rows, const CUtensorMap &tmap_q, const TcArgs &a, uint32_t grid,
                            size_t smem, cudaStream_t st);
 cudaError_t launch_finalize_tc(const FinalizeArgs &f, uint32_t b, cudaStream_t st);

@@ -125,8 +125,8 @@ struct sg_store {
     __half *d_qh = nullptr; size_t qh_cap = 0;             // fp16 queries, 128-row padded
     float *d_qerr = nullptr; size_t qmeta_cap = 0;         // [b_pad] |q - fp16(q)|
     float *d_qnorm = nullptr;                              // [b_pad]
-    uint32_t *d_gtau = nullptr, *d_cand_count = nullptr, *d_flags = nullptr, *d_nflag = nullptr;
-    uint64_t *d_cand = nullptr; size_t cand_cap_q = 0;     // [b_pad][TC_CAND_CAP]
+    uint32_t *d_gtau = nullptr, *d_flags = nullptr, *d_nflag = nullptr;
+    uint64_t *d_cand = nullptr; size_t cand_cap_q = 0;     // [b_pad][grid][kk] per-CTA candidate lists
     uint32_t *h_flags = nullptr; size_t hflags_cap = 0;    // pinned: [0] = n_flagged, [1..] flags
     uint64_t tc_searches = 0, tc_flagged = 0;              // statistics (sg_store_tc_stats)
 
@@ -359,15 +359,16 @@ int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint
     int rc;
     if ((rc = grow(s->d_qh, s->qh_cap, (size_t)b_pad * s->dim)) != SG_OK) return rc;
     if (b_pad > s->qmeta_cap) {
-        size_t c[5] = {s->qmeta_cap, s->qmeta_cap, s->qmeta_cap, s->qmeta_cap, s->qmeta_cap};
+        size_t c[4] = {s->qmeta_cap, s->qmeta_cap, s->qmeta_cap, s->qmeta_cap};
         if ((rc = grow(s->d_qerr, c[0], b_pad)) != SG_OK) return rc;
         if ((rc = grow(s->d_qnorm, c[1], b_pad)) != SG_OK) return rc;
         if ((rc = grow(s->d_gtau, c[2], b_pad)) != SG_OK) return rc;
-        if ((rc = grow(s->d_cand_count, c[3], b_pad)) != SG_OK) return rc;
-        if ((rc = grow(s->d_flags, c[4], b_pad)) != SG_OK) return rc;
+        if ((rc = grow(s->d_flags, c[3], b_pad)) != SG_OK) return rc;
         s->qmeta_cap = c[0];
     }
-    if ((rc = grow(s->d_cand, s->cand_cap_q, (size_t)b_pad * TC_CAND_CAP)) != SG_OK) return rc;
+    const uint64_t n_tiles = (s->n + 127) / 128;
+    const uint32_t grid = (uint32_t)(n_tiles < (uint64_t)s->sm_count ? n_tiles : s->sm_count);
+    if ((rc = grow(s->d_cand, s->cand_cap_q, (size_t)b_pad * grid * kk)) != SG_OK) return rc;
     if ((size_t)b + 1 > s->hflags_cap) {
         if (s->h_flags) cudaFreeHost(s->h_flags);
         s->h_flags = nullptr;
@@ -380,10 +381,7 @@ int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint
     if ((rc = encode_corpus_tmap(&tmap_q, s->d_qh, true, s->dim, b_pad, 128)) != SG_OK) return rc;
 
     SG_CUDA_TRY(cudaMemsetAsync(s->d_nflag, 0, 4, st));
-    SG_CUDA_TRY(launch_prep_queries(d_q, b, b_pad, s->dim, s->d_qh, s->d_qerr, s->d_qnorm, s->d_gtau, s->d_cand_count,
-                                    s->d_flags, st));
-    const uint64_t n_tiles = (s->n + 127) / 128;
-    const uint32_t grid = (uint32_t)(n_tiles < (uint64_t)s->sm_count ? n_tiles : s->sm_count);
+    SG_CUDA_TRY(launch_prep_queries(d_q, b, b_pad, s->dim, s->d_qh, s->d_qerr, s->d_qnorm, s->d_gtau, s->d_flags, st));
     const size_t smem = tc_smem_bytes(s->dim, stages, kk);
     const bool prof = s->profiling && 2 * (size_t)(s->ev_count + 1) <= s->ev.size();
     if (prof) SG_CUDA_TRY(cudaEventRecord(s->ev[2 * s->ev_count], st));
@@ -397,9 +395,7 @@ int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint
         a.kk = kk;
         a.deleted = s->n_deleted ? s->d_deleted : nullptr;
         a.gtau = s->d_gtau;
-        a.cand = s->d_cand;
-        a.cand_count = s->d_cand_count;
-        a.cand_cap = TC_CAND_CAP;
+        a.lists = s->d_cand;
         cudaError_t e = launch_scan_tc(tmap_rows, tmap_q, a, grid, smem, st);
         if (e != cudaSuccess) {
             set_error("tensor-core scan launch failed: %s", cudaGetErrorString(e));
@@ -420,9 +416,8 @@ int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint
     f.order = (uint32_t)s->order;
     f.id_base = s->id_base;
     f.n_live = s->n - s->n_deleted;
-    f.cand = s->d_cand;
-    f.cand_count = s->d_cand_count;
-    f.cand_cap = TC_CAND_CAP;
+    f.lists = s->d_cand;
+    f.n_lists = grid;
     f.err = s->d_qerr;
     f.qnorm = s->d_qnorm;
     f.max_row_norm = s->d_max_norm;
@@ -559,7 +554,6 @@ void sg_store_destroy(sg_store *s)
     cudaFree(s->d_qerr);
     cudaFree(s->d_qnorm);
     cudaFree(s->d_gtau);
-    cudaFree(s->d_cand_count);
     cudaFree(s->d_flags);
     cudaFree(s->d_nflag);
     cudaFree(s->d_cand);

@@ -32,7 +32,7 @@ def test_batched_matches_oracle(sg, oracle, n, b):
     st = sg.GpuVectorStore(384, "f16")
     st.append_synthetic(SEED, 0, n)
     seen = oracle.synth_corpus(SEED, 0, n, 384, f16_round=True)
-    queries, near = oracle.synth_queries(SEED + b, n, b, 384)
+    queries, near = oracle.synth_queries(SEED, n, b, 384)
     before = st.tc_stats()
     ids, _ = check_batch(oracle, st, seen, queries, 10)
     after = st.tc_stats()
