@@ -99,23 +99,6 @@ SG_DEVICE_INLINE uint32_t ld_relaxed_u32(const uint32_t *p)
     return v;
 }
 
-// sorted insert of `key` into the thread's ascending list (entry j at my[j*128]); returns
-// (new_count << 32) | new_threshold.  Out of line: hits are rare, the compare loop stays small.
-__device__ __noinline__ uint64_t list_insert(uint64_t *my, uint32_t cnt, uint32_t tau, uint32_t KK, uint64_t key)
-{
-    uint32_t p = cnt < KK ? cnt : KK - 1;
-    if (cnt < KK || key < my[(size_t)p * TC_M]) {
-        while (p > 0 && my[(size_t)(p - 1) * TC_M] > key) {
-            my[(size_t)p * TC_M] = my[(size_t)(p - 1) * TC_M];
-            --p;
-        }
-        my[(size_t)p * TC_M] = key;
-        if (cnt < KK) ++cnt;
-        if (cnt == KK) tau = (uint32_t)(my[(size_t)(KK - 1) * TC_M] >> 32);
-    }
-    return ((uint64_t)cnt << 32) | tau;
-}
-
 // ---- K1: the sweep -----------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
@@ -210,60 +193,84 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
         }
     } else if (warp >= 4) {
         // ===== epilogue: thread t <-> query t <-> TMEM lane t =====
+        // Each query's candidate list (KK == 32 sorted keys) lives in shared memory as one row of 32
+        // entries.  A hit is inserted by the WHOLE warp: lane i holds entry i, one ballot finds the
+        // position, one shuffle shifts the tail -- no dependent shared-memory chain, no divergence.
         const uint32_t t = threadIdx.x - 128;
+        const uint32_t wq = (warp & 3) * 32;             // first query of this warp
+        uint64_t *wlists = lists + (size_t)wq * 32;      // [32 queries][32 entries]
+        for (uint32_t i = lane; i < 32 * 32; i += 32) wlists[i] = KEY_SENTINEL;
+        __syncwarp();
         const bool active = t < a.nq;
-        uint64_t *my = lists + t;                      // entry j at my[j * 128]
-        for (uint32_t j = 0; j < KK; ++j) my[(size_t)j * TC_M] = KEY_SENTINEL;
-        uint32_t cnt = 0;
-        uint32_t tau = 0xFFFFFFFFu;                    // accept key32 <= tau
+        float tau_f = active ? -__uint_as_float(0x7F800000u) : __uint_as_float(0x7F800000u);  // -inf / never
+        uint32_t tau_pub = 0xFFFFFFFFu;                  // last threshold key this lane shared
         uint32_t *gtau = a.gtau + (size_t)a.q_tile * TC_M + t;
-        const uint32_t lane_base = ((warp & 3) * 32) << 16;
+        const uint32_t lane_base = (wq) << 16;
 
         for (uint64_t it = 0; it < my_tiles; ++it) {
             const uint64_t tile = blockIdx.x + it * gridDim.x;
             const uint32_t acc = (uint32_t)(it % TC_ACC_STAGES);
             const uint32_t acc_ph = (uint32_t)((it / TC_ACC_STAGES) & 1);
             if (active) {
-                uint32_t g = ld_relaxed_u32(gtau);
-                if (g < tau) tau = g;
+                const uint32_t g = ld_relaxed_u32(gtau);
+                if (g != 0xFFFFFFFFu) tau_f = fmaxf(tau_f, -key32_to_dist(g));
             }
             mbar_wait(smem_u32(tfull_bar + acc), acc_ph);
             tc_fence_after();
-            bool changed = false;
 #pragma unroll 1
             for (uint32_t c = 0; c < TC_N / 32; ++c) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + lane_base + acc * TC_N + c * 32, r);
                 tmem_ld_wait();
-                if (active) {
+                const uint64_t row0 = tile * TC_N + c * 32;      // 32-aligned: one bitmap word
+                uint32_t dead = 0;
+                if (a.deleted && row0 < a.n_rows) dead = __ldg(a.deleted + (row0 >> 5));
+                if (row0 + 32 > a.n_rows) dead |= row0 >= a.n_rows ? 0xFFFFFFFFu : ~((1u << (uint32_t)(a.n_rows - row0)) - 1u);
 #pragma unroll
-                    for (uint32_t j = 0; j < 32; ++j) {
-                        const uint32_t key32 = order_key32(neg_dot_to_dist(__uint_as_float(r[j])));
-                        if (key32 <= tau) {
-                            const uint64_t row = tile * TC_N + c * 32 + j;
-                            bool ok = row < a.n_rows;
-                            if (ok && a.deleted) ok = !((__ldg(a.deleted + (row >> 5)) >> (row & 31)) & 1u);
-                            if (ok) {
-                                const uint32_t tau_old = tau;
-                                const uint64_t r2 = list_insert(my, cnt, tau, KK, make_key(key32, (uint32_t)row));
-                                cnt = (uint32_t)(r2 >> 32);
-                                tau = (uint32_t)r2;
-                                changed |= tau != tau_old;
+                for (uint32_t j = 0; j < 32; ++j) {
+                    const float sc = __uint_as_float(r[j]);
+                    uint32_t m = __ballot_sync(0xFFFFFFFFu, sc >= tau_f);
+                    if (m && !((dead >> j) & 1u)) {
+                        const uint32_t row = (uint32_t)(row0 + j);
+                        do {                                   // one cooperative insertion per hitting query
+                            const uint32_t L = __ffs(m) - 1;
+                            m &= m - 1;
+                            const uint32_t k32 = order_key32(-__shfl_sync(0xFFFFFFFFu, sc, L));
+                            const uint64_t key = make_key(k32, row);
+                            uint64_t *ql = wlists + (size_t)L * 32;
+                            const uint64_t e = ql[lane];
+                            const uint32_t p = __popc(__ballot_sync(0xFFFFFFFFu, e < key));
+                            if (p < 32) {
+                                const uint32_t e_lo = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)e, 1);
+                                const uint32_t e_hi = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)(e >> 32), 1);
+                                const uint64_t ne = lane < p ? e : (lane == p ? key : (((uint64_t)e_hi << 32) | e_lo));
+                                ql[lane] = ne;
+                                const uint32_t last = __shfl_sync(0xFFFFFFFFu, (uint32_t)(ne >> 32), 31);
+                                if (lane == L && last != 0xFFFFFFFFu) tau_f = -key32_to_dist(last);
                             }
-                        }
+                            __syncwarp();
+                        } while (m);
                     }
                 }
             }
             tc_fence_before();
             mbar_arrive(smem_u32(tempty_bar + acc));       // 128 arrivals release the accumulator
-            if (active && changed) atomicMin(gtau, tau);    // share the threshold GPU-wide
+            if (active && tau_f > -__uint_as_float(0x7F800000u)) {   // share the threshold GPU-wide when it moved
+                const uint32_t k32 = order_key32(-tau_f);
+                if (k32 < tau_pub) {
+                    tau_pub = k32;
+                    atomicMin(gtau, k32);
+                }
+            }
         }
 
-        // publish this CTA's sorted list for the query (KEY_SENTINEL padded); K2 merges the lists
-        if (active) {
-            const uint32_t qg = a.q_tile * TC_M + t;
-            uint64_t *out = a.lists + ((size_t)qg * gridDim.x + blockIdx.x) * KK;
-            for (uint32_t j = 0; j < KK; ++j) out[j] = my[(size_t)j * TC_M];
+        // publish this CTA's sorted list for every query of the warp (KEY_SENTINEL padded)
+        __syncwarp();
+        for (uint32_t qi = 0; qi < 32; ++qi) {
+            const uint32_t qt = wq + qi;
+            if (qt >= a.nq) break;
+            const uint32_t qg = a.q_tile * TC_M + qt;
+            a.lists[((size_t)qg * gridDim.x + blockIdx.x) * 32 + lane] = wlists[(size_t)qi * 32 + lane];
         }
     }
 
