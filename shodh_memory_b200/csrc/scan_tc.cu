@@ -80,6 +80,10 @@ SG_DEVICE_INLINE void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
         : "r"(taddr)
         : "memory");
 }
+SG_DEVICE_INLINE void tmem_ld1(uint32_t taddr, uint32_t &v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+}
 SG_DEVICE_INLINE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4 in
@@ -143,7 +147,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
     const uint32_t tmem_base = *tmem_slot;
 
     const uint64_t n_tiles = (a.n_rows + TC_N - 1) / TC_N;
-    const uint64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    uint64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (a.tile_limit && my_tiles > a.tile_limit) my_tiles = a.tile_limit;   // pre-pass: a prefix of this CTA's tiles
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -194,15 +199,18 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
     } else if (warp >= 4) {
         // ===== epilogue: thread t <-> query t <-> TMEM lane t =====
         // Each query's candidate list (KK == 32 sorted keys) lives in shared memory as one row of 32
-        // entries.  A hit is inserted by the WHOLE warp: lane i holds entry i, one ballot finds the
-        // position, one shuffle shifts the tail -- no dependent shared-memory chain, no divergence.
+        // entries.  The common case per 32-column chunk is "no score reaches any threshold": one
+        // max-tree per lane and one vote.  A hit is inserted by the WHOLE warp: lane i holds entry i,
+        // one ballot finds the position, one shuffle shifts the tail.
         const uint32_t t = threadIdx.x - 128;
         const uint32_t wq = (warp & 3) * 32;             // first query of this warp
         uint64_t *wlists = lists + (size_t)wq * 32;      // [32 queries][32 entries]
         for (uint32_t i = lane; i < 32 * 32; i += 32) wlists[i] = KEY_SENTINEL;
         __syncwarp();
         const bool active = t < a.nq;
-        float tau_f = active ? -__uint_as_float(0x7F800000u) : __uint_as_float(0x7F800000u);  // -inf / never
+        const float NEG_INF = -__uint_as_float(0x7F800000u);
+        float tau_f = active ? NEG_INF : -NEG_INF;       // similarity threshold: -inf / never
+        float mx_all = NEG_INF;                          // pre-pass: best live score seen by this lane
         uint32_t tau_pub = 0xFFFFFFFFu;                  // last threshold key this lane shared
         uint32_t *gtau = a.gtau + (size_t)a.q_tile * TC_M + t;
         const uint32_t lane_base = (wq) << 16;
@@ -211,7 +219,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
             const uint64_t tile = blockIdx.x + it * gridDim.x;
             const uint32_t acc = (uint32_t)(it % TC_ACC_STAGES);
             const uint32_t acc_ph = (uint32_t)((it / TC_ACC_STAGES) & 1);
-            if (active) {
+            if (active && a.mode == 0) {
                 const uint32_t g = ld_relaxed_u32(gtau);
                 if (g != 0xFFFFFFFFu) tau_f = fmaxf(tau_f, -key32_to_dist(g));
             }
@@ -220,24 +228,52 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
 #pragma unroll 1
             for (uint32_t c = 0; c < TC_N / 32; ++c) {
                 uint32_t r[32];
-                tmem_ld32(tmem_base + lane_base + acc * TC_N + c * 32, r);
+                const uint32_t taddr = tmem_base + lane_base + acc * TC_N + c * 32;
+                tmem_ld32(taddr, r);
                 tmem_ld_wait();
                 const uint64_t row0 = tile * TC_N + c * 32;      // 32-aligned: one bitmap word
                 uint32_t dead = 0;
                 if (a.deleted && row0 < a.n_rows) dead = __ldg(a.deleted + (row0 >> 5));
                 if (row0 + 32 > a.n_rows) dead |= row0 >= a.n_rows ? 0xFFFFFFFFu : ~((1u << (uint32_t)(a.n_rows - row0)) - 1u);
+                if (dead) {                                      // rare: neutralise dead columns
 #pragma unroll
-                for (uint32_t j = 0; j < 32; ++j) {
-                    const float sc = __uint_as_float(r[j]);
-                    uint32_t m = __ballot_sync(0xFFFFFFFFu, sc >= tau_f);
-                    if (m && !((dead >> j) & 1u)) {
-                        const uint32_t row = (uint32_t)(row0 + j);
-                        do {                                   // one cooperative insertion per hitting query
-                            const uint32_t L = __ffs(m) - 1;
-                            m &= m - 1;
-                            const uint32_t k32 = order_key32(-__shfl_sync(0xFFFFFFFFu, sc, L));
-                            const uint64_t key = make_key(k32, row);
-                            uint64_t *ql = wlists + (size_t)L * 32;
+                    for (uint32_t j = 0; j < 32; ++j)
+                        if ((dead >> j) & 1u) r[j] = __float_as_uint(NEG_INF);
+                }
+                float m0 = fmaxf(fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3])));
+                float m1 = fmaxf(fmaxf(__uint_as_float(r[4]), __uint_as_float(r[5])), fmaxf(__uint_as_float(r[6]), __uint_as_float(r[7])));
+                float m2 = fmaxf(fmaxf(__uint_as_float(r[8]), __uint_as_float(r[9])), fmaxf(__uint_as_float(r[10]), __uint_as_float(r[11])));
+                float m3 = fmaxf(fmaxf(__uint_as_float(r[12]), __uint_as_float(r[13])), fmaxf(__uint_as_float(r[14]), __uint_as_float(r[15])));
+                float m4 = fmaxf(fmaxf(__uint_as_float(r[16]), __uint_as_float(r[17])), fmaxf(__uint_as_float(r[18]), __uint_as_float(r[19])));
+                float m5 = fmaxf(fmaxf(__uint_as_float(r[20]), __uint_as_float(r[21])), fmaxf(__uint_as_float(r[22]), __uint_as_float(r[23])));
+                float m6 = fmaxf(fmaxf(__uint_as_float(r[24]), __uint_as_float(r[25])), fmaxf(__uint_as_float(r[26]), __uint_as_float(r[27])));
+                float m7 = fmaxf(fmaxf(__uint_as_float(r[28]), __uint_as_float(r[29])), fmaxf(__uint_as_float(r[30]), __uint_as_float(r[31])));
+                const float mx = fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
+                if (a.mode == 1) {                               // pre-pass: only the running maximum
+                    mx_all = fmaxf(mx_all, mx);
+                    continue;
+                }
+                if (__any_sync(0xFFFFFFFFu, mx >= tau_f)) {
+                    // slow path, cost proportional to the number of hits
+                    uint32_t mask = 0;
+#pragma unroll
+                    for (uint32_t j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) >= tau_f) ? (1u << j) : 0u;
+                    uint32_t lanes = __ballot_sync(0xFFFFFFFFu, mask != 0);
+                    while (lanes) {
+                        const uint32_t L = __ffs(lanes) - 1;
+                        lanes &= lanes - 1;
+                        uint32_t mL = __shfl_sync(0xFFFFFFFFu, mask, L);
+                        uint64_t *ql = wlists + (size_t)L * 32;
+                        while (mL) {
+                            const uint32_t j = __ffs(mL) - 1;
+                            mL &= mL - 1;
+                            uint32_t v;
+                            tmem_ld1(taddr + j, v);              // column j for every lane; lane L's is the hit
+                            tmem_ld_wait();
+                            const float sc = __uint_as_float(__shfl_sync(0xFFFFFFFFu, v, L));
+                            const float tauL = __shfl_sync(0xFFFFFFFFu, tau_f, L);
+                            if (!(sc >= tauL)) continue;         // the threshold moved since the mask was taken
+                            const uint64_t key = make_key(order_key32(-sc), (uint32_t)(row0 + j));
                             const uint64_t e = ql[lane];
                             const uint32_t p = __popc(__ballot_sync(0xFFFFFFFFu, e < key));
                             if (p < 32) {
@@ -249,13 +285,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
                                 if (lane == L && last != 0xFFFFFFFFu) tau_f = -key32_to_dist(last);
                             }
                             __syncwarp();
-                        } while (m);
+                        }
                     }
                 }
             }
             tc_fence_before();
             mbar_arrive(smem_u32(tempty_bar + acc));       // 128 arrivals release the accumulator
-            if (active && tau_f > -__uint_as_float(0x7F800000u)) {   // share the threshold GPU-wide when it moved
+            if (a.mode == 0 && active && tau_f > NEG_INF) {  // share the threshold GPU-wide when it moved
                 const uint32_t k32 = order_key32(-tau_f);
                 if (k32 < tau_pub) {
                     tau_pub = k32;
@@ -264,13 +300,18 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
             }
         }
 
-        // publish this CTA's sorted list for every query of the warp (KEY_SENTINEL padded)
         __syncwarp();
-        for (uint32_t qi = 0; qi < 32; ++qi) {
-            const uint32_t qt = wq + qi;
-            if (qt >= a.nq) break;
-            const uint32_t qg = a.q_tile * TC_M + qt;
-            a.lists[((size_t)qg * gridDim.x + blockIdx.x) * 32 + lane] = wlists[(size_t)qi * 32 + lane];
+        if (a.mode == 1) {
+            // pre-pass result: this CTA's best live score per query (a distinct row per CTA)
+            if (active) a.maxima[((size_t)a.q_tile * TC_M + t) * gridDim.x + blockIdx.x] = mx_all;
+        } else {
+            // publish this CTA's sorted list for every query of the warp (KEY_SENTINEL padded)
+            for (uint32_t qi = 0; qi < 32; ++qi) {
+                const uint32_t qt = wq + qi;
+                if (qt >= a.nq) break;
+                const uint32_t qg = a.q_tile * TC_M + qt;
+                a.lists[((size_t)qg * gridDim.x + blockIdx.x) * 32 + lane] = wlists[(size_t)qi * 32 + lane];
+            }
         }
     }
 
@@ -322,6 +363,31 @@ __global__ void prep_queries_kernel(const float *__restrict__ q, uint32_t b, uin
         gtau[row] = 0xFFFFFFFFu;
         if (row < b) flags[row] = 0;
         (void)b_pad;
+    }
+}
+
+// ---- threshold seeding from the pre-pass -------------------------------------------------------
+// maxima[q][cta] = best live approximate score CTA `cta` saw for query q over its first tiles.  The
+// kk-th largest of them is a valid lower bound on the global kk-th best (kk distinct rows reach it).
+__global__ void __launch_bounds__(256)
+tau_init_kernel(const float *__restrict__ maxima, uint32_t n_cta, uint32_t kk, uint32_t *__restrict__ gtau)
+{
+    __shared__ uint64_t keys[256];
+    const uint32_t q = blockIdx.x;
+    const uint32_t M = next_pow2(n_cta < 2 ? 2 : n_cta);
+    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) {
+        uint64_t key = KEY_SENTINEL;
+        if (i < n_cta) {
+            const float m = maxima[(size_t)q * n_cta + i];
+            if (m > -__uint_as_float(0x7F800000u)) key = make_key(order_key32(-m), i);
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    block_bitonic_sort(keys, M);
+    if (threadIdx.x == 0) {
+        const uint64_t kth = n_cta >= kk ? keys[kk - 1] : KEY_SENTINEL;
+        gtau[q] = kth == KEY_SENTINEL ? 0xFFFFFFFFu : (uint32_t)(kth >> 32);
     }
 }
 
@@ -462,6 +528,15 @@ cudaError_t launch_scan_tc(const CUtensorMap &tmap_rows, const CUtensorMap &tmap
     cudaError_t e = cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     scan_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmap_rows, tmap_q, a);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tau_init(const float *d_maxima, uint32_t b_pad, uint32_t n_cta, uint32_t kk, uint32_t *d_gtau,
+                            cudaStream_t st)
+{
+    if (n_cta > 256) return cudaErrorInvalidValue;
+    tau_init_kernel<<<b_pad, 256, 0, st>>>(d_maxima, n_cta, kk, d_gtau);
     count_launch();
     return cudaGetLastError();
 }

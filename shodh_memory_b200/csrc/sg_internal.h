@@ -33,6 +33,9 @@ struct TcArgs {
     const uint32_t *deleted;
     uint32_t *gtau;           // [b_pad] shared threshold per query (best CTA-local kk-th distance key so far)
     uint64_t *lists;          // [b_pad][gridDim.x][kk] each CTA's sorted approximate candidates
+    uint32_t mode;            // 0 = sweep; 1 = pre-pass (per-CTA maxima only, seeds the thresholds)
+    uint32_t tile_limit;      // pre-pass: tiles per CTA (0 = all)
+    float *maxima;            // [b_pad][gridDim.x] pre-pass output
 };
 struct FinalizeArgs {
     const float *queries;     // [b][dim] f32 (the exact operands)
@@ -53,6 +56,8 @@ cudaError_t launch_prep_queries(const float *d_q, uint32_t b, uint32_t b_pad, ui
                                 float *d_qnorm, uint32_t *d_gtau, uint32_t *d_flags, cudaStream_t st);
 cudaError_t launch_scan_tc(const CUtensorMap &tmap_rows, const CUtensorMap &tmap_q, const TcArgs &a, uint32_t grid,
                            size_t smem, cudaStream_t st);
+cudaError_t launch_tau_init(const float *d_maxima, uint32_t b_pad, uint32_t n_cta, uint32_t kk, uint32_t *d_gtau,
+                            cudaStream_t st);
 cudaError_t launch_finalize_tc(const FinalizeArgs &f, uint32_t b, cudaStream_t st);
 
 // ---- select.cu ----
