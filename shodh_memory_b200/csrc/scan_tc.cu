@@ -258,6 +258,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
                     uint32_t mask = 0;
 #pragma unroll
                     for (uint32_t j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) >= tau_f) ? (1u << j) : 0u;
+                    mask &= ~dead;                               // (-inf >= -inf) would let dead columns through
                     uint32_t lanes = __ballot_sync(0xFFFFFFFFu, mask != 0);
                     while (lanes) {
                         const uint32_t L = __ffs(lanes) - 1;
