@@ -119,7 +119,7 @@ class ClockSampler:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
@@ -241,7 +241,7 @@ def main():
     store.local.profile_read()
 
     # ---------------- batch-1 latency (configs[2]): top-100, device-resident ----------------
-    b1_steps = max(steps, 50)
+    b1_steps = max(steps, 200)
     for _ in range(warmup):
         store.search_device(dq[:1], B1_K)
     barrier()
@@ -278,14 +278,16 @@ def main():
                     parallelism=f"row-shard x{world}" + (", 1 NCCL all-gather of per-shard top-k + merge" if world > 1 else ""),
                     l2="per-GPU shard %.2f GB >> 126 MB L2: every sweep streams from HBM, no flush needed" % (alg_bytes / 1e9)),
         roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
-                      kernel="scan_exact_kernel", algorithmic_bytes_per_step=alg_bytes,
+                      kernel=("scan_tc_kernel (tcgen05 sweep, 128 queries per launch)" if BATCH >= 5 and TOPK <= 24
+                              else "scan_exact_kernel"), algorithmic_bytes_per_step=alg_bytes,
                       scan_ms_per_step=scan_step_ms, sweep_launches_per_step=int(sweeps_per_step), peak_source=peak_src,
                       note="achieved = bytes ONE sweep of the shard must read / time of ALL sweep launches of the step"),
         e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=BATCH * DIM * 4,
                  d2h_bytes_per_step=BATCH * TOPK * 8 + BATCH * 4, ms_per_step=e2e_ms / steps),
         batch1=dict(value=1e3 / b1_ms, unit=UNIT, k=B1_K, ms_per_query=b1_ms,
                     roofline=dict(bound="hbm", achieved=b1_achieved, peak=peak, unit="GB/s", frac=b1_achieved / peak,
-                                  scan_ms=b1_scan_ms)),
+                                  scan_ms=b1_scan_ms, kernel="scan_exact_kernel")),
+        tensor_path=dict(zip(("queries", "exact_reruns"), store.local.tc_stats())),
         gpu_launches=int(launches), clocks=clocks)
     if cpu:
         line["cpu_baseline"] = dict(value=cpu["value"], unit=UNIT, cores=cpu["cores"], kind=cpu["kind"], sample=cpu["sample"])
