@@ -96,11 +96,198 @@ SG_DEVICE_INLINE uint64_t make_sw128_desc(uint32_t smem_addr)
 // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=f16 (0), both K-major, N>>3 at bit 17, M>>4 at bit 24
 __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) { return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24); }
 
+// ---- cluster / CTA-pair helpers ------------------------------------------------------------------
+SG_DEVICE_INLINE uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+SG_DEVICE_INLINE void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_addr` in CTA `rank` of the cluster
+SG_DEVICE_INLINE uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+SG_DEVICE_INLINE void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+SG_DEVICE_INLINE void tmem_alloc2(uint32_t smem_dst, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+SG_DEVICE_INLINE void tmem_dealloc2(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+SG_DEVICE_INLINE void umma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the barrier at the same offset in every CTA of `mask` once the pair's MMAs retire
+SG_DEVICE_INLINE void umma_commit_2cta(uint32_t bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+// pair-mode TMA load: data lands in THIS CTA's shared memory, the bytes are credited to `leader_bar`
+SG_DEVICE_INLINE void tma_load_2d_2cta(uint32_t dst_smem, const CUtensorMap *tmap, uint32_t leader_bar, int32_t x, int32_t y)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst_smem), "l"((uint64_t)tmap), "r"(leader_bar), "r"(x), "r"(y)
+        : "memory");
+}
+
 SG_DEVICE_INLINE uint32_t ld_relaxed_u32(const uint32_t *p)
 {
     uint32_t v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+
+
+// ---- the epilogue shared by the 1-CTA and the CTA-pair kernels -------------------------------------
+// thread t (0..127 of the 4 epilogue warps) <-> query q_base + t <-> TMEM lane t.  Each query's
+// candidate list (32 sorted keys) lives in shared memory as one row of 32 entries.  The common case
+// per 32-column chunk is "no score reaches any threshold": one max-tree per lane and one vote.  A hit
+// is re-read with tcgen05.ld.x1 and inserted by the WHOLE warp (lane i holds entry i; one ballot
+// finds the position, one shuffle shifts the tail) -- no dependent shared-memory chain.
+// NCOLS = corpus rows (TMEM columns) per accumulator stage.  tempty_cluster_addr is the
+// shared::cluster address of the accumulator-empty barriers (the leader CTA's in pair mode).
+template <uint32_t NCOLS>
+SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint64_t *lists, uint32_t tmem_base, uint64_t *tfull_bar,
+                                  uint32_t tempty_cluster_addr, uint64_t my_tiles, uint64_t tile0, uint64_t tile_stride,
+                                  uint32_t q_base, uint32_t nq_local, uint32_t list_idx, uint32_t n_lists,
+                                  uint32_t acc_stages)
+{
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t t = threadIdx.x - 128;
+    const uint32_t wq = (warp & 3) * 32;             // first query of this warp
+    uint64_t *wlists = lists + (size_t)wq * 32;      // [32 queries][32 entries]
+    for (uint32_t i = lane; i < 32 * 32; i += 32) wlists[i] = KEY_SENTINEL;
+    __syncwarp();
+    const bool active = t < nq_local;
+    const float NEG_INF = -__uint_as_float(0x7F800000u);
+    float tau_f = active ? NEG_INF : -NEG_INF;       // similarity threshold: -inf / never
+    float mx_all = NEG_INF;                          // pre-pass: best live score seen by this lane
+    uint32_t tau_pub = 0xFFFFFFFFu;                  // last threshold key this lane shared
+    uint32_t *gtau = a.gtau + (size_t)q_base + t;
+    const uint32_t lane_base = (wq) << 16;
+
+    for (uint64_t it = 0; it < my_tiles; ++it) {
+        const uint64_t tile = tile0 + it * tile_stride;
+        const uint32_t acc = (uint32_t)(it % acc_stages);
+        const uint32_t acc_ph = (uint32_t)((it / acc_stages) & 1);
+        if (active && a.mode == 0) {
+            const uint32_t g = ld_relaxed_u32(gtau);
+            if (g != 0xFFFFFFFFu) tau_f = fmaxf(tau_f, -key32_to_dist(g));
+        }
+        mbar_wait(smem_u32(tfull_bar + acc), acc_ph);
+        tc_fence_after();
+#pragma unroll 1
+        for (uint32_t c = 0; c < NCOLS / 32; ++c) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + lane_base + acc * NCOLS + c * 32;
+            tmem_ld32(taddr, r);
+            tmem_ld_wait();
+            const uint64_t row0 = tile * NCOLS + c * 32;     // 32-aligned: one bitmap word
+            uint32_t dead = 0;
+            if (a.deleted && row0 < a.n_rows) dead = __ldg(a.deleted + (row0 >> 5));
+            if (row0 + 32 > a.n_rows) dead |= row0 >= a.n_rows ? 0xFFFFFFFFu : ~((1u << (uint32_t)(a.n_rows - row0)) - 1u);
+            if (dead) {                                      // rare: neutralise dead columns
+#pragma unroll
+                for (uint32_t j = 0; j < 32; ++j)
+                    if ((dead >> j) & 1u) r[j] = __float_as_uint(NEG_INF);
+            }
+            float m0 = fmaxf(fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3])));
+            float m1 = fmaxf(fmaxf(__uint_as_float(r[4]), __uint_as_float(r[5])), fmaxf(__uint_as_float(r[6]), __uint_as_float(r[7])));
+            float m2 = fmaxf(fmaxf(__uint_as_float(r[8]), __uint_as_float(r[9])), fmaxf(__uint_as_float(r[10]), __uint_as_float(r[11])));
+            float m3 = fmaxf(fmaxf(__uint_as_float(r[12]), __uint_as_float(r[13])), fmaxf(__uint_as_float(r[14]), __uint_as_float(r[15])));
+            float m4 = fmaxf(fmaxf(__uint_as_float(r[16]), __uint_as_float(r[17])), fmaxf(__uint_as_float(r[18]), __uint_as_float(r[19])));
+            float m5 = fmaxf(fmaxf(__uint_as_float(r[20]), __uint_as_float(r[21])), fmaxf(__uint_as_float(r[22]), __uint_as_float(r[23])));
+            float m6 = fmaxf(fmaxf(__uint_as_float(r[24]), __uint_as_float(r[25])), fmaxf(__uint_as_float(r[26]), __uint_as_float(r[27])));
+            float m7 = fmaxf(fmaxf(__uint_as_float(r[28]), __uint_as_float(r[29])), fmaxf(__uint_as_float(r[30]), __uint_as_float(r[31])));
+            const float mx = fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
+            if (a.mode == 1) {                               // pre-pass: only the running maximum
+                mx_all = fmaxf(mx_all, mx);
+                continue;
+            }
+            if (__any_sync(0xFFFFFFFFu, mx >= tau_f)) {
+                // slow path, cost proportional to the number of hits
+                uint32_t mask = 0;
+#pragma unroll
+                for (uint32_t j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) >= tau_f) ? (1u << j) : 0u;
+                mask &= ~dead;                               // (-inf >= -inf) would let dead columns through
+                uint32_t lanes = __ballot_sync(0xFFFFFFFFu, mask != 0);
+                while (lanes) {
+                    const uint32_t L = __ffs(lanes) - 1;
+                    lanes &= lanes - 1;
+                    uint32_t mL = __shfl_sync(0xFFFFFFFFu, mask, L);
+                    uint64_t *ql = wlists + (size_t)L * 32;
+                    while (mL) {
+                        const uint32_t j = __ffs(mL) - 1;
+                        mL &= mL - 1;
+                        uint32_t v;
+                        tmem_ld1(taddr + j, v);              // column j for every lane; lane L's is the hit
+                        tmem_ld_wait();
+                        const float sc = __uint_as_float(__shfl_sync(0xFFFFFFFFu, v, L));
+                        const float tauL = __shfl_sync(0xFFFFFFFFu, tau_f, L);
+                        if (!(sc >= tauL)) continue;         // the threshold moved since the mask was taken
+                        const uint64_t key = make_key(order_key32(-sc), (uint32_t)(row0 + j));
+                        const uint64_t e = ql[lane];
+                        const uint32_t p = __popc(__ballot_sync(0xFFFFFFFFu, e < key));
+                        if (p < 32) {
+                            const uint32_t e_lo = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)e, 1);
+                            const uint32_t e_hi = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)(e >> 32), 1);
+                            const uint64_t ne = lane < p ? e : (lane == p ? key : (((uint64_t)e_hi << 32) | e_lo));
+                            ql[lane] = ne;
+                            const uint32_t last = __shfl_sync(0xFFFFFFFFu, (uint32_t)(ne >> 32), 31);
+                            if (lane == L && last != 0xFFFFFFFFu) tau_f = -key32_to_dist(last);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        mbar_arrive_cluster(tempty_cluster_addr + 8 * acc);  // all epilogue threads release the accumulator
+        if (a.mode == 0 && active && tau_f > NEG_INF) {      // share the threshold GPU-wide when it moved
+            const uint32_t k32 = order_key32(-tau_f);
+            if (k32 < tau_pub) {
+                tau_pub = k32;
+                atomicMin(gtau, k32);
+            }
+        }
+    }
+
+    __syncwarp();
+    if (a.mode == 1) {
+        // pre-pass result: this CTA's (pair's) best live score per query -- a distinct row per list
+        if (active) a.maxima[((size_t)q_base + t) * n_lists + list_idx] = mx_all;
+    } else {
+        // publish the sorted list of every query of the warp (KEY_SENTINEL padded)
+        for (uint32_t qi = 0; qi < 32; ++qi) {
+            const uint32_t qt = wq + qi;
+            if (qt >= nq_local) break;
+            a.lists[((size_t)(q_base + qt) * n_lists + list_idx) * 32 + lane] = wlists[(size_t)qi * 32 + lane];
+        }
+    }
 }
 
 // ---- K1: the sweep -----------------------------------------------------------------------------
@@ -198,122 +385,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
         }
     } else if (warp >= 4) {
         // ===== epilogue: thread t <-> query t <-> TMEM lane t =====
-        // Each query's candidate list (KK == 32 sorted keys) lives in shared memory as one row of 32
-        // entries.  The common case per 32-column chunk is "no score reaches any threshold": one
-        // max-tree per lane and one vote.  A hit is inserted by the WHOLE warp: lane i holds entry i,
-        // one ballot finds the position, one shuffle shifts the tail.
-        const uint32_t t = threadIdx.x - 128;
-        const uint32_t wq = (warp & 3) * 32;             // first query of this warp
-        uint64_t *wlists = lists + (size_t)wq * 32;      // [32 queries][32 entries]
-        for (uint32_t i = lane; i < 32 * 32; i += 32) wlists[i] = KEY_SENTINEL;
-        __syncwarp();
-        const bool active = t < a.nq;
-        const float NEG_INF = -__uint_as_float(0x7F800000u);
-        float tau_f = active ? NEG_INF : -NEG_INF;       // similarity threshold: -inf / never
-        float mx_all = NEG_INF;                          // pre-pass: best live score seen by this lane
-        uint32_t tau_pub = 0xFFFFFFFFu;                  // last threshold key this lane shared
-        uint32_t *gtau = a.gtau + (size_t)a.q_tile * TC_M + t;
-        const uint32_t lane_base = (wq) << 16;
-
-        for (uint64_t it = 0; it < my_tiles; ++it) {
-            const uint64_t tile = blockIdx.x + it * gridDim.x;
-            const uint32_t acc = (uint32_t)(it % TC_ACC_STAGES);
-            const uint32_t acc_ph = (uint32_t)((it / TC_ACC_STAGES) & 1);
-            if (active && a.mode == 0) {
-                const uint32_t g = ld_relaxed_u32(gtau);
-                if (g != 0xFFFFFFFFu) tau_f = fmaxf(tau_f, -key32_to_dist(g));
-            }
-            mbar_wait(smem_u32(tfull_bar + acc), acc_ph);
-            tc_fence_after();
-#pragma unroll 1
-            for (uint32_t c = 0; c < TC_N / 32; ++c) {
-                uint32_t r[32];
-                const uint32_t taddr = tmem_base + lane_base + acc * TC_N + c * 32;
-                tmem_ld32(taddr, r);
-                tmem_ld_wait();
-                const uint64_t row0 = tile * TC_N + c * 32;      // 32-aligned: one bitmap word
-                uint32_t dead = 0;
-                if (a.deleted && row0 < a.n_rows) dead = __ldg(a.deleted + (row0 >> 5));
-                if (row0 + 32 > a.n_rows) dead |= row0 >= a.n_rows ? 0xFFFFFFFFu : ~((1u << (uint32_t)(a.n_rows - row0)) - 1u);
-                if (dead) {                                      // rare: neutralise dead columns
-#pragma unroll
-                    for (uint32_t j = 0; j < 32; ++j)
-                        if ((dead >> j) & 1u) r[j] = __float_as_uint(NEG_INF);
-                }
-                float m0 = fmaxf(fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3])));
-                float m1 = fmaxf(fmaxf(__uint_as_float(r[4]), __uint_as_float(r[5])), fmaxf(__uint_as_float(r[6]), __uint_as_float(r[7])));
-                float m2 = fmaxf(fmaxf(__uint_as_float(r[8]), __uint_as_float(r[9])), fmaxf(__uint_as_float(r[10]), __uint_as_float(r[11])));
-                float m3 = fmaxf(fmaxf(__uint_as_float(r[12]), __uint_as_float(r[13])), fmaxf(__uint_as_float(r[14]), __uint_as_float(r[15])));
-                float m4 = fmaxf(fmaxf(__uint_as_float(r[16]), __uint_as_float(r[17])), fmaxf(__uint_as_float(r[18]), __uint_as_float(r[19])));
-                float m5 = fmaxf(fmaxf(__uint_as_float(r[20]), __uint_as_float(r[21])), fmaxf(__uint_as_float(r[22]), __uint_as_float(r[23])));
-                float m6 = fmaxf(fmaxf(__uint_as_float(r[24]), __uint_as_float(r[25])), fmaxf(__uint_as_float(r[26]), __uint_as_float(r[27])));
-                float m7 = fmaxf(fmaxf(__uint_as_float(r[28]), __uint_as_float(r[29])), fmaxf(__uint_as_float(r[30]), __uint_as_float(r[31])));
-                const float mx = fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
-                if (a.mode == 1) {                               // pre-pass: only the running maximum
-                    mx_all = fmaxf(mx_all, mx);
-                    continue;
-                }
-                if (__any_sync(0xFFFFFFFFu, mx >= tau_f)) {
-                    // slow path, cost proportional to the number of hits
-                    uint32_t mask = 0;
-#pragma unroll
-                    for (uint32_t j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) >= tau_f) ? (1u << j) : 0u;
-                    mask &= ~dead;                               // (-inf >= -inf) would let dead columns through
-                    uint32_t lanes = __ballot_sync(0xFFFFFFFFu, mask != 0);
-                    while (lanes) {
-                        const uint32_t L = __ffs(lanes) - 1;
-                        lanes &= lanes - 1;
-                        uint32_t mL = __shfl_sync(0xFFFFFFFFu, mask, L);
-                        uint64_t *ql = wlists + (size_t)L * 32;
-                        while (mL) {
-                            const uint32_t j = __ffs(mL) - 1;
-                            mL &= mL - 1;
-                            uint32_t v;
-                            tmem_ld1(taddr + j, v);              // column j for every lane; lane L's is the hit
-                            tmem_ld_wait();
-                            const float sc = __uint_as_float(__shfl_sync(0xFFFFFFFFu, v, L));
-                            const float tauL = __shfl_sync(0xFFFFFFFFu, tau_f, L);
-                            if (!(sc >= tauL)) continue;         // the threshold moved since the mask was taken
-                            const uint64_t key = make_key(order_key32(-sc), (uint32_t)(row0 + j));
-                            const uint64_t e = ql[lane];
-                            const uint32_t p = __popc(__ballot_sync(0xFFFFFFFFu, e < key));
-                            if (p < 32) {
-                                const uint32_t e_lo = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)e, 1);
-                                const uint32_t e_hi = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)(e >> 32), 1);
-                                const uint64_t ne = lane < p ? e : (lane == p ? key : (((uint64_t)e_hi << 32) | e_lo));
-                                ql[lane] = ne;
-                                const uint32_t last = __shfl_sync(0xFFFFFFFFu, (uint32_t)(ne >> 32), 31);
-                                if (lane == L && last != 0xFFFFFFFFu) tau_f = -key32_to_dist(last);
-                            }
-                            __syncwarp();
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(smem_u32(tempty_bar + acc));       // 128 arrivals release the accumulator
-            if (a.mode == 0 && active && tau_f > NEG_INF) {  // share the threshold GPU-wide when it moved
-                const uint32_t k32 = order_key32(-tau_f);
-                if (k32 < tau_pub) {
-                    tau_pub = k32;
-                    atomicMin(gtau, k32);
-                }
-            }
-        }
-
-        __syncwarp();
-        if (a.mode == 1) {
-            // pre-pass result: this CTA's best live score per query (a distinct row per CTA)
-            if (active) a.maxima[((size_t)a.q_tile * TC_M + t) * gridDim.x + blockIdx.x] = mx_all;
-        } else {
-            // publish this CTA's sorted list for every query of the warp (KEY_SENTINEL padded)
-            for (uint32_t qi = 0; qi < 32; ++qi) {
-                const uint32_t qt = wq + qi;
-                if (qt >= a.nq) break;
-                const uint32_t qg = a.q_tile * TC_M + qt;
-                a.lists[((size_t)qg * gridDim.x + blockIdx.x) * 32 + lane] = wlists[(size_t)qi * 32 + lane];
-            }
-        }
+        tc_epilogue<TC_N>(a, lists, tmem_base, tfull_bar, smem_u32(tempty_bar), my_tiles, /*tile0=*/blockIdx.x,
+                          /*tile_stride=*/gridDim.x, /*q_base=*/a.q_tile * TC_M, /*nq_local=*/a.nq,
+                          /*list_idx=*/blockIdx.x, /*n_lists=*/gridDim.x, TC_ACC_STAGES);
     }
 
     tc_fence_before();
@@ -321,6 +395,136 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
+    }
+}
+
+
+// ---- K1 (CTA-pair form): 256 queries per sweep ----------------------------------------------------
+// Two CTAs of a cluster (one TPC) act as one MMA unit: tcgen05.mma.cta_group::2 with M = 256 (each
+// CTA holds its own 128 queries as the A operand and receives their 128 accumulator rows in its own
+// TMEM) and N = 256 corpus rows per tile, of which each CTA loads HALF (128 rows) -- the tensor
+// core reads both halves, so every corpus byte is fetched once per pair and the shared-memory read
+// traffic per FLOP is half that of the 1-CTA form.  One sweep therefore serves 256 queries.
+// Barrier choreography (the leader is cluster rank 0):
+//   full[s]   leader's only, 2 arrivals: leader's arrive.expect_tx(2 x 16 KB) + the peer's remote
+//             arrive; both CTAs' cta_group::2 TMA loads credit their bytes to it;
+//   empty[s]  per CTA; the leader's tcgen05.commit multicasts the arrival to both;
+//   tfull[a]  per CTA, same multicast commit;  tempty[a] leader's only, 256 epilogue arrivals.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
+                const TcArgs a)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr uint32_t N2 = 256;                 // corpus rows per pair tile (TMEM columns per stage)
+    constexpr uint32_t ACC2 = 2;                 // 2 x 256 = 512 TMEM columns
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const uint32_t nkb = a.dim / TC_KB;
+    const uint32_t S = a.stages;
+
+    uint8_t *a_base = smem;                                         // this CTA's 128 queries
+    uint8_t *b_base = a_base + (size_t)nkb * TC_M * 128;            // S x 16 KB: this CTA's half of each tile
+    uint64_t *lists = reinterpret_cast<uint64_t *>(b_base + (size_t)S * TC_STAGE_BYTES);
+    uint64_t *bars = lists + (size_t)32 * TC_M;
+    uint64_t *full_bar = bars;
+    uint64_t *empty_bar = bars + S;
+    uint64_t *tfull_bar = bars + 2 * S;
+    uint64_t *tempty_bar = tfull_bar + ACC2;
+    uint64_t *a_bar = tempty_bar + ACC2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_bar + 1);
+
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < S; ++i) {
+            mbar_init(smem_u32(full_bar + i), 2);
+            mbar_init(smem_u32(empty_bar + i), 1);
+        }
+        for (uint32_t i = 0; i < ACC2; ++i) {
+            mbar_init(smem_u32(tfull_bar + i), 1);
+            mbar_init(smem_u32(tempty_bar + i), 256);
+        }
+        mbar_init(smem_u32(a_bar), 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&tmap_rows);
+        tma_prefetch_desc(&tmap_q);
+    }
+    cluster_sync_all();                                  // both CTAs resident, barriers initialised
+    if (warp == 2) tmem_alloc2(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const uint32_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const uint64_t n_tiles = (a.n_rows + N2 - 1) / N2;
+    uint64_t my_tiles = cluster_id < n_tiles ? (n_tiles - cluster_id + n_clusters - 1) / n_clusters : 0;
+    if (a.tile_limit && my_tiles > a.tile_limit) my_tiles = a.tile_limit;
+
+    // resident A operand: this CTA's 128 queries.  Everyone waits, then the pair synchronises so the
+    // leader's MMA thread may read the peer's A through the pair datapath.
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(smem_u32(a_bar), nkb * TC_M * 128);
+        for (uint32_t kb = 0; kb < nkb; ++kb)
+            tma_load_2d(smem_u32(a_base + (size_t)kb * TC_M * 128), &tmap_q, smem_u32(a_bar), (int32_t)(kb * TC_KB),
+                        (int32_t)(a.q_tile * 256 + rank * TC_M));
+    }
+    mbar_wait(smem_u32(a_bar), 0);
+    cluster_sync_all();
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): my half of every tile =====
+        if (lane == 0) {
+            uint32_t st = 0, ph = 0;
+            for (uint64_t it = 0; it < my_tiles; ++it) {
+                const uint64_t tile = cluster_id + it * n_clusters;
+                for (uint32_t kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(smem_u32(empty_bar + st), ph ^ 1);
+                    const uint32_t lfull = mapa_u32(smem_u32(full_bar + st), 0);
+                    if (leader) mbar_arrive_expect_tx(smem_u32(full_bar + st), 2 * TC_STAGE_BYTES);
+                    else mbar_arrive_cluster(lfull);
+                    tma_load_2d_2cta(smem_u32(b_base + (size_t)st * TC_STAGE_BYTES), &tmap_rows, lfull,
+                                     (int32_t)(kb * TC_KB), (int32_t)(tile * N2 + rank * TC_M));
+                    if (++st == S) { st = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: the leader's single thread drives the pair =====
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(256, N2);
+            uint32_t st = 0, ph = 0;
+            for (uint64_t it = 0; it < my_tiles; ++it) {
+                const uint32_t acc = (uint32_t)(it % ACC2);
+                const uint32_t acc_ph = (uint32_t)((it / ACC2) & 1);
+                mbar_wait(smem_u32(tempty_bar + acc), acc_ph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * N2;
+                for (uint32_t kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(smem_u32(full_bar + st), ph);
+                    tc_fence_after();
+                    const uint64_t da = make_sw128_desc(smem_u32(a_base + (size_t)kb * TC_M * 128));
+                    const uint64_t db = make_sw128_desc(smem_u32(b_base + (size_t)st * TC_STAGE_BYTES));
+#pragma unroll
+                    for (uint32_t k = 0; k < TC_KB / 16; ++k)
+                        umma_f16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit_2cta(smem_u32(empty_bar + st), 3);     // frees the slot in BOTH CTAs
+                    if (++st == S) { st = 0; ph ^= 1; }
+                }
+                umma_commit_2cta(smem_u32(tfull_bar + acc), 3);        // accumulators ready in BOTH CTAs
+            }
+        }
+    } else if (warp >= 4) {
+        tc_epilogue<N2>(a, lists, tmem_base, tfull_bar, mapa_u32(smem_u32(tempty_bar), 0), my_tiles, /*tile0=*/cluster_id,
+                        /*tile_stride=*/n_clusters, /*q_base=*/a.q_tile * 256 + rank * TC_M,
+                        /*nq_local=*/a.nq > rank * TC_M ? (a.nq - rank * TC_M < TC_M ? a.nq - rank * TC_M : TC_M) : 0,
+                        /*list_idx=*/cluster_id, /*n_lists=*/n_clusters, ACC2);
+    }
+
+    tc_fence_before();
+    cluster_sync_all();          // nobody may still signal or read the peer's barriers / TMEM
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, 512);
     }
 }
 
@@ -529,6 +733,16 @@ cudaError_t launch_scan_tc(const CUtensorMap &tmap_rows, const CUtensorMap &tmap
     cudaError_t e = cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     scan_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmap_rows, tmap_q, a);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan_tc2(const CUtensorMap &tmap_rows, const CUtensorMap &tmap_q, const TcArgs &a, uint32_t grid,
+                            size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(scan_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    scan_tc2_kernel<<<grid, TC_THREADS, smem, st>>>(tmap_rows, tmap_q, a);   // __cluster_dims__(2,1,1): grid must be even
     count_launch();
     return cudaGetLastError();
 }

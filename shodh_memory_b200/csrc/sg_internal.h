@@ -26,8 +26,8 @@ constexpr uint32_t TC_CAND_CAP = 1024;  // candidates at or above the heads thre
 struct TcArgs {
     uint64_t n_rows;
     uint32_t dim;
-    uint32_t nq;              // live queries in this 128-query tile
-    uint32_t q_tile;          // which 128-query tile
+    uint32_t nq;              // live queries in this query tile (128 per tile; 256 in pair mode)
+    uint32_t q_tile;          // which query tile
     uint32_t stages;          // B ring depth
     uint32_t kk;              // candidates kept per query (k + slack)
     const uint32_t *deleted;
@@ -56,6 +56,8 @@ cudaError_t launch_prep_queries(const float *d_q, uint32_t b, uint32_t b_pad, ui
                                 float *d_qnorm, uint32_t *d_gtau, uint32_t *d_flags, cudaStream_t st);
 cudaError_t launch_scan_tc(const CUtensorMap &tmap_rows, const CUtensorMap &tmap_q, const TcArgs &a, uint32_t grid,
                            size_t smem, cudaStream_t st);
+cudaError_t launch_scan_tc2(const CUtensorMap &tmap_rows, const CUtensorMap &tmap_q, const TcArgs &a, uint32_t grid,
+                            size_t smem, cudaStream_t st);
 cudaError_t launch_tau_init(const float *d_maxima, uint32_t b_pad, uint32_t n_cta, uint32_t kk, uint32_t *d_gtau,
                             cudaStream_t st);
 cudaError_t launch_finalize_tc(const FinalizeArgs &f, uint32_t b, cudaStream_t st);

@@ -356,7 +356,12 @@ bool tc_eligible(const sg_store *s, uint32_t b, uint32_t k, uint32_t *kk_out, ui
 int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint32_t kk, uint32_t stages,
                      uint32_t *d_ids, float *d_dist, uint32_t *d_counts, cudaStream_t st)
 {
-    const uint32_t b_pad = (b + 127) / 128 * 128;
+    // CTA-pair form (256 queries per sweep) for b > 128; 1-CTA form (128 per sweep) otherwise
+    const int pair_env = env_u32("SG_TC_PAIR", 1);
+    const bool pair = pair_env == 2 || (pair_env == 1 && b > 128);
+    const uint32_t qtile = pair ? 256 : 128;          // queries per sweep
+    const uint32_t rows_tile = pair ? 256 : 128;      // corpus rows per (pair) tile
+    const uint32_t b_pad = (b + qtile - 1) / qtile * qtile;
     int rc;
     if ((rc = grow(s->d_qh, s->qh_cap, (size_t)b_pad * s->dim)) != SG_OK) return rc;
     if (b_pad > s->qmeta_cap) {
@@ -367,9 +372,11 @@ int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint
         if ((rc = grow(s->d_flags, c[3], b_pad)) != SG_OK) return rc;
         s->qmeta_cap = c[0];
     }
-    const uint64_t n_tiles = (s->n + 127) / 128;
-    const uint32_t grid = (uint32_t)(n_tiles < (uint64_t)s->sm_count ? n_tiles : s->sm_count);
-    if ((rc = grow(s->d_cand, s->cand_cap_q, (size_t)b_pad * grid * kk)) != SG_OK) return rc;
+    const uint64_t n_tiles = (s->n + rows_tile - 1) / rows_tile;
+    const uint32_t units_max = pair ? (uint32_t)s->sm_count / 2 : (uint32_t)s->sm_count;   // clusters or CTAs
+    const uint32_t n_lists = (uint32_t)(n_tiles < units_max ? n_tiles : units_max);
+    const uint32_t grid = pair ? 2 * n_lists : n_lists;
+    if ((rc = grow(s->d_cand, s->cand_cap_q, (size_t)b_pad * n_lists * kk)) != SG_OK) return rc;
     if ((size_t)b + 1 > s->hflags_cap) {
         if (s->h_flags) cudaFreeHost(s->h_flags);
         s->h_flags = nullptr;
@@ -386,18 +393,18 @@ int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint
     const size_t smem = tc_smem_bytes(s->dim, stages, kk);
     const bool prof = s->profiling && 2 * (size_t)(s->ev_count + 1) <= s->ev.size();
     if (prof) SG_CUDA_TRY(cudaEventRecord(s->ev[2 * s->ev_count], st));
-    // pre-pass (large corpora): every CTA scores its first few tiles and keeps only its best live score
-    // per query; the kk-th largest of those maxima seeds a valid GPU-wide threshold, so the sweep does
-    // ~100x fewer list insertions than with CTA-local thresholds alone.
-    const uint32_t pre_tiles = (uint32_t)env_u32("SG_TC_PRE_TILES", 8);
-    const bool prepass = pre_tiles && grid >= kk && n_tiles >= (uint64_t)grid * pre_tiles * 8;
-    if (prepass && (rc = grow(s->d_maxima, s->maxima_cap, (size_t)b_pad * grid)) != SG_OK) return rc;
+    // pre-pass (large corpora): every CTA (pair) scores its first few tiles and keeps only its best live
+    // score per query; the kk-th largest of those maxima seeds a valid GPU-wide threshold, so the sweep
+    // does far fewer list insertions than with CTA-local thresholds alone.
+    const uint32_t pre_tiles = (uint32_t)env_u32("SG_TC_PRE_TILES", pair ? 4 : 8);
+    const bool prepass = pre_tiles && n_lists >= kk && n_tiles >= (uint64_t)n_lists * pre_tiles * 8;
+    if (prepass && (rc = grow(s->d_maxima, s->maxima_cap, (size_t)b_pad * n_lists)) != SG_OK) return rc;
     for (int pass = prepass ? 1 : 0; pass >= 0; --pass) {
-        for (uint32_t qt = 0; qt < b_pad / 128; ++qt) {
+        for (uint32_t qt = 0; qt < b_pad / qtile; ++qt) {
             TcArgs a;
             a.n_rows = s->n;
             a.dim = s->dim;
-            a.nq = b - qt * 128 < 128 ? b - qt * 128 : 128;
+            a.nq = b - qt * qtile < qtile ? b - qt * qtile : qtile;
             a.q_tile = qt;
             a.stages = stages;
             a.kk = kk;
@@ -407,14 +414,15 @@ int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint
             a.mode = (uint32_t)pass;
             a.tile_limit = pass ? pre_tiles : 0;
             a.maxima = s->d_maxima;
-            cudaError_t e = launch_scan_tc(tmap_rows, tmap_q, a, grid, smem, st);
+            cudaError_t e = pair ? launch_scan_tc2(tmap_rows, tmap_q, a, grid, smem, st)
+                                 : launch_scan_tc(tmap_rows, tmap_q, a, grid, smem, st);
             if (e != cudaSuccess) {
                 set_error("tensor-core scan launch failed: %s", cudaGetErrorString(e));
                 return SG_ERR_CUDA;
             }
             if (!pass) ++s->last_scan_launches;
         }
-        if (pass) SG_CUDA_TRY(launch_tau_init(s->d_maxima, b, grid, kk, s->d_gtau, st));
+        if (pass) SG_CUDA_TRY(launch_tau_init(s->d_maxima, b, n_lists, kk, s->d_gtau, st));
     }
     if (prof) {
         SG_CUDA_TRY(cudaEventRecord(s->ev[2 * s->ev_count + 1], st));
@@ -430,7 +438,7 @@ int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint
     f.id_base = s->id_base;
     f.n_live = s->n - s->n_deleted;
     f.lists = s->d_cand;
-    f.n_lists = grid;
+    f.n_lists = n_lists;
     f.err = s->d_qerr;
     f.qnorm = s->d_qnorm;
     f.max_row_norm = s->d_max_norm;

@@ -119,3 +119,37 @@ def test_unnormalised_rows_still_exact(sg, oracle):
     queries = rng.standard_normal((20, 384)).astype(F)
     check_batch(oracle, st, oracle.round_f16(corpus), queries, 10)
     st.close()
+
+
+@pytest.mark.parametrize("n", [4096, 70_001])
+@pytest.mark.parametrize("b", [5, 129, 256, 300])
+def test_pair_kernel_matches_oracle(sg, oracle, n, b, monkeypatch):
+    """CTA-pair form (tcgen05.mma.cta_group::2, 256 queries per sweep), forced for every batch size."""
+    monkeypatch.setenv("SG_TC_PAIR", "2")
+    st = sg.GpuVectorStore(384, "f16")
+    st.append_synthetic(SEED, 0, n)
+    seen = oracle.synth_corpus(SEED, 0, n, 384, f16_round=True)
+    queries, near = oracle.synth_queries(SEED, n, b, 384)
+    for d in (3, 128, 255, 256, n - 1):
+        st.mark_deleted(d)
+    before = st.tc_stats()
+    check_batch(oracle, st, seen, queries, 10, deleted=[3, 128, 255, 256, n - 1])
+    after = st.tc_stats()
+    assert after[0] - before[0] == b
+    assert after[1] - before[1] <= max(2, b // 8)          # a wrong row mapping would flag everything
+    st.close()
+
+
+def test_pair_kernel_large_with_prepass(sg, oracle, monkeypatch):
+    """2M rows: the pre-pass / threshold seeding is active; compare with the exact path."""
+    n, b = 2_000_000, 256
+    st = sg.GpuVectorStore(384, "f16")
+    st.append_synthetic(SEED, 0, n)
+    queries, _ = oracle.synth_queries(SEED, n, b, 384)
+    tc = st.search_batch(queries, 10)
+    assert st.tc_stats() == (b, 0)
+    monkeypatch.setenv("SG_TC_DISABLE", "1")
+    ex = st.search_batch(queries[:16], 10)
+    for x, y in zip(tc, ex):
+        assert x[:16].tobytes() == y.tobytes()
+    st.close()
