@@ -14,7 +14,7 @@ q = torch.nn.functional.normalize(torch.randn(512, 384, generator=g), dim=1).cud
 stream = torch.cuda.current_stream().cuda_stream
 st.set_profiling(True)
 bytes_sweep = n * 384 * 2
-for b in [5, 16, 64, 128, 256, 512]:
+for b in [int(x) for x in os.environ.get("BS", "5,16,64,128,256,512").split(",")]:
     k = 10
     ids = torch.empty((b, k), dtype=torch.int32, device="cuda"); dist = torch.empty((b, k), device="cuda")
     cnt = torch.empty(b, dtype=torch.int32, device="cuda")

@@ -183,6 +183,7 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint64_t *lists, uint32_t tme
     for (uint32_t i = lane; i < 32 * 32; i += 32) wlists[i] = KEY_SENTINEL;
     __syncwarp();
     const bool active = t < nq_local;
+    const uint32_t KKE = a.kk;                       // candidates kept per query and list (<= 32)
     const float NEG_INF = -__uint_as_float(0x7F800000u);
     float tau_f = active ? NEG_INF : -NEG_INF;       // similarity threshold: -inf / never
     float mx_all = NEG_INF;                          // pre-pass: best live score seen by this lane
@@ -252,12 +253,13 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint64_t *lists, uint32_t tme
                         const uint64_t key = make_key(order_key32(-sc), (uint32_t)(row0 + j));
                         const uint64_t e = ql[lane];
                         const uint32_t p = __popc(__ballot_sync(0xFFFFFFFFu, e < key));
-                        if (p < 32) {
+                        if (p < KKE) {                       // lanes >= KKE always hold KEY_SENTINEL
                             const uint32_t e_lo = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)e, 1);
                             const uint32_t e_hi = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)(e >> 32), 1);
-                            const uint64_t ne = lane < p ? e : (lane == p ? key : (((uint64_t)e_hi << 32) | e_lo));
+                            uint64_t ne = lane < p ? e : (lane == p ? key : (((uint64_t)e_hi << 32) | e_lo));
+                            if (lane >= KKE) ne = KEY_SENTINEL;
                             ql[lane] = ne;
-                            const uint32_t last = __shfl_sync(0xFFFFFFFFu, (uint32_t)(ne >> 32), 31);
+                            const uint32_t last = __shfl_sync(0xFFFFFFFFu, (uint32_t)(ne >> 32), KKE - 1);
                             if (lane == L && last != 0xFFFFFFFFu) tau_f = -key32_to_dist(last);
                         }
                         __syncwarp();
@@ -299,13 +301,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t nkb = a.dim / TC_KB;          // K-blocks per row
     const uint32_t S = a.stages;
-    const uint32_t KK = a.kk;
 
     // carve-up: A block | B ring | per-query lists | barriers | tmem ptr
     uint8_t *a_base = smem;                                         // nkb x (128 x 128 B)
     uint8_t *b_base = a_base + (size_t)nkb * TC_M * 128;            // S x 16 KB
-    uint64_t *lists = reinterpret_cast<uint64_t *>(b_base + (size_t)S * TC_STAGE_BYTES);  // [KK][128]
-    uint64_t *bars = lists + (size_t)KK * TC_M;
+    uint64_t *lists = reinterpret_cast<uint64_t *>(b_base + (size_t)S * TC_STAGE_BYTES);  // [128 queries][32]
+    uint64_t *bars = lists + (size_t)32 * TC_M;
     uint64_t *full_bar = bars;                       // [S]
     uint64_t *empty_bar = bars + S;                  // [S]
     uint64_t *tfull_bar = bars + 2 * S;              // [TC_ACC_STAGES]
@@ -630,12 +631,12 @@ finalize_tc_kernel(const FinalizeArgs f)
     __shared__ uint32_t s_flag, s_n;
     const uint32_t q = blockIdx.x;
     const uint32_t L = f.n_lists;
-    const uint64_t *ql = f.lists + (size_t)q * L * f.kk;
+    const uint64_t *ql = f.lists + (size_t)q * L * 32;   // every list is 32 slots, the first f.kk are used
     for (uint32_t i = threadIdx.x; i < f.dim; i += blockDim.x) q_s[i] = f.queries[(size_t)q * f.dim + i];
     // (1) threshold from the list heads: at least kk candidates (kk distinct heads) have key <= T0,
     //     so every member of the global top-kk has key <= T0.
     const uint32_t MH = next_pow2(L < 2 ? 2 : L);
-    for (uint32_t i = threadIdx.x; i < MH; i += blockDim.x) keys[i] = i < L ? ql[(size_t)i * f.kk] : KEY_SENTINEL;
+    for (uint32_t i = threadIdx.x; i < MH; i += blockDim.x) keys[i] = i < L ? ql[(size_t)i * 32] : KEY_SENTINEL;
     if (threadIdx.x == 0) {
         s_flag = 0;
         s_n = 0;
@@ -647,7 +648,7 @@ finalize_tc_kernel(const FinalizeArgs f)
     // (2) gather every entry with key <= T0 (lists are sorted: a prefix of each)
     for (uint32_t i = threadIdx.x; i < L; i += blockDim.x) {
         for (uint32_t j = 0; j < f.kk; ++j) {
-            const uint64_t key = ql[(size_t)i * f.kk + j];
+            const uint64_t key = ql[(size_t)i * 32 + j];
             if (key == KEY_SENTINEL || key > T0) break;
             const uint32_t slot = atomicAdd(&s_n, 1u);
             if (slot < TC_CAND_CAP) keys[slot] = key;
@@ -714,7 +715,8 @@ size_t tc_smem_bytes(uint32_t dim, uint32_t stages, uint32_t kk)
 {
     size_t s = (size_t)(dim / TC_KB) * TC_M * 128;          // A
     s += (size_t)stages * TC_STAGE_BYTES;                    // B ring
-    s += (size_t)kk * TC_M * 8;                              // lists
+    (void)kk;
+    s += (size_t)32 * TC_M * 8;                              // lists: 32 slots per query
     s += (size_t)(2 * stages + 2 * TC_ACC_STAGES + 1) * 8 + 16;
     return s;
 }

@@ -342,7 +342,11 @@ bool tc_eligible(const sg_store *s, uint32_t b, uint32_t k, uint32_t *kk_out, ui
     if (env_u32("SG_TC_DISABLE", 0)) return false;
     if (b < (uint32_t)env_u32("SG_TC_MIN_B", 5)) return false;
     if (k > 24 || s->n < 4096) return false;
-    const uint32_t kk = 32;                       // k + slack (>= 8 spare candidates)
+    // candidates kept per query and list = k + slack; fewer candidates => a tighter seeded threshold and
+    // fewer list insertions, more slack => fewer exact re-runs on tie-heavy corpora
+    uint32_t kk = k <= 10 ? 16 : 32;
+    const uint32_t kk_env = (uint32_t)env_u32("SG_TC_KK", 0);
+    if (kk_env >= k + 2 && kk_env <= 32) kk = kk_env;
     for (uint32_t stages = 8; stages >= 3; --stages) {
         if (tc_smem_bytes(s->dim, stages, kk) <= 227 * 1024) {
             *kk_out = kk;
@@ -376,7 +380,7 @@ int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint
     const uint32_t units_max = pair ? (uint32_t)s->sm_count / 2 : (uint32_t)s->sm_count;   // clusters or CTAs
     const uint32_t n_lists = (uint32_t)(n_tiles < units_max ? n_tiles : units_max);
     const uint32_t grid = pair ? 2 * n_lists : n_lists;
-    if ((rc = grow(s->d_cand, s->cand_cap_q, (size_t)b_pad * n_lists * kk)) != SG_OK) return rc;
+    if ((rc = grow(s->d_cand, s->cand_cap_q, (size_t)b_pad * n_lists * 32)) != SG_OK) return rc;
     if ((size_t)b + 1 > s->hflags_cap) {
         if (s->h_flags) cudaFreeHost(s->h_flags);
         s->h_flags = nullptr;
