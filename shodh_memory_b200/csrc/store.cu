@@ -400,7 +400,7 @@ int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint
     // pre-pass (large corpora): every CTA (pair) scores its first few tiles and keeps only its best live
     // score per query; the kk-th largest of those maxima seeds a valid GPU-wide threshold, so the sweep
     // does far fewer list insertions than with CTA-local thresholds alone.
-    const uint32_t pre_tiles = (uint32_t)env_u32("SG_TC_PRE_TILES", pair ? 4 : 8);
+    const uint32_t pre_tiles = (uint32_t)env_u32("SG_TC_PRE_TILES", pair ? 16 : 4);
     const bool prepass = pre_tiles && n_lists >= kk && n_tiles >= (uint64_t)n_lists * pre_tiles * 8;
     if (prepass && (rc = grow(s->d_maxima, s->maxima_cap, (size_t)b_pad * n_lists)) != SG_OK) return rc;
     for (int pass = prepass ? 1 : 0; pass >= 0; --pass) {

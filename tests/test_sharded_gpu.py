@@ -1,0 +1,58 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): two ranks, row-sharded store, one NCCL
+all-gather of per-shard top-k, strided merge -- must equal the single-store result bit for bit."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["SG_ROOT"])
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+import shodh_memory_b200 as sg
+N, B, K, SEED = 300_000, 48, 10, 23821
+st = sg.ShardedGpuStore(N, 384, "f16", rank, world, rank)
+st.fill_synthetic(SEED)
+g = torch.Generator().manual_seed(5)
+q = torch.nn.functional.normalize(torch.randn(B, 384, generator=g), dim=1)
+dq = q.cuda()
+for b, k in ((B, K), (1, 100), (3, 10)):
+    ids, dst, cnt = st.search_device(dq[:b], k)
+    torch.cuda.synchronize()
+    if rank == 0:
+        ref = sg.GpuVectorStore(384, "f16", 0)
+        ref.append_synthetic(SEED, 0, N)
+        rid, rdist, rcnt = ref.search_batch(q[:b].numpy(), k)
+        assert np.array_equal(ids.cpu().numpy().view(np.uint32), rid), (b, k)
+        assert np.array_equal(dst.cpu().numpy().view(np.uint32), rdist.view(np.uint32)), (b, k)
+        assert np.array_equal(cnt.cpu().numpy().view(np.uint32), rcnt)
+        ref.close()
+h_ids, h_dist, h_cnt = st.search(q.pin_memory(), K)       # end-to-end host form
+if rank == 0:
+    ids, dst, cnt = st.search_device(dq, K); torch.cuda.synchronize()
+    assert np.array_equal(h_ids.numpy(), ids.cpu().numpy())
+    print("SHARDED_OK")
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_two_gpu_sharded_search_equals_single_store(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, SG_ROOT=ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29571", str(script)],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "SHARDED_OK" in out.stdout
