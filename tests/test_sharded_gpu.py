@@ -34,9 +34,10 @@ for b, k in ((B, K), (1, 100), (3, 10)):
         assert np.array_equal(dst.cpu().numpy().view(np.uint32), rdist.view(np.uint32)), (b, k)
         assert np.array_equal(cnt.cpu().numpy().view(np.uint32), rcnt)
         ref.close()
-h_ids, h_dist, h_cnt = st.search(q.pin_memory(), K)       # end-to-end host form
+h_ids, h_dist, h_cnt = st.search(q.pin_memory(), K)       # end-to-end host form (collective: all ranks)
+h_ids = h_ids.clone()
+ids, dst, cnt = st.search_device(dq, K); torch.cuda.synchronize()
 if rank == 0:
-    ids, dst, cnt = st.search_device(dq, K); torch.cuda.synchronize()
     assert np.array_equal(h_ids.numpy(), ids.cpu().numpy())
     print("SHARDED_OK")
 dist.barrier()
