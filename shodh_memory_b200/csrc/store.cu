@@ -141,6 +141,11 @@ namespace {
 
 int check_device(int device, int *sm_count)
 {
+    // cudaGetDeviceProperties costs milliseconds: query each device once
+    static std::mutex mu;
+    static int cached_sms[64];
+    static int cached_rc[64];
+    static bool cached[64];
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
@@ -148,17 +153,25 @@ int check_device(int device, int *sm_count)
                   e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
         return SG_ERR_NO_DEVICE;
     }
-    if (device < 0 || device >= n) {
+    if (device < 0 || device >= n || device >= 64) {
         set_error("device ordinal %d out of range (0..%d)", device, n - 1);
         return SG_ERR_INVALID;
     }
-    cudaDeviceProp p;
-    SG_CUDA_TRY(cudaGetDeviceProperties(&p, device));
-    if (p.major != 10) {
-        set_error("device %d is sm_%d%d; libshodh_gpu is built for sm_100a (B200) only", device, p.major, p.minor);
-        return SG_ERR_NO_DEVICE;
+    std::lock_guard<std::mutex> g(mu);
+    if (!cached[device]) {
+        cudaDeviceProp p;
+        SG_CUDA_TRY(cudaGetDeviceProperties(&p, device));
+        cached_sms[device] = p.multiProcessorCount;
+        cached_rc[device] = p.major == 10 ? SG_OK : SG_ERR_NO_DEVICE;
+        cached[device] = true;
+        if (p.major != 10)
+            set_error("device %d is sm_%d%d; libshodh_gpu is built for sm_100a (B200) only", device, p.major, p.minor);
     }
-    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cached_rc[device] != SG_OK) {
+        set_error("device %d is not an sm_100 device; libshodh_gpu is built for sm_100a (B200) only", device);
+        return cached_rc[device];
+    }
+    if (sm_count) *sm_count = cached_sms[device];
     return SG_OK;
 }
 
