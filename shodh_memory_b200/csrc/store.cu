@@ -79,10 +79,10 @@ int encode_corpus_tmap(CUtensorMap *out, const void *d_rows, bool f16, uint32_t 
     return SG_OK;
 }
 
-static int env_u32(const char *name, uint32_t dflt)
+static int env_u32(const char *name, int dflt)
 {
     const char *v = getenv(name);
-    if (!v || !*v) return (int)dflt;
+    if (!v || !*v) return dflt;
     return atoi(v);
 }
 
@@ -413,8 +413,13 @@ int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint
     // pre-pass (large corpora): every CTA (pair) scores its first few tiles and keeps only its best live
     // score per query; the kk-th largest of those maxima seeds a valid GPU-wide threshold, so the sweep
     // does far fewer list insertions than with CTA-local thresholds alone.
-    const uint32_t pre_tiles = (uint32_t)env_u32("SG_TC_PRE_TILES", pair ? 16 : 4);
-    const bool prepass = pre_tiles && n_lists >= kk && n_tiles >= (uint64_t)n_lists * pre_tiles * 8;
+    // tiles of the pre-pass per list: ~1/8 of a list's tiles at most, 16 (pair) / 4 (1-CTA) on large corpora
+    const uint64_t tiles_per_list = n_tiles / n_lists;
+    uint32_t pre_tiles = pair ? 16 : 4;
+    if (tiles_per_list / 8 < pre_tiles) pre_tiles = (uint32_t)(tiles_per_list / 8);
+    const int pre_env = env_u32("SG_TC_PRE_TILES", -1);
+    if (pre_env >= 0) pre_tiles = (uint32_t)pre_env;
+    const bool prepass = pre_tiles > 0 && n_lists >= kk;
     if (prepass && (rc = grow(s->d_maxima, s->maxima_cap, (size_t)b_pad * n_lists)) != SG_OK) return rc;
     for (int pass = prepass ? 1 : 0; pass >= 0; --pass) {
         for (uint32_t qt = 0; qt < b_pad / qtile; ++qt) {
