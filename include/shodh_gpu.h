@@ -191,6 +191,29 @@ SG_API int sg_fuse_topk(int device, const sg_fuse_weights *w, const sg_fuse_conf
                         uint32_t *order_out, float *score_out, uint32_t *n_out,
                         float *all_scores_out);
 
+/* ---- sentence encoder: replaces the ONNX Runtime session + pooling inside MiniLMEmbedder
+ * (src/embeddings/minilm.rs: generate_embedding_onnx :883-982, generate_embeddings_batch_onnx
+ * :996-1115 = session.run + masked mean-pool + finalize_pooled :846-878), i.e. the body of
+ * `impl Embedder for MiniLMEmbedder` (:1195-1377; trait src/embeddings/mod.rs:52-88).
+ * Tokenisation / prefixes / metrics stay on the host, as in the reference. ------------------- */
+
+/* weights_path: an SGW1 blob (shodh_memory_b200/encoder.py::export_bert_weights writes it from a
+ * HuggingFace BERT/MiniLM state_dict: 6 layers x 384 hidden x 12 heads x 1536 FFN). */
+SG_API int sg_encoder_create(sg_encoder **out, int device, const char *weights_path);
+SG_API void sg_encoder_destroy(sg_encoder *e);
+/* Embedder::dimension (minilm.rs:1206-1208) */
+SG_API int sg_encoder_dim(const sg_encoder *e, uint32_t *dim_out);
+/* Embedder::encode_batch on token ids: input_ids / attention_mask [b,L] i64 (the tensors the
+ * reference binds at minilm.rs:924-934; token_type_ids are all zero there) -> emb_out [b,384]
+ * f32, masked-mean-pooled and L2-normalised; all-masked rows (empty text) give zeros
+ * (minilm.rs:1123-1125).  L <= 512. */
+SG_API int sg_encoder_encode(sg_encoder *e, const int64_t *input_ids, const int64_t *attention_mask,
+                             uint32_t b, uint32_t L, float *emb_out);
+/* same with device-resident inputs/outputs, asynchronous on cuda_stream: feeds
+ * sg_store_search_device without leaving the GPU (BASELINE config 5). */
+SG_API int sg_encoder_encode_device(sg_encoder *e, const int64_t *d_input_ids, const int64_t *d_attention_mask,
+                                    uint32_t b, uint32_t L, float *d_emb_out, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

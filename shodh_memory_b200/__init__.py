@@ -5,6 +5,7 @@ host-side mirror of the reference's VamanaIndex / relevance surface for tests an
 Importing the package loads lib/libshodh_gpu.so and fails loudly if it is missing."""
 from . import capi
 from .capi import SgError
+from .encoder import GpuMiniLM, export_bert_weights
 from .relevance import fuse_topk
 from .vector_store import GpuVectorStore, merge_topk_device
 
@@ -33,5 +34,5 @@ def __getattr__(name):  # torch-dependent helpers load lazily (the C ABI itself 
     raise AttributeError(name)
 
 
-__all__ = ["GpuVectorStore", "ShardedGpuStore", "merge_topk_device", "fuse_topk", "SgError", "version", "kernel_launch_count",
+__all__ = ["GpuVectorStore", "ShardedGpuStore", "GpuMiniLM", "export_bert_weights", "merge_topk_device", "fuse_topk", "SgError", "version", "kernel_launch_count",
            "device_count", "capi"]

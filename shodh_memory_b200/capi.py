@@ -92,6 +92,13 @@ def lib() -> C.CDLL:
                                                C.c_uint64, vp, vp, vp, vp]
     L.sg_store_tc_stats.argtypes = [vp, u64p, u64p]
     L.sg_store_profile_read.argtypes = [vp, f32p, C.c_uint32, u32p, u32p]
+    i64p = C.POINTER(C.c_int64)
+    L.sg_encoder_create.argtypes = [C.POINTER(vp), C.c_int, C.c_char_p]
+    L.sg_encoder_destroy.argtypes = [vp]
+    L.sg_encoder_destroy.restype = None
+    L.sg_encoder_dim.argtypes = [vp, u32p]
+    L.sg_encoder_encode.argtypes = [vp, i64p, i64p, C.c_uint32, C.c_uint32, f32p]
+    L.sg_encoder_encode_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp]
     L.sg_fuse_default_weights.argtypes = [C.POINTER(FuseWeights)]
     L.sg_fuse_default_weights.restype = None
     L.sg_fuse_default_config.argtypes = [C.POINTER(FuseConfig)]

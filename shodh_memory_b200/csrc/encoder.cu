@@ -1,0 +1,756 @@
+// encoder.cu -- MiniLM-L6 (BERT, 6 layers x 384 hidden x 12 heads, FFN 1536) sentence encoder.
+//
+// Replaces the ONNX Runtime session + pooling of MiniLMEmbedder (reference
+// src/embeddings/minilm.rs): session.run :939-948 / :1065-1074 (third-party C++ BERT forward),
+// masked mean-pool :959-978 / :1083-1108, finalize_pooled :846-878 (NaN scrub, L2 norm).
+// Tokenisation stays on the host (tokenizers crate); the C ABI takes input_ids / attention_mask.
+//
+// B200 mapping.  Every dense contraction is a tcgen05 GEMM (C[T,N] = A[T,K] . W[N,K]^T, fp16
+// operands, f32 accumulation in TMEM) with the element-wise work fused into the epilogue that
+// reads the accumulator out of TMEM:
+//   QKV projection    N=1152  tile 128x128   epilogue: + bias                       -> fp16
+//   attention out     N=384   tile 128x384   epilogue: + bias + residual, LayerNorm  -> fp16
+//   FFN up            N=1536  tile 128x128   epilogue: + bias, erf-GELU              -> fp16
+//   FFN down          N=384   tile 128x384   epilogue: + bias + residual, LayerNorm  -> fp16 (+f32 last layer)
+// (a 128x384 tile keeps a whole hidden row inside one CTA's TMEM, so LayerNorm needs no second
+// kernel).  Operands are staged by TMA (SWIZZLE_128B, K-major -- PyTorch's [out,in] weight layout
+// IS the K-major B operand).  Attention (L <= 512, d = 32; ~4 % of the FLOPs) and the embedding
+// gather + LayerNorm run on CUDA cores; pooling follows the reference's summation order exactly.
+// Parity: "unpinned" against the reference (no weights / ONNX Runtime in this environment); the
+// kernel is checked against a PyTorch fp32 BertModel with the same weights (tests/test_encoder_gpu.py).
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "sg_internal.h"
+#include "sg_tc.cuh"
+
+namespace sg {
+namespace {
+
+constexpr uint32_t EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RES_LN = 2;
+constexpr uint32_t G_THREADS = 256;
+
+struct GemmArgs {
+    uint32_t K;            // reduction length (multiple of 64)
+    uint32_t N;            // output width
+    uint32_t stages;
+    const float *bias;     // [N]
+    const __half *residual;  // [M_pad, N] (EPI_BIAS_RES_LN)
+    const float *gamma, *beta;
+    float eps;
+    __half *out;           // [M_pad, N]
+    float *out_f32;        // optional f32 copy (EPI_BIAS_RES_LN)
+};
+
+SG_DEVICE_INLINE float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// C tile = 128 rows x BN columns, one tile per CTA.  grid = (M_pad/128, N/BN).
+template <uint32_t BN, uint32_t EPI>
+__global__ void __launch_bounds__(G_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const GemmArgs g)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr uint32_t A_BYTES = 128 * 128;              // 128 rows x 64 fp16
+    constexpr uint32_t B_BYTES = BN * 128;
+    constexpr uint32_t STAGE = A_BYTES + B_BYTES;
+    constexpr uint32_t TCOLS = BN <= 128 ? 128 : (BN <= 256 ? 256 : 512);
+    constexpr uint32_t NSPLIT = BN > 256 ? 2 : 1;        // MMA N <= 256: a 384-wide tile is 2 x 192
+    constexpr uint32_t MMA_N = BN / NSPLIT;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t S = g.stages;
+    const uint32_t nkb = g.K / 64;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * STAGE);
+    uint64_t *full_bar = bars, *empty_bar = bars + S, *done_bar = bars + 2 * S;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
+
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < S; ++i) {
+            mbar_init(smem_u32(full_bar + i), 1);
+            mbar_init(smem_u32(empty_bar + i), 1);
+        }
+        mbar_init(smem_u32(done_bar), 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_w);
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), TCOLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t st = 0, ph = 0;
+            for (uint32_t kb = 0; kb < nkb; ++kb) {
+                mbar_wait(smem_u32(empty_bar + st), ph ^ 1);
+                mbar_arrive_expect_tx(smem_u32(full_bar + st), STAGE);
+                const uint32_t sa = smem_u32(smem + (size_t)st * STAGE);
+                tma_load_2d(sa, &tmap_a, smem_u32(full_bar + st), (int32_t)(kb * 64), (int32_t)m0);
+#pragma unroll
+                for (uint32_t h = 0; h < NSPLIT; ++h)
+                    tma_load_2d(sa + A_BYTES + h * MMA_N * 128, &tmap_w, smem_u32(full_bar + st), (int32_t)(kb * 64),
+                                (int32_t)(n0 + h * MMA_N));
+                if (++st == S) { st = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(128, MMA_N);
+            uint32_t st = 0, ph = 0;
+            for (uint32_t kb = 0; kb < nkb; ++kb) {
+                mbar_wait(smem_u32(full_bar + st), ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)st * STAGE);
+                const uint64_t da = make_sw128_desc(sa);
+#pragma unroll
+                for (uint32_t h = 0; h < NSPLIT; ++h) {
+                    const uint64_t db = make_sw128_desc(sa + A_BYTES + h * MMA_N * 128);
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; ++k)
+                        umma_f16(tmem_base + h * MMA_N, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                }
+                umma_commit(smem_u32(empty_bar + st));
+                if (++st == S) { st = 0; ph ^= 1; }
+            }
+            umma_commit(smem_u32(done_bar));
+        }
+    } else if (warp >= 4) {
+        // epilogue: thread t <-> output row m0 + t <-> TMEM lane t
+        const uint32_t t = threadIdx.x - 128;
+        const uint32_t row = m0 + t;
+        const uint32_t lane_base = ((warp & 3) * 32) << 16;
+        mbar_wait(smem_u32(done_bar), 0);
+        tc_fence_after();
+        if constexpr (EPI == EPI_BIAS_RES_LN) {
+            // BN == N == hidden: the whole row is in this thread's TMEM lane.  Three passes over
+            // TMEM (mean, variance, normalise): cheap, and numerically the two-pass variance.
+            const __half *res = g.residual + (size_t)row * g.N;
+            float sum = 0.0f;
+#pragma unroll 1
+            for (uint32_t c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + lane_base + c * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (uint32_t j = 0; j < 32; ++j)
+                    sum += __uint_as_float(r[j]) + g.bias[c * 32 + j] + __half2float(res[c * 32 + j]);
+            }
+            const float mean = sum / (float)BN;
+            float var = 0.0f;
+#pragma unroll 1
+            for (uint32_t c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + lane_base + c * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (uint32_t j = 0; j < 32; ++j) {
+                    const float d = __uint_as_float(r[j]) + g.bias[c * 32 + j] + __half2float(res[c * 32 + j]) - mean;
+                    var += d * d;
+                }
+            }
+            const float rstd = rsqrtf(var / (float)BN + g.eps);
+#pragma unroll 1
+            for (uint32_t c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + lane_base + c * 32, r);
+                tmem_ld_wait();
+                __align__(16) __half o[32];
+#pragma unroll
+                for (uint32_t j = 0; j < 32; ++j) {
+                    const uint32_t col = c * 32 + j;
+                    const float v = __uint_as_float(r[j]) + g.bias[col] + __half2float(res[col]);
+                    const float y = (v - mean) * rstd * g.gamma[col] + g.beta[col];
+                    o[j] = __float2half_rn(y);
+                    if (g.out_f32) g.out_f32[(size_t)row * g.N + col] = y;
+                }
+                uint4 *dst = reinterpret_cast<uint4 *>(g.out + (size_t)row * g.N + c * 32);
+#pragma unroll
+                for (uint32_t q = 0; q < 4; ++q) dst[q] = reinterpret_cast<const uint4 *>(o)[q];
+            }
+        } else {
+#pragma unroll 1
+            for (uint32_t c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + lane_base + c * 32, r);
+                tmem_ld_wait();
+                __align__(16) __half o[32];
+#pragma unroll
+                for (uint32_t j = 0; j < 32; ++j) {
+                    float v = __uint_as_float(r[j]) + g.bias[n0 + c * 32 + j];
+                    if constexpr (EPI == EPI_BIAS_GELU) v = gelu_erf(v);
+                    o[j] = __float2half_rn(v);
+                }
+                uint4 *dst = reinterpret_cast<uint4 *>(g.out + (size_t)row * g.N + n0 + c * 32);
+#pragma unroll
+                for (uint32_t q = 0; q < 4; ++q) dst[q] = reinterpret_cast<const uint4 *>(o)[q];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TCOLS);
+    }
+}
+
+// ---- embeddings: word + position + token_type(0), LayerNorm -> fp16 ---------------------------------
+// one warp per token; rows >= T (padding up to a multiple of 128) are zeroed.
+__global__ void embed_ln_kernel(const int64_t *__restrict__ ids, uint32_t T, uint32_t T_pad, uint32_t L, uint32_t H,
+                                uint32_t vocab, const float *__restrict__ word, const float *__restrict__ pos,
+                                const float *__restrict__ type0, const float *__restrict__ gamma,
+                                const float *__restrict__ beta, float eps, __half *__restrict__ out)
+{
+    const uint32_t tok = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (tok >= T_pad) return;
+    if (tok >= T) {
+        for (uint32_t d = lane; d < H; d += 32) out[(size_t)tok * H + d] = __float2half_rn(0.0f);
+        return;
+    }
+    int64_t id = ids[tok];
+    if (id < 0 || id >= (int64_t)vocab) id = 0;
+    const uint32_t p = tok % L;
+    float v[16];                                            // H <= 512
+    float sum = 0.0f;
+    uint32_t n = 0;
+    for (uint32_t d = lane; d < H; d += 32, ++n) {
+        v[n] = word[(size_t)id * H + d] + pos[(size_t)p * H + d] + type0[d];
+        sum += v[n];
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    const float mean = sum / (float)H;
+    float var = 0.0f;
+    for (uint32_t i = 0; i < n; ++i) var += (v[i] - mean) * (v[i] - mean);
+    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xFFFFFFFFu, var, o);
+    const float rstd = rsqrtf(var / (float)H + eps);
+    n = 0;
+    for (uint32_t d = lane; d < H; d += 32, ++n)
+        out[(size_t)tok * H + d] = __float2half_rn((v[n] - mean) * rstd * gamma[d] + beta[d]);
+}
+
+// ---- attention: one CTA per (sequence, head); d = 32; keys/values of the head in shared memory ------
+// softmax(q.k/sqrt(d) + mask) . v with an online (running max) softmax; masked keys contribute
+// exp(-inf) = 0, exactly like the additive -inf mask of the reference graph.
+__global__ void __launch_bounds__(128)
+attention_kernel(const __half *__restrict__ qkv, const int64_t *__restrict__ mask, uint32_t L, uint32_t H,
+                 uint32_t heads, __half *__restrict__ ctx)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    constexpr uint32_t D = 32;
+    const uint32_t b = blockIdx.x / heads, h = blockIdx.x % heads;
+    __half *ks = reinterpret_cast<__half *>(smem_raw);       // [L][32]
+    __half *vs = ks + (size_t)L * D;                        // [L][32]
+    uint8_t *ms = reinterpret_cast<uint8_t *>(vs + (size_t)L * D);
+    const size_t row_stride = 3 * (size_t)H;
+    const __half *base = qkv + (size_t)b * L * row_stride;
+    for (uint32_t i = threadIdx.x; i < L * 4; i += blockDim.x) {   // 4 x 16 B per row of 32 halfs
+        const uint32_t j = i >> 2, part = i & 3;
+        reinterpret_cast<uint4 *>(ks)[i] = *reinterpret_cast<const uint4 *>(base + j * row_stride + H + h * D + part * 8);
+        reinterpret_cast<uint4 *>(vs)[i] = *reinterpret_cast<const uint4 *>(base + j * row_stride + 2 * H + h * D + part * 8);
+    }
+    for (uint32_t j = threadIdx.x; j < L; j += blockDim.x) ms[j] = mask[(size_t)b * L + j] == 1 ? 1 : 0;
+    __syncthreads();
+    const float scale = 0.17677669529663687f;              // 1/sqrt(32)
+    for (uint32_t i = threadIdx.x; i < L; i += blockDim.x) {
+        float q[D];
+        const __half *qp = base + i * row_stride + h * D;
+#pragma unroll
+        for (uint32_t d = 0; d < D; ++d) q[d] = __half2float(qp[d]) * scale;
+        float m = -__uint_as_float(0x7F800000u), l = 0.0f, acc[D];
+#pragma unroll
+        for (uint32_t d = 0; d < D; ++d) acc[d] = 0.0f;
+        for (uint32_t j = 0; j < L; ++j) {
+            if (!ms[j]) continue;
+            const __half2 *kp = reinterpret_cast<const __half2 *>(ks + (size_t)j * D);
+            float s = 0.0f;
+#pragma unroll
+            for (uint32_t d = 0; d < D / 2; ++d) {
+                const float2 kk = __half22float2(kp[d]);
+                s = fmaf(q[2 * d], kk.x, s);
+                s = fmaf(q[2 * d + 1], kk.y, s);
+            }
+            const float m_new = fmaxf(m, s);
+            const float corr = __expf(m - m_new), p = __expf(s - m_new);
+            l = l * corr + p;
+            const __half2 *vp = reinterpret_cast<const __half2 *>(vs + (size_t)j * D);
+#pragma unroll
+            for (uint32_t d = 0; d < D / 2; ++d) {
+                const float2 vv = __half22float2(vp[d]);
+                acc[2 * d] = acc[2 * d] * corr + p * vv.x;
+                acc[2 * d + 1] = acc[2 * d + 1] * corr + p * vv.y;
+            }
+            m = m_new;
+        }
+        const float inv = l > 0.0f ? 1.0f / l : 0.0f;
+        __half *op = ctx + ((size_t)b * L + i) * H + h * D;
+#pragma unroll
+        for (uint32_t d = 0; d < D; ++d) op[d] = __float2half_rn(acc[d] * inv);
+    }
+}
+
+// ---- masked mean-pool + finalize (reference minilm.rs:959-978, :846-878) -----------------------------
+// pooled[d] += h[s][d] for s ascending over mask==1; /= mask_sum; NaN/Inf -> 0; norm = sqrt(sum x^2)
+// left-to-right; divide by norm if norm > f32::EPSILON.  One CTA per sequence, one thread per dim.
+__global__ void pool_norm_kernel(const float *__restrict__ hidden, const int64_t *__restrict__ mask, uint32_t L,
+                                 uint32_t H, float *__restrict__ out)
+{
+    extern __shared__ float pooled[];
+    __shared__ float s_norm;
+    const uint32_t b = blockIdx.x;
+    for (uint32_t d = threadIdx.x; d < H; d += blockDim.x) {
+        float acc = 0.0f, msum = 0.0f;
+        for (uint32_t s = 0; s < L; ++s) {
+            if (mask[(size_t)b * L + s] == 1) {
+                acc = __fadd_rn(acc, hidden[((size_t)b * L + s) * H + d]);
+                msum = __fadd_rn(msum, 1.0f);
+            }
+        }
+        if (msum > 0.0f) acc = __fdiv_rn(acc, msum);
+        if (isnan(acc) || isinf(acc)) acc = 0.0f;
+        pooled[d] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float ss = 0.0f;
+        for (uint32_t d = 0; d < H; ++d) ss = __fadd_rn(ss, __fmul_rn(pooled[d], pooled[d]));
+        s_norm = __fsqrt_rn(ss);
+    }
+    __syncthreads();
+    const float norm = s_norm;
+    for (uint32_t d = threadIdx.x; d < H; d += blockDim.x) {
+        float v = pooled[d];
+        if (norm > 1.1920929e-7f && !isnan(norm)) v = __fdiv_rn(v, norm);
+        out[(size_t)b * H + d] = v;
+    }
+}
+
+__global__ void f32_to_f16_rows_kernel(const float *__restrict__ src, __half *__restrict__ dst, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = __float2half_rn(src[i]);
+}
+
+int encode_tmap(CUtensorMap *out, const void *ptr, uint32_t k, uint64_t rows, uint32_t box_rows)
+{
+    return encode_corpus_tmap(out, ptr, true, k, rows, box_rows);
+}
+
+template <uint32_t BN, uint32_t EPI>
+cudaError_t launch_gemm(const CUtensorMap &ta, const CUtensorMap &tw, const GemmArgs &g, uint32_t m_tiles, cudaStream_t st)
+{
+    constexpr uint32_t STAGE = 128 * 128 + BN * 128;
+    const size_t smem = (size_t)g.stages * STAGE + (2 * g.stages + 1) * 8 + 16;
+    auto kern = gemm_tc_kernel<BN, EPI>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<dim3(m_tiles, g.N / BN), G_THREADS, smem, st>>>(ta, tw, g);
+    count_launch();
+    return cudaGetLastError();
+}
+
+struct Layer {
+    __half *wqkv, *wo, *w1, *w2;          // [1152,H] [H,H] [F,H] [H,F]
+    float *bqkv, *bo, *b1, *b2, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+};
+
+}  // namespace
+}  // namespace sg
+
+using namespace sg;
+
+struct sg_encoder {
+    int device = 0;
+    uint32_t layers = 0, hidden = 0, heads = 0, ffn = 0, vocab = 0, max_pos = 0;
+    float eps = 1e-12f;
+    float *word = nullptr, *pos = nullptr, *type0 = nullptr, *emb_g = nullptr, *emb_b = nullptr;
+    std::vector<Layer> L;
+    std::vector<void *> allocs;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    // activations (grown on demand)
+    size_t cap_tokens = 0;
+    __half *h0 = nullptr, *h1 = nullptr, *qkv = nullptr, *ctx = nullptr, *mid = nullptr;
+    float *hf32 = nullptr;
+    int64_t *d_ids = nullptr, *d_mask = nullptr;
+    float *d_emb = nullptr;
+    size_t cap_b = 0;
+    void *h_pinned = nullptr;
+    size_t pinned_cap = 0;
+};
+
+namespace {
+
+struct Blob {
+    std::vector<uint8_t> data;
+    struct T { std::string name; std::vector<uint32_t> shape; const float *ptr; size_t n; };
+    std::vector<T> tensors;
+    uint32_t hdr[6] = {0, 0, 0, 0, 0, 0};
+    const T *find(const std::string &n) const
+    {
+        for (const auto &t : tensors)
+            if (t.name == n) return &t;
+        return nullptr;
+    }
+};
+
+// "SGW1" | u32 version | u32 layers hidden heads ffn vocab max_pos | u32 n_tensors |
+// per tensor: u32 name_len, name, u32 ndim, u32 dims[ndim], f32 data (little endian)
+int load_blob(const char *path, Blob &b)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) {
+        set_error("cannot open weights file %s", path);
+        return SG_ERR_INVALID;
+    }
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    b.data.resize((size_t)sz);
+    size_t got = fread(b.data.data(), 1, (size_t)sz, f);
+    fclose(f);
+    if (got != (size_t)sz || sz < 40 || memcmp(b.data.data(), "SGW1", 4) != 0) {
+        set_error("%s is not an SGW1 weights file", path);
+        return SG_ERR_INVALID;
+    }
+    const uint8_t *p = b.data.data() + 4, *end = b.data.data() + sz;
+    auto rd = [&](uint32_t &v) {
+        if (p + 4 > end) return false;
+        memcpy(&v, p, 4);
+        p += 4;
+        return true;
+    };
+    uint32_t version = 0, n = 0;
+    if (!rd(version) || version != 1) {
+        set_error("unsupported SGW1 version");
+        return SG_ERR_INVALID;
+    }
+    for (int i = 0; i < 6; ++i)
+        if (!rd(b.hdr[i])) return SG_ERR_INVALID;
+    if (!rd(n)) return SG_ERR_INVALID;
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t nl = 0, nd = 0;
+        if (!rd(nl) || p + nl > end) return SG_ERR_INVALID;
+        Blob::T t;
+        t.name.assign(reinterpret_cast<const char *>(p), nl);
+        p += nl;
+        if (!rd(nd) || nd > 4) return SG_ERR_INVALID;
+        size_t cnt = 1;
+        for (uint32_t d = 0; d < nd; ++d) {
+            uint32_t x = 0;
+            if (!rd(x)) return SG_ERR_INVALID;
+            t.shape.push_back(x);
+            cnt *= x;
+        }
+        // data is 4-byte aligned relative to the file start by construction of the writer
+        if (p + cnt * 4 > end) {
+            set_error("truncated tensor %s", t.name.c_str());
+            return SG_ERR_INVALID;
+        }
+        t.ptr = reinterpret_cast<const float *>(p);
+        t.n = cnt;
+        p += cnt * 4;
+        b.tensors.push_back(t);
+    }
+    return SG_OK;
+}
+
+int upload_f32(sg_encoder *e, const Blob &b, const std::string &name, size_t expect, float **out)
+{
+    const Blob::T *t = b.find(name);
+    if (!t || t->n != expect) {
+        set_error("weights: tensor %s missing or of wrong size (want %zu elements)", name.c_str(), expect);
+        return SG_ERR_INVALID;
+    }
+    std::vector<float> tmp(t->n);
+    memcpy(tmp.data(), t->ptr, t->n * 4);   // the blob pointer may be unaligned
+    SG_CUDA_TRY(cudaMalloc(out, t->n * 4));
+    e->allocs.push_back(*out);
+    SG_CUDA_TRY(cudaMemcpy(*out, tmp.data(), t->n * 4, cudaMemcpyHostToDevice));
+    return SG_OK;
+}
+
+// concatenates the named [rows_i, cols] f32 tensors along rows and stores them as fp16
+int upload_f16_cat(sg_encoder *e, const Blob &b, const std::vector<std::string> &names, size_t rows_each, size_t cols,
+                   __half **out)
+{
+    std::vector<float> tmp;
+    for (const auto &nm : names) {
+        const Blob::T *t = b.find(nm);
+        if (!t || t->n != rows_each * cols) {
+            set_error("weights: tensor %s missing or of wrong size", nm.c_str());
+            return SG_ERR_INVALID;
+        }
+        const size_t off = tmp.size();
+        tmp.resize(off + t->n);
+        memcpy(tmp.data() + off, t->ptr, t->n * 4);
+    }
+    float *d32 = nullptr;
+    SG_CUDA_TRY(cudaMalloc(&d32, tmp.size() * 4));
+    cudaError_t er = cudaMemcpy(d32, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice);
+    if (er == cudaSuccess) er = cudaMalloc(out, tmp.size() * 2);
+    if (er == cudaSuccess) {
+        e->allocs.push_back(*out);
+        f32_to_f16_rows_kernel<<<256, 256>>>(d32, *out, tmp.size());
+        count_launch();
+        er = cudaDeviceSynchronize();
+    }
+    cudaFree(d32);
+    if (er != cudaSuccess) {
+        set_error("weight upload failed: %s", cudaGetErrorString(er));
+        return SG_ERR_CUDA;
+    }
+    return SG_OK;
+}
+
+int upload_bias_cat(sg_encoder *e, const Blob &b, const std::vector<std::string> &names, size_t each, float **out)
+{
+    std::vector<float> tmp;
+    for (const auto &nm : names) {
+        const Blob::T *t = b.find(nm);
+        if (!t || t->n != each) {
+            set_error("weights: tensor %s missing or of wrong size", nm.c_str());
+            return SG_ERR_INVALID;
+        }
+        const size_t off = tmp.size();
+        tmp.resize(off + t->n);
+        memcpy(tmp.data() + off, t->ptr, t->n * 4);
+    }
+    SG_CUDA_TRY(cudaMalloc(out, tmp.size() * 4));
+    e->allocs.push_back(*out);
+    SG_CUDA_TRY(cudaMemcpy(*out, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice));
+    return SG_OK;
+}
+
+template <typename T>
+int regrow(T *&p, size_t elems)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+    SG_CUDA_TRY(cudaMalloc(&p, elems * sizeof(T)));
+    return SG_OK;
+}
+
+int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_mask, uint32_t b, uint32_t L, float *d_out,
+                         cudaStream_t st)
+{
+    const uint32_t H = e->hidden, F = e->ffn;
+    const uint32_t T = b * L, T_pad = (T + 127) / 128 * 128, m_tiles = T_pad / 128;
+    int rc;
+    if (T_pad > e->cap_tokens) {
+        const size_t c = (size_t)T_pad;
+        if ((rc = regrow(e->h0, c * H)) != SG_OK) return rc;
+        if ((rc = regrow(e->h1, c * H)) != SG_OK) return rc;
+        if ((rc = regrow(e->qkv, c * 3 * H)) != SG_OK) return rc;
+        if ((rc = regrow(e->ctx, c * H)) != SG_OK) return rc;
+        if ((rc = regrow(e->mid, c * F)) != SG_OK) return rc;
+        if ((rc = regrow(e->hf32, c * H)) != SG_OK) return rc;
+        e->cap_tokens = c;
+    }
+    // ctx rows beyond T are never written by attention: keep them finite
+    SG_CUDA_TRY(cudaMemsetAsync(e->ctx, 0, (size_t)T_pad * H * 2, st));
+    embed_ln_kernel<<<(T_pad * 32 + 255) / 256, 256, 0, st>>>(d_ids, T, T_pad, L, H, e->vocab, e->word, e->pos, e->type0,
+                                                               e->emb_g, e->emb_b, e->eps, e->h0);
+    count_launch();
+    CUtensorMap t_h0, t_h1, t_ctx, t_mid;
+    if ((rc = encode_tmap(&t_h0, e->h0, H, T_pad, 128)) != SG_OK) return rc;
+    if ((rc = encode_tmap(&t_h1, e->h1, H, T_pad, 128)) != SG_OK) return rc;
+    if ((rc = encode_tmap(&t_ctx, e->ctx, H, T_pad, 128)) != SG_OK) return rc;
+    if ((rc = encode_tmap(&t_mid, e->mid, F, T_pad, 128)) != SG_OK) return rc;
+    const size_t att_smem = (size_t)L * 32 * 2 * 2 + L;
+    if (att_smem > 48 * 1024)
+        SG_CUDA_TRY(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
+    for (uint32_t l = 0; l < e->layers; ++l) {
+        const Layer &ly = e->L[l];
+        CUtensorMap t_wqkv, t_wo, t_w1, t_w2;
+        if ((rc = encode_tmap(&t_wqkv, ly.wqkv, H, 3 * H, 128)) != SG_OK) return rc;
+        if ((rc = encode_tmap(&t_wo, ly.wo, H, H, H / 2)) != SG_OK) return rc;
+        if ((rc = encode_tmap(&t_w1, ly.w1, H, F, 128)) != SG_OK) return rc;
+        if ((rc = encode_tmap(&t_w2, ly.w2, F, H, H / 2)) != SG_OK) return rc;
+        GemmArgs g{};
+        // QKV = h0 . Wqkv^T + b
+        g.K = H; g.N = 3 * H; g.stages = 4; g.bias = ly.bqkv; g.out = e->qkv;
+        SG_CUDA_TRY((launch_gemm<128, EPI_BIAS>(t_h0, t_wqkv, g, m_tiles, st)));
+        attention_kernel<<<b * e->heads, 128, att_smem, st>>>(e->qkv, d_mask, L, H, e->heads, e->ctx);
+        count_launch();
+        // h1 = LN(ctx . Wo^T + b + h0)
+        g = GemmArgs{};
+        g.K = H; g.N = H; g.stages = 3; g.bias = ly.bo; g.residual = e->h0; g.gamma = ly.ln1_g; g.beta = ly.ln1_b;
+        g.eps = e->eps; g.out = e->h1;
+        SG_CUDA_TRY((launch_gemm<384, EPI_BIAS_RES_LN>(t_ctx, t_wo, g, m_tiles, st)));
+        // mid = gelu(h1 . W1^T + b)
+        g = GemmArgs{};
+        g.K = H; g.N = F; g.stages = 4; g.bias = ly.b1; g.out = e->mid;
+        SG_CUDA_TRY((launch_gemm<128, EPI_BIAS_GELU>(t_h1, t_w1, g, m_tiles, st)));
+        // h0 = LN(mid . W2^T + b + h1)
+        g = GemmArgs{};
+        g.K = F; g.N = H; g.stages = 3; g.bias = ly.b2; g.residual = e->h1; g.gamma = ly.ln2_g; g.beta = ly.ln2_b;
+        g.eps = e->eps; g.out = e->h0; g.out_f32 = (l + 1 == e->layers) ? e->hf32 : nullptr;
+        SG_CUDA_TRY((launch_gemm<384, EPI_BIAS_RES_LN>(t_mid, t_w2, g, m_tiles, st)));
+    }
+    pool_norm_kernel<<<b, 128, H * 4, st>>>(e->hf32, d_mask, L, H, d_out);
+    count_launch();
+    SG_CUDA_TRY(cudaGetLastError());
+    return SG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sg_encoder_create(sg_encoder **out, int device, const char *weights_path)
+{
+    if (!out || !weights_path) return SG_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device available; libshodh_gpu has no CPU fallback");
+        return SG_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) return SG_ERR_INVALID;
+    cudaDeviceProp prop;
+    SG_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; libshodh_gpu is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return SG_ERR_NO_DEVICE;
+    }
+    Blob blob;
+    int rc = load_blob(weights_path, blob);
+    if (rc != SG_OK) return rc;
+    SG_CUDA_TRY(cudaSetDevice(device));
+    sg_encoder *e = new (std::nothrow) sg_encoder();
+    if (!e) return SG_ERR_OOM;
+    e->device = device;
+    e->layers = blob.hdr[0]; e->hidden = blob.hdr[1]; e->heads = blob.hdr[2];
+    e->ffn = blob.hdr[3]; e->vocab = blob.hdr[4]; e->max_pos = blob.hdr[5];
+    auto fail = [&](int code) {
+        for (void *p : e->allocs) cudaFree(p);
+        delete e;
+        return code;
+    };
+    if (e->hidden != 384 || e->heads * 32 != e->hidden || e->ffn % 128 != 0 || e->layers == 0 || e->layers > 48) {
+        set_error("unsupported encoder shape (hidden=%u heads=%u ffn=%u): the kernels cover hidden 384 / head dim 32", e->hidden,
+                  e->heads, e->ffn);
+        return fail(SG_ERR_UNSUPPORTED);
+    }
+    const size_t H = e->hidden, F = e->ffn;
+    const std::string em = "embeddings.";
+    if ((rc = upload_f32(e, blob, em + "word_embeddings.weight", (size_t)e->vocab * H, &e->word)) != SG_OK) return fail(rc);
+    if ((rc = upload_f32(e, blob, em + "position_embeddings.weight", (size_t)e->max_pos * H, &e->pos)) != SG_OK) return fail(rc);
+    {
+        const Blob::T *t = blob.find(em + "token_type_embeddings.weight");
+        if (!t || t->n < H) {
+            set_error("weights: token_type_embeddings missing");
+            return fail(SG_ERR_INVALID);
+        }
+        std::vector<float> tmp(H);
+        memcpy(tmp.data(), t->ptr, H * 4);
+        if (cudaMalloc(&e->type0, H * 4) != cudaSuccess) return fail(SG_ERR_OOM);
+        e->allocs.push_back(e->type0);
+        cudaMemcpy(e->type0, tmp.data(), H * 4, cudaMemcpyHostToDevice);
+    }
+    if ((rc = upload_f32(e, blob, em + "LayerNorm.weight", H, &e->emb_g)) != SG_OK) return fail(rc);
+    if ((rc = upload_f32(e, blob, em + "LayerNorm.bias", H, &e->emb_b)) != SG_OK) return fail(rc);
+    e->L.resize(e->layers);
+    for (uint32_t l = 0; l < e->layers; ++l) {
+        const std::string p = "encoder.layer." + std::to_string(l) + ".";
+        Layer &ly = e->L[l];
+        if ((rc = upload_f16_cat(e, blob, {p + "attention.self.query.weight", p + "attention.self.key.weight",
+                                           p + "attention.self.value.weight"}, H, H, &ly.wqkv)) != SG_OK) return fail(rc);
+        if ((rc = upload_bias_cat(e, blob, {p + "attention.self.query.bias", p + "attention.self.key.bias",
+                                            p + "attention.self.value.bias"}, H, &ly.bqkv)) != SG_OK) return fail(rc);
+        if ((rc = upload_f16_cat(e, blob, {p + "attention.output.dense.weight"}, H, H, &ly.wo)) != SG_OK) return fail(rc);
+        if ((rc = upload_f32(e, blob, p + "attention.output.dense.bias", H, &ly.bo)) != SG_OK) return fail(rc);
+        if ((rc = upload_f32(e, blob, p + "attention.output.LayerNorm.weight", H, &ly.ln1_g)) != SG_OK) return fail(rc);
+        if ((rc = upload_f32(e, blob, p + "attention.output.LayerNorm.bias", H, &ly.ln1_b)) != SG_OK) return fail(rc);
+        if ((rc = upload_f16_cat(e, blob, {p + "intermediate.dense.weight"}, F, H, &ly.w1)) != SG_OK) return fail(rc);
+        if ((rc = upload_f32(e, blob, p + "intermediate.dense.bias", F, &ly.b1)) != SG_OK) return fail(rc);
+        if ((rc = upload_f16_cat(e, blob, {p + "output.dense.weight"}, H, F, &ly.w2)) != SG_OK) return fail(rc);
+        if ((rc = upload_f32(e, blob, p + "output.dense.bias", H, &ly.b2)) != SG_OK) return fail(rc);
+        if ((rc = upload_f32(e, blob, p + "output.LayerNorm.weight", H, &ly.ln2_g)) != SG_OK) return fail(rc);
+        if ((rc = upload_f32(e, blob, p + "output.LayerNorm.bias", H, &ly.ln2_b)) != SG_OK) return fail(rc);
+    }
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(SG_ERR_CUDA);
+    *out = e;
+    return SG_OK;
+}
+
+void sg_encoder_destroy(sg_encoder *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (void *p : e->allocs) cudaFree(p);
+    cudaFree(e->h0); cudaFree(e->h1); cudaFree(e->qkv); cudaFree(e->ctx); cudaFree(e->mid); cudaFree(e->hf32);
+    cudaFree(e->d_ids); cudaFree(e->d_mask); cudaFree(e->d_emb);
+    if (e->h_pinned) cudaFreeHost(e->h_pinned);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int sg_encoder_dim(const sg_encoder *e, uint32_t *dim_out)
+{
+    if (!e || !dim_out) return SG_ERR_INVALID;
+    *dim_out = e->hidden;
+    return SG_OK;
+}
+
+int sg_encoder_encode_device(sg_encoder *e, const int64_t *d_ids, const int64_t *d_mask, uint32_t b, uint32_t L,
+                             float *d_emb_out, void *cuda_stream)
+{
+    if (!e || (b && (!d_ids || !d_mask || !d_emb_out))) return SG_ERR_INVALID;
+    if (b == 0) return SG_OK;
+    if (L == 0 || L > e->max_pos || L > 512) {
+        set_error("sequence length %u outside 1..%u", L, e->max_pos < 512 ? e->max_pos : 512);
+        return SG_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> g(e->mu);
+    SG_CUDA_TRY(cudaSetDevice(e->device));
+    return encode_device_locked(e, d_ids, d_mask, b, L, d_emb_out, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int sg_encoder_encode(sg_encoder *e, const int64_t *ids, const int64_t *mask, uint32_t b, uint32_t L, float *emb_out)
+{
+    if (!e || (b && (!ids || !mask || !emb_out))) return SG_ERR_INVALID;
+    if (b == 0) return SG_OK;
+    if (L == 0 || L > e->max_pos || L > 512) {
+        set_error("sequence length %u outside 1..%u", L, e->max_pos < 512 ? e->max_pos : 512);
+        return SG_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> g(e->mu);
+    SG_CUDA_TRY(cudaSetDevice(e->device));
+    const size_t n = (size_t)b * L, ob = (size_t)b * e->hidden * 4;
+    if (n > e->cap_b) {
+        int rc;
+        if ((rc = regrow(e->d_ids, n)) != SG_OK) return rc;
+        if ((rc = regrow(e->d_mask, n)) != SG_OK) return rc;
+        if ((rc = regrow(e->d_emb, n * e->hidden)) != SG_OK) return rc;   // b <= n
+        e->cap_b = n;
+    }
+    const size_t need = 2 * n * 8 + ob;
+    if (need > e->pinned_cap) {
+        if (e->h_pinned) cudaFreeHost(e->h_pinned);
+        e->h_pinned = nullptr;
+        e->pinned_cap = 0;
+        SG_CUDA_TRY(cudaHostAlloc(&e->h_pinned, need, cudaHostAllocDefault));
+        e->pinned_cap = need;
+    }
+    uint8_t *hp = static_cast<uint8_t *>(e->h_pinned);
+    memcpy(hp, ids, n * 8);
+    memcpy(hp + n * 8, mask, n * 8);
+    SG_CUDA_TRY(cudaMemcpyAsync(e->d_ids, hp, n * 8, cudaMemcpyHostToDevice, e->stream));
+    SG_CUDA_TRY(cudaMemcpyAsync(e->d_mask, hp + n * 8, n * 8, cudaMemcpyHostToDevice, e->stream));
+    int rc = encode_device_locked(e, e->d_ids, e->d_mask, b, L, e->d_emb, e->stream);
+    if (rc != SG_OK) return rc;
+    SG_CUDA_TRY(cudaMemcpyAsync(hp + 2 * n * 8, e->d_emb, ob, cudaMemcpyDeviceToHost, e->stream));
+    SG_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    memcpy(emb_out, hp + 2 * n * 8, ob);
+    return SG_OK;
+}
+
+}  // extern "C"

@@ -27,6 +27,7 @@
 // HBM-bound: algorithmic bytes per sweep = n_rows * dim * 2; the MMA work per row is
 // 12 cycles against ~33 cycles of HBM time per row per SM.
 #include "sg_internal.h"
+#include "sg_tc.cuh"
 
 namespace sg {
 namespace {
@@ -37,122 +38,6 @@ constexpr uint32_t TC_KB = 64;          // fp16 elements per K-block (one 128B s
 constexpr uint32_t TC_STAGE_BYTES = TC_N * 128;   // 16 KB
 constexpr uint32_t TC_ACC_STAGES = 4;   // 4 x 128 = 512 TMEM columns
 constexpr uint32_t TC_THREADS = 256;
-
-// ---- tcgen05 wrappers ---------------------------------------------------------------------
-SG_DEVICE_INLINE void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-SG_DEVICE_INLINE void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-SG_DEVICE_INLINE void tmem_alloc(uint32_t smem_dst, uint32_t ncols)
-{
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-SG_DEVICE_INLINE void tmem_dealloc(uint32_t taddr, uint32_t ncols)
-{
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, f32 accumulate
-SG_DEVICE_INLINE void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrive on an mbarrier once all previously issued MMAs have completed
-SG_DEVICE_INLINE void umma_commit(uint32_t bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-SG_DEVICE_INLINE void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-SG_DEVICE_INLINE void tmem_ld1(uint32_t taddr, uint32_t &v)
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
-}
-SG_DEVICE_INLINE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4 in
-// bits [0,14), stride byte offset (8 rows x 128 B = 1024) >> 4 in [32,46), version 1 at bit 46,
-// layout type 2 (SWIZZLE_128B) in [61,64).  The leading byte offset is unused for this layout.
-SG_DEVICE_INLINE uint64_t make_sw128_desc(uint32_t smem_addr)
-{
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor: D=f32 (bits 4-5 = 1), A=B=f16 (0), both K-major, N>>3 at bit 17, M>>4 at bit 24
-__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) { return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24); }
-
-// ---- cluster / CTA-pair helpers ------------------------------------------------------------------
-SG_DEVICE_INLINE uint32_t cluster_ctarank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-SG_DEVICE_INLINE void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `local_addr` in CTA `rank` of the cluster
-SG_DEVICE_INLINE uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
-{
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-    return r;
-}
-SG_DEVICE_INLINE void mbar_arrive_cluster(uint32_t cluster_addr)
-{
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-SG_DEVICE_INLINE void tmem_alloc2(uint32_t smem_dst, uint32_t ncols)
-{
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-SG_DEVICE_INLINE void tmem_dealloc2(uint32_t taddr, uint32_t ncols)
-{
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-SG_DEVICE_INLINE void umma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrive on the barrier at the same offset in every CTA of `mask` once the pair's MMAs retire
-SG_DEVICE_INLINE void umma_commit_2cta(uint32_t bar, uint16_t mask)
-{
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(mask) : "memory");
-}
-// pair-mode TMA load: data lands in THIS CTA's shared memory, the bytes are credited to `leader_bar`
-SG_DEVICE_INLINE void tma_load_2d_2cta(uint32_t dst_smem, const CUtensorMap *tmap, uint32_t leader_bar, int32_t x, int32_t y)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
-        "[%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst_smem), "l"((uint64_t)tmap), "r"(leader_bar), "r"(x), "r"(y)
-        : "memory");
-}
 
 SG_DEVICE_INLINE uint32_t ld_relaxed_u32(const uint32_t *p)
 {
