@@ -193,6 +193,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    tc_peak_early = peaks()[1]
     sampler = None
     if rank == 0:
         try:
@@ -256,6 +257,65 @@ def main():
     barrier()
     b1_ms = max_over_ranks(e0.elapsed_time(e1)) / b1_steps
     b1_scan, _ = store.local.profile_read()
+    # ---------------- encoder (configs[4]): MiniLM-L6, random-init weights, 64-token queries ----------------
+    enc_res = None
+    if rank == 0 and os.environ.get("SG_BENCH_ENCODER", "1") == "1":
+        import tempfile
+        wpath = os.path.join(tempfile.gettempdir(), f"sg_minilm_random_{os.getpid()}.sgw")
+        sg.export_bert_weights(sg.random_minilm_state_dict(SEED), wpath, 6, 384, 12, 1536, 30522, 512)
+        enc = sg.GpuMiniLM(wpath, local_rank)
+        os.remove(wpath)
+        LQ = 64
+        rng = np.random.default_rng(SEED + 1)
+        ids_np = rng.integers(1000, 30522, (BATCH, LQ)).astype(np.int64)
+        ids_np[:, 0], ids_np[:, -1] = 101, 102
+        d_ids = torch.from_numpy(ids_np).to(dev)
+        d_mask = torch.ones((BATCH, LQ), dtype=torch.int64, device=dev)
+        d_emb = torch.empty((BATCH, DIM), dtype=torch.float32, device=dev)
+        cs = torch.cuda.current_stream().cuda_stream
+
+        def time_enc(b, reps):
+            for _ in range(3):
+                enc.encode_ids_device(d_ids.data_ptr(), d_mask.data_ptr(), b, LQ, d_emb.data_ptr(), cs)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                enc.encode_ids_device(d_ids.data_ptr(), d_mask.data_ptr(), b, LQ, d_emb.data_ptr(), cs)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+        ms1, msb = time_enc(1, 100), time_enc(BATCH, 20)
+        flops_tok = 6 * 2 * (4 * 384 * 384 + 2 * 384 * 1536) + 6 * 4 * LQ * 384
+        tf = flops_tok * BATCH * LQ / (msb * 1e-3) / 1e12
+        # end-to-end recall for one query: host ids -> H2D -> encoder -> exact scan of this rank's shard -> D2H
+        h_ids = torch.from_numpy(ids_np[:1]).pin_memory()
+        h_mask = torch.ones((1, LQ), dtype=torch.int64).pin_memory()
+        out_i = torch.empty((1, TOPK), dtype=torch.int32, device=dev)
+        out_d = torch.empty((1, TOPK), dtype=torch.float32, device=dev)
+        out_c = torch.empty(1, dtype=torch.int32, device=dev)
+        h_out = torch.empty((1, TOPK), dtype=torch.int32).pin_memory()
+
+        def recall_once():
+            d_ids[:1].copy_(h_ids, non_blocking=True)
+            d_mask[:1].copy_(h_mask, non_blocking=True)
+            enc.encode_ids_device(d_ids.data_ptr(), d_mask.data_ptr(), 1, LQ, d_emb.data_ptr(), cs)
+            store.local.search_device(d_emb.data_ptr(), 1, TOPK, out_i.data_ptr(), out_d.data_ptr(), out_c.data_ptr(), cs)
+            h_out.copy_(out_i, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        for _ in range(3):
+            recall_once()
+        t0 = time.perf_counter()
+        for _ in range(50):
+            recall_once()
+        rec_ms = (time.perf_counter() - t0) * 1e3 / 50
+        enc_res = dict(model="MiniLM-L6 architecture (6x384, 12 heads, FFN 1536), random-init weights, fp16 tensor-core GEMMs",
+                       tokens_per_query=LQ, encode_ms_batch1=ms1, encode_ms_batch256=msb,
+                       queries_per_s_batch256=BATCH / (msb * 1e-3),
+                       tensor=dict(achieved=tf, peak=tc_peak_early, unit="TFLOP/s", frac=tf / tc_peak_early),
+                       recall_e2e_batch1=dict(ms_per_query=rec_ms, rows=int(local_rows),
+                                              note="pinned host ids -> H2D -> encoder -> exact top-%d scan of this "
+                                                   "rank's shard -> D2H, one stream" % TOPK))
+        enc.close()
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
@@ -309,6 +369,7 @@ def main():
                     roofline=dict(bound="hbm", achieved=b1_achieved, peak=peak, unit="GB/s", frac=b1_achieved / peak,
                                   scan_ms=b1_scan_ms, kernel="scan_exact_kernel")),
         tensor_path=dict(zip(("queries", "exact_reruns"), store.local.tc_stats())),
+        encoder=enc_res,
         gpu_launches=int(launches), clocks=clocks)
     if cpu:
         line["cpu_baseline"] = dict(value=cpu["value"], unit=UNIT, cores=cpu["cores"], kind=cpu["kind"], sample=cpu["sample"])

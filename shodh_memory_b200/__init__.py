@@ -5,7 +5,7 @@ host-side mirror of the reference's VamanaIndex / relevance surface for tests an
 Importing the package loads lib/libshodh_gpu.so and fails loudly if it is missing."""
 from . import capi
 from .capi import SgError
-from .encoder import GpuMiniLM, export_bert_weights
+from .encoder import GpuMiniLM, export_bert_weights, random_minilm_state_dict
 from .relevance import fuse_topk
 from .vector_store import GpuVectorStore, merge_topk_device
 

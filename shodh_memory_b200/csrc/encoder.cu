@@ -49,7 +49,7 @@ SG_DEVICE_INLINE float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.
 
 // C tile = 128 rows x BN columns, one tile per CTA.  grid = (M_pad/128, N/BN).
 template <uint32_t BN, uint32_t EPI>
-__global__ void __launch_bounds__(G_THREADS, 1)
+__global__ void __launch_bounds__(G_THREADS, BN <= 128 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const GemmArgs g)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -574,7 +574,7 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
         if ((rc = encode_tmap(&t_w2, ly.w2, F, H, H / 2)) != SG_OK) return rc;
         GemmArgs g{};
         // QKV = h0 . Wqkv^T + b
-        g.K = H; g.N = 3 * H; g.stages = 4; g.bias = ly.bqkv; g.out = e->qkv;
+        g.K = H; g.N = 3 * H; g.stages = 3; g.bias = ly.bqkv; g.out = e->qkv;   // 96 KB: two CTAs per SM
         SG_CUDA_TRY((launch_gemm<128, EPI_BIAS>(t_h0, t_wqkv, g, m_tiles, st)));
         attention_kernel<<<b * e->heads, 128, att_smem, st>>>(e->qkv, d_mask, L, H, e->heads, e->ctx);
         count_launch();
@@ -585,7 +585,7 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
         SG_CUDA_TRY((launch_gemm<384, EPI_BIAS_RES_LN>(t_ctx, t_wo, g, m_tiles, st)));
         // mid = gelu(h1 . W1^T + b)
         g = GemmArgs{};
-        g.K = H; g.N = F; g.stages = 4; g.bias = ly.b1; g.out = e->mid;
+        g.K = H; g.N = F; g.stages = 3; g.bias = ly.b1; g.out = e->mid;
         SG_CUDA_TRY((launch_gemm<128, EPI_BIAS_GELU>(t_h1, t_w1, g, m_tiles, st)));
         // h0 = LN(mid . W2^T + b + h1)
         g = GemmArgs{};

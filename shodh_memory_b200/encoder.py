@@ -33,6 +33,26 @@ def export_bert_weights(state_dict, path: str, layers: int, hidden: int, heads: 
             f.write(a.tobytes())
 
 
+def random_minilm_state_dict(seed: int = 0, layers: int = 6, hidden: int = 384, ffn: int = 1536, vocab: int = 30522,
+                             max_pos: int = 512) -> dict:
+    """Seeded random weights with the MiniLM-L6 parameter names/shapes (no checkpoint is available offline)."""
+    rng = np.random.default_rng(seed)
+    def w(*shape, s=0.05):
+        return (rng.standard_normal(shape) * s).astype(np.float32)
+    sd = {"embeddings.word_embeddings.weight": w(vocab, hidden), "embeddings.position_embeddings.weight": w(max_pos, hidden),
+          "embeddings.token_type_embeddings.weight": w(2, hidden),
+          "embeddings.LayerNorm.weight": 1 + w(hidden, s=0.1), "embeddings.LayerNorm.bias": w(hidden)}
+    for l in range(layers):
+        p = f"encoder.layer.{l}."
+        for nm in ("attention.self.query", "attention.self.key", "attention.self.value", "attention.output.dense"):
+            sd[p + nm + ".weight"], sd[p + nm + ".bias"] = w(hidden, hidden, s=0.06), w(hidden)
+        sd[p + "intermediate.dense.weight"], sd[p + "intermediate.dense.bias"] = w(ffn, hidden, s=0.06), w(ffn)
+        sd[p + "output.dense.weight"], sd[p + "output.dense.bias"] = w(hidden, ffn, s=0.06), w(hidden)
+        for nm in ("attention.output.LayerNorm", "output.LayerNorm"):
+            sd[p + nm + ".weight"], sd[p + nm + ".bias"] = 1 + w(hidden, s=0.1), w(hidden)
+    return sd
+
+
 class GpuMiniLM:
     """`impl Embedder` on token ids: dimension(), encode_ids() (= encode / encode_batch after tokenising)."""
 

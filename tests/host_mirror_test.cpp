@@ -1,0 +1,63 @@
+// Exercises the C++ host mirror (shodh_memory_b200/host/shodh_gpu.hpp) like the reference's own unit
+// tests exercise VamanaIndex: vamana.rs:1697-1711 (5 vectors, top-1), retrieval.rs:2430-2438 (self
+// retrieval), similarity.rs:108-115 (k > candidates), vamana.rs:766-768 (empty -> Ok([])).
+// Built and run by tests/test_host_cpp.py (GPU) / compile-checked on CPU.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+#include "../shodh_memory_b200/host/shodh_gpu.hpp"
+
+#define REQUIRE(c) do { if (!(c)) { std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
+
+static std::vector<float> test_vector(size_t i, size_t dim)   // retrieval.rs:2430-2438
+{
+    std::vector<float> v(dim, 1.0f);
+    v[i % dim] += 0.5f * std::sqrt((float)dim);
+    float s = 0.0f;
+    for (float x : v) s += x * x;
+    float norm = std::sqrt(s);
+    for (float &x : v) x /= norm;
+    return v;
+}
+
+int main()
+{
+    try {
+        shodh::GpuVectorStore st(384, SG_DTYPE_F32, 0);
+        std::vector<float> q0 = test_vector(0, 384);
+        REQUIRE(st.search(q0, 5).empty());                        // empty index -> Ok(vec![])
+        const size_t n = 300;
+        for (size_t i = 0; i < n; ++i) REQUIRE(st.add_vector(test_vector(i, 384)) == i);   // dense sequential ids
+        REQUIRE(st.len() == n);
+        for (size_t i : {0u, 7u, 299u}) {
+            auto r = st.search(test_vector(i, 384), 5);
+            REQUIRE(r.size() == 5 && r[0].first == i);
+            REQUIRE(std::fabs(-r[0].second - 1.0f) < 1e-5f);
+            for (size_t j = 1; j < r.size(); ++j)                  // ascending (dist, id)
+                REQUIRE(r[j - 1].second < r[j].second || (r[j - 1].second == r[j].second && r[j - 1].first < r[j].first));
+        }
+        REQUIRE(st.mark_deleted(7) && !st.mark_deleted(100000) && st.is_deleted(7) && st.deleted_count() == 1);
+        REQUIRE(st.search(test_vector(7, 384), 3)[0].first != 7);
+        REQUIRE(st.search(q0, 1000).size() == n - 1);              // k > live rows
+        std::vector<float> batch;
+        for (size_t i = 0; i < 9; ++i) { auto v = test_vector(10 + i, 384); batch.insert(batch.end(), v.begin(), v.end()); }
+        auto rb = st.search_batch(batch, 9, 3);
+        for (size_t i = 0; i < 9; ++i) REQUIRE(rb[i][0].first == 10 + i);
+        bool threw = false;
+        try { st.add_vector(std::vector<float>(10, 0.0f)); } catch (const shodh::Error &e) { threw = e.code == SG_ERR_DIM; }
+        REQUIRE(threw);
+        // relevance ranking through the mirror (relevance.rs:1960-1979 pins)
+        float sem[2] = {0.9f, 0.1f}, ent[2] = {0.9f, 0.1f}, tag[2] = {0.9f, 0.1f}, imp[2] = {0.9f, 0.1f}, mom[2] = {0.9f, -0.9f}, gr[2] = {0.9f, 0.1f};
+        uint32_t acc[2] = {16, 0};
+        int64_t created[2] = {1000, 1000};
+        sg_candidate_feats f{sem, ent, tag, imp, mom, acc, gr, created};
+        auto ranked = shodh::fuse_and_rank(f, 2, 1000 + 100 * 3600);
+        REQUIRE(ranked.size() == 1 && ranked[0].candidate == 0 && ranked[0].score > 0.8f);
+        std::printf("HOST_MIRROR_OK\n");
+        return 0;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "exception: %s\n", e.what());
+        return 2;
+    }
+}
