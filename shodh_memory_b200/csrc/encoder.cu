@@ -127,46 +127,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(smem_u32(done_bar), 0);
         tc_fence_after();
         if constexpr (EPI == EPI_BIAS_RES_LN) {
-            // BN == N == hidden: the whole row is in this thread's TMEM lane.  Three passes over
-            // TMEM (mean, variance, normalise): cheap, and numerically the two-pass variance.
-            const __half *res = g.residual + (size_t)row * g.N;
-            float sum = 0.0f;
+            // BN == N == hidden: the whole row is in this thread's TMEM lane.  Pass 1: v = acc + bias +
+            // residual, accumulate sum and sum of squares (f32); pass 2: recompute v, normalise, store.
+            const uint4 *res4 = reinterpret_cast<const uint4 *>(g.residual + (size_t)row * g.N);   // 8 halfs each
+            const float4 *bias4 = reinterpret_cast<const float4 *>(g.bias);
+            const float4 *gam4 = reinterpret_cast<const float4 *>(g.gamma);
+            const float4 *bet4 = reinterpret_cast<const float4 *>(g.beta);
+            float sum = 0.0f, sq = 0.0f;
 #pragma unroll 1
             for (uint32_t c = 0; c < BN / 32; ++c) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + lane_base + c * 32, r);
+                uint4 rv[4];
+#pragma unroll
+                for (uint32_t q = 0; q < 4; ++q) rv[q] = res4[c * 4 + q];
                 tmem_ld_wait();
 #pragma unroll
-                for (uint32_t j = 0; j < 32; ++j)
-                    sum += __uint_as_float(r[j]) + g.bias[c * 32 + j] + __half2float(res[c * 32 + j]);
-            }
-            const float mean = sum / (float)BN;
-            float var = 0.0f;
-#pragma unroll 1
-            for (uint32_t c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + lane_base + c * 32, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (uint32_t j = 0; j < 32; ++j) {
-                    const float d = __uint_as_float(r[j]) + g.bias[c * 32 + j] + __half2float(res[c * 32 + j]) - mean;
-                    var += d * d;
+                for (uint32_t q = 0; q < 8; ++q) {
+                    const float4 bb = __ldg(bias4 + c * 8 + q);
+                    const __half2 *hp = reinterpret_cast<const __half2 *>(&rv[q >> 1]) + (q & 1) * 2;
+                    const float2 r01 = __half22float2(hp[0]), r23 = __half22float2(hp[1]);
+                    const float v0 = __uint_as_float(r[4 * q]) + bb.x + r01.x, v1 = __uint_as_float(r[4 * q + 1]) + bb.y + r01.y;
+                    const float v2 = __uint_as_float(r[4 * q + 2]) + bb.z + r23.x, v3 = __uint_as_float(r[4 * q + 3]) + bb.w + r23.y;
+                    sum += (v0 + v1) + (v2 + v3);
+                    sq += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
                 }
             }
-            const float rstd = rsqrtf(var / (float)BN + g.eps);
+            const float mean = sum / (float)BN;
+            const float var = fmaxf(sq / (float)BN - mean * mean, 0.0f);
+            const float rstd = rsqrtf(var + g.eps);
 #pragma unroll 1
             for (uint32_t c = 0; c < BN / 32; ++c) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + lane_base + c * 32, r);
+                uint4 rv[4];
+#pragma unroll
+                for (uint32_t q = 0; q < 4; ++q) rv[q] = res4[c * 4 + q];
                 tmem_ld_wait();
                 __align__(16) __half o[32];
 #pragma unroll
-                for (uint32_t j = 0; j < 32; ++j) {
-                    const uint32_t col = c * 32 + j;
-                    const float v = __uint_as_float(r[j]) + g.bias[col] + __half2float(res[col]);
-                    const float y = (v - mean) * rstd * g.gamma[col] + g.beta[col];
-                    o[j] = __float2half_rn(y);
-                    if (g.out_f32) g.out_f32[(size_t)row * g.N + col] = y;
+                for (uint32_t q = 0; q < 8; ++q) {
+                    const float4 bb = __ldg(bias4 + c * 8 + q), gg = __ldg(gam4 + c * 8 + q), be = __ldg(bet4 + c * 8 + q);
+                    const __half2 *hp = reinterpret_cast<const __half2 *>(&rv[q >> 1]) + (q & 1) * 2;
+                    const float2 r01 = __half22float2(hp[0]), r23 = __half22float2(hp[1]);
+                    float y[4];
+                    y[0] = (__uint_as_float(r[4 * q]) + bb.x + r01.x - mean) * rstd * gg.x + be.x;
+                    y[1] = (__uint_as_float(r[4 * q + 1]) + bb.y + r01.y - mean) * rstd * gg.y + be.y;
+                    y[2] = (__uint_as_float(r[4 * q + 2]) + bb.z + r23.x - mean) * rstd * gg.z + be.z;
+                    y[3] = (__uint_as_float(r[4 * q + 3]) + bb.w + r23.y - mean) * rstd * gg.w + be.w;
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j) o[4 * q + j] = __float2half_rn(y[j]);
+                    if (g.out_f32)
+                        *reinterpret_cast<float4 *>(g.out_f32 + (size_t)row * g.N + c * 32 + 4 * q) = make_float4(y[0], y[1], y[2], y[3]);
                 }
                 uint4 *dst = reinterpret_cast<uint4 *>(g.out + (size_t)row * g.N + c * 32);
 #pragma unroll
@@ -233,9 +245,11 @@ __global__ void embed_ln_kernel(const int64_t *__restrict__ ids, uint32_t T, uin
         out[(size_t)tok * H + d] = __float2half_rn((v[n] - mean) * rstd * gamma[d] + beta[d]);
 }
 
-// ---- attention: one CTA per (sequence, head); d = 32; keys/values of the head in shared memory ------
-// softmax(q.k/sqrt(d) + mask) . v with an online (running max) softmax; masked keys contribute
-// exp(-inf) = 0, exactly like the additive -inf mask of the reference graph.
+// ---- attention: one CTA per (sequence, head); d = 32; one WARP per query row -----------------------
+// scores: lane j handles keys j, j+32, ...; softmax statistics by warp shuffles; P.V: lane d owns output
+// dimension d and the probabilities are broadcast by shuffle.  Masked keys get exp(-inf) = 0, exactly
+// like the additive -inf mask of the reference graph.  K is held TRANSPOSED in shared memory
+// ([32][L+1] floats) so that the per-lane key reads are conflict-free; V as [L][32] floats.
 __global__ void __launch_bounds__(128)
 attention_kernel(const __half *__restrict__ qkv, const int64_t *__restrict__ mask, uint32_t L, uint32_t H,
                  uint32_t heads, __half *__restrict__ ctx)
@@ -243,53 +257,56 @@ attention_kernel(const __half *__restrict__ qkv, const int64_t *__restrict__ mas
     extern __shared__ __align__(16) uint8_t smem_raw[];
     constexpr uint32_t D = 32;
     const uint32_t b = blockIdx.x / heads, h = blockIdx.x % heads;
-    __half *ks = reinterpret_cast<__half *>(smem_raw);       // [L][32]
-    __half *vs = ks + (size_t)L * D;                        // [L][32]
-    uint8_t *ms = reinterpret_cast<uint8_t *>(vs + (size_t)L * D);
+    const uint32_t LP = L + 1;
+    float *kt = reinterpret_cast<float *>(smem_raw);          // [32][L+1]
+    float *vs = kt + (size_t)D * LP;                         // [L][32]
+    float *ps = vs + (size_t)L * D;                          // [4 warps][L] probabilities
+    uint8_t *ms = reinterpret_cast<uint8_t *>(ps + 4 * (size_t)L);
     const size_t row_stride = 3 * (size_t)H;
     const __half *base = qkv + (size_t)b * L * row_stride;
-    for (uint32_t i = threadIdx.x; i < L * 4; i += blockDim.x) {   // 4 x 16 B per row of 32 halfs
-        const uint32_t j = i >> 2, part = i & 3;
-        reinterpret_cast<uint4 *>(ks)[i] = *reinterpret_cast<const uint4 *>(base + j * row_stride + H + h * D + part * 8);
-        reinterpret_cast<uint4 *>(vs)[i] = *reinterpret_cast<const uint4 *>(base + j * row_stride + 2 * H + h * D + part * 8);
+    for (uint32_t i = threadIdx.x; i < L * D; i += blockDim.x) {
+        const uint32_t j = i >> 5, d = i & 31;
+        kt[(size_t)d * LP + j] = __half2float(base[j * row_stride + H + h * D + d]);
+        vs[i] = __half2float(base[j * row_stride + 2 * H + h * D + d]);
     }
     for (uint32_t j = threadIdx.x; j < L; j += blockDim.x) ms[j] = mask[(size_t)b * L + j] == 1 ? 1 : 0;
     __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float scale = 0.17677669529663687f;              // 1/sqrt(32)
-    for (uint32_t i = threadIdx.x; i < L; i += blockDim.x) {
-        float q[D];
-        const __half *qp = base + i * row_stride + h * D;
+    const float NEG_INF = -__uint_as_float(0x7F800000u);
+    float *pw = ps + (size_t)warp * L;
+    for (uint32_t i = warp; i < L; i += 4) {
+        const float qd = __half2float(base[i * row_stride + h * D + lane]) * scale;   // lane d holds q[d]
+        float mx = NEG_INF;
+        for (uint32_t j0 = 0; j0 < L; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            float sc = 0.0f;
 #pragma unroll
-        for (uint32_t d = 0; d < D; ++d) q[d] = __half2float(qp[d]) * scale;
-        float m = -__uint_as_float(0x7F800000u), l = 0.0f, acc[D];
-#pragma unroll
-        for (uint32_t d = 0; d < D; ++d) acc[d] = 0.0f;
-        for (uint32_t j = 0; j < L; ++j) {
-            if (!ms[j]) continue;
-            const __half2 *kp = reinterpret_cast<const __half2 *>(ks + (size_t)j * D);
-            float s = 0.0f;
-#pragma unroll
-            for (uint32_t d = 0; d < D / 2; ++d) {
-                const float2 kk = __half22float2(kp[d]);
-                s = fmaf(q[2 * d], kk.x, s);
-                s = fmaf(q[2 * d + 1], kk.y, s);
+            for (uint32_t d = 0; d < D; ++d) {
+                const float qv = __shfl_sync(0xFFFFFFFFu, qd, d);
+                if (j < L) sc = fmaf(qv, kt[(size_t)d * LP + j], sc);
             }
-            const float m_new = fmaxf(m, s);
-            const float corr = __expf(m - m_new), p = __expf(s - m_new);
-            l = l * corr + p;
-            const __half2 *vp = reinterpret_cast<const __half2 *>(vs + (size_t)j * D);
-#pragma unroll
-            for (uint32_t d = 0; d < D / 2; ++d) {
-                const float2 vv = __half22float2(vp[d]);
-                acc[2 * d] = acc[2 * d] * corr + p * vv.x;
-                acc[2 * d + 1] = acc[2 * d + 1] * corr + p * vv.y;
+            if (j < L) {
+                if (!ms[j]) sc = NEG_INF;
+                pw[j] = sc;
+                mx = fmaxf(mx, sc);
             }
-            m = m_new;
         }
-        const float inv = l > 0.0f ? 1.0f / l : 0.0f;
-        __half *op = ctx + ((size_t)b * L + i) * H + h * D;
-#pragma unroll
-        for (uint32_t d = 0; d < D; ++d) op[d] = __float2half_rn(acc[d] * inv);
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        float lsum = 0.0f;
+        __syncwarp();
+        for (uint32_t j = lane; j < L; j += 32) {
+            const float p = mx > NEG_INF ? __expf(pw[j] - mx) : 0.0f;
+            pw[j] = p;
+            lsum += p;
+        }
+        for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xFFFFFFFFu, lsum, o);
+        __syncwarp();
+        float acc = 0.0f;                                    // output dimension `lane`
+        for (uint32_t j = 0; j < L; ++j) acc = fmaf(pw[j], vs[(size_t)j * D + lane], acc);
+        const float inv = lsum > 0.0f ? 1.0f / lsum : 0.0f;
+        ctx[((size_t)b * L + i) * H + h * D + lane] = __float2half_rn(acc * inv);
+        __syncwarp();
     }
 }
 
@@ -562,7 +579,7 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
     if ((rc = encode_tmap(&t_h1, e->h1, H, T_pad, 128)) != SG_OK) return rc;
     if ((rc = encode_tmap(&t_ctx, e->ctx, H, T_pad, 128)) != SG_OK) return rc;
     if ((rc = encode_tmap(&t_mid, e->mid, F, T_pad, 128)) != SG_OK) return rc;
-    const size_t att_smem = (size_t)L * 32 * 2 * 2 + L;
+    const size_t att_smem = ((size_t)32 * (L + 1) + (size_t)L * 32 + 4 * (size_t)L) * 4 + L;
     if (att_smem > 48 * 1024)
         SG_CUDA_TRY(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
     for (uint32_t l = 0; l < e->layers; ++l) {
