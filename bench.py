@@ -51,14 +51,29 @@ def peaks():
 # reference arm / cpu_baseline: the oracle port of VamanaIndex::brute_force_search "as written"
 # (per-row clone + full sort, vamana.rs:1167-1188), one query per host thread.
 # ----------------------------------------------------------------------------------------------
-def cpu_reference(steps: int, warmup: int):
+def cpu_reference(steps: int, warmup: int, budget_s: float = 90.0):
+    """Times the oracle port of brute_force_search AS WRITTEN on all host threads.  The row sample is sized so
+    the whole (steps + warmup) run stays within ~budget_s: scan cost is linear in rows, and the reported
+    queries/s is scaled to the full corpus."""
     from oracle import oracle as o  # the ONE place bench.py executes oracle/ (cpu_baseline / --impl reference)
     threads = o.max_threads()
-    corpus = o.synth_corpus(SEED, 0, CPU_SAMPLE_ROWS, DIM, f16_round=True)
-    queries, _ = o.synth_queries(SEED, ROWS, max(threads, 1) * (steps + warmup), DIM)
-    scale = CPU_SAMPLE_ROWS / ROWS
+    rows = CPU_SAMPLE_ROWS
+    total = steps + warmup
+    # calibrate on 50k rows, then pick the sample size that fits the time budget
+    cal_rows = min(50_000, rows)
+    cal = o.synth_corpus(SEED, 0, cal_rows, DIM, f16_round=True)
+    calq, _ = o.synth_queries(SEED, ROWS, threads, DIM)
+    t0 = time.perf_counter()
+    o.brute_force_search_batch(cal, calq, TOPK, as_written=True, threads=threads)
+    per_row = (time.perf_counter() - t0) / cal_rows
+    fit = int(budget_s / total / max(per_row, 1e-12))
+    rows = max(20_000, min(rows, fit))
+    corpus = o.synth_corpus(SEED, 0, rows, DIM, f16_round=True)
+    queries, _ = o.synth_queries(SEED, ROWS, max(threads, 1) * total, DIM)
+    scale = rows / ROWS
     times = []
-    for s in range(steps + warmup):
+    used = threads
+    for s in range(total):
         q = queries[s * threads:(s + 1) * threads]
         t0 = time.perf_counter()
         _, _, _, used = o.brute_force_search_batch(corpus, q, TOPK, as_written=True, threads=threads)
@@ -68,7 +83,7 @@ def cpu_reference(steps: int, warmup: int):
     t = float(np.mean(times))
     qps_sample = threads / t
     return dict(value=qps_sample * scale, unit=UNIT, cores=int(used), kind="port",
-                sample=(f"{threads} queries/step (one per host thread) x {CPU_SAMPLE_ROWS} rows of the {ROWS}-row corpus, "
+                sample=(f"{threads} queries/step (one per host thread) x {rows} rows of the {ROWS}-row corpus, "
                         f"top-{TOPK}, reference as written (row clone + full sort); qps scaled by {scale:g} "
                         f"(scan cost is linear in rows)"),
                 ms_per_step=t * 1e3)
@@ -330,7 +345,7 @@ def main():
     b1_scan_ms = float(np.mean(b1_scan)) if len(b1_scan) else float("nan")
     b1_achieved = alg_bytes / (b1_scan_ms * 1e-3) / 1e9
 
-    cpu = cpu_reference(2, 1) if world == 1 else None
+    cpu = cpu_reference(2, 1, budget_s=12.0) if world == 1 else None
 
     # Which roofline binds the sweep?  One sweep must move alg_bytes from HBM AND (tensor path) do
     # 2*rows*dim*queries_per_sweep FLOP on the tensor pipe; at 256 queries per sweep the tensor time exceeds

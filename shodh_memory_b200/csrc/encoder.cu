@@ -310,6 +310,135 @@ attention_kernel(const __half *__restrict__ qkv, const int64_t *__restrict__ mas
     }
 }
 
+// ---- attention, L <= 128: register-blocked S = QK^T, softmax, O = PV in shared memory --------------
+// grid = (sequences * heads, ceil(L / 64)); 128 threads; each CTA owns a block of 64 query rows.
+// Phase A: every thread computes 4 rows x 4 (strided) key columns of S per micro-tile -- operands in
+// padded f32 shared memory, conflict-free; Phase B: one warp per row does the masked softmax;
+// Phase C: 4 rows x 4 (strided) output dims per thread.  ~4k instructions per thread with full ILP.
+__global__ void __launch_bounds__(128)
+attention_small_kernel(const __half *__restrict__ qkv, const int64_t *__restrict__ mask, uint32_t L, uint32_t H,
+                       uint32_t heads, __half *__restrict__ ctx)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    constexpr uint32_t D = 32, DP = 33, QB = 64;
+    const uint32_t b = blockIdx.x / heads, h = blockIdx.x % heads;
+    const uint32_t q0 = blockIdx.y * QB;
+    const uint32_t L4 = (L + 3) & ~3u, SP = L4 + 1, CS = L4 / 4;
+    float *Ks = reinterpret_cast<float *>(smem_raw);        // [L4][33]
+    float *Vs = Ks + (size_t)L4 * DP;                       // [L4][33]
+    float *Qs = Vs + (size_t)L4 * DP;                       // [64][33]
+    float *Ss = Qs + (size_t)QB * DP;                       // [64][L4+1]
+    const size_t row_stride = 3 * (size_t)H;
+    const __half *base = qkv + (size_t)b * L * row_stride;
+    const float NEG_INF = -__uint_as_float(0x7F800000u);
+    // loads: 16-byte pieces (8 halfs)
+    for (uint32_t i = threadIdx.x; i < L4 * 4; i += blockDim.x) {
+        const uint32_t j = i >> 2, part = i & 3;
+        uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+        if (j < L) {
+            kv = *reinterpret_cast<const uint4 *>(base + j * row_stride + H + h * D + part * 8);
+            vv = *reinterpret_cast<const uint4 *>(base + j * row_stride + 2 * H + h * D + part * 8);
+        }
+        const __half2 *kh = reinterpret_cast<const __half2 *>(&kv), *vh = reinterpret_cast<const __half2 *>(&vv);
+#pragma unroll
+        for (uint32_t e = 0; e < 4; ++e) {
+            const float2 kf = __half22float2(kh[e]), vf = __half22float2(vh[e]);
+            Ks[(size_t)j * DP + part * 8 + 2 * e] = kf.x; Ks[(size_t)j * DP + part * 8 + 2 * e + 1] = kf.y;
+            Vs[(size_t)j * DP + part * 8 + 2 * e] = vf.x; Vs[(size_t)j * DP + part * 8 + 2 * e + 1] = vf.y;
+        }
+    }
+    const float scale = 0.17677669529663687f;              // 1/sqrt(32)
+    for (uint32_t i = threadIdx.x; i < QB * 4; i += blockDim.x) {
+        const uint32_t r = i >> 2, part = i & 3;
+        uint4 qv = make_uint4(0, 0, 0, 0);
+        if (q0 + r < L) qv = *reinterpret_cast<const uint4 *>(base + (q0 + r) * row_stride + h * D + part * 8);
+        const __half2 *qh = reinterpret_cast<const __half2 *>(&qv);
+#pragma unroll
+        for (uint32_t e = 0; e < 4; ++e) {
+            const float2 qf = __half22float2(qh[e]);
+            Qs[(size_t)r * DP + part * 8 + 2 * e] = qf.x * scale; Qs[(size_t)r * DP + part * 8 + 2 * e + 1] = qf.y * scale;
+        }
+    }
+    __syncthreads();
+    // Phase A: S block [64][L4]
+    const uint32_t n_tiles = (QB / 4) * CS;
+    for (uint32_t tIdx = threadIdx.x; tIdx < n_tiles; tIdx += blockDim.x) {
+        const uint32_t ti = tIdx / CS, cj = tIdx - ti * CS;
+        float acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+#pragma unroll 8
+        for (uint32_t d = 0; d < D; ++d) {
+            float qv[4], kv[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) qv[r] = Qs[(size_t)(4 * ti + r) * DP + d];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) kv[c] = Ks[(size_t)(cj + c * CS) * DP + d];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(qv[r], kv[c], acc[r][c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t j = cj + c * CS;
+            const bool live = j < L && mask[(size_t)b * L + j] == 1;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) Ss[(size_t)(4 * ti + r) * SP + j] = live ? acc[r][c] : NEG_INF;
+        }
+    }
+    __syncthreads();
+    // Phase B: softmax, one warp per row
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t r = warp; r < QB; r += 4) {
+        float *srow = Ss + (size_t)r * SP;
+        float mx = NEG_INF;
+        for (uint32_t j = lane; j < L4; j += 32) mx = fmaxf(mx, srow[j]);
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        float sum = 0.0f;
+        for (uint32_t j = lane; j < L4; j += 32) {
+            const float p = mx > NEG_INF ? __expf(srow[j] - mx) : 0.0f;
+            srow[j] = p;
+            sum += p;
+        }
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+        const float inv = sum > 0.0f ? 1.0f / sum : 0.0f;
+        for (uint32_t j = lane; j < L4; j += 32) srow[j] *= inv;
+    }
+    __syncthreads();
+    // Phase C: O block [64][32] = P . V ; thread -> 4 rows x dims {dj, dj+8, dj+16, dj+24}
+    {
+        const uint32_t ti = threadIdx.x >> 3, dj = threadIdx.x & 7;
+        float acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+#pragma unroll 4
+        for (uint32_t j = 0; j < L4; ++j) {
+            float pv[4], vv[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) pv[r] = Ss[(size_t)(4 * ti + r) * SP + j];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) vv[c] = Vs[(size_t)j * DP + dj + 8 * c];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(pv[r], vv[c], acc[r][c]);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t i = q0 + 4 * ti + r;
+            if (i < L) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) ctx[((size_t)b * L + i) * H + h * D + dj + 8 * c] = __float2half_rn(acc[r][c]);
+            }
+        }
+    }
+}
+
 // ---- masked mean-pool + finalize (reference minilm.rs:959-978, :846-878) -----------------------------
 // pooled[d] += h[s][d] for s ascending over mask==1; /= mask_sum; NaN/Inf -> 0; norm = sqrt(sum x^2)
 // left-to-right; divide by norm if norm > f32::EPSILON.  One CTA per sequence, one thread per dim.
@@ -593,7 +722,15 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
         // QKV = h0 . Wqkv^T + b
         g.K = H; g.N = 3 * H; g.stages = 3; g.bias = ly.bqkv; g.out = e->qkv;   // 96 KB: two CTAs per SM
         SG_CUDA_TRY((launch_gemm<128, EPI_BIAS>(t_h0, t_wqkv, g, m_tiles, st)));
-        attention_kernel<<<b * e->heads, 128, att_smem, st>>>(e->qkv, d_mask, L, H, e->heads, e->ctx);
+        if (L <= 128) {
+            const uint32_t L4 = (L + 3) & ~3u;
+            const size_t sm = ((size_t)2 * L4 * 33 + 64 * 33 + (size_t)64 * (L4 + 1)) * 4;
+            if (sm > 48 * 1024)
+                SG_CUDA_TRY(cudaFuncSetAttribute(attention_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            attention_small_kernel<<<dim3(b * e->heads, (L + 63) / 64), 128, sm, st>>>(e->qkv, d_mask, L, H, e->heads, e->ctx);
+        } else {
+            attention_kernel<<<b * e->heads, 128, att_smem, st>>>(e->qkv, d_mask, L, H, e->heads, e->ctx);
+        }
         count_launch();
         // h1 = LN(ctx . Wo^T + b + h0)
         g = GemmArgs{};
@@ -610,7 +747,7 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
         g.eps = e->eps; g.out = e->h0; g.out_f32 = (l + 1 == e->layers) ? e->hf32 : nullptr;
         SG_CUDA_TRY((launch_gemm<384, EPI_BIAS_RES_LN>(t_mid, t_w2, g, m_tiles, st)));
     }
-    pool_norm_kernel<<<b, 128, H * 4, st>>>(e->hf32, d_mask, L, H, d_out);
+    pool_norm_kernel<<<b, 384, H * 4, st>>>(e->hf32, d_mask, L, H, d_out);
     count_launch();
     SG_CUDA_TRY(cudaGetLastError());
     return SG_OK;
