@@ -176,7 +176,7 @@ def main():
     import shodh_memory_b200 as sg
     dev = torch.device("cuda", local_rank)
 
-    store = sg.ShardedGpuStore(ROWS, DIM, "f16", rank, world, local_rank)
+    store = sg.ShardedGpuStore(ROWS, DIM, "f16", rank, world, local_rank, exchange=os.environ.get("SG_BENCH_EXCHANGE", "auto"))
     store.fill_synthetic(SEED)
     local_rows = store.hi - store.lo
 
@@ -375,7 +375,9 @@ def main():
         config=dict(workload=f"{ROWS}x{DIM} fp16 corpus resident in HBM, batch-{BATCH} f32 queries, exact top-{TOPK} "
                              f"(dist=-dot in the reference's summation order; ids bit-identical to the CPU path)",
                     rows=ROWS, dim=DIM, batch=BATCH, k=TOPK, corpus_dtype="f16",
-                    parallelism=f"row-shard x{world}" + (", 1 NCCL all-gather of per-shard top-k + merge" if world > 1 else ""),
+                    parallelism=f"row-shard x{world}" + (
+                        "" if world == 1 else (", fused P2P push + merge kernel over NVLink peer memory" if store.exchange_mode == "p2p"
+                                                else ", 1 NCCL all-gather of per-shard top-k + merge kernel")),
                     l2="per-GPU shard %.2f GB >> 126 MB L2: every sweep streams from HBM, no flush needed" % (alg_bytes / 1e9)),
         roofline=roofline,
         e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=BATCH * DIM * 4,

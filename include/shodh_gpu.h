@@ -140,6 +140,18 @@ SG_API int sg_merge_topk_device_strided(int device, const uint32_t *d_ids, const
                                         uint64_t query_stride, uint32_t *d_ids_out, float *d_dist_out,
                                         uint32_t *d_counts_out, void *cuda_stream);
 
+/* Fused exchange + merge over NVLink peer memory (the product path for N > 1; the NCCL all-gather +
+ * sg_merge_topk_device_strided pair is the baseline it replaces).  peer_buffers[r] = device address of
+ * rank r's symmetric buffer of sg_exchange_buffer_words(world,b,k) 32-bit words, zero-initialised once and
+ * mapped on every rank (e.g. torch symmetric memory).  Every rank calls this with the same (b, k) and an
+ * epoch that increases by 1 per call (>= 1): the kernel pushes this rank's lists into every peer, signals
+ * per (rank, query) flags, waits for the peers' flags and merges -- no collective launch, no barrier. */
+SG_API uint64_t sg_exchange_buffer_words(uint32_t world, uint32_t b, uint32_t k);
+SG_API int sg_exchange_merge_topk_device(int device, const uint64_t *peer_buffers, uint32_t rank, uint32_t world,
+                                         uint32_t epoch, const uint32_t *d_ids, const float *d_dist, uint32_t b,
+                                         uint32_t k, uint32_t *d_ids_out, float *d_dist_out, uint32_t *d_counts_out,
+                                         void *cuda_stream);
+
 /* CUDA-event timing of the scan kernel(s) inside each search (bench.py roofline): with
  * profiling on, every search records an event pair around its sweep launches on the stream
  * it runs on (no synchronisation).  sg_store_profile_read waits for the last recorded

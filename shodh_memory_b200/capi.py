@@ -90,6 +90,10 @@ def lib() -> C.CDLL:
     L.sg_merge_topk_device.argtypes = [C.c_int, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
     L.sg_merge_topk_device_strided.argtypes = [C.c_int, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
                                                C.c_uint64, vp, vp, vp, vp]
+    L.sg_exchange_buffer_words.restype = C.c_uint64
+    L.sg_exchange_buffer_words.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+    L.sg_exchange_merge_topk_device.argtypes = [C.c_int, u64p, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32,
+                                                C.c_uint32, vp, vp, vp, vp]
     L.sg_store_tc_stats.argtypes = [vp, u64p, u64p]
     L.sg_store_profile_read.argtypes = [vp, f32p, C.c_uint32, u32p, u32p]
     i64p = C.POINTER(C.c_int64)

@@ -15,6 +15,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import capi
 from .vector_store import GpuVectorStore, merge_topk_device
 
 
@@ -38,14 +39,57 @@ def exchange(local_pack: torch.Tensor, world: int, group=None) -> torch.Tensor:
     return out.view((world,) + tuple(local_pack.shape))
 
 
+class PeerExchange:
+    """Symmetric (peer-mapped) buffers for the fused exchange+merge kernel, one per (b, k)."""
+
+    def __init__(self, rank: int, world: int, device: int, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.symm_mem, self.rank, self.world, self.device = symm_mem, rank, world, device
+        self.group = group if group is not None else dist.group.WORLD
+        self._bufs = {}
+
+    def get(self, b: int, k: int):
+        key = (b, k)
+        if key not in self._bufs:
+            import ctypes as C
+            words = int(capi.lib().sg_exchange_buffer_words(self.world, b, k))
+            t = self.symm_mem.empty(words, dtype=torch.int32, device=torch.device("cuda", self.device))
+            hdl = self.symm_mem.rendezvous(t, self.group)
+            t.zero_()
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)               # every rank's flags are zero before anyone pushes
+            ptrs = (C.c_uint64 * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+            self._bufs[key] = dict(t=t, hdl=hdl, ptrs=ptrs, epoch=0)
+        return self._bufs[key]
+
+
 class ShardedGpuStore:
     def __init__(self, n_total: int, dim: int = 384, dtype: str = "f16", rank: int = 0, world: int = 1,
-                 device: int = 0, group=None):
+                 device: int = 0, group=None, exchange: str = "auto"):
+        """exchange: "p2p" = fused push+merge kernel over peer memory, "nccl" = all-gather + merge kernel
+        (the baseline), "auto" = p2p when torch symmetric memory can be set up, else nccl."""
         self.n_total, self.dim, self.rank, self.world, self.device, self.group = n_total, dim, rank, world, device, group
         self.lo, self.hi = shard_range(n_total, rank, world)
         self.local = GpuVectorStore(dim, dtype, device)
         self.local.set_id_base(self.lo)
         self._bufs = {}
+        self.peer = None
+        self.exchange_mode = "nccl"
+        if world > 1 and exchange in ("auto", "p2p") and world <= 8:
+            try:
+                self.peer = PeerExchange(rank, world, device, group)
+                self.peer.get(1, 1)                      # probe: allocation + rendezvous must work on every rank
+                ok = torch.ones(1, device=torch.device("cuda", device))
+            except Exception as e:                       # noqa: BLE001 - any failure means "no peer mapping here"
+                if exchange == "p2p":
+                    raise
+                self.peer = None
+                ok = torch.zeros(1, device=torch.device("cuda", device))
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)   # all ranks must agree on the mode
+            if ok.item() > 0 and self.peer is not None:
+                self.exchange_mode = "p2p"
+            else:
+                self.peer = None
 
     def fill_synthetic(self, seed: int) -> None:
         self.local.reserve(self.hi - self.lo)
@@ -78,6 +122,13 @@ class ShardedGpuStore:
                                  bufs["cnt"].data_ptr(), stream)
         if self.world == 1:
             return pack[0], pack[1].view(torch.float32), bufs["cnt"]
+        if self.peer is not None:
+            x = self.peer.get(b, k)
+            x["epoch"] += 1
+            capi.check(capi.lib().sg_exchange_merge_topk_device(
+                self.device, x["ptrs"], self.rank, self.world, x["epoch"], pack[0].data_ptr(), pack[1].data_ptr(), b, k,
+                bufs["out_ids"].data_ptr(), bufs["out_dist"].data_ptr(), bufs["out_cnt"].data_ptr(), stream))
+            return bufs["out_ids"], bufs["out_dist"], bufs["out_cnt"]
         gathered = exchange(pack, self.world, self.group)
         ls, qs, doff = gathered_strides(b, k)
         base = gathered.data_ptr()

@@ -18,12 +18,14 @@ torch.cuda.set_device(rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
 import shodh_memory_b200 as sg
 N, B, K, SEED = 300_000, 48, 10, 23821
-st = sg.ShardedGpuStore(N, 384, "f16", rank, world, rank)
+mode = os.environ.get("SG_TEST_EXCHANGE", "p2p")
+st = sg.ShardedGpuStore(N, 384, "f16", rank, world, rank, exchange=mode)
+assert st.exchange_mode == mode, st.exchange_mode
 st.fill_synthetic(SEED)
 g = torch.Generator().manual_seed(5)
 q = torch.nn.functional.normalize(torch.randn(B, 384, generator=g), dim=1)
 dq = q.cuda()
-for b, k in ((B, K), (1, 100), (3, 10)):
+for b, k in ((B, K), (1, 100), (3, 10), (B, K), (B, K)):     # repeats exercise the epoch / double buffering
     ids, dst, cnt = st.search_device(dq[:b], k)
     torch.cuda.synchronize()
     if rank == 0:
@@ -45,13 +47,15 @@ dist.destroy_process_group()
 '''
 
 
-def test_two_gpu_sharded_search_equals_single_store(tmp_path):
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+def test_two_gpu_sharded_search_equals_single_store(tmp_path, mode):
+    """p2p = fused push + merge kernel over NVLink peer memory; nccl = all-gather + merge (baseline)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, SG_ROOT=ROOT)
+    env = dict(os.environ, SG_ROOT=ROOT, SG_TEST_EXCHANGE=mode)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29571", str(script)],
                          capture_output=True, text=True, env=env, timeout=600)
