@@ -530,11 +530,11 @@ finalize_tc_kernel(const FinalizeArgs f)
     block_bitonic_sort(keys, MH);
     const uint64_t T0 = L >= f.kk ? keys[f.kk - 1] : KEY_SENTINEL;
     __syncthreads();
-    // (2) gather every entry with key <= T0 (lists are sorted: a prefix of each)
-    for (uint32_t i = threadIdx.x; i < L; i += blockDim.x) {
-        for (uint32_t j = 0; j < f.kk; ++j) {
-            const uint64_t key = ql[(size_t)i * 32 + j];
-            if (key == KEY_SENTINEL || key > T0) break;
+    // (2) gather every entry with key <= T0 -- all threads, coalesced over the [L][32] list block
+    for (uint32_t e = threadIdx.x; e < L * 32; e += blockDim.x) {
+        if ((e & 31) >= f.kk) continue;
+        const uint64_t key = ql[e];
+        if (key != KEY_SENTINEL && key <= T0) {
             const uint32_t slot = atomicAdd(&s_n, 1u);
             if (slot < TC_CAND_CAP) keys[slot] = key;
         }
@@ -553,11 +553,21 @@ finalize_tc_kernel(const FinalizeArgs f)
     const bool dropped_any = (f.n_live > kk);
     const float weakest_approx_sim = kk ? -key32_to_dist((uint32_t)(keys[kk - 1] >> 32)) : 0.0f;
     __syncthreads();
-    // exact re-score: one thread per candidate (sequential chain, like the reference)
+    // exact re-score: stage the kk candidate rows in shared memory (coalesced), then one thread per
+    // candidate walks the reference's sequential chain.  Row pitch dim/2 + 1 words: conflict-free.
+    extern __shared__ __align__(16) uint8_t rows_raw[];
+    uint32_t *rows_s = reinterpret_cast<uint32_t *>(rows_raw);
+    const uint32_t pitch = f.dim / 2 + 1;
+    for (uint32_t c = 0; c < kk; ++c) {
+        const uint32_t row = (uint32_t)(keys[c] & 0xFFFFFFFFu);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(reinterpret_cast<const __half *>(f.rows) + (size_t)row * f.dim);
+        for (uint32_t w = threadIdx.x; w < f.dim / 2; w += blockDim.x) rows_s[(size_t)c * pitch + w] = src[w];
+    }
+    __syncthreads();
     uint64_t exact_key = KEY_SENTINEL;
     if (threadIdx.x < kk) {
         const uint32_t row = (uint32_t)(keys[threadIdx.x] & 0xFFFFFFFFu);
-        const __half *rp = reinterpret_cast<const __half *>(f.rows) + (size_t)row * f.dim;
+        const __half *rp = reinterpret_cast<const __half *>(rows_s + (size_t)threadIdx.x * pitch);
         float dot = f.order == SG_ORDER_AVX2 ? exact_dot<SG_ORDER_AVX2>(q_s, rp, f.dim)
                                              : exact_dot<SG_ORDER_SCALAR>(q_s, rp, f.dim);
         exact_key = make_key(order_key32(neg_dot_to_dist(dot)), row);
@@ -645,7 +655,12 @@ cudaError_t launch_tau_init(const float *d_maxima, uint32_t b_pad, uint32_t n_ct
 
 cudaError_t launch_finalize_tc(const FinalizeArgs &f, uint32_t b, cudaStream_t st)
 {
-    finalize_tc_kernel<<<b, 256, 0, st>>>(f);
+    const size_t smem = (size_t)f.kk * (f.dim / 2 + 1) * 4;
+    if (smem > 32 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(finalize_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    finalize_tc_kernel<<<b, 256, smem, st>>>(f);
     count_launch();
     return cudaGetLastError();
 }

@@ -32,6 +32,58 @@ merge_kernel(const uint64_t *__restrict__ lists, const uint32_t *__restrict__ id
     const size_t base = (size_t)q * n_per_query_total + first;
 
     uint32_t kept = 0, pos = 0;
+    // Fast path for SORTED lists of k slots each (every producer in this library writes them sorted):
+    // take the first c = ceil(k / n_lists) entries of every list; the k-th smallest of those, T0, has at
+    // least k entries at or below it, so the global top-k all satisfy key <= T0.  Filter everything by T0
+    // (typically ~k..2k survivors) and sort only the survivors.  Falls through to the chunked bitonic
+    // path if the survivors do not fit (pathological inputs).
+    const uint32_t n_lists_here = n_per_query / k;
+    __shared__ uint32_t s_surv;
+    __shared__ uint64_t s_T0;
+    if (n_lists_here >= 2 && n_lists_here * k == n_per_query && n_per_query > 2 * k) {
+        const uint32_t c = (k + n_lists_here - 1) / n_lists_here;
+        const uint32_t nh = c * n_lists_here;                       // <= k + n_lists
+        if (nh <= SORT_MAX) {
+            auto load_key = [&](uint32_t e) -> uint64_t {
+                if constexpr (PAIRS) {
+                    const uint32_t ee = first + e, l = ee / k, j = ee - l * k;
+                    const size_t at = (size_t)l * list_stride + (size_t)q * query_stride + j;
+                    const uint32_t id = ids_in[at];
+                    return (id == 0xFFFFFFFFu) ? KEY_SENTINEL : make_key(order_key32(dist_in[at]), id);
+                } else {
+                    return lists[base + e];
+                }
+            };
+            const uint32_t MH = next_pow2(nh < 2 ? 2 : nh);
+            for (uint32_t i = threadIdx.x; i < MH; i += blockDim.x)
+                buf[i] = i < nh ? load_key((i / c) * k + (i % c)) : KEY_SENTINEL;
+            if (threadIdx.x == 0) s_surv = 0;
+            __syncthreads();
+            block_bitonic_sort(buf, MH);
+            if (threadIdx.x == 0) s_T0 = buf[k - 1];
+            __syncthreads();
+            const uint64_t T0 = s_T0;
+            __syncthreads();
+            for (uint32_t e = threadIdx.x; e < n_per_query; e += blockDim.x) {
+                const uint64_t key = load_key(e);
+                if (key != KEY_SENTINEL && key <= T0) {
+                    const uint32_t slot = atomicAdd(&s_surv, 1u);
+                    if (slot < SORT_MAX) buf[slot] = key;
+                }
+            }
+            __syncthreads();
+            const uint32_t ns = s_surv;
+            if (ns <= SORT_MAX) {
+                const uint32_t M = next_pow2(ns < 2 ? 2 : ns);
+                for (uint32_t i = ns + threadIdx.x; i < M; i += blockDim.x) buf[i] = KEY_SENTINEL;
+                __syncthreads();
+                block_bitonic_sort(buf, M);
+                kept = ns < k ? ns : k;
+                pos = n_per_query;                                   // done: skip the chunked path
+            }
+            __syncthreads();
+        }
+    }
     while (pos < n_per_query) {
         uint32_t take = n_per_query - pos;
         if (take > SORT_MAX - kept) take = SORT_MAX - kept;
@@ -90,7 +142,7 @@ cudaError_t launch(const uint64_t *lists, const uint32_t *ids_in, const float *d
 {
     if (b == 0) return cudaSuccess;
     const uint32_t per_cta = n_groups > 1 ? group_keys : n_per_query;
-    uint32_t need = per_cta < SORT_MAX ? next_pow2(per_cta < 2 ? 2 : per_cta) : SORT_MAX;
+    uint32_t need = per_cta < SORT_MAX ? next_pow2(per_cta < 2 ? 2 : per_cta) : SORT_MAX;   // survivors <= per_cta
     if (need < k) need = next_pow2(k);
     size_t smem = (size_t)need * 8;
     uint32_t threads = need / 2 < 1024 ? (need / 2 < 32 ? 32 : need / 2) : 1024;
@@ -108,6 +160,9 @@ cudaError_t launch(const uint64_t *lists, const uint32_t *ids_in, const float *d
 // how many first-level groups a (n_lists x k)-key merge is split into (1 = single level)
 uint32_t merge_groups(uint32_t n_lists, uint32_t k)
 {
+    // with the sorted-list threshold path one CTA per query handles every shape this library produces
+    // (first ceil(k/n_lists) entries of each list <= 8192 keys); keep the two-level split only beyond that
+    if ((uint64_t)((k + (n_lists ? n_lists : 1) - 1) / (n_lists ? n_lists : 1)) * n_lists <= 8192) return 1;
     if ((uint64_t)n_lists * k <= 4096) return 1;
     uint32_t lists_per_group = 2048 / k ? 2048 / k : 1;
     if (lists_per_group < 2) lists_per_group = 2;
