@@ -71,10 +71,14 @@ scan_exact_kernel(const __grid_constant__ CUtensorMap tmap, const ScanArgs a)
     uint32_t *cnt_s = reinterpret_cast<uint32_t *>(cand + (size_t)W * QB * C);    // [W][QB]
     uint64_t *bars = reinterpret_cast<uint64_t *>(cnt_s + ((W * QB + 1) & ~1u));  // [W][ring]
 
-    for (uint32_t i = threadIdx.x; i < (uint32_t)QB * dim; i += blockDim.x) {
-        uint32_t q = i / dim;
-        q_s[i] = (q < a.nq) ? a.queries[i] : 0.0f;
+    // "flagged" mode (device-side conditional re-run of uncertified tensor-path queries): the number
+    // of queries and their indices live in device memory; with zero flagged queries every CTA exits here.
+    uint32_t n_total = a.nq;
+    if (a.flag_count) {
+        n_total = *a.flag_count;
+        if (n_total == 0) return;
     }
+    const uint32_t n_groups = a.flag_count ? (n_total + QB - 1) / QB : 1;
     const uint32_t my_bars = smem_u32(bars + (size_t)warp * ring);
     const uint32_t my_ring = smem_u32(ring_base + (size_t)warp * ring * BOX_BYTES);
     if (lane == 0) {
@@ -92,10 +96,23 @@ scan_exact_kernel(const __grid_constant__ CUtensorMap tmap, const ScanArgs a)
     const uint64_t my_boxes = my_tiles * nbox;
     const int32_t box_elems = F16 ? 64 : 32;
 
+    uint32_t slot = 0, phase = 0, issue_slot = 0;          // ring position: carried across groups
+    for (uint32_t grp = 0; grp < n_groups; ++grp) {
+    const uint32_t nq_grp = a.flag_count ? (n_total - grp * QB < (uint32_t)QB ? n_total - grp * QB : (uint32_t)QB) : a.nq;
+    for (uint32_t i = threadIdx.x; i < (uint32_t)QB * dim; i += blockDim.x) {
+        const uint32_t q = i / dim, d = i - q * dim;
+        float v = 0.0f;
+        if (q < nq_grp) {
+            const uint32_t qi = a.flag_list ? a.flag_list[grp * QB + q] : q;
+            v = a.queries[(size_t)qi * dim + d];
+        }
+        q_s[i] = v;
+    }
+    __syncthreads();
     // producer state (lane 0 only uses it, but keep it warp-uniform)
     uint64_t issued = 0;
     uint64_t issue_tile = gw;
-    uint32_t issue_j = 0, issue_slot = 0;
+    uint32_t issue_j = 0;
     auto issue_one = [&]() {
         if (lane == 0) {
             uint32_t bar = my_bars + 8 * issue_slot;
@@ -123,7 +140,6 @@ scan_exact_kernel(const __grid_constant__ CUtensorMap tmap, const ScanArgs a)
     }
     uint64_t *my_cand = cand + (size_t)warp * QB * C;
 
-    uint32_t slot = 0, phase = 0;
     const uint32_t sw = (lane & 7) << 4;  // 128B-swizzle XOR term for this lane's row
 
     for (uint64_t it = 0; it < my_tiles; ++it) {
@@ -228,7 +244,7 @@ scan_exact_kernel(const __grid_constant__ CUtensorMap tmap, const ScanArgs a)
             const uint32_t key32 = order_key32(neg_dot_to_dist(dot));
             uint64_t *buf = my_cand + (size_t)q * C;
             if (tk.cnt[q] + 32 > C) compact(buf, tk.cnt[q], tk.tau[q], a.k, lane);
-            const bool hit = live && (q < (int)a.nq) && key32 <= tk.tau[q];
+            const bool hit = live && (q < (int)nq_grp) && key32 <= tk.tau[q];
             const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
             if (m) {
                 if (hit) buf[tk.cnt[q] + __popc(m & ((1u << lane) - 1))] = make_key(key32, (uint32_t)row);
@@ -249,7 +265,7 @@ scan_exact_kernel(const __grid_constant__ CUtensorMap tmap, const ScanArgs a)
     uint64_t *mbuf = reinterpret_cast<uint64_t *>(ring_base);
     const uint32_t k = a.k;
     const uint32_t M = next_pow2(W * k < 2 ? 2 : W * k);
-    for (uint32_t q = 0; q < a.nq; ++q) {
+    for (uint32_t q = 0; q < nq_grp; ++q) {
         for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) {
             uint32_t w = i / k, r = i - w * k;
             uint64_t key = KEY_SENTINEL;
@@ -258,10 +274,11 @@ scan_exact_kernel(const __grid_constant__ CUtensorMap tmap, const ScanArgs a)
         }
         __syncthreads();
         block_bitonic_sort(mbuf, M);
-        uint64_t *out = a.out_lists + ((size_t)q * gridDim.x + blockIdx.x) * k;
+        uint64_t *out = a.out_lists + ((size_t)(grp * QB + q) * gridDim.x + blockIdx.x) * k;
         for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) out[i] = mbuf[i];
         __syncthreads();
     }
+    }  // group loop
 }
 
 template <int QB, bool F16, int ORDER>

@@ -600,7 +600,11 @@ finalize_tc_kernel(const FinalizeArgs f)
     if (threadIdx.x == 0) {
         f.counts_out[q] = out_n;
         f.flags[q] = s_flag;
-        if (s_flag) atomicAdd(f.n_flagged, 1u);
+        if (s_flag) {
+            const uint32_t slot = atomicAdd(f.n_flagged, 1u);   // arrival order is irrelevant: slots are independent
+            f.flag_list[slot] = q;
+            atomicAdd(f.flag_total, 1ull);
+        }
     }
 }
 

@@ -21,11 +21,14 @@ merge_kernel(const uint64_t *__restrict__ lists, const uint32_t *__restrict__ id
              const float *__restrict__ dist_in, uint32_t n_per_query_total, uint32_t group_keys, uint32_t n_groups,
              uint32_t k, uint32_t id_base, uint64_t list_stride, uint64_t query_stride,
              uint64_t *__restrict__ keys_out, uint32_t *__restrict__ ids_out, float *__restrict__ dist_out,
-             uint32_t *__restrict__ counts)
+             uint32_t *__restrict__ counts, const uint32_t *__restrict__ slot_count,
+             const uint32_t *__restrict__ slot_to_query)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint64_t *buf = reinterpret_cast<uint64_t *>(smem_raw);
+    if (slot_count && blockIdx.x >= *slot_count) return;          // flagged form: nothing to do for this slot
     const uint32_t q = blockIdx.x / n_groups, grp = blockIdx.x - q * n_groups;
+    const uint32_t q_out = slot_to_query ? slot_to_query[q] : q;  // where the result goes
     const uint32_t first = grp * group_keys;
     const uint32_t n_per_query = first >= n_per_query_total ? 0
                                  : (n_per_query_total - first < group_keys ? n_per_query_total - first : group_keys);
@@ -120,8 +123,8 @@ merge_kernel(const uint64_t *__restrict__ lists, const uint32_t *__restrict__ id
     for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
         uint64_t key = i < kept ? buf[i] : KEY_SENTINEL;
         bool valid = key != KEY_SENTINEL;
-        ids_out[(size_t)q * k + i] = valid ? (uint32_t)(key & 0xFFFFFFFFu) + id_base : 0xFFFFFFFFu;
-        dist_out[(size_t)q * k + i] = valid ? key32_to_dist((uint32_t)(key >> 32)) : __uint_as_float(0x7F800000u);
+        ids_out[(size_t)q_out * k + i] = valid ? (uint32_t)(key & 0xFFFFFFFFu) + id_base : 0xFFFFFFFFu;
+        dist_out[(size_t)q_out * k + i] = valid ? key32_to_dist((uint32_t)(key >> 32)) : __uint_as_float(0x7F800000u);
         local += valid;
     }
     // block reduce the count of valid results
@@ -131,14 +134,15 @@ merge_kernel(const uint64_t *__restrict__ lists, const uint32_t *__restrict__ id
     for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xFFFFFFFFu, local, o);
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(&s_cnt, local);
     __syncthreads();
-    if (threadIdx.x == 0) counts[q] = s_cnt;
+    if (threadIdx.x == 0) counts[q_out] = s_cnt;
 }
 
 template <bool PAIRS>
 cudaError_t launch(const uint64_t *lists, const uint32_t *ids_in, const float *dist_in, uint32_t b,
                    uint32_t n_per_query, uint32_t group_keys, uint32_t n_groups, uint32_t k, uint32_t id_base,
                    uint64_t list_stride, uint64_t query_stride, uint64_t *keys_out, uint32_t *ids, float *dist,
-                   uint32_t *counts, cudaStream_t st)
+                   uint32_t *counts, cudaStream_t st, const uint32_t *slot_count = nullptr,
+                   const uint32_t *slot_to_query = nullptr)
 {
     if (b == 0) return cudaSuccess;
     const uint32_t per_cta = n_groups > 1 ? group_keys : n_per_query;
@@ -150,7 +154,8 @@ cudaError_t launch(const uint64_t *lists, const uint32_t *ids_in, const float *d
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SORT_MAX * 8));
     if (e != cudaSuccess) return e;
     kern<<<b * n_groups, threads, smem, st>>>(lists, ids_in, dist_in, n_per_query, group_keys, n_groups, k, id_base,
-                                              list_stride, query_stride, keys_out, ids, dist, counts);
+                                              list_stride, query_stride, keys_out, ids, dist, counts, slot_count,
+                                              slot_to_query);
     count_launch();
     return cudaGetLastError();
 }
@@ -184,6 +189,14 @@ cudaError_t launch_merge_keys(const uint64_t *d_lists, uint32_t b, uint32_t n_li
     }
     return launch<false>(d_lists, nullptr, nullptr, b, n_lists * k, n_lists * k, 1, k, id_base, 0, 0, nullptr, d_ids,
                          d_dist, d_counts, st);
+}
+
+cudaError_t launch_merge_keys_flagged(const uint64_t *d_lists, uint32_t b, uint32_t n_lists, uint32_t k, uint32_t id_base,
+                                      const uint32_t *d_slot_count, const uint32_t *d_slot_to_query, uint32_t *d_ids,
+                                      float *d_dist, uint32_t *d_counts, cudaStream_t st)
+{
+    return launch<false>(d_lists, nullptr, nullptr, b, n_lists * k, n_lists * k, 1, k, id_base, 0, 0, nullptr, d_ids,
+                         d_dist, d_counts, st, d_slot_count, d_slot_to_query);
 }
 
 cudaError_t launch_merge_pairs(const uint32_t *d_ids_in, const float *d_dist_in, uint32_t b, uint32_t n_lists,

@@ -16,6 +16,8 @@ struct ScanArgs {
     uint32_t nbox;            // 128-byte boxes per row (dim * esize / 128)
     uint32_t ring;            // box slots per warp
     uint64_t *out_lists;      // [nq][gridDim.x][k] sorted keys, KEY_SENTINEL padded
+    const uint32_t *flag_count;  // flagged mode: device count of queries to run (null = run a.nq queries)
+    const uint32_t *flag_list;   // flagged mode: their indices into `queries`
 };
 size_t scan_smem_bytes(uint32_t W, uint32_t ring, uint32_t qb, uint32_t dim, uint32_t cap);
 cudaError_t launch_scan_exact(const CUtensorMap &tmap, const ScanArgs &a, int qb, bool f16, int order,
@@ -49,7 +51,9 @@ struct FinalizeArgs {
     float c_acc;              // accumulation-error coefficient of the bound
     uint32_t *ids_out; float *dist_out; uint32_t *counts_out;
     uint32_t *flags;          // [b] 1 = could not be certified
-    uint32_t *n_flagged;      // device counter
+    uint32_t *n_flagged;      // device counter (reset per search)
+    uint32_t *flag_list;      // [b] indices of the uncertified queries, in arrival order
+    unsigned long long *flag_total;  // cumulative statistics
 };
 size_t tc_smem_bytes(uint32_t dim, uint32_t stages, uint32_t kk);
 cudaError_t launch_prep_queries(const float *d_q, uint32_t b, uint32_t b_pad, uint32_t dim, __half *d_qh, float *d_err,
@@ -69,6 +73,10 @@ uint32_t merge_groups(uint32_t n_lists, uint32_t k);
 cudaError_t launch_merge_keys(const uint64_t *d_lists, uint32_t b, uint32_t n_lists, uint32_t k, uint32_t id_base,
                               uint64_t *d_scratch, uint32_t *d_ids, float *d_dist, uint32_t *d_counts,
                               cudaStream_t st);
+// flagged form: CTA i handles slot i of d_lists iff i < *d_slot_count and writes query d_slot_to_query[i]
+cudaError_t launch_merge_keys_flagged(const uint64_t *d_lists, uint32_t b, uint32_t n_lists, uint32_t k, uint32_t id_base,
+                                      const uint32_t *d_slot_count, const uint32_t *d_slot_to_query, uint32_t *d_ids,
+                                      float *d_dist, uint32_t *d_counts, cudaStream_t st);
 // lists as (ids, dist) pairs [b][n_per_query]; id 0xFFFFFFFF marks an empty slot
 cudaError_t launch_merge_pairs(const uint32_t *d_ids_in, const float *d_dist_in, uint32_t b, uint32_t n_lists,
                                uint32_t k, uint64_t list_stride, uint64_t query_stride, uint32_t *d_ids,

@@ -126,9 +126,9 @@ struct sg_store {
     float *d_qerr = nullptr; size_t qmeta_cap = 0;         // [b_pad] |q - fp16(q)|
     float *d_qnorm = nullptr;                              // [b_pad]
     float *d_maxima = nullptr; size_t maxima_cap = 0;      // [b_pad][grid] pre-pass maxima
-    uint32_t *d_gtau = nullptr, *d_flags = nullptr, *d_nflag = nullptr;
+    uint32_t *d_gtau = nullptr, *d_flags = nullptr, *d_nflag = nullptr, *d_flag_list = nullptr;
+    unsigned long long *d_flag_total = nullptr;            // cumulative count of uncertified queries
     uint64_t *d_cand = nullptr; size_t cand_cap_q = 0;     // [b_pad][grid][kk] per-CTA candidate lists
-    uint32_t *h_flags = nullptr; size_t hflags_cap = 0;    // pinned: [0] = n_flagged, [1..] flags
     uint64_t tc_searches = 0, tc_flagged = 0;              // statistics (sg_store_tc_stats)
 
     bool profiling = false;
@@ -328,6 +328,8 @@ int search_exact_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, u
         a.nbox = s->dim * s->esize / 128;
         a.ring = plan.ring;
         a.out_lists = s->d_lists + (size_t)done * L * k;
+        a.flag_count = nullptr;
+        a.flag_list = nullptr;
         size_t smem = scan_smem_bytes(plan.W, plan.ring, qb, s->dim, plan.cap);
         cudaError_t e = launch_scan_exact(tmap, a, (int)qb, s->dtype == SG_DTYPE_F16, s->order, L, plan.W, smem, st);
         if (e != cudaSuccess) {
@@ -382,7 +384,8 @@ int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint
     int rc;
     if ((rc = grow(s->d_qh, s->qh_cap, (size_t)b_pad * s->dim)) != SG_OK) return rc;
     if (b_pad > s->qmeta_cap) {
-        size_t c[4] = {s->qmeta_cap, s->qmeta_cap, s->qmeta_cap, s->qmeta_cap};
+        size_t c[5] = {s->qmeta_cap, s->qmeta_cap, s->qmeta_cap, s->qmeta_cap, s->qmeta_cap};
+        if ((rc = grow(s->d_flag_list, c[4], b_pad)) != SG_OK) return rc;
         if ((rc = grow(s->d_qerr, c[0], b_pad)) != SG_OK) return rc;
         if ((rc = grow(s->d_qnorm, c[1], b_pad)) != SG_OK) return rc;
         if ((rc = grow(s->d_gtau, c[2], b_pad)) != SG_OK) return rc;
@@ -394,13 +397,6 @@ int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint
     const uint32_t n_lists = (uint32_t)(n_tiles < units_max ? n_tiles : units_max);
     const uint32_t grid = pair ? 2 * n_lists : n_lists;
     if ((rc = grow(s->d_cand, s->cand_cap_q, (size_t)b_pad * n_lists * 32)) != SG_OK) return rc;
-    if ((size_t)b + 1 > s->hflags_cap) {
-        if (s->h_flags) cudaFreeHost(s->h_flags);
-        s->h_flags = nullptr;
-        s->hflags_cap = 0;
-        SG_CUDA_TRY(cudaHostAlloc(&s->h_flags, ((size_t)b_pad + 1) * 4, cudaHostAllocDefault));
-        s->hflags_cap = (size_t)b_pad + 1;
-    }
     CUtensorMap tmap_rows, tmap_q;
     if ((rc = encode_corpus_tmap(&tmap_rows, s->d_rows, true, s->dim, s->n, 128)) != SG_OK) return rc;
     if ((rc = encode_corpus_tmap(&tmap_q, s->d_qh, true, s->dim, b_pad, 128)) != SG_OK) return rc;
@@ -470,29 +466,42 @@ int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint
     f.counts_out = d_counts;
     f.flags = s->d_flags;
     f.n_flagged = s->d_nflag;
+    f.flag_list = s->d_flag_list;
+    f.flag_total = s->d_flag_total;
     SG_CUDA_TRY(launch_finalize_tc(f, b, st));
 
-    // certification outcome: the (rare) flagged queries are re-run on the exact path.  This is the
-    // one host round trip of the batched path (4 bytes).
-    SG_CUDA_TRY(cudaMemcpyAsync(s->h_flags, s->d_nflag, 4, cudaMemcpyDeviceToHost, st));
-    SG_CUDA_TRY(cudaStreamSynchronize(st));
+    // Certification outcome, handled ON THE DEVICE (no host round trip, the call stays asynchronous):
+    // the exact sweep is launched in "flagged" mode -- it reads the number and indices of uncertified
+    // queries from device memory, exits at once when there are none (the normal case, ~3 us), and
+    // otherwise re-runs them 4 per sweep; the flagged merge then overwrites exactly those result rows.
     s->tc_searches += b;
-    const uint32_t n_flagged = s->h_flags[0];
-    if (n_flagged) {
-        s->tc_flagged += n_flagged;
-        SG_CUDA_TRY(cudaMemcpyAsync(s->h_flags + 1, s->d_flags, (size_t)b * 4, cudaMemcpyDeviceToHost, st));
-        SG_CUDA_TRY(cudaStreamSynchronize(st));
-        uint32_t i = 0;
-        while (i < b) {
-            if (!s->h_flags[1 + i]) { ++i; continue; }
-            uint32_t j = i;
-            while (j < b && j - i < 4 && s->h_flags[1 + j]) ++j;   // a run of up to 4 flagged neighbours: one sweep
-            rc = search_exact_locked(s, d_q + (size_t)i * s->dim, j - i, k, d_ids + (size_t)i * k,
-                                     d_dist + (size_t)i * k, d_counts + i, st, false);
-            if (rc != SG_OK) return rc;
-            i = j;
-        }
+    ScanPlan plan;
+    if ((rc = plan_scan(s, k, 4, &plan)) != SG_OK) return rc;
+    const uint32_t LA = plan.grid;
+    if ((rc = grow(s->d_lists, s->lists_cap, (size_t)b * LA * k)) != SG_OK) return rc;
+    CUtensorMap tmap32;
+    if ((rc = encode_corpus_tmap(&tmap32, s->d_rows, true, s->dim, s->n, 32)) != SG_OK) return rc;
+    ScanArgs sa;
+    sa.queries = d_q;
+    sa.nq = 0;
+    sa.dim = s->dim;
+    sa.n_rows = s->n;
+    sa.deleted = s->n_deleted ? s->d_deleted : nullptr;
+    sa.k = k;
+    sa.cap = plan.cap;
+    sa.nbox = s->dim * s->esize / 128;
+    sa.ring = plan.ring;
+    sa.out_lists = s->d_lists;
+    sa.flag_count = s->d_nflag;
+    sa.flag_list = s->d_flag_list;
+    cudaError_t e2 = launch_scan_exact(tmap32, sa, 4, true, s->order, LA, plan.W,
+                                       scan_smem_bytes(plan.W, plan.ring, 4, s->dim, plan.cap), st);
+    if (e2 != cudaSuccess) {
+        set_error("flagged exact sweep launch failed: %s", cudaGetErrorString(e2));
+        return SG_ERR_CUDA;
     }
+    SG_CUDA_TRY(launch_merge_keys_flagged(s->d_lists, b, LA, k, s->id_base, s->d_nflag, s->d_flag_list, d_ids, d_dist,
+                                          d_counts, st));
     return SG_OK;
 }
 
@@ -568,6 +577,8 @@ int sg_store_create(sg_store **out, int device, uint32_t dim, int dtype, int met
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_max_norm, sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&s->d_nflag, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_flag_total, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(s->d_flag_total, 0, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(s->d_max_norm, 0, sizeof(float));
     if (e != cudaSuccess) {
         set_error("stream/event creation failed: %s", cudaGetErrorString(e));
@@ -600,8 +611,9 @@ void sg_store_destroy(sg_store *s)
     cudaFree(s->d_gtau);
     cudaFree(s->d_flags);
     cudaFree(s->d_nflag);
+    cudaFree(s->d_flag_list);
+    cudaFree(s->d_flag_total);
     cudaFree(s->d_cand);
-    if (s->h_flags) cudaFreeHost(s->h_flags);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -830,7 +842,12 @@ int sg_store_tc_stats(sg_store *s, uint64_t *queries_out, uint64_t *flagged_out)
     if (!s) return SG_ERR_INVALID;
     std::lock_guard<std::mutex> g(s->mu);
     if (queries_out) *queries_out = s->tc_searches;
-    if (flagged_out) *flagged_out = s->tc_flagged;
+    if (flagged_out) {
+        SG_CUDA_TRY(cudaSetDevice(s->device));
+        unsigned long long v = 0;
+        SG_CUDA_TRY(cudaMemcpy(&v, s->d_flag_total, sizeof(v), cudaMemcpyDeviceToHost));   // synchronises the device
+        *flagged_out = v;
+    }
     return SG_OK;
 }
 
