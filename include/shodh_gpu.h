@@ -93,9 +93,19 @@ SG_API int sg_store_clear_deleted(sg_store *s);
 /* VamanaIndex::len (vamana.rs:976-979): rows ever appended (deleted included). */
 SG_API int sg_store_len(const sg_store *s, uint64_t *n_out);
 SG_API int sg_store_deleted_count(const sg_store *s, uint64_t *n_out);
+SG_API int sg_store_dim(const sg_store *s, uint32_t *dim_out);
 
 /* VamanaIndex::get_vector / extract_all_vectors: rows [first, first+n) upcast to f32. */
 SG_API int sg_store_get_vectors(sg_store *s, uint64_t first, uint64_t n, float *rows_f32_out);
+
+/* VamanaIndex::load_from_file (src/vector_db/vamana_persist.rs:290-400): read the reference's persisted
+ * "VAMA" v1 index file into an EMPTY store -- vectors section (dense f32 rows) uploaded as-is, deleted ids
+ * applied, graph section skipped (the GPU store scans exactly).  The store's dim must equal the file's.
+ * verify_checksum != 0 checks the FNV-1a-64 checksum like the reference does (:303-312). */
+SG_API int sg_store_load_vama(sg_store *s, const char *path, int verify_checksum);
+/* header / layout of a VAMA file without touching a GPU (host-side parser only) */
+SG_API int sg_vama_inspect(const char *path, int verify_checksum, uint64_t *num_vectors_out, uint32_t *dimension_out,
+                           uint32_t *deleted_count_out, uint32_t *metric_out, uint64_t *vectors_offset_out);
 
 /* summation order of the exact scores (default SG_ORDER_SCALAR) */
 SG_API int sg_store_set_order(sg_store *s, int order);

@@ -7,7 +7,7 @@ from . import capi
 from .capi import SgError
 from .encoder import GpuMiniLM, export_bert_weights, random_minilm_state_dict
 from .relevance import fuse_topk
-from .vector_store import GpuVectorStore, merge_topk_device
+from .vector_store import GpuVectorStore, merge_topk_device, vama_inspect
 
 capi.lib()  # load now: no lazy CPU fallback, a missing extension is an ImportError
 

@@ -1,0 +1,215 @@
+// persist.cu -- loading the reference's persisted index file ("VAMA" v1) straight into the GPU store.
+//
+// SURVEY.md 8f item 2.  File format (reference src/vector_db/vamana_persist.rs:6-34, header byte
+// offsets :96-111): 64-byte little-endian header { "VAMA", version u32 = 1, num_vectors u64 @8,
+// dimension u32 @16, max_degree u32 @20, medoid u32 @24, distance_metric u8 @28, deleted_count u32
+// @29, incremental_inserts u64 @33, checksum u64 @41 }, then deleted ids [u32; deleted_count], then
+// the graph (per node: neighbour_count u16 + [u32; count]), then -- aligned to 64 bytes -- the
+// vectors, row-major [[f32; dimension]; num_vectors].  checksum = FNV-1a-64 over every byte after
+// the header (:155-163, :269, :303-312).  The vectors section is exactly the dense f32 matrix
+// sg_store_append takes; the graph is skipped (the GPU store scans exactly, it needs no graph).
+// This is host-side file plumbing; no arithmetic of the hot path happens here.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "sg_internal.h"
+
+namespace {
+
+struct VamaInfo {
+    uint64_t num_vectors = 0;
+    uint32_t dimension = 0, max_degree = 0, medoid = 0, deleted_count = 0;
+    uint8_t metric = 0;
+    uint64_t incremental_inserts = 0, checksum = 0, vectors_offset = 0, file_size = 0;
+};
+
+uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+uint64_t rd64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
+
+// parses header + walks the graph section to find the vectors; optionally verifies the checksum
+int vama_parse(FILE *f, VamaInfo &vi, std::vector<uint32_t> *deleted, int verify, int *checksum_ok)
+{
+    uint8_t h[64];
+    if (fseek(f, 0, SEEK_END) != 0) return SG_ERR_INVALID;
+    vi.file_size = (uint64_t)ftell(f);
+    fseek(f, 0, SEEK_SET);
+    if (vi.file_size < 64 || fread(h, 1, 64, f) != 64 || memcmp(h, "VAMA", 4) != 0) {
+        sg::set_error("not a VAMA file (bad magic or shorter than the 64-byte header)");
+        return SG_ERR_INVALID;
+    }
+    if (rd32(h + 4) != 1) {
+        sg::set_error("unsupported VAMA version %u", rd32(h + 4));
+        return SG_ERR_UNSUPPORTED;
+    }
+    vi.num_vectors = rd64(h + 8);
+    vi.dimension = rd32(h + 16);
+    vi.max_degree = rd32(h + 20);
+    vi.medoid = rd32(h + 24);
+    vi.metric = h[28];
+    vi.deleted_count = rd32(h + 29);
+    vi.incremental_inserts = rd64(h + 33);
+    vi.checksum = rd64(h + 41);
+    uint64_t off = 64 + (uint64_t)vi.deleted_count * 4;
+    if (off > vi.file_size) {
+        sg::set_error("VAMA file truncated in the deleted-ids section");
+        return SG_ERR_INVALID;
+    }
+    if (deleted) {
+        deleted->resize(vi.deleted_count);
+        if (vi.deleted_count && fread(deleted->data(), 4, vi.deleted_count, f) != vi.deleted_count) return SG_ERR_INVALID;
+    }
+    // graph: variable-length records; buffered walk
+    fseek(f, (long)off, SEEK_SET);
+    std::vector<uint8_t> buf(1 << 20);
+    size_t have = 0, pos = 0;
+    uint64_t file_pos = off;
+    auto need = [&](size_t n) -> bool {
+        if (have - pos >= n) return true;
+        memmove(buf.data(), buf.data() + pos, have - pos);
+        have -= pos;
+        pos = 0;
+        size_t got = fread(buf.data() + have, 1, buf.size() - have, f);
+        have += got;
+        return have - pos >= n;
+    };
+    for (uint64_t node = 0; node < vi.num_vectors; ++node) {
+        if (!need(2)) {
+            sg::set_error("VAMA file truncated in the graph section (node %llu)", (unsigned long long)node);
+            return SG_ERR_INVALID;
+        }
+        uint16_t cnt;
+        memcpy(&cnt, buf.data() + pos, 2);
+        pos += 2;
+        file_pos += 2;
+        size_t skip = (size_t)cnt * 4;
+        while (skip) {
+            if (!need(1)) {
+                sg::set_error("VAMA file truncated in the graph section (node %llu)", (unsigned long long)node);
+                return SG_ERR_INVALID;
+            }
+            size_t take = have - pos < skip ? have - pos : skip;
+            pos += take;
+            file_pos += take;
+            skip -= take;
+        }
+    }
+    vi.vectors_offset = (file_pos + 63) & ~63ull;
+    const uint64_t want = vi.vectors_offset + vi.num_vectors * (uint64_t)vi.dimension * 4;
+    if (want > vi.file_size) {
+        sg::set_error("VAMA file truncated in the vectors section (%llu < %llu bytes)", (unsigned long long)vi.file_size,
+                      (unsigned long long)want);
+        return SG_ERR_INVALID;
+    }
+    if (verify) {
+        fseek(f, 64, SEEK_SET);
+        uint64_t hash = 0xcbf29ce484222325ull;
+        size_t got;
+        while ((got = fread(buf.data(), 1, buf.size(), f)) > 0)
+            for (size_t i = 0; i < got; ++i) {
+                hash ^= buf[i];
+                hash *= 0x100000001b3ull;
+            }
+        if (checksum_ok) *checksum_ok = hash == vi.checksum;
+        if (hash != vi.checksum) {
+            sg::set_error("VAMA checksum mismatch: stored %llx, computed %llx", (unsigned long long)vi.checksum,
+                          (unsigned long long)hash);
+            return SG_ERR_INVALID;
+        }
+    } else if (checksum_ok) {
+        *checksum_ok = -1;
+    }
+    return SG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sg_vama_inspect(const char *path, int verify_checksum, uint64_t *num_vectors_out, uint32_t *dimension_out,
+                    uint32_t *deleted_count_out, uint32_t *metric_out, uint64_t *vectors_offset_out)
+{
+    if (!path) return SG_ERR_INVALID;
+    FILE *f = fopen(path, "rb");
+    if (!f) {
+        sg::set_error("cannot open %s", path);
+        return SG_ERR_INVALID;
+    }
+    VamaInfo vi;
+    int rc = vama_parse(f, vi, nullptr, verify_checksum, nullptr);
+    fclose(f);
+    if (rc != SG_OK) return rc;
+    if (num_vectors_out) *num_vectors_out = vi.num_vectors;
+    if (dimension_out) *dimension_out = vi.dimension;
+    if (deleted_count_out) *deleted_count_out = vi.deleted_count;
+    if (metric_out) *metric_out = vi.metric;
+    if (vectors_offset_out) *vectors_offset_out = vi.vectors_offset;
+    return SG_OK;
+}
+
+int sg_store_load_vama(sg_store *s, const char *path, int verify_checksum)
+{
+    if (!s || !path) return SG_ERR_INVALID;
+    uint64_t have = 0;
+    int rc = sg_store_len(s, &have);
+    if (rc != SG_OK) return rc;
+    if (have != 0) {
+        sg::set_error("sg_store_load_vama needs an empty store (ids must equal the file's row numbers)");
+        return SG_ERR_INVALID;
+    }
+    FILE *f = fopen(path, "rb");
+    if (!f) {
+        sg::set_error("cannot open %s", path);
+        return SG_ERR_INVALID;
+    }
+    VamaInfo vi;
+    std::vector<uint32_t> deleted;
+    rc = vama_parse(f, vi, &deleted, verify_checksum, nullptr);
+    if (rc != SG_OK) {
+        fclose(f);
+        return rc;
+    }
+    uint32_t store_dim = 0;
+    sg_store_dim(s, &store_dim);
+    if (store_dim != vi.dimension) {
+        fclose(f);
+        sg::set_error("dimension mismatch: the file holds %u-d vectors, the store is %u-d", vi.dimension, store_dim);
+        return SG_ERR_DIM;
+    }
+    if (vi.metric != 0) {
+        fclose(f);
+        sg::set_error("VAMA file uses distance metric %u; only NormalizedDotProduct (0) is supported", vi.metric);
+        return SG_ERR_UNSUPPORTED;
+    }
+    // upload the vectors section in 32 MB pieces through the normal append path (rounds to the store dtype)
+    rc = sg_store_reserve(s, vi.num_vectors);
+    const size_t dim = vi.dimension;
+    const size_t rows_per = dim ? ((size_t)32 << 20) / (dim * 4) : 0;
+    std::vector<float> chunk;
+    if (rc == SG_OK && rows_per == 0) rc = SG_ERR_DIM;
+    if (rc == SG_OK) {
+        chunk.resize(rows_per * dim);
+        fseek(f, (long)vi.vectors_offset, SEEK_SET);
+        uint64_t done = 0;
+        while (rc == SG_OK && done < vi.num_vectors) {
+            const size_t n = vi.num_vectors - done < rows_per ? (size_t)(vi.num_vectors - done) : rows_per;
+            if (fread(chunk.data(), 4, n * dim, f) != n * dim) {
+                sg::set_error("short read in the vectors section");
+                rc = SG_ERR_INVALID;
+                break;
+            }
+            rc = sg_store_append(s, chunk.data(), n, nullptr);   // returns SG_ERR_DIM-like errors from the store
+            done += n;
+        }
+    }
+    fclose(f);
+    if (rc != SG_OK) return rc;
+    for (uint32_t id : deleted) {
+        int ok = 0;
+        rc = sg_store_mark_deleted(s, id, &ok);
+        if (rc != SG_OK) return rc;
+    }
+    return SG_OK;
+}
+
+}  // extern "C"

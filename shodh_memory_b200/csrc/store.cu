@@ -729,6 +729,13 @@ int sg_store_len(const sg_store *s, uint64_t *n_out)
     return SG_OK;
 }
 
+int sg_store_dim(const sg_store *s, uint32_t *dim_out)
+{
+    if (!s || !dim_out) return SG_ERR_INVALID;
+    *dim_out = s->dim;
+    return SG_OK;
+}
+
 int sg_store_deleted_count(const sg_store *s, uint64_t *n_out)
 {
     if (!s || !n_out) return SG_ERR_INVALID;

@@ -97,6 +97,10 @@ class GpuVectorStore:
     def extract_all_vectors(self) -> np.ndarray:
         return self.get_vectors(0, len(self))
 
+    def load_from_file(self, path: str, verify_checksum: bool = True) -> None:
+        """VamanaIndex::load_from_file: the reference's "VAMA" v1 file -> this (empty) store."""
+        capi.check(capi.lib().sg_store_load_vama(self._h, path.encode(), int(verify_checksum)))
+
     def set_order(self, order: str) -> None:
         capi.check(capi.lib().sg_store_set_order(
             self._h, capi.SG_ORDER_AVX2 if order == "avx2" else capi.SG_ORDER_SCALAR))
@@ -149,6 +153,15 @@ class GpuVectorStore:
         ms, n = C.c_float(), C.c_uint32()
         capi.check(capi.lib().sg_store_last_scan_ms(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+
+def vama_inspect(path: str, verify_checksum: bool = True) -> dict:
+    n, off = C.c_uint64(), C.c_uint64()
+    dim, dc, metric = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    capi.check(capi.lib().sg_vama_inspect(path.encode(), int(verify_checksum), C.byref(n), C.byref(dim), C.byref(dc),
+                                          C.byref(metric), C.byref(off)))
+    return dict(num_vectors=n.value, dimension=dim.value, deleted_count=dc.value, metric=metric.value,
+                vectors_offset=off.value)
 
 
 def merge_topk_device(device: int, d_ids: int, d_dist: int, b: int, n_lists: int, k: int, d_ids_out: int,
