@@ -439,6 +439,144 @@ attention_small_kernel(const __half *__restrict__ qkv, const int64_t *__restrict
     }
 }
 
+// ---- attention on the legacy tensor path (mma.sync m16n8k16), L <= 128 ---------------------------
+// grid = (sequences * heads, ceil(L / 64)); 4 warps, each owns 16 query rows.  S = Q K^T (2 k-steps over
+// d = 32) stays in registers, the masked softmax is done on the accumulator fragments (quad shuffles),
+// and the f32 probabilities are re-packed in registers as the A operand of P V (the C fragment of two
+// adjacent 8-key tiles IS the A fragment of one 16-key step).  K sits row-major in shared memory
+// (pitch 40 halfs), V transposed ([32][L16 + 8]); both pitches make the fragment loads conflict-free.
+// Attention is ~4 % of the encoder's FLOPs; this kernel exists to get it out of the way of the tcgen05 GEMMs.
+SG_DEVICE_INLINE void mma_m16n8k16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+SG_DEVICE_INLINE uint32_t pack_half2(float lo, float hi)
+{
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+template <uint32_t KS>   // KS = L16 / 16: 16-key steps (1..8)
+__global__ void __launch_bounds__(128)
+attention_mma_kernel(const __half *__restrict__ qkv, const int64_t *__restrict__ mask, uint32_t L, uint32_t H,
+                     uint32_t heads, __half *__restrict__ ctx)
+{
+    constexpr uint32_t D = 32, L16 = KS * 16, NT = KS * 2, KP = 40, VP = L16 + 8;
+    __shared__ __align__(16) __half Ks[L16 * KP];
+    __shared__ __align__(16) __half Vt[D * VP];
+    __shared__ float mbias[L16];                       // 0 for live keys, -inf for masked / padding
+    const uint32_t b = blockIdx.x / heads, h = blockIdx.x % heads;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t g = lane >> 2, tq = lane & 3;       // fragment row group / quad lane
+    const size_t row_stride = 3 * (size_t)H;
+    const __half *base = qkv + (size_t)b * L * row_stride;
+    const float NEG_INF = -__uint_as_float(0x7F800000u);
+    for (uint32_t i = threadIdx.x; i < L16 * 4; i += blockDim.x) {
+        const uint32_t j = i >> 2, part = i & 3;
+        uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+        if (j < L) {
+            kv = *reinterpret_cast<const uint4 *>(base + j * row_stride + H + h * D + part * 8);
+            vv = *reinterpret_cast<const uint4 *>(base + j * row_stride + 2 * H + h * D + part * 8);
+        }
+        *reinterpret_cast<uint4 *>(Ks + (size_t)j * KP + part * 8) = kv;
+        const __half *vh = reinterpret_cast<const __half *>(&vv);
+#pragma unroll
+        for (uint32_t e = 0; e < 8; ++e) Vt[(size_t)(part * 8 + e) * VP + j] = vh[e];
+    }
+    for (uint32_t j = threadIdx.x; j < L16; j += blockDim.x)
+        mbias[j] = (j < L && mask[(size_t)b * L + j] == 1) ? 0.0f : NEG_INF;
+    __syncthreads();
+
+    const uint32_t r0 = blockIdx.y * 64 + warp * 16 + g;     // this thread's rows: r0 and r0 + 8
+    if (blockIdx.y * 64 + warp * 16 >= L) return;
+    // Q fragments for both k-steps (d 0..15, 16..31), straight from global memory
+    uint32_t qa[2][4];
+#pragma unroll
+    for (uint32_t ks = 0; ks < 2; ++ks) {
+        const uint32_t d0 = ks * 16 + tq * 2;
+        const __half *q0 = base + (size_t)r0 * row_stride + h * D;
+        const __half *q1 = base + (size_t)(r0 + 8) * row_stride + h * D;
+        qa[ks][0] = r0 < L ? *reinterpret_cast<const uint32_t *>(q0 + d0) : 0u;
+        qa[ks][1] = r0 + 8 < L ? *reinterpret_cast<const uint32_t *>(q1 + d0) : 0u;
+        qa[ks][2] = r0 < L ? *reinterpret_cast<const uint32_t *>(q0 + d0 + 8) : 0u;
+        qa[ks][3] = r0 + 8 < L ? *reinterpret_cast<const uint32_t *>(q1 + d0 + 8) : 0u;
+    }
+    // S = Q K^T
+    float sacc[NT][4];
+#pragma unroll
+    for (uint32_t nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sacc[nt][e] = 0.0f;
+#pragma unroll
+        for (uint32_t ks = 0; ks < 2; ++ks) {
+            const __half *kp = Ks + (size_t)(nt * 8 + g) * KP + ks * 16 + tq * 2;
+            mma_m16n8k16(sacc[nt], qa[ks], *reinterpret_cast<const uint32_t *>(kp), *reinterpret_cast<const uint32_t *>(kp + 8));
+        }
+    }
+    // masked softmax on the fragments: rows r0 (elements 0,1) and r0+8 (elements 2,3)
+    const float scale = 0.17677669529663687f;
+    float mx0 = NEG_INF, mx1 = NEG_INF;
+#pragma unroll
+    for (uint32_t nt = 0; nt < NT; ++nt) {
+        const float b0 = mbias[nt * 8 + tq * 2], b1 = mbias[nt * 8 + tq * 2 + 1];
+        sacc[nt][0] = sacc[nt][0] * scale + b0; sacc[nt][1] = sacc[nt][1] * scale + b1;
+        sacc[nt][2] = sacc[nt][2] * scale + b0; sacc[nt][3] = sacc[nt][3] * scale + b1;
+        mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xFFFFFFFFu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xFFFFFFFFu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xFFFFFFFFu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xFFFFFFFFu, mx1, 2));
+    float sum0 = 0.0f, sum1 = 0.0f;
+#pragma unroll
+    for (uint32_t nt = 0; nt < NT; ++nt) {
+        sacc[nt][0] = mx0 > NEG_INF ? __expf(sacc[nt][0] - mx0) : 0.0f;
+        sacc[nt][1] = mx0 > NEG_INF ? __expf(sacc[nt][1] - mx0) : 0.0f;
+        sacc[nt][2] = mx1 > NEG_INF ? __expf(sacc[nt][2] - mx1) : 0.0f;
+        sacc[nt][3] = mx1 > NEG_INF ? __expf(sacc[nt][3] - mx1) : 0.0f;
+        sum0 += sacc[nt][0] + sacc[nt][1];
+        sum1 += sacc[nt][2] + sacc[nt][3];
+    }
+    sum0 += __shfl_xor_sync(0xFFFFFFFFu, sum0, 1); sum0 += __shfl_xor_sync(0xFFFFFFFFu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xFFFFFFFFu, sum1, 1); sum1 += __shfl_xor_sync(0xFFFFFFFFu, sum1, 2);
+    // O = P V : per 16-key step, the P A-fragment is built from two adjacent S tiles
+    float oacc[4][4];
+#pragma unroll
+    for (uint32_t dt = 0; dt < 4; ++dt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) oacc[dt][e] = 0.0f;
+#pragma unroll
+    for (uint32_t ks = 0; ks < KS; ++ks) {
+        uint32_t pa[4];
+        pa[0] = pack_half2(sacc[2 * ks][0], sacc[2 * ks][1]);
+        pa[1] = pack_half2(sacc[2 * ks][2], sacc[2 * ks][3]);
+        pa[2] = pack_half2(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1]);
+        pa[3] = pack_half2(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3]);
+#pragma unroll
+        for (uint32_t dt = 0; dt < 4; ++dt) {
+            const __half *vp = Vt + (size_t)(dt * 8 + g) * VP + ks * 16 + tq * 2;
+            mma_m16n8k16(oacc[dt], pa, *reinterpret_cast<const uint32_t *>(vp), *reinterpret_cast<const uint32_t *>(vp + 8));
+        }
+    }
+    const float inv0 = sum0 > 0.0f ? 1.0f / sum0 : 0.0f, inv1 = sum1 > 0.0f ? 1.0f / sum1 : 0.0f;
+#pragma unroll
+    for (uint32_t dt = 0; dt < 4; ++dt) {
+        const uint32_t d = dt * 8 + tq * 2;
+        if (r0 < L)
+            *reinterpret_cast<uint32_t *>(ctx + ((size_t)b * L + r0) * H + h * D + d) = pack_half2(oacc[dt][0] * inv0, oacc[dt][1] * inv0);
+        if (r0 + 8 < L)
+            *reinterpret_cast<uint32_t *>(ctx + ((size_t)b * L + r0 + 8) * H + h * D + d) = pack_half2(oacc[dt][2] * inv1, oacc[dt][3] * inv1);
+    }
+}
+
+template <uint32_t KS>
+void launch_attention_mma(const __half *qkv, const int64_t *mask, uint32_t b, uint32_t L, uint32_t H, uint32_t heads,
+                          __half *ctx, cudaStream_t st)
+{
+    attention_mma_kernel<KS><<<dim3(b * heads, (L + 63) / 64), 128, 0, st>>>(qkv, mask, L, H, heads, ctx);
+}
+
 // ---- masked mean-pool + finalize (reference minilm.rs:959-978, :846-878) -----------------------------
 // pooled[d] += h[s][d] for s ascending over mask==1; /= mask_sum; NaN/Inf -> 0; norm = sqrt(sum x^2)
 // left-to-right; divide by norm if norm > f32::EPSILON.  One CTA per sequence, one thread per dim.
@@ -722,7 +860,18 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
         // QKV = h0 . Wqkv^T + b
         g.K = H; g.N = 3 * H; g.stages = 3; g.bias = ly.bqkv; g.out = e->qkv;   // 96 KB: two CTAs per SM
         SG_CUDA_TRY((launch_gemm<128, EPI_BIAS>(t_h0, t_wqkv, g, m_tiles, st)));
-        if (L <= 128) {
+        if (L <= 128 && !getenv("SG_ENC_ATTN_SIMT")) {
+            switch ((L + 15) / 16) {
+            case 1: launch_attention_mma<1>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st); break;
+            case 2: launch_attention_mma<2>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st); break;
+            case 3: launch_attention_mma<3>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st); break;
+            case 4: launch_attention_mma<4>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st); break;
+            case 5: launch_attention_mma<5>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st); break;
+            case 6: launch_attention_mma<6>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st); break;
+            case 7: launch_attention_mma<7>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st); break;
+            default: launch_attention_mma<8>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st); break;
+            }
+        } else if (L <= 128) {
             const uint32_t L4 = (L + 3) & ~3u;
             const size_t sm = ((size_t)2 * L4 * 33 + 64 * 33 + (size_t)64 * (L4 + 1)) * 4;
             if (sm > 48 * 1024)
