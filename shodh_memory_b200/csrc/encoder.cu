@@ -45,7 +45,16 @@ struct GemmArgs {
     float *out_f32;        // optional f32 copy (EPI_BIAS_RES_LN)
 };
 
-SG_DEVICE_INLINE float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf-GELU.  erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the fp16 output rounding):
+// one reciprocal, one exp, five FMAs instead of libdevice erff's ~35 instructions.
+SG_DEVICE_INLINE float gelu_erf(float x)
+{
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+    const float erf_abs = 1.0f - poly * __expf(-z * z);
+    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 
 // C tile = 128 rows x BN columns, one tile per CTA.  grid = (M_pad/128, N/BN).
 template <uint32_t BN, uint32_t EPI>
@@ -65,6 +74,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * STAGE);
     uint64_t *full_bar = bars, *empty_bar = bars + S, *done_bar = bars + 2 * S;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
+    // [3][BN]: bias, gamma, beta of this tile's columns (16-byte aligned for float4 reads)
+    float *par_s = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~static_cast<uintptr_t>(15));
 
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < S; ++i) {
@@ -124,15 +135,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t t = threadIdx.x - 128;
         const uint32_t row = m0 + t;
         const uint32_t lane_base = ((warp & 3) * 32) << 16;
+        // stage the per-column parameters while the main loop runs (named barrier over the 4 epilogue warps)
+        for (uint32_t i = t; i < BN; i += 128) {
+            par_s[i] = g.bias[n0 + i];
+            if constexpr (EPI == EPI_BIAS_RES_LN) {
+                par_s[BN + i] = g.gamma[n0 + i];
+                par_s[2 * BN + i] = g.beta[n0 + i];
+            }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         mbar_wait(smem_u32(done_bar), 0);
         tc_fence_after();
         if constexpr (EPI == EPI_BIAS_RES_LN) {
             // BN == N == hidden: the whole row is in this thread's TMEM lane.  Pass 1: v = acc + bias +
-            // residual, accumulate sum and sum of squares (f32); pass 2: recompute v, normalise, store.
+            // residual is written BACK into TMEM while sum / sum of squares accumulate; pass 2 reads v from
+            // TMEM only.  bias / gamma / beta were staged in shared memory during the main loop.
             const uint4 *res4 = reinterpret_cast<const uint4 *>(g.residual + (size_t)row * g.N);   // 8 halfs each
-            const float4 *bias4 = reinterpret_cast<const float4 *>(g.bias);
-            const float4 *gam4 = reinterpret_cast<const float4 *>(g.gamma);
-            const float4 *bet4 = reinterpret_cast<const float4 *>(g.beta);
+            const float4 *bias4 = reinterpret_cast<const float4 *>(par_s);
+            const float4 *gam4 = reinterpret_cast<const float4 *>(par_s + BN);
+            const float4 *bet4 = reinterpret_cast<const float4 *>(par_s + 2 * BN);
             float sum = 0.0f, sq = 0.0f;
 #pragma unroll 1
             for (uint32_t c = 0; c < BN / 32; ++c) {
@@ -144,15 +165,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 tmem_ld_wait();
 #pragma unroll
                 for (uint32_t q = 0; q < 8; ++q) {
-                    const float4 bb = __ldg(bias4 + c * 8 + q);
+                    const float4 bb = bias4[c * 8 + q];
                     const __half2 *hp = reinterpret_cast<const __half2 *>(&rv[q >> 1]) + (q & 1) * 2;
                     const float2 r01 = __half22float2(hp[0]), r23 = __half22float2(hp[1]);
                     const float v0 = __uint_as_float(r[4 * q]) + bb.x + r01.x, v1 = __uint_as_float(r[4 * q + 1]) + bb.y + r01.y;
                     const float v2 = __uint_as_float(r[4 * q + 2]) + bb.z + r23.x, v3 = __uint_as_float(r[4 * q + 3]) + bb.w + r23.y;
                     sum += (v0 + v1) + (v2 + v3);
                     sq += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
+                    r[4 * q] = __float_as_uint(v0); r[4 * q + 1] = __float_as_uint(v1);
+                    r[4 * q + 2] = __float_as_uint(v2); r[4 * q + 3] = __float_as_uint(v3);
                 }
+                tmem_st32(tmem_base + lane_base + c * 32, r);
             }
+            tmem_st_wait();
             const float mean = sum / (float)BN;
             const float var = fmaxf(sq / (float)BN - mean * mean, 0.0f);
             const float rstd = rsqrtf(var + g.eps);
@@ -160,21 +185,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (uint32_t c = 0; c < BN / 32; ++c) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + lane_base + c * 32, r);
-                uint4 rv[4];
-#pragma unroll
-                for (uint32_t q = 0; q < 4; ++q) rv[q] = res4[c * 4 + q];
                 tmem_ld_wait();
                 __align__(16) __half o[32];
 #pragma unroll
                 for (uint32_t q = 0; q < 8; ++q) {
-                    const float4 bb = __ldg(bias4 + c * 8 + q), gg = __ldg(gam4 + c * 8 + q), be = __ldg(bet4 + c * 8 + q);
-                    const __half2 *hp = reinterpret_cast<const __half2 *>(&rv[q >> 1]) + (q & 1) * 2;
-                    const float2 r01 = __half22float2(hp[0]), r23 = __half22float2(hp[1]);
+                    const float4 gg = gam4[c * 8 + q], be = bet4[c * 8 + q];
                     float y[4];
-                    y[0] = (__uint_as_float(r[4 * q]) + bb.x + r01.x - mean) * rstd * gg.x + be.x;
-                    y[1] = (__uint_as_float(r[4 * q + 1]) + bb.y + r01.y - mean) * rstd * gg.y + be.y;
-                    y[2] = (__uint_as_float(r[4 * q + 2]) + bb.z + r23.x - mean) * rstd * gg.z + be.z;
-                    y[3] = (__uint_as_float(r[4 * q + 3]) + bb.w + r23.y - mean) * rstd * gg.w + be.w;
+                    y[0] = (__uint_as_float(r[4 * q]) - mean) * rstd * gg.x + be.x;
+                    y[1] = (__uint_as_float(r[4 * q + 1]) - mean) * rstd * gg.y + be.y;
+                    y[2] = (__uint_as_float(r[4 * q + 2]) - mean) * rstd * gg.z + be.z;
+                    y[3] = (__uint_as_float(r[4 * q + 3]) - mean) * rstd * gg.w + be.w;
 #pragma unroll
                     for (uint32_t j = 0; j < 4; ++j) o[4 * q + j] = __float2half_rn(y[j]);
                     if (g.out_f32)
@@ -193,7 +213,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 __align__(16) __half o[32];
 #pragma unroll
                 for (uint32_t j = 0; j < 32; ++j) {
-                    float v = __uint_as_float(r[j]) + g.bias[n0 + c * 32 + j];
+                    float v = __uint_as_float(r[j]) + par_s[c * 32 + j];
                     if constexpr (EPI == EPI_BIAS_GELU) v = gelu_erf(v);
                     o[j] = __float2half_rn(v);
                 }
@@ -629,7 +649,7 @@ template <uint32_t BN, uint32_t EPI>
 cudaError_t launch_gemm(const CUtensorMap &ta, const CUtensorMap &tw, const GemmArgs &g, uint32_t m_tiles, cudaStream_t st)
 {
     constexpr uint32_t STAGE = 128 * 128 + BN * 128;
-    const size_t smem = (size_t)g.stages * STAGE + (2 * g.stages + 1) * 8 + 16;
+    const size_t smem = (size_t)g.stages * STAGE + (2 * g.stages + 1) * 8 + 48 + 3 * BN * 4;
     auto kern = gemm_tc_kernel<BN, EPI>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
