@@ -231,6 +231,121 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
 }
 
+// ---- persistent 128x128-tile GEMM: epilogue of tile i overlaps the main loop of tile i+1 -----------
+// Same roles as gemm_tc_kernel, but every CTA walks tiles t = blockIdx.x, +gridDim.x, ... with TWO
+// accumulator stages in TMEM (2 x 128 columns), so the bias/GELU/convert/store epilogue (which costs
+// about as much as the 6-K-block main loop of a hidden-384 GEMM) runs while the tensor core already
+// works on the next tile.  96 KB of shared memory per CTA: two CTAs per SM (2 x 256 TMEM columns).
+template <uint32_t EPI>
+__global__ void __launch_bounds__(G_THREADS, 2)
+gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                       const GemmArgs g, const uint32_t m_tiles, const uint32_t n_tiles)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr uint32_t BN = 128, A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE = A_BYTES + B_BYTES, ACC = 2;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t S = g.stages, nkb = g.K / 64;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * STAGE);
+    uint64_t *full_bar = bars, *empty_bar = bars + S, *tfull_bar = bars + 2 * S, *tempty_bar = tfull_bar + ACC;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + ACC);
+    float *bias_s = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~static_cast<uintptr_t>(15));  // [ACC][128]
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < S; ++i) {
+            mbar_init(smem_u32(full_bar + i), 1);
+            mbar_init(smem_u32(empty_bar + i), 1);
+        }
+        for (uint32_t i = 0; i < ACC; ++i) {
+            mbar_init(smem_u32(tfull_bar + i), 1);
+            mbar_init(smem_u32(tempty_bar + i), 128);
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_w);
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), ACC * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t total = m_tiles * n_tiles;
+    const uint32_t my_tiles = blockIdx.x < total ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t st = 0, ph = 0;
+            for (uint32_t i = 0; i < my_tiles; ++i) {
+                const uint32_t tile = blockIdx.x + i * gridDim.x, m0 = (tile / n_tiles) * 128, n0 = (tile % n_tiles) * BN;
+                for (uint32_t kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(smem_u32(empty_bar + st), ph ^ 1);
+                    mbar_arrive_expect_tx(smem_u32(full_bar + st), STAGE);
+                    const uint32_t sa = smem_u32(smem + (size_t)st * STAGE);
+                    tma_load_2d(sa, &tmap_a, smem_u32(full_bar + st), (int32_t)(kb * 64), (int32_t)m0);
+                    tma_load_2d(sa + A_BYTES, &tmap_w, smem_u32(full_bar + st), (int32_t)(kb * 64), (int32_t)n0);
+                    if (++st == S) { st = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(128, BN);
+            uint32_t st = 0, ph = 0;
+            for (uint32_t i = 0; i < my_tiles; ++i) {
+                const uint32_t acc = i & 1, acc_ph = (i >> 1) & 1;
+                mbar_wait(smem_u32(tempty_bar + acc), acc_ph ^ 1);
+                tc_fence_after();
+                for (uint32_t kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(smem_u32(full_bar + st), ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)st * STAGE);
+                    const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + A_BYTES);
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; ++k)
+                        umma_f16(tmem_base + acc * BN, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(smem_u32(empty_bar + st));
+                    if (++st == S) { st = 0; ph ^= 1; }
+                }
+                umma_commit(smem_u32(tfull_bar + acc));
+            }
+        }
+    } else if (warp >= 4) {
+        const uint32_t t = threadIdx.x - 128;
+        const uint32_t lane_base = ((warp & 3) * 32) << 16;
+        for (uint32_t i = 0; i < my_tiles; ++i) {
+            const uint32_t tile = blockIdx.x + i * gridDim.x, m0 = (tile / n_tiles) * 128, n0 = (tile % n_tiles) * BN;
+            const uint32_t acc = i & 1, acc_ph = (i >> 1) & 1;
+            bias_s[acc * BN + t] = g.bias[n0 + t];            // safe: this slot's previous tile was fully drained
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(smem_u32(tfull_bar + acc), acc_ph);
+            tc_fence_after();
+            const uint32_t row = m0 + t;
+#pragma unroll 1
+            for (uint32_t c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + lane_base + acc * BN + c * 32, r);
+                tmem_ld_wait();
+                __align__(16) __half o[32];
+#pragma unroll
+                for (uint32_t j = 0; j < 32; ++j) {
+                    float v = __uint_as_float(r[j]) + bias_s[acc * BN + c * 32 + j];
+                    if constexpr (EPI == EPI_BIAS_GELU) v = gelu_erf(v);
+                    o[j] = __float2half_rn(v);
+                }
+                uint4 *dst = reinterpret_cast<uint4 *>(g.out + (size_t)row * g.N + n0 + c * 32);
+#pragma unroll
+                for (uint32_t q = 0; q < 4; ++q) dst[q] = reinterpret_cast<const uint4 *>(o)[q];
+            }
+            tc_fence_before();
+            mbar_arrive(smem_u32(tempty_bar + acc));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, ACC * BN);
+    }
+}
+
 // ---- embeddings: word + position + token_type(0), LayerNorm -> fp16 ---------------------------------
 // one warp per token; rows >= T (padding up to a multiple of 128) are zeroed.
 __global__ void embed_ln_kernel(const int64_t *__restrict__ ids, uint32_t T, uint32_t T_pad, uint32_t L, uint32_t H,
@@ -658,6 +773,21 @@ cudaError_t launch_gemm(const CUtensorMap &ta, const CUtensorMap &tw, const Gemm
     return cudaGetLastError();
 }
 
+template <uint32_t EPI>
+cudaError_t launch_gemm_persist(const CUtensorMap &ta, const CUtensorMap &tw, const GemmArgs &g, uint32_t m_tiles,
+                                uint32_t sm_count, cudaStream_t st)
+{
+    const uint32_t n_tiles = g.N / 128, total = m_tiles * n_tiles;
+    const size_t smem = (size_t)g.stages * (128 * 128 + 128 * 128) + (2 * g.stages + 4) * 8 + 48 + 2 * 128 * 4;
+    auto kern = gemm_tc_persist_kernel<EPI>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const uint32_t grid = total < 2 * sm_count ? total : 2 * sm_count;
+    kern<<<grid, G_THREADS, smem, st>>>(ta, tw, g, m_tiles, n_tiles);
+    count_launch();
+    return cudaGetLastError();
+}
+
 struct Layer {
     __half *wqkv, *wo, *w1, *w2;          // [1152,H] [H,H] [F,H] [H,F]
     float *bqkv, *bo, *b1, *b2, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
@@ -869,6 +999,7 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
     const size_t att_smem = ((size_t)32 * (L + 1) + (size_t)L * 32 + 4 * (size_t)L) * 4 + L;
     if (att_smem > 48 * 1024)
         SG_CUDA_TRY(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
+    const bool persist = m_tiles * 9 >= 2 * 148 && !getenv("SG_ENC_NO_PERSIST");   // enough tiles to fill 2 CTAs per SM
     for (uint32_t l = 0; l < e->layers; ++l) {
         const Layer &ly = e->L[l];
         CUtensorMap t_wqkv, t_wo, t_w1, t_w2;
@@ -879,7 +1010,8 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
         GemmArgs g{};
         // QKV = h0 . Wqkv^T + b
         g.K = H; g.N = 3 * H; g.stages = 3; g.bias = ly.bqkv; g.out = e->qkv;   // 96 KB: two CTAs per SM
-        SG_CUDA_TRY((launch_gemm<128, EPI_BIAS>(t_h0, t_wqkv, g, m_tiles, st)));
+        if (persist) SG_CUDA_TRY((launch_gemm_persist<EPI_BIAS>(t_h0, t_wqkv, g, m_tiles, 148, st)));
+        else SG_CUDA_TRY((launch_gemm<128, EPI_BIAS>(t_h0, t_wqkv, g, m_tiles, st)));
         if (L <= 128 && !getenv("SG_ENC_ATTN_SIMT")) {
             switch ((L + 15) / 16) {
             case 1: launch_attention_mma<1>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st); break;
@@ -909,7 +1041,8 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
         // mid = gelu(h1 . W1^T + b)
         g = GemmArgs{};
         g.K = H; g.N = F; g.stages = 3; g.bias = ly.b1; g.out = e->mid;
-        SG_CUDA_TRY((launch_gemm<128, EPI_BIAS_GELU>(t_h1, t_w1, g, m_tiles, st)));
+        if (persist) SG_CUDA_TRY((launch_gemm_persist<EPI_BIAS_GELU>(t_h1, t_w1, g, m_tiles, 148, st)));
+        else SG_CUDA_TRY((launch_gemm<128, EPI_BIAS_GELU>(t_h1, t_w1, g, m_tiles, st)));
         // h0 = LN(mid . W2^T + b + h1)
         g = GemmArgs{};
         g.K = F; g.N = H; g.stages = 3; g.bias = ly.b2; g.residual = e->h1; g.gamma = ly.ln2_g; g.beta = ly.ln2_b;
