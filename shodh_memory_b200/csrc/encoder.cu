@@ -239,13 +239,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 template <uint32_t EPI>
 __global__ void __launch_bounds__(G_THREADS, 2)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                       const GemmArgs g, const uint32_t m_tiles, const uint32_t n_tiles)
+                       const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g, const uint32_t m_tiles,
+                       const uint32_t n_tiles)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr uint32_t BN = 128, A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE = A_BYTES + B_BYTES, ACC = 2;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t S = g.stages, nkb = g.K / 64;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * STAGE);
+    // output staging: the 128x128 fp16 tile as two SWIZZLE_128B boxes (64 columns each), drained by TMA stores
+    uint8_t *stage_out = smem + (size_t)S * STAGE;                      // 32 KB, 1024-aligned
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage_out + 2 * 128 * 128);
     uint64_t *full_bar = bars, *empty_bar = bars + S, *tfull_bar = bars + 2 * S, *tempty_bar = tfull_bar + ACC;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + ACC);
     float *bias_s = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~static_cast<uintptr_t>(15));  // [ACC][128]
@@ -314,10 +317,11 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             const uint32_t tile = blockIdx.x + i * gridDim.x, m0 = (tile / n_tiles) * 128, n0 = (tile % n_tiles) * BN;
             const uint32_t acc = i & 1, acc_ph = (i >> 1) & 1;
             bias_s[acc * BN + t] = g.bias[n0 + t];            // safe: this slot's previous tile was fully drained
+            if (t == 0) tma_store_wait_read();                // the previous tile's TMA stores have consumed the staging
             asm volatile("bar.sync 1, 128;" ::: "memory");
             mbar_wait(smem_u32(tfull_bar + acc), acc_ph);
             tc_fence_after();
-            const uint32_t row = m0 + t;
+            const uint32_t sw = (t & 7) << 4;
 #pragma unroll 1
             for (uint32_t c = 0; c < BN / 32; ++c) {
                 uint32_t r[32];
@@ -330,13 +334,23 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     if constexpr (EPI == EPI_BIAS_GELU) v = gelu_erf(v);
                     o[j] = __float2half_rn(v);
                 }
-                uint4 *dst = reinterpret_cast<uint4 *>(g.out + (size_t)row * g.N + n0 + c * 32);
+                // row t of box (c / 2): 16-byte pieces (c % 2) * 4 + q, XOR-swizzled like the TMA expects
+                uint8_t *rowp = stage_out + (size_t)(c >> 1) * (128 * 128) + (size_t)t * 128;
 #pragma unroll
-                for (uint32_t q = 0; q < 4; ++q) dst[q] = reinterpret_cast<const uint4 *>(o)[q];
+                for (uint32_t q = 0; q < 4; ++q)
+                    *reinterpret_cast<uint4 *>(rowp + ((((c & 1) * 4 + q) << 4) ^ sw)) = reinterpret_cast<const uint4 *>(o)[q];
             }
             tc_fence_before();
-            mbar_arrive(smem_u32(tempty_bar + acc));
+            mbar_arrive(smem_u32(tempty_bar + acc));          // accumulator drained: the next tile may start
+            fence_proxy_async();                              // generic smem writes -> visible to the TMA engine
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (t == 0) {
+                tma_store_2d(&tmap_out, smem_u32(stage_out), (int32_t)n0, (int32_t)m0);
+                tma_store_2d(&tmap_out, smem_u32(stage_out + 128 * 128), (int32_t)(n0 + 64), (int32_t)m0);
+                tma_store_commit();
+            }
         }
+        if (t == 0) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -774,16 +788,16 @@ cudaError_t launch_gemm(const CUtensorMap &ta, const CUtensorMap &tw, const Gemm
 }
 
 template <uint32_t EPI>
-cudaError_t launch_gemm_persist(const CUtensorMap &ta, const CUtensorMap &tw, const GemmArgs &g, uint32_t m_tiles,
-                                uint32_t sm_count, cudaStream_t st)
+cudaError_t launch_gemm_persist(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &tout, const GemmArgs &g,
+                                uint32_t m_tiles, uint32_t sm_count, cudaStream_t st)
 {
     const uint32_t n_tiles = g.N / 128, total = m_tiles * n_tiles;
-    const size_t smem = (size_t)g.stages * (128 * 128 + 128 * 128) + (2 * g.stages + 4) * 8 + 48 + 2 * 128 * 4;
+    const size_t smem = (size_t)g.stages * (128 * 128 + 128 * 128) + 2 * 128 * 128 + (2 * g.stages + 4) * 8 + 48 + 2 * 128 * 4;
     auto kern = gemm_tc_persist_kernel<EPI>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const uint32_t grid = total < 2 * sm_count ? total : 2 * sm_count;
-    kern<<<grid, G_THREADS, smem, st>>>(ta, tw, g, m_tiles, n_tiles);
+    kern<<<grid, G_THREADS, smem, st>>>(ta, tw, tout, g, m_tiles, n_tiles);
     count_launch();
     return cudaGetLastError();
 }
@@ -991,11 +1005,12 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
     embed_ln_kernel<<<(T_pad * 32 + 255) / 256, 256, 0, st>>>(d_ids, T, T_pad, L, H, e->vocab, e->word, e->pos, e->type0,
                                                                e->emb_g, e->emb_b, e->eps, e->h0);
     count_launch();
-    CUtensorMap t_h0, t_h1, t_ctx, t_mid;
+    CUtensorMap t_h0, t_h1, t_ctx, t_mid, t_qkv_out;
     if ((rc = encode_tmap(&t_h0, e->h0, H, T_pad, 128)) != SG_OK) return rc;
     if ((rc = encode_tmap(&t_h1, e->h1, H, T_pad, 128)) != SG_OK) return rc;
     if ((rc = encode_tmap(&t_ctx, e->ctx, H, T_pad, 128)) != SG_OK) return rc;
-    if ((rc = encode_tmap(&t_mid, e->mid, F, T_pad, 128)) != SG_OK) return rc;
+    if ((rc = encode_tmap(&t_mid, e->mid, F, T_pad, 128)) != SG_OK) return rc;          // load map of FFN-down == store map of FFN-up
+    if ((rc = encode_tmap(&t_qkv_out, e->qkv, 3 * H, T_pad, 128)) != SG_OK) return rc;
     const size_t att_smem = ((size_t)32 * (L + 1) + (size_t)L * 32 + 4 * (size_t)L) * 4 + L;
     if (att_smem > 48 * 1024)
         SG_CUDA_TRY(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
@@ -1010,7 +1025,10 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
         GemmArgs g{};
         // QKV = h0 . Wqkv^T + b
         g.K = H; g.N = 3 * H; g.stages = 3; g.bias = ly.bqkv; g.out = e->qkv;   // 96 KB: two CTAs per SM
-        if (persist) SG_CUDA_TRY((launch_gemm_persist<EPI_BIAS>(t_h0, t_wqkv, g, m_tiles, 148, st)));
+        if (persist) {
+            g.stages = 2;
+            SG_CUDA_TRY((launch_gemm_persist<EPI_BIAS>(t_h0, t_wqkv, t_qkv_out, g, m_tiles, 148, st)));
+        }
         else SG_CUDA_TRY((launch_gemm<128, EPI_BIAS>(t_h0, t_wqkv, g, m_tiles, st)));
         if (L <= 128 && !getenv("SG_ENC_ATTN_SIMT")) {
             switch ((L + 15) / 16) {
@@ -1041,7 +1059,10 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
         // mid = gelu(h1 . W1^T + b)
         g = GemmArgs{};
         g.K = H; g.N = F; g.stages = 3; g.bias = ly.b1; g.out = e->mid;
-        if (persist) SG_CUDA_TRY((launch_gemm_persist<EPI_BIAS_GELU>(t_h1, t_w1, g, m_tiles, 148, st)));
+        if (persist) {
+            g.stages = 2;
+            SG_CUDA_TRY((launch_gemm_persist<EPI_BIAS_GELU>(t_h1, t_w1, t_mid, g, m_tiles, 148, st)));
+        }
         else SG_CUDA_TRY((launch_gemm<128, EPI_BIAS_GELU>(t_h1, t_w1, g, m_tiles, st)));
         // h0 = LN(mid . W2^T + b + h1)
         g = GemmArgs{};

@@ -109,6 +109,16 @@ SG_DEVICE_INLINE void tma_load_2d(uint32_t dst_smem, const CUtensorMap *tmap, ui
         ::"r"(dst_smem), "l"((uint64_t)tmap), "r"(bar), "r"(x), "r"(y)
         : "memory");
 }
+// 2-D tiled TMA store shared -> global (bulk async-group completion; SASS: UTMASTG)
+SG_DEVICE_INLINE void tma_store_2d(const CUtensorMap *tmap, uint32_t src_smem, int32_t x, int32_t y)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"((uint64_t)tmap), "r"(src_smem), "r"(x), "r"(y)
+                 : "memory");
+}
+SG_DEVICE_INLINE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+SG_DEVICE_INLINE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+SG_DEVICE_INLINE void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 SG_DEVICE_INLINE void tma_prefetch_desc(const CUtensorMap *tmap)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tmap) : "memory");
