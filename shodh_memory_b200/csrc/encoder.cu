@@ -32,6 +32,7 @@ namespace {
 
 constexpr uint32_t EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RES_LN = 2;
 constexpr uint32_t G_THREADS = 256;
+constexpr uint32_t P_THREADS = 384;   // persistent GEMM: 4 control warps + 8 epilogue warps
 
 struct GemmArgs {
     uint32_t K;            // reduction length (multiple of 64)
@@ -57,8 +58,10 @@ SG_DEVICE_INLINE float gelu_erf(float x)
 }
 
 // C tile = 128 rows x BN columns, one tile per CTA.  grid = (M_pad/128, N/BN).
+// The LayerNorm form runs 8 epilogue warps (384 threads): warps w and w+4 share a TMEM lane quarter and
+// each owns half of the row's columns; the row statistics are combined through shared memory.
 template <uint32_t BN, uint32_t EPI>
-__global__ void __launch_bounds__(G_THREADS, BN <= 128 ? 2 : 1)
+__global__ void __launch_bounds__(EPI == EPI_BIAS_RES_LN ? P_THREADS : G_THREADS, BN <= 128 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const GemmArgs g)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -132,18 +135,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else if (warp >= 4) {
         // epilogue: thread t <-> output row m0 + t <-> TMEM lane t
-        const uint32_t t = threadIdx.x - 128;
+        constexpr uint32_t EPI_T = EPI == EPI_BIAS_RES_LN ? 256 : 128;     // epilogue threads
+        const uint32_t et = threadIdx.x - 128;
+        const uint32_t t = et & 127;                                       // tile row = TMEM lane
+        const uint32_t half = et >> 7;                                     // LN form: which half of the columns
         const uint32_t row = m0 + t;
         const uint32_t lane_base = ((warp & 3) * 32) << 16;
-        // stage the per-column parameters while the main loop runs (named barrier over the 4 epilogue warps)
-        for (uint32_t i = t; i < BN; i += 128) {
+        // stage the per-column parameters while the main loop runs (named barrier over the epilogue warps)
+        for (uint32_t i = et; i < BN; i += EPI_T) {
             par_s[i] = g.bias[n0 + i];
             if constexpr (EPI == EPI_BIAS_RES_LN) {
                 par_s[BN + i] = g.gamma[n0 + i];
                 par_s[2 * BN + i] = g.beta[n0 + i];
             }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_T) : "memory");
         mbar_wait(smem_u32(done_bar), 0);
         tc_fence_after();
         if constexpr (EPI == EPI_BIAS_RES_LN) {
@@ -155,8 +161,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const float4 *gam4 = reinterpret_cast<const float4 *>(par_s + BN);
             const float4 *bet4 = reinterpret_cast<const float4 *>(par_s + 2 * BN);
             float sum = 0.0f, sq = 0.0f;
+            constexpr uint32_t CH = BN / 64;                    // chunks per half
 #pragma unroll 1
-            for (uint32_t c = 0; c < BN / 32; ++c) {
+            for (uint32_t c = half * CH; c < half * CH + CH; ++c) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + lane_base + c * 32, r);
                 uint4 rv[4];
@@ -178,11 +185,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 tmem_st32(tmem_base + lane_base + c * 32, r);
             }
             tmem_st_wait();
+            // combine the two halves' statistics (each thread wrote its own half back into TMEM)
+            float *part = par_s + 3 * BN;                       // [2][128][2]
+            part[(half * 128 + t) * 2] = sum;
+            part[(half * 128 + t) * 2 + 1] = sq;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            sum += part[((half ^ 1) * 128 + t) * 2];
+            sq += part[((half ^ 1) * 128 + t) * 2 + 1];
             const float mean = sum / (float)BN;
             const float var = fmaxf(sq / (float)BN - mean * mean, 0.0f);
             const float rstd = rsqrtf(var + g.eps);
 #pragma unroll 1
-            for (uint32_t c = 0; c < BN / 32; ++c) {
+            for (uint32_t c = half * CH; c < half * CH + CH; ++c) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + lane_base + c * 32, r);
                 tmem_ld_wait();
@@ -237,7 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // about as much as the 6-K-block main loop of a hidden-384 GEMM) runs while the tensor core already
 // works on the next tile.  96 KB of shared memory per CTA: two CTAs per SM (2 x 256 TMEM columns).
 template <uint32_t EPI>
-__global__ void __launch_bounds__(G_THREADS, 2)
+__global__ void __launch_bounds__(P_THREADS, 2)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                        const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g, const uint32_t m_tiles,
                        const uint32_t n_tiles)
@@ -259,7 +273,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         }
         for (uint32_t i = 0; i < ACC; ++i) {
             mbar_init(smem_u32(tfull_bar + i), 1);
-            mbar_init(smem_u32(tempty_bar + i), 128);
+            mbar_init(smem_u32(tempty_bar + i), 256);
         }
         mbar_fence_init();
         tma_prefetch_desc(&tmap_a);
@@ -311,19 +325,23 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             }
         }
     } else if (warp >= 4) {
-        const uint32_t t = threadIdx.x - 128;
+        // 8 epilogue warps: warps w and w+4 share TMEM lane quarter (w % 4); the first takes columns
+        // 0..63 of the tile, the second 64..127 -> twice the drain throughput of a 4-warp epilogue
+        const uint32_t et = threadIdx.x - 128;                 // 0..255
+        const uint32_t t = et & 127;                           // tile row = TMEM lane
+        const uint32_t half = et >> 7;                         // which 64-column half
         const uint32_t lane_base = ((warp & 3) * 32) << 16;
         for (uint32_t i = 0; i < my_tiles; ++i) {
             const uint32_t tile = blockIdx.x + i * gridDim.x, m0 = (tile / n_tiles) * 128, n0 = (tile % n_tiles) * BN;
             const uint32_t acc = i & 1, acc_ph = (i >> 1) & 1;
-            bias_s[acc * BN + t] = g.bias[n0 + t];            // safe: this slot's previous tile was fully drained
-            if (t == 0) tma_store_wait_read();                // the previous tile's TMA stores have consumed the staging
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (half == 0) bias_s[acc * BN + t] = g.bias[n0 + t];   // safe: this slot's previous tile was fully drained
+            if (et == 0) tma_store_wait_read();               // the previous tile's TMA stores have consumed the staging
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(smem_u32(tfull_bar + acc), acc_ph);
             tc_fence_after();
             const uint32_t sw = (t & 7) << 4;
 #pragma unroll 1
-            for (uint32_t c = 0; c < BN / 32; ++c) {
+            for (uint32_t c = half * 2; c < half * 2 + 2; ++c) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + lane_base + acc * BN + c * 32, r);
                 tmem_ld_wait();
@@ -343,14 +361,14 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             tc_fence_before();
             mbar_arrive(smem_u32(tempty_bar + acc));          // accumulator drained: the next tile may start
             fence_proxy_async();                              // generic smem writes -> visible to the TMA engine
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (t == 0) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (et == 0) {
                 tma_store_2d(&tmap_out, smem_u32(stage_out), (int32_t)n0, (int32_t)m0);
                 tma_store_2d(&tmap_out, smem_u32(stage_out + 128 * 128), (int32_t)(n0 + 64), (int32_t)m0);
                 tma_store_commit();
             }
         }
-        if (t == 0) tma_store_wait_all();
+        if (et == 0) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -778,11 +796,11 @@ template <uint32_t BN, uint32_t EPI>
 cudaError_t launch_gemm(const CUtensorMap &ta, const CUtensorMap &tw, const GemmArgs &g, uint32_t m_tiles, cudaStream_t st)
 {
     constexpr uint32_t STAGE = 128 * 128 + BN * 128;
-    const size_t smem = (size_t)g.stages * STAGE + (2 * g.stages + 1) * 8 + 48 + 3 * BN * 4;
+    const size_t smem = (size_t)g.stages * STAGE + (2 * g.stages + 1) * 8 + 48 + 3 * BN * 4 + 2 * 128 * 2 * 4;
     auto kern = gemm_tc_kernel<BN, EPI>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<dim3(m_tiles, g.N / BN), G_THREADS, smem, st>>>(ta, tw, g);
+    kern<<<dim3(m_tiles, g.N / BN), EPI == EPI_BIAS_RES_LN ? P_THREADS : G_THREADS, smem, st>>>(ta, tw, g);
     count_launch();
     return cudaGetLastError();
 }
@@ -797,7 +815,7 @@ cudaError_t launch_gemm_persist(const CUtensorMap &ta, const CUtensorMap &tw, co
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const uint32_t grid = total < 2 * sm_count ? total : 2 * sm_count;
-    kern<<<grid, G_THREADS, smem, st>>>(ta, tw, tout, g, m_tiles, n_tiles);
+    kern<<<grid, P_THREADS, smem, st>>>(ta, tw, tout, g, m_tiles, n_tiles);
     count_launch();
     return cudaGetLastError();
 }
