@@ -245,6 +245,168 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
 }
 
+// ---- LayerNorm GEMM split over a 3-CTA cluster ---------------------------------------------------
+// out = LayerNorm(A . W^T + bias + residual) with N = 384 = 3 x 128: the three CTAs of a cluster each
+// compute 128 of the 384 output columns of the same 128 rows (so the weight matrix is streamed by three
+// SMs in parallel -- what matters for the single-query case, where the whole GEMM is ONE row tile), and
+// exchange per-row (sum, sum of squares) partials through distributed shared memory before normalising.
+// 8 epilogue warps: warps w and w+4 share TMEM lane quarter w%4 and own 64 columns each.
+__global__ void __cluster_dims__(3, 1, 1) __launch_bounds__(P_THREADS, 1)
+gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const GemmArgs g)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr uint32_t BN = 128, A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE = A_BYTES + B_BYTES;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t S = g.stages, nkb = g.K / 64;
+    const uint32_t crank = cluster_ctarank();
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * STAGE);
+    uint64_t *full_bar = bars, *empty_bar = bars + S, *done_bar = bars + 2 * S;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
+    float *par_s = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~static_cast<uintptr_t>(15));
+    float *part = par_s + 3 * BN;        // [2 halves][128 rows][2]  this CTA's partial statistics (read by the peers)
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < S; ++i) {
+            mbar_init(smem_u32(full_bar + i), 1);
+            mbar_init(smem_u32(empty_bar + i), 1);
+        }
+        mbar_init(smem_u32(done_bar), 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_w);
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t m0 = (blockIdx.x / 3) * 128, n0 = crank * BN;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t st = 0, ph = 0;
+            for (uint32_t kb = 0; kb < nkb; ++kb) {
+                mbar_wait(smem_u32(empty_bar + st), ph ^ 1);
+                mbar_arrive_expect_tx(smem_u32(full_bar + st), STAGE);
+                const uint32_t sa = smem_u32(smem + (size_t)st * STAGE);
+                tma_load_2d(sa, &tmap_a, smem_u32(full_bar + st), (int32_t)(kb * 64), (int32_t)m0);
+                tma_load_2d(sa + A_BYTES, &tmap_w, smem_u32(full_bar + st), (int32_t)(kb * 64), (int32_t)n0);
+                if (++st == S) { st = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(128, BN);
+            uint32_t st = 0, ph = 0;
+            for (uint32_t kb = 0; kb < nkb; ++kb) {
+                mbar_wait(smem_u32(full_bar + st), ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)st * STAGE);
+                const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + A_BYTES);
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                umma_commit(smem_u32(empty_bar + st));
+                if (++st == S) { st = 0; ph ^= 1; }
+            }
+            umma_commit(smem_u32(done_bar));
+        }
+    }
+    float sum = 0.0f, sq = 0.0f;
+    const uint32_t et = threadIdx.x - 128, t = et & 127, half = (et >> 7) & 1;
+    const uint32_t row = m0 + t;
+    const uint32_t lane_base = ((warp & 3) * 32) << 16;
+    const bool epi = warp >= 4;
+    if (epi) {
+        for (uint32_t i = et; i < BN; i += 256) {
+            par_s[i] = g.bias[n0 + i];
+            par_s[BN + i] = g.gamma[n0 + i];
+            par_s[2 * BN + i] = g.beta[n0 + i];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mbar_wait(smem_u32(done_bar), 0);
+        tc_fence_after();
+        const uint4 *res4 = reinterpret_cast<const uint4 *>(g.residual + (size_t)row * g.N + n0);
+        const float4 *bias4 = reinterpret_cast<const float4 *>(par_s);
+#pragma unroll 1
+        for (uint32_t c = half * 2; c < half * 2 + 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + lane_base + c * 32, r);
+            uint4 rv[4];
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) rv[q] = res4[c * 4 + q];
+            tmem_ld_wait();
+#pragma unroll
+            for (uint32_t q = 0; q < 8; ++q) {
+                const float4 bb = bias4[c * 8 + q];
+                const __half2 *hp = reinterpret_cast<const __half2 *>(&rv[q >> 1]) + (q & 1) * 2;
+                const float2 r01 = __half22float2(hp[0]), r23 = __half22float2(hp[1]);
+                const float v0 = __uint_as_float(r[4 * q]) + bb.x + r01.x, v1 = __uint_as_float(r[4 * q + 1]) + bb.y + r01.y;
+                const float v2 = __uint_as_float(r[4 * q + 2]) + bb.z + r23.x, v3 = __uint_as_float(r[4 * q + 3]) + bb.w + r23.y;
+                sum += (v0 + v1) + (v2 + v3);
+                sq += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
+                r[4 * q] = __float_as_uint(v0); r[4 * q + 1] = __float_as_uint(v1);
+                r[4 * q + 2] = __float_as_uint(v2); r[4 * q + 3] = __float_as_uint(v3);
+            }
+            tmem_st32(tmem_base + lane_base + c * 32, r);
+        }
+        tmem_st_wait();
+        part[(half * 128 + t) * 2] = sum;
+        part[(half * 128 + t) * 2 + 1] = sq;
+    }
+    // every CTA's partials are in its shared memory: cluster barrier (release/acquire), then read the peers'
+    cluster_sync_all();
+    if (epi) {
+        sum = 0.0f;
+        sq = 0.0f;
+        const uint32_t my_part = smem_u32(part);
+#pragma unroll
+        for (uint32_t r = 0; r < 3; ++r) {
+            const uint32_t base = mapa_u32(my_part, r);
+#pragma unroll
+            for (uint32_t h = 0; h < 2; ++h) {
+                float a, b;
+                asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(a) : "r"(base + ((h * 128 + t) * 2) * 4) : "memory");
+                asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(b) : "r"(base + ((h * 128 + t) * 2 + 1) * 4) : "memory");
+                sum += a;
+                sq += b;
+            }
+        }
+        const float mean = sum / (float)g.N;
+        const float var = fmaxf(sq / (float)g.N - mean * mean, 0.0f);
+        const float rstd = rsqrtf(var + g.eps);
+        const float4 *gam4 = reinterpret_cast<const float4 *>(par_s + BN);
+        const float4 *bet4 = reinterpret_cast<const float4 *>(par_s + 2 * BN);
+#pragma unroll 1
+        for (uint32_t c = half * 2; c < half * 2 + 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + lane_base + c * 32, r);
+            tmem_ld_wait();
+            __align__(16) __half o[32];
+#pragma unroll
+            for (uint32_t q = 0; q < 8; ++q) {
+                const float4 gg = gam4[c * 8 + q], be = bet4[c * 8 + q];
+                float y[4];
+                y[0] = (__uint_as_float(r[4 * q]) - mean) * rstd * gg.x + be.x;
+                y[1] = (__uint_as_float(r[4 * q + 1]) - mean) * rstd * gg.y + be.y;
+                y[2] = (__uint_as_float(r[4 * q + 2]) - mean) * rstd * gg.z + be.z;
+                y[3] = (__uint_as_float(r[4 * q + 3]) - mean) * rstd * gg.w + be.w;
+#pragma unroll
+                for (uint32_t j = 0; j < 4; ++j) o[4 * q + j] = __float2half_rn(y[j]);
+                if (g.out_f32)
+                    *reinterpret_cast<float4 *>(g.out_f32 + (size_t)row * g.N + n0 + c * 32 + 4 * q) = make_float4(y[0], y[1], y[2], y[3]);
+            }
+            uint4 *dst = reinterpret_cast<uint4 *>(g.out + (size_t)row * g.N + n0 + c * 32);
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) dst[q] = reinterpret_cast<const uint4 *>(o)[q];
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();              // peers may still be reading this CTA's partials
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 128);
+    }
+}
+
 // ---- persistent 128x128-tile GEMM: epilogue of tile i overlaps the main loop of tile i+1 -----------
 // Same roles as gemm_tc_kernel, but every CTA walks tiles t = blockIdx.x, +gridDim.x, ... with TWO
 // accumulator stages in TMEM (2 x 128 columns), so the bias/GELU/convert/store epilogue (which costs
@@ -820,6 +982,17 @@ cudaError_t launch_gemm_persist(const CUtensorMap &ta, const CUtensorMap &tw, co
     return cudaGetLastError();
 }
 
+cudaError_t launch_gemm_ln_cluster(const CUtensorMap &ta, const CUtensorMap &tw, const GemmArgs &g, uint32_t m_tiles,
+                                   cudaStream_t st)
+{
+    const size_t smem = (size_t)g.stages * (128 * 128 + 128 * 128) + (2 * g.stages + 1) * 8 + 48 + 3 * 128 * 4 + 2 * 128 * 2 * 4;
+    cudaError_t e = cudaFuncSetAttribute(gemm_ln_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    gemm_ln_cluster_kernel<<<m_tiles * 3, P_THREADS, smem, st>>>(ta, tw, g);    // __cluster_dims__(3,1,1)
+    count_launch();
+    return cudaGetLastError();
+}
+
 struct Layer {
     __half *wqkv, *wo, *w1, *w2;          // [1152,H] [H,H] [F,H] [H,F]
     float *bqkv, *bo, *b1, *b2, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
@@ -1032,14 +1205,15 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
     const size_t att_smem = ((size_t)32 * (L + 1) + (size_t)L * 32 + 4 * (size_t)L) * 4 + L;
     if (att_smem > 48 * 1024)
         SG_CUDA_TRY(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
+    const bool ln_cluster = !getenv("SG_ENC_NO_LN_CLUSTER");   // 3-CTA cluster LayerNorm GEMM (weights streamed by 3 SMs)
     const bool persist = m_tiles * 9 >= 2 * 148 && !getenv("SG_ENC_NO_PERSIST");   // enough tiles to fill 2 CTAs per SM
     for (uint32_t l = 0; l < e->layers; ++l) {
         const Layer &ly = e->L[l];
         CUtensorMap t_wqkv, t_wo, t_w1, t_w2;
         if ((rc = encode_tmap(&t_wqkv, ly.wqkv, H, 3 * H, 128)) != SG_OK) return rc;
-        if ((rc = encode_tmap(&t_wo, ly.wo, H, H, H / 2)) != SG_OK) return rc;
+        if ((rc = encode_tmap(&t_wo, ly.wo, H, H, ln_cluster ? 128 : H / 2)) != SG_OK) return rc;
         if ((rc = encode_tmap(&t_w1, ly.w1, H, F, 128)) != SG_OK) return rc;
-        if ((rc = encode_tmap(&t_w2, ly.w2, F, H, H / 2)) != SG_OK) return rc;
+        if ((rc = encode_tmap(&t_w2, ly.w2, F, H, ln_cluster ? 128 : H / 2)) != SG_OK) return rc;
         GemmArgs g{};
         // QKV = h0 . Wqkv^T + b
         g.K = H; g.N = 3 * H; g.stages = 3; g.bias = ly.bqkv; g.out = e->qkv;   // 96 KB: two CTAs per SM
@@ -1073,7 +1247,12 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
         g = GemmArgs{};
         g.K = H; g.N = H; g.stages = 3; g.bias = ly.bo; g.residual = e->h0; g.gamma = ly.ln1_g; g.beta = ly.ln1_b;
         g.eps = e->eps; g.out = e->h1;
-        SG_CUDA_TRY((launch_gemm<384, EPI_BIAS_RES_LN>(t_ctx, t_wo, g, m_tiles, st)));
+        if (ln_cluster) {
+            g.stages = 6;
+            SG_CUDA_TRY(launch_gemm_ln_cluster(t_ctx, t_wo, g, m_tiles, st));
+        } else {
+            SG_CUDA_TRY((launch_gemm<384, EPI_BIAS_RES_LN>(t_ctx, t_wo, g, m_tiles, st)));
+        }
         // mid = gelu(h1 . W1^T + b)
         g = GemmArgs{};
         g.K = H; g.N = F; g.stages = 3; g.bias = ly.b1; g.out = e->mid;
@@ -1086,7 +1265,12 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
         g = GemmArgs{};
         g.K = F; g.N = H; g.stages = 3; g.bias = ly.b2; g.residual = e->h1; g.gamma = ly.ln2_g; g.beta = ly.ln2_b;
         g.eps = e->eps; g.out = e->h0; g.out_f32 = (l + 1 == e->layers) ? e->hf32 : nullptr;
-        SG_CUDA_TRY((launch_gemm<384, EPI_BIAS_RES_LN>(t_mid, t_w2, g, m_tiles, st)));
+        if (ln_cluster) {
+            g.stages = 6;
+            SG_CUDA_TRY(launch_gemm_ln_cluster(t_mid, t_w2, g, m_tiles, st));
+        } else {
+            SG_CUDA_TRY((launch_gemm<384, EPI_BIAS_RES_LN>(t_mid, t_w2, g, m_tiles, st)));
+        }
     }
     pool_norm_kernel<<<b, 384, H * 4, st>>>(e->hf32, d_mask, L, H, d_out);
     count_launch();
