@@ -409,10 +409,12 @@ int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint
     // pre-pass (large corpora): every CTA (pair) scores its first few tiles and keeps only its best live
     // score per query; the kk-th largest of those maxima seeds a valid GPU-wide threshold, so the sweep
     // does far fewer list insertions than with CTA-local thresholds alone.
-    // tiles of the pre-pass per list: ~1/8 of a list's tiles at most, 16 (pair) / 4 (1-CTA) on large corpora
+    // tiles of the pre-pass per list: ~1/16 of a list's tiles at most (the pre-pass rows are scanned twice),
+    // 16 (pair) / 4 (1-CTA) on large corpora
     const uint64_t tiles_per_list = n_tiles / n_lists;
     uint32_t pre_tiles = pair ? 16 : 4;
-    if (tiles_per_list / 8 < pre_tiles) pre_tiles = (uint32_t)(tiles_per_list / 8);
+    if (tiles_per_list / 16 < pre_tiles) pre_tiles = (uint32_t)(tiles_per_list / 16);
+    if (pre_tiles == 0 && tiles_per_list >= 8) pre_tiles = 1;
     const int pre_env = env_u32("SG_TC_PRE_TILES", -1);
     if (pre_env >= 0) pre_tiles = (uint32_t)pre_env;
     const bool prepass = pre_tiles > 0 && n_lists >= kk;
