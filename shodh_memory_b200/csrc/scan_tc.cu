@@ -631,8 +631,15 @@ cudaError_t launch_prep_queries(const float *d_q, uint32_t b, uint32_t b_pad, ui
 cudaError_t launch_scan_tc(const CUtensorMap &tmap_rows, const CUtensorMap &tmap_q, const TcArgs &a, uint32_t grid,
                            size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    static size_t smem_set_dev[64] = {0};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    size_t &smem_set = smem_set_dev[dev_ & 63];
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        smem_set = smem;
+    }
     scan_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmap_rows, tmap_q, a);
     count_launch();
     return cudaGetLastError();
@@ -641,8 +648,15 @@ cudaError_t launch_scan_tc(const CUtensorMap &tmap_rows, const CUtensorMap &tmap
 cudaError_t launch_scan_tc2(const CUtensorMap &tmap_rows, const CUtensorMap &tmap_q, const TcArgs &a, uint32_t grid,
                             size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(scan_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    static size_t smem_set_dev[64] = {0};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    size_t &smem_set = smem_set_dev[dev_ & 63];
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(scan_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        smem_set = smem;
+    }
     scan_tc2_kernel<<<grid, TC_THREADS, smem, st>>>(tmap_rows, tmap_q, a);   // __cluster_dims__(2,1,1): grid must be even
     count_launch();
     return cudaGetLastError();

@@ -151,8 +151,15 @@ cudaError_t launch(const uint64_t *lists, const uint32_t *ids_in, const float *d
     size_t smem = (size_t)need * 8;
     uint32_t threads = need / 2 < 1024 ? (need / 2 < 32 ? 32 : need / 2) : 1024;
     auto kern = merge_kernel<PAIRS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SORT_MAX * 8));
-    if (e != cudaSuccess) return e;
+    static bool attr_set_dev[64] = {false};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    bool &attr_set = attr_set_dev[dev_ & 63];
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SORT_MAX * 8));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
     kern<<<b * n_groups, threads, smem, st>>>(lists, ids_in, dist_in, n_per_query, group_keys, n_groups, k, id_base,
                                               list_stride, query_stride, keys_out, ids, dist, counts, slot_count,
                                               slot_to_query);
