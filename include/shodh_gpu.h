@@ -123,6 +123,16 @@ SG_API int sg_store_set_id_base(sg_store *s, uint32_t id_base);
 SG_API int sg_store_search(sg_store *s, const float *queries_f32, uint32_t b, uint32_t k,
                            uint32_t *ids_out, float *dist_out, uint32_t *counts_out);
 
+/* RetrievalEngine::search_ids from the embedding on (src/memory/retrieval.rs:905-964): the vector id ->
+ * MemoryId table of IdMapping (vec2mem[i] = the Uuid of the memory that owns vector i as two big-endian
+ * u64 halves; all-ones = no mapping) is registered once; a search then asks the scan for
+ * limit * VECTOR_SEARCH_CANDIDATE_MULTIPLIER(2) * 2 candidates (:915-916), and ON THE DEVICE converts
+ * similarity = -distance, keeps the best chunk per memory, sorts (similarity desc, MemoryId asc) and
+ * truncates to limit (:927-961).  mem_out [b,limit,2] u64, sim_out [b,limit], counts_out [b]; limit <= 256. */
+SG_API int sg_store_set_memory_ids(sg_store *s, const uint64_t *vec2mem, uint64_t n);
+SG_API int sg_store_search_memory_ids(sg_store *s, const float *queries_f32, uint32_t b, uint32_t limit,
+                                      uint64_t *mem_out, float *sim_out, uint32_t *counts_out);
+
 /* same, with queries and results resident in device memory and asynchronous on
  * `cuda_stream` (a cudaStream_t; NULL = the CUDA default stream).  This is the
  * form the GPU encoder feeds and the multi-GPU exchange consumes. */

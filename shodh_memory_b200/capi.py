@@ -89,6 +89,8 @@ def lib() -> C.CDLL:
     L.sg_store_set_profiling.argtypes = [vp, C.c_int]
     L.sg_store_last_scan_ms.argtypes = [vp, f32p, u32p]
     L.sg_store_search.argtypes = [vp, f32p, C.c_uint32, C.c_uint32, u32p, f32p, u32p]
+    L.sg_store_set_memory_ids.argtypes = [vp, u64p, C.c_uint64]
+    L.sg_store_search_memory_ids.argtypes = [vp, f32p, C.c_uint32, C.c_uint32, u64p, f32p, u32p]
     L.sg_store_search_device.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
     L.sg_merge_topk_device.argtypes = [C.c_int, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
     L.sg_merge_topk_device_strided.argtypes = [C.c_int, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,

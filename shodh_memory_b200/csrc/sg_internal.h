@@ -102,6 +102,11 @@ cudaError_t launch_fuse_rank(const FuseDev &f, uint32_t n, sg_fuse_weights w, sg
                              int64_t now_s, uint32_t *d_order, float *d_score, uint32_t *d_n_out,
                              float *d_all, cudaStream_t st);
 
+// ---- post.cu ----
+cudaError_t launch_search_ids_post(const uint32_t *d_ids, const float *d_dist, const uint32_t *d_counts, uint32_t b, uint32_t k,
+                                   const uint64_t *d_vec2mem, uint64_t n_map, uint32_t id_base, uint32_t limit,
+                                   uint64_t *d_mem_out, float *d_sim_out, uint32_t *d_cnt_out, cudaStream_t st);
+
 // ---- tensor map (store.cu) ----
 int encode_corpus_tmap(CUtensorMap *out, const void *d_rows, bool f16, uint32_t dim, uint64_t n_rows,
                        uint32_t box_rows);

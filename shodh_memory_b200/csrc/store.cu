@@ -131,6 +131,10 @@ struct sg_store {
     uint64_t *d_cand = nullptr; size_t cand_cap_q = 0;     // [b_pad][grid][kk] per-CTA candidate lists
     uint64_t tc_searches = 0, tc_flagged = 0;              // statistics (sg_store_tc_stats)
 
+    // vector id -> MemoryId table (IdMapping of RetrievalEngine, retrieval.rs:64-140) + search_ids scratch
+    uint64_t *d_vec2mem = nullptr; uint64_t n_map = 0; size_t map_cap = 0;
+    uint64_t *d_mem_out = nullptr; float *d_sim_out = nullptr; uint32_t *d_memcnt = nullptr; size_t post_cap = 0, postc_cap = 0;
+
     bool profiling = false;
     std::vector<cudaEvent_t> ev;  // pairs: ev[2i] before, ev[2i+1] after the sweep launches of search i
     uint32_t ev_count = 0;        // searches recorded since the last read/reset
@@ -605,6 +609,10 @@ void sg_store_destroy(sg_store *s)
     cudaFree(s->d_dist);
     cudaFree(s->d_counts);
     cudaFree(s->d_stage);
+    cudaFree(s->d_vec2mem);
+    cudaFree(s->d_mem_out);
+    cudaFree(s->d_sim_out);
+    cudaFree(s->d_memcnt);
     cudaFree(s->d_max_norm);
     cudaFree(s->d_qh);
     cudaFree(s->d_qerr);
@@ -905,6 +913,71 @@ int sg_store_search(sg_store *s, const float *queries, uint32_t b, uint32_t k, u
     memcpy(ids_out, hp + qbytes, rbytes);
     memcpy(dist_out, hp + qbytes + rbytes, rbytes);
     memcpy(counts_out, hp + qbytes + 2 * rbytes, cbytes);
+    return SG_OK;
+}
+
+int sg_store_set_memory_ids(sg_store *s, const uint64_t *vec2mem, uint64_t n)
+{
+    if (!s || (n && !vec2mem)) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    SG_CUDA_TRY(cudaSetDevice(s->device));
+    int rc = grow(s->d_vec2mem, s->map_cap, (size_t)(n ? n : 1) * 2);
+    if (rc != SG_OK) return rc;
+    if (n) SG_CUDA_TRY(cudaMemcpy(s->d_vec2mem, vec2mem, (size_t)n * 16, cudaMemcpyHostToDevice));
+    s->n_map = n;
+    return SG_OK;
+}
+
+int sg_store_search_memory_ids(sg_store *s, const float *queries, uint32_t b, uint32_t limit, uint64_t *mem_out,
+                               float *sim_out, uint32_t *counts_out)
+{
+    if (!s || (b && (!queries || !mem_out || !sim_out || !counts_out))) return SG_ERR_INVALID;
+    if (b == 0) return SG_OK;
+    // retrieval.rs:915-916: k = limit * VECTOR_SEARCH_CANDIDATE_MULTIPLIER (2, constants.rs:350) * 2
+    const uint64_t k64 = (uint64_t)limit * 4;
+    if (limit == 0 || k64 > 1024) {
+        set_error("limit=%u: the scan is asked for 4*limit candidates, supported up to 1024", limit);
+        return limit == 0 ? SG_ERR_INVALID : SG_ERR_UNSUPPORTED;
+    }
+    const uint32_t k = (uint32_t)k64;
+    std::lock_guard<std::mutex> g(s->mu);
+    SG_CUDA_TRY(cudaSetDevice(s->device));
+    const size_t qbytes = (size_t)b * s->dim * 4;
+    int rc = grow_pinned(s, qbytes + (size_t)b * limit * 20 + (size_t)b * 4);
+    if (rc != SG_OK) return rc;
+    if ((rc = grow(s->d_queries, s->q_cap, (size_t)b * s->dim)) != SG_OK) return rc;
+    if ((size_t)b * k > s->res_cap) {
+        size_t c1 = s->res_cap, c2 = s->res_cap;
+        if ((rc = grow(s->d_ids, c1, (size_t)b * k)) != SG_OK) return rc;
+        if ((rc = grow(s->d_dist, c2, (size_t)b * k)) != SG_OK) return rc;
+        s->res_cap = c1 < c2 ? c1 : c2;
+    }
+    if ((rc = grow(s->d_counts, s->cnt_cap, (size_t)b)) != SG_OK) return rc;
+    if ((size_t)b * limit > s->post_cap) {
+        size_t c1 = s->post_cap, c2 = s->post_cap;
+        uint64_t *m = s->d_mem_out;
+        size_t cm = c1 * 2;
+        if ((rc = grow(m, cm, (size_t)b * limit * 2)) != SG_OK) return rc;
+        s->d_mem_out = m;
+        if ((rc = grow(s->d_sim_out, c2, (size_t)b * limit)) != SG_OK) return rc;
+        s->post_cap = c2 < cm / 2 ? c2 : cm / 2;
+    }
+    if ((rc = grow(s->d_memcnt, s->postc_cap, (size_t)b)) != SG_OK) return rc;
+    uint8_t *hp = static_cast<uint8_t *>(s->h_pinned);
+    memcpy(hp, queries, qbytes);
+    SG_CUDA_TRY(cudaMemcpyAsync(s->d_queries, hp, qbytes, cudaMemcpyHostToDevice, s->stream));
+    rc = search_device_locked(s, s->d_queries, b, k, s->d_ids, s->d_dist, s->d_counts, s->stream);
+    if (rc != SG_OK) return rc;
+    SG_CUDA_TRY(launch_search_ids_post(s->d_ids, s->d_dist, s->d_counts, b, k, s->d_vec2mem, s->n_map, s->id_base, limit,
+                                       s->d_mem_out, s->d_sim_out, s->d_memcnt, s->stream));
+    const size_t mb = (size_t)b * limit * 16, sb = (size_t)b * limit * 4;
+    SG_CUDA_TRY(cudaMemcpyAsync(hp + qbytes, s->d_mem_out, mb, cudaMemcpyDeviceToHost, s->stream));
+    SG_CUDA_TRY(cudaMemcpyAsync(hp + qbytes + mb, s->d_sim_out, sb, cudaMemcpyDeviceToHost, s->stream));
+    SG_CUDA_TRY(cudaMemcpyAsync(hp + qbytes + mb + sb, s->d_memcnt, (size_t)b * 4, cudaMemcpyDeviceToHost, s->stream));
+    SG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    memcpy(mem_out, hp + qbytes, mb);
+    memcpy(sim_out, hp + qbytes + mb, sb);
+    memcpy(counts_out, hp + qbytes + mb + sb, (size_t)b * 4);
     return SG_OK;
 }
 

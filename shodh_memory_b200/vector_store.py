@@ -127,6 +127,22 @@ class GpuVectorStore:
                                               _ptr(dist, C.c_float), _ptr(counts, C.c_uint32)))
         return ids, dist, counts
 
+    def set_memory_ids(self, vec2mem) -> None:
+        """IdMapping (retrieval.rs:64-140): vec2mem [n,2] u64 = MemoryId (uuid hi, lo) of every vector id."""
+        t = np.ascontiguousarray(vec2mem, np.uint64)
+        capi.check(capi.lib().sg_store_set_memory_ids(self._h, _ptr(t, C.c_uint64), t.shape[0]))
+
+    def search_ids(self, queries, limit: int):
+        """RetrievalEngine::search_ids after the embed step -> (mem ids [b,limit,2] u64, sims [b,limit], counts [b])."""
+        q = np.ascontiguousarray(queries, np.float32)
+        b = q.shape[0]
+        mem = np.empty((b, limit, 2), np.uint64)
+        sim = np.empty((b, limit), np.float32)
+        cnt = np.zeros(b, np.uint32)
+        capi.check(capi.lib().sg_store_search_memory_ids(self._h, _ptr(q, C.c_float), b, limit, _ptr(mem, C.c_uint64),
+                                                         _ptr(sim, C.c_float), _ptr(cnt, C.c_uint32)))
+        return mem, sim, cnt
+
     def search_device(self, d_queries: int, b: int, k: int, d_ids: int, d_dist: int, d_counts: int,
                       stream: int = 0) -> None:
         """Raw device pointers (ints), asynchronous on `stream` (a cudaStream_t value)."""
