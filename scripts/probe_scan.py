@@ -15,7 +15,7 @@ dq = torch.tensor(q).cuda()
 stream = torch.cuda.current_stream().cuda_stream
 st.set_profiling(True)
 bytes_sweep = n * 384 * 2
-for (w, r) in [(8, 6), (6, 6), (4, 6), (8, 4), (12, 4), (16, 3), (9, 5), (8, 5)]:
+for (w, r) in [(8, 6), (4, 6), (5, 6), (6, 6), (8, 4), (10, 4), (12, 4), (6, 5), (8, 5), (16, 3)]:
     os.environ["SG_SCAN_WARPS"] = str(w); os.environ["SG_SCAN_RING"] = str(r)
     for b, k in [(1, 10), (1, 100), (2, 10), (4, 10)]:
         ids = torch.empty((b, k), dtype=torch.int32, device="cuda"); dist = torch.empty((b, k), device="cuda")
@@ -25,7 +25,7 @@ for (w, r) in [(8, 6), (6, 6), (4, 6), (8, 4), (12, 4), (16, 3), (9, 5), (8, 5)]
                 st.search_device(dq.data_ptr(), b, k, ids.data_ptr(), dist.data_ptr(), cnt.data_ptr(), stream)
             torch.cuda.synchronize()
             ms = []
-            for _ in range(10):
+            for _ in range(40):
                 st.search_device(dq.data_ptr(), b, k, ids.data_ptr(), dist.data_ptr(), cnt.data_ptr(), stream)
                 torch.cuda.synchronize()
                 ms.append(st.last_scan_ms()[0])

@@ -268,7 +268,11 @@ int plan_scan(const sg_store *s, uint32_t k, uint32_t qb, ScanPlan *p)
     uint32_t kp = 32;
     while (kp < k) kp <<= 1;
     p->cap = 2 * kp;
-    uint32_t ring = (uint32_t)env_u32("SG_SCAN_RING", nbox < 6 ? (nbox < 3 ? 3 : nbox) : 6);
+    // ring depth per warp: 6 boxes (one 384-d fp16 row tile) for multi-query sweeps; 4 measured ~5 % faster
+    // for the single-query sweep at 10M rows (1.10 / 1.12 ms vs 1.16 / 1.18 ms for k = 10 / 100)
+    uint32_t ring_dflt = nbox < 6 ? (nbox < 3 ? 3 : nbox) : 6;
+    if (qb == 1 && ring_dflt > 4) ring_dflt = 4;
+    uint32_t ring = (uint32_t)env_u32("SG_SCAN_RING", (int)ring_dflt);
     if (ring < 2) ring = 2;
     uint32_t Wmax = (uint32_t)env_u32("SG_SCAN_WARPS", 8);
     if (Wmax > 16) Wmax = 16;
