@@ -370,7 +370,8 @@ bool tc_eligible(const sg_store *s, uint32_t b, uint32_t k, uint32_t *kk_out, ui
     uint32_t kk = k <= 10 ? 16 : 32;
     const uint32_t kk_env = (uint32_t)env_u32("SG_TC_KK", 0);
     if (kk_env >= k + 2 && kk_env <= 32) kk = kk_env;
-    for (uint32_t stages = 8; stages >= 3; --stages) {
+    const uint32_t st_max = (uint32_t)env_u32("SG_TC_STAGES", 8);
+    for (uint32_t stages = st_max < 3 ? 3 : (st_max > 8 ? 8 : st_max); stages >= 3; --stages) {
         if (tc_smem_bytes(s->dim, stages, kk) <= 227 * 1024) {
             *kk_out = kk;
             *stages_out = stages;

@@ -299,3 +299,49 @@ def test_search_device_pointers_and_profiling(sg, oracle):
     assert np.array_equal(ids.cpu().numpy().view(np.uint32), h_ids)
     assert np.array_equal(bits(dist.cpu().numpy()), bits(h_dist))
     st.close()
+
+
+def test_k_1024_and_large_k_batches(sg, oracle):
+    """Documented limit k <= 1024; k > 24 with b >= 5 takes the exact sweep in groups of 4 queries."""
+    n = 6000
+    corpus = oracle.synth_corpus(SEED, 0, n, 384)
+    seen = oracle.round_f16(corpus)
+    st = sg.GpuVectorStore(384, "f16")
+    st.add_vectors(corpus)
+    q, _ = oracle.synth_queries(SEED, n, 7, 384)
+    assert_same(oracle, st, seen, q[:1], 1024)
+    assert_same(oracle, st, seen, q[:2], 500)
+    assert_same(oracle, st, seen, q, 120)                 # the reference's k = 12 x max_results for top-10
+    with pytest.raises(sg.SgError):
+        st.search_batch(q[:1], 1025)
+    st.close()
+
+
+def test_concurrent_callers_serialise_correctly(sg, oracle):
+    """The handle may be shared by many threads (spawn_blocking workers in the reference, recall.rs:513)."""
+    import threading
+    n = 50_000
+    st = sg.GpuVectorStore(384, "f16")
+    st.append_synthetic(SEED, 0, n)
+    seen = oracle.synth_corpus(SEED, 0, n, 384, f16_round=True)
+    q, _ = oracle.synth_queries(SEED, n, 16, 384)
+    want = [oracle.brute_force_search(seen, q[i], 10) for i in range(16)]
+    errors = []
+
+    def worker(i):
+        try:
+            for _ in range(5):
+                if i % 4 == 0:                             # some callers batch (tensor path), most do single queries
+                    ids, dist, _ = st.search_batch(q[:8], 10)
+                    for j in range(8):
+                        assert np.array_equal(ids[j], want[j][0]) and np.array_equal(bits(dist[j]), bits(want[j][1]))
+                else:
+                    res = st.search(q[i], 10)
+                    assert [r[0] for r in res] == want[i][0].tolist()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(16)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors, errors[:3]
+    st.close()

@@ -153,3 +153,15 @@ def test_pair_kernel_large_with_prepass(sg, oracle, monkeypatch):
     for x, y in zip(tc, ex):
         assert x[:16].tobytes() == y.tobytes()
     st.close()
+
+
+def test_many_query_tiles(sg, oracle):
+    """b = 600: three 256-query sweeps (pair kernel), the last one partially filled."""
+    n, b = 30_000, 600
+    st = sg.GpuVectorStore(384, "f16")
+    st.append_synthetic(SEED, 0, n)
+    seen = oracle.synth_corpus(SEED, 0, n, 384, f16_round=True)
+    queries, _ = oracle.synth_queries(SEED, n, b, 384)
+    check_batch(oracle, st, seen, queries, 10)
+    assert st.tc_stats()[0] == b
+    st.close()
