@@ -66,7 +66,7 @@ def make_batch(b, L, seed, ragged=True):
     return ids, mask
 
 
-@pytest.mark.parametrize("b,L", [(1, 64), (3, 17), (8, 128), (5, 256), (33, 64)])
+@pytest.mark.parametrize("b,L", [(1, 64), (3, 17), (8, 128), (5, 256), (33, 64), (160, 64), (320, 64)])
 def test_encoder_matches_torch_fp32(model_and_encoder, oracle, b, L):
     model, enc = model_and_encoder
     assert enc.dimension() == 384                                    # minilm.rs:1206-1208
