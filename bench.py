@@ -51,6 +51,69 @@ def peaks():
 # reference arm / cpu_baseline: the oracle port of VamanaIndex::brute_force_search "as written"
 # (per-row clone + full sort, vamana.rs:1167-1188), one query per host thread.
 # ----------------------------------------------------------------------------------------------
+def traffic_from_capture(kernel: str, local_rows: int):
+    """DRAM bytes per launch from the committed ncu --set full capture, scaled by rows to this shard."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        c = json.load(open(p))[kernel]
+    except Exception:
+        return None, None
+    per_row = (c["dram_bytes_read"] + c["dram_bytes_write"]) / c["rows"]
+    return per_row * local_rows, (f"profiles/r01_traffic.json: ncu dram__bytes_read+write of {kernel} at {c['rows']} rows "
+                                  f"({(c['dram_bytes_read'] + c['dram_bytes_write']) / c['algorithmic_bytes']:.4f}x algorithmic), "
+                                  f"scaled by rows")
+
+
+def cpu_detail(budget_rows: int = 100_000):
+    """SURVEY 8(d) CPU baselines beside the headline one, all on a small row sample and scaled linearly to the
+    full corpus: the reference loop single-threaded (it IS sequential, vamana.rs:1173) as written and with the
+    incidental waste removed (heap top-k, no row clone), and the waste-free loop on all host threads."""
+    from oracle import oracle as o
+    threads = o.max_threads()
+    corpus = o.synth_corpus(SEED, 0, budget_rows, DIM, f16_round=True)
+    queries, _ = o.synth_queries(SEED, ROWS, max(threads, 4), DIM)
+    scale = budget_rows / ROWS
+    out = {}
+
+    def run(name, nq, as_written, thr):
+        o.brute_force_search_batch(corpus, queries[:nq], TOPK, as_written=as_written, threads=thr)
+        t0 = time.perf_counter()
+        o.brute_force_search_batch(corpus, queries[:nq], TOPK, as_written=as_written, threads=thr)
+        out[name] = nq / (time.perf_counter() - t0) * scale
+    run("as_written_1_thread", 4, True, 1)
+    run("heap_topk_no_clone_1_thread", 4, False, 1)
+    run(f"heap_topk_no_clone_{threads}_threads", threads, False, threads)
+    out["unit"] = UNIT
+    out["sample"] = f"{budget_rows} rows of {ROWS}, scaled linearly"
+    return out
+
+
+def cpu_encoder_ms(L: int, threads: int):
+    """PyTorch-CPU fp32 forward of the MiniLM-L6 architecture (the checker model of tests/test_encoder_gpu.py),
+    one query of L tokens, `threads` intra-op threads (reference default: 2, minilm.rs:67)."""
+    try:
+        import torch
+        from transformers import BertConfig, BertModel
+    except Exception:
+        return None
+    cfg = BertConfig(vocab_size=30522, hidden_size=384, num_hidden_layers=6, num_attention_heads=12,
+                     intermediate_size=1536, max_position_embeddings=512)
+    model = BertModel(cfg, add_pooling_layer=False).eval()
+    prev = torch.get_num_threads()
+    torch.set_num_threads(threads)
+    ids = torch.randint(1000, 30522, (1, L))
+    mask = torch.ones((1, L), dtype=torch.int64)
+    with torch.no_grad():
+        for _ in range(2):
+            model(input_ids=ids, attention_mask=mask)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            model(input_ids=ids, attention_mask=mask)
+        ms = (time.perf_counter() - t0) * 1e3 / 5
+    torch.set_num_threads(prev)
+    return ms
+
+
 def cpu_reference(steps: int, warmup: int, budget_s: float = 90.0):
     """Times the oracle port of brute_force_search AS WRITTEN on all host threads.  The row sample is sized so
     the whole (steps + warmup) run stays within ~budget_s: scan cost is linear in rows, and the reported
@@ -225,13 +288,16 @@ def main():
     store.local.profile_read()
     launches0 = sg.kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]   # per-step marks: median / p95
     e0.record()
-    for _ in range(steps):
+    for i in range(steps):
         store.search_device(dq, TOPK)
+        marks[i].record()
     e1.record()
     barrier()
     launches = sg.kernel_launch_count() - launches0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
+    per_step = np.array([(marks[i - 1] if i else e0).elapsed_time(marks[i]) for i in range(steps)])
     scan_ms, sweeps_per_step = store.local.profile_read()
     ms_per_step = ms_total / steps
     value = BATCH * steps / (ms_total / 1e3)
@@ -346,6 +412,14 @@ def main():
     b1_achieved = alg_bytes / (b1_scan_ms * 1e-3) / 1e9
 
     cpu = cpu_reference(2, 1, budget_s=12.0) if world == 1 else None
+    cpu_more = None
+    if world == 1 and os.environ.get("SG_BENCH_CPU_DETAIL", "1") == "1":
+        cpu_more = cpu_detail()
+        if enc_res is not None:
+            enc_res["cpu_torch_fp32_ms"] = {"L64_2_threads": cpu_encoder_ms(64, 2), "L256_2_threads": cpu_encoder_ms(256, 2),
+                                            "L64_all_threads": cpu_encoder_ms(64, os.cpu_count() or 2),
+                                            "note": "HF BertModel fp32 on this box's host, one query; the reference pads to 256 "
+                                                    "and runs ONNX Runtime with 2 intra-op threads (minilm.rs:67,912-921)"}
 
     # Which roofline binds the sweep?  One sweep must move alg_bytes from HBM AND (tensor path) do
     # 2*rows*dim*queries_per_sweep FLOP on the tensor pipe; at 256 queries per sweep the tensor time exceeds
@@ -358,11 +432,14 @@ def main():
     hbm_view = dict(achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak)
     if tensor_path and t_tc > t_hbm:
         tf = flops_step / (scan_step_ms * 1e-3) / 1e12
-        roofline = dict(bound="tensor", achieved=tf, peak=tc_peak, unit="TFLOP/s", frac=tf / tc_peak, traffic=None,
+        traffic, traffic_src = traffic_from_capture("scan_tc2_kernel", local_rows)
+        roofline = dict(bound="tensor", achieved=tf, peak=tc_peak, unit="TFLOP/s", frac=tf / tc_peak, traffic=traffic,
+                        traffic_source=traffic_src,
                         kernel="scan_tc2_kernel (tcgen05.mma.cta_group::2, 256 queries x 256 rows per tile)",
                         flops_per_step=flops_step, hbm=hbm_view)
     else:
-        roofline = dict(bound="hbm", traffic=None,
+        traffic, traffic_src = (None, None) if tensor_path else traffic_from_capture("scan_exact_kernel", local_rows)
+        roofline = dict(bound="hbm", traffic=traffic, traffic_source=traffic_src,
                         kernel=("scan_tc_kernel (tcgen05 sweep)" if tensor_path else "scan_exact_kernel"), **hbm_view)
     roofline.update(algorithmic_bytes_per_step=alg_bytes, scan_ms_per_step=scan_step_ms,
                     sweep_launches_per_step=int(sweeps_per_step), peak_source=peak_src,
@@ -371,6 +448,7 @@ def main():
 
     line = dict(
         metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=steps, warmup=warmup, ms_per_step=ms_per_step,
+        ms_per_step_median=float(np.median(per_step)), ms_per_step_p95=float(np.percentile(per_step, 95)),
         higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
         config=dict(workload=f"{ROWS}x{DIM} fp16 corpus resident in HBM, batch-{BATCH} f32 queries, exact top-{TOPK} "
                              f"(dist=-dot in the reference's summation order; ids bit-identical to the CPU path)",
@@ -384,12 +462,15 @@ def main():
                  d2h_bytes_per_step=BATCH * TOPK * 8 + BATCH * 4, ms_per_step=e2e_ms / steps),
         batch1=dict(value=1e3 / b1_ms, unit=UNIT, k=B1_K, ms_per_query=b1_ms,
                     roofline=dict(bound="hbm", achieved=b1_achieved, peak=peak, unit="GB/s", frac=b1_achieved / peak,
-                                  scan_ms=b1_scan_ms, kernel="scan_exact_kernel")),
+                                  scan_ms=b1_scan_ms, kernel="scan_exact_kernel",
+                                  traffic=traffic_from_capture("scan_exact_kernel", local_rows)[0])),
         tensor_path=dict(zip(("queries", "exact_reruns"), store.local.tc_stats())),
         encoder=enc_res,
         gpu_launches=int(launches), clocks=clocks)
     if cpu:
         line["cpu_baseline"] = dict(value=cpu["value"], unit=UNIT, cores=cpu["cores"], kind=cpu["kind"], sample=cpu["sample"])
+    if cpu_more:
+        line["cpu_baseline"]["detail"] = cpu_more
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
