@@ -417,7 +417,7 @@ def main():
         cpu_more = cpu_detail()
         if enc_res is not None:
             enc_res["cpu_torch_fp32_ms"] = {"L64_2_threads": cpu_encoder_ms(64, 2), "L256_2_threads": cpu_encoder_ms(256, 2),
-                                            "L64_all_threads": cpu_encoder_ms(64, os.cpu_count() or 2),
+                                            "L64_8_threads": cpu_encoder_ms(64, min(8, os.cpu_count() or 2)),
                                             "note": "HF BertModel fp32 on this box's host, one query; the reference pads to 256 "
                                                     "and runs ONNX Runtime with 2 intra-op threads (minilm.rs:67,912-921)"}
 
@@ -463,6 +463,8 @@ def main():
         batch1=dict(value=1e3 / b1_ms, unit=UNIT, k=B1_K, ms_per_query=b1_ms,
                     roofline=dict(bound="hbm", achieved=b1_achieved, peak=peak, unit="GB/s", frac=b1_achieved / peak,
                                   scan_ms=b1_scan_ms, kernel="scan_exact_kernel",
+                                  note="peak = measured COPY bandwidth (read+write); a read-only sweep can slightly exceed it "
+                                       "(ncu: 80 % of the 8.2 TB/s DRAM peak, profiles/r01_scan_exact_ncu.md)",
                                   traffic=traffic_from_capture("scan_exact_kernel", local_rows)[0])),
         tensor_path=dict(zip(("queries", "exact_reruns"), store.local.tc_stats())),
         encoder=enc_res,

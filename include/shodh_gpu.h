@@ -223,6 +223,17 @@ SG_API int sg_fuse_topk(int device, const sg_fuse_weights *w, const sg_fuse_conf
                         uint32_t *order_out, float *score_out, uint32_t *n_out,
                         float *all_scores_out);
 
+/* RRFusion::new(k, weights).fuse(ranked_lists) (src/memory/hybrid_search.rs:537-594): the hand-off from the
+ * retrieval legs (BM25 list from the host, vector list from sg_store_search_memory_ids) to the fused
+ * candidate list.  mem_ids [n_total,2] u64 = the lists concatenated in rank order (Uuid as two big-endian
+ * halves); list_offsets [n_lists+1]; weights [n_weights] RAW (normalised here exactly like RRFusion::new;
+ * lists beyond n_weights use 1.0 like `weights.get(i).unwrap_or(1.0)`).  Output: the distinct ids with
+ * score = sum in list order of w / (k + rank + 1), sorted (score total_cmp desc, MemoryId asc);
+ * mem_out [n_total,2], score_out [n_total], *n_out = number of distinct ids.  n_total <= 2048. */
+SG_API int sg_rrf_fuse(int device, float k, const float *weights, uint32_t n_weights, const uint64_t *mem_ids,
+                       const uint32_t *list_offsets, uint32_t n_lists, uint64_t *mem_out, float *score_out,
+                       uint32_t *n_out);
+
 /* ---- sentence encoder: replaces the ONNX Runtime session + pooling inside MiniLMEmbedder
  * (src/embeddings/minilm.rs: generate_embedding_onnx :883-982, generate_embeddings_batch_onnx
  * :996-1115 = session.run + masked mean-pool + finalize_pooled :846-878), i.e. the body of

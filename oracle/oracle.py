@@ -285,3 +285,23 @@ def round_f16(a) -> np.ndarray:
 
 def max_threads() -> int:
     return int(lib().so_max_threads())
+
+
+def rrf_fuse(k, weights, lists):
+    """hybrid_search.rs::RRFusion::new(k, weights).fuse(lists).  lists: sequence of [n_i, 2] u64 arrays
+    (MemoryId as uuid hi/lo) in rank order -> (ids [m,2] u64, scores [m] f32)."""
+    weights = np.ascontiguousarray(weights, dtype=np.float32)
+    lists = [np.ascontiguousarray(x, dtype=np.uint64).reshape(-1, 2) for x in lists]
+    offsets = np.zeros(len(lists) + 1, dtype=np.uint32)
+    offsets[1:] = np.cumsum([x.shape[0] for x in lists])
+    ids = np.ascontiguousarray(np.concatenate(lists, axis=0) if lists else np.zeros((0, 2), np.uint64))
+    n = int(offsets[-1])
+    out_ids = np.zeros((max(n, 1), 2), dtype=np.uint64)
+    out_sc = np.zeros(max(n, 1), dtype=np.float32)
+    f = lib().so_rrf_fuse
+    f.restype = C.c_uint32
+    f.argtypes = [C.c_float, C.POINTER(C.c_float), C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_uint32,
+                  C.POINTER(C.c_uint64), C.POINTER(C.c_float)]
+    m = f(float(k), _p(weights, C.c_float), weights.size, _p(ids, C.c_uint64), _p(offsets, C.c_uint32), len(lists),
+          _p(out_ids, C.c_uint64), _p(out_sc, C.c_float))
+    return out_ids[:m].copy(), out_sc[:m].copy()

@@ -445,6 +445,64 @@ SO_EXPORT uint32_t so_search_ids_post(const uint32_t *vec_ids, const float *dist
     return r;
 }
 
+/* src/memory/hybrid_search.rs:537-594 RRFusion::new + RRFusion::fuse.
+ * new: weights normalised by their f32 left-fold sum (1/len each when sum <= 0).
+ * fuse: lists in order, entries in rank order: scores[id] += weight / (k + (rank+1) as f32)
+ * starting from 0.0 (lists beyond the weight vector use weight 1.0); the union is sorted by
+ * (score total_cmp desc, MemoryId asc).  ids: [n_total][2] u64 (uuid hi/lo, big-endian halves);
+ * offsets: [n_lists+1].  Returns the number of distinct ids. */
+typedef struct { uint64_t hi, lo; float score; } so_rrf_ent;
+static int cmp_rrf(const void *pa, const void *pb)
+{
+    const so_rrf_ent *a = (const so_rrf_ent *)pa, *b = (const so_rrf_ent *)pb;
+    int32_t ka, kb;
+    memcpy(&ka, &a->score, 4);
+    memcpy(&kb, &b->score, 4);
+    ka ^= (int32_t)(((uint32_t)(ka >> 31)) >> 1);     /* f32::total_cmp key */
+    kb ^= (int32_t)(((uint32_t)(kb >> 31)) >> 1);
+    if (ka != kb) return ka > kb ? -1 : 1;            /* descending */
+    if (a->hi != b->hi) return a->hi < b->hi ? -1 : 1;
+    if (a->lo != b->lo) return a->lo < b->lo ? -1 : 1;
+    return 0;
+}
+SO_EXPORT uint32_t so_rrf_fuse(float k, const float *weights, uint32_t n_weights, const uint64_t *ids,
+                               const uint32_t *offsets, uint32_t n_lists, uint64_t *ids_out, float *score_out)
+{
+    float wn[64];
+    float sum = 0.0f;
+    if (n_weights > 64) n_weights = 64;
+    for (uint32_t i = 0; i < n_weights; ++i) sum = sum + weights[i];
+    for (uint32_t i = 0; i < n_weights; ++i) wn[i] = sum > 0.0f ? weights[i] / sum : 1.0f / (float)n_weights;
+    const uint32_t n_total = offsets[n_lists];
+    so_rrf_ent *u = (so_rrf_ent *)malloc(sizeof(so_rrf_ent) * (size_t)(n_total ? n_total : 1));
+    uint32_t m = 0;
+    for (uint32_t l = 0; l < n_lists; ++l) {
+        const float w = l < n_weights ? wn[l] : 1.0f;
+        for (uint32_t e = offsets[l]; e < offsets[l + 1]; ++e) {
+            const uint32_t rank = e - offsets[l];
+            const float c = w / (k + (float)(rank + 1));
+            uint32_t j = 0;
+            for (; j < m; ++j)
+                if (u[j].hi == ids[2 * (size_t)e] && u[j].lo == ids[2 * (size_t)e + 1]) break;
+            if (j == m) {
+                u[m].hi = ids[2 * (size_t)e];
+                u[m].lo = ids[2 * (size_t)e + 1];
+                u[m].score = 0.0f;
+                ++m;
+            }
+            u[j].score = u[j].score + c;
+        }
+    }
+    qsort(u, m, sizeof(so_rrf_ent), cmp_rrf);
+    for (uint32_t j = 0; j < m; ++j) {
+        ids_out[2 * (size_t)j] = u[j].hi;
+        ids_out[2 * (size_t)j + 1] = u[j].lo;
+        score_out[j] = u[j].score;
+    }
+    free(u);
+    return m;
+}
+
 /* ------------------------------------------------------------------------- */
 /* a12 / a13: relevance fusion                                                */
 /* ------------------------------------------------------------------------- */

@@ -114,6 +114,8 @@ def lib() -> C.CDLL:
     L.sg_fuse_default_config.restype = None
     L.sg_fuse_topk.argtypes = [C.c_int, C.POINTER(FuseWeights), C.POINTER(FuseConfig),
                                C.POINTER(CandidateFeats), C.c_uint32, C.c_int64, u32p, f32p, u32p, f32p]
+    L.sg_rrf_fuse.argtypes = [C.c_int, C.c_float, f32p, C.c_uint32, C.POINTER(C.c_uint64), u32p, C.c_uint32,
+                              C.POINTER(C.c_uint64), f32p, u32p]
     _lib = L
     return L
 

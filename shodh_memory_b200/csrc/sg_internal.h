@@ -103,6 +103,9 @@ cudaError_t launch_fuse_rank(const FuseDev &f, uint32_t n, sg_fuse_weights w, sg
                              float *d_all, cudaStream_t st);
 
 // ---- post.cu ----
+cudaError_t launch_rrf_fuse(float k, const float *d_weights, uint32_t n_weights, const uint64_t *d_ids, const uint32_t *d_offsets,
+                            uint32_t n_lists, uint32_t n_total, uint64_t *d_ids_out, float *d_score_out, uint32_t *d_n_out,
+                            cudaStream_t st);
 cudaError_t launch_search_ids_post(const uint32_t *d_ids, const float *d_dist, const uint32_t *d_counts, uint32_t b, uint32_t k,
                                    const uint64_t *d_vec2mem, uint64_t n_map, uint32_t id_base, uint32_t limit,
                                    uint64_t *d_mem_out, float *d_sim_out, uint32_t *d_cnt_out, cudaStream_t st);

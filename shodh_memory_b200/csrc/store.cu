@@ -1112,4 +1112,70 @@ int sg_fuse_topk(int device, const sg_fuse_weights *w, const sg_fuse_config *cfg
     return ret;
 }
 
+int sg_rrf_fuse(int device, float k, const float *weights, uint32_t n_weights, const uint64_t *mem_ids,
+                const uint32_t *list_offsets, uint32_t n_lists, uint64_t *mem_out, float *score_out, uint32_t *n_out)
+{
+    if (!n_out || !list_offsets || (n_weights && !weights)) return SG_ERR_INVALID;
+    *n_out = 0;
+    if (n_lists == 0) return SG_OK;
+    const uint32_t n_total = list_offsets[n_lists];
+    for (uint32_t l = 0; l < n_lists; ++l)
+        if (list_offsets[l] > list_offsets[l + 1]) {
+            set_error("sg_rrf_fuse: list_offsets must be non-decreasing");
+            return SG_ERR_INVALID;
+        }
+    if (n_total == 0) return SG_OK;
+    if (!mem_ids || !mem_out || !score_out) return SG_ERR_INVALID;
+    if (n_total > 2048 || n_weights > 64 || n_lists > 64) {
+        set_error("sg_rrf_fuse supports up to 2048 ranked entries and 64 lists per call (got %u entries, %u lists)", n_total, n_lists);
+        return SG_ERR_UNSUPPORTED;
+    }
+    int rc = check_device(device, nullptr);
+    if (rc != SG_OK) return rc;
+    SG_CUDA_TRY(cudaSetDevice(device));
+    // arena: ids [n,2] u64 | offsets | weights || ids_out [n,2] u64 | scores | n_out
+    const size_t o_ids = 0, o_off = (size_t)n_total * 16, o_w = o_off + ((size_t)(n_lists + 1) * 4 + 15) / 16 * 16;
+    const size_t in_bytes = o_w + ((size_t)(n_weights ? n_weights : 1) * 4 + 15) / 16 * 16;
+    const size_t o_out = in_bytes, o_sc = o_out + (size_t)n_total * 16, o_n = o_sc + ((size_t)n_total * 4 + 15) / 16 * 16;
+    const size_t total = o_n + 16;
+    uint8_t *d = nullptr, *h = nullptr;
+    SG_CUDA_TRY(cudaMalloc(&d, total));
+    cudaError_t e = cudaHostAlloc(&h, total, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        set_error("cudaHostAlloc: %s", cudaGetErrorString(e));
+        return SG_ERR_OOM;
+    }
+    cudaStream_t st = nullptr;
+    e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    int ret = SG_OK;
+    if (e == cudaSuccess) {
+        memcpy(h + o_ids, mem_ids, (size_t)n_total * 16);
+        memcpy(h + o_off, list_offsets, (size_t)(n_lists + 1) * 4);
+        if (n_weights) memcpy(h + o_w, weights, (size_t)n_weights * 4);
+        e = cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess)
+            e = launch_rrf_fuse(k, reinterpret_cast<const float *>(d + o_w), n_weights, reinterpret_cast<const uint64_t *>(d + o_ids),
+                                reinterpret_cast<const uint32_t *>(d + o_off), n_lists, n_total,
+                                reinterpret_cast<uint64_t *>(d + o_out), reinterpret_cast<float *>(d + o_sc),
+                                reinterpret_cast<uint32_t *>(d + o_n), st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h + o_out, d + o_out, total - o_out, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) {
+            const uint32_t m = *reinterpret_cast<uint32_t *>(h + o_n);
+            *n_out = m;
+            memcpy(mem_out, h + o_out, (size_t)m * 16);
+            memcpy(score_out, h + o_sc, (size_t)m * 4);
+        }
+    }
+    if (e != cudaSuccess) {
+        set_error("sg_rrf_fuse: %s", cudaGetErrorString(e));
+        ret = SG_ERR_CUDA;
+    }
+    if (st) cudaStreamDestroy(st);
+    cudaFreeHost(h);
+    cudaFree(d);
+    return ret;
+}
+
 }  // extern "C"

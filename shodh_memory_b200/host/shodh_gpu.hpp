@@ -138,4 +138,35 @@ inline std::vector<Surfaced> fuse_and_rank(const sg_candidate_feats &feats, uint
     return out;
 }
 
+struct MemoryId { uint64_t hi, lo; };   // Uuid as two big-endian halves
+
+/// RRFusion (src/memory/hybrid_search.rs:529-594): weights are normalised inside the library like RRFusion::new
+class RRFusion {
+public:
+    RRFusion(float k, std::vector<float> weights, int device = 0) : k_(k), weights_(std::move(weights)), device_(device) {}
+    /// Each input list is in rank order; returns (MemoryId, rrf_score) sorted (score desc, MemoryId asc).
+    std::vector<std::pair<MemoryId, float>> fuse(const std::vector<std::vector<MemoryId>> &ranked_lists) const
+    {
+        std::vector<uint32_t> offsets(ranked_lists.size() + 1, 0);
+        std::vector<uint64_t> ids;
+        for (size_t l = 0; l < ranked_lists.size(); ++l) {
+            for (const MemoryId &m : ranked_lists[l]) { ids.push_back(m.hi); ids.push_back(m.lo); }
+            offsets[l + 1] = (uint32_t)(ids.size() / 2);
+        }
+        const size_t n = ids.size() / 2;
+        std::vector<uint64_t> out(2 * (n ? n : 1));
+        std::vector<float> score(n ? n : 1);
+        uint32_t m = 0;
+        check(sg_rrf_fuse(device_, k_, weights_.data(), (uint32_t)weights_.size(), ids.data(), offsets.data(),
+                          (uint32_t)ranked_lists.size(), out.data(), score.data(), &m));
+        std::vector<std::pair<MemoryId, float>> r;
+        for (uint32_t i = 0; i < m; ++i) r.push_back({MemoryId{out[2 * i], out[2 * i + 1]}, score[i]});
+        return r;
+    }
+private:
+    float k_;
+    std::vector<float> weights_;
+    int device_;
+};
+
 }  // namespace shodh

@@ -58,3 +58,35 @@ def fuse_topk(feats: dict, now_unix_s: int, max_results: int = 5, min_score: flo
                                        score.ctypes.data_as(C.POINTER(C.c_float)), C.byref(m),
                                        allsc.ctypes.data_as(C.POINTER(C.c_float))))
     return order[:m.value].copy(), score[:m.value].copy(), allsc[:n].copy()
+
+
+class RRFusion:
+    """Mirror of `RRFusion` (reference src/memory/hybrid_search.rs:529-594): `RRFusion(k, weights).fuse(lists)`.
+
+    A ranked list is an `[n, 2]` u64 array of MemoryIds (Uuid as two big-endian halves) in rank order -- what
+    `GpuVectorStore.search_ids` returns for the vector leg.  Returns (ids [m,2] u64, rrf_scores [m] f32) sorted
+    (score desc by total_cmp, MemoryId asc).  Weights are passed RAW; the library normalises them like
+    `RRFusion::new`."""
+
+    def __init__(self, k: float, weights, device: int = 0):
+        self.k = float(k)
+        self.weights = np.ascontiguousarray(weights, dtype=np.float32)
+        self.device = int(device)
+
+    def fuse(self, ranked_lists):
+        lists = [np.ascontiguousarray(x, dtype=np.uint64).reshape(-1, 2) for x in ranked_lists]
+        offsets = np.zeros(len(lists) + 1, dtype=np.uint32)
+        if lists:
+            offsets[1:] = np.cumsum([x.shape[0] for x in lists])
+        n = int(offsets[-1])
+        ids = np.ascontiguousarray(np.concatenate(lists, axis=0)) if n else np.zeros((1, 2), np.uint64)
+        out_ids = np.zeros((max(n, 1), 2), dtype=np.uint64)
+        out_sc = np.zeros(max(n, 1), dtype=np.float32)
+        m = C.c_uint32(0)
+        u64p = C.POINTER(C.c_uint64)
+        capi.check(capi.lib().sg_rrf_fuse(self.device, self.k, self.weights.ctypes.data_as(C.POINTER(C.c_float)),
+                                          self.weights.size, ids.ctypes.data_as(u64p),
+                                          offsets.ctypes.data_as(C.POINTER(C.c_uint32)), len(lists),
+                                          out_ids.ctypes.data_as(u64p), out_sc.ctypes.data_as(C.POINTER(C.c_float)),
+                                          C.byref(m)))
+        return out_ids[:m.value].copy(), out_sc[:m.value].copy()

@@ -359,3 +359,42 @@ def test_synth_is_deterministic_unit_norm_and_shardable(oracle):
     assert np.allclose(np.linalg.norm(q.astype(np.float64), axis=1), 1.0, atol=1e-6)
     for i in range(1, 8, 2):
         assert float(q[i] @ a[int(near[i])]) > 0.99
+
+
+# ---- hybrid_search.rs:969-1052, :1172-1240 (RRFusion unit tests) ----
+def _mid(rng):
+    return rng.integers(0, 2**63, 2, dtype=np.uint64)
+
+
+def test_rrf_fusion_basic_disjoint_ties(oracle):
+    rng = np.random.default_rng(11)
+    id1, id2, id3 = _mid(rng), _mid(rng), _mid(rng)
+    ids, sc = oracle.rrf_fuse(60.0, [0.5, 0.5], [np.stack([id1, id2, id3]), np.stack([id2, id1, id3])])
+    assert len(ids) == 3 and np.array_equal(ids[2], id3)              # :1008
+    by = {tuple(i): s for i, s in zip(ids, sc)}
+    assert abs(by[tuple(id1)] - by[tuple(id2)]) < 1e-4 and by[tuple(id3)] < by[tuple(id1)]
+    ids, sc = oracle.rrf_fuse(60.0, [0.5, 0.5], [id1[None], id2[None]])
+    assert len(ids) == 2 and abs(sc[0] - sc[1]) < 1e-3                # :1026-1028
+    lo, hi = np.zeros(2, np.uint64), np.full(2, 2**64 - 1, np.uint64)  # :1038-1051 tie -> lower MemoryId first
+    ids, sc = oracle.rrf_fuse(60.0, [0.5, 0.5], [hi[None], lo[None]])
+    assert sc[0] == sc[1] and np.array_equal(ids[0], lo) and np.array_equal(ids[1], hi)
+
+
+def test_rrf_weights_and_k(oracle):
+    rng = np.random.default_rng(12)
+    id1, id2, id3 = _mid(rng), _mid(rng), _mid(rng)
+    bm25, vec = np.stack([id1, id2]), np.stack([id2, id1])
+    assert np.array_equal(oracle.rrf_fuse(60.0, [0.8, 0.2], [bm25, vec])[0][0], id1)   # :1187-1188
+    assert np.array_equal(oracle.rrf_fuse(60.0, [0.2, 0.8], [bm25, vec])[0][0], id2)   # :1191-1195
+    l1, l2 = np.stack([id1, id2, id3]), np.stack([id3, id2, id1])
+    rel = []
+    for k in (1.0, 100.0):                                                              # :1198-1238
+        ids, sc = oracle.rrf_fuse(k, [0.5, 0.5], [l1, l2])
+        s2 = sc[[np.array_equal(i, id2) for i in ids]][0]
+        rel.append(s2 / sc[0])
+    assert rel[1] >= rel[0] - 0.01
+    # the formula itself: w/(k + rank + 1), weights normalised, f32
+    ids, sc = oracle.rrf_fuse(45.0, [0.35, 0.40], [id1[None], id2[None]])
+    w = np.float32(0.35) + np.float32(0.40)
+    want = sorted([np.float32(0.35) / w / np.float32(46.0), np.float32(0.40) / w / np.float32(46.0)], reverse=True)
+    assert list(sc) == want
