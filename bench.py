@@ -338,6 +338,29 @@ def main():
     barrier()
     b1_ms = max_over_ranks(e0.elapsed_time(e1)) / b1_steps
     b1_scan, _ = store.local.profile_read()
+    # ---------------- configs[2] whole: batch-1 top-100 + relevance fusion through the host C ABI ----------------
+    fused_ms = None
+    if rank == 0 and world == 1:
+        rng = np.random.default_rng(SEED + 2)
+        now = 1_790_000_000
+        n_c = B1_K
+        side = dict(entity=np.where(rng.random(n_c) < 0.3, rng.random(n_c), 0.0).astype(np.float32),
+                    tag=np.where(rng.random(n_c) < 0.3, rng.random(n_c), 0.0).astype(np.float32),
+                    importance=rng.random(n_c).astype(np.float32), momentum=rng.uniform(-1, 1, n_c).astype(np.float32),
+                    access_count=np.minimum(rng.geometric(0.3, n_c), 64).astype(np.uint32),
+                    graph=rng.random(n_c).astype(np.float32),
+                    created_at=(now - rng.integers(0, 72 * 3600, n_c)).astype(np.int64))
+
+        def recall_fused(i):
+            _, dist, _ = store.local.search_batch(q_np[i % BATCH:i % BATCH + 1], B1_K)     # sg_store_search
+            return sg.fuse_topk(dict(side, semantic=-dist[0]), now, max_results=10)        # sg_fuse_topk
+        for i in range(5):
+            recall_fused(i)
+        t0 = time.perf_counter()
+        for i in range(100):
+            recall_fused(i)
+        fused_ms = (time.perf_counter() - t0) * 1e3 / 100
+        store.local.profile_read()
     # ---------------- encoder (configs[4]): MiniLM-L6, random-init weights, 64-token queries ----------------
     enc_res = None
     if rank == 0 and os.environ.get("SG_BENCH_ENCODER", "1") == "1":
@@ -461,6 +484,7 @@ def main():
         e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=BATCH * DIM * 4,
                  d2h_bytes_per_step=BATCH * TOPK * 8 + BATCH * 4, ms_per_step=e2e_ms / steps),
         batch1=dict(value=1e3 / b1_ms, unit=UNIT, k=B1_K, ms_per_query=b1_ms,
+                    with_fusion_host_api_ms=fused_ms,   # configs[2]: sg_store_search(top-100) + sg_fuse_topk, host buffers, wall clock
                     roofline=dict(bound="hbm", achieved=b1_achieved, peak=peak, unit="GB/s", frac=b1_achieved / peak,
                                   scan_ms=b1_scan_ms, kernel="scan_exact_kernel",
                                   note="peak = measured COPY bandwidth (read+write); a read-only sweep can slightly exceed it "

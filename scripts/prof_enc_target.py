@@ -11,7 +11,7 @@ ids = torch.from_numpy(rng.integers(1000, 30522, (256, 64)).astype(np.int64)).cu
 mask = torch.ones((256, 64), dtype=torch.int64, device="cuda")
 out = torch.empty((256, 384), device="cuda")
 cs = torch.cuda.current_stream().cuda_stream
-for b in (1, 1, 256, 256):
+for b in ([int(os.environ['B'])] * 2 if os.environ.get('B') else (1, 1, 256, 256)):
     enc.encode_ids_device(ids.data_ptr(), mask.data_ptr(), b, 64, out.data_ptr(), cs)
 torch.cuda.synchronize()
 print("done")

@@ -33,6 +33,7 @@ namespace {
 constexpr uint32_t EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RES_LN = 2;
 constexpr uint32_t G_THREADS = 256;
 constexpr uint32_t P_THREADS = 384;   // persistent GEMM: 4 control warps + 8 epilogue warps
+constexpr uint32_t LN_THREADS = 640;  // LayerNorm-fused 128x384 tile: 4 control warps + 16 epilogue warps
 
 struct GemmArgs {
     uint32_t K;            // reduction length (multiple of 64)
@@ -46,22 +47,33 @@ struct GemmArgs {
     float *out_f32;        // optional f32 copy (EPI_BIAS_RES_LN)
 };
 
-// erf-GELU.  erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the fp16 output rounding):
-// one reciprocal, one exp, five FMAs instead of libdevice erff's ~35 instructions.
+// erf-GELU, x * Phi(x), in 12 instructions.  Phi(x) = 1 / (1 + exp(-logit Phi(x))) and logit Phi is odd and
+// smooth, so it is fitted by x * P(x^2) (degree-9 odd minimax fit on |x| <= 6, coefficients pre-multiplied by
+// -log2 e): max |error| of the GELU value 3.0e-6 over the whole real line -- two orders below the fp16
+// rounding of the output -- with one ex2.approx and one rcp.approx and no slow-path branches.  (The ncu
+// source view of the first version, Abramowitz-Stegun 7.1.26 with an IEEE reciprocal, showed the
+// FFN-up epilogue issue-bound at 32 instructions per element: profiles/r01_encoder_ncu.md.)
 SG_DEVICE_INLINE float gelu_erf(float x)
 {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-    const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
-    const float erf_abs = 1.0f - poly * __expf(-z * z);
-    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+    const float xc = fminf(fmaxf(x, -6.0f), 6.0f);
+    const float x2 = xc * xc;
+    float p = fmaf(x2, -3.2290400e-06f, 8.8239125e-05f);
+    p = fmaf(x2, p, 3.6026838e-04f);
+    p = fmaf(x2, p, -1.0522668e-01f);
+    p = fmaf(x2, p, -2.3020454e+00f);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xc * p));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
 }
 
 // C tile = 128 rows x BN columns, one tile per CTA.  grid = (M_pad/128, N/BN).
-// The LayerNorm form runs 8 epilogue warps (384 threads): warps w and w+4 share a TMEM lane quarter and
-// each owns half of the row's columns; the row statistics are combined through shared memory.
+// The LayerNorm form runs 16 epilogue warps (640 threads): warps w, w+4, w+8, w+12 share a TMEM lane quarter
+// and each owns a quarter of the row's columns (one tile per CTA, so the epilogue is a pure latency chain:
+// four column groups shorten it 4x); the residual rows are prefetched into registers while the main loop
+// runs; the row statistics are combined through shared memory.
 template <uint32_t BN, uint32_t EPI>
-__global__ void __launch_bounds__(EPI == EPI_BIAS_RES_LN ? P_THREADS : G_THREADS, BN <= 128 ? 2 : 1)
+__global__ void __launch_bounds__(EPI == EPI_BIAS_RES_LN ? LN_THREADS : G_THREADS, BN <= 128 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const GemmArgs g)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -135,10 +147,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else if (warp >= 4) {
         // epilogue: thread t <-> output row m0 + t <-> TMEM lane t
-        constexpr uint32_t EPI_T = EPI == EPI_BIAS_RES_LN ? 256 : 128;     // epilogue threads
+        constexpr uint32_t EPI_T = EPI == EPI_BIAS_RES_LN ? 512 : 128;     // epilogue threads
         const uint32_t et = threadIdx.x - 128;
         const uint32_t t = et & 127;                                       // tile row = TMEM lane
-        const uint32_t half = et >> 7;                                     // LN form: which half of the columns
+        const uint32_t qtr = et >> 7;                                      // LN form: which quarter of the columns
         const uint32_t row = m0 + t;
         const uint32_t lane_base = ((warp & 3) * 32) << 16;
         // stage the per-column parameters while the main loop runs (named barrier over the epilogue warps)
@@ -149,6 +161,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 par_s[2 * BN + i] = g.beta[n0 + i];
             }
         }
+        // LN form: this thread's quarter of the residual row (BN/4 halfs) is fetched NOW, under the main loop
+        uint4 rv[EPI == EPI_BIAS_RES_LN ? BN / 32 : 1];
+        if constexpr (EPI == EPI_BIAS_RES_LN) {
+            const uint4 *res4 = reinterpret_cast<const uint4 *>(g.residual + (size_t)row * g.N) + qtr * (BN / 32);
+#pragma unroll
+            for (uint32_t q = 0; q < BN / 32; ++q) rv[q] = res4[q];
+        }
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_T) : "memory");
         mbar_wait(smem_u32(done_bar), 0);
         tc_fence_after();
@@ -156,24 +175,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // BN == N == hidden: the whole row is in this thread's TMEM lane.  Pass 1: v = acc + bias +
             // residual is written BACK into TMEM while sum / sum of squares accumulate; pass 2 reads v from
             // TMEM only.  bias / gamma / beta were staged in shared memory during the main loop.
-            const uint4 *res4 = reinterpret_cast<const uint4 *>(g.residual + (size_t)row * g.N);   // 8 halfs each
             const float4 *bias4 = reinterpret_cast<const float4 *>(par_s);
             const float4 *gam4 = reinterpret_cast<const float4 *>(par_s + BN);
             const float4 *bet4 = reinterpret_cast<const float4 *>(par_s + 2 * BN);
             float sum = 0.0f, sq = 0.0f;
-            constexpr uint32_t CH = BN / 64;                    // chunks per half
-#pragma unroll 1
-            for (uint32_t c = half * CH; c < half * CH + CH; ++c) {
+            constexpr uint32_t CH = BN / 128;                   // 32-column chunks per quarter
+#pragma unroll
+            for (uint32_t ci = 0; ci < CH; ++ci) {
+                const uint32_t c = qtr * CH + ci;
                 uint32_t r[32];
                 tmem_ld32(tmem_base + lane_base + c * 32, r);
-                uint4 rv[4];
-#pragma unroll
-                for (uint32_t q = 0; q < 4; ++q) rv[q] = res4[c * 4 + q];
                 tmem_ld_wait();
 #pragma unroll
                 for (uint32_t q = 0; q < 8; ++q) {
                     const float4 bb = bias4[c * 8 + q];
-                    const __half2 *hp = reinterpret_cast<const __half2 *>(&rv[q >> 1]) + (q & 1) * 2;
+                    const __half2 *hp = reinterpret_cast<const __half2 *>(&rv[ci * 4 + (q >> 1)]) + (q & 1) * 2;
                     const float2 r01 = __half22float2(hp[0]), r23 = __half22float2(hp[1]);
                     const float v0 = __uint_as_float(r[4 * q]) + bb.x + r01.x, v1 = __uint_as_float(r[4 * q + 1]) + bb.y + r01.y;
                     const float v2 = __uint_as_float(r[4 * q + 2]) + bb.z + r23.x, v3 = __uint_as_float(r[4 * q + 3]) + bb.w + r23.y;
@@ -185,18 +201,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 tmem_st32(tmem_base + lane_base + c * 32, r);
             }
             tmem_st_wait();
-            // combine the two halves' statistics (each thread wrote its own half back into TMEM)
-            float *part = par_s + 3 * BN;                       // [2][128][2]
-            part[(half * 128 + t) * 2] = sum;
-            part[(half * 128 + t) * 2 + 1] = sq;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            sum += part[((half ^ 1) * 128 + t) * 2];
-            sq += part[((half ^ 1) * 128 + t) * 2 + 1];
+            // combine the four quarters' statistics (each thread wrote its own quarter back into TMEM)
+            float *part = par_s + 3 * BN;                       // [4][128][2]
+            part[(qtr * 128 + t) * 2] = sum;
+            part[(qtr * 128 + t) * 2 + 1] = sq;
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            sum = (part[t * 2] + part[(128 + t) * 2]) + (part[(256 + t) * 2] + part[(384 + t) * 2]);
+            sq = (part[t * 2 + 1] + part[(128 + t) * 2 + 1]) + (part[(256 + t) * 2 + 1] + part[(384 + t) * 2 + 1]);
             const float mean = sum / (float)BN;
             const float var = fmaxf(sq / (float)BN - mean * mean, 0.0f);
             const float rstd = rsqrtf(var + g.eps);
 #pragma unroll 1
-            for (uint32_t c = half * CH; c < half * CH + CH; ++c) {
+            for (uint32_t c = qtr * CH; c < qtr * CH + CH; ++c) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + lane_base + c * 32, r);
                 tmem_ld_wait();
@@ -958,11 +974,11 @@ template <uint32_t BN, uint32_t EPI>
 cudaError_t launch_gemm(const CUtensorMap &ta, const CUtensorMap &tw, const GemmArgs &g, uint32_t m_tiles, cudaStream_t st)
 {
     constexpr uint32_t STAGE = 128 * 128 + BN * 128;
-    const size_t smem = (size_t)g.stages * STAGE + (2 * g.stages + 1) * 8 + 48 + 3 * BN * 4 + 2 * 128 * 2 * 4;
+    const size_t smem = (size_t)g.stages * STAGE + (2 * g.stages + 1) * 8 + 48 + 3 * BN * 4 + 4 * 128 * 2 * 4;
     auto kern = gemm_tc_kernel<BN, EPI>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<dim3(m_tiles, g.N / BN), EPI == EPI_BIAS_RES_LN ? P_THREADS : G_THREADS, smem, st>>>(ta, tw, g);
+    kern<<<dim3(m_tiles, g.N / BN), EPI == EPI_BIAS_RES_LN ? LN_THREADS : G_THREADS, smem, st>>>(ta, tw, g);
     count_launch();
     return cudaGetLastError();
 }

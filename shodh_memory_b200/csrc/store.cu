@@ -1035,6 +1035,54 @@ void sg_fuse_default_config(sg_fuse_config *c)
     c->max_results = 5;
 }
 
+}  // extern "C"
+
+namespace {
+// Per-device transient arena for the small host-buffer calls (sg_fuse_topk, sg_rrf_fuse): they sit on the
+// batch-1 latency path, where a cudaMalloc + cudaHostAlloc + stream create per call would cost more than the
+// kernel.  Grown on demand, kept for the life of the process; calls on one device serialise on the mutex.
+struct CallScratch {
+    std::mutex mu;
+    uint8_t *d = nullptr, *h = nullptr;
+    size_t cap = 0;
+    cudaStream_t st = nullptr;
+};
+CallScratch g_call_scratch[64];
+
+// returns SG_OK with the mutex HELD (caller unlocks), or an error with it released
+int scratch_acquire(int device, size_t bytes, CallScratch **out)
+{
+    if (device < 0 || device >= 64) return SG_ERR_INVALID;
+    CallScratch &c = g_call_scratch[device];
+    c.mu.lock();
+    cudaError_t e = cudaSuccess;
+    if (!c.st) e = cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking);
+    if (e == cudaSuccess && bytes > c.cap) {
+        if (c.d) cudaFree(c.d);
+        if (c.h) cudaFreeHost(c.h);
+        c.d = c.h = nullptr;
+        c.cap = 0;
+        const size_t want = bytes < (size_t)1 << 16 ? (size_t)1 << 16 : bytes;
+        e = cudaMalloc(&c.d, want);
+        if (e == cudaSuccess) e = cudaHostAlloc(&c.h, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) c.cap = want;
+    }
+    if (e != cudaSuccess) {
+        if (c.d) cudaFree(c.d);
+        if (c.h) cudaFreeHost(c.h);
+        c.d = c.h = nullptr;
+        c.cap = 0;
+        c.mu.unlock();
+        set_error("scratch allocation: %s", cudaGetErrorString(e));
+        return SG_ERR_OOM;
+    }
+    *out = &c;
+    return SG_OK;
+}
+}  // namespace
+
+extern "C" {
+
 int sg_fuse_topk(int device, const sg_fuse_weights *w, const sg_fuse_config *cfg, const sg_candidate_feats *f,
                  uint32_t n, int64_t now_unix_s, uint32_t *order_out, float *score_out, uint32_t *n_out,
                  float *all_scores_out)
@@ -1052,18 +1100,14 @@ int sg_fuse_topk(int device, const sg_fuse_weights *w, const sg_fuse_config *cfg
     // one transient arena: 6 f32 + 1 u32 + 1 i64 per candidate in, order/score/all/n out
     const size_t in_bytes = (size_t)n * (7 * 4 + 8);
     const size_t out_bytes = (size_t)cfg->max_results * 8 + (size_t)n * 4 + 16;
-    uint8_t *d = nullptr, *h = nullptr;
-    SG_CUDA_TRY(cudaMalloc(&d, in_bytes + out_bytes + 32));
-    cudaError_t e = cudaHostAlloc(&h, in_bytes + out_bytes + 32, cudaHostAllocDefault);
-    if (e != cudaSuccess) {
-        cudaFree(d);
-        set_error("cudaHostAlloc: %s", cudaGetErrorString(e));
-        return SG_ERR_OOM;
-    }
-    cudaStream_t st = nullptr;
-    e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    CallScratch *sc = nullptr;
+    rc = scratch_acquire(device, in_bytes + out_bytes + 32, &sc);
+    if (rc != SG_OK) return rc;
+    uint8_t *d = sc->d, *h = sc->h;
+    cudaStream_t st = sc->st;
+    cudaError_t e = cudaSuccess;
     int ret = SG_OK;
-    if (e == cudaSuccess) {
+    {
         // created_at first (8-byte aligned), then the 4-byte arrays
         size_t off = 0;
         memcpy(h + off, f->created_at_unix_s, (size_t)n * 8); const size_t o_created = off; off += (size_t)n * 8;
@@ -1106,9 +1150,7 @@ int sg_fuse_topk(int device, const sg_fuse_weights *w, const sg_fuse_config *cfg
         set_error("sg_fuse_topk: %s", cudaGetErrorString(e));
         ret = SG_ERR_CUDA;
     }
-    if (st) cudaStreamDestroy(st);
-    cudaFreeHost(h);
-    cudaFree(d);
+    sc->mu.unlock();
     return ret;
 }
 
@@ -1138,18 +1180,14 @@ int sg_rrf_fuse(int device, float k, const float *weights, uint32_t n_weights, c
     const size_t in_bytes = o_w + ((size_t)(n_weights ? n_weights : 1) * 4 + 15) / 16 * 16;
     const size_t o_out = in_bytes, o_sc = o_out + (size_t)n_total * 16, o_n = o_sc + ((size_t)n_total * 4 + 15) / 16 * 16;
     const size_t total = o_n + 16;
-    uint8_t *d = nullptr, *h = nullptr;
-    SG_CUDA_TRY(cudaMalloc(&d, total));
-    cudaError_t e = cudaHostAlloc(&h, total, cudaHostAllocDefault);
-    if (e != cudaSuccess) {
-        cudaFree(d);
-        set_error("cudaHostAlloc: %s", cudaGetErrorString(e));
-        return SG_ERR_OOM;
-    }
-    cudaStream_t st = nullptr;
-    e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    CallScratch *sc = nullptr;
+    rc = scratch_acquire(device, total, &sc);
+    if (rc != SG_OK) return rc;
+    uint8_t *d = sc->d, *h = sc->h;
+    cudaStream_t st = sc->st;
+    cudaError_t e = cudaSuccess;
     int ret = SG_OK;
-    if (e == cudaSuccess) {
+    {
         memcpy(h + o_ids, mem_ids, (size_t)n_total * 16);
         memcpy(h + o_off, list_offsets, (size_t)(n_lists + 1) * 4);
         if (n_weights) memcpy(h + o_w, weights, (size_t)n_weights * 4);
@@ -1172,9 +1210,7 @@ int sg_rrf_fuse(int device, float k, const float *weights, uint32_t n_weights, c
         set_error("sg_rrf_fuse: %s", cudaGetErrorString(e));
         ret = SG_ERR_CUDA;
     }
-    if (st) cudaStreamDestroy(st);
-    cudaFreeHost(h);
-    cudaFree(d);
+    sc->mu.unlock();
     return ret;
 }
 
