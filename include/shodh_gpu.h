@@ -46,9 +46,17 @@ typedef enum sg_status {
 /* element type the corpus is held in on the device (queries are always f32) */
 typedef enum sg_dtype { SG_DTYPE_F32 = 0, SG_DTYPE_F16 = 1 } sg_dtype;
 
-/* src/vector_db/vamana.rs:44-60 DistanceMetric.  RetrievalEngine only permits
- * NormalizedDotProduct (src/memory/retrieval.rs:188-193): distance = -dot. */
-typedef enum sg_metric { SG_METRIC_NEG_DOT = 0 } sg_metric;
+/* src/vector_db/vamana.rs:38-54 DistanceMetric, dispatched by VamanaIndex::distance (:755-761).
+ * RetrievalEngine only permits NormalizedDotProduct (src/memory/retrieval.rs:188-193); the other
+ * two are what a standalone VamanaIndex accepts.  All are scored in the reference's summation order
+ * by the exact sweep; only NEG_DOT batches use the tensor-core sweep. */
+typedef enum sg_metric {
+    SG_METRIC_NEG_DOT = 0,    /* normalized_distance_inline (distance_inline.rs:479-481): -dot */
+    SG_METRIC_EUCLIDEAN = 1,  /* euclidean_squared_inline (:184-305): |a-b|^2 */
+    SG_METRIC_COSINE = 2,     /* 1 - cosine_similarity_inline (:444-458) */
+    SG_METRIC_COSINE_SIM = 3  /* -cosine_similarity of src/similarity.rs:10-24 ranked as top_k_similar does
+                                 (:27-48: score desc, ties keep input order); what sg_top_k_similar runs on */
+} sg_metric;
 
 /* which summation order the exact scores reproduce */
 typedef enum sg_order {
@@ -122,6 +130,14 @@ SG_API int sg_store_set_id_base(sg_store *s, uint32_t id_base);
  * Limit: k <= 1024. */
 SG_API int sg_store_search(sg_store *s, const float *queries_f32, uint32_t b, uint32_t k,
                            uint32_t *ids_out, float *dist_out, uint32_t *counts_out);
+
+/* src/similarity.rs:27-48 top_k_similar(query, candidates, k) with cosine_similarity (:10-24: three dots in
+ * dot_product_inline's order, 0 on a zero norm or length mismatch, clamp to [-1,1]): candidates is a dense
+ * [n,dim] f32 matrix (the reference's &[(Vec<f32>,T)] with T = the row position), scored on the device in the
+ * reference's summation order and ranked (score desc, position asc) -- OrderedFloat order, stable sort.
+ * Writes min(k,n) positions and scores.  dim must be a multiple of 32, k <= 1024. */
+SG_API int sg_top_k_similar(int device, const float *query, uint32_t query_dim, const float *candidates, uint64_t n,
+                            uint32_t dim, uint32_t k, int order, uint32_t *pos_out, float *score_out, uint32_t *n_out);
 
 /* RetrievalEngine::search_ids from the embedding on (src/memory/retrieval.rs:905-964): the vector id ->
  * MemoryId table of IdMapping (vec2mem[i] = the Uuid of the memory that owns vector i as two big-endian

@@ -41,6 +41,14 @@ def lib() -> C.CDLL:
         L.so_dot.argtypes = [f32p, f32p, C.c_uint32, C.c_int]
         L.so_euclidean_squared.restype = C.c_float
         L.so_euclidean_squared.argtypes = [f32p, f32p, C.c_uint32]
+        L.so_euclidean_squared_avx2.restype = C.c_float
+        L.so_euclidean_squared_avx2.argtypes = [f32p, f32p, C.c_uint32]
+        L.so_l2_norm_squared_avx2.restype = C.c_float
+        L.so_l2_norm_squared_avx2.argtypes = [f32p, C.c_uint32]
+        L.so_cosine_similarity_inline_v.restype = C.c_float
+        L.so_cosine_similarity_inline_v.argtypes = [f32p, f32p, C.c_uint32, C.c_int]
+        L.so_distance.restype = C.c_float
+        L.so_distance.argtypes = [f32p, f32p, C.c_uint32, C.c_int, C.c_int]
         L.so_l2_norm.restype = C.c_float
         L.so_l2_norm.argtypes = [f32p, C.c_uint32]
         L.so_l2_norm_squared.restype = C.c_float
@@ -108,9 +116,22 @@ def dot(a, b, variant=VARIANT_SCALAR) -> float:
     return float(lib().so_dot(_p(a, C.c_float), _p(b, C.c_float), a.size, variant))
 
 
-def euclidean_squared(a, b) -> float:
+def euclidean_squared(a, b, variant=VARIANT_SCALAR) -> float:
     a, b = _f32(a), _f32(b)
-    return float(lib().so_euclidean_squared(_p(a, C.c_float), _p(b, C.c_float), a.size))
+    fn = lib().so_euclidean_squared_avx2 if variant == VARIANT_AVX2 else lib().so_euclidean_squared
+    return float(fn(_p(a, C.c_float), _p(b, C.c_float), a.size))
+
+
+def l2_norm_squared(a, variant=VARIANT_SCALAR) -> float:
+    a = _f32(a)
+    fn = lib().so_l2_norm_squared_avx2 if variant == VARIANT_AVX2 else lib().so_l2_norm_squared
+    return float(fn(_p(a, C.c_float), a.size))
+
+
+def distance(a, b, metric=METRIC_NEG_DOT, variant=VARIANT_SCALAR) -> float:
+    """VamanaIndex::distance (vamana.rs:755-761)."""
+    a, b = _f32(a), _f32(b)
+    return float(lib().so_distance(_p(a, C.c_float), _p(b, C.c_float), a.size, metric, variant))
 
 
 def l2_norm(a) -> float:
@@ -128,9 +149,9 @@ def cosine_similarity(a, b, variant=VARIANT_SCALAR) -> float:
     return float(lib().so_cosine_similarity(_p(a, C.c_float), a.size, _p(b, C.c_float), b.size, variant))
 
 
-def cosine_similarity_inline(a, b) -> float:
+def cosine_similarity_inline(a, b, variant=VARIANT_SCALAR) -> float:
     a, b = _f32(a), _f32(b)
-    return float(lib().so_cosine_similarity_inline(_p(a, C.c_float), _p(b, C.c_float), a.size))
+    return float(lib().so_cosine_similarity_inline_v(_p(a, C.c_float), _p(b, C.c_float), a.size, variant))
 
 
 def normalize(a) -> np.ndarray:

@@ -120,6 +120,29 @@ SO_EXPORT float so_euclidean_squared(const float *a, const float *b, uint32_t le
     return sum;
 }
 
+/* src/vector_db/distance_inline.rs:218-252 euclidean_squared_avx2_inline, lane by lane:
+ * diff = a - b; sum = fma(diff, diff, sum) per block of 8; lanes summed left to right;
+ * scalar tail `result += diff*diff` (not fused). */
+__attribute__((target("fma")))
+SO_EXPORT float so_euclidean_squared_avx2(const float *a, const float *b, uint32_t len)
+{
+    uint32_t simd_len = len & ~7u;
+    float lane[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t i = 0; i < simd_len; i += 8)
+        for (int j = 0; j < 8; ++j) {
+            float diff = a[i + j] - b[i + j];
+            lane[j] = __builtin_fmaf(diff, diff, lane[j]);
+        }
+    float result = lane[0] + lane[1];
+    for (int j = 2; j < 8; ++j) result = result + lane[j];
+    for (uint32_t j = simd_len; j < len; ++j) {
+        float diff = a[j] - b[j];
+        float p = diff * diff;
+        result = result + p;
+    }
+    return result;
+}
+
 /* src/vector_db/distance_inline.rs:415-431 l2_norm_squared_scalar_inline */
 SO_EXPORT float so_l2_norm_squared(const float *a, uint32_t len)
 {
@@ -134,6 +157,24 @@ SO_EXPORT float so_l2_norm_squared(const float *a, uint32_t len)
     }
     for (uint32_t j = unroll_len; j < len; ++j) sum += a[j] * a[j];
     return sum;
+}
+
+/* src/vector_db/distance_inline.rs:357-388 l2_norm_squared_avx2_inline: sum = fma(va, va, sum) per block
+ * of 8, lanes summed left to right, scalar tail not fused. */
+__attribute__((target("fma")))
+SO_EXPORT float so_l2_norm_squared_avx2(const float *a, uint32_t len)
+{
+    uint32_t simd_len = len & ~7u;
+    float lane[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t i = 0; i < simd_len; i += 8)
+        for (int j = 0; j < 8; ++j) lane[j] = __builtin_fmaf(a[i + j], a[i + j], lane[j]);
+    float result = lane[0] + lane[1];
+    for (int j = 2; j < 8; ++j) result = result + lane[j];
+    for (uint32_t j = simd_len; j < len; ++j) {
+        float p = a[j] * a[j];
+        result = result + p;
+    }
+    return result;
 }
 
 /* src/vector_db/distance_inline.rs:315-317 l2_norm_inline */
@@ -170,15 +211,20 @@ SO_EXPORT float so_cosine_similarity(const float *a, uint32_t len_a, const float
 }
 
 /* src/vector_db/distance_inline.rs:444-458 cosine_similarity_inline:
- * dot / sqrt(|a|^2 * |b|^2), `< 1e-10 -> 0`, no clamp. */
-SO_EXPORT float so_cosine_similarity_inline(const float *a, const float *b, uint32_t len)
+ * dot / sqrt(|a|^2 * |b|^2), `< 1e-10 -> 0`, no clamp.  variant picks the build
+ * (scalar / avx2+fma) for the dot and for both l2_norm_squared_inline calls. */
+SO_EXPORT float so_cosine_similarity_inline_v(const float *a, const float *b, uint32_t len, int variant)
 {
-    float dot = so_dot_scalar(a, b, len);
-    float na = so_l2_norm_squared(a, len);
-    float nb = so_l2_norm_squared(b, len);
+    float dot = so_dot(a, b, len, variant);
+    float na = variant == 1 ? so_l2_norm_squared_avx2(a, len) : so_l2_norm_squared(a, len);
+    float nb = variant == 1 ? so_l2_norm_squared_avx2(b, len) : so_l2_norm_squared(b, len);
     float denominator = sqrtf(na * nb);
     if (denominator < 1e-10f) return 0.0f;
     return dot / denominator;
+}
+SO_EXPORT float so_cosine_similarity_inline(const float *a, const float *b, uint32_t len)
+{
+    return so_cosine_similarity_inline_v(a, b, len, 0);
 }
 
 /* src/vector_db/distance_inline.rs:494-503 normalize_inplace */
@@ -196,8 +242,8 @@ SO_EXPORT void so_normalize_inplace(float *a, uint32_t len)
 SO_EXPORT float so_distance(const float *a, const float *b, uint32_t len, int metric, int variant)
 {
     switch (metric) {
-    case 1: return so_euclidean_squared(a, b, len);
-    case 2: return 1.0f - so_cosine_similarity_inline(a, b, len);
+    case 1: return variant == 1 ? so_euclidean_squared_avx2(a, b, len) : so_euclidean_squared(a, b, len);
+    case 2: return 1.0f - so_cosine_similarity_inline_v(a, b, len, variant);
     default: return so_normalized_distance(a, b, len, variant);
     }
 }

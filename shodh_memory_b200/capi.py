@@ -15,7 +15,7 @@ SG_OK = 0
 SG_ERR_INVALID, SG_ERR_CUDA, SG_ERR_OOM, SG_ERR_DIM = -1, -2, -3, -4
 SG_ERR_UNSUPPORTED, SG_ERR_NO_DEVICE, SG_ERR_NOT_BUILT = -5, -6, -7
 SG_DTYPE_F32, SG_DTYPE_F16 = 0, 1
-SG_METRIC_NEG_DOT = 0
+SG_METRIC_NEG_DOT, SG_METRIC_EUCLIDEAN, SG_METRIC_COSINE, SG_METRIC_COSINE_SIM = 0, 1, 2, 3
 SG_ORDER_SCALAR, SG_ORDER_AVX2 = 0, 1
 
 
@@ -89,6 +89,8 @@ def lib() -> C.CDLL:
     L.sg_store_set_profiling.argtypes = [vp, C.c_int]
     L.sg_store_last_scan_ms.argtypes = [vp, f32p, u32p]
     L.sg_store_search.argtypes = [vp, f32p, C.c_uint32, C.c_uint32, u32p, f32p, u32p]
+    L.sg_top_k_similar.argtypes = [C.c_int, f32p, C.c_uint32, f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, u32p, f32p,
+                                   u32p]
     L.sg_store_set_memory_ids.argtypes = [vp, u64p, C.c_uint64]
     L.sg_store_search_memory_ids.argtypes = [vp, f32p, C.c_uint32, C.c_uint32, u64p, f32p, u32p]
     L.sg_store_search_device.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]

@@ -40,6 +40,85 @@ struct WarpTopK {
     uint32_t tau[QB];
 };
 
+
+// ---- per-metric accumulation of 4 consecutive elements (query q, row x) -------------------------
+// METRIC 0 (NormalizedDotProduct), 2 (Cosine) and 3 (similarity.rs cosine) accumulate q*x in the
+// order of dot_product_{scalar,avx2}_inline (distance_inline.rs:157-173 / :67-111); METRIC 1
+// (Euclidean) accumulates (q-x)^2 in the order of euclidean_squared_{scalar,avx2}_inline
+// (:284-305 / :218-252).  `o` selects the AVX lane group (element e -> lane e % 8).
+template <int ORDER, int METRIC>
+SG_DEVICE_INLINE void accum4(float *acc, const float4 q, float x0, float x1, float x2, float x3, int o)
+{
+    if constexpr (METRIC == SG_METRIC_EUCLIDEAN) {
+        const float d0 = __fsub_rn(q.x, x0), d1 = __fsub_rn(q.y, x1), d2 = __fsub_rn(q.z, x2), d3 = __fsub_rn(q.w, x3);
+        if constexpr (ORDER == SG_ORDER_SCALAR) {
+            const float g = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)),
+                                      __fmul_rn(d3, d3));
+            acc[0] = __fadd_rn(acc[0], g);
+        } else {
+            acc[o + 0] = __fmaf_rn(d0, d0, acc[o + 0]);
+            acc[o + 1] = __fmaf_rn(d1, d1, acc[o + 1]);
+            acc[o + 2] = __fmaf_rn(d2, d2, acc[o + 2]);
+            acc[o + 3] = __fmaf_rn(d3, d3, acc[o + 3]);
+        }
+    } else {
+        if constexpr (ORDER == SG_ORDER_SCALAR) {
+            // sum = sum + (((p0+p1)+p2)+p3), every product rounded (no FMA)
+            const float g = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(q.x, x0), __fmul_rn(q.y, x1)), __fmul_rn(q.z, x2)),
+                                      __fmul_rn(q.w, x3));
+            acc[0] = __fadd_rn(acc[0], g);
+        } else {
+            // 8 AVX lanes, fused multiply-add
+            acc[o + 0] = __fmaf_rn(q.x, x0, acc[o + 0]);
+            acc[o + 1] = __fmaf_rn(q.y, x1, acc[o + 1]);
+            acc[o + 2] = __fmaf_rn(q.z, x2, acc[o + 2]);
+            acc[o + 3] = __fmaf_rn(q.w, x3, acc[o + 3]);
+        }
+    }
+}
+// lanes summed left to right (distance_inline.rs:95-103); the scalar build has one accumulator
+template <int ORDER>
+SG_DEVICE_INLINE float hsum(const float *acc)
+{
+    if constexpr (ORDER == SG_ORDER_SCALAR) {
+        return acc[0];
+    } else {
+        float r = __fadd_rn(acc[0], acc[1]);
+#pragma unroll
+        for (int t = 2; t < 8; ++t) r = __fadd_rn(r, acc[t]);
+        return r;
+    }
+}
+SG_DEVICE_INLINE float canon_nan(float x) { return (x != x) ? __uint_as_float(0x7FC00000u) : x; }
+
+// accumulated sums -> the distance the ranking uses.  qn2 / rn2 = |query|^2 / |row|^2 in the same order.
+template <int METRIC>
+SG_DEVICE_INLINE float finish_distance(float s, float qn2, float rn2)
+{
+    if constexpr (METRIC == SG_METRIC_NEG_DOT) {
+        return neg_dot_to_dist(s);
+    } else if constexpr (METRIC == SG_METRIC_EUCLIDEAN) {
+        return canon_nan(s);
+    } else if constexpr (METRIC == SG_METRIC_COSINE) {
+        // 1 - cosine_similarity_inline (distance_inline.rs:444-458): dot / sqrt(|a|^2 |b|^2), `< 1e-10 -> 0`
+        const float den = __fsqrt_rn(__fmul_rn(qn2, rn2));
+        const float c = (den < 1e-10f) ? 0.0f : __fdiv_rn(s, den);
+        return canon_nan(__fsub_rn(1.0f, c));
+    } else {
+        // -cosine_similarity (similarity.rs:10-24): 0 on a zero norm, clamp to [-1,1] (NaN stays NaN).
+        // OrderedFloat order for top_k_similar (:27-48): NaN greatest, -0 == +0, ties keep input order.
+        const float na = __fsqrt_rn(qn2), nb = __fsqrt_rn(rn2);
+        float c = 0.0f;
+        if (!(na == 0.0f || nb == 0.0f)) {
+            c = __fdiv_rn(s, __fmul_rn(na, nb));
+            if (c < -1.0f) c = -1.0f;
+            if (c > 1.0f) c = 1.0f;
+        }
+        c = (c != c) ? __uint_as_float(0x7FC00000u) : __fadd_rn(c, 0.0f);   // one NaN, no -0
+        return -c;                                                            // -NaN sorts first in totalOrder
+    }
+}
+
 // sort the warp's candidate buffer, keep the best k, refresh the threshold
 SG_DEVICE_INLINE void compact(uint64_t *buf, uint32_t &cnt, uint32_t &tau, uint32_t k, uint32_t lane)
 {
@@ -51,7 +130,7 @@ SG_DEVICE_INLINE void compact(uint64_t *buf, uint32_t &cnt, uint32_t &tau, uint3
     if (cnt == k) tau = (uint32_t)(buf[k - 1] >> 32);
 }
 
-template <int QB, bool F16, int ORDER>
+template <int QB, bool F16, int ORDER, int METRIC>
 __global__ void __launch_bounds__(512, 1)
 scan_exact_kernel(const __grid_constant__ CUtensorMap tmap, const ScanArgs a)
 {
@@ -70,6 +149,7 @@ scan_exact_kernel(const __grid_constant__ CUtensorMap tmap, const ScanArgs a)
     uint64_t *cand = reinterpret_cast<uint64_t *>(q_s + (size_t)QB * dim);        // [W][QB][C]
     uint32_t *cnt_s = reinterpret_cast<uint32_t *>(cand + (size_t)W * QB * C);    // [W][QB]
     uint64_t *bars = reinterpret_cast<uint64_t *>(cnt_s + ((W * QB + 1) & ~1u));  // [W][ring]
+    float *qn_s = reinterpret_cast<float *>(bars + (size_t)W * ring);             // [QB] |query|^2 (cosine metrics)
 
     // "flagged" mode (device-side conditional re-run of uncertified tensor-path queries): the number
     // of queries and their indices live in device memory; with zero flagged queries every CTA exits here.
@@ -109,6 +189,22 @@ scan_exact_kernel(const __grid_constant__ CUtensorMap tmap, const ScanArgs a)
         q_s[i] = v;
     }
     __syncthreads();
+    if constexpr (METRIC == SG_METRIC_COSINE || METRIC == SG_METRIC_COSINE_SIM) {
+        // |query|^2 once per sweep, in the reference's order (l2_norm_squared_*_inline :366-431 == dot(a,a))
+        if (threadIdx.x < (uint32_t)QB) {
+            constexpr int NA = (ORDER == SG_ORDER_AVX2) ? 8 : 1;
+            float nacc[NA];
+#pragma unroll
+            for (int t = 0; t < NA; ++t) nacc[t] = 0.0f;
+            const float *qq = q_s + (size_t)threadIdx.x * dim;
+            for (uint32_t d = 0; d < dim; d += 4) {
+                const float4 v4 = *reinterpret_cast<const float4 *>(qq + d);
+                accum4<ORDER, SG_METRIC_NEG_DOT>(nacc, v4, v4.x, v4.y, v4.z, v4.w, (int)(d & 4));
+            }
+            qn_s[threadIdx.x] = hsum<ORDER>(nacc);
+        }
+        __syncthreads();
+    }
     // producer state (lane 0 only uses it, but keep it warp-uniform)
     uint64_t issued = 0;
     uint64_t issue_tile = gw;
@@ -148,7 +244,11 @@ scan_exact_kernel(const __grid_constant__ CUtensorMap tmap, const ScanArgs a)
         if (a.deleted) del_word = __ldg(a.deleted + tile);
 
         constexpr int NACC = (ORDER == SG_ORDER_AVX2) ? 8 : 1;
+        constexpr bool ROWNORM = (METRIC == SG_METRIC_COSINE || METRIC == SG_METRIC_COSINE_SIM);
         float acc[QB][NACC];
+        float racc[NACC];      // |row|^2 chain (cosine metrics only)
+#pragma unroll
+        for (int t = 0; t < NACC; ++t) racc[t] = 0.0f;
 #pragma unroll
         for (int q = 0; q < QB; ++q)
 #pragma unroll
@@ -173,49 +273,26 @@ scan_exact_kernel(const __grid_constant__ CUtensorMap tmap, const ScanArgs a)
                         f = __half22float2(*reinterpret_cast<__half2 *>(&v.z)); x[4] = f.x; x[5] = f.y;
                         f = __half22float2(*reinterpret_cast<__half2 *>(&v.w)); x[6] = f.x; x[7] = f.y;
                     }
+                    if constexpr (ROWNORM) {
+                        accum4<ORDER, SG_METRIC_NEG_DOT>(racc, make_float4(x[0], x[1], x[2], x[3]), x[0], x[1], x[2], x[3], 0);
+                        accum4<ORDER, SG_METRIC_NEG_DOT>(racc, make_float4(x[4], x[5], x[6], x[7]), x[4], x[5], x[6], x[7], 4);
+                    }
 #pragma unroll
                     for (int q = 0; q < QB; ++q) {
                         const float4 qa = *reinterpret_cast<const float4 *>(qj + q * dim + c * 8);
                         const float4 qb = *reinterpret_cast<const float4 *>(qj + q * dim + c * 8 + 4);
-                        if constexpr (ORDER == SG_ORDER_SCALAR) {
-                            // sum = sum + (((p0+p1)+p2)+p3), every product rounded (no FMA)
-                            float g0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(qa.x, x[0]), __fmul_rn(qa.y, x[1])),
-                                                           __fmul_rn(qa.z, x[2])), __fmul_rn(qa.w, x[3]));
-                            acc[q][0] = __fadd_rn(acc[q][0], g0);
-                            float g1 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(qb.x, x[4]), __fmul_rn(qb.y, x[5])),
-                                                           __fmul_rn(qb.z, x[6])), __fmul_rn(qb.w, x[7]));
-                            acc[q][0] = __fadd_rn(acc[q][0], g1);
-                        } else {
-                            // 8 AVX lanes, fused multiply-add, element e -> lane e % 8
-                            acc[q][0] = __fmaf_rn(qa.x, x[0], acc[q][0]);
-                            acc[q][1] = __fmaf_rn(qa.y, x[1], acc[q][1]);
-                            acc[q][2] = __fmaf_rn(qa.z, x[2], acc[q][2]);
-                            acc[q][3] = __fmaf_rn(qa.w, x[3], acc[q][3]);
-                            acc[q][4] = __fmaf_rn(qb.x, x[4], acc[q][4]);
-                            acc[q][5] = __fmaf_rn(qb.y, x[5], acc[q][5]);
-                            acc[q][6] = __fmaf_rn(qb.z, x[6], acc[q][6]);
-                            acc[q][7] = __fmaf_rn(qb.w, x[7], acc[q][7]);
-                        }
+                        accum4<ORDER, METRIC>(acc[q], qa, x[0], x[1], x[2], x[3], 0);
+                        accum4<ORDER, METRIC>(acc[q], qb, x[4], x[5], x[6], x[7], 4);
                     }
                 } else {
                     const float x0 = __uint_as_float(v.x), x1 = __uint_as_float(v.y);
                     const float x2 = __uint_as_float(v.z), x3 = __uint_as_float(v.w);
+                    const int o = (c & 1) * 4;
+                    if constexpr (ROWNORM) accum4<ORDER, SG_METRIC_NEG_DOT>(racc, make_float4(x0, x1, x2, x3), x0, x1, x2, x3, o);
 #pragma unroll
                     for (int q = 0; q < QB; ++q) {
                         const float4 qa = *reinterpret_cast<const float4 *>(qj + q * dim + c * 4);
-                        if constexpr (ORDER == SG_ORDER_SCALAR) {
-                            float g0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(qa.x, x0), __fmul_rn(qa.y, x1)),
-                                                           __fmul_rn(qa.z, x2)), __fmul_rn(qa.w, x3));
-                            acc[q][0] = __fadd_rn(acc[q][0], g0);
-                        } else {
-                            constexpr int dummy = 0;
-                            (void)dummy;
-                            const int o = (c & 1) * 4;
-                            acc[q][o + 0] = __fmaf_rn(qa.x, x0, acc[q][o + 0]);
-                            acc[q][o + 1] = __fmaf_rn(qa.y, x1, acc[q][o + 1]);
-                            acc[q][o + 2] = __fmaf_rn(qa.z, x2, acc[q][o + 2]);
-                            acc[q][o + 3] = __fmaf_rn(qa.w, x3, acc[q][o + 3]);
-                        }
+                        accum4<ORDER, METRIC>(acc[q], qa, x0, x1, x2, x3, o);
                     }
                 }
             }
@@ -233,15 +310,12 @@ scan_exact_kernel(const __grid_constant__ CUtensorMap tmap, const ScanArgs a)
         const bool live = row < a.n_rows && !((del_word >> lane) & 1u);
 #pragma unroll
         for (int q = 0; q < QB; ++q) {
-            float dot;
-            if constexpr (ORDER == SG_ORDER_SCALAR) {
-                dot = acc[q][0];
-            } else {
-                dot = __fadd_rn(acc[q][0], acc[q][1]);
-#pragma unroll
-                for (int t = 2; t < 8; ++t) dot = __fadd_rn(dot, acc[q][t]);
+            float qn2 = 0.0f, rn2 = 0.0f;
+            if constexpr (ROWNORM) {
+                qn2 = qn_s[q];
+                rn2 = hsum<ORDER>(racc);
             }
-            const uint32_t key32 = order_key32(neg_dot_to_dist(dot));
+            const uint32_t key32 = order_key32(finish_distance<METRIC>(hsum<ORDER>(acc[q]), qn2, rn2));
             uint64_t *buf = my_cand + (size_t)q * C;
             if (tk.cnt[q] + 32 > C) compact(buf, tk.cnt[q], tk.tau[q], a.k, lane);
             const bool hit = live && (q < (int)nq_grp) && key32 <= tk.tau[q];
@@ -281,11 +355,11 @@ scan_exact_kernel(const __grid_constant__ CUtensorMap tmap, const ScanArgs a)
     }  // group loop
 }
 
-template <int QB, bool F16, int ORDER>
+template <int QB, bool F16, int ORDER, int METRIC>
 cudaError_t launch_t(const CUtensorMap &tmap, const ScanArgs &a, dim3 grid, dim3 block, size_t smem,
                      cudaStream_t st)
 {
-    auto kern = scan_exact_kernel<QB, F16, ORDER>;
+    auto kern = scan_exact_kernel<QB, F16, ORDER, METRIC>;
     static size_t smem_set_dev[64] = {0};     // per instantiation and device: raise the opt-in limit only when it grows
     int dev_ = 0;
     cudaGetDevice(&dev_);
@@ -309,24 +383,42 @@ size_t scan_smem_bytes(uint32_t W, uint32_t ring, uint32_t qb, uint32_t dim, uin
     s += (size_t)W * qb * cap * 8;
     s += (size_t)((W * qb + 1) & ~1u) * 4;
     s += (size_t)W * ring * 8;
+    s += 16;  // |query|^2 per query of the sweep
     return s;
 }
 
-cudaError_t launch_scan_exact(const CUtensorMap &tmap, const ScanArgs &a, int qb, bool f16, int order,
+template <int QB, int METRIC>
+static cudaError_t launch_qm(const CUtensorMap &tmap, const ScanArgs &a, bool f16, int order, dim3 g, dim3 b, size_t smem,
+                             cudaStream_t st)
+{
+    if (f16) return order == SG_ORDER_AVX2 ? launch_t<QB, true, SG_ORDER_AVX2, METRIC>(tmap, a, g, b, smem, st)
+                                           : launch_t<QB, true, SG_ORDER_SCALAR, METRIC>(tmap, a, g, b, smem, st);
+    return order == SG_ORDER_AVX2 ? launch_t<QB, false, SG_ORDER_AVX2, METRIC>(tmap, a, g, b, smem, st)
+                                  : launch_t<QB, false, SG_ORDER_SCALAR, METRIC>(tmap, a, g, b, smem, st);
+}
+
+// NormalizedDotProduct sweeps serve 1, 2 or 4 queries; the other metrics (not on RetrievalEngine's path,
+// retrieval.rs:188-193) are instantiated for 1 and 4 only.
+cudaError_t launch_scan_exact(const CUtensorMap &tmap, const ScanArgs &a, int qb, bool f16, int order, int metric,
                               uint32_t grid, uint32_t W, size_t smem, cudaStream_t st)
 {
     dim3 g(grid), b(W * 32);
-#define SG_DISPATCH(QB)                                                                         \
-    if (qb == QB) {                                                                             \
-        if (f16) return order == SG_ORDER_AVX2 ? launch_t<QB, true, SG_ORDER_AVX2>(tmap, a, g, b, smem, st)   \
-                                               : launch_t<QB, true, SG_ORDER_SCALAR>(tmap, a, g, b, smem, st); \
-        return order == SG_ORDER_AVX2 ? launch_t<QB, false, SG_ORDER_AVX2>(tmap, a, g, b, smem, st)     \
-                                      : launch_t<QB, false, SG_ORDER_SCALAR>(tmap, a, g, b, smem, st);  \
+    if (metric == SG_METRIC_NEG_DOT) {
+        if (qb == 1) return launch_qm<1, SG_METRIC_NEG_DOT>(tmap, a, f16, order, g, b, smem, st);
+        if (qb == 2) return launch_qm<2, SG_METRIC_NEG_DOT>(tmap, a, f16, order, g, b, smem, st);
+        if (qb == 4) return launch_qm<4, SG_METRIC_NEG_DOT>(tmap, a, f16, order, g, b, smem, st);
+        return cudaErrorInvalidValue;
     }
-    SG_DISPATCH(1)
-    SG_DISPATCH(2)
-    SG_DISPATCH(4)
-#undef SG_DISPATCH
+#define SG_DISPATCH_METRIC(M)                                                                  \
+    if (metric == M) {                                                                         \
+        if (qb == 1) return launch_qm<1, M>(tmap, a, f16, order, g, b, smem, st);              \
+        if (qb == 4) return launch_qm<4, M>(tmap, a, f16, order, g, b, smem, st);              \
+        return cudaErrorInvalidValue;                                                          \
+    }
+    SG_DISPATCH_METRIC(SG_METRIC_EUCLIDEAN)
+    SG_DISPATCH_METRIC(SG_METRIC_COSINE)
+    SG_DISPATCH_METRIC(SG_METRIC_COSINE_SIM)
+#undef SG_DISPATCH_METRIC
     return cudaErrorInvalidValue;
 }
 

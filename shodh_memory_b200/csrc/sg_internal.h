@@ -20,7 +20,7 @@ struct ScanArgs {
     const uint32_t *flag_list;   // flagged mode: their indices into `queries`
 };
 size_t scan_smem_bytes(uint32_t W, uint32_t ring, uint32_t qb, uint32_t dim, uint32_t cap);
-cudaError_t launch_scan_exact(const CUtensorMap &tmap, const ScanArgs &a, int qb, bool f16, int order,
+cudaError_t launch_scan_exact(const CUtensorMap &tmap, const ScanArgs &a, int qb, bool f16, int order, int metric,
                               uint32_t grid, uint32_t W, size_t smem, cudaStream_t st);
 
 // ---- scan_tc.cu (tensor-core sweep) ----

@@ -304,7 +304,9 @@ int search_exact_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, u
         return SG_OK;
     }
     // one plan for the widest sweep; narrower sweeps reuse W/ring/grid (their smem is smaller)
-    const uint32_t qb_max = b >= 3 ? 4 : b;
+    // NormalizedDotProduct sweeps exist for 1, 2 and 4 queries, the other metrics for 1 and 4
+    const bool nd = s->metric == SG_METRIC_NEG_DOT;
+    const uint32_t qb_max = b >= (nd ? 3u : 2u) ? 4 : b;
     ScanPlan plan;
     int rc = plan_scan(s, k, qb_max, &plan);
     if (rc != SG_OK) return rc;
@@ -323,7 +325,7 @@ int search_exact_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, u
     uint32_t done = 0;
     while (done < b) {
         const uint32_t rem = b - done;
-        const uint32_t qb = rem >= 3 ? 4 : rem;
+        const uint32_t qb = rem >= (nd ? 3u : 2u) ? 4 : rem;
         const uint32_t nq = rem < qb ? rem : qb;
         ScanArgs a;
         a.queries = d_q + (size_t)done * s->dim;
@@ -339,7 +341,7 @@ int search_exact_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, u
         a.flag_count = nullptr;
         a.flag_list = nullptr;
         size_t smem = scan_smem_bytes(plan.W, plan.ring, qb, s->dim, plan.cap);
-        cudaError_t e = launch_scan_exact(tmap, a, (int)qb, s->dtype == SG_DTYPE_F16, s->order, L, plan.W, smem, st);
+        cudaError_t e = launch_scan_exact(tmap, a, (int)qb, s->dtype == SG_DTYPE_F16, s->order, s->metric, L, plan.W, smem, st);
         if (e != cudaSuccess) {
             set_error("scan kernel launch failed: %s", cudaGetErrorString(e));
             return SG_ERR_CUDA;
@@ -361,7 +363,7 @@ int search_exact_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, u
 // re-run on path A.  Returns SG_ERR_UNSUPPORTED (without side effects) if the shape does not fit.
 bool tc_eligible(const sg_store *s, uint32_t b, uint32_t k, uint32_t *kk_out, uint32_t *stages_out)
 {
-    if (s->dtype != SG_DTYPE_F16 || s->dim % 64 != 0) return false;
+    if (s->dtype != SG_DTYPE_F16 || s->dim % 64 != 0 || s->metric != SG_METRIC_NEG_DOT) return false;
     if (env_u32("SG_TC_DISABLE", 0)) return false;
     if (b < (uint32_t)env_u32("SG_TC_MIN_B", 5)) return false;
     if (k > 24 || s->n < 4096) return false;
@@ -505,7 +507,7 @@ int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint
     sa.out_lists = s->d_lists;
     sa.flag_count = s->d_nflag;
     sa.flag_list = s->d_flag_list;
-    cudaError_t e2 = launch_scan_exact(tmap32, sa, 4, true, s->order, LA, plan.W,
+    cudaError_t e2 = launch_scan_exact(tmap32, sa, 4, true, s->order, SG_METRIC_NEG_DOT, LA, plan.W,
                                        scan_smem_bytes(plan.W, plan.ring, 4, s->dim, plan.cap), st);
     if (e2 != cudaSuccess) {
         set_error("flagged exact sweep launch failed: %s", cudaGetErrorString(e2));
@@ -564,9 +566,9 @@ int sg_store_create(sg_store **out, int device, uint32_t dim, int dtype, int met
         set_error("unknown dtype %d", dtype);
         return SG_ERR_INVALID;
     }
-    if (metric != SG_METRIC_NEG_DOT) {
-        set_error("only NormalizedDotProduct is supported (RetrievalEngine refuses the others, retrieval.rs:188-193)");
-        return SG_ERR_UNSUPPORTED;
+    if (metric < SG_METRIC_NEG_DOT || metric > SG_METRIC_COSINE_SIM) {
+        set_error("unknown metric %d", metric);
+        return SG_ERR_INVALID;
     }
     const uint32_t mult = dtype == SG_DTYPE_F16 ? 64 : 32;
     if (dim == 0 || dim % mult != 0 || dim > 2048) {
@@ -919,6 +921,42 @@ int sg_store_search(sg_store *s, const float *queries, uint32_t b, uint32_t k, u
     memcpy(dist_out, hp + qbytes + rbytes, rbytes);
     memcpy(counts_out, hp + qbytes + 2 * rbytes, cbytes);
     return SG_OK;
+}
+
+int sg_top_k_similar(int device, const float *query, uint32_t query_dim, const float *candidates, uint64_t n,
+                     uint32_t dim, uint32_t k, int order, uint32_t *pos_out, float *score_out, uint32_t *n_out)
+{
+    if (!n_out || (n && k && (!query || !candidates || !pos_out || !score_out))) return SG_ERR_INVALID;
+    *n_out = 0;
+    if (n == 0 || k == 0) return SG_OK;
+    const uint32_t r = (uint32_t)(n < k ? n : k);
+    if (query_dim != dim) {
+        // cosine_similarity returns 0.0 on a length mismatch (similarity.rs:11-13): every score ties at 0 and
+        // the stable sort keeps the input order
+        for (uint32_t i = 0; i < r; ++i) {
+            pos_out[i] = i;
+            score_out[i] = 0.0f;
+        }
+        *n_out = r;
+        return SG_OK;
+    }
+    if (k > 1024) {
+        set_error("sg_top_k_similar: k=%u outside the supported range 1..1024", k);
+        return SG_ERR_UNSUPPORTED;
+    }
+    sg_store *st = nullptr;
+    int rc = sg_store_create(&st, device, dim, SG_DTYPE_F32, SG_METRIC_COSINE_SIM);
+    if (rc != SG_OK) return rc;
+    if ((rc = sg_store_set_order(st, order)) == SG_OK && (rc = sg_store_append(st, candidates, n, nullptr)) == SG_OK) {
+        uint32_t cnt = 0;
+        rc = sg_store_search(st, query, 1, k, pos_out, score_out, &cnt);
+        if (rc == SG_OK) {
+            for (uint32_t i = 0; i < cnt; ++i) score_out[i] = -score_out[i];   // the store ranks by -similarity
+            *n_out = cnt;
+        }
+    }
+    sg_store_destroy(st);
+    return rc;
 }
 
 int sg_store_set_memory_ids(sg_store *s, const uint64_t *vec2mem, uint64_t n)

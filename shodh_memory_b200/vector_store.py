@@ -14,6 +14,9 @@ import numpy as np
 from . import capi
 
 _DT = {"f16": capi.SG_DTYPE_F16, "f32": capi.SG_DTYPE_F32}
+# DistanceMetric (vamana.rs:38-54) + the similarity.rs ranking sg_top_k_similar uses
+_METRIC = {"neg_dot": capi.SG_METRIC_NEG_DOT, "euclidean": capi.SG_METRIC_EUCLIDEAN, "cosine": capi.SG_METRIC_COSINE,
+           "cosine_sim": capi.SG_METRIC_COSINE_SIM}
 
 
 def _ptr(a: np.ndarray, ty):
@@ -21,12 +24,13 @@ def _ptr(a: np.ndarray, ty):
 
 
 class GpuVectorStore:
-    def __init__(self, dim: int = 384, dtype: str = "f16", device: int = 0):
+    def __init__(self, dim: int = 384, dtype: str = "f16", device: int = 0, metric: str = "neg_dot"):
         self._h = C.c_void_p()
         self.dim = dim
         self.dtype = dtype
         self.device = device
-        capi.check(capi.lib().sg_store_create(C.byref(self._h), device, dim, _DT[dtype], capi.SG_METRIC_NEG_DOT))
+        self.metric = metric
+        capi.check(capi.lib().sg_store_create(C.byref(self._h), device, dim, _DT[dtype], _METRIC[metric]))
 
     # -- lifecycle --------------------------------------------------------------------
     def close(self) -> None:
@@ -169,6 +173,28 @@ class GpuVectorStore:
         ms, n = C.c_float(), C.c_uint32()
         capi.check(capi.lib().sg_store_last_scan_ms(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+
+def top_k_similar(query, candidates, k: int, order: str = "scalar", device: int = 0):
+    """similarity.rs::top_k_similar(query, candidates, k) -> (positions [r] u32, scores [r] f32), r = min(k, n)."""
+    q = np.ascontiguousarray(query, np.float32).ravel()
+    c = np.ascontiguousarray(candidates, np.float32)
+    if c.ndim != 2:
+        raise capi.SgError(capi.SG_ERR_DIM, f"expected [n,dim] candidates, got {c.shape}")
+    n, dim = c.shape
+    pos = np.empty(max(k, 1), np.uint32)
+    sc = np.empty(max(k, 1), np.float32)
+    r = C.c_uint32()
+    capi.check(capi.lib().sg_top_k_similar(device, _ptr(q, C.c_float), q.size, _ptr(c, C.c_float), n, dim, k,
+                                           capi.SG_ORDER_AVX2 if order == "avx2" else capi.SG_ORDER_SCALAR,
+                                           _ptr(pos, C.c_uint32), _ptr(sc, C.c_float), C.byref(r)))
+    return pos[:r.value].copy(), sc[:r.value].copy()
+
+
+def cosine_similarity(a, b, order: str = "scalar", device: int = 0) -> float:
+    """similarity.rs::cosine_similarity(a, b) evaluated on the device (one candidate)."""
+    _, sc = top_k_similar(a, np.asarray(b, np.float32)[None, :], 1, order, device)
+    return float(sc[0])
 
 
 def vama_inspect(path: str, verify_checksum: bool = True) -> dict:

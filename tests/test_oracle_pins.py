@@ -73,6 +73,48 @@ def test_c_dot_matches_python_restatement(oracle, n):
     assert oracle.dot(a, b, oracle.VARIANT_AVX2) == dot_avx2_py(a, b)
 
 
+def euclid_py(a, b, avx2):
+    """distance_inline.rs:284-305 (scalar) / :218-252 (avx2+fma), one rounding per operation."""
+    a = np.asarray(a, F); b = np.asarray(b, F)
+    n = len(a)
+    if not avx2:
+        s = F(0)
+        for i in range(0, n & ~3, 4):
+            d = [F(a[i + j] - b[i + j]) for j in range(4)]
+            s = F(s + F(F(F(F(d[0] * d[0]) + F(d[1] * d[1])) + F(d[2] * d[2])) + F(d[3] * d[3])))
+        for j in range(n & ~3, n):
+            d = F(a[j] - b[j]); s = F(s + F(d * d))
+        return float(s)
+    lane = [F(0)] * 8
+    for i in range(0, n & ~7, 8):
+        for j in range(8):
+            d = F(a[i + j] - b[i + j])
+            lane[j] = fma32(d, d, lane[j])
+    r = lane[0]
+    for j in range(1, 8):
+        r = F(r + lane[j])
+    for j in range(n & ~7, n):
+        d = F(a[j] - b[j]); r = F(r + F(d * d))
+    return float(r)
+
+
+@pytest.mark.parametrize("n", [4, 8, 13, 384])
+def test_c_euclidean_norm_cosine_match_python_restatement(oracle, n):
+    """both builds of euclidean_squared_inline / l2_norm_squared_inline / cosine_similarity_inline"""
+    rng = np.random.default_rng(n)
+    for _ in range(5):
+        a = (rng.standard_normal(n) * 3).astype(F); b = (rng.standard_normal(n) * 0.7).astype(F)
+        for variant in (0, 1):
+            assert oracle.euclidean_squared(a, b, variant) == euclid_py(a, b, variant == 1)
+            dot = dot_avx2_py if variant else dot_scalar_py
+            assert oracle.l2_norm_squared(a, variant) == dot(a, a)       # same operation order as dot(a, a)
+            den = F(np.sqrt(F(F(dot(a, a)) * F(dot(b, b)))))
+            want = float(F(F(dot(a, b)) / den))
+            assert oracle.cosine_similarity_inline(a, b, variant) == want
+            assert oracle.distance(a, b, 2, variant) == float(F(F(1) - F(want)))
+            assert oracle.distance(a, b, 1, variant) == oracle.euclidean_squared(a, b, variant)
+
+
 def test_summation_orders_differ_somewhere(oracle):
     """The two reference builds are genuinely different functions; the oracle keeps both."""
     rng = np.random.default_rng(7)
