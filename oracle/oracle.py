@@ -14,6 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "liboracle.so")
 _SRC = os.path.join(_HERE, "shodh_oracle.c")
+_SRCS = [_SRC, os.path.join(_HERE, "vamana_oracle.c"), os.path.join(_HERE, "build.sh")]
 
 DEFAULT_WEIGHTS = np.array([0.18, 0.17, 0.05, 0.05, 0.28, 0.14, 0.13], dtype=np.float32)
 
@@ -22,7 +23,7 @@ VARIANT_SCALAR, VARIANT_AVX2 = 0, 1
 
 
 def build(force: bool = False) -> str:
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(p) for p in _SRCS):
         subprocess.check_call(["sh", os.path.join(_HERE, "build.sh")])
     return _SO
 
@@ -98,6 +99,28 @@ def lib() -> C.CDLL:
         L.so_round_f16.argtypes = [f32p, f32p, C.c_uint64]
         L.so_max_threads.restype = C.c_int
         L.so_max_threads.argtypes = []
+        # vamana_oracle.c
+        L.so_greedy_search.restype = C.c_uint32
+        L.so_greedy_search.argtypes = [f32p, C.c_uint64, C.c_uint32, u32p, u32p, C.c_uint32, C.c_uint64, f32p,
+                                       C.c_uint32, C.c_uint32, C.c_int, C.c_int, u32p, f32p, u64p]
+        L.so_vamana_search.restype = C.c_uint32
+        L.so_vamana_search.argtypes = [f32p, C.c_uint64, C.c_uint32, u32p, u32p, C.c_uint32, C.c_uint32, u32p,
+                                       C.c_uint64, f32p, C.c_uint32, C.c_int, C.c_int, u32p, f32p, u64p]
+        L.so_robust_prune.restype = C.c_uint32
+        L.so_robust_prune.argtypes = [f32p, C.c_uint32, C.c_uint32, u32p, f32p, C.c_uint32, C.c_uint32, C.c_float,
+                                      C.c_int, C.c_int, u32p]
+        L.so_find_medoid.restype = C.c_uint32
+        L.so_find_medoid.argtypes = [f32p, C.c_uint64, C.c_uint32, C.c_int, C.c_int]
+        L.so_vamana_init_graph.restype = None
+        L.so_vamana_init_graph.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, u32p, u32p]
+        L.so_vamana_build.restype = C.c_uint32
+        L.so_vamana_build.argtypes = [f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_int,
+                                      C.c_int, C.c_uint32, C.c_uint32, u32p, u32p]
+        L.so_vamana_add_vector.restype = None
+        L.so_vamana_add_vector.argtypes = [f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_uint32,
+                                           C.c_uint32, u32p, u32p]
+        L.so_recall_at_k.restype = C.c_double
+        L.so_recall_at_k.argtypes = [u32p, u32p, u32p, u32p, C.c_uint32, C.c_uint32]
         _lib = L
     return _lib
 
@@ -326,3 +349,134 @@ def rrf_fuse(k, weights, lists):
     m = f(float(k), _p(weights, C.c_float), weights.size, _p(ids, C.c_uint64), _p(offsets, C.c_uint32), len(lists),
           _p(out_ids, C.c_uint64), _p(out_sc, C.c_float))
     return out_ids[:m].copy(), out_sc[:m].copy()
+
+
+# ---------------------------------------------------------------------------------------------
+# Vamana graph index (vamana_oracle.c): reference src/vector_db/vamana.rs
+# ---------------------------------------------------------------------------------------------
+class VamanaOracle:
+    """VamanaIndex restated on the CPU: build / add_vector / search (ANN arm) / mark_deleted.
+
+    Graph = deg [n] u32 + nbr [n, stride] u32 (stride = max_degree + 1), medoid.  Defaults are
+    VamanaConfig::default (vamana.rs:80-91): R = 32, L = 75, alpha = 1.2, NormalizedDotProduct."""
+
+    def __init__(self, dim, max_degree=32, search_list_size=75, alpha=1.2, metric=METRIC_NEG_DOT,
+                 variant=VARIANT_SCALAR):
+        self.dim, self.R, self.L, self.alpha = dim, max_degree, search_list_size, alpha
+        self.metric, self.variant = metric, variant
+        self.stride = max_degree + 1
+        self.vectors = np.zeros((0, dim), np.float32)
+        self.deg = np.zeros(0, np.uint32)
+        self.nbr = np.zeros((0, self.stride), np.uint32)
+        self.medoid = 0
+        self.deleted = set()
+
+    def __len__(self):
+        return self.vectors.shape[0]
+
+    def build(self, vectors, seed=0, init_graph=None):
+        """VamanaIndex::build (vamana.rs:200-284); init_graph = (deg, nbr) overrides the seeded random start."""
+        self.vectors = _f32(vectors).copy()
+        n = len(self)
+        self.deg = np.zeros(n, np.uint32)
+        self.nbr = np.zeros((n, self.stride), np.uint32)
+        if n == 0:
+            return 0
+        if init_graph is None:
+            lib().so_vamana_init_graph(n, self.R, self.stride, seed, _p(self.deg, C.c_uint32), _p(self.nbr, C.c_uint32))
+        else:
+            d0, n0 = init_graph
+            self.deg[:] = d0
+            self.nbr[:, :n0.shape[1]] = n0
+        self.medoid = int(lib().so_find_medoid(_p(self.vectors, C.c_float), n, self.dim, self.metric, self.variant))
+        return int(lib().so_vamana_build(_p(self.vectors, C.c_float), n, self.dim, self.R, self.L, self.alpha,
+                                         self.metric, self.variant, self.medoid, self.stride,
+                                         _p(self.deg, C.c_uint32), _p(self.nbr, C.c_uint32)))
+
+    def set_graph(self, vectors, deg, nbr, medoid):
+        self.vectors = _f32(vectors).copy()
+        n = len(self)
+        self.deg = np.ascontiguousarray(deg, np.uint32).copy()
+        self.nbr = np.zeros((n, self.stride), np.uint32)
+        nbr = np.asarray(nbr, np.uint32)
+        self.nbr[:, :nbr.shape[1]] = nbr[:, :self.stride]
+        self.medoid = int(medoid)
+
+    def add_vector(self, vector):
+        """VamanaIndex::add_vector (vamana.rs:853-973) -> the new id."""
+        n = len(self)
+        self.vectors = np.ascontiguousarray(np.vstack([self.vectors, _f32(vector)[None, :]]))
+        self.deg = np.concatenate([self.deg, np.zeros(1, np.uint32)])
+        self.nbr = np.ascontiguousarray(np.vstack([self.nbr, np.zeros((1, self.stride), np.uint32)]))
+        if n == 0:
+            self.medoid = 0
+        lib().so_vamana_add_vector(_p(self.vectors, C.c_float), n, self.dim, self.R, self.metric, self.variant,
+                                   self.medoid, self.stride, _p(self.deg, C.c_uint32), _p(self.nbr, C.c_uint32))
+        return n
+
+    def mark_deleted(self, vid):
+        self.deleted.add(int(vid))
+
+    def greedy_search(self, query, k, entry=None, stats=False):
+        query = _f32(query)
+        ids = np.zeros(max(k, 1), np.uint32)
+        dist = np.zeros(max(k, 1), np.float32)
+        st = np.zeros(2, np.uint64)
+        n = len(self)
+        r = lib().so_greedy_search(_p(self.vectors, C.c_float), n, self.dim, _p(self.deg, C.c_uint32),
+                                   _p(self.nbr, C.c_uint32), self.stride, n, _p(query, C.c_float), k,
+                                   self.medoid if entry is None else entry, self.metric, self.variant,
+                                   _p(ids, C.c_uint32), _p(dist, C.c_float), _p(st, C.c_uint64))
+        return (ids[:r].copy(), dist[:r].copy(), st) if stats else (ids[:r].copy(), dist[:r].copy())
+
+    def search(self, query, k, stats=False):
+        """VamanaIndex::search, ANN arm (vamana.rs:779-807) -> (ids, dist)."""
+        query = _f32(query)
+        ids = np.zeros(max(k, 1), np.uint32)
+        dist = np.zeros(max(k, 1), np.float32)
+        st = np.zeros(2, np.uint64)
+        n = len(self)
+        bm = deleted_bitmap(n, self.deleted) if self.deleted else None
+        r = lib().so_vamana_search(_p(self.vectors, C.c_float), n, self.dim, _p(self.deg, C.c_uint32),
+                                   _p(self.nbr, C.c_uint32), self.stride, self.medoid,
+                                   None if bm is None else _p(bm, C.c_uint32), len(self.deleted),
+                                   _p(query, C.c_float), k, self.metric, self.variant, _p(ids, C.c_uint32),
+                                   _p(dist, C.c_float), _p(st, C.c_uint64))
+        return (ids[:r].copy(), dist[:r].copy(), st) if stats else (ids[:r].copy(), dist[:r].copy())
+
+    def robust_prune(self, node_id, cand_ids, cand_dist):
+        cand_ids = np.ascontiguousarray(cand_ids, np.uint32)
+        cand_dist = _f32(cand_dist)
+        out = np.zeros(self.R + 1, np.uint32)
+        m = lib().so_robust_prune(_p(self.vectors, C.c_float), self.dim, node_id, _p(cand_ids, C.c_uint32),
+                                  _p(cand_dist, C.c_float), cand_ids.size, self.R, self.alpha, self.metric,
+                                  self.variant, _p(out, C.c_uint32))
+        return out[:m].copy()
+
+
+def find_medoid(corpus, metric=METRIC_NEG_DOT, variant=VARIANT_SCALAR) -> int:
+    corpus = _f32(corpus)
+    return int(lib().so_find_medoid(_p(corpus, C.c_float), corpus.shape[0], corpus.shape[1], metric, variant))
+
+
+def recall_at_k(ann_ids, ann_counts, exact_ids, exact_counts) -> float:
+    a = np.ascontiguousarray(ann_ids, np.uint32)
+    e = np.ascontiguousarray(exact_ids, np.uint32)
+    assert a.shape == e.shape
+    ac = np.ascontiguousarray(ann_counts, np.uint32)
+    ec = np.ascontiguousarray(exact_counts, np.uint32)
+    return float(lib().so_recall_at_k(_p(a, C.c_uint32), _p(ac, C.c_uint32), _p(e, C.c_uint32), _p(ec, C.c_uint32),
+                                      a.shape[0], a.shape[1]))
+
+
+def clustered_corpus(seed, n, dim, n_clusters=None, spread=0.35):
+    """Unit vectors around random centres (ANN needs structure; i.i.d. unit vectors in 384-d have none)."""
+    rng = np.random.default_rng(seed)
+    c = n_clusters or max(4, int(round(n ** 0.5 / 2)))
+    centres = rng.standard_normal((c, dim)).astype(np.float32)
+    centres /= np.linalg.norm(centres, axis=1, keepdims=True)
+    which = rng.integers(0, c, n)
+    x = centres[which] + (spread / np.sqrt(dim)) * rng.standard_normal((n, dim)).astype(np.float32) * np.sqrt(dim) / np.sqrt(dim)
+    x = x.astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    return np.ascontiguousarray(x, np.float32)
