@@ -102,13 +102,15 @@ SG_API int sg_store_clear_deleted(sg_store *s);
 SG_API int sg_store_len(const sg_store *s, uint64_t *n_out);
 SG_API int sg_store_deleted_count(const sg_store *s, uint64_t *n_out);
 SG_API int sg_store_dim(const sg_store *s, uint32_t *dim_out);
+SG_API int sg_store_metric(const sg_store *s, int *metric_out);
 
 /* VamanaIndex::get_vector / extract_all_vectors: rows [first, first+n) upcast to f32. */
 SG_API int sg_store_get_vectors(sg_store *s, uint64_t first, uint64_t n, float *rows_f32_out);
 
 /* VamanaIndex::load_from_file (src/vector_db/vamana_persist.rs:290-400): read the reference's persisted
  * "VAMA" v1 index file into an EMPTY store -- vectors section (dense f32 rows) uploaded as-is, deleted ids
- * applied, graph section skipped (the GPU store scans exactly).  The store's dim must equal the file's.
+ * applied, graph section + medoid uploaded (sg_store_set_graph) so sg_store_search_ann walks the graph the
+ * reference built; the exact sweep ignores it.  The store's dim and metric must equal the file's.
  * verify_checksum != 0 checks the FNV-1a-64 checksum like the reference does (:303-312). */
 SG_API int sg_store_load_vama(sg_store *s, const char *path, int verify_checksum);
 /* header / layout of a VAMA file without touching a GPU (host-side parser only) */
@@ -187,6 +189,47 @@ SG_API int sg_exchange_merge_topk_device(int device, const uint64_t *peer_buffer
                                          uint32_t epoch, const uint32_t *d_ids, const float *d_dist, uint32_t b,
                                          uint32_t k, uint32_t *d_ids_out, float *d_dist_out, uint32_t *d_counts_out,
                                          void *cuda_stream);
+
+/* ---- Vamana graph index: the reference's DEFAULT search arm -------------------------
+ * src/vector_db/vamana.rs: build :200-284, search :779-807 -> greedy_search :576-657, add_vector :853-973.
+ * The exact sweep above needs no graph; these entry points exist so that an index the reference built (or
+ * its VAMA file, sg_store_load_vama) is searched the way the reference searches it, and so that corpora
+ * beyond the exact sweep's reach (>= 10^8 rows per GPU) keep a sub-millisecond path.
+ *
+ * sg_store_search_ann: VamanaIndex::search without SHODH_VECTOR_EXACT: beam search from the medoid with
+ * beam k (+ min(deleted, 2k) when rows are soft-deleted, :785-796), deleted ids dropped, k results
+ * (id, distance) ascending.  GIVEN THE SAME GRAPH THE RESULT IS THE REFERENCE'S, id for id and bit for bit:
+ * SearchCandidate's order (distance total_cmp, id) is total, so the heaps' pops are determined, and every
+ * distance is evaluated in the reference's summation order.  SG_ERR_NOT_BUILT when rows exist but no graph
+ * ("Vamana graph not built", :780-784).  stats_out (may be NULL) [b,2]: nodes expanded, distance
+ * evaluations per query.  Limits: k <= 1024, beam <= 2048, max_degree <= 64.
+ *
+ * sg_store_build_graph: VamanaIndex::build over the rows already in the store: random start graph, medoid
+ * (centroid summed in row order, arg-min by the exact sweep -- the reference's medoid exactly), two passes of
+ * beam search (search_list_size) + robust_prune (alpha-RNG rule with the +1 offset for NormalizedDotProduct,
+ * :711-727) + back-edges.  Nodes are processed in batches, not one by one, so the graph differs from a
+ * sequential build edge for edge (the reference's own start graph is random per run); the contract is
+ * recall against the exact sweep (tests/test_vamana_gpu.py).  Defaults of VamanaConfig: 32, 75, 1.2.
+ *
+ * sg_store_set_graph / sg_store_get_graph: upload / download the adjacency (deg [n], nbr [n,stride]).
+ * sg_store_enable_graph: an EMPTY store grows its graph incrementally from the first sg_store_append on,
+ * one VamanaIndex::add_vector per row (beam max_degree, neighbours as found, back-edges kept to the
+ * max_degree closest by (distance, id), :905-966) -- edge for edge the reference's sequence.  Once a store
+ * has a graph (built, set, loaded or enabled), every later append links its rows the same way. */
+SG_API int sg_store_enable_graph(sg_store *s, uint32_t max_degree, uint32_t search_list_size, float alpha);
+SG_API int sg_store_build_graph(sg_store *s, uint32_t max_degree, uint32_t search_list_size, float alpha, uint64_t seed);
+SG_API int sg_store_set_graph(sg_store *s, uint32_t max_degree, uint32_t medoid, const uint32_t *deg, const uint32_t *nbr,
+                              uint32_t stride, uint64_t n_nodes);
+SG_API int sg_store_get_graph(sg_store *s, uint32_t *deg_out, uint32_t *nbr_out /* [n_nodes, max_degree] */,
+                              uint64_t n_nodes);
+SG_API int sg_store_graph_info(sg_store *s, uint32_t *max_degree_out, uint32_t *medoid_out, uint64_t *graph_len_out);
+SG_API int sg_store_search_ann(sg_store *s, const float *queries_f32, uint32_t b, uint32_t k, uint32_t *ids_out,
+                               float *dist_out, uint32_t *counts_out, uint64_t *stats_out);
+/* device pointers, asynchronous on cuda_stream; d_flags (may be NULL) [b]: bit 0 = the query's visited table
+ * filled up and its result is incomplete (the host-buffer form re-runs such queries with a larger table) */
+SG_API int sg_store_search_ann_device(sg_store *s, const float *d_queries_f32, uint32_t b, uint32_t k, uint32_t *d_ids_out,
+                                      float *d_dist_out, uint32_t *d_counts_out, uint32_t *d_flags, void *cuda_stream);
+SG_API int sg_store_ann_stats(sg_store *s, uint64_t *queries_out, uint64_t *retries_out);
 
 /* CUDA-event timing of the scan kernel(s) inside each search (bench.py roofline): with
  * profiling on, every search records an event pair around its sweep launches on the stream

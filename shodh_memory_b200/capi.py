@@ -102,6 +102,15 @@ def lib() -> C.CDLL:
     L.sg_exchange_merge_topk_device.argtypes = [C.c_int, u64p, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32,
                                                 C.c_uint32, vp, vp, vp, vp]
     L.sg_store_tc_stats.argtypes = [vp, u64p, u64p]
+    L.sg_store_metric.argtypes = [vp, C.POINTER(C.c_int)]
+    L.sg_store_enable_graph.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_float]
+    L.sg_store_build_graph.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_float, C.c_uint64]
+    L.sg_store_set_graph.argtypes = [vp, C.c_uint32, C.c_uint32, u32p, u32p, C.c_uint32, C.c_uint64]
+    L.sg_store_get_graph.argtypes = [vp, u32p, u32p, C.c_uint64]
+    L.sg_store_graph_info.argtypes = [vp, u32p, u32p, u64p]
+    L.sg_store_search_ann.argtypes = [vp, f32p, C.c_uint32, C.c_uint32, u32p, f32p, u32p, u64p]
+    L.sg_store_search_ann_device.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp]
+    L.sg_store_ann_stats.argtypes = [vp, u64p, u64p]
     L.sg_store_profile_read.argtypes = [vp, f32p, C.c_uint32, u32p, u32p]
     i64p = C.POINTER(C.c_int64)
     L.sg_encoder_create.argtypes = [C.POINTER(vp), C.c_int, C.c_char_p]

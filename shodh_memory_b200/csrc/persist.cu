@@ -7,8 +7,10 @@
 // the graph (per node: neighbour_count u16 + [u32; count]), then -- aligned to 64 bytes -- the
 // vectors, row-major [[f32; dimension]; num_vectors].  checksum = FNV-1a-64 over every byte after
 // the header (:155-163, :269, :303-312).  The vectors section is exactly the dense f32 matrix
-// sg_store_append takes; the graph is skipped (the GPU store scans exactly, it needs no graph).
-// This is host-side file plumbing; no arithmetic of the hot path happens here.
+// sg_store_append takes; the graph section (with the header's medoid and max_degree) is uploaded with
+// sg_store_set_graph so the index is searchable by sg_store_search_ann exactly as the reference
+// would search it (the exact sweep needs no graph).  This is host-side file plumbing; no arithmetic
+// of the hot path happens here.
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -28,7 +30,8 @@ uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
 uint64_t rd64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
 
 // parses header + walks the graph section to find the vectors; optionally verifies the checksum
-int vama_parse(FILE *f, VamaInfo &vi, std::vector<uint32_t> *deleted, int verify, int *checksum_ok)
+int vama_parse(FILE *f, VamaInfo &vi, std::vector<uint32_t> *deleted, int verify, int *checksum_ok,
+               std::vector<uint32_t> *deg_out = nullptr, std::vector<uint32_t> *nbr_out = nullptr)
 {
     uint8_t h[64];
     if (fseek(f, 0, SEEK_END) != 0) return SG_ERR_INVALID;
@@ -59,6 +62,14 @@ int vama_parse(FILE *f, VamaInfo &vi, std::vector<uint32_t> *deleted, int verify
         deleted->resize(vi.deleted_count);
         if (vi.deleted_count && fread(deleted->data(), 4, vi.deleted_count, f) != vi.deleted_count) return SG_ERR_INVALID;
     }
+    if (deg_out) deg_out->assign(vi.num_vectors, 0);
+    if (nbr_out) {
+        if (vi.max_degree == 0 || vi.max_degree > 64) {
+            sg::set_error("VAMA graph: max_degree %u outside 1..64", vi.max_degree);
+            return SG_ERR_UNSUPPORTED;
+        }
+        nbr_out->assign(vi.num_vectors * (size_t)vi.max_degree, 0xFFFFFFFFu);
+    }
     // graph: variable-length records; buffered walk
     fseek(f, (long)off, SEEK_SET);
     std::vector<uint8_t> buf(1 << 20);
@@ -82,13 +93,21 @@ int vama_parse(FILE *f, VamaInfo &vi, std::vector<uint32_t> *deleted, int verify
         memcpy(&cnt, buf.data() + pos, 2);
         pos += 2;
         file_pos += 2;
-        size_t skip = (size_t)cnt * 4;
+        if (nbr_out && cnt > vi.max_degree) {
+            sg::set_error("VAMA graph: node %llu lists %u neighbours, max_degree is %u", (unsigned long long)node, cnt,
+                          vi.max_degree);
+            return SG_ERR_INVALID;
+        }
+        if (deg_out) (*deg_out)[node] = cnt;
+        size_t skip = (size_t)cnt * 4, copied = 0;
         while (skip) {
             if (!need(1)) {
                 sg::set_error("VAMA file truncated in the graph section (node %llu)", (unsigned long long)node);
                 return SG_ERR_INVALID;
             }
             size_t take = have - pos < skip ? have - pos : skip;
+            if (nbr_out) memcpy(reinterpret_cast<uint8_t *>(nbr_out->data() + node * vi.max_degree) + copied, buf.data() + pos, take);
+            copied += take;
             pos += take;
             file_pos += take;
             skip -= take;
@@ -163,8 +182,8 @@ int sg_store_load_vama(sg_store *s, const char *path, int verify_checksum)
         return SG_ERR_INVALID;
     }
     VamaInfo vi;
-    std::vector<uint32_t> deleted;
-    rc = vama_parse(f, vi, &deleted, verify_checksum, nullptr);
+    std::vector<uint32_t> deleted, deg, nbr;
+    rc = vama_parse(f, vi, &deleted, verify_checksum, nullptr, &deg, &nbr);
     if (rc != SG_OK) {
         fclose(f);
         return rc;
@@ -176,10 +195,12 @@ int sg_store_load_vama(sg_store *s, const char *path, int verify_checksum)
         sg::set_error("dimension mismatch: the file holds %u-d vectors, the store is %u-d", vi.dimension, store_dim);
         return SG_ERR_DIM;
     }
-    if (vi.metric != 0) {
+    int store_metric = 0;
+    sg_store_metric(s, &store_metric);
+    if ((int)vi.metric != store_metric) {      // DistanceMetric as u8: 0 NormalizedDotProduct, 1 Euclidean, 2 Cosine
         fclose(f);
-        sg::set_error("VAMA file uses distance metric %u; only NormalizedDotProduct (0) is supported", vi.metric);
-        return SG_ERR_UNSUPPORTED;
+        sg::set_error("VAMA file uses distance metric %u, the store was created with metric %d", vi.metric, store_metric);
+        return SG_ERR_INVALID;
     }
     // upload the vectors section in 32 MB pieces through the normal append path (rounds to the store dtype)
     rc = sg_store_reserve(s, vi.num_vectors);
@@ -209,7 +230,12 @@ int sg_store_load_vama(sg_store *s, const char *path, int verify_checksum)
         rc = sg_store_mark_deleted(s, id, &ok);
         if (rc != SG_OK) return rc;
     }
-    return SG_OK;
+    // the graph as the reference built it: searched as-is by sg_store_search_ann
+    bool any_edge = false;
+    for (uint32_t d : deg) any_edge |= d != 0;
+    if (vi.num_vectors && (any_edge || vi.num_vectors == 1))
+        rc = sg_store_set_graph(s, vi.max_degree, vi.medoid, deg.data(), nbr.data(), vi.max_degree, vi.num_vectors);
+    return rc;
 }
 
 }  // extern "C"

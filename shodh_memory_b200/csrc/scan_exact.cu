@@ -26,6 +26,7 @@
 //     at the end; one sorted list of k keys per (query, CTA) goes to HBM.
 // Algorithmic bytes per sweep = n_rows * dim * sizeof(elem)  (SURVEY.md 8d).
 #include "sg_internal.h"
+#include "sg_dist.cuh"
 
 namespace sg {
 
@@ -40,84 +41,6 @@ struct WarpTopK {
     uint32_t tau[QB];
 };
 
-
-// ---- per-metric accumulation of 4 consecutive elements (query q, row x) -------------------------
-// METRIC 0 (NormalizedDotProduct), 2 (Cosine) and 3 (similarity.rs cosine) accumulate q*x in the
-// order of dot_product_{scalar,avx2}_inline (distance_inline.rs:157-173 / :67-111); METRIC 1
-// (Euclidean) accumulates (q-x)^2 in the order of euclidean_squared_{scalar,avx2}_inline
-// (:284-305 / :218-252).  `o` selects the AVX lane group (element e -> lane e % 8).
-template <int ORDER, int METRIC>
-SG_DEVICE_INLINE void accum4(float *acc, const float4 q, float x0, float x1, float x2, float x3, int o)
-{
-    if constexpr (METRIC == SG_METRIC_EUCLIDEAN) {
-        const float d0 = __fsub_rn(q.x, x0), d1 = __fsub_rn(q.y, x1), d2 = __fsub_rn(q.z, x2), d3 = __fsub_rn(q.w, x3);
-        if constexpr (ORDER == SG_ORDER_SCALAR) {
-            const float g = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)),
-                                      __fmul_rn(d3, d3));
-            acc[0] = __fadd_rn(acc[0], g);
-        } else {
-            acc[o + 0] = __fmaf_rn(d0, d0, acc[o + 0]);
-            acc[o + 1] = __fmaf_rn(d1, d1, acc[o + 1]);
-            acc[o + 2] = __fmaf_rn(d2, d2, acc[o + 2]);
-            acc[o + 3] = __fmaf_rn(d3, d3, acc[o + 3]);
-        }
-    } else {
-        if constexpr (ORDER == SG_ORDER_SCALAR) {
-            // sum = sum + (((p0+p1)+p2)+p3), every product rounded (no FMA)
-            const float g = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(q.x, x0), __fmul_rn(q.y, x1)), __fmul_rn(q.z, x2)),
-                                      __fmul_rn(q.w, x3));
-            acc[0] = __fadd_rn(acc[0], g);
-        } else {
-            // 8 AVX lanes, fused multiply-add
-            acc[o + 0] = __fmaf_rn(q.x, x0, acc[o + 0]);
-            acc[o + 1] = __fmaf_rn(q.y, x1, acc[o + 1]);
-            acc[o + 2] = __fmaf_rn(q.z, x2, acc[o + 2]);
-            acc[o + 3] = __fmaf_rn(q.w, x3, acc[o + 3]);
-        }
-    }
-}
-// lanes summed left to right (distance_inline.rs:95-103); the scalar build has one accumulator
-template <int ORDER>
-SG_DEVICE_INLINE float hsum(const float *acc)
-{
-    if constexpr (ORDER == SG_ORDER_SCALAR) {
-        return acc[0];
-    } else {
-        float r = __fadd_rn(acc[0], acc[1]);
-#pragma unroll
-        for (int t = 2; t < 8; ++t) r = __fadd_rn(r, acc[t]);
-        return r;
-    }
-}
-SG_DEVICE_INLINE float canon_nan(float x) { return (x != x) ? __uint_as_float(0x7FC00000u) : x; }
-
-// accumulated sums -> the distance the ranking uses.  qn2 / rn2 = |query|^2 / |row|^2 in the same order.
-template <int METRIC>
-SG_DEVICE_INLINE float finish_distance(float s, float qn2, float rn2)
-{
-    if constexpr (METRIC == SG_METRIC_NEG_DOT) {
-        return neg_dot_to_dist(s);
-    } else if constexpr (METRIC == SG_METRIC_EUCLIDEAN) {
-        return canon_nan(s);
-    } else if constexpr (METRIC == SG_METRIC_COSINE) {
-        // 1 - cosine_similarity_inline (distance_inline.rs:444-458): dot / sqrt(|a|^2 |b|^2), `< 1e-10 -> 0`
-        const float den = __fsqrt_rn(__fmul_rn(qn2, rn2));
-        const float c = (den < 1e-10f) ? 0.0f : __fdiv_rn(s, den);
-        return canon_nan(__fsub_rn(1.0f, c));
-    } else {
-        // -cosine_similarity (similarity.rs:10-24): 0 on a zero norm, clamp to [-1,1] (NaN stays NaN).
-        // OrderedFloat order for top_k_similar (:27-48): NaN greatest, -0 == +0, ties keep input order.
-        const float na = __fsqrt_rn(qn2), nb = __fsqrt_rn(rn2);
-        float c = 0.0f;
-        if (!(na == 0.0f || nb == 0.0f)) {
-            c = __fdiv_rn(s, __fmul_rn(na, nb));
-            if (c < -1.0f) c = -1.0f;
-            if (c > 1.0f) c = 1.0f;
-        }
-        c = (c != c) ? __uint_as_float(0x7FC00000u) : __fadd_rn(c, 0.0f);   // one NaN, no -0
-        return -c;                                                            // -NaN sorts first in totalOrder
-    }
-}
 
 // sort the warp's candidate buffer, keep the best k, refresh the threshold
 SG_DEVICE_INLINE void compact(uint64_t *buf, uint32_t &cnt, uint32_t &tau, uint32_t k, uint32_t lane)
@@ -191,18 +114,7 @@ scan_exact_kernel(const __grid_constant__ CUtensorMap tmap, const ScanArgs a)
     __syncthreads();
     if constexpr (METRIC == SG_METRIC_COSINE || METRIC == SG_METRIC_COSINE_SIM) {
         // |query|^2 once per sweep, in the reference's order (l2_norm_squared_*_inline :366-431 == dot(a,a))
-        if (threadIdx.x < (uint32_t)QB) {
-            constexpr int NA = (ORDER == SG_ORDER_AVX2) ? 8 : 1;
-            float nacc[NA];
-#pragma unroll
-            for (int t = 0; t < NA; ++t) nacc[t] = 0.0f;
-            const float *qq = q_s + (size_t)threadIdx.x * dim;
-            for (uint32_t d = 0; d < dim; d += 4) {
-                const float4 v4 = *reinterpret_cast<const float4 *>(qq + d);
-                accum4<ORDER, SG_METRIC_NEG_DOT>(nacc, v4, v4.x, v4.y, v4.z, v4.w, (int)(d & 4));
-            }
-            qn_s[threadIdx.x] = hsum<ORDER>(nacc);
-        }
+        if (threadIdx.x < (uint32_t)QB) qn_s[threadIdx.x] = norm2_smem<ORDER>(q_s + (size_t)threadIdx.x * dim, dim);
         __syncthreads();
     }
     // producer state (lane 0 only uses it, but keep it warp-uniform)

@@ -110,6 +110,51 @@ cudaError_t launch_search_ids_post(const uint32_t *d_ids, const float *d_dist, c
                                    const uint64_t *d_vec2mem, uint64_t n_map, uint32_t id_base, uint32_t limit,
                                    uint64_t *d_mem_out, float *d_sim_out, uint32_t *d_cnt_out, cudaStream_t st);
 
+// ---- vamana.cu (graph index: beam search, incremental linking, medoid, bulk build) ----
+struct AnnArgs {
+    const void *rows;            // the store's row matrix
+    uint32_t dim;
+    uint64_t n_rows;             // rows in storage (ids >= n_rows in a list are ignored)
+    const uint32_t *graph;       // [graph_len][gs] neighbour ids, 0xFFFFFFFF-padded
+    uint32_t gs;                 // list stride = max_degree
+    uint64_t graph_len;          // graph.len(): nodes beyond it have no list yet (vamana.rs:606-609)
+    uint32_t entry;              // medoid
+    const float *queries;        // [nq][dim] f32, or null when query_rows is set
+    const uint32_t *query_rows;  // query q = store row query_rows[q] (build / add_vector)
+    uint32_t nq;
+    uint32_t K;                  // beam width = the k greedy_search is called with
+    uint32_t k_out;              // results written per query (after dropping deleted ids)
+    const uint32_t *deleted;     // soft-delete bitmap or null
+    uint32_t id_base;
+    uint32_t *vis;               // [nq][H] visited hash tables, 0xFFFFFFFF-filled
+    uint32_t H;                  // power of two
+    uint32_t *ids_out; float *dist_out; uint32_t *counts_out;   // [nq][k_out], [nq][k_out], [nq]
+    uint32_t *flags;             // [nq] or null: bit 0 = visited table filled up (result incomplete), bit 1 = > 32 ties dropped
+    unsigned long long *stats;   // [nq][2] or null: nodes expanded, distance evaluations
+};
+// shared memory per query warp: query f32 + the sorted list (K + 32 keys) + expanded flags
+__host__ __device__ inline size_t ann_warp_smem_bytes(uint32_t dim, uint32_t K)
+{
+    const size_t cap = (size_t)K + 32;
+    return (((size_t)dim * 4 + 15) & ~(size_t)15) + cap * 8 + ((cap + 15) & ~(size_t)15);
+}
+cudaError_t launch_ann_search(const AnnArgs &a, bool f16, int order, int metric, cudaStream_t st);
+cudaError_t launch_graph_link(const void *rows, bool f16, int order, int metric, uint32_t dim, uint32_t *graph, uint32_t gs,
+                              uint32_t id, const uint32_t *res_ids, const uint32_t *res_count, cudaStream_t st);
+cudaError_t launch_centroid(const void *rows, bool f16, uint32_t dim, uint64_t n, float *d_centroid, cudaStream_t st);
+cudaError_t launch_graph_init(uint32_t *graph, uint32_t gs, uint64_t n, uint64_t seed, cudaStream_t st);
+cudaError_t launch_iota(uint32_t *out, uint32_t first, uint32_t n, cudaStream_t st);
+cudaError_t launch_graph_degree(const uint32_t *graph, uint32_t gs, uint64_t n, uint32_t *deg, cudaStream_t st);
+cudaError_t launch_build_prune(const void *rows, bool f16, uint32_t dim, int metric, float alpha, const uint32_t *graph,
+                               uint32_t gs, const uint32_t *node_ids, uint32_t n_nodes, const uint32_t *res_ids,
+                               const uint32_t *res_counts, uint32_t L, uint32_t *new_lists, cudaStream_t st);
+cudaError_t launch_build_apply(uint32_t *graph, uint32_t gs, const uint32_t *node_ids, uint32_t n_nodes,
+                               const uint32_t *new_lists, uint32_t *inbox, uint32_t *inbox_cnt, uint32_t ecap,
+                               uint32_t *touched, uint32_t *n_touched, cudaStream_t st);
+cudaError_t launch_build_backedges(const void *rows, bool f16, uint32_t dim, int metric, float alpha, uint32_t *graph,
+                                   uint32_t gs, const uint32_t *touched, const uint32_t *n_touched, const uint32_t *inbox,
+                                   uint32_t *inbox_cnt, uint32_t ecap, uint32_t grid, cudaStream_t st);
+
 // ---- tensor map (store.cu) ----
 int encode_corpus_tmap(CUtensorMap *out, const void *d_rows, bool f16, uint32_t dim, uint64_t n_rows,
                        uint32_t box_rows);

@@ -1,0 +1,109 @@
+// sg_store_internal.h -- the store object and the host helpers shared by store.cu and graph_api.cu.
+#pragma once
+#include <mutex>
+#include <vector>
+
+#include "sg_internal.h"
+
+using namespace sg;
+
+// ---------------------------------------------------------------------------------------
+// the store
+// ---------------------------------------------------------------------------------------
+struct sg_store {
+    int device = 0;
+    int sm_count = 148;
+    uint32_t dim = 0;
+    int dtype = SG_DTYPE_F16;
+    int metric = SG_METRIC_NEG_DOT;
+    int order = SG_ORDER_SCALAR;
+    uint32_t id_base = 0;
+    uint32_t esize = 2;
+
+    void *d_rows = nullptr;
+    uint64_t n = 0, cap = 0;
+    uint32_t *d_deleted = nullptr;       // bitmap, cap/32 (+pad) words
+    std::vector<uint32_t> h_deleted;     // host mirror
+    uint64_t n_deleted = 0;
+
+    cudaStream_t stream = nullptr;
+    mutable std::mutex mu;
+
+    // scratch
+    float *d_queries = nullptr;  size_t q_cap = 0;      // floats
+    uint64_t *d_lists = nullptr; size_t lists_cap = 0;  // keys
+    uint64_t *d_lists2 = nullptr; size_t lists2_cap = 0; // first-level merge output
+    uint32_t *d_ids = nullptr; float *d_dist = nullptr; uint32_t *d_counts = nullptr; size_t res_cap = 0, cnt_cap = 0;
+    void *h_pinned = nullptr; size_t pinned_cap = 0;
+    float *d_stage = nullptr; size_t stage_cap = 0;     // floats, append staging
+
+    // tensor-core path scratch
+    float *d_max_norm = nullptr;                           // device scalar: bound on |row|_2 over the store
+    __half *d_qh = nullptr; size_t qh_cap = 0;             // fp16 queries, 128-row padded
+    float *d_qerr = nullptr; size_t qmeta_cap = 0;         // [b_pad] |q - fp16(q)|
+    float *d_qnorm = nullptr;                              // [b_pad]
+    float *d_maxima = nullptr; size_t maxima_cap = 0;      // [b_pad][grid] pre-pass maxima
+    uint32_t *d_gtau = nullptr, *d_flags = nullptr, *d_nflag = nullptr, *d_flag_list = nullptr;
+    unsigned long long *d_flag_total = nullptr;            // cumulative count of uncertified queries
+    uint64_t *d_cand = nullptr; size_t cand_cap_q = 0;     // [b_pad][grid][kk] per-CTA candidate lists
+    uint64_t tc_searches = 0, tc_flagged = 0;              // statistics (sg_store_tc_stats)
+
+    // vector id -> MemoryId table (IdMapping of RetrievalEngine, retrieval.rs:64-140) + search_ids scratch
+    uint64_t *d_vec2mem = nullptr; uint64_t n_map = 0; size_t map_cap = 0;
+    uint64_t *d_mem_out = nullptr; float *d_sim_out = nullptr; uint32_t *d_memcnt = nullptr; size_t post_cap = 0, postc_cap = 0;
+
+    // Vamana graph (vamana.cu / graph_api.cu): adjacency [cap][gs] u32, 0xFFFFFFFF-padded; graph_len nodes have lists
+    uint32_t *d_graph = nullptr; uint64_t graph_cap = 0;   // rows allocated
+    uint32_t gs = 0;                                       // max_degree R (list stride), 0 = no graph
+    uint64_t graph_len = 0;
+    uint32_t medoid = 0;
+    uint32_t search_list_size = 75; float alpha = 1.2f;    // VamanaConfig::default (vamana.rs:80-91)
+    uint32_t *d_vis = nullptr; size_t vis_cap = 0;         // visited hash tables of the batch in flight
+    uint32_t *d_ann_flags = nullptr; size_t ann_flags_cap = 0;
+    uint64_t *d_ann_stats = nullptr; size_t ann_stats_cap = 0;
+    uint32_t *d_g32 = nullptr; size_t g32_cap = 0;         // build / insert scratch (u32)
+    float *d_gf32 = nullptr; size_t gf32_cap = 0;          // build / insert scratch (f32)
+    uint64_t ann_searches = 0, ann_retries = 0;
+
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev;  // pairs: ev[2i] before, ev[2i+1] after the sweep launches of search i
+    uint32_t ev_count = 0;        // searches recorded since the last read/reset
+    uint32_t last_scan_launches = 0;
+};
+
+
+namespace sg {
+
+int check_device(int device, int *sm_count);
+int grow_pinned(sg_store *s, size_t bytes);
+int ensure_rows(sg_store *s, uint64_t need_rows);
+// exact path A; all pointers are device pointers; asynchronous on st.  use_deleted = false scores every row.
+int search_exact_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint32_t *d_ids, float *d_dist,
+                        uint32_t *d_counts, cudaStream_t st, bool record, bool use_deleted = true);
+// graph_api.cu: link rows [first, first+n) into the graph one by one (VamanaIndex::add_vector); no-op without a graph
+int graph_append_locked(sg_store *s, uint64_t first, uint64_t n);
+void graph_free(sg_store *s);
+
+template <typename T>
+int grow(T *&ptr, size_t &cap, size_t need, bool keep = false, cudaStream_t st = nullptr)
+{
+    if (need <= cap) return SG_OK;
+    size_t ncap = need + need / 2;
+    T *np = nullptr;
+    SG_CUDA_TRY(cudaMalloc(&np, ncap * sizeof(T)));
+    if (keep && ptr && cap) {
+        cudaError_t e = cudaMemcpyAsync(np, ptr, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            cudaFree(np);
+            set_error("device copy during growth failed: %s", cudaGetErrorString(e));
+            return SG_ERR_CUDA;
+        }
+    }
+    if (ptr) cudaFree(ptr);
+    ptr = np;
+    cap = ncap;
+    return SG_OK;
+}
+
+}  // namespace sg

@@ -14,7 +14,7 @@
 #include <mutex>
 #include <vector>
 
-#include "sg_internal.h"
+#include "sg_store_internal.h"
 
 namespace sg {
 
@@ -90,58 +90,7 @@ static int env_u32(const char *name, int dflt)
 
 using namespace sg;
 
-// ---------------------------------------------------------------------------------------
-// the store
-// ---------------------------------------------------------------------------------------
-struct sg_store {
-    int device = 0;
-    int sm_count = 148;
-    uint32_t dim = 0;
-    int dtype = SG_DTYPE_F16;
-    int metric = SG_METRIC_NEG_DOT;
-    int order = SG_ORDER_SCALAR;
-    uint32_t id_base = 0;
-    uint32_t esize = 2;
-
-    void *d_rows = nullptr;
-    uint64_t n = 0, cap = 0;
-    uint32_t *d_deleted = nullptr;       // bitmap, cap/32 (+pad) words
-    std::vector<uint32_t> h_deleted;     // host mirror
-    uint64_t n_deleted = 0;
-
-    cudaStream_t stream = nullptr;
-    mutable std::mutex mu;
-
-    // scratch
-    float *d_queries = nullptr;  size_t q_cap = 0;      // floats
-    uint64_t *d_lists = nullptr; size_t lists_cap = 0;  // keys
-    uint64_t *d_lists2 = nullptr; size_t lists2_cap = 0; // first-level merge output
-    uint32_t *d_ids = nullptr; float *d_dist = nullptr; uint32_t *d_counts = nullptr; size_t res_cap = 0, cnt_cap = 0;
-    void *h_pinned = nullptr; size_t pinned_cap = 0;
-    float *d_stage = nullptr; size_t stage_cap = 0;     // floats, append staging
-
-    // tensor-core path scratch
-    float *d_max_norm = nullptr;                           // device scalar: bound on |row|_2 over the store
-    __half *d_qh = nullptr; size_t qh_cap = 0;             // fp16 queries, 128-row padded
-    float *d_qerr = nullptr; size_t qmeta_cap = 0;         // [b_pad] |q - fp16(q)|
-    float *d_qnorm = nullptr;                              // [b_pad]
-    float *d_maxima = nullptr; size_t maxima_cap = 0;      // [b_pad][grid] pre-pass maxima
-    uint32_t *d_gtau = nullptr, *d_flags = nullptr, *d_nflag = nullptr, *d_flag_list = nullptr;
-    unsigned long long *d_flag_total = nullptr;            // cumulative count of uncertified queries
-    uint64_t *d_cand = nullptr; size_t cand_cap_q = 0;     // [b_pad][grid][kk] per-CTA candidate lists
-    uint64_t tc_searches = 0, tc_flagged = 0;              // statistics (sg_store_tc_stats)
-
-    // vector id -> MemoryId table (IdMapping of RetrievalEngine, retrieval.rs:64-140) + search_ids scratch
-    uint64_t *d_vec2mem = nullptr; uint64_t n_map = 0; size_t map_cap = 0;
-    uint64_t *d_mem_out = nullptr; float *d_sim_out = nullptr; uint32_t *d_memcnt = nullptr; size_t post_cap = 0, postc_cap = 0;
-
-    bool profiling = false;
-    std::vector<cudaEvent_t> ev;  // pairs: ev[2i] before, ev[2i+1] after the sweep launches of search i
-    uint32_t ev_count = 0;        // searches recorded since the last read/reset
-    uint32_t last_scan_launches = 0;
-};
-
-namespace {
+namespace sg {
 
 int check_device(int device, int *sm_count)
 {
@@ -176,28 +125,6 @@ int check_device(int device, int *sm_count)
         return cached_rc[device];
     }
     if (sm_count) *sm_count = cached_sms[device];
-    return SG_OK;
-}
-
-template <typename T>
-int grow(T *&ptr, size_t &cap, size_t need, bool keep = false, cudaStream_t st = nullptr)
-{
-    if (need <= cap) return SG_OK;
-    size_t ncap = need + need / 2;
-    T *np = nullptr;
-    SG_CUDA_TRY(cudaMalloc(&np, ncap * sizeof(T)));
-    if (keep && ptr && cap) {
-        cudaError_t e = cudaMemcpyAsync(np, ptr, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) {
-            cudaFree(np);
-            set_error("device copy during growth failed: %s", cudaGetErrorString(e));
-            return SG_ERR_CUDA;
-        }
-    }
-    if (ptr) cudaFree(ptr);
-    ptr = np;
-    cap = ncap;
     return SG_OK;
 }
 
@@ -256,6 +183,10 @@ int ensure_rows(sg_store *s, uint64_t need_rows)
     return SG_OK;
 }
 
+}  // namespace sg
+
+namespace {
+
 struct ScanPlan {
     uint32_t W, ring, cap, grid;
     size_t smem[5];  // indexed by qb (1,2,4)
@@ -295,9 +226,13 @@ int plan_scan(const sg_store *s, uint32_t k, uint32_t qb, ScanPlan *p)
     return SG_ERR_UNSUPPORTED;
 }
 
+}  // namespace
+
+namespace sg {
+
 // exact path A.  all pointers are device pointers; runs asynchronously on st
 int search_exact_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint32_t *d_ids, float *d_dist,
-                        uint32_t *d_counts, cudaStream_t st, bool record)
+                        uint32_t *d_counts, cudaStream_t st, bool record, bool use_deleted)
 {
     if (s->n == 0) {  // VamanaIndex::search on an empty index: Ok(vec![]) (vamana.rs:766-768)
         SG_CUDA_TRY(launch_merge_keys(nullptr, b, 0, k, s->id_base, nullptr, d_ids, d_dist, d_counts, st));
@@ -332,7 +267,7 @@ int search_exact_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, u
         a.nq = nq;
         a.dim = s->dim;
         a.n_rows = s->n;
-        a.deleted = s->n_deleted ? s->d_deleted : nullptr;
+        a.deleted = (s->n_deleted && use_deleted) ? s->d_deleted : nullptr;
         a.k = k;
         a.cap = plan.cap;
         a.nbox = s->dim * s->esize / 128;
@@ -357,6 +292,10 @@ int search_exact_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, u
                                   d_counts, st));
     return SG_OK;
 }
+
+}  // namespace sg
+
+namespace {
 
 
 // tensor-core path B: approximate sweep + exact re-score + certification; uncertified queries are
@@ -631,6 +570,7 @@ void sg_store_destroy(sg_store *s)
     cudaFree(s->d_flag_list);
     cudaFree(s->d_flag_total);
     cudaFree(s->d_cand);
+    graph_free(s);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -677,8 +617,9 @@ int sg_store_append(sg_store *s, const float *rows, uint64_t n, uint32_t *first_
         SG_CUDA_TRY(cudaStreamSynchronize(s->stream));
         done += cnt;
     }
+    const uint64_t first = s->n;
     s->n += n;
-    return SG_OK;
+    return graph_append_locked(s, first, n);   // VamanaIndex::add_vector links each new row when a graph exists
 }
 
 int sg_store_append_synthetic(sg_store *s, uint64_t seed, uint64_t first_row, uint64_t n)
@@ -692,8 +633,9 @@ int sg_store_append_synthetic(sg_store *s, uint64_t seed, uint64_t first_row, ui
     SG_CUDA_TRY(launch_synth_rows(dst, s->dtype == SG_DTYPE_F16, seed, first_row, n, s->dim, s->stream));
     SG_CUDA_TRY(launch_max_row_norm(dst, s->dtype == SG_DTYPE_F16, n, s->dim, s->d_max_norm, s->stream));
     SG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    const uint64_t first = s->n;
     s->n += n;
-    return SG_OK;
+    return graph_append_locked(s, first, n);
 }
 
 int sg_store_mark_deleted(sg_store *s, uint32_t id, int *ok_out)
@@ -750,6 +692,13 @@ int sg_store_dim(const sg_store *s, uint32_t *dim_out)
 {
     if (!s || !dim_out) return SG_ERR_INVALID;
     *dim_out = s->dim;
+    return SG_OK;
+}
+
+int sg_store_metric(const sg_store *s, int *metric_out)
+{
+    if (!s || !metric_out) return SG_ERR_INVALID;
+    *metric_out = s->metric;
     return SG_OK;
 }
 

@@ -131,6 +131,66 @@ class GpuVectorStore:
                                               _ptr(dist, C.c_float), _ptr(counts, C.c_uint32)))
         return ids, dist, counts
 
+    # -- Vamana graph index (VamanaIndex::build / search's ANN arm / add_vector) -----------------------
+    def enable_graph(self, max_degree: int = 32, search_list_size: int = 75, alpha: float = 1.2) -> None:
+        """An empty store links every appended row like VamanaIndex::add_vector from now on."""
+        capi.check(capi.lib().sg_store_enable_graph(self._h, max_degree, search_list_size, alpha))
+
+    def build_graph(self, max_degree: int = 32, search_list_size: int = 75, alpha: float = 1.2, seed: int = 0) -> None:
+        """VamanaIndex::build over the rows in the store (VamanaConfig::default: R 32, L 75, alpha 1.2)."""
+        capi.check(capi.lib().sg_store_build_graph(self._h, max_degree, search_list_size, alpha, seed))
+
+    def set_graph(self, deg, nbr, medoid: int, max_degree: int) -> None:
+        """Upload an adjacency built elsewhere (deg [n] u32, nbr [n, stride] u32)."""
+        deg = np.ascontiguousarray(deg, np.uint32)
+        nbr = np.ascontiguousarray(nbr, np.uint32)
+        capi.check(capi.lib().sg_store_set_graph(self._h, max_degree, medoid, _ptr(deg, C.c_uint32), _ptr(nbr, C.c_uint32),
+                                                 nbr.shape[1] if nbr.ndim == 2 else max_degree, deg.size))
+
+    def graph_info(self) -> dict:
+        r, m, n = C.c_uint32(), C.c_uint32(), C.c_uint64()
+        capi.check(capi.lib().sg_store_graph_info(self._h, C.byref(r), C.byref(m), C.byref(n)))
+        return dict(max_degree=r.value, medoid=m.value, graph_len=n.value)
+
+    def get_graph(self):
+        """-> (deg [n] u32, nbr [n, max_degree] u32 with 0xFFFFFFFF padding, medoid)"""
+        info = self.graph_info()
+        n, r = info["graph_len"], info["max_degree"]
+        deg = np.zeros(n, np.uint32)
+        nbr = np.zeros((n, max(r, 1)), np.uint32)
+        capi.check(capi.lib().sg_store_get_graph(self._h, _ptr(deg, C.c_uint32), _ptr(nbr, C.c_uint32), n))
+        return deg, nbr, info["medoid"]
+
+    def search_ann(self, query, k: int):
+        """VamanaIndex::search, ANN arm -> list[(id, distance)] ascending."""
+        ids, dist, counts, _ = self.search_ann_batch(np.asarray(query, np.float32)[None, :], k)
+        c = int(counts[0])
+        return [(int(i), float(d)) for i, d in zip(ids[0, :c], dist[0, :c])]
+
+    def search_ann_batch(self, queries, k: int):
+        """-> (ids [b,k], dist [b,k], counts [b], stats [b,2] = nodes expanded, distance evaluations)."""
+        q = np.ascontiguousarray(queries, np.float32)
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise capi.SgError(capi.SG_ERR_DIM, f"expected [b,{self.dim}] queries, got {q.shape}")
+        b = q.shape[0]
+        ids = np.empty((b, k), np.uint32)
+        dist = np.empty((b, k), np.float32)
+        counts = np.zeros(b, np.uint32)
+        stats = np.zeros((b, 2), np.uint64)
+        capi.check(capi.lib().sg_store_search_ann(self._h, _ptr(q, C.c_float), b, k, _ptr(ids, C.c_uint32),
+                                                  _ptr(dist, C.c_float), _ptr(counts, C.c_uint32), _ptr(stats, C.c_uint64)))
+        return ids, dist, counts, stats
+
+    def search_ann_device(self, d_queries: int, b: int, k: int, d_ids: int, d_dist: int, d_counts: int, d_flags: int = 0,
+                          stream: int = 0) -> None:
+        capi.check(capi.lib().sg_store_search_ann_device(self._h, d_queries, b, k, d_ids, d_dist, d_counts, d_flags, stream))
+
+    def ann_stats(self):
+        """-> (queries served by the graph search, re-runs with a larger visited table)"""
+        a, b = C.c_uint64(), C.c_uint64()
+        capi.check(capi.lib().sg_store_ann_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def set_memory_ids(self, vec2mem) -> None:
         """IdMapping (retrieval.rs:64-140): vec2mem [n,2] u64 = MemoryId (uuid hi, lo) of every vector id."""
         t = np.ascontiguousarray(vec2mem, np.uint64)

@@ -9,7 +9,7 @@ import pytest
 SEED = 23821
 
 
-def write_vama(path, vectors, deleted=(), neighbors=None, metric=0, corrupt=False, version=1):
+def write_vama(path, vectors, deleted=(), neighbors=None, metric=0, corrupt=False, version=1, medoid=0, max_degree=32):
     n, dim = vectors.shape
     rng = np.random.default_rng(0)
     body = bytearray()
@@ -32,8 +32,8 @@ def write_vama(path, vectors, deleted=(), neighbors=None, metric=0, corrupt=Fals
     struct.pack_into("<I", hdr, 4, version)
     struct.pack_into("<Q", hdr, 8, n)
     struct.pack_into("<I", hdr, 16, dim)
-    struct.pack_into("<I", hdr, 20, 32)
-    struct.pack_into("<I", hdr, 24, 0)
+    struct.pack_into("<I", hdr, 20, max_degree)
+    struct.pack_into("<I", hdr, 24, medoid)
     hdr[28] = metric
     struct.pack_into("<I", hdr, 29, len(deleted))
     struct.pack_into("<Q", hdr, 33, 0)
