@@ -420,6 +420,76 @@ def main():
                                               note="pinned host ids -> H2D -> encoder -> exact top-%d scan of this "
                                                    "rank's shard -> D2H, one stream" % TOPK))
         enc.close()
+    # ---------------- graph index: VamanaIndex::search's default ANN arm on the device ----------------
+    # Opt-out with SG_BENCH_ANN=0.  A separate clustered corpus (i.i.d. unit vectors have no neighbourhood structure
+    # for a graph to follow): device build (R 32, L 75, alpha 1.2), then batch-256 and batch-1 beam searches with the
+    # reference's k = 4 x limit = 40 for top-10 (retrieval.rs:915-916), recall@10 against the exact sweep of the same store.
+    ann_res = None
+    if rank == 0 and world == 1 and os.environ.get("SG_BENCH_ANN", "1") == "1":
+        try:
+            ann_rows = int(os.environ.get("SG_BENCH_ANN_ROWS", 1_000_000))
+            rng = np.random.default_rng(SEED + 7)
+            n_c = max(16, int(ann_rows ** 0.5))
+            centres = rng.standard_normal((n_c, DIM)).astype(np.float32)
+            centres /= np.linalg.norm(centres, axis=1, keepdims=True)
+            g = sg.GpuVectorStore(DIM, "f16", local_rank)
+            g.reserve(ann_rows)
+            for lo in range(0, ann_rows, 100_000):
+                m = min(100_000, ann_rows - lo)
+                x = centres[rng.integers(0, n_c, m)] + (0.35 / np.sqrt(DIM)) * rng.standard_normal((m, DIM)).astype(np.float32)
+                x /= np.linalg.norm(x, axis=1, keepdims=True)
+                g.add_vectors(x.astype(np.float32))
+            t0 = time.perf_counter()
+            g.build_graph(32, 75, 1.2, SEED)
+            build_s = time.perf_counter() - t0
+            picks = rng.integers(0, ann_rows, BATCH)
+            aq = np.stack([g.get_vectors(int(j), 1)[0] for j in picks]) + (0.05 / np.sqrt(DIM)) * rng.standard_normal((BATCH, DIM)).astype(np.float32)
+            aq = np.ascontiguousarray(aq / np.linalg.norm(aq, axis=1, keepdims=True), np.float32)
+            KB = 4 * TOPK
+            ids_a, _, cnt_a, st_a = g.search_ann_batch(aq, KB)
+            ids_e, _, cnt_e = g.search_batch(aq, TOPK)
+            hits = sum(len(set(ids_a[i, :TOPK].tolist()) & set(ids_e[i, :cnt_e[i]].tolist())) for i in range(BATCH))
+            rec = hits / float(cnt_e.sum())
+            g.set_profiling(True)
+            for _ in range(3):
+                g.search_ann_batch(aq, KB)
+            g.profile_read()
+            reps = 30
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                g.search_ann_batch(aq, KB)
+            ann_e2e_ms = (time.perf_counter() - t0) * 1e3 / reps
+            kms, _ = g.profile_read()
+            ann_kernel_ms = float(np.mean(kms)) if len(kms) else float("nan")
+            for _ in range(3):
+                g.search_ann_batch(aq[:1], KB)
+            g.profile_read()
+            t0 = time.perf_counter()
+            for i in range(100):
+                g.search_ann_batch(aq[i % BATCH:i % BATCH + 1], KB)
+            ann_b1_ms = (time.perf_counter() - t0) * 1e3 / 100
+            k1, _ = g.profile_read()
+            g.set_profiling(False)
+            t0 = time.perf_counter()
+            for _ in range(10):
+                g.search_batch(aq, TOPK)
+            exact_ms = (time.perf_counter() - t0) * 1e3 / 10
+            evals = float(st_a[:, 1].mean())
+            ann_bytes = float(st_a[:, 1].sum()) * DIM * 2
+            ann_res = dict(rows=ann_rows, corpus="clustered unit vectors, %d centres, fp16" % n_c, max_degree=32, search_list_size=75,
+                           alpha=1.2, build_s=build_s, beam_k=KB, recall_at_10_vs_exact=rec,
+                           batch256=dict(kernel_ms=ann_kernel_ms, queries_per_s_kernel=BATCH / (ann_kernel_ms * 1e-3),
+                                         host_api_ms=ann_e2e_ms, queries_per_s_host_api=BATCH / (ann_e2e_ms * 1e-3)),
+                           batch1=dict(kernel_ms=float(np.mean(k1)) if len(k1) else None, host_api_ms=ann_b1_ms),
+                           nodes_expanded_per_query=float(st_a[:, 0].mean()), distance_evals_per_query=evals,
+                           roofline=dict(bound="hbm (random 768-byte row reads, latency-bound per query)",
+                                         algorithmic_bytes_per_step=ann_bytes, achieved=ann_bytes / (ann_kernel_ms * 1e-3) / 1e9,
+                                         peak=peaks()[0], unit="GB/s", frac=ann_bytes / (ann_kernel_ms * 1e-3) / 1e9 / peaks()[0]),
+                           exact_sweep_same_store_host_api_ms=exact_ms, retries=g.ann_stats()[1],
+                           kernel="ann_search_kernel (one warp per query; result == the reference's greedy_search on the same graph)")
+            g.close()
+        except Exception as ex:  # the headline line must still print
+            ann_res = dict(error=repr(ex))
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
@@ -492,6 +562,7 @@ def main():
                                   traffic=traffic_from_capture("scan_exact_kernel", local_rows)[0])),
         tensor_path=dict(zip(("queries", "exact_reruns"), store.local.tc_stats())),
         encoder=enc_res,
+        graph_index=ann_res,
         gpu_launches=int(launches), clocks=clocks)
     if cpu:
         line["cpu_baseline"] = dict(value=cpu["value"], unit=UNIT, cores=cpu["cores"], kind=cpu["kind"], sample=cpu["sample"])

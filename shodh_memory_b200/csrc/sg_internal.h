@@ -135,8 +135,8 @@ struct AnnArgs {
 // shared memory per query warp: query f32 + the sorted list (K + 32 keys) + expanded flags
 __host__ __device__ inline size_t ann_warp_smem_bytes(uint32_t dim, uint32_t K)
 {
-    const size_t cap = (size_t)K + 32;
-    return (((size_t)dim * 4 + 15) & ~(size_t)15) + cap * 8 + ((cap + 15) & ~(size_t)15);
+    const size_t cap = (size_t)K + 32;   // every piece a multiple of 16 bytes: the query is read as float4
+    return (((size_t)dim * 4 + 15) & ~(size_t)15) + ((cap * 8 + 15) & ~(size_t)15) + ((cap + 15) & ~(size_t)15);
 }
 cudaError_t launch_ann_search(const AnnArgs &a, bool f16, int order, int metric, cudaStream_t st);
 cudaError_t launch_graph_link(const void *rows, bool f16, int order, int metric, uint32_t dim, uint32_t *graph, uint32_t gs,

@@ -82,7 +82,7 @@ ann_search_kernel(const AnnArgs a)
     uint8_t *base = smem + (size_t)warp * ann_warp_smem_bytes(dim, K);
     float *q_s = reinterpret_cast<float *>(base);
     uint64_t *P = reinterpret_cast<uint64_t *>(base + align16((size_t)dim * 4));
-    uint8_t *ex = reinterpret_cast<uint8_t *>(P + CAP);
+    uint8_t *ex = reinterpret_cast<uint8_t *>(P) + align16((size_t)CAP * 8);
 
     if (a.query_rows) {
         load_row_f32<F16>(a.rows, dim, a.query_rows[q], q_s, lane);

@@ -34,9 +34,11 @@ inline void check(int rc)
 
 class GpuVectorStore {
 public:
-    explicit GpuVectorStore(uint32_t dim = 384, sg_dtype dtype = SG_DTYPE_F16, int device = 0) : dim_(dim)
+    /// metric = VamanaConfig::distance_metric (vamana.rs:38-54); RetrievalEngine uses NormalizedDotProduct
+    explicit GpuVectorStore(uint32_t dim = 384, sg_dtype dtype = SG_DTYPE_F16, int device = 0,
+                            sg_metric metric = SG_METRIC_NEG_DOT) : dim_(dim)
     {
-        check(sg_store_create(&h_, device, dim, dtype, SG_METRIC_NEG_DOT));
+        check(sg_store_create(&h_, device, dim, dtype, metric));
     }
     ~GpuVectorStore() { sg_store_destroy(h_); }
     GpuVectorStore(const GpuVectorStore &) = delete;
@@ -91,12 +93,51 @@ public:
             for (uint32_t j = 0; j < cnt[q]; ++j) out[q].emplace_back(ids[q * k + j], dist[q * k + j]);
         return out;
     }
+    /// VamanaIndex::build's graph half over the rows already uploaded (VamanaConfig::default: 32, 75, 1.2)
+    void build_graph(uint32_t max_degree = 32, uint32_t search_list_size = 75, float alpha = 1.2f, uint64_t seed = 0)
+    {
+        check(sg_store_build_graph(h_, max_degree, search_list_size, alpha, seed));
+    }
+    /// an empty index that links every add_vector like the reference does (vamana.rs:853-973)
+    void enable_graph(uint32_t max_degree = 32, uint32_t search_list_size = 75, float alpha = 1.2f)
+    {
+        check(sg_store_enable_graph(h_, max_degree, search_list_size, alpha));
+    }
+    /// VamanaIndex::search without SHODH_VECTOR_EXACT: beam search over the graph (vamana.rs:779-807);
+    /// throws Error(SG_ERR_NOT_BUILT) where the reference says "Vamana graph not built"
+    std::vector<std::pair<uint32_t, float>> search_ann(const std::vector<float> &query, size_t k)
+    {
+        if (query.size() != dim_) throw Error(SG_ERR_DIM, "dimension mismatch");
+        std::vector<uint32_t> ids(k);
+        std::vector<float> dist(k);
+        uint32_t cnt = 0;
+        check(sg_store_search_ann(h_, query.data(), 1, (uint32_t)k, ids.data(), dist.data(), &cnt, nullptr));
+        std::vector<std::pair<uint32_t, float>> out;
+        for (uint32_t j = 0; j < cnt; ++j) out.emplace_back(ids[j], dist[j]);
+        return out;
+    }
     sg_store *handle() { return h_; }
 
 private:
     sg_store *h_ = nullptr;
     uint32_t dim_;
 };
+
+/// similarity.rs::top_k_similar over a dense candidate matrix: (score, position) by score descending, ties in
+/// input order; cosine_similarity is 0 on a zero norm or a length mismatch (similarity.rs:10-48)
+inline std::vector<std::pair<float, uint32_t>> top_k_similar(const std::vector<float> &query, const std::vector<float> &candidates_flat,
+                                                              size_t dim, size_t k, int device = 0, sg_order order = SG_ORDER_SCALAR)
+{
+    const size_t n = dim ? candidates_flat.size() / dim : 0;
+    std::vector<uint32_t> pos(k ? k : 1);
+    std::vector<float> sc(k ? k : 1);
+    uint32_t r = 0;
+    check(sg_top_k_similar(device, query.data(), (uint32_t)query.size(), candidates_flat.data(), n, (uint32_t)dim, (uint32_t)k,
+                           order, pos.data(), sc.data(), &r));
+    std::vector<std::pair<float, uint32_t>> out;
+    for (uint32_t j = 0; j < r; ++j) out.emplace_back(sc[j], pos[j]);
+    return out;
+}
 
 class GpuMiniLM {
 public:

@@ -54,6 +54,27 @@ int main()
         sg_candidate_feats f{sem, ent, tag, imp, mom, acc, gr, created};
         auto ranked = shodh::fuse_and_rank(f, 2, 1000 + 100 * 3600);
         REQUIRE(ranked.size() == 1 && ranked[0].candidate == 0 && ranked[0].score > 0.8f);
+        // similarity.rs:89-105: top_k_similar orders by cosine and truncates
+        {
+            std::vector<float> cands(3 * 32, 0.0f), q(32, 0.0f);
+            cands[0 * 32 + 1] = 1.0f;                              // orthogonal
+            cands[1 * 32 + 0] = 1.0f;                              // identical
+            cands[2 * 32 + 0] = -1.0f;                             // opposite
+            q[0] = 1.0f;
+            auto top = shodh::top_k_similar(q, cands, 32, 2);
+            REQUIRE(top.size() == 2 && top[0].second == 1 && top[0].first == 1.0f && top[1].second == 0 && top[1].first == 0.0f);
+        }
+        // the graph arm: "not built" is an error, a built graph answers like vamana.rs:1697-1711
+        {
+            bool nb = false;
+            try { st.search_ann(q0, 3); } catch (const shodh::Error &e) { nb = e.code == SG_ERR_NOT_BUILT; }
+            REQUIRE(nb);
+            st.build_graph(16, 40, 1.2f, 1);
+            auto r = st.search_ann(test_vector(11, 384), 5);
+            REQUIRE(r.size() == 5 && r[0].first == 11);
+            REQUIRE(st.add_vector(test_vector(300, 384)) == 300);  // linked into the graph like add_vector
+            REQUIRE(st.search_ann(test_vector(300, 384), 3).size() == 3);
+        }
         std::printf("HOST_MIRROR_OK\n");
         return 0;
     } catch (const std::exception &e) {

@@ -158,3 +158,66 @@ def test_find_medoid(oracle):
     cen = (cen / F(300)).astype(F)
     d = [oracle.distance(r, cen, 0, 0) for r in x]
     assert oracle.find_medoid(x) == int(np.argmin(d))
+
+
+# ---- the device kernel's formulation of greedy_search, modelled step by step -------------------------
+def greedy_single_array_py(o, V, query, K, entry, slack=32):
+    """shodh_memory_b200/csrc/vamana.cu::ann_search_kernel in pure Python: ONE sorted array P that is both
+    heaps of the reference (w = its first K entries, candidates = its unexpanded entries); entries beyond
+    the K-th survive only while they tie the K-th distance.  Must give the reference's result and traversal."""
+    dist = lambda i: F(o.distance(query, V.vectors[i], V.metric, V.variant))
+    tk = lambda d, i: (o.total_order_key(float(d)), int(i))
+    d0 = dist(entry)
+    P = [[tk(d0, entry), d0, entry, False]]           # key, dist, id, expanded
+    visited = {entry}
+    hops, evals = 0, 1
+    while True:
+        cur = next((e for e in P if not e[3]), None)
+        if cur is None:
+            break
+        wl = min(len(P), K)
+        if cur[1] > P[wl - 1][1]:
+            break
+        cur[3] = True
+        hops += 1
+        nbrs = [int(v) for v in V.nbr[cur[2], :V.deg[cur[2]]]]
+        for c0 in range(0, len(nbrs), 32):            # one neighbour per lane
+            lanes = []
+            for v in nbrs[c0:c0 + 32]:
+                if v not in visited:
+                    visited.add(v)
+                    lanes.append((v, dist(v)))
+                    evals += 1
+            if len(P) >= K:                            # pre-filter against the K-th distance as it stands
+                lanes = [(v, d) for v, d in lanes if d < P[K - 1][1]]
+            for v, d in lanes:                         # lane order
+                if len(P) >= K and not (d < P[K - 1][1]):
+                    continue
+                e = [tk(d, v), d, v, False]
+                pos = sum(1 for x in P if x[0] < e[0])
+                P.insert(pos, e)
+                if len(P) > K:
+                    wd = P[K - 1][1]
+                    cut = next((i for i in range(K, len(P)) if P[i][1] > wd), None)
+                    if cut is not None:
+                        del P[cut:]
+                    assert len(P) < K + slack
+    w = P[:min(len(P), K)]
+    return [e[2] for e in w], [e[1] for e in w], (hops, evals)
+
+
+@pytest.mark.parametrize("dups", [False, True])
+def test_single_array_formulation_equals_two_heaps(oracle, dups):
+    x = oracle.clustered_corpus(17, 300, 16)
+    if dups:                                           # exact distance ties: every row of the first 100 three times
+        x = np.vstack([x, x[:100], x[:100]]).astype(F)
+    V = oracle.VamanaOracle(16, max_degree=6, search_list_size=16)
+    V.build(x, seed=4)
+    rng = np.random.default_rng(3)
+    for t in range(30):
+        q = x[rng.integers(0, len(x))] if dups else (x[rng.integers(0, len(x))] + F(0.1) * rng.standard_normal(16)).astype(F)
+        for k in (1, 2, 4, 9, 33):
+            ids, dist, st = V.greedy_search(q, k, stats=True)
+            sids, sdist, sst = greedy_single_array_py(oracle, V, q, k, V.medoid)
+            assert list(ids) == sids and [float(d) for d in dist] == [float(d) for d in sdist], (t, k)
+            assert (int(st[0]), int(st[1])) == sst, (t, k, st, sst)
