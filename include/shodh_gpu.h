@@ -90,6 +90,10 @@ SG_API int sg_store_reserve(sg_store *s, uint64_t n_rows);
  * rebuild_from_vectors: append n row-major f32 rows (rounded to the store dtype
  * on the device, round-to-nearest-even).  first_id_out receives the id of row 0. */
 SG_API int sg_store_append(sg_store *s, const float *rows_f32, uint64_t n, uint32_t *first_id_out);
+/* the same for rows that are already on the device (e.g. sg_encoder_encode_device output: batched document
+ * ingest, retrieval.rs:668-676 -> minilm.rs:996, without a host round trip); returns after the rows are in. */
+SG_API int sg_store_append_device(sg_store *s, const float *d_rows_f32, uint64_t n, uint32_t *first_id_out,
+                                  void *cuda_stream);
 
 /* VamanaIndex::mark_deleted (vamana.rs:813-820): soft delete.  *ok_out = 1 if id < len
  * (the reference returns true, also for an id that was already deleted), 0 otherwise. */

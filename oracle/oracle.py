@@ -480,3 +480,19 @@ def clustered_corpus(seed, n, dim, n_clusters=None, spread=0.35):
     x = x.astype(np.float32)
     x /= np.linalg.norm(x, axis=1, keepdims=True)
     return np.ascontiguousarray(x, np.float32)
+
+
+def manifold_corpus(seed, n, dim, latent=12, noise=0.05):
+    """Unit vectors on a low-dimensional manifold: normalize(z A + noise), z ~ N(0, I_latent).  Sentence
+    embeddings have low intrinsic dimension; the alpha-RNG prune of a Vamana graph relies on that (on tight
+    isolated clusters or i.i.d. unit vectors every cluster-mate is "unoccluded" and the lists lose their
+    long-range edges -- for the reference's build just the same)."""
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((latent, dim)).astype(np.float32)
+    out = np.empty((n, dim), np.float32)
+    for lo in range(0, n, 100_000):
+        m = min(100_000, n - lo)
+        z = rng.standard_normal((m, latent)).astype(np.float32)
+        x = z @ A + (noise * np.sqrt(latent)) * rng.standard_normal((m, dim)).astype(np.float32)
+        out[lo:lo + m] = x / np.linalg.norm(x, axis=1, keepdims=True)
+    return out

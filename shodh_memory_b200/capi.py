@@ -74,6 +74,7 @@ def lib() -> C.CDLL:
     L.sg_store_destroy.restype = None
     L.sg_store_reserve.argtypes = [vp, C.c_uint64]
     L.sg_store_append.argtypes = [vp, f32p, C.c_uint64, u32p]
+    L.sg_store_append_device.argtypes = [vp, vp, C.c_uint64, u32p, vp]
     L.sg_store_append_synthetic.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64]
     L.sg_store_mark_deleted.argtypes = [vp, C.c_uint32, C.POINTER(C.c_int)]
     L.sg_store_is_deleted.argtypes = [vp, C.c_uint32, C.POINTER(C.c_int)]

@@ -6,6 +6,7 @@
 // as-is.  The exact sweep (sg_store_search) needs none of this; a graph exists only after
 // sg_store_build_graph / sg_store_set_graph / sg_store_enable_graph / a VAMA load.
 #include <cfloat>
+#include <cstdlib>
 #include <cstring>
 
 #include "sg_store_internal.h"
@@ -361,6 +362,10 @@ int sg_store_build_graph(sg_store *s, uint32_t max_degree, uint32_t search_list_
         return SG_ERR_OOM;
     }
     const uint32_t H = default_table_size(L);
+    // back-edge prunes visit the list in id order, as the reference's zero-distance candidates do (:251-262);
+    // SG_GRAPH_BACKEDGE_BY_DISTANCE=1 orders them by true distance instead
+    const char *bd = getenv("SG_GRAPH_BACKEDGE_BY_DISTANCE");
+    const bool by_id = !(bd && *bd == '1');
     uint32_t *d_nodes = s->d_g32 + o_nodes, *d_cnt = s->d_g32 + o_cnt, *d_res = s->d_g32 + o_res, *d_new = s->d_g32 + o_new,
              *d_touch = s->d_g32 + o_touch, *d_ntouch = s->d_g32 + o_ntouch;
     rc = SG_OK;
@@ -382,7 +387,7 @@ int sg_store_build_graph(sg_store *s, uint32_t max_degree, uint32_t search_list_
                 const uint64_t gmax = (uint64_t)s->sm_count * 8;
                 if (grid > gmax) grid = gmax;
                 e = launch_build_backedges(s->d_rows, f16, s->dim, s->metric, alpha, s->d_graph, gs, d_touch, d_ntouch, d_inbox,
-                                           d_inbox_cnt, ecap, (uint32_t)grid, st);
+                                           d_inbox_cnt, ecap, by_id, (uint32_t)grid, st);
             }
             if (e != cudaSuccess) {
                 set_error("graph build launch failed: %s", cudaGetErrorString(e));

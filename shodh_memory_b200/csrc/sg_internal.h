@@ -153,7 +153,7 @@ cudaError_t launch_build_apply(uint32_t *graph, uint32_t gs, const uint32_t *nod
                                uint32_t *touched, uint32_t *n_touched, cudaStream_t st);
 cudaError_t launch_build_backedges(const void *rows, bool f16, uint32_t dim, int metric, float alpha, uint32_t *graph,
                                    uint32_t gs, const uint32_t *touched, const uint32_t *n_touched, const uint32_t *inbox,
-                                   uint32_t *inbox_cnt, uint32_t ecap, uint32_t grid, cudaStream_t st);
+                                   uint32_t *inbox_cnt, uint32_t ecap, bool by_id, uint32_t grid, cudaStream_t st);
 
 // ---- tensor map (store.cu) ----
 int encode_corpus_tmap(CUtensorMap *out, const void *d_rows, bool f16, uint32_t dim, uint64_t n_rows,

@@ -622,6 +622,30 @@ int sg_store_append(sg_store *s, const float *rows, uint64_t n, uint32_t *first_
     return graph_append_locked(s, first, n);   // VamanaIndex::add_vector links each new row when a graph exists
 }
 
+int sg_store_append_device(sg_store *s, const float *d_rows, uint64_t n, uint32_t *first_id_out, void *cuda_stream)
+{
+    if (!s || (!d_rows && n)) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    SG_CUDA_TRY(cudaSetDevice(s->device));
+    if (first_id_out) *first_id_out = (uint32_t)s->n;
+    if (n == 0) return SG_OK;
+    int rc = ensure_rows(s, s->n + n);
+    if (rc != SG_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const size_t elems = (size_t)n * s->dim;
+    uint8_t *dst = static_cast<uint8_t *>(s->d_rows) + s->n * (size_t)s->dim * s->esize;
+    if (s->dtype == SG_DTYPE_F16) {
+        SG_CUDA_TRY(launch_f32_to_f16(d_rows, reinterpret_cast<__half *>(dst), elems, st));
+    } else {
+        SG_CUDA_TRY(cudaMemcpyAsync(dst, d_rows, elems * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    SG_CUDA_TRY(launch_max_row_norm(dst, s->dtype == SG_DTYPE_F16, n, s->dim, s->d_max_norm, st));
+    SG_CUDA_TRY(cudaStreamSynchronize(st));
+    const uint64_t first = s->n;
+    s->n += n;
+    return graph_append_locked(s, first, n);
+}
+
 int sg_store_append_synthetic(sg_store *s, uint64_t seed, uint64_t first_row, uint64_t n)
 {
     if (!s) return SG_ERR_INVALID;

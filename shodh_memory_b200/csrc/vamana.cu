@@ -411,10 +411,14 @@ constexpr uint32_t PRUNE_MAX_CAND = 128;
 // robust_prune (:665-746) for one node by one CTA of 128 threads.  cand[0..n_cand) (shared memory) are
 // candidate ids, duplicates and the node itself allowed; on return out[0..gs) (global) holds the kept
 // ids in selection order, NONE-padded.  keys/kept/kept_ne/flag are shared scratch.
+// by_id = the back-edge form (:251-262): the reference hands robust_prune the neighbour list with distance 0.0
+// for every entry, so the candidates are visited in ID order (node->candidate distances are still the true
+// ones); dnc is shared scratch for those distances.
 template <bool F16>
 SG_DEVICE_INLINE void block_robust_prune(const void *rows, uint32_t dim, int metric, float alpha, uint32_t node,
                                          const uint32_t *cand, uint32_t n_cand, uint32_t gs, uint32_t *out,
-                                         uint64_t *keys, uint32_t *kept, float *kept_ne, uint32_t *flag)
+                                         uint64_t *keys, uint32_t *kept, float *kept_ne, uint32_t *flag,
+                                         bool by_id = false, float *dnc = nullptr)
 {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     // distance node -> candidate, one warp per candidate
@@ -423,11 +427,24 @@ SG_DEVICE_INLINE void block_robust_prune(const void *rows, uint32_t dim, int met
     for (uint32_t i = warp; i < n_cand; i += W) {
         const uint32_t c = cand[i];
         if (c == NONE || c == node) continue;
-        const float d = warp_pair_distance<F16>(rows, dim, node, c, metric, lane);
-        if (lane == 0) keys[i] = make_key(order_key32(canon_nan(d)), c);
+        if (by_id) {
+            if (lane == 0) keys[i] = make_key(0u, c);
+        } else {
+            const float d = warp_pair_distance<F16>(rows, dim, node, c, metric, lane);
+            if (lane == 0) keys[i] = make_key(order_key32(canon_nan(d)), c);
+        }
     }
     __syncthreads();
     block_bitonic_sort(keys, PRUNE_MAX_CAND);          // (distance, id) ascending; duplicates become neighbours
+    if (by_id) {
+        for (uint32_t i = warp; i < n_cand; i += W) {
+            const uint64_t kc = keys[i];
+            if (kc == KEY_SENTINEL) break;
+            const float d = warp_pair_distance<F16>(rows, dim, node, (uint32_t)kc, metric, lane);
+            if (lane == 0) dnc[i] = canon_nan(d);
+        }
+        __syncthreads();
+    }
     const float off = metric == SG_METRIC_NEG_DOT ? 1.0f : 0.0f;
     uint32_t m = 0;                                    // kept so far (uniform: every thread tracks it)
     for (uint32_t i = 0; i < n_cand && m < gs; ++i) {
@@ -435,7 +452,7 @@ SG_DEVICE_INLINE void block_robust_prune(const void *rows, uint32_t dim, int met
         if (kc == KEY_SENTINEL) break;
         if (i > 0 && kc == keys[i - 1]) continue;      // the same id twice
         const uint32_t c = (uint32_t)kc;
-        const float d_nc = key32_to_dist((uint32_t)(kc >> 32));
+        const float d_nc = by_id ? dnc[i] : key32_to_dist((uint32_t)(kc >> 32));
         if (threadIdx.x == 0) *flag = 0;
         __syncthreads();
         for (uint32_t e = warp; e < m; e += W) {
@@ -517,13 +534,14 @@ template <bool F16>
 __global__ void __launch_bounds__(128)
 build_backedge_apply_kernel(const void *rows, uint32_t dim, int metric, float alpha, uint32_t *graph, uint32_t gs,
                             const uint32_t *touched, const uint32_t *n_touched, const uint32_t *inbox, uint32_t *inbox_cnt,
-                            uint32_t ecap)
+                            uint32_t ecap, bool by_id)
 {
     __shared__ uint64_t keys[PRUNE_MAX_CAND];
     __shared__ uint32_t cand[PRUNE_MAX_CAND];
     __shared__ uint32_t kept[64];
     __shared__ float kept_ne[64];
     __shared__ uint32_t flag;
+    __shared__ float dnc[PRUNE_MAX_CAND];
     for (uint32_t b = blockIdx.x; b < *n_touched; b += gridDim.x) {
         const uint32_t p = touched[b];
         uint32_t ne = inbox_cnt[p];
@@ -537,7 +555,7 @@ build_backedge_apply_kernel(const void *rows, uint32_t dim, int metric, float al
         if (deg + ne <= gs) {
             for (uint32_t i = threadIdx.x; i < ne; i += blockDim.x) row[deg + i] = cand[gs + i];
         } else {
-            block_robust_prune<F16>(rows, dim, metric, alpha, p, cand, gs + ne, gs, row, keys, kept, kept_ne, &flag);
+            block_robust_prune<F16>(rows, dim, metric, alpha, p, cand, gs + ne, gs, row, keys, kept, kept_ne, &flag, by_id, dnc);
         }
         __syncthreads();
         if (threadIdx.x == 0) inbox_cnt[p] = 0;
@@ -686,12 +704,12 @@ cudaError_t launch_build_apply(uint32_t *graph, uint32_t gs, const uint32_t *nod
 
 cudaError_t launch_build_backedges(const void *rows, bool f16, uint32_t dim, int metric, float alpha, uint32_t *graph,
                                    uint32_t gs, const uint32_t *touched, const uint32_t *n_touched, const uint32_t *inbox,
-                                   uint32_t *inbox_cnt, uint32_t ecap, uint32_t grid, cudaStream_t st)
+                                   uint32_t *inbox_cnt, uint32_t ecap, bool by_id, uint32_t grid, cudaStream_t st)
 {
     if (f16) build_backedge_apply_kernel<true><<<grid, 128, 0, st>>>(rows, dim, metric, alpha, graph, gs, touched, n_touched,
-                                                                    inbox, inbox_cnt, ecap);
+                                                                    inbox, inbox_cnt, ecap, by_id);
     else build_backedge_apply_kernel<false><<<grid, 128, 0, st>>>(rows, dim, metric, alpha, graph, gs, touched, n_touched,
-                                                                  inbox, inbox_cnt, ecap);
+                                                                  inbox, inbox_cnt, ecap, by_id);
     count_launch();
     return cudaGetLastError();
 }

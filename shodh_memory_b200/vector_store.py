@@ -72,6 +72,12 @@ class GpuVectorStore:
 
     build = add_vectors
 
+    def add_vectors_device(self, d_rows: int, n: int, stream: int = 0) -> int:
+        """rows already on the device ([n,dim] f32, raw pointer) -> id of the first appended row"""
+        first = C.c_uint32()
+        capi.check(capi.lib().sg_store_append_device(self._h, d_rows, n, C.byref(first), stream))
+        return first.value
+
     def append_synthetic(self, seed: int, first_row: int, n: int) -> None:
         capi.check(capi.lib().sg_store_append_synthetic(self._h, seed, first_row, n))
 

@@ -109,3 +109,21 @@ def test_top_k_similar_edge_cases(sg, oracle):
     pos, sc = sg.top_k_similar(q, e[:5], 3)
     rpos, rsc = oracle.top_k_similar(q, e[:5], 3)
     assert np.array_equal(pos, rpos) and np.isnan(sc).all() and np.isnan(rsc).all()
+
+
+def test_append_from_device_memory(sg, oracle):
+    """sg_store_append_device: rows that are already in HBM (encoder output) go in without a host round trip"""
+    import torch
+    rows = oracle.synth_corpus(SEED, 0, 3000, 384)
+    d = torch.from_numpy(rows).cuda()
+    for dtype in ("f16", "f32"):
+        st = sg.GpuVectorStore(384, dtype)
+        assert st.add_vectors(rows[:1000]) == 0
+        assert st.add_vectors_device(d[1000:].data_ptr(), 2000, torch.cuda.current_stream().cuda_stream) == 1000
+        want = oracle.round_f16(rows) if dtype == "f16" else rows
+        assert len(st) == 3000 and np.array_equal(bits(st.extract_all_vectors()), bits(want))
+        q, _ = oracle.synth_queries(SEED, 3000, 6, 384)
+        ids, dist, _ = st.search_batch(q, 10)
+        rid, rdist, _, _ = oracle.brute_force_search_batch(want, q, 10)
+        assert np.array_equal(ids, rid) and np.array_equal(bits(dist), bits(rdist))
+        st.close()
