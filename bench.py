@@ -445,47 +445,50 @@ def main():
             picks = rng.integers(0, ann_rows, BATCH)
             aq = np.stack([g.get_vectors(int(j), 1)[0] for j in picks]) + 0.02 * rng.standard_normal((BATCH, DIM)).astype(np.float32)
             aq = np.ascontiguousarray(aq / np.linalg.norm(aq, axis=1, keepdims=True), np.float32)
-            KB = 4 * TOPK
-            ids_a, _, cnt_a, st_a = g.search_ann_batch(aq, KB)
             ids_e, _, cnt_e = g.search_batch(aq, TOPK)
-            hits = sum(len(set(ids_a[i, :TOPK].tolist()) & set(ids_e[i, :cnt_e[i]].tolist())) for i in range(BATCH))
-            rec = hits / float(cnt_e.sum())
-            g.set_profiling(True)
-            for _ in range(3):
-                g.search_ann_batch(aq, KB)
-            g.profile_read()
-            reps = 30
-            t0 = time.perf_counter()
-            for _ in range(reps):
-                g.search_ann_batch(aq, KB)
-            ann_e2e_ms = (time.perf_counter() - t0) * 1e3 / reps
-            kms, _ = g.profile_read()
-            ann_kernel_ms = float(np.mean(kms)) if len(kms) else float("nan")
-            for _ in range(3):
-                g.search_ann_batch(aq[:1], KB)
-            g.profile_read()
-            t0 = time.perf_counter()
-            for i in range(100):
-                g.search_ann_batch(aq[i % BATCH:i % BATCH + 1], KB)
-            ann_b1_ms = (time.perf_counter() - t0) * 1e3 / 100
-            k1, _ = g.profile_read()
-            g.set_profiling(False)
             t0 = time.perf_counter()
             for _ in range(10):
                 g.search_batch(aq, TOPK)
             exact_ms = (time.perf_counter() - t0) * 1e3 / 10
-            evals = float(st_a[:, 1].mean())
-            ann_bytes = float(st_a[:, 1].sum()) * DIM * 2
-            ann_res = dict(rows=ann_rows, corpus="unit vectors on a %d-dimensional manifold (z A + noise), fp16" % latent, max_degree=32, search_list_size=75,
-                           alpha=1.2, build_s=build_s, beam_k=KB, recall_at_10_vs_exact=rec,
-                           batch256=dict(kernel_ms=ann_kernel_ms, queries_per_s_kernel=BATCH / (ann_kernel_ms * 1e-3),
-                                         host_api_ms=ann_e2e_ms, queries_per_s_host_api=BATCH / (ann_e2e_ms * 1e-3)),
-                           batch1=dict(kernel_ms=float(np.mean(k1)) if len(k1) else None, host_api_ms=ann_b1_ms),
-                           nodes_expanded_per_query=float(st_a[:, 0].mean()), distance_evals_per_query=evals,
-                           roofline=dict(bound="hbm (random 768-byte row reads, latency-bound per query)",
-                                         algorithmic_bytes_per_step=ann_bytes, achieved=ann_bytes / (ann_kernel_ms * 1e-3) / 1e9,
-                                         peak=peaks()[0], unit="GB/s", frac=ann_bytes / (ann_kernel_ms * 1e-3) / 1e9 / peaks()[0]),
-                           exact_sweep_same_store_host_api_ms=exact_ms, retries=g.ann_stats()[1],
+            g.set_profiling(True)
+            beams = {}
+            # beam 120 = the reference's request for top-10 (k = 12 x max_results: retrieval.rs:916 x memory/mod.rs:3585);
+            # beam 40 = search_ids' own 4 x limit (retrieval.rs:915-916)
+            for KB in (12 * TOPK, 4 * TOPK):
+                ids_a, _, cnt_a, st_a = g.search_ann_batch(aq, KB)
+                hits = sum(len(set(ids_a[i, :TOPK].tolist()) & set(ids_e[i, :cnt_e[i]].tolist())) for i in range(BATCH))
+                for _ in range(3):
+                    g.search_ann_batch(aq, KB)
+                g.profile_read()
+                reps = 30
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    g.search_ann_batch(aq, KB)
+                host_ms = (time.perf_counter() - t0) * 1e3 / reps
+                kms, _ = g.profile_read()
+                kernel_ms = float(np.mean(kms)) if len(kms) else float("nan")
+                for _ in range(3):
+                    g.search_ann_batch(aq[:1], KB)
+                g.profile_read()
+                t0 = time.perf_counter()
+                for i in range(100):
+                    g.search_ann_batch(aq[i % BATCH:i % BATCH + 1], KB)
+                b1_host = (time.perf_counter() - t0) * 1e3 / 100
+                k1, _ = g.profile_read()
+                nbytes = float(st_a[:, 1].sum()) * DIM * 2
+                beams["beam_%d" % KB] = dict(
+                    recall_at_10_vs_exact=hits / float(cnt_e.sum()),
+                    batch256=dict(kernel_ms=kernel_ms, queries_per_s_kernel=BATCH / (kernel_ms * 1e-3), host_api_ms=host_ms,
+                                  queries_per_s_host_api=BATCH / (host_ms * 1e-3)),
+                    batch1=dict(kernel_ms=float(np.mean(k1)) if len(k1) else None, host_api_ms=b1_host),
+                    nodes_expanded_per_query=float(st_a[:, 0].mean()), distance_evals_per_query=float(st_a[:, 1].mean()),
+                    roofline=dict(bound="hbm (random 768-byte row reads, latency-bound per query)", algorithmic_bytes_per_step=nbytes,
+                                  achieved=nbytes / (kernel_ms * 1e-3) / 1e9, peak=peaks()[0], unit="GB/s",
+                                  frac=nbytes / (kernel_ms * 1e-3) / 1e9 / peaks()[0]))
+            g.set_profiling(False)
+            ann_res = dict(rows=ann_rows, corpus="unit vectors on a %d-dimensional manifold (z A + noise), fp16" % latent,
+                           max_degree=32, search_list_size=75, alpha=1.2, build_s=build_s, **beams,
+                           exact_sweep_same_store_batch256_host_api_ms=exact_ms, retries=g.ann_stats()[1],
                            kernel="ann_search_kernel (one warp per query; result == the reference's greedy_search on the same graph)")
             g.close()
         except Exception as ex:  # the headline line must still print

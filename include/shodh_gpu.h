@@ -117,6 +117,9 @@ SG_API int sg_store_get_vectors(sg_store *s, uint64_t first, uint64_t n, float *
  * reference built; the exact sweep ignores it.  The store's dim and metric must equal the file's.
  * verify_checksum != 0 checks the FNV-1a-64 checksum like the reference does (:303-312). */
 SG_API int sg_store_load_vama(sg_store *s, const char *path, int verify_checksum);
+/* VamanaIndex::save_to_file (vamana_persist.rs:175-280): the store (rows upcast to f32, deleted ids, graph and
+ * medoid if it has them, else empty lists) written as a VAMA v1 file the reference's load_from_file accepts. */
+SG_API int sg_store_save_vama(sg_store *s, const char *path);
 /* header / layout of a VAMA file without touching a GPU (host-side parser only) */
 SG_API int sg_vama_inspect(const char *path, int verify_checksum, uint64_t *num_vectors_out, uint32_t *dimension_out,
                            uint32_t *deleted_count_out, uint32_t *metric_out, uint64_t *vectors_offset_out);

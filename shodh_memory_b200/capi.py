@@ -84,6 +84,7 @@ def lib() -> C.CDLL:
     L.sg_store_dim.argtypes = [vp, u32p]
     L.sg_store_get_vectors.argtypes = [vp, C.c_uint64, C.c_uint64, f32p]
     L.sg_store_load_vama.argtypes = [vp, C.c_char_p, C.c_int]
+    L.sg_store_save_vama.argtypes = [vp, C.c_char_p]
     L.sg_vama_inspect.argtypes = [C.c_char_p, C.c_int, u64p, u32p, u32p, u32p, u64p]
     L.sg_store_set_order.argtypes = [vp, C.c_int]
     L.sg_store_set_id_base.argtypes = [vp, C.c_uint32]

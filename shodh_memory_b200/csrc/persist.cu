@@ -238,4 +238,100 @@ int sg_store_load_vama(sg_store *s, const char *path, int verify_checksum)
     return rc;
 }
 
+
+int sg_store_save_vama(sg_store *s, const char *path)
+{
+    if (!s || !path) return SG_ERR_INVALID;
+    uint64_t n = 0, graph_len = 0, n_deleted = 0;
+    uint32_t dim = 0, max_degree = 0, medoid = 0;
+    int metric = 0;
+    int rc = sg_store_len(s, &n);
+    if (rc == SG_OK) rc = sg_store_dim(s, &dim);
+    if (rc == SG_OK) rc = sg_store_metric(s, &metric);
+    if (rc == SG_OK) rc = sg_store_graph_info(s, &max_degree, &medoid, &graph_len);
+    if (rc == SG_OK) rc = sg_store_deleted_count(s, &n_deleted);
+    if (rc != SG_OK) return rc;
+    if (metric > 2) {
+        sg::set_error("metric %d has no DistanceMetric value in the VAMA header", metric);
+        return SG_ERR_UNSUPPORTED;
+    }
+    std::vector<uint32_t> deg(n, 0), nbr;
+    if (graph_len) {
+        if (graph_len != n) {
+            sg::set_error("the graph covers %llu of %llu rows", (unsigned long long)graph_len, (unsigned long long)n);
+            return SG_ERR_INVALID;
+        }
+        nbr.resize((size_t)n * max_degree);
+        if ((rc = sg_store_get_graph(s, deg.data(), nbr.data(), n)) != SG_OK) return rc;
+    } else {
+        max_degree = 32;   // VamanaConfig::default; every list is empty
+    }
+    FILE *f = fopen(path, "wb+");
+    if (!f) {
+        sg::set_error("cannot create %s", path);
+        return SG_ERR_INVALID;
+    }
+    uint64_t hash = 0xcbf29ce484222325ull;
+    uint64_t off = 64;
+    bool io_ok = true;
+    auto put = [&](const void *p, size_t bytes) {
+        const uint8_t *b = static_cast<const uint8_t *>(p);
+        for (size_t i = 0; i < bytes; ++i) {
+            hash ^= b[i];
+            hash *= 0x100000001b3ull;
+        }
+        io_ok = io_ok && fwrite(p, 1, bytes, f) == bytes;
+        off += bytes;
+    };
+    uint8_t h[64];
+    memset(h, 0, sizeof(h));
+    io_ok = fwrite(h, 1, 64, f) == 64;                      // header placeholder, rewritten with the checksum
+    uint32_t n_del_written = 0;
+    for (uint64_t id = 0; id < n && n_deleted; ++id) {      // deleted ids (ascending; the reference's set order is arbitrary)
+        int d = 0;
+        if ((rc = sg_store_is_deleted(s, (uint32_t)id, &d)) != SG_OK) break;
+        if (d) {
+            const uint32_t v = (uint32_t)id;
+            put(&v, 4);
+            ++n_del_written;
+        }
+    }
+    for (uint64_t i = 0; i < n && rc == SG_OK; ++i) {       // graph: u16 count + u32 ids
+        const uint16_t c = (uint16_t)deg[i];
+        put(&c, 2);
+        if (c) put(nbr.data() + i * max_degree, (size_t)c * 4);
+    }
+    const uint8_t zeros[64] = {0};
+    if (off % 64) put(zeros, 64 - off % 64);                // vectors start 64-byte aligned (:212-215)
+    const size_t rows_per = dim ? ((size_t)32 << 20) / ((size_t)dim * 4) : 0;
+    std::vector<float> chunk(rows_per * dim);
+    for (uint64_t done = 0; done < n && rc == SG_OK && rows_per;) {
+        const size_t m = n - done < rows_per ? (size_t)(n - done) : rows_per;
+        rc = sg_store_get_vectors(s, done, m, chunk.data());
+        if (rc == SG_OK) put(chunk.data(), m * dim * 4);
+        done += m;
+    }
+    if (rc == SG_OK) {
+        memcpy(h, "VAMA", 4);
+        const uint32_t version = 1;
+        const uint64_t inc = 0;
+        memcpy(h + 4, &version, 4);
+        memcpy(h + 8, &n, 8);
+        memcpy(h + 16, &dim, 4);
+        memcpy(h + 20, &max_degree, 4);
+        memcpy(h + 24, &medoid, 4);
+        h[28] = (uint8_t)metric;
+        memcpy(h + 29, &n_del_written, 4);
+        memcpy(h + 33, &inc, 8);
+        memcpy(h + 41, &hash, 8);
+        io_ok = io_ok && fseek(f, 0, SEEK_SET) == 0 && fwrite(h, 1, 64, f) == 64;
+    }
+    io_ok = (fclose(f) == 0) && io_ok;
+    if (rc == SG_OK && !io_ok) {
+        sg::set_error("writing %s failed", path);
+        rc = SG_ERR_INVALID;
+    }
+    return rc;
+}
+
 }  // extern "C"

@@ -85,11 +85,12 @@ SG_DEVICE_INLINE float finish_distance(float s, float qn2, float rn2)
 }
 
 
-// One (query, row) distance with the row read straight from global memory by ONE thread, 16 bytes at
-// a time, in the reference's order (the graph kernels score <= 32 scattered rows per step: one row per
-// lane, the query broadcast from shared memory).  q_s: the query as f32 in shared memory.
-template <bool F16, int ORDER, int METRIC>
-SG_DEVICE_INLINE float row_distance(const void *rows, uint32_t dim, uint64_t row, const float *q_s, float qn2)
+// One (query, row) distance computed by ONE thread from a row it reads 16 bytes at a time, in the
+// reference's order (the graph kernels score <= 32 scattered rows per step: one row per lane, the query
+// broadcast from shared memory).  row_ptr: the row in global memory (LDG = true, read-only path) or staged
+// in shared memory (LDG = false).  q_s: the query as f32 in shared memory.
+template <bool F16, int ORDER, int METRIC, bool LDG>
+SG_DEVICE_INLINE float row_distance_ptr(const void *row_ptr, uint32_t dim, const float *q_s, float qn2)
 {
     constexpr int NACC = (ORDER == SG_ORDER_AVX2) ? 8 : 1;
     constexpr bool ROWNORM = (METRIC == SG_METRIC_COSINE || METRIC == SG_METRIC_COSINE_SIM);
@@ -97,11 +98,13 @@ SG_DEVICE_INLINE float row_distance(const void *rows, uint32_t dim, uint64_t row
 #pragma unroll
     for (int t = 0; t < NACC; ++t) acc[t] = racc[t] = 0.0f;
     if constexpr (F16) {
-        const uint4 *p = reinterpret_cast<const uint4 *>(static_cast<const __half *>(rows) + row * dim);
+        const uint4 *p = static_cast<const uint4 *>(row_ptr);
         const uint32_t nchunk = dim >> 3;
 #pragma unroll 8
         for (uint32_t c = 0; c < nchunk; ++c) {
-            uint4 v = __ldg(p + c);
+            uint4 v;
+            if constexpr (LDG) v = __ldg(p + c);
+            else v = p[c];
             float x[8];
             float2 f;
             f = __half22float2(*reinterpret_cast<__half2 *>(&v.x)); x[0] = f.x; x[1] = f.y;
@@ -118,11 +121,18 @@ SG_DEVICE_INLINE float row_distance(const void *rows, uint32_t dim, uint64_t row
             accum4<ORDER, METRIC>(acc, qb, x[4], x[5], x[6], x[7], 4);
         }
     } else {
-        const float4 *p = reinterpret_cast<const float4 *>(static_cast<const float *>(rows) + row * dim);
+        const float4 *p = static_cast<const float4 *>(row_ptr);
         const uint32_t nchunk = dim >> 3;           // two float4 per step keeps the AVX lane group a constant
 #pragma unroll 4
         for (uint32_t c = 0; c < nchunk; ++c) {
-            const float4 v0 = __ldg(p + 2 * c), v1 = __ldg(p + 2 * c + 1);
+            float4 v0, v1;
+            if constexpr (LDG) {
+                v0 = __ldg(p + 2 * c);
+                v1 = __ldg(p + 2 * c + 1);
+            } else {
+                v0 = p[2 * c];
+                v1 = p[2 * c + 1];
+            }
             const float4 qa = *reinterpret_cast<const float4 *>(q_s + c * 8);
             const float4 qb = *reinterpret_cast<const float4 *>(q_s + c * 8 + 4);
             if constexpr (ROWNORM) {
@@ -136,6 +146,13 @@ SG_DEVICE_INLINE float row_distance(const void *rows, uint32_t dim, uint64_t row
     float rn2 = 0.0f;
     if constexpr (ROWNORM) rn2 = hsum<ORDER>(racc);
     return finish_distance<METRIC>(hsum<ORDER>(acc), qn2, rn2);
+}
+
+template <bool F16, int ORDER, int METRIC>
+SG_DEVICE_INLINE float row_distance(const void *rows, uint32_t dim, uint64_t row, const float *q_s, float qn2)
+{
+    const uint8_t *p = static_cast<const uint8_t *>(rows) + row * dim * (F16 ? 2 : 4);
+    return row_distance_ptr<F16, ORDER, METRIC, true>(p, dim, q_s, qn2);
 }
 
 // |v|^2 of an f32 vector in shared memory, in the order of l2_norm_squared_*_inline (== dot(v, v))

@@ -138,6 +138,11 @@ __host__ __device__ inline size_t ann_warp_smem_bytes(uint32_t dim, uint32_t K)
     const size_t cap = (size_t)K + 32;   // every piece a multiple of 16 bytes: the query is read as float4
     return (((size_t)dim * 4 + 15) & ~(size_t)15) + ((cap * 8 + 15) & ~(size_t)15) + ((cap + 15) & ~(size_t)15);
 }
+// staging buffer of the beam search: 32 rows, each padded by 16 bytes (conflict-free lane-per-row reads)
+__host__ __device__ inline size_t ann_stage_smem_bytes(uint32_t dim, bool f16)
+{
+    return (size_t)32 * ((size_t)dim * (f16 ? 2 : 4) + 16);
+}
 cudaError_t launch_ann_search(const AnnArgs &a, bool f16, int order, int metric, cudaStream_t st);
 cudaError_t launch_graph_link(const void *rows, bool f16, int order, int metric, uint32_t dim, uint32_t *graph, uint32_t gs,
                               uint32_t id, const uint32_t *res_ids, const uint32_t *res_count, cudaStream_t st);

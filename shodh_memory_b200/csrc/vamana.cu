@@ -21,6 +21,8 @@
 // `w.len() < k || dist < w.peek().distance` test evaluated against the list as it evolves.
 // Random 768-byte row reads: latency-bound per query, so throughput comes from many queries in
 // flight (4 warps per CTA, all SMs).  Algorithmic bytes = distance evaluations x row bytes.
+#include <cstdlib>
+
 #include "sg_internal.h"
 #include "sg_dist.cuh"
 
@@ -70,7 +72,21 @@ SG_DEVICE_INLINE void load_row_f32(const void *rows, uint32_t dim, uint64_t row,
     }
 }
 
-template <bool F16, int ORDER, int METRIC>
+// 16-byte asynchronous copy global -> shared (LDGSTS), L2 only
+SG_DEVICE_INLINE void cp_async16(void *dst_smem, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+SG_DEVICE_INLINE void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// STAGE: the <= 32 rows of a step are first copied into shared memory with cp.async -- every 16-byte piece of
+// every row in flight at once, one HBM round trip per step -- and each lane then walks ITS row out of shared
+// memory (rows padded by 16 bytes: conflict-free).  Without STAGE (rows too long for shared memory) each lane
+// reads its row straight from global memory, eight 16-byte loads at a time.
+template <bool F16, int ORDER, int METRIC, bool STAGE>
 __global__ void __launch_bounds__(128)
 ann_search_kernel(const AnnArgs a)
 {
@@ -79,10 +95,12 @@ ann_search_kernel(const AnnArgs a)
     const uint32_t q = blockIdx.x * W + warp;
     if (q >= a.nq) return;                       // warps are independent: no block-wide barrier anywhere
     const uint32_t dim = a.dim, K = a.K, CAP = K + ANN_SLACK;
-    uint8_t *base = smem + (size_t)warp * ann_warp_smem_bytes(dim, K);
+    uint8_t *base = smem + (size_t)warp * (ann_warp_smem_bytes(dim, K) + (STAGE ? ann_stage_smem_bytes(dim, F16) : 0));
     float *q_s = reinterpret_cast<float *>(base);
     uint64_t *P = reinterpret_cast<uint64_t *>(base + align16((size_t)dim * 4));
     uint8_t *ex = reinterpret_cast<uint8_t *>(P) + align16((size_t)CAP * 8);
+    uint8_t *rowbuf = base + ann_warp_smem_bytes(dim, K);          // STAGE: [32][row_bytes + 16]
+    const uint32_t row_bytes = dim * (F16 ? 2u : 4u), pitch = row_bytes + 16;
 
     if (a.query_rows) {
         load_row_f32<F16>(a.rows, dim, a.query_rows[q], q_s, lane);
@@ -144,7 +162,22 @@ ann_search_kernel(const AnnArgs a)
             evals += __popc(newmask);
             if (vis_count > (a.H >> 1)) flag |= 1u;                       // visited table half full: stop admitting ids
             float d = 0.0f;
-            if (isnew) d = row_distance<F16, ORDER, METRIC>(a.rows, dim, nb, q_s, qn2);
+            if constexpr (STAGE) {
+                uint32_t m = newmask;
+                while (m) {                                               // row j -> rowbuf[j], a warp-wide coalesced copy each
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t rj = __shfl_sync(FULL, nb, j);
+                    const uint8_t *src = static_cast<const uint8_t *>(a.rows) + (size_t)rj * row_bytes;
+                    for (uint32_t c = lane * 16; c < row_bytes; c += 512) cp_async16(rowbuf + (size_t)j * pitch + c, src + c);
+                }
+                cp_async_wait_all();
+                __syncwarp();
+                if (isnew) d = row_distance_ptr<F16, ORDER, METRIC, false>(rowbuf + (size_t)lane * pitch, dim, q_s, qn2);
+                __syncwarp();                                             // rowbuf is reused by the next chunk / step
+            } else {
+                if (isnew) d = row_distance<F16, ORDER, METRIC>(a.rows, dim, nb, q_s, qn2);
+            }
             // a lane whose distance already fails `dist < w.peek()` on a full w can never pass later
             // (the k-th distance only falls): drop it before the sequential part
             bool cand = isnew;
@@ -590,11 +623,20 @@ template <bool F16, int ORDER, int METRIC>
 cudaError_t launch_ann_t(const AnnArgs &a, cudaStream_t st)
 {
     const uint32_t W = 4;
-    const size_t smem = (size_t)W * ann_warp_smem_bytes(a.dim, a.K);
-    auto kern = ann_search_kernel<F16, ORDER, METRIC>;
-    cudaError_t e = set_smem(kern, smem);
-    if (e != cudaSuccess) return e;
-    kern<<<(a.nq + W - 1) / W, W * 32, smem, st>>>(a);
+    const size_t plain = (size_t)W * ann_warp_smem_bytes(a.dim, a.K);
+    const size_t staged = plain + (size_t)W * ann_stage_smem_bytes(a.dim, F16);
+    static const bool no_stage = getenv("SG_ANN_NO_STAGE") != nullptr;
+    if (staged <= 200 * 1024 && !no_stage) {
+        auto kern = ann_search_kernel<F16, ORDER, METRIC, true>;
+        cudaError_t e = set_smem(kern, staged);
+        if (e != cudaSuccess) return e;
+        kern<<<(a.nq + W - 1) / W, W * 32, staged, st>>>(a);
+    } else {
+        auto kern = ann_search_kernel<F16, ORDER, METRIC, false>;
+        cudaError_t e = set_smem(kern, plain);
+        if (e != cudaSuccess) return e;
+        kern<<<(a.nq + W - 1) / W, W * 32, plain, st>>>(a);
+    }
     count_launch();
     return cudaGetLastError();
 }

@@ -111,6 +111,10 @@ class GpuVectorStore:
         """VamanaIndex::load_from_file: the reference's "VAMA" v1 file -> this (empty) store."""
         capi.check(capi.lib().sg_store_load_vama(self._h, path.encode(), int(verify_checksum)))
 
+    def save_to_file(self, path: str) -> None:
+        """VamanaIndex::save_to_file: rows, deleted ids, graph + medoid -> a "VAMA" v1 file."""
+        capi.check(capi.lib().sg_store_save_vama(self._h, path.encode()))
+
     def set_order(self, order: str) -> None:
         capi.check(capi.lib().sg_store_set_order(
             self._h, capi.SG_ORDER_AVX2 if order == "avx2" else capi.SG_ORDER_SCALAR))

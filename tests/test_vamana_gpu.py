@@ -263,3 +263,35 @@ def test_vama_file_with_graph_is_searched_as_the_reference_would(sg, oracle, tmp
         rid, rdist = V.search(q[i], 10)
         assert np.array_equal(ids[i, :counts[i]], rid) and np.array_equal(bits(dist[i, :counts[i]]), bits(rdist))
     st.close()
+
+
+def test_save_to_file_round_trip(sg, oracle, tmp_path):
+    """vamana_persist.rs:175-280 / :415-470 (save, load, search gives the same results)"""
+    dim, R = 128, 12
+    x = oracle.manifold_corpus(51, 1500, dim)
+    st = sg.GpuVectorStore(dim, "f16")
+    st.add_vectors(x)
+    st.build_graph(max_degree=R, search_list_size=30)
+    st.mark_deleted(11)
+    st.mark_deleted(900)
+    p = str(tmp_path / "saved.idx")
+    st.save_to_file(p)
+    info = sg.vama_inspect(p)                                          # header + checksum verify
+    assert info["num_vectors"] == 1500 and info["dimension"] == dim and info["deleted_count"] == 2 and info["metric"] == 0
+    raw = open(p, "rb").read()
+    assert raw[:4] == b"VAMA" and struct.unpack_from("<I", raw, 20)[0] == R
+    assert struct.unpack_from("<I", raw, 24)[0] == st.graph_info()["medoid"]
+    assert list(struct.unpack_from("<2I", raw, 64)) == [11, 900]
+    vec = np.frombuffer(raw, "<f4", 1500 * dim, info["vectors_offset"]).reshape(1500, dim)
+    assert np.array_equal(bits(vec), bits(oracle.round_f16(x)))
+    st2 = sg.GpuVectorStore(dim, "f16")
+    st2.load_from_file(p)
+    d1, n1, m1 = st.get_graph()
+    d2, n2, m2 = st2.get_graph()
+    assert m1 == m2 and np.array_equal(d1, d2) and np.array_equal(n1, n2) and st2.deleted_count() == 2
+    q = queries_near(x, 16, 3, noise=0.02)
+    a = st.search_ann_batch(q, 10)
+    b = st2.search_ann_batch(q, 10)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(bits(a[1]), bits(b[1]))
+    st.close()
+    st2.close()
