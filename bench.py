@@ -486,7 +486,27 @@ def main():
                                   achieved=nbytes / (kernel_ms * 1e-3) / 1e9, peak=peaks()[0], unit="GB/s",
                                   frac=nbytes / (kernel_ms * 1e-3) / 1e9 / peaks()[0]))
             g.set_profiling(False)
-            ann_res = dict(rows=ann_rows, corpus="unit vectors on a %d-dimensional manifold (z A + noise), fp16" % latent,
+            # the reference's greedy_search on the host, same graph, same queries (oracle port, ONE thread), and
+            # an id-for-id check of the device answers against it
+            cpu_graph = None
+            try:
+                from oracle import oracle as o
+                deg, nbr, medoid = g.get_graph()
+                V = o.VamanaOracle(DIM, max_degree=32, search_list_size=75)
+                V.set_graph(g.get_vectors(0, ann_rows), deg, np.where(nbr == 0xFFFFFFFF, 0, nbr), medoid)
+                cpu_graph = {}
+                for KB in (12 * TOPK, 4 * TOPK):
+                    ids_a, _, cnt_a, _ = g.search_ann_batch(aq[:64], KB)
+                    t0 = time.perf_counter()
+                    ref = [V.search(aq[i], KB)[0] for i in range(64)]
+                    ms = (time.perf_counter() - t0) * 1e3 / 64
+                    same = all(np.array_equal(ids_a[i, :cnt_a[i]], ref[i]) for i in range(64))
+                    cpu_graph["beam_%d" % KB] = dict(ms_per_query_1_thread=ms, ids_identical_to_device=bool(same))
+                cpu_graph["kind"] = "port (oracle/vamana_oracle.c restatement of greedy_search), 64 queries, 1 thread"
+                del V
+            except Exception as ex:
+                cpu_graph = dict(error=repr(ex))
+            ann_res = dict(cpu_reference=cpu_graph, rows=ann_rows, corpus="unit vectors on a %d-dimensional manifold (z A + noise), fp16" % latent,
                            max_degree=32, search_list_size=75, alpha=1.2, build_s=build_s, **beams,
                            exact_sweep_same_store_batch256_host_api_ms=exact_ms, retries=g.ann_stats()[1],
                            kernel="ann_search_kernel (one warp per query; result == the reference's greedy_search on the same graph)")

@@ -237,6 +237,10 @@ SG_API int sg_store_search_ann(sg_store *s, const float *queries_f32, uint32_t b
 SG_API int sg_store_search_ann_device(sg_store *s, const float *d_queries_f32, uint32_t b, uint32_t k, uint32_t *d_ids_out,
                                       float *d_dist_out, uint32_t *d_counts_out, uint32_t *d_flags, void *cuda_stream);
 SG_API int sg_store_ann_stats(sg_store *s, uint64_t *queries_out, uint64_t *retries_out);
+/* profiling hook: cycles_out[0..5) (may be NULL) = SM cycles the beam-search warps spent, summed over all queries
+ * since the last call, in: pop, list read + visited set, row fetch, scoring, insertion.  enable != 0 keeps
+ * counting (a clock64 read per phase), 0 switches it off. */
+SG_API int sg_store_ann_phase_cycles(sg_store *s, int enable, uint64_t *cycles_out);
 
 /* CUDA-event timing of the scan kernel(s) inside each search (bench.py roofline): with
  * profiling on, every search records an event pair around its sweep launches on the stream

@@ -113,6 +113,7 @@ def lib() -> C.CDLL:
     L.sg_store_search_ann.argtypes = [vp, f32p, C.c_uint32, C.c_uint32, u32p, f32p, u32p, u64p]
     L.sg_store_search_ann_device.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp]
     L.sg_store_ann_stats.argtypes = [vp, u64p, u64p]
+    L.sg_store_ann_phase_cycles.argtypes = [vp, C.c_int, u64p]
     L.sg_store_profile_read.argtypes = [vp, f32p, C.c_uint32, u32p, u32p]
     i64p = C.POINTER(C.c_int64)
     L.sg_encoder_create.argtypes = [C.POINTER(vp), C.c_int, C.c_char_p]

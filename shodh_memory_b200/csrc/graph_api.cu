@@ -113,6 +113,7 @@ int ann_launch(sg_store *s, const float *d_q, const uint32_t *d_query_rows, uint
         a.counts_out = d_counts + done;
         a.flags = d_flags ? d_flags + done : nullptr;
         a.stats = d_stats ? d_stats + 2 * (size_t)done : nullptr;
+        a.phase = s->d_ann_phase;
         cudaError_t e = launch_ann_search(a, s->dtype == SG_DTYPE_F16, s->order, s->metric, st);
         if (e != cudaSuccess) {
             set_error("graph search launch failed: %s", cudaGetErrorString(e));
@@ -153,6 +154,7 @@ void graph_free(sg_store *s)
     cudaFree(s->d_ann_stats);
     cudaFree(s->d_g32);
     cudaFree(s->d_gf32);
+    cudaFree(s->d_ann_phase);
     s->d_graph = nullptr;
     s->d_vis = nullptr;
 }
@@ -507,6 +509,26 @@ int sg_store_search_ann(sg_store *s, const float *queries, uint32_t b, uint32_t 
     memcpy(dist_out, h_dist, rbytes);
     memcpy(counts_out, h_cnt, cbytes);
     if (stats_out) memcpy(stats_out, h_stats, sbytes);
+    return SG_OK;
+}
+
+int sg_store_ann_phase_cycles(sg_store *s, int enable, uint64_t *cycles_out)
+{
+    if (!s) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    SG_CUDA_TRY(cudaSetDevice(s->device));
+    if (s->d_ann_phase && cycles_out) {
+        SG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+        SG_CUDA_TRY(cudaMemcpy(cycles_out, s->d_ann_phase, 8 * 8, cudaMemcpyDeviceToHost));
+    } else if (cycles_out) {
+        memset(cycles_out, 0, 8 * 8);
+    }
+    if (enable && !s->d_ann_phase) SG_CUDA_TRY(cudaMalloc(&s->d_ann_phase, 8 * 8));
+    if (!enable && s->d_ann_phase) {
+        cudaFree(s->d_ann_phase);
+        s->d_ann_phase = nullptr;
+    }
+    if (s->d_ann_phase) SG_CUDA_TRY(cudaMemset(s->d_ann_phase, 0, 8 * 8));
     return SG_OK;
 }
 

@@ -131,17 +131,19 @@ struct AnnArgs {
     uint32_t *ids_out; float *dist_out; uint32_t *counts_out;   // [nq][k_out], [nq][k_out], [nq]
     uint32_t *flags;             // [nq] or null: bit 0 = visited table filled up (result incomplete), bit 1 = > 32 ties dropped
     unsigned long long *stats;   // [nq][2] or null: nodes expanded, distance evaluations
+    unsigned long long *phase;   // [8] or null: SM cycles per phase summed over queries (profiling hook)
 };
-// shared memory per query warp: query f32 + the sorted list (K + 32 keys) + expanded flags
+// shared memory per query warp: query f32 + two copies of the sorted list (K + 32 keys + expanded flags each:
+// the batched merge writes the new list beside the old one) + 32 candidate keys
 __host__ __device__ inline size_t ann_warp_smem_bytes(uint32_t dim, uint32_t K)
 {
     const size_t cap = (size_t)K + 32;   // every piece a multiple of 16 bytes: the query is read as float4
-    return (((size_t)dim * 4 + 15) & ~(size_t)15) + ((cap * 8 + 15) & ~(size_t)15) + ((cap + 15) & ~(size_t)15);
+    return (((size_t)dim * 4 + 15) & ~(size_t)15) + 2 * (((cap * 8 + 15) & ~(size_t)15) + ((cap + 15) & ~(size_t)15)) + 256;
 }
 // staging buffer of the beam search: 32 rows, each padded by 16 bytes (conflict-free lane-per-row reads)
 __host__ __device__ inline size_t ann_stage_smem_bytes(uint32_t dim, bool f16)
 {
-    return (size_t)32 * ((size_t)dim * (f16 ? 2 : 4) + 16);
+    return (size_t)32 * ((size_t)dim * (f16 ? 2 : 4) + 16) + 16;   // + the warp's mbarrier
 }
 cudaError_t launch_ann_search(const AnnArgs &a, bool f16, int order, int metric, cudaStream_t st);
 cudaError_t launch_graph_link(const void *rows, bool f16, int order, int metric, uint32_t dim, uint32_t *graph, uint32_t gs,

@@ -64,6 +64,7 @@ struct sg_store {
     uint32_t *d_g32 = nullptr; size_t g32_cap = 0;         // build / insert scratch (u32)
     float *d_gf32 = nullptr; size_t gf32_cap = 0;          // build / insert scratch (f32)
     uint64_t ann_searches = 0, ann_retries = 0;
+    unsigned long long *d_ann_phase = nullptr;             // profiling hook: cycles per phase of the beam search
 
     bool profiling = false;
     std::vector<cudaEvent_t> ev;  // pairs: ev[2i] before, ev[2i+1] after the sweep launches of search i

@@ -72,19 +72,18 @@ SG_DEVICE_INLINE void load_row_f32(const void *rows, uint32_t dim, uint64_t row,
     }
 }
 
-// 16-byte asynchronous copy global -> shared (LDGSTS), L2 only
-SG_DEVICE_INLINE void cp_async16(void *dst_smem, const void *src)
+// one whole row global -> shared by the TMA engine (cp.async.bulk, SASS UBLKCP), completion on an mbarrier
+SG_DEVICE_INLINE void bulk_row_load(void *dst_smem, const void *src, uint32_t bytes, uint32_t bar)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
 }
-SG_DEVICE_INLINE void cp_async_wait_all()
-{
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
+SG_DEVICE_INLINE void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// STAGE: the <= 32 rows of a step are first copied into shared memory with cp.async -- every 16-byte piece of
-// every row in flight at once, one HBM round trip per step -- and each lane then walks ITS row out of shared
-// memory (rows padded by 16 bytes: conflict-free).  Without STAGE (rows too long for shared memory) each lane
+// STAGE: the <= 32 rows of a step are first copied into shared memory by the TMA engine -- each lane issues ONE
+// bulk copy for its row, all rows in flight at once behind one mbarrier, one HBM round trip per step -- and
+// each lane then walks ITS row out of shared memory (rows padded by 16 bytes: conflict-free).  Without STAGE (rows too long for shared memory) each lane
 // reads its row straight from global memory, eight 16-byte loads at a time.
 template <bool F16, int ORDER, int METRIC, bool STAGE>
 __global__ void __launch_bounds__(128)
@@ -97,10 +96,22 @@ ann_search_kernel(const AnnArgs a)
     const uint32_t dim = a.dim, K = a.K, CAP = K + ANN_SLACK;
     uint8_t *base = smem + (size_t)warp * (ann_warp_smem_bytes(dim, K) + (STAGE ? ann_stage_smem_bytes(dim, F16) : 0));
     float *q_s = reinterpret_cast<float *>(base);
+    const size_t list_bytes = align16((size_t)CAP * 8) + align16((size_t)CAP);
     uint64_t *P = reinterpret_cast<uint64_t *>(base + align16((size_t)dim * 4));
     uint8_t *ex = reinterpret_cast<uint8_t *>(P) + align16((size_t)CAP * 8);
+    uint64_t *P2 = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(P) + list_bytes);   // the merge's output list
+    uint8_t *ex2 = reinterpret_cast<uint8_t *>(P2) + align16((size_t)CAP * 8);
+    uint64_t *Cs = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(P2) + list_bytes);  // [32] candidate keys
     uint8_t *rowbuf = base + ann_warp_smem_bytes(dim, K);          // STAGE: [32][row_bytes + 16]
     const uint32_t row_bytes = dim * (F16 ? 2u : 4u), pitch = row_bytes + 16;
+    const uint32_t bar = smem_u32(rowbuf + (size_t)32 * pitch);   // STAGE: the warp's mbarrier
+    uint32_t bar_phase = 0;
+    if constexpr (STAGE) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            mbar_fence_init();
+        }
+    }
 
     if (a.query_rows) {
         load_row_f32<F16>(a.rows, dim, a.query_rows[q], q_s, lane);
@@ -127,6 +138,16 @@ ann_search_kernel(const AnnArgs a)
     }
     uint32_t pn = 1;
     __syncwarp();
+    // profiling hook: cycles per phase (0 pop, 1 list read + visited set, 2 row fetch, 3 scoring, 4 insertion)
+    const bool prof = a.phase != nullptr;
+    long long ph[5] = {0, 0, 0, 0, 0}, tprev = prof ? clock64() : 0;
+    auto mark = [&](int i) {
+        if (prof) {
+            const long long t = clock64();
+            ph[i] += t - tprev;
+            tprev = t;
+        }
+    };
 
     for (;;) {
         // candidates.pop(): the first entry of P that has not been expanded
@@ -149,6 +170,7 @@ ann_search_kernel(const AnnArgs a)
         const uint32_t cid = (uint32_t)ckey;
         if (cid >= a.graph_len) continue;                                                                // :606-609
         ++hops;
+        mark(0);
         for (uint32_t c0 = 0; c0 < a.gs; c0 += 32) {
             uint32_t nb = NONE;
             if (c0 + lane < a.gs) nb = a.graph[(size_t)cid * a.gs + c0 + lane];
@@ -157,32 +179,109 @@ ann_search_kernel(const AnnArgs a)
             bool isnew = false;
             if (valid && (uint32_t)(__ffs(same) - 1) == lane && !(flag & 1u)) isnew = vis_insert(vis, hmask, nb);
             const uint32_t newmask = __ballot_sync(FULL, isnew);
+            mark(1);
             if (!newmask) continue;
             vis_count += __popc(newmask);
             evals += __popc(newmask);
             if (vis_count > (a.H >> 1)) flag |= 1u;                       // visited table half full: stop admitting ids
             float d = 0.0f;
             if constexpr (STAGE) {
-                uint32_t m = newmask;
-                while (m) {                                               // row j -> rowbuf[j], a warp-wide coalesced copy each
-                    const int j = __ffs(m) - 1;
-                    m &= m - 1;
-                    const uint32_t rj = __shfl_sync(FULL, nb, j);
-                    const uint8_t *src = static_cast<const uint8_t *>(a.rows) + (size_t)rj * row_bytes;
-                    for (uint32_t c = lane * 16; c < row_bytes; c += 512) cp_async16(rowbuf + (size_t)j * pitch + c, src + c);
-                }
-                cp_async_wait_all();
+                if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)__popc(newmask) * row_bytes);
                 __syncwarp();
+                if (isnew)
+                    bulk_row_load(rowbuf + (size_t)lane * pitch, static_cast<const uint8_t *>(a.rows) + (size_t)nb * row_bytes,
+                                  row_bytes, bar);
+                mbar_wait(bar, bar_phase);
+                bar_phase ^= 1;
+                mark(2);
                 if (isnew) d = row_distance_ptr<F16, ORDER, METRIC, false>(rowbuf + (size_t)lane * pitch, dim, q_s, qn2);
                 __syncwarp();                                             // rowbuf is reused by the next chunk / step
             } else {
                 if (isnew) d = row_distance<F16, ORDER, METRIC>(a.rows, dim, nb, q_s, qn2);
+            }
+            mark(3);
+            {
+                // the node most likely to be expanded next is the better of the first unexpanded entry of P and
+                // the best new row: start pulling its neighbour list into L2 while the insertion runs
+                uint64_t best = isnew ? make_key(order_key32(d), nb) : KEY_SENTINEL;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const uint64_t other = __shfl_xor_sync(FULL, best, o);
+                    best = other < best ? other : best;
+                }
+                if (lane == 0 && best != KEY_SENTINEL && (uint32_t)best < a.graph_len)
+                    prefetch_l2(a.graph + (size_t)(uint32_t)best * a.gs);
             }
             // a lane whose distance already fails `dist < w.peek()` on a full w can never pass later
             // (the k-th distance only falls): drop it before the sequential part
             bool cand = isnew;
             if (pn >= K && cand) cand = d < key32_to_dist((uint32_t)(P[K - 1] >> 32));
             uint32_t todo = __ballot_sync(FULL, cand);
+            // Batched merge.  With no float-equal distances in play the sequential rule below is order-independent:
+            // the list after all of this step's candidates is exactly the first K of sorted(P + candidates) (a
+            // candidate inside the union's top K is strictly closer than the K-th it is tested against; one outside
+            // is refused or pushed out and trimmed).  So every entry's new position is computed in parallel --
+            // old index + number of smaller candidates; candidate: lower_bound in P + rank among the candidates --
+            // and scattered into the second list.  Equal distances (next to a new entry, or across the K-th
+            // boundary), NaNs, or a tail of ties already present make the outcome order-dependent: then the new
+            // list is discarded and the candidates go through the sequential path, the reference's rule verbatim.
+            {
+                const uint32_t m = __popc(todo);
+                bool fast = m > 2 && pn <= K;
+                if (fast && __ballot_sync(FULL, cand && d != d)) fast = false;
+                if (fast) {
+                    const float last = key32_to_dist((uint32_t)(P[pn - 1] >> 32));
+                    if (last != last) fast = false;
+                }
+                if (fast) {
+                    const uint32_t total = pn + m, keepN = total < K + 1 ? total : K + 1;
+                    const uint64_t kx = make_key(order_key32(d), nb);
+                    if (cand) Cs[__popc(todo & ((1u << lane) - 1))] = kx;
+                    __syncwarp();
+                    if (cand) {
+                        uint32_t np = 0;
+                        for (uint32_t j = 0; j < m; ++j) np += Cs[j] < kx;
+                        uint32_t lo = 0, hi = pn;
+                        while (lo < hi) {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            if (P[mid] < kx) lo = mid + 1;
+                            else hi = mid;
+                        }
+                        np += lo;
+                        if (np < keepN) {
+                            P2[np] = kx;
+                            ex2[np] = 2;                                  // 2 = entered in this step
+                        }
+                    }
+                    for (uint32_t i = lane; i < pn; i += 32) {
+                        const uint64_t key = P[i];
+                        uint32_t np = i;
+                        for (uint32_t j = 0; j < m; ++j) np += Cs[j] < key;
+                        if (np < keepN) {
+                            P2[np] = key;
+                            ex2[np] = ex[i];
+                        }
+                    }
+                    __syncwarp();
+                    bool tie = false;
+                    for (uint32_t i = lane; i + 1 < keepN; i += 32) {
+                        const float da = key32_to_dist((uint32_t)(P2[i] >> 32)), db = key32_to_dist((uint32_t)(P2[i + 1] >> 32));
+                        if (da == db && (ex2[i] == 2 || ex2[i + 1] == 2 || i == K - 1)) tie = true;
+                    }
+                    if (__ballot_sync(FULL, tie)) {
+                        fast = false;                                     // P is untouched: redo in order
+                    } else {
+                        const uint32_t newpn = total < K ? total : K;
+                        for (uint32_t i = lane; i < newpn; i += 32)
+                            if (ex2[i] == 2) ex2[i] = 0;
+                        uint64_t *tp = P; P = P2; P2 = tp;
+                        uint8_t *te = ex; ex = ex2; ex2 = te;
+                        pn = newpn;
+                        todo = 0;
+                    }
+                    __syncwarp();
+                }
+            }
             while (todo) {                                                // neighbour order == lane order (:612)
                 const int src = __ffs(todo) - 1;
                 todo &= todo - 1;
@@ -232,8 +331,11 @@ ann_search_kernel(const AnnArgs a)
                     }
                 }
             }
+            mark(4);
         }
     }
+    if (prof && lane == 0)
+        for (int i = 0; i < 5; ++i) atomicAdd(a.phase + i, (unsigned long long)ph[i]);
 
     // w, ascending; VamanaIndex::search drops soft-deleted ids and takes k (:798-804)
     const uint32_t wl = pn < K ? pn : K;
@@ -625,8 +727,12 @@ cudaError_t launch_ann_t(const AnnArgs &a, cudaStream_t st)
     const uint32_t W = 4;
     const size_t plain = (size_t)W * ann_warp_smem_bytes(a.dim, a.K);
     const size_t staged = plain + (size_t)W * ann_stage_smem_bytes(a.dim, F16);
+    // Staging buys latency (one HBM round trip per step) and costs occupancy (27 KB per warp at 384-d fp16: 8 warps per
+    // SM).  Measured on 300k x 384: staged 2.2 vs 1.3 Mq/s at 1024 queries, 2.8 vs 3.7 Mq/s at 8192 -- large batches
+    // run unstaged, where ~28 resident warps per SM hide the latency instead (2.9 TB/s of row reads).
     static const bool no_stage = getenv("SG_ANN_NO_STAGE") != nullptr;
-    if (staged <= 200 * 1024 && !no_stage) {
+    static const uint32_t stage_max_q = getenv("SG_ANN_STAGE_MAX_Q") ? (uint32_t)atoi(getenv("SG_ANN_STAGE_MAX_Q")) : 4096u;
+    if (staged <= 200 * 1024 && !no_stage && a.nq < stage_max_q) {
         auto kern = ann_search_kernel<F16, ORDER, METRIC, true>;
         cudaError_t e = set_smem(kern, staged);
         if (e != cudaSuccess) return e;

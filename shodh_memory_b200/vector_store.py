@@ -195,6 +195,12 @@ class GpuVectorStore:
                           stream: int = 0) -> None:
         capi.check(capi.lib().sg_store_search_ann_device(self._h, d_queries, b, k, d_ids, d_dist, d_counts, d_flags, stream))
 
+    def ann_phase_cycles(self, enable: bool = True) -> np.ndarray:
+        """profiling hook -> cycles in (pop, list read + visited set, row fetch, scoring, insertion) since the last call"""
+        out = np.zeros(8, np.uint64)
+        capi.check(capi.lib().sg_store_ann_phase_cycles(self._h, int(enable), _ptr(out, C.c_uint64)))
+        return out[:5]
+
     def ann_stats(self):
         """-> (queries served by the graph search, re-runs with a larger visited table)"""
         a, b = C.c_uint64(), C.c_uint64()

@@ -161,7 +161,10 @@ def test_find_medoid(oracle):
 
 
 # ---- the device kernel's formulation of greedy_search, modelled step by step -------------------------
-def greedy_single_array_py(o, V, query, K, entry, slack=32):
+fast_steps, slow_steps = [0], [0]
+
+
+def greedy_single_array_py(o, V, query, K, entry, slack=32, batched=True):
     """shodh_memory_b200/csrc/vamana.cu::ann_search_kernel in pure Python: ONE sorted array P that is both
     heaps of the reference (w = its first K entries, candidates = its unexpanded entries); entries beyond
     the K-th survive only while they tie the K-th distance.  Must give the reference's result and traversal."""
@@ -190,6 +193,18 @@ def greedy_single_array_py(o, V, query, K, entry, slack=32):
                     evals += 1
             if len(P) >= K:                            # pre-filter against the K-th distance as it stands
                 lanes = [(v, d) for v, d in lanes if d < P[K - 1][1]]
+            # batched merge (the kernel's fast path): with no float-equal distances next to a new entry or across
+            # the K-th boundary, the result of the sequential rule is the first K of sorted(P + candidates)
+            if batched and len(lanes) > 2 and len(P) <= K and not any(np.isnan(d) for _, d in lanes) \
+                    and not np.isnan(P[-1][1]):
+                M = sorted(P + [[tk(d, v), d, v, 2] for v, d in lanes], key=lambda e: e[0])[:K + 1]
+                tie = any(M[i][1] == M[i + 1][1] and (M[i][3] == 2 or M[i + 1][3] == 2 or i == K - 1)
+                          for i in range(len(M) - 1))
+                if not tie:
+                    P = [[e[0], e[1], e[2], False if e[3] == 2 else e[3]] for e in M[:K]]
+                    fast_steps[0] += 1
+                    continue
+                slow_steps[0] += 1
             for v, d in lanes:                         # lane order
                 if len(P) >= K and not (d < P[K - 1][1]):
                     continue
@@ -218,6 +233,8 @@ def test_single_array_formulation_equals_two_heaps(oracle, dups):
         q = x[rng.integers(0, len(x))] if dups else (x[rng.integers(0, len(x))] + F(0.1) * rng.standard_normal(16)).astype(F)
         for k in (1, 2, 4, 9, 33):
             ids, dist, st = V.greedy_search(q, k, stats=True)
-            sids, sdist, sst = greedy_single_array_py(oracle, V, q, k, V.medoid)
-            assert list(ids) == sids and [float(d) for d in dist] == [float(d) for d in sdist], (t, k)
-            assert (int(st[0]), int(st[1])) == sst, (t, k, st, sst)
+            for batched in (False, True):
+                sids, sdist, sst = greedy_single_array_py(oracle, V, q, k, V.medoid, batched=batched)
+                assert list(ids) == sids and [float(d) for d in dist] == [float(d) for d in sdist], (t, k, batched)
+                assert (int(st[0]), int(st[1])) == sst, (t, k, batched, st, sst)
+    assert fast_steps[0] > 0 and (slow_steps[0] > 0 or not dups)      # both paths were exercised
