@@ -44,17 +44,37 @@ SG_DEVICE_INLINE uint32_t hash32(uint32_t x)
     return x;
 }
 
-// `visited.insert(id)`: true when the id was not in the set yet
-SG_DEVICE_INLINE bool vis_insert(uint32_t *tab, uint32_t mask, uint32_t id)
+// `visited.insert(id)` for up to 32 ids at once, one per lane (want = this lane has an id to insert): true when
+// the id was not in the set yet.  The table belongs to ONE warp, so no atomics are needed: a lane reads a whole
+// 4-slot bucket with one 16-byte L2 load, and lanes that pick the same empty slot in the same round are
+// separated with match_any (the lowest lane takes it, the others look again and see it filled).  Buckets are
+// probed linearly.  All 32 lanes must call.
+SG_DEVICE_INLINE bool vis_insert_warp(uint32_t *tab, uint32_t mask, uint32_t id, bool want, uint32_t lane)
 {
-    uint32_t h = hash32(id) & mask;
-    for (uint32_t p = 0; p <= mask; ++p) {
-        const uint32_t old = atomicCAS(tab + h, NONE, id);
-        if (old == NONE) return true;
-        if (old == id) return false;
-        h = (h + 1) & mask;
+    uint32_t h = hash32(id) & mask & ~3u;
+    bool pending = want, isnew = false;
+    for (uint32_t probes = 0; __any_sync(FULL, pending); ++probes) {
+        uint32_t tgt = 0xFFFFFF00u + lane;                       // distinct per lane: "no slot wanted this round"
+        if (pending) {
+            const uint4 b = __ldcg(reinterpret_cast<const uint4 *>(tab + h));
+            if (b.x == id || b.y == id || b.z == id || b.w == id) {
+                pending = false;
+            } else {
+                const int e = b.x == NONE ? 0 : (b.y == NONE ? 1 : (b.z == NONE ? 2 : (b.w == NONE ? 3 : -1)));
+                if (e >= 0) tgt = h + (uint32_t)e;
+                else if (probes > mask) pending = false;        // table full (cannot happen below half load)
+                else h = (h + 4) & mask;
+            }
+        }
+        const uint32_t same = __match_any_sync(FULL, tgt);
+        if (pending && tgt < 0xFFFFFF00u && (uint32_t)(__ffs(same) - 1) == lane) {
+            __stcg(tab + tgt, id);
+            isnew = true;
+            pending = false;
+        }
+        __syncwarp();                                            // the round's stores are visible to the next round's loads
     }
-    return false;
+    return isnew;
 }
 
 SG_DEVICE_INLINE size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -133,7 +153,7 @@ ann_search_kernel(const AnnArgs a)
         if (lane == 0) {
             P[0] = make_key(order_key32(d0), a.entry);
             ex[0] = 0;
-            vis_insert(vis, hmask, a.entry);
+            __stcg(vis + (hash32(a.entry) & hmask & ~3u), a.entry);
         }
     }
     uint32_t pn = 1;
@@ -176,8 +196,7 @@ ann_search_kernel(const AnnArgs a)
             if (c0 + lane < a.gs) nb = a.graph[(size_t)cid * a.gs + c0 + lane];
             const bool valid = nb != NONE && nb < a.n_rows;
             const uint32_t same = __match_any_sync(FULL, nb);             // a list never repeats an id; be safe anyway
-            bool isnew = false;
-            if (valid && (uint32_t)(__ffs(same) - 1) == lane && !(flag & 1u)) isnew = vis_insert(vis, hmask, nb);
+            const bool isnew = vis_insert_warp(vis, hmask, nb, valid && (uint32_t)(__ffs(same) - 1) == lane && !(flag & 1u), lane);
             const uint32_t newmask = __ballot_sync(FULL, isnew);
             mark(1);
             if (!newmask) continue;
@@ -724,9 +743,21 @@ cudaError_t set_smem(K kern, size_t smem)
 template <bool F16, int ORDER, int METRIC>
 cudaError_t launch_ann_t(const AnnArgs &a, cudaStream_t st)
 {
-    const uint32_t W = 4;
-    const size_t plain = (size_t)W * ann_warp_smem_bytes(a.dim, a.K);
-    const size_t staged = plain + (size_t)W * ann_stage_smem_bytes(a.dim, F16);
+    // warps per CTA: whatever keeps the most query warps resident per SM (227 KB of shared memory, 1 KB reserved per CTA)
+    const size_t per_warp_plain = ann_warp_smem_bytes(a.dim, a.K), per_warp_staged = per_warp_plain + ann_stage_smem_bytes(a.dim, F16);
+    uint32_t W = 4;
+    {
+        size_t best = 0;
+        for (uint32_t w = 4; w >= 1; --w) {
+            const size_t cta = w * per_warp_staged + 1024;
+            const size_t resident = cta <= 227 * 1024 ? w * ((227 * 1024) / cta) : 0;
+            if (resident > best) {
+                best = resident;
+                W = w;
+            }
+        }
+    }
+    const size_t staged = (size_t)W * per_warp_staged;
     // Staging buys latency (one HBM round trip per step) and costs occupancy (27 KB per warp at 384-d fp16: 8 warps per
     // SM).  Measured on 300k x 384: staged 2.2 vs 1.3 Mq/s at 1024 queries, 2.8 vs 3.7 Mq/s at 8192 -- large batches
     // run unstaged, where ~28 resident warps per SM hide the latency instead (2.9 TB/s of row reads).
@@ -738,6 +769,8 @@ cudaError_t launch_ann_t(const AnnArgs &a, cudaStream_t st)
         if (e != cudaSuccess) return e;
         kern<<<(a.nq + W - 1) / W, W * 32, staged, st>>>(a);
     } else {
+        W = 4;
+        const size_t plain = (size_t)W * per_warp_plain;
         auto kern = ann_search_kernel<F16, ORDER, METRIC, false>;
         cudaError_t e = set_smem(kern, plain);
         if (e != cudaSuccess) return e;
