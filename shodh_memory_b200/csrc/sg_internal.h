@@ -134,11 +134,11 @@ struct AnnArgs {
     unsigned long long *phase;   // [8] or null: SM cycles per phase summed over queries (profiling hook)
 };
 // shared memory per query warp: query f32 + two copies of the sorted list (K + 32 keys + expanded flags each:
-// the batched merge writes the new list beside the old one) + 32 candidate keys
+// the batched merge writes the new list beside the old one) + 32 candidate keys + the visited set's 1 KB slot arbiter
 __host__ __device__ inline size_t ann_warp_smem_bytes(uint32_t dim, uint32_t K)
 {
     const size_t cap = (size_t)K + 32;   // every piece a multiple of 16 bytes: the query is read as float4
-    return (((size_t)dim * 4 + 15) & ~(size_t)15) + 2 * (((cap * 8 + 15) & ~(size_t)15) + ((cap + 15) & ~(size_t)15)) + 256;
+    return (((size_t)dim * 4 + 15) & ~(size_t)15) + 2 * (((cap * 8 + 15) & ~(size_t)15) + ((cap + 15) & ~(size_t)15)) + 256 + 1024;
 }
 // staging buffer of the beam search: 32 rows, each padded by 16 bytes (conflict-free lane-per-row reads)
 __host__ __device__ inline size_t ann_stage_smem_bytes(uint32_t dim, bool f16)

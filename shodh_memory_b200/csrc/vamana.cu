@@ -47,27 +47,34 @@ SG_DEVICE_INLINE uint32_t hash32(uint32_t x)
 // `visited.insert(id)` for up to 32 ids at once, one per lane (want = this lane has an id to insert): true when
 // the id was not in the set yet.  The table belongs to ONE warp, so no atomics are needed: a lane reads a whole
 // 4-slot bucket with one 16-byte L2 load, and lanes that pick the same empty slot in the same round are
-// separated with match_any (the lowest lane takes it, the others look again and see it filled).  Buckets are
-// probed linearly.  All 32 lanes must call.
-SG_DEVICE_INLINE bool vis_insert_warp(uint32_t *tab, uint32_t mask, uint32_t id, bool want, uint32_t lane)
+// separated through a 1 KB arbiter in shared memory (each writes its lane number at arb[slot % 1024]; who reads
+// its own number back takes the slot, the others look again and see it filled -- a list that repeated an id would
+// be caught the same way: same id, same slot).  match_any would do this too, but costs ~1000 cycles on 32
+// distinct values.  Buckets are probed linearly.  All 32 lanes must call.
+SG_DEVICE_INLINE bool vis_insert_warp(uint32_t *tab, uint32_t mask, uint32_t id, bool want, uint32_t lane, uint8_t *arb)
 {
     uint32_t h = hash32(id) & mask & ~3u;
     bool pending = want, isnew = false;
     for (uint32_t probes = 0; __any_sync(FULL, pending); ++probes) {
-        uint32_t tgt = 0xFFFFFF00u + lane;                       // distinct per lane: "no slot wanted this round"
+        uint32_t tgt = NONE;
         if (pending) {
             const uint4 b = __ldcg(reinterpret_cast<const uint4 *>(tab + h));
             if (b.x == id || b.y == id || b.z == id || b.w == id) {
                 pending = false;
             } else {
                 const int e = b.x == NONE ? 0 : (b.y == NONE ? 1 : (b.z == NONE ? 2 : (b.w == NONE ? 3 : -1)));
-                if (e >= 0) tgt = h + (uint32_t)e;
-                else if (probes > mask) pending = false;        // table full (cannot happen below half load)
-                else h = (h + 4) & mask;
+                if (e >= 0) {
+                    tgt = h + (uint32_t)e;
+                    arb[tgt & 1023u] = (uint8_t)lane;
+                } else if (probes > mask) {
+                    pending = false;                             // table full (cannot happen below half load)
+                } else {
+                    h = (h + 4) & mask;
+                }
             }
         }
-        const uint32_t same = __match_any_sync(FULL, tgt);
-        if (pending && tgt < 0xFFFFFF00u && (uint32_t)(__ffs(same) - 1) == lane) {
+        __syncwarp();
+        if (tgt != NONE && arb[tgt & 1023u] == (uint8_t)lane) {
             __stcg(tab + tgt, id);
             isnew = true;
             pending = false;
@@ -122,6 +129,7 @@ ann_search_kernel(const AnnArgs a)
     uint64_t *P2 = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(P) + list_bytes);   // the merge's output list
     uint8_t *ex2 = reinterpret_cast<uint8_t *>(P2) + align16((size_t)CAP * 8);
     uint64_t *Cs = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(P2) + list_bytes);  // [32] candidate keys
+    uint8_t *arb = reinterpret_cast<uint8_t *>(Cs) + 256;                                       // [1024] slot arbiter
     uint8_t *rowbuf = base + ann_warp_smem_bytes(dim, K);          // STAGE: [32][row_bytes + 16]
     const uint32_t row_bytes = dim * (F16 ? 2u : 4u), pitch = row_bytes + 16;
     const uint32_t bar = smem_u32(rowbuf + (size_t)32 * pitch);   // STAGE: the warp's mbarrier
@@ -195,8 +203,7 @@ ann_search_kernel(const AnnArgs a)
             uint32_t nb = NONE;
             if (c0 + lane < a.gs) nb = a.graph[(size_t)cid * a.gs + c0 + lane];
             const bool valid = nb != NONE && nb < a.n_rows;
-            const uint32_t same = __match_any_sync(FULL, nb);             // a list never repeats an id; be safe anyway
-            const bool isnew = vis_insert_warp(vis, hmask, nb, valid && (uint32_t)(__ffs(same) - 1) == lane && !(flag & 1u), lane);
+            const bool isnew = vis_insert_warp(vis, hmask, nb, valid && !(flag & 1u), lane, arb);
             const uint32_t newmask = __ballot_sync(FULL, isnew);
             mark(1);
             if (!newmask) continue;
