@@ -326,7 +326,10 @@ int sg_store_build_graph(sg_store *s, uint32_t max_degree, uint32_t search_list_
     uint64_t B = n / 32;
     if (B < 64) B = 64;
     if (B > 16384) B = 16384;
+    if (const char *e = getenv("SG_GRAPH_BATCH")) B = (uint64_t)atoll(e) > 0 ? (uint64_t)atoll(e) : B;   // tuning knobs
     if (B > n) B = n;
+    int passes = 2;
+    if (const char *e = getenv("SG_GRAPH_PASSES")) passes = atoi(e) > 0 ? atoi(e) : 2;
     const size_t o_nodes = 0, o_cnt = o_nodes + B, o_res = o_cnt + B, o_new = o_res + B * L, o_touch = o_new + B * gs,
                  o_ntouch = o_touch + B * gs, g32_total = o_ntouch + 4;
     if ((rc = grow(s->d_g32, s->g32_cap, g32_total)) != SG_OK) return rc;
@@ -352,7 +355,10 @@ int sg_store_build_graph(sg_store *s, uint32_t max_degree, uint32_t search_list_
     s->graph_len = n;
 
     // Step 4 (:221-281): two passes; per batch: beam search (L) from the medoid -> robust_prune -> edges + back-edges
-    const uint32_t ecap = 32;
+    uint32_t ecap = 32;
+    if (const char *e = getenv("SG_GRAPH_INBOX")) ecap = (uint32_t)atoi(e);
+    if (ecap < 1) ecap = 1;
+    if (ecap + gs > 128) ecap = 128 - gs;
     uint32_t *d_inbox = nullptr, *d_inbox_cnt = nullptr;
     SG_CUDA_TRY(cudaMalloc(&d_inbox, n * (size_t)ecap * 4));
     cudaError_t e = cudaMalloc(&d_inbox_cnt, n * 4);
@@ -364,14 +370,16 @@ int sg_store_build_graph(sg_store *s, uint32_t max_degree, uint32_t search_list_
         return SG_ERR_OOM;
     }
     const uint32_t H = default_table_size(L);
-    // back-edge prunes visit the list in id order, as the reference's zero-distance candidates do (:251-262);
-    // SG_GRAPH_BACKEDGE_BY_DISTANCE=1 orders them by true distance instead
-    const char *bd = getenv("SG_GRAPH_BACKEDGE_BY_DISTANCE");
-    const bool by_id = !(bd && *bd == '1');
+    // Back-edge prunes order their candidates by true distance.  The reference hands that prune zero distances, so it
+    // walks the list in id order (:251-262); one insertion at a time that is harmless, but with a whole batch of
+    // arrivals per target it systematically drops the highest ids: recall@10 0.87 vs 1.00 on 300k x 384 (beam 40).
+    // SG_GRAPH_BACKEDGE_BY_ID=1 selects the reference's order.
+    const char *bd = getenv("SG_GRAPH_BACKEDGE_BY_ID");
+    const bool by_id = bd && *bd == '1';
     uint32_t *d_nodes = s->d_g32 + o_nodes, *d_cnt = s->d_g32 + o_cnt, *d_res = s->d_g32 + o_res, *d_new = s->d_g32 + o_new,
              *d_touch = s->d_g32 + o_touch, *d_ntouch = s->d_g32 + o_ntouch;
     rc = SG_OK;
-    for (int pass = 0; pass < 2 && rc == SG_OK; ++pass) {
+    for (int pass = 0; pass < passes && rc == SG_OK; ++pass) {
         for (uint64_t first = 0; first < n && rc == SG_OK; first += B) {
             const uint32_t m = (uint32_t)(n - first < B ? n - first : B);
             e = launch_iota(d_nodes, (uint32_t)first, m, st);
