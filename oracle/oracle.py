@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "liboracle.so")
 _SRC = os.path.join(_HERE, "shodh_oracle.c")
-_SRCS = [_SRC, os.path.join(_HERE, "vamana_oracle.c"), os.path.join(_HERE, "build.sh")]
+_SRCS = [_SRC, os.path.join(_HERE, "vamana_oracle.c"), os.path.join(_HERE, "pq_oracle.c"), os.path.join(_HERE, "build.sh")]
 
 DEFAULT_WEIGHTS = np.array([0.18, 0.17, 0.05, 0.05, 0.28, 0.14, 0.13], dtype=np.float32)
 
@@ -119,6 +119,23 @@ def lib() -> C.CDLL:
         L.so_vamana_add_vector.restype = None
         L.so_vamana_add_vector.argtypes = [f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_uint32,
                                            C.c_uint32, u32p, u32p]
+        # pq_oracle.c
+        u8p = C.POINTER(C.c_uint8)
+        L.so_pq_train.restype = C.c_uint32
+        L.so_pq_train.argtypes = [f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p, f32p]
+        L.so_pq_encode.restype = None
+        L.so_pq_encode.argtypes = [f32p, C.c_uint32, C.c_uint32, C.c_uint32, f32p, C.c_uint64, u8p]
+        L.so_pq_decode.restype = None
+        L.so_pq_decode.argtypes = [f32p, C.c_uint32, C.c_uint32, C.c_uint32, u8p, C.c_uint64, f32p]
+        L.so_pq_table.restype = None
+        L.so_pq_table.argtypes = [f32p, C.c_uint32, C.c_uint32, C.c_uint32, f32p, f32p]
+        L.so_pq_distance_with_table.restype = C.c_float
+        L.so_pq_distance_with_table.argtypes = [f32p, C.c_uint32, C.c_uint32, u8p]
+        L.so_pq_asymmetric_distance.restype = C.c_float
+        L.so_pq_asymmetric_distance.argtypes = [f32p, C.c_uint32, C.c_uint32, C.c_uint32, f32p, u8p]
+        L.so_pq_search.restype = C.c_uint32
+        L.so_pq_search.argtypes = [f32p, C.c_uint32, C.c_uint32, C.c_uint32, u32p, u8p, C.c_uint64, f32p, C.c_uint32,
+                                   u32p, f32p]
         L.so_recall_at_k.restype = C.c_double
         L.so_recall_at_k.argtypes = [u32p, u32p, u32p, u32p, C.c_uint32, C.c_uint32]
         _lib = L
@@ -496,3 +513,80 @@ def manifold_corpus(seed, n, dim, latent=12, noise=0.05):
         x = z @ A + (noise * np.sqrt(latent)) * rng.standard_normal((m, dim)).astype(np.float32)
         out[lo:lo + m] = x / np.linalg.norm(x, axis=1, keepdims=True)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Product Quantization (pq_oracle.c): reference src/vector_db/pq.rs
+# ---------------------------------------------------------------------------------------------
+class PQOracle:
+    """ProductQuantizer + CompressedVectorStore restated on the CPU.  centroids [m, k, ds] f32."""
+
+    def __init__(self, dim=384, subvec_dim=8, num_centroids=256, kmeans_iterations=20):
+        assert dim % subvec_dim == 0
+        self.dim, self.ds, self.m = dim, subvec_dim, dim // subvec_dim
+        self.num_centroids, self.iterations = num_centroids, kmeans_iterations
+        self.centroids = None
+        self.k = 0
+        self.ids = np.zeros(0, np.uint32)
+        self.codes = np.zeros((0, self.m), np.uint8)
+
+    def shuffled_orders(self, n, seed=0):
+        """one index permutation per subspace (the reference shuffles with thread_rng inside kmeans, pq.rs:157-159)"""
+        rng = np.random.default_rng(seed)
+        return np.stack([rng.permutation(n) for _ in range(self.m)]).astype(np.uint32)
+
+    def train(self, vectors, seed=0, orders=None):
+        v = _f32(vectors)
+        n = v.shape[0]
+        orders = self.shuffled_orders(n, seed) if orders is None else np.ascontiguousarray(orders, np.uint32)
+        self.k = min(self.num_centroids, n)
+        self.centroids = np.zeros((self.m, self.k, self.ds), np.float32)
+        k = lib().so_pq_train(_p(v, C.c_float), n, self.dim, self.ds, self.num_centroids, self.iterations,
+                              _p(orders, C.c_uint32), _p(self.centroids, C.c_float))
+        assert k == self.k
+        return self
+
+    def encode(self, vectors):
+        v = _f32(vectors).reshape(-1, self.dim)
+        out = np.zeros((v.shape[0], self.m), np.uint8)
+        lib().so_pq_encode(_p(self.centroids, C.c_float), self.m, self.k, self.ds, _p(v, C.c_float), v.shape[0],
+                           _p(out, C.c_uint8))
+        return out
+
+    def decode(self, codes):
+        c = np.ascontiguousarray(codes, np.uint8).reshape(-1, self.m)
+        out = np.zeros((c.shape[0], self.dim), np.float32)
+        lib().so_pq_decode(_p(self.centroids, C.c_float), self.m, self.k, self.ds, _p(c, C.c_uint8), c.shape[0],
+                           _p(out, C.c_float))
+        return out
+
+    def table(self, query):
+        q = _f32(query)
+        t = np.zeros((self.m, self.k), np.float32)
+        lib().so_pq_table(_p(self.centroids, C.c_float), self.m, self.k, self.ds, _p(q, C.c_float), _p(t, C.c_float))
+        return t
+
+    def distance_with_table(self, table, codes):
+        t = _f32(table)
+        c = np.ascontiguousarray(codes, np.uint8)
+        return float(lib().so_pq_distance_with_table(_p(t, C.c_float), self.m, self.k, _p(c, C.c_uint8)))
+
+    def asymmetric_distance(self, query, codes):
+        q = _f32(query)
+        c = np.ascontiguousarray(codes, np.uint8)
+        return float(lib().so_pq_asymmetric_distance(_p(self.centroids, C.c_float), self.m, self.k, self.ds,
+                                                     _p(q, C.c_float), _p(c, C.c_uint8)))
+
+    def add(self, ids, vectors):
+        """CompressedVectorStore::add for unique ids"""
+        self.ids = np.concatenate([self.ids, np.ascontiguousarray(ids, np.uint32)])
+        self.codes = np.ascontiguousarray(np.vstack([self.codes, self.encode(vectors)]))
+
+    def search(self, query, topk):
+        q = _f32(query)
+        ids = np.zeros(max(topk, 1), np.uint32)
+        dist = np.zeros(max(topk, 1), np.float32)
+        r = lib().so_pq_search(_p(self.centroids, C.c_float), self.m, self.k, self.ds, _p(self.ids, C.c_uint32),
+                               _p(self.codes, C.c_uint8), self.ids.size, _p(q, C.c_float), topk, _p(ids, C.c_uint32),
+                               _p(dist, C.c_float))
+        return ids[:r].copy(), dist[:r].copy()

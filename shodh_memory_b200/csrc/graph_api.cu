@@ -279,6 +279,7 @@ int sg_store_get_graph(sg_store *s, uint32_t *deg_out, uint32_t *nbr_out, uint64
     if (!s || (n_nodes && (!deg_out || !nbr_out))) return SG_ERR_INVALID;
     std::lock_guard<std::mutex> g(s->mu);
     SG_CUDA_TRY(cudaSetDevice(s->device));
+    if (n_nodes == 0 && (s->gs == 0 || s->graph_len == 0)) return SG_OK;
     if (s->gs == 0 || n_nodes != s->graph_len) {
         set_error("sg_store_get_graph: the graph has %llu nodes, %llu requested", (unsigned long long)(s->gs ? s->graph_len : 0),
                   (unsigned long long)n_nodes);
