@@ -242,6 +242,34 @@ SG_API int sg_store_ann_stats(sg_store *s, uint64_t *queries_out, uint64_t *retr
  * counting (a clock64 read per phase), 0 switches it off. */
 SG_API int sg_store_ann_phase_cycles(sg_store *s, int enable, uint64_t *cycles_out);
 
+/* ---- Product Quantization: src/vector_db/pq.rs ----------------------------------------
+ * ProductQuantizer (train :94-215, encode :220-257, decode :260-290, build_distance_table :329-353,
+ * distance_with_table :358-369) and CompressedVectorStore (add :428-432, search :449-466) on the device, every
+ * f32 operation in the reference's order, so codes, tables, distances and the (distance, id) ranking are
+ * bit-identical to the CPU path.  centroids: [dim / subvec_dim][num_centroids][subvec_dim] f32.
+ *   sg_pq_create  a quantizer from trained centroids (the reference's struct is serde-serialisable);
+ *   sg_pq_train   k-means per subspace like ProductQuantizer::train; `orders` [num_subvectors][n] are the shuffled
+ *                 index orders the reference draws from thread_rng inside kmeans (:157-159) -- given the same
+ *                 orders the centroids equal the CPU's bit for bit; num_centroids is capped at n (:118);
+ *   sg_pq_add     CompressedVectorStore::add for n vectors (ids must be unique: the reference's map would overwrite);
+ *   sg_pq_search  CompressedVectorStore::search for b queries: ids_out / dist_out [b, k], counts_out [b].
+ * Limits: subvec_dim <= 16, dim / subvec_dim a multiple of 4, num_centroids <= 256, k <= 1024. */
+typedef struct sg_pq sg_pq;
+SG_API int sg_pq_create(sg_pq **out, int device, uint32_t dim, uint32_t subvec_dim, uint32_t num_centroids,
+                        const float *centroids);
+SG_API int sg_pq_train(sg_pq **out, int device, uint32_t dim, uint32_t subvec_dim, uint32_t num_centroids,
+                       uint32_t iterations, const float *vectors_f32, uint64_t n, const uint32_t *orders);
+SG_API void sg_pq_destroy(sg_pq *p);
+SG_API int sg_pq_info(sg_pq *p, uint32_t *dim_out, uint32_t *num_subvectors_out, uint32_t *num_centroids_out,
+                      uint64_t *len_out);
+SG_API int sg_pq_get_centroids(sg_pq *p, float *centroids_out);
+SG_API int sg_pq_encode(sg_pq *p, const float *rows_f32, uint64_t n, uint8_t *codes_out /* [n, num_subvectors] */);
+SG_API int sg_pq_decode(sg_pq *p, const uint8_t *codes, uint64_t n, float *rows_f32_out);
+SG_API int sg_pq_table(sg_pq *p, const float *query_f32, float *table_out /* [num_subvectors, num_centroids] */);
+SG_API int sg_pq_add(sg_pq *p, const uint32_t *ids, const float *rows_f32, uint64_t n);
+SG_API int sg_pq_search(sg_pq *p, const float *queries_f32, uint32_t b, uint32_t k, uint32_t *ids_out, float *dist_out,
+                        uint32_t *counts_out);
+
 /* CUDA-event timing of the scan kernel(s) inside each search (bench.py roofline): with
  * profiling on, every search records an event pair around its sweep launches on the stream
  * it runs on (no synchronisation).  sg_store_profile_read waits for the last recorded

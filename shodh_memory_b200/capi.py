@@ -116,6 +116,18 @@ def lib() -> C.CDLL:
     L.sg_store_ann_phase_cycles.argtypes = [vp, C.c_int, u64p]
     L.sg_store_profile_read.argtypes = [vp, f32p, C.c_uint32, u32p, u32p]
     i64p = C.POINTER(C.c_int64)
+    u8p = C.POINTER(C.c_uint8)
+    L.sg_pq_create.argtypes = [C.POINTER(vp), C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, f32p]
+    L.sg_pq_train.argtypes = [C.POINTER(vp), C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, f32p, C.c_uint64, u32p]
+    L.sg_pq_destroy.argtypes = [vp]
+    L.sg_pq_destroy.restype = None
+    L.sg_pq_info.argtypes = [vp, u32p, u32p, u32p, u64p]
+    L.sg_pq_get_centroids.argtypes = [vp, f32p]
+    L.sg_pq_encode.argtypes = [vp, f32p, C.c_uint64, u8p]
+    L.sg_pq_decode.argtypes = [vp, u8p, C.c_uint64, f32p]
+    L.sg_pq_table.argtypes = [vp, f32p, f32p]
+    L.sg_pq_add.argtypes = [vp, u32p, f32p, C.c_uint64]
+    L.sg_pq_search.argtypes = [vp, f32p, C.c_uint32, C.c_uint32, u32p, f32p, u32p]
     L.sg_encoder_create.argtypes = [C.POINTER(vp), C.c_int, C.c_char_p]
     L.sg_encoder_destroy.argtypes = [vp]
     L.sg_encoder_destroy.restype = None
