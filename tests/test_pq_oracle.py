@@ -32,7 +32,7 @@ def test_compression_ratio(oracle):
 def test_distance_table(oracle):
     """pq.rs:534-551: table distance == direct asymmetric distance (n = 100 < 256 -> k = 100 centroids)"""
     v = np.random.default_rng(1).random((100, 384), dtype=F)
-    pq = oracle.PQOracle(384).train(v, seed=2)
+    pq = oracle.PQOracle(384, kmeans_iterations=5).train(v, seed=2)
     assert pq.k == 100
     codes = pq.encode(v[1:2])[0]
     direct = pq.asymmetric_distance(v[0], codes)
@@ -43,7 +43,7 @@ def test_distance_table(oracle):
 def test_compressed_store_search(oracle):
     """pq.rs:554-577: the query vector itself is within the top 5 of 10 results"""
     v = np.random.default_rng(2).random((1000, 384), dtype=F)
-    pq = oracle.PQOracle(384).train(v, seed=3)
+    pq = oracle.PQOracle(384, kmeans_iterations=4).train(v, seed=3)
     pq.add(np.arange(1000), v)
     ids, dist = pq.search(v[0], 10)
     assert len(ids) == 10 and 0 in ids[:5]
