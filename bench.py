@@ -420,6 +420,7 @@ def main():
                                               note="pinned host ids -> H2D -> encoder -> exact top-%d scan of this "
                                                    "rank's shard -> D2H, one stream" % TOPK))
         enc.close()
+    tc_stats_val = store.local.tc_stats() if rank == 0 else (0, 0)   # read before the optional legs below
     # ---------------- graph index: VamanaIndex::search's default ANN arm on the device ----------------
     # Opt-out with SG_BENCH_ANN=0.  A separate low-intrinsic-dimension corpus (i.i.d. unit vectors have no neighbourhood
     # structure for a graph to follow): device build (R 32, L 75, alpha 1.2), then batch-256 and batch-1 beam searches with the
@@ -535,6 +536,68 @@ def main():
             g.close()
         except Exception as ex:  # the headline line must still print
             ann_res = dict(error=repr(ex))
+    # ---------------- Product Quantization: CompressedVectorStore::search on the device ----------------
+    pq_res = None
+    if rank == 0 and world == 1 and os.environ.get("SG_BENCH_PQ", "1") == "1":
+        try:
+            from oracle import oracle as o
+            pq_rows = int(os.environ.get("SG_BENCH_PQ_ROWS", 1_000_000))
+            rng = np.random.default_rng(SEED + 11)
+            A = rng.standard_normal((12, DIM)).astype(np.float32)
+
+            def pq_rows_gen(m):
+                x = rng.standard_normal((m, 12)).astype(np.float32) @ A + 0.17 * rng.standard_normal((m, DIM)).astype(np.float32)
+                return np.ascontiguousarray(x / np.linalg.norm(x, axis=1, keepdims=True), np.float32)
+            train = pq_rows_gen(5000)
+            orders = np.stack([rng.permutation(5000) for _ in range(DIM // 8)]).astype(np.uint32)
+            t0 = time.perf_counter()
+            pq = sg.GpuProductQuantizer.train(train, orders, kmeans_iterations=20, device=local_rank)   # PQConfig::minilm()
+            train_s = time.perf_counter() - t0
+            t_add = 0.0
+            first_chunk = None
+            for lo in range(0, pq_rows, 100_000):
+                m = min(100_000, pq_rows - lo)
+                x = pq_rows_gen(m)
+                if first_chunk is None:
+                    first_chunk = x
+                t0 = time.perf_counter()
+                pq.add(np.arange(lo, lo + m, dtype=np.uint32), x)
+                t_add += time.perf_counter() - t0
+            pq_q = np.ascontiguousarray(first_chunk[:BATCH] + 0.01 * rng.standard_normal((BATCH, DIM)).astype(np.float32), np.float32)
+            for _ in range(2):
+                pq.search_batch(pq_q, TOPK)
+            t0 = time.perf_counter()
+            reps = 5
+            for _ in range(reps):
+                gi, gd, gc = pq.search_batch(pq_q, TOPK)
+            ms = (time.perf_counter() - t0) * 1e3 / reps
+            t0 = time.perf_counter()
+            for i in range(20):
+                pq.search_batch(pq_q[i:i + 1], TOPK)
+            ms1 = (time.perf_counter() - t0) * 1e3 / 20
+            # CPU: the oracle port of CompressedVectorStore::search on a 100k-vector slice of the same store, 1 thread
+            ref = o.PQOracle(DIM)
+            ref.centroids, ref.k = pq.centroids, pq.num_centroids
+            ref.ids = np.arange(100_000, dtype=np.uint32)
+            ref.codes = pq.encode(first_chunk)            # device codes == oracle codes (tests/test_pq_gpu.py); saves 10 s of host encode
+            t0 = time.perf_counter()
+            for i in range(4):
+                ref.search(pq_q[i], TOPK)
+            cpu_ms = (time.perf_counter() - t0) * 1e3 / 4 * (pq_rows / 100_000)
+            sweeps = (BATCH + 1) // 2
+            nbytes = float(pq_rows) * (DIM // 8 + 4)
+            pq_res = dict(rows=pq_rows, code_bytes=DIM // 8, train_s_5000x20=train_s, encode_add_rows_per_s=pq_rows / t_add,
+                          batch256=dict(host_api_ms=ms, queries_per_s=BATCH / (ms * 1e-3), sweeps=sweeps,
+                                        roofline=dict(bound="hbm (code stream) / shared-memory gathers", algorithmic_bytes_per_sweep=nbytes,
+                                                      achieved=nbytes * sweeps / (ms * 1e-3) / 1e9, peak=peaks()[0], unit="GB/s",
+                                                      frac=nbytes * sweeps / (ms * 1e-3) / 1e9 / peaks()[0],
+                                                      note="wall clock of sg_pq_search incl. H2D/D2H and table build; 2 queries per sweep")),
+                          batch1_host_api_ms=ms1,
+                          cpu_reference=dict(ms_per_query_1_thread=cpu_ms, kind="port (oracle/pq_oracle.c), 100k-vector slice scaled linearly"),
+                          kernel="pq_scan_kernel (48 table look-ups per vector in the reference's order; ids and distances bit-identical to the CPU path)")
+            pq.close()
+        except Exception as ex:
+            pq_res = dict(error=repr(ex))
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
@@ -605,9 +668,10 @@ def main():
                                   note="peak = measured COPY bandwidth (read+write); a read-only sweep can slightly exceed it "
                                        "(ncu: 80 % of the 8.2 TB/s DRAM peak, profiles/r01_scan_exact_ncu.md)",
                                   traffic=traffic_from_capture("scan_exact_kernel", local_rows)[0])),
-        tensor_path=dict(zip(("queries", "exact_reruns"), store.local.tc_stats())),
+        tensor_path=dict(zip(("queries", "exact_reruns"), tc_stats_val)),
         encoder=enc_res,
         graph_index=ann_res,
+        product_quantization=pq_res,
         gpu_launches=int(launches), clocks=clocks)
     if cpu:
         line["cpu_baseline"] = dict(value=cpu["value"], unit=UNIT, cores=cpu["cores"], kind=cpu["kind"], sample=cpu["sample"])

@@ -123,6 +123,53 @@ private:
     uint32_t dim_;
 };
 
+/// ProductQuantizer + CompressedVectorStore (src/vector_db/pq.rs) over sg_pq_*: codes, tables and the
+/// (distance, id) ranking are bit-identical to the CPU path
+class GpuProductQuantizer {
+public:
+    /// from trained centroids, flattened [num_subvectors][num_centroids][subvec_dim]
+    GpuProductQuantizer(const std::vector<float> &centroids, uint32_t dim, uint32_t subvec_dim, uint32_t num_centroids, int device = 0)
+        : dim_(dim), m_(dim / subvec_dim)
+    {
+        if (centroids.size() != (size_t)dim * num_centroids) throw Error(SG_ERR_DIM, "centroid array has the wrong size");
+        check(sg_pq_create(&h_, device, dim, subvec_dim, num_centroids, centroids.data()));
+    }
+    ~GpuProductQuantizer() { sg_pq_destroy(h_); }
+    GpuProductQuantizer(const GpuProductQuantizer &) = delete;
+    GpuProductQuantizer &operator=(const GpuProductQuantizer &) = delete;
+    /// ProductQuantizer::encode
+    std::vector<uint8_t> encode(const std::vector<float> &v)
+    {
+        if (v.size() != dim_) throw Error(SG_ERR_DIM, "dimension mismatch");
+        std::vector<uint8_t> codes(m_);
+        check(sg_pq_encode(h_, v.data(), 1, codes.data()));
+        return codes;
+    }
+    /// CompressedVectorStore::add
+    void add(uint32_t id, const std::vector<float> &v)
+    {
+        if (v.size() != dim_) throw Error(SG_ERR_DIM, "dimension mismatch");
+        check(sg_pq_add(h_, &id, v.data(), 1));
+    }
+    /// CompressedVectorStore::search -> (id, distance) ascending by (distance, id)
+    std::vector<std::pair<uint32_t, float>> search(const std::vector<float> &query, size_t k)
+    {
+        if (query.size() != dim_) throw Error(SG_ERR_DIM, "dimension mismatch");
+        std::vector<uint32_t> ids(k);
+        std::vector<float> dist(k);
+        uint32_t cnt = 0;
+        check(sg_pq_search(h_, query.data(), 1, (uint32_t)k, ids.data(), dist.data(), &cnt));
+        std::vector<std::pair<uint32_t, float>> out;
+        for (uint32_t j = 0; j < cnt; ++j) out.emplace_back(ids[j], dist[j]);
+        return out;
+    }
+    size_t len() { uint64_t n = 0; check(sg_pq_info(h_, nullptr, nullptr, nullptr, &n)); return (size_t)n; }
+
+private:
+    sg_pq *h_ = nullptr;
+    uint32_t dim_, m_;
+};
+
 /// similarity.rs::top_k_similar over a dense candidate matrix: (score, position) by score descending, ties in
 /// input order; cosine_similarity is 0 on a zero norm or a length mismatch (similarity.rs:10-48)
 inline std::vector<std::pair<float, uint32_t>> top_k_similar(const std::vector<float> &query, const std::vector<float> &candidates_flat,
