@@ -111,15 +111,25 @@ class ShardedGpuStore:
                 out_cnt=torch.empty(b, dtype=torch.int32, device=dev))
         return self._bufs[key]
 
-    def search_device(self, d_queries: torch.Tensor, k: int):
+    def build_graph(self, max_degree: int = 32, search_list_size: int = 75, alpha: float = 1.2, seed: int = 0) -> None:
+        """One Vamana graph per shard (VamanaIndex::build over this rank's rows); search_device(..., ann=True) then
+        walks every shard's graph and merges the per-shard results exactly like the exact path does."""
+        self.local.build_graph(max_degree, search_list_size, alpha, seed + self.rank)
+
+    def search_device(self, d_queries: torch.Tensor, k: int, ann: bool = False):
         """d_queries: f32 [b,dim] on this rank's GPU (same on every rank).  Asynchronous on the
-        current torch stream.  Returns (ids int32 [b,k] (bit pattern of u32), dist f32 [b,k], counts)."""
+        current torch stream.  Returns (ids int32 [b,k] (bit pattern of u32), dist f32 [b,k], counts).
+        ann=True: the local step is the graph search (sg_store_search_ann_device) instead of the exact sweep."""
         b = d_queries.shape[0]
         bufs = self._buffers(b, k)
         stream = torch.cuda.current_stream().cuda_stream
         pack = bufs["pack"]
-        self.local.search_device(d_queries.data_ptr(), b, k, pack[0].data_ptr(), pack[1].data_ptr(),
-                                 bufs["cnt"].data_ptr(), stream)
+        if ann:
+            self.local.search_ann_device(d_queries.data_ptr(), b, k, pack[0].data_ptr(), pack[1].data_ptr(),
+                                         bufs["cnt"].data_ptr(), 0, stream)
+        else:
+            self.local.search_device(d_queries.data_ptr(), b, k, pack[0].data_ptr(), pack[1].data_ptr(),
+                                     bufs["cnt"].data_ptr(), stream)
         if self.world == 1:
             return pack[0], pack[1].view(torch.float32), bufs["cnt"]
         if self.peer is not None:

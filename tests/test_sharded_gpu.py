@@ -61,3 +61,53 @@ def test_two_gpu_sharded_search_equals_single_store(tmp_path, mode):
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "SHARDED_OK" in out.stdout
+
+
+ANN_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["SG_ROOT"])
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+import shodh_memory_b200 as sg
+from oracle import oracle as o
+N, B, K = 60_000, 64, 10
+x = o.manifold_corpus(9, N, 384)
+st = sg.ShardedGpuStore(N, 384, "f16", rank, world, rank)
+st.add_rows(x)
+st.build_graph()                                            # one Vamana graph per shard
+rng = np.random.default_rng(3)
+q = x[rng.integers(0, N, B)] + 0.02 * rng.standard_normal((B, 384)).astype(np.float32)
+q = np.ascontiguousarray(q / np.linalg.norm(q, axis=1, keepdims=True), np.float32)
+dq = torch.from_numpy(q).cuda()
+ids, dst, cnt = st.search_device(dq, 40, ann=True)         # per-shard beam search, then the usual exchange + merge
+torch.cuda.synchronize()
+ann = ids.cpu().numpy().view(np.uint32).copy()
+adist = dst.cpu().numpy().copy()
+eids, edst, ecnt = st.search_device(dq, K)                 # exact, for recall
+torch.cuda.synchronize()
+if rank == 0:
+    ex = eids.cpu().numpy().view(np.uint32)
+    hits = sum(len(set(ann[i, :K].tolist()) & set(ex[i].tolist())) for i in range(B))
+    assert hits / (B * K) >= 0.9, hits / (B * K)
+    assert (np.diff(adist[:, :K], axis=1) >= 0).all()      # merged list ascending
+    print("SHARDED_ANN_OK", hits / (B * K))
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_two_gpu_sharded_graph_search(tmp_path):
+    """one graph per shard, per-shard beam search, then the same exchange + merge as the exact path"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "ann_worker.py"
+    script.write_text(ANN_WORKER)
+    env = dict(os.environ, SG_ROOT=ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29573", str(script)],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "SHARDED_ANN_OK" in out.stdout
