@@ -5,5 +5,5 @@ set -e
 cd "$(dirname "$0")"
 mkdir -p _build
 gcc -O2 -ffp-contract=off -fno-fast-math -fopenmp -fvisibility=hidden -shared -fPIC \
-    -o _build/liboracle.so shodh_oracle.c vamana_oracle.c pq_oracle.c -lm
+    -o _build/liboracle.so shodh_oracle.c vamana_oracle.c pq_oracle.c spann_oracle.c -lm
 echo "built oracle/_build/liboracle.so"

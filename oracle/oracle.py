@@ -14,7 +14,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "liboracle.so")
 _SRC = os.path.join(_HERE, "shodh_oracle.c")
-_SRCS = [_SRC, os.path.join(_HERE, "vamana_oracle.c"), os.path.join(_HERE, "pq_oracle.c"), os.path.join(_HERE, "build.sh")]
+_SRCS = [_SRC, os.path.join(_HERE, "vamana_oracle.c"), os.path.join(_HERE, "pq_oracle.c"), os.path.join(_HERE, "spann_oracle.c"),
+         os.path.join(_HERE, "build.sh")]
 
 DEFAULT_WEIGHTS = np.array([0.18, 0.17, 0.05, 0.05, 0.28, 0.14, 0.13], dtype=np.float32)
 
@@ -136,6 +137,18 @@ def lib() -> C.CDLL:
         L.so_pq_search.restype = C.c_uint32
         L.so_pq_search.argtypes = [f32p, C.c_uint32, C.c_uint32, C.c_uint32, u32p, u8p, C.c_uint64, f32p, C.c_uint32,
                                    u32p, f32p]
+        # spann_oracle.c
+        L.so_spann_distance.restype = C.c_float
+        L.so_spann_distance.argtypes = [f32p, f32p, C.c_uint32, C.c_int]
+        L.so_spann_nearest_centroid.restype = C.c_uint32
+        L.so_spann_nearest_centroid.argtypes = [f32p, f32p, C.c_uint32, C.c_uint32, C.c_int]
+        L.so_spann_kmeans.restype = C.c_uint32
+        L.so_spann_kmeans.argtypes = [f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u32p, f32p]
+        L.so_spann_assign.restype = None
+        L.so_spann_assign.argtypes = [f32p, C.c_uint64, C.c_uint32, f32p, C.c_uint32, C.c_int, u32p]
+        L.so_spann_search.restype = C.c_uint32
+        L.so_spann_search.argtypes = [f32p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, u64p, u32p, u8p, f32p, C.c_uint32,
+                                      C.c_uint32, C.c_uint32, f32p, C.c_uint32, u32p, f32p, u32p]
         L.so_recall_at_k.restype = C.c_double
         L.so_recall_at_k.argtypes = [u32p, u32p, u32p, u32p, C.c_uint32, C.c_uint32]
         _lib = L
@@ -590,3 +603,87 @@ class PQOracle:
                                _p(self.codes, C.c_uint8), self.ids.size, _p(q, C.c_float), topk, _p(ids, C.c_uint32),
                                _p(dist, C.c_float))
         return ids[:r].copy(), dist[:r].copy()
+
+
+# ---------------------------------------------------------------------------------------------
+# SPANN partitioned index (spann_oracle.c): reference src/vector_db/spann.rs
+# ---------------------------------------------------------------------------------------------
+class SpannOracle:
+    """SpannIndex restated on the CPU: build / insert / search.  Posting lists are kept per partition as
+    (ids, codes) and flattened to CSR for the C search."""
+
+    def __init__(self, dim=384, num_partitions=None, num_probes=10, kmeans_iterations=25, metric=METRIC_NEG_DOT,
+                 use_pq=True, pq_iterations=20):
+        self.dim, self.num_partitions_cfg, self.num_probes = dim, num_partitions, num_probes
+        self.iterations, self.metric, self.use_pq, self.pq_iterations = kmeans_iterations, metric, use_pq, pq_iterations
+        self.centroids = np.zeros((0, dim), np.float32)
+        self.pq = None
+        self.part_ids, self.part_codes = [], []
+
+    def compute_partitions(self, n):
+        """SpannConfig::compute_partitions (:136-139)"""
+        import math
+        return self.num_partitions_cfg or max(int(math.ceil(math.sqrt(float(n)))), 1)
+
+    def __len__(self):
+        return sum(len(p) for p in self.part_ids)
+
+    def build(self, vectors, seed=0, order=None, pq_orders=None):
+        v = _f32(vectors)
+        if v.shape[0] == 0:
+            raise ValueError("Cannot build index from empty vectors")
+        if not self.use_pq:
+            raise ValueError("SPANN requires PQ (use_pq=true): posting lists store only PQ codes")
+        if v.shape[1] != self.dim:
+            raise ValueError(f"Vector dimension {v.shape[1]} doesn't match config {self.dim}")
+        n = v.shape[0]
+        k = self.compute_partitions(n)
+        rng = np.random.default_rng(seed)
+        self.order = rng.permutation(n).astype(np.uint32) if order is None else np.ascontiguousarray(order, np.uint32)
+        self.centroids = np.zeros((k, self.dim), np.float32)
+        self.kmeans_iterations_run = int(lib().so_spann_kmeans(_p(v, C.c_float), n, self.dim, k, self.iterations, self.metric,
+                                                               _p(self.order, C.c_uint32), _p(self.centroids, C.c_float)))
+        self.pq = PQOracle(self.dim, kmeans_iterations=self.pq_iterations)
+        self.pq_orders = self.pq.shuffled_orders(n, seed + 1) if pq_orders is None else pq_orders
+        self.pq.train(v, orders=self.pq_orders)
+        part = np.zeros(n, np.uint32)
+        lib().so_spann_assign(_p(v, C.c_float), n, self.dim, _p(self.centroids, C.c_float), k, self.metric, _p(part, C.c_uint32))
+        codes = self.pq.encode(v)
+        self.part_ids = [np.nonzero(part == p)[0].astype(np.uint32) for p in range(k)]       # vector order inside a partition
+        self.part_codes = [codes[i] for i in self.part_ids]
+        return self
+
+    def insert(self, vector_id, vector):
+        """SpannIndex::insert (:1006-1051)"""
+        if self.centroids.shape[0] == 0:
+            raise ValueError("Cannot insert into empty index - build first")
+        v = _f32(vector)
+        p = int(lib().so_spann_nearest_centroid(_p(v, C.c_float), _p(self.centroids, C.c_float), self.centroids.shape[0],
+                                                self.dim, self.metric))
+        self.part_ids[p] = np.concatenate([self.part_ids[p], np.array([vector_id], np.uint32)])
+        self.part_codes[p] = np.vstack([self.part_codes[p], self.pq.encode(v[None, :])])
+        return p
+
+    def csr(self):
+        off = np.zeros(len(self.part_ids) + 1, np.uint64)
+        off[1:] = np.cumsum([len(p) for p in self.part_ids])
+        ids = np.concatenate(self.part_ids).astype(np.uint32) if len(self) else np.zeros(0, np.uint32)
+        codes = np.ascontiguousarray(np.vstack(self.part_codes), np.uint8) if len(self) else np.zeros((0, self.pq.m), np.uint8)
+        return off, ids, codes
+
+    def search(self, query, k, with_probes=False):
+        q = _f32(query)
+        if self.centroids.shape[0] == 0:
+            return (np.zeros(0, np.uint32), np.zeros(0, np.float32))
+        if q.size != self.dim:
+            raise ValueError(f"Query dimension {q.size} doesn't match index dimension {self.dim}")
+        off, ids, codes = self.csr()
+        out_i = np.zeros(max(k, 1), np.uint32)
+        out_d = np.zeros(max(k, 1), np.float32)
+        probes = np.zeros(max(self.num_probes, 1), np.uint32)
+        r = lib().so_spann_search(_p(self.centroids, C.c_float), self.centroids.shape[0], self.dim, self.metric, self.num_probes,
+                                  _p(off, C.c_uint64), _p(ids, C.c_uint32), _p(codes, C.c_uint8),
+                                  _p(self.pq.centroids, C.c_float), self.pq.m, self.pq.k, self.pq.ds, _p(q, C.c_float), k,
+                                  _p(out_i, C.c_uint32), _p(out_d, C.c_float), _p(probes, C.c_uint32))
+        res = (out_i[:r].copy(), out_d[:r].copy())
+        return res + (probes[:min(self.num_probes, self.centroids.shape[0])].copy(),) if with_probes else res
