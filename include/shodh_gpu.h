@@ -270,6 +270,36 @@ SG_API int sg_pq_add(sg_pq *p, const uint32_t *ids, const float *rows_f32, uint6
 SG_API int sg_pq_search(sg_pq *p, const float *queries_f32, uint32_t b, uint32_t k, uint32_t *ids_out, float *dist_out,
                         uint32_t *counts_out);
 
+/* ---- SPANN partitioned index: src/vector_db/spann.rs ---------------------------------
+ * SpannIndex::{build :363-463, search :574-693, insert :1006-1051}: P = ceil(sqrt(n)) k-means partitions over the
+ * full vectors, a product quantizer, per partition a posting list of (vector id, PQ code).  A search ranks the
+ * partitions by compute_distance(query, centroid) (:562-572; ties by index), probes the first num_probes and keeps
+ * the k smallest ADC distances, sorted (distance total_cmp, id).  One CTA per query does all of it; every f32
+ * operation is the reference's, so probes, distances and ids match the CPU path bit for bit.
+ *   sg_spann_build   `order` [n] and `pq_orders` [dim/8][n] are the shuffled index orders the reference draws from
+ *                    thread_rng inside its two k-means; num_partitions = 0 -> ceil(sqrt(n)); PQ = PQConfig::for_dimension.
+ *   sg_spann_create  from arrays (an index built elsewhere): centroids [P,dim], PQ centroids [dim/ds][kc][ds],
+ *                    posting lists as CSR part_off [P+1] + ids / codes grouped by partition.
+ *   sg_spann_get     the same arrays back (any pointer may be NULL).
+ * metric: 0 NormalizedDotProduct / 2 Cosine -> 1 - dot, 1 Euclidean.  Limits: P <= 4096, k <= 512.
+ * STATUS: compiled for sm_100a and covered by tests/test_spann_gpu.py, which have NOT run on a GPU yet (written
+ * after this round's GPU budget was spent); the tests are opt-in (SHODH_UNVERIFIED=1) until they have. */
+typedef struct sg_spann sg_spann;
+SG_API int sg_spann_build(sg_spann **out, int device, uint32_t dim, uint32_t num_partitions, uint32_t num_probes,
+                          uint32_t kmeans_iterations, int metric, const float *vectors_f32, uint64_t n,
+                          const uint32_t *order, uint32_t pq_iterations, const uint32_t *pq_orders);
+SG_API int sg_spann_create(sg_spann **out, int device, uint32_t dim, uint32_t num_partitions, uint32_t num_probes, int metric,
+                           const float *centroids, const float *pq_centroids, uint32_t subvec_dim, uint32_t num_centroids,
+                           const uint64_t *part_off, const uint32_t *ids, const uint8_t *codes);
+SG_API void sg_spann_destroy(sg_spann *s);
+SG_API int sg_spann_info(sg_spann *s, uint32_t *num_partitions_out, uint64_t *len_out, uint32_t *num_probes_out);
+SG_API int sg_spann_get(sg_spann *s, float *centroids_out, float *pq_centroids_out, uint64_t *part_off_out,
+                        uint32_t *ids_out, uint8_t *codes_out);
+SG_API int sg_spann_set_probes(sg_spann *s, uint32_t num_probes);
+SG_API int sg_spann_insert(sg_spann *s, uint32_t vector_id, const float *vector_f32);
+SG_API int sg_spann_search(sg_spann *s, const float *queries_f32, uint32_t b, uint32_t k, uint32_t *ids_out,
+                           float *dist_out, uint32_t *counts_out);
+
 /* CUDA-event timing of the scan kernel(s) inside each search (bench.py roofline): with
  * profiling on, every search records an event pair around its sweep launches on the stream
  * it runs on (no synchronisation).  sg_store_profile_read waits for the last recorded

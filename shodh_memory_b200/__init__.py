@@ -8,6 +8,7 @@ from .capi import SgError
 from .encoder import GpuMiniLM, export_bert_weights, random_minilm_state_dict
 from .pq import GpuProductQuantizer
 from .relevance import fuse_topk, RRFusion
+from .spann import GpuSpannIndex
 from .vector_store import GpuVectorStore, merge_topk_device, vama_inspect, top_k_similar, cosine_similarity
 
 capi.lib()  # load now: no lazy CPU fallback, a missing extension is an ImportError
@@ -35,5 +36,5 @@ def __getattr__(name):  # torch-dependent helpers load lazily (the C ABI itself 
     raise AttributeError(name)
 
 
-__all__ = ["GpuVectorStore", "ShardedGpuStore", "GpuMiniLM", "GpuProductQuantizer", "export_bert_weights", "merge_topk_device", "top_k_similar", "cosine_similarity", "fuse_topk", "RRFusion", "SgError", "version", "kernel_launch_count",
+__all__ = ["GpuVectorStore", "ShardedGpuStore", "GpuMiniLM", "GpuProductQuantizer", "GpuSpannIndex", "export_bert_weights", "merge_topk_device", "top_k_similar", "cosine_similarity", "fuse_topk", "RRFusion", "SgError", "version", "kernel_launch_count",
            "device_count", "capi"]

@@ -128,6 +128,17 @@ def lib() -> C.CDLL:
     L.sg_pq_table.argtypes = [vp, f32p, f32p]
     L.sg_pq_add.argtypes = [vp, u32p, f32p, C.c_uint64]
     L.sg_pq_search.argtypes = [vp, f32p, C.c_uint32, C.c_uint32, u32p, f32p, u32p]
+    L.sg_spann_build.argtypes = [C.POINTER(vp), C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, f32p, C.c_uint64,
+                                 u32p, C.c_uint32, u32p]
+    L.sg_spann_create.argtypes = [C.POINTER(vp), C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, f32p, f32p, C.c_uint32,
+                                  C.c_uint32, u64p, u32p, u8p]
+    L.sg_spann_destroy.argtypes = [vp]
+    L.sg_spann_destroy.restype = None
+    L.sg_spann_info.argtypes = [vp, u32p, u64p, u32p]
+    L.sg_spann_get.argtypes = [vp, f32p, f32p, u64p, u32p, u8p]
+    L.sg_spann_set_probes.argtypes = [vp, C.c_uint32]
+    L.sg_spann_insert.argtypes = [vp, C.c_uint32, f32p]
+    L.sg_spann_search.argtypes = [vp, f32p, C.c_uint32, C.c_uint32, u32p, f32p, u32p]
     L.sg_encoder_create.argtypes = [C.POINTER(vp), C.c_int, C.c_char_p]
     L.sg_encoder_destroy.argtypes = [vp]
     L.sg_encoder_destroy.restype = None
