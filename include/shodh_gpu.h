@@ -281,9 +281,7 @@ SG_API int sg_pq_search(sg_pq *p, const float *queries_f32, uint32_t b, uint32_t
  *   sg_spann_create  from arrays (an index built elsewhere): centroids [P,dim], PQ centroids [dim/ds][kc][ds],
  *                    posting lists as CSR part_off [P+1] + ids / codes grouped by partition.
  *   sg_spann_get     the same arrays back (any pointer may be NULL).
- * metric: 0 NormalizedDotProduct / 2 Cosine -> 1 - dot, 1 Euclidean.  Limits: P <= 4096, k <= 512.
- * STATUS: compiled for sm_100a and covered by tests/test_spann_gpu.py, which have NOT run on a GPU yet (written
- * after this round's GPU budget was spent); the tests are opt-in (SHODH_UNVERIFIED=1) until they have. */
+ * metric: 0 NormalizedDotProduct / 2 Cosine -> 1 - dot, 1 Euclidean.  Limits: P <= 4096, k <= 512. */
 typedef struct sg_spann sg_spann;
 SG_API int sg_spann_build(sg_spann **out, int device, uint32_t dim, uint32_t num_partitions, uint32_t num_probes,
                           uint32_t kmeans_iterations, int metric, const float *vectors_f32, uint64_t n,
