@@ -598,6 +598,65 @@ def main():
             pq.close()
         except Exception as ex:
             pq_res = dict(error=repr(ex))
+    # ---------------- SPANN: one CTA per query over a 10M-entry partitioned PQ index ----------------
+    # The index is synthetic at full scale (random unit centroids, random codebooks and codes, equal-sized posting lists):
+    # the search cost depends on the shapes (P = ceil(sqrt(n)) centroids, num_probes x n / P entries per query), not on the
+    # values; 4 queries are checked id-for-id against the oracle port of SpannIndex::search on the same arrays.
+    spann_res = None
+    if rank == 0 and world == 1 and os.environ.get("SG_BENCH_SPANN", "1") == "1":
+        try:
+            import ctypes as C
+            from oracle import oracle as o
+            sp_rows = int(os.environ.get("SG_BENCH_SPANN_ROWS", 10_000_000))
+            rng = np.random.default_rng(SEED + 13)
+            P = int(np.ceil(np.sqrt(sp_rows)))
+            cent = rng.standard_normal((P, DIM)).astype(np.float32)
+            cent /= np.linalg.norm(cent, axis=1, keepdims=True)
+            pqc = (rng.standard_normal((DIM // 8, 256, 8)) * 0.05).astype(np.float32)
+            off = np.linspace(0, sp_rows, P + 1).astype(np.uint64)
+            ids_sp = np.arange(sp_rows, dtype=np.uint32)
+            codes_sp = rng.integers(0, 256, (sp_rows, DIM // 8), dtype=np.uint8)
+            t0 = time.perf_counter()
+            sp = sg.GpuSpannIndex.from_arrays(cent, pqc, off, ids_sp, codes_sp, num_probes=10, device=local_rank)
+            load_s = time.perf_counter() - t0
+            sq = rng.standard_normal((BATCH, DIM)).astype(np.float32)
+            sq = np.ascontiguousarray(sq / np.linalg.norm(sq, axis=1, keepdims=True), np.float32)
+            for _ in range(3):
+                gi, gd, gc = sp.search_batch(sq, TOPK)
+            t0 = time.perf_counter()
+            reps = 20
+            for _ in range(reps):
+                sp.search_batch(sq, TOPK)
+            ms = (time.perf_counter() - t0) * 1e3 / reps
+            t0 = time.perf_counter()
+            for i in range(50):
+                sp.search_batch(sq[i:i + 1], TOPK)
+            ms1 = (time.perf_counter() - t0) * 1e3 / 50
+            f32p, u32p, u64p, u8p = (C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint8))
+            same, cpu_ms = True, 0.0
+            for i in range(4):
+                oi = np.zeros(TOPK, np.uint32); od = np.zeros(TOPK, np.float32)
+                t0 = time.perf_counter()
+                r = o.lib().so_spann_search(cent.ctypes.data_as(f32p), P, DIM, 0, 10, off.ctypes.data_as(u64p),
+                                            ids_sp.ctypes.data_as(u32p), codes_sp.ctypes.data_as(u8p), pqc.ctypes.data_as(f32p),
+                                            DIM // 8, 256, 8, sq[i].ctypes.data_as(f32p), TOPK, oi.ctypes.data_as(u32p),
+                                            od.ctypes.data_as(f32p), None)
+                cpu_ms += (time.perf_counter() - t0) * 1e3 / 4
+                same = same and r == int(gc[i]) and np.array_equal(gi[i, :r], oi[:r]) and \
+                    np.array_equal(gd[i, :r].view(np.uint32), od[:r].view(np.uint32))
+            entries = 10.0 * sp_rows / P
+            bytes_q = P * DIM * 4 + entries * (DIM // 8 + 4)
+            spann_res = dict(rows=sp_rows, partitions=P, num_probes=10, entries_scanned_per_query=entries, upload_s=load_s,
+                             batch256=dict(host_api_ms=ms, queries_per_s=BATCH / (ms * 1e-3)), batch1_host_api_ms=ms1,
+                             algorithmic_bytes_per_query=bytes_q,
+                             achieved_GBps_batch256=bytes_q * BATCH / (ms * 1e-3) / 1e9,
+                             cpu_reference=dict(ms_per_query_1_thread=cpu_ms, ids_and_distances_identical_to_device=bool(same),
+                                                kind="port (oracle/spann_oracle.c restatement of SpannIndex::search), 4 queries"),
+                             kernel="spann_search_kernel (one CTA per query: ADC table, centroid ranking, probed posting lists, top-k)")
+            sp.close()
+            del codes_sp, ids_sp
+        except Exception as ex:
+            spann_res = dict(error=repr(ex))
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
@@ -672,6 +731,7 @@ def main():
         encoder=enc_res,
         graph_index=ann_res,
         product_quantization=pq_res,
+        spann=spann_res,
         gpu_launches=int(launches), clocks=clocks)
     if cpu:
         line["cpu_baseline"] = dict(value=cpu["value"], unit=UNIT, cores=cpu["cores"], kind=cpu["kind"], sample=cpu["sample"])
