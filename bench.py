@@ -152,6 +152,159 @@ def cpu_reference(steps: int, warmup: int, budget_s: float = 90.0):
                 ms_per_step=t * 1e3)
 
 
+# ----------------------------------------------------------------------------------------------
+# Optional legs that run in a CHILD process (`bench.py --leg NAME`): a fault or a hang inside one of them
+# cannot take the headline line down with it (the parent waits with a timeout and records the outcome).
+# ----------------------------------------------------------------------------------------------
+def leg_pq(sg, local_rank):
+    """Product Quantization (SURVEY 8f-4): CompressedVectorStore::search on the device."""
+    from oracle import oracle as o
+    pq_rows = int(os.environ.get("SG_BENCH_PQ_ROWS", 1_000_000))
+    rng = np.random.default_rng(SEED + 11)
+    A = rng.standard_normal((12, DIM)).astype(np.float32)
+
+    def pq_rows_gen(m):
+        x = rng.standard_normal((m, 12)).astype(np.float32) @ A + 0.17 * rng.standard_normal((m, DIM)).astype(np.float32)
+        return np.ascontiguousarray(x / np.linalg.norm(x, axis=1, keepdims=True), np.float32)
+    train = pq_rows_gen(5000)
+    orders = np.stack([rng.permutation(5000) for _ in range(DIM // 8)]).astype(np.uint32)
+    t0 = time.perf_counter()
+    pq = sg.GpuProductQuantizer.train(train, orders, kmeans_iterations=20, device=local_rank)   # PQConfig::minilm()
+    train_s = time.perf_counter() - t0
+    t_add = 0.0
+    first_chunk = None
+    for lo in range(0, pq_rows, 100_000):
+        m = min(100_000, pq_rows - lo)
+        x = pq_rows_gen(m)
+        if first_chunk is None:
+            first_chunk = x
+        t0 = time.perf_counter()
+        pq.add(np.arange(lo, lo + m, dtype=np.uint32), x)
+        t_add += time.perf_counter() - t0
+    pq_q = np.ascontiguousarray(first_chunk[:BATCH] + 0.01 * rng.standard_normal((BATCH, DIM)).astype(np.float32), np.float32)
+    for _ in range(2):
+        pq.search_batch(pq_q, TOPK)
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        gi, gd, gc = pq.search_batch(pq_q, TOPK)
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    t0 = time.perf_counter()
+    for i in range(20):
+        pq.search_batch(pq_q[i:i + 1], TOPK)
+    ms1 = (time.perf_counter() - t0) * 1e3 / 20
+    # CPU: the oracle port of CompressedVectorStore::search on a 100k-vector slice of the same store, 1 thread
+    ref = o.PQOracle(DIM)
+    ref.centroids, ref.k = pq.centroids, pq.num_centroids
+    ref.ids = np.arange(100_000, dtype=np.uint32)
+    ref.codes = pq.encode(first_chunk)            # device codes == oracle codes (tests/test_pq_gpu.py); saves 10 s of host encode
+    t0 = time.perf_counter()
+    for i in range(4):
+        ref.search(pq_q[i], TOPK)
+    cpu_ms = (time.perf_counter() - t0) * 1e3 / 4 * (pq_rows / 100_000)
+    sweeps = (BATCH + 1) // 2
+    nbytes = float(pq_rows) * (DIM // 8 + 4)
+    pq_res = dict(rows=pq_rows, code_bytes=DIM // 8, train_s_5000x20=train_s, encode_add_rows_per_s=pq_rows / t_add,
+                  batch256=dict(host_api_ms=ms, queries_per_s=BATCH / (ms * 1e-3), sweeps=sweeps,
+                                roofline=dict(bound="hbm (code stream) / shared-memory gathers", algorithmic_bytes_per_sweep=nbytes,
+                                              achieved=nbytes * sweeps / (ms * 1e-3) / 1e9, peak=peaks()[0], unit="GB/s",
+                                              frac=nbytes * sweeps / (ms * 1e-3) / 1e9 / peaks()[0],
+                                              note="wall clock of sg_pq_search incl. H2D/D2H and table build; 2 queries per sweep")),
+                  batch1_host_api_ms=ms1,
+                  cpu_reference=dict(ms_per_query_1_thread=cpu_ms, kind="port (oracle/pq_oracle.c), 100k-vector slice scaled linearly"),
+                  kernel="pq_scan_kernel (48 table look-ups per vector in the reference's order; ids and distances bit-identical to the CPU path)")
+    pq.close()
+    return pq_res
+
+
+def leg_spann(sg, local_rank):
+    """SPANN: one CTA per query over a 10M-entry partitioned PQ index.  The index is synthetic at full
+    scale (random unit centroids, random codebooks and codes, equal-sized posting lists): the search cost depends on the
+    shapes (P = ceil(sqrt(n)) centroids, num_probes x n / P entries per query), not on the values; 4 queries are
+    checked id-for-id against the oracle port of SpannIndex::search on the same arrays."""
+    import ctypes as C
+    from oracle import oracle as o
+    sp_rows = int(os.environ.get("SG_BENCH_SPANN_ROWS", 10_000_000))
+    rng = np.random.default_rng(SEED + 13)
+    P = int(np.ceil(np.sqrt(sp_rows)))
+    cent = rng.standard_normal((P, DIM)).astype(np.float32)
+    cent /= np.linalg.norm(cent, axis=1, keepdims=True)
+    pqc = (rng.standard_normal((DIM // 8, 256, 8)) * 0.05).astype(np.float32)
+    off = np.linspace(0, sp_rows, P + 1).astype(np.uint64)
+    ids_sp = np.arange(sp_rows, dtype=np.uint32)
+    codes_sp = rng.integers(0, 256, (sp_rows, DIM // 8), dtype=np.uint8)
+    t0 = time.perf_counter()
+    sp = sg.GpuSpannIndex.from_arrays(cent, pqc, off, ids_sp, codes_sp, num_probes=10, device=local_rank)
+    load_s = time.perf_counter() - t0
+    sq = rng.standard_normal((BATCH, DIM)).astype(np.float32)
+    sq = np.ascontiguousarray(sq / np.linalg.norm(sq, axis=1, keepdims=True), np.float32)
+    for _ in range(3):
+        gi, gd, gc = sp.search_batch(sq, TOPK)
+    t0 = time.perf_counter()
+    reps = 20
+    for _ in range(reps):
+        sp.search_batch(sq, TOPK)
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    t0 = time.perf_counter()
+    for i in range(50):
+        sp.search_batch(sq[i:i + 1], TOPK)
+    ms1 = (time.perf_counter() - t0) * 1e3 / 50
+    f32p, u32p, u64p, u8p = (C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint8))
+    same, cpu_ms = True, 0.0
+    for i in range(4):
+        oi = np.zeros(TOPK, np.uint32); od = np.zeros(TOPK, np.float32)
+        t0 = time.perf_counter()
+        r = o.lib().so_spann_search(cent.ctypes.data_as(f32p), P, DIM, 0, 10, off.ctypes.data_as(u64p),
+                                    ids_sp.ctypes.data_as(u32p), codes_sp.ctypes.data_as(u8p), pqc.ctypes.data_as(f32p),
+                                    DIM // 8, 256, 8, sq[i].ctypes.data_as(f32p), TOPK, oi.ctypes.data_as(u32p),
+                                    od.ctypes.data_as(f32p), None)
+        cpu_ms += (time.perf_counter() - t0) * 1e3 / 4
+        same = same and r == int(gc[i]) and np.array_equal(gi[i, :r], oi[:r]) and \
+            np.array_equal(gd[i, :r].view(np.uint32), od[:r].view(np.uint32))
+    entries = 10.0 * sp_rows / P
+    bytes_q = P * DIM * 4 + entries * (DIM // 8 + 4)
+    spann_res = dict(rows=sp_rows, partitions=P, num_probes=10, entries_scanned_per_query=entries, upload_s=load_s,
+                     batch256=dict(host_api_ms=ms, queries_per_s=BATCH / (ms * 1e-3)), batch1_host_api_ms=ms1,
+                     algorithmic_bytes_per_query=bytes_q,
+                     achieved_GBps_batch256=bytes_q * BATCH / (ms * 1e-3) / 1e9,
+                     cpu_reference=dict(ms_per_query_1_thread=cpu_ms, ids_and_distances_identical_to_device=bool(same),
+                                        kind="port (oracle/spann_oracle.c restatement of SpannIndex::search), 4 queries"),
+                     kernel="spann_search_kernel (one CTA per query: ADC table, centroid ranking, probed posting lists, top-k)")
+    sp.close()
+    return spann_res
+
+
+LEGS = {"pq": leg_pq, "spann": leg_spann}
+
+
+def run_leg_child(name, local_rank):
+    """child side of --leg: one JSON line on stdout"""
+    try:
+        import __graft_entry__ as ge
+        ge.build()
+        import shodh_memory_b200 as sg
+        res = LEGS[name](sg, local_rank)
+    except Exception as ex:  # noqa: BLE001
+        res = dict(error=repr(ex))
+    print(json.dumps(res), flush=True)
+    return 0
+
+
+def run_leg(name, local_rank, timeout_s=240):
+    """parent side: run the leg in its own process on the same GPU"""
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--leg", name, "--leg-device", str(local_rank)],
+                             capture_output=True, text=True, timeout=timeout_s)
+        lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+        if not lines:
+            return dict(error=f"leg {name}: no result (exit {out.returncode}): {out.stderr[-300:]}")
+        return json.loads(lines[-1])
+    except subprocess.TimeoutExpired:
+        return dict(error=f"leg {name}: timed out after {timeout_s} s (child killed)")
+    except Exception as ex:  # noqa: BLE001
+        return dict(error=f"leg {name}: {ex!r}")
+
+
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -203,7 +356,11 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--leg", default=None, choices=sorted(LEGS))          # internal: run one optional leg and print its JSON
+    ap.add_argument("--leg-device", type=int, default=0)
     args = ap.parse_args()
+    if args.leg:
+        return run_leg_child(args.leg, args.leg_device)
     steps, warmup = max(args.steps, 1), max(args.warmup, 3 if args.impl == "b200" else 1)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -536,127 +693,12 @@ def main():
             g.close()
         except Exception as ex:  # the headline line must still print
             ann_res = dict(error=repr(ex))
-    # ---------------- Product Quantization: CompressedVectorStore::search on the device ----------------
-    pq_res = None
+    # ---------------- Product Quantization and SPANN: each in its own child process ----------------
+    pq_res = spann_res = None
     if rank == 0 and world == 1 and os.environ.get("SG_BENCH_PQ", "1") == "1":
-        try:
-            from oracle import oracle as o
-            pq_rows = int(os.environ.get("SG_BENCH_PQ_ROWS", 1_000_000))
-            rng = np.random.default_rng(SEED + 11)
-            A = rng.standard_normal((12, DIM)).astype(np.float32)
-
-            def pq_rows_gen(m):
-                x = rng.standard_normal((m, 12)).astype(np.float32) @ A + 0.17 * rng.standard_normal((m, DIM)).astype(np.float32)
-                return np.ascontiguousarray(x / np.linalg.norm(x, axis=1, keepdims=True), np.float32)
-            train = pq_rows_gen(5000)
-            orders = np.stack([rng.permutation(5000) for _ in range(DIM // 8)]).astype(np.uint32)
-            t0 = time.perf_counter()
-            pq = sg.GpuProductQuantizer.train(train, orders, kmeans_iterations=20, device=local_rank)   # PQConfig::minilm()
-            train_s = time.perf_counter() - t0
-            t_add = 0.0
-            first_chunk = None
-            for lo in range(0, pq_rows, 100_000):
-                m = min(100_000, pq_rows - lo)
-                x = pq_rows_gen(m)
-                if first_chunk is None:
-                    first_chunk = x
-                t0 = time.perf_counter()
-                pq.add(np.arange(lo, lo + m, dtype=np.uint32), x)
-                t_add += time.perf_counter() - t0
-            pq_q = np.ascontiguousarray(first_chunk[:BATCH] + 0.01 * rng.standard_normal((BATCH, DIM)).astype(np.float32), np.float32)
-            for _ in range(2):
-                pq.search_batch(pq_q, TOPK)
-            t0 = time.perf_counter()
-            reps = 5
-            for _ in range(reps):
-                gi, gd, gc = pq.search_batch(pq_q, TOPK)
-            ms = (time.perf_counter() - t0) * 1e3 / reps
-            t0 = time.perf_counter()
-            for i in range(20):
-                pq.search_batch(pq_q[i:i + 1], TOPK)
-            ms1 = (time.perf_counter() - t0) * 1e3 / 20
-            # CPU: the oracle port of CompressedVectorStore::search on a 100k-vector slice of the same store, 1 thread
-            ref = o.PQOracle(DIM)
-            ref.centroids, ref.k = pq.centroids, pq.num_centroids
-            ref.ids = np.arange(100_000, dtype=np.uint32)
-            ref.codes = pq.encode(first_chunk)            # device codes == oracle codes (tests/test_pq_gpu.py); saves 10 s of host encode
-            t0 = time.perf_counter()
-            for i in range(4):
-                ref.search(pq_q[i], TOPK)
-            cpu_ms = (time.perf_counter() - t0) * 1e3 / 4 * (pq_rows / 100_000)
-            sweeps = (BATCH + 1) // 2
-            nbytes = float(pq_rows) * (DIM // 8 + 4)
-            pq_res = dict(rows=pq_rows, code_bytes=DIM // 8, train_s_5000x20=train_s, encode_add_rows_per_s=pq_rows / t_add,
-                          batch256=dict(host_api_ms=ms, queries_per_s=BATCH / (ms * 1e-3), sweeps=sweeps,
-                                        roofline=dict(bound="hbm (code stream) / shared-memory gathers", algorithmic_bytes_per_sweep=nbytes,
-                                                      achieved=nbytes * sweeps / (ms * 1e-3) / 1e9, peak=peaks()[0], unit="GB/s",
-                                                      frac=nbytes * sweeps / (ms * 1e-3) / 1e9 / peaks()[0],
-                                                      note="wall clock of sg_pq_search incl. H2D/D2H and table build; 2 queries per sweep")),
-                          batch1_host_api_ms=ms1,
-                          cpu_reference=dict(ms_per_query_1_thread=cpu_ms, kind="port (oracle/pq_oracle.c), 100k-vector slice scaled linearly"),
-                          kernel="pq_scan_kernel (48 table look-ups per vector in the reference's order; ids and distances bit-identical to the CPU path)")
-            pq.close()
-        except Exception as ex:
-            pq_res = dict(error=repr(ex))
-    # ---------------- SPANN: one CTA per query over a 10M-entry partitioned PQ index ----------------
-    # The index is synthetic at full scale (random unit centroids, random codebooks and codes, equal-sized posting lists):
-    # the search cost depends on the shapes (P = ceil(sqrt(n)) centroids, num_probes x n / P entries per query), not on the
-    # values; 4 queries are checked id-for-id against the oracle port of SpannIndex::search on the same arrays.
-    spann_res = None
+        pq_res = run_leg("pq", local_rank)
     if rank == 0 and world == 1 and os.environ.get("SG_BENCH_SPANN", "1") == "1":
-        try:
-            import ctypes as C
-            from oracle import oracle as o
-            sp_rows = int(os.environ.get("SG_BENCH_SPANN_ROWS", 10_000_000))
-            rng = np.random.default_rng(SEED + 13)
-            P = int(np.ceil(np.sqrt(sp_rows)))
-            cent = rng.standard_normal((P, DIM)).astype(np.float32)
-            cent /= np.linalg.norm(cent, axis=1, keepdims=True)
-            pqc = (rng.standard_normal((DIM // 8, 256, 8)) * 0.05).astype(np.float32)
-            off = np.linspace(0, sp_rows, P + 1).astype(np.uint64)
-            ids_sp = np.arange(sp_rows, dtype=np.uint32)
-            codes_sp = rng.integers(0, 256, (sp_rows, DIM // 8), dtype=np.uint8)
-            t0 = time.perf_counter()
-            sp = sg.GpuSpannIndex.from_arrays(cent, pqc, off, ids_sp, codes_sp, num_probes=10, device=local_rank)
-            load_s = time.perf_counter() - t0
-            sq = rng.standard_normal((BATCH, DIM)).astype(np.float32)
-            sq = np.ascontiguousarray(sq / np.linalg.norm(sq, axis=1, keepdims=True), np.float32)
-            for _ in range(3):
-                gi, gd, gc = sp.search_batch(sq, TOPK)
-            t0 = time.perf_counter()
-            reps = 20
-            for _ in range(reps):
-                sp.search_batch(sq, TOPK)
-            ms = (time.perf_counter() - t0) * 1e3 / reps
-            t0 = time.perf_counter()
-            for i in range(50):
-                sp.search_batch(sq[i:i + 1], TOPK)
-            ms1 = (time.perf_counter() - t0) * 1e3 / 50
-            f32p, u32p, u64p, u8p = (C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint8))
-            same, cpu_ms = True, 0.0
-            for i in range(4):
-                oi = np.zeros(TOPK, np.uint32); od = np.zeros(TOPK, np.float32)
-                t0 = time.perf_counter()
-                r = o.lib().so_spann_search(cent.ctypes.data_as(f32p), P, DIM, 0, 10, off.ctypes.data_as(u64p),
-                                            ids_sp.ctypes.data_as(u32p), codes_sp.ctypes.data_as(u8p), pqc.ctypes.data_as(f32p),
-                                            DIM // 8, 256, 8, sq[i].ctypes.data_as(f32p), TOPK, oi.ctypes.data_as(u32p),
-                                            od.ctypes.data_as(f32p), None)
-                cpu_ms += (time.perf_counter() - t0) * 1e3 / 4
-                same = same and r == int(gc[i]) and np.array_equal(gi[i, :r], oi[:r]) and \
-                    np.array_equal(gd[i, :r].view(np.uint32), od[:r].view(np.uint32))
-            entries = 10.0 * sp_rows / P
-            bytes_q = P * DIM * 4 + entries * (DIM // 8 + 4)
-            spann_res = dict(rows=sp_rows, partitions=P, num_probes=10, entries_scanned_per_query=entries, upload_s=load_s,
-                             batch256=dict(host_api_ms=ms, queries_per_s=BATCH / (ms * 1e-3)), batch1_host_api_ms=ms1,
-                             algorithmic_bytes_per_query=bytes_q,
-                             achieved_GBps_batch256=bytes_q * BATCH / (ms * 1e-3) / 1e9,
-                             cpu_reference=dict(ms_per_query_1_thread=cpu_ms, ids_and_distances_identical_to_device=bool(same),
-                                                kind="port (oracle/spann_oracle.c restatement of SpannIndex::search), 4 queries"),
-                             kernel="spann_search_kernel (one CTA per query: ADC table, centroid ranking, probed posting lists, top-k)")
-            sp.close()
-            del codes_sp, ids_sp
-        except Exception as ex:
-            spann_res = dict(error=repr(ex))
+        spann_res = run_leg("spann", local_rank)
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:

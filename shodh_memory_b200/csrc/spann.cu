@@ -304,6 +304,19 @@ int sp_alloc(sg_spann **out, int device, uint32_t dim, uint32_t n_part, uint32_t
         set_error("unknown metric %d", metric);
         return SG_ERR_INVALID;
     }
+    {
+        int ndev = 0;
+        cudaError_t ce = cudaGetDeviceCount(&ndev);
+        if (ce != cudaSuccess || ndev == 0) {
+            set_error("no CUDA device available (%s); libshodh_gpu has no CPU fallback",
+                      ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
+            return SG_ERR_NO_DEVICE;
+        }
+        if (device < 0 || device >= ndev) {
+            set_error("device ordinal %d out of range (0..%d)", device, ndev - 1);
+            return SG_ERR_INVALID;
+        }
+    }
     sg_spann *s = new (std::nothrow) sg_spann();
     if (!s) return SG_ERR_OOM;
     s->device = device;

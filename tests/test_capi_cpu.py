@@ -30,6 +30,18 @@ def test_no_cpu_fallback_without_gpu(sg):
     with pytest.raises(sg.SgError) as e:
         sg.GpuVectorStore(384, "f16")
     assert e.value.code == sg.capi.SG_ERR_NO_DEVICE
+    import numpy as np
+    with pytest.raises(sg.SgError) as e:                       # every other entry point that owns device state, too
+        sg.GpuProductQuantizer.from_centroids(np.zeros((48, 256, 8), np.float32))
+    assert e.value.code == sg.capi.SG_ERR_NO_DEVICE
+    with pytest.raises(sg.SgError) as e:
+        sg.GpuSpannIndex.from_arrays(np.zeros((4, 384), np.float32), np.zeros((48, 256, 8), np.float32),
+                                     np.zeros(5, np.uint64), np.zeros(0, np.uint32), np.zeros((0, 48), np.uint8))
+    assert e.value.code == sg.capi.SG_ERR_NO_DEVICE
+    with pytest.raises(sg.SgError) as e:
+        sg.top_k_similar(np.ones(32, np.float32), np.ones((3, 32), np.float32), 2)
+    assert e.value.code == sg.capi.SG_ERR_NO_DEVICE
+    assert "UBLKCP" in subprocess.run(["cuobjdump", "-sass", sg.capi.LIB_PATH], capture_output=True, text=True).stdout
 
 
 def test_product_package_does_not_import_the_oracle():
