@@ -127,3 +127,24 @@ def test_encoder_feeds_the_store_on_device(model_and_encoder, sg, oracle):
     assert np.array_equal(out_i.cpu().numpy().view(np.uint32)[0], rid)
     assert np.array_equal(out_d.cpu().numpy().view(np.uint32)[0], rdist.view(np.uint32))
     st.close()
+
+
+def test_batched_document_ingest_stays_on_the_device(model_and_encoder, sg):
+    """SURVEY 8f-4 batched ingest (retrieval.rs:668-676 -> minilm.rs:996): encode_batch output goes straight into
+    the store (sg_encoder_encode_device -> sg_store_append_device), no host round trip for the embeddings."""
+    import torch
+    model, enc = model_and_encoder
+    ids, mask = make_batch(48, 64, seed=21)
+    want = enc.encode_ids(ids, mask)                                   # the host-buffer form of the same encoder
+    d_ids, d_mask = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+    emb = torch.empty((48, 384), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    st = sg.GpuVectorStore(384, "f32")
+    enc.encode_ids_device(d_ids.data_ptr(), d_mask.data_ptr(), 48, 64, emb.data_ptr(), stream)
+    assert st.add_vectors_device(emb.data_ptr(), 48, stream) == 0      # same stream: ordered after the encoder
+    assert len(st) == 48
+    got = st.extract_all_vectors()
+    assert np.abs(got - want).max() <= 1e-6
+    for i in (0, 17, 47):                                              # every document finds itself
+        assert st.search(got[i], 1)[0][0] == i
+    st.close()
