@@ -293,7 +293,24 @@ SG_API void sg_spann_destroy(sg_spann *s);
 SG_API int sg_spann_info(sg_spann *s, uint32_t *num_partitions_out, uint64_t *len_out, uint32_t *num_probes_out);
 SG_API int sg_spann_get(sg_spann *s, float *centroids_out, float *pq_centroids_out, uint64_t *part_off_out,
                         uint32_t *ids_out, uint8_t *codes_out);
+SG_API int sg_spann_shape(sg_spann *s, uint32_t *dim_out, uint32_t *num_subvectors_out, uint32_t *num_centroids_out,
+                          uint32_t *subvec_dim_out, int *metric_out);
 SG_API int sg_spann_set_probes(sg_spann *s, uint32_t num_probes);
+/* SpannIndex::save_to_file / load_from_file / verify_index_file (spann.rs:750-1003, :1069-1083): the reference's
+ * "SPAN" v1 index file (128-byte header, centroids, PQ codebook, posting index, posting data; FNV-1a-64 checksum).
+ * The sg_spann_file_* functions are plain host code (no device): inspect = header + optional checksum check,
+ * read = the arrays sg_spann_create takes (sizes from inspect), write = the same arrays to a file the reference
+ * loads.  load_file / save_file compose them with sg_spann_create / sg_spann_get. */
+SG_API int sg_spann_file_inspect(const char *path, int verify_checksum, uint64_t *num_vectors_out, uint32_t *num_partitions_out,
+                                 uint32_t *dimension_out, uint32_t *num_subvectors_out, uint32_t *num_centroids_out,
+                                 uint32_t *subvec_dim_out, uint32_t *metric_out);
+SG_API int sg_spann_file_read(const char *path, float *centroids_out, float *pq_centroids_out, uint64_t *part_off_out,
+                              uint32_t *ids_out, uint8_t *codes_out);
+SG_API int sg_spann_file_write(const char *path, uint32_t dim, uint32_t num_partitions, uint32_t metric, const float *centroids,
+                               uint32_t num_subvectors, uint32_t num_centroids, uint32_t subvec_dim, const float *pq_centroids,
+                               const uint64_t *part_off, const uint32_t *ids, const uint8_t *codes);
+SG_API int sg_spann_load_file(sg_spann **out, int device, const char *path, uint32_t num_probes, int verify_checksum);
+SG_API int sg_spann_save_file(sg_spann *s, const char *path);
 SG_API int sg_spann_insert(sg_spann *s, uint32_t vector_id, const float *vector_f32);
 SG_API int sg_spann_search(sg_spann *s, const float *queries_f32, uint32_t b, uint32_t k, uint32_t *ids_out,
                            float *dist_out, uint32_t *counts_out);

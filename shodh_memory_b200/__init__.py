@@ -8,7 +8,7 @@ from .capi import SgError
 from .encoder import GpuMiniLM, export_bert_weights, random_minilm_state_dict
 from .pq import GpuProductQuantizer
 from .relevance import fuse_topk, RRFusion
-from .spann import GpuSpannIndex
+from .spann import GpuSpannIndex, spann_file_inspect, spann_file_read, spann_file_write
 from .vector_store import GpuVectorStore, merge_topk_device, vama_inspect, top_k_similar, cosine_similarity
 
 capi.lib()  # load now: no lazy CPU fallback, a missing extension is an ImportError

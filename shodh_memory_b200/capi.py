@@ -137,6 +137,13 @@ def lib() -> C.CDLL:
     L.sg_spann_info.argtypes = [vp, u32p, u64p, u32p]
     L.sg_spann_get.argtypes = [vp, f32p, f32p, u64p, u32p, u8p]
     L.sg_spann_set_probes.argtypes = [vp, C.c_uint32]
+    L.sg_spann_shape.argtypes = [vp, u32p, u32p, u32p, u32p, C.POINTER(C.c_int)]
+    L.sg_spann_file_inspect.argtypes = [C.c_char_p, C.c_int, u64p, u32p, u32p, u32p, u32p, u32p, u32p]
+    L.sg_spann_file_read.argtypes = [C.c_char_p, f32p, f32p, u64p, u32p, u8p]
+    L.sg_spann_file_write.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, f32p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                      f32p, u64p, u32p, u8p]
+    L.sg_spann_load_file.argtypes = [C.POINTER(vp), C.c_int, C.c_char_p, C.c_uint32, C.c_int]
+    L.sg_spann_save_file.argtypes = [vp, C.c_char_p]
     L.sg_spann_insert.argtypes = [vp, C.c_uint32, f32p]
     L.sg_spann_search.argtypes = [vp, f32p, C.c_uint32, C.c_uint32, u32p, f32p, u32p]
     L.sg_encoder_create.argtypes = [C.POINTER(vp), C.c_int, C.c_char_p]

@@ -549,6 +549,18 @@ int sg_spann_info(sg_spann *s, uint32_t *num_partitions_out, uint64_t *len_out, 
     return SG_OK;
 }
 
+int sg_spann_shape(sg_spann *s, uint32_t *dim_out, uint32_t *num_subvectors_out, uint32_t *num_centroids_out,
+                   uint32_t *subvec_dim_out, int *metric_out)
+{
+    if (!s) return SG_ERR_INVALID;
+    if (dim_out) *dim_out = s->dim;
+    if (num_subvectors_out) *num_subvectors_out = s->m;
+    if (num_centroids_out) *num_centroids_out = s->kc;
+    if (subvec_dim_out) *subvec_dim_out = s->ds;
+    if (metric_out) *metric_out = s->metric;
+    return SG_OK;
+}
+
 int sg_spann_get(sg_spann *s, float *centroids_out, float *pq_centroids_out, uint64_t *part_off_out, uint32_t *ids_out,
                  uint8_t *codes_out)
 {

@@ -47,6 +47,18 @@ class GpuSpannIndex:
                                               _ptr(off, C.c_uint64), _ptr(i, C.c_uint32), _ptr(cd, C.c_uint8)))
         return cls(h, c.shape[1])
 
+    @classmethod
+    def load_from_file(cls, path: str, num_probes: int = 10, verify_checksum: bool = True, device: int = 0) -> "GpuSpannIndex":
+        """SpannIndex::load_from_file: the reference's "SPAN" v1 file -> a device index."""
+        info = spann_file_inspect(path, verify_checksum)
+        h = C.c_void_p()
+        capi.check(capi.lib().sg_spann_load_file(C.byref(h), device, path.encode(), num_probes, int(verify_checksum)))
+        return cls(h, info["dimension"])
+
+    def save_to_file(self, path: str) -> None:
+        """SpannIndex::save_to_file"""
+        capi.check(capi.lib().sg_spann_save_file(self._h, path.encode()))
+
     def close(self) -> None:
         if self._h:
             capi.lib().sg_spann_destroy(self._h)
@@ -102,3 +114,36 @@ class GpuSpannIndex:
     def search(self, query, k: int):
         ids, dist, cnt = self.search_batch(np.asarray(query, np.float32)[None, :], k)
         return [(int(i), float(d)) for i, d in zip(ids[0, :cnt[0]], dist[0, :cnt[0]])]
+
+
+# ---- the "SPAN" v1 file (spann.rs:10-56): plain host code, no device needed ---------------------------------
+def spann_file_inspect(path: str, verify_checksum: bool = True) -> dict:
+    n = C.c_uint64()
+    v = [C.c_uint32() for _ in range(6)]
+    capi.check(capi.lib().sg_spann_file_inspect(path.encode(), int(verify_checksum), C.byref(n), *[C.byref(x) for x in v]))
+    keys = ("num_partitions", "dimension", "num_subvectors", "num_centroids", "subvec_dim", "metric")
+    return dict(num_vectors=n.value, **{k: x.value for k, x in zip(keys, v)})
+
+
+def spann_file_read(path: str):
+    """-> (centroids [P,dim], pq_centroids [m,kc,ds], part_off [P+1], ids [n], codes [n,m])"""
+    i = spann_file_inspect(path, False)
+    cent = np.zeros((i["num_partitions"], i["dimension"]), np.float32)
+    pqc = np.zeros((i["num_subvectors"], i["num_centroids"], i["subvec_dim"]), np.float32)
+    off = np.zeros(i["num_partitions"] + 1, np.uint64)
+    ids = np.zeros(max(i["num_vectors"], 1), np.uint32)
+    codes = np.zeros((max(i["num_vectors"], 1), i["num_subvectors"]), np.uint8)
+    capi.check(capi.lib().sg_spann_file_read(path.encode(), _ptr(cent, C.c_float), _ptr(pqc, C.c_float), _ptr(off, C.c_uint64),
+                                             _ptr(ids, C.c_uint32), _ptr(codes, C.c_uint8)))
+    return cent, pqc, off, ids[:i["num_vectors"]], codes[:i["num_vectors"]]
+
+
+def spann_file_write(path: str, centroids, pq_centroids, part_off, ids, codes, metric: int = 0) -> None:
+    c = np.ascontiguousarray(centroids, np.float32)
+    pc = np.ascontiguousarray(pq_centroids, np.float32)
+    off = np.ascontiguousarray(part_off, np.uint64)
+    i = np.ascontiguousarray(ids, np.uint32)
+    cd = np.ascontiguousarray(codes, np.uint8)
+    capi.check(capi.lib().sg_spann_file_write(path.encode(), c.shape[1], c.shape[0], metric, _ptr(c, C.c_float), pc.shape[0],
+                                              pc.shape[1], pc.shape[2], _ptr(pc, C.c_float), _ptr(off, C.c_uint64),
+                                              _ptr(i, C.c_uint32), _ptr(cd, C.c_uint8)))
