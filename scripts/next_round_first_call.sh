@@ -1,0 +1,44 @@
+#!/bin/bash
+# First GPU call of the next round (one GPU):   gpurun --timeout 900 -- 'bash scripts/next_round_first_call.sh'
+#   1. the whole GPU suite (everything was green piecewise at the end of round 1; the encoder->store ingest test and
+#      the SPAN file round trip are compositions of verified pieces that have not run together yet)
+#   2. the full bench (fills the product_quantization / spann legs that were never read)
+#   3. ncu --set full of pq_scan_kernel and spann_search_kernel (no capture exists yet)
+mkdir -p gpurun_out
+timeout 420 python -m pytest tests -q -x --tb=short -m gpu -p no:cacheprovider > gpurun_out/gpu_tests.log 2>&1
+echo "gpu tests exit $?" >> gpurun_out/gpu_tests.log
+tail -c 1500 gpurun_out/gpu_tests.log
+timeout 420 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
+echo "bench exit $?"
+python - <<'PY'
+import json
+try:
+    d = json.loads(open("gpurun_out/bench.json").read().strip().splitlines()[-1])
+    print(json.dumps({k: d.get(k) for k in ("value", "e2e", "product_quantization", "spann")})[:4000])
+except Exception as e:
+    print("bench parse failed", e)
+PY
+cat > /tmp/pq_target.py <<'PY'
+import sys, numpy as np, torch
+sys.path.insert(0, ".")
+import shodh_memory_b200 as sg
+rng = np.random.default_rng(0)
+pq = sg.GpuProductQuantizer.from_centroids((rng.standard_normal((48, 256, 8)) * 0.05).astype(np.float32))
+for lo in range(0, 2_000_000, 200_000):
+    pq.add(np.arange(lo, lo + 200_000, dtype=np.uint32), rng.standard_normal((200_000, 384)).astype(np.float32) * 0.05)
+q = rng.standard_normal((8, 384)).astype(np.float32) * 0.05
+pq.search_batch(q, 10)
+P = 1415
+cent = rng.standard_normal((P, 384)).astype(np.float32); cent /= np.linalg.norm(cent, axis=1, keepdims=True)
+off = np.linspace(0, 2_000_000, P + 1).astype(np.uint64)
+sp = sg.GpuSpannIndex.from_arrays(cent, (rng.standard_normal((48, 256, 8)) * 0.05).astype(np.float32), off,
+                                  np.arange(2_000_000, dtype=np.uint32), rng.integers(0, 256, (2_000_000, 48), dtype=np.uint8))
+sp.search_batch(rng.standard_normal((256, 384)).astype(np.float32), 10)
+torch.cuda.profiler.start()
+pq.search_batch(q, 10)
+sp.search_batch(rng.standard_normal((256, 384)).astype(np.float32), 10)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+PY
+timeout 240 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"pq_scan|spann_search" -c 5 -f \
+    -o gpurun_out/pq_spann_r02 python /tmp/pq_target.py 2>&1 | tail -4
