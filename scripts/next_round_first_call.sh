@@ -1,11 +1,12 @@
 #!/bin/bash
 # First GPU call of the next round (one GPU):   gpurun --timeout 900 -- 'bash scripts/next_round_first_call.sh'
 #   1. the whole GPU suite (everything was green piecewise at the end of round 1; the encoder->store ingest test and
-#      the SPAN file round trip are compositions of verified pieces that have not run together yet)
+#      the SPAN file round trip are compositions of verified pieces that have not run together yet; SHODH_UNVERIFIED=1
+#      also runs the one opt-in test: the member-list PQ training path for large training sets)
 #   2. the full bench (fills the product_quantization / spann legs that were never read)
 #   3. ncu --set full of pq_scan_kernel and spann_search_kernel (no capture exists yet)
 mkdir -p gpurun_out
-timeout 420 python -m pytest tests -q -x --tb=short -m gpu -p no:cacheprovider > gpurun_out/gpu_tests.log 2>&1
+SHODH_UNVERIFIED=1 timeout 420 python -m pytest tests -q -x --tb=short -m gpu -p no:cacheprovider > gpurun_out/gpu_tests.log 2>&1
 echo "gpu tests exit $?" >> gpurun_out/gpu_tests.log
 tail -c 1500 gpurun_out/gpu_tests.log
 timeout 420 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err

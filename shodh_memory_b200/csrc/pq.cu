@@ -16,6 +16,8 @@
 // vector, reads its 48 bytes word by word (consecutive threads read consecutive vectors: a warp covers 1536
 // contiguous bytes, every line is used whole out of L1), adds the 48 entries in order, and feeds the same per-warp
 // threshold / append / bitonic-compact top-k as the exact sweep.  Algorithmic bytes per scan = n x (m + 4).
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -146,6 +148,23 @@ __global__ void pq_update_kernel(const float *vecs, uint64_t n, uint32_t dim, ui
             ++cnt;
         }
     if (cnt) centroids[t] = __fdiv_rn(acc, (float)cnt);
+}
+
+// the same update for large training sets: members of (subspace s, cluster c) are members[s*n + moff[s*(k+1)+c] ..
+// moff[s*(k+1)+c+1]), listed in vector order (a stable counting sort of the assignments, arranged by the host), so a
+// thread adds only its own cluster's members -- n*dim work in total instead of n per thread -- in the same order
+__global__ void pq_update_members_kernel(const float *vecs, uint64_t n, uint32_t dim, uint32_t ds, uint32_t k, const uint64_t *moff,
+                                         const uint32_t *members, float *centroids, uint32_t m)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)m * k * ds) return;
+    const uint32_t j = (uint32_t)(t % ds), c = (uint32_t)((t / ds) % k), s = (uint32_t)(t / ((uint64_t)ds * k));
+    const uint64_t lo = moff[(size_t)s * (k + 1) + c], hi = moff[(size_t)s * (k + 1) + c + 1];
+    if (hi == lo) return;
+    const uint32_t *mem = members + (size_t)s * n;
+    float acc = 0.0f;
+    for (uint64_t e = lo; e < hi; ++e) acc = __fadd_rn(acc, vecs[(size_t)mem[e] * dim + (size_t)s * ds + j]);
+    centroids[t] = __fdiv_rn(acc, (float)(hi - lo));
 }
 
 // initial centroids (:160-170): the first k entries of the shuffled order (wrapping when n < k)
@@ -436,13 +455,57 @@ int sg_pq_train(sg_pq **out, int device, uint32_t dim, uint32_t subvec_dim, uint
         const uint64_t tot = (uint64_t)m * k * ds;
         pq_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, p->stream>>>(d_vecs, n, dim, ds, k, d_order, p->d_centroids, m);
         count_launch();
-        for (uint32_t it = 0; it < iterations; ++it) {
+        // small training sets: every thread walks the whole assignment list (no host round trip); large ones
+        // (n >= SG_PQ_MEMBERS_MIN_N, default 20000): per-cluster member lists in vector order, arranged by the host
+        const char *thr = getenv("SG_PQ_MEMBERS_MIN_N");
+        const uint64_t members_min_n = thr ? (uint64_t)atoll(thr) : 20000;
+        const bool use_members = n >= members_min_n;
+        uint32_t *d_members = nullptr;
+        uint64_t *d_moff = nullptr;
+        std::vector<uint32_t> h_assign, h_members;
+        std::vector<uint64_t> h_moff, cur;
+        if (use_members) {
+            e = cudaMalloc(&d_members, (size_t)m * n * 4);
+            if (e == cudaSuccess) e = cudaMalloc(&d_moff, (size_t)m * (k + 1) * 8);
+            h_assign.resize((size_t)m * n);
+            h_members.resize((size_t)m * n);
+            h_moff.resize((size_t)m * (k + 1));
+            cur.resize(k);
+        }
+        for (uint32_t it = 0; it < iterations && e == cudaSuccess; ++it) {
             dim3 grid((unsigned)((n + 255) / 256), m);
             pq_assign_kernel<<<grid, 256, (size_t)k * ds * 4, p->stream>>>(d_vecs, n, dim, ds, k, p->d_centroids, d_assign);
-            pq_update_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, p->stream>>>(d_vecs, n, dim, ds, k, d_assign, p->d_centroids, m);
-            count_launch(2);
+            count_launch();
+            if (!use_members) {
+                pq_update_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, p->stream>>>(d_vecs, n, dim, ds, k, d_assign, p->d_centroids, m);
+                count_launch();
+                continue;
+            }
+            e = cudaMemcpyAsync(h_assign.data(), d_assign, (size_t)m * n * 4, cudaMemcpyDeviceToHost, p->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+            if (e != cudaSuccess) break;
+            for (uint32_t s2 = 0; s2 < m; ++s2) {                       // stable counting sort of subspace s2's assignments
+                const uint32_t *as = h_assign.data() + (size_t)s2 * n;
+                uint64_t *off = h_moff.data() + (size_t)s2 * (k + 1);
+                std::fill(off, off + k + 1, 0);
+                for (uint64_t i = 0; i < n; ++i) ++off[as[i] + 1];
+                for (uint32_t c = 0; c < k; ++c) off[c + 1] += off[c];
+                std::copy(off, off + k, cur.begin());
+                uint32_t *mem = h_members.data() + (size_t)s2 * n;
+                for (uint64_t i = 0; i < n; ++i) mem[cur[as[i]]++] = (uint32_t)i;
+            }
+            e = cudaMemcpyAsync(d_moff, h_moff.data(), h_moff.size() * 8, cudaMemcpyHostToDevice, p->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_members, h_members.data(), (size_t)m * n * 4, cudaMemcpyHostToDevice, p->stream);
+            if (e == cudaSuccess) {
+                pq_update_members_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, p->stream>>>(d_vecs, n, dim, ds, k, d_moff, d_members,
+                                                                                           p->d_centroids, m);
+                count_launch();
+                e = cudaStreamSynchronize(p->stream);
+            }
         }
-        e = cudaGetLastError();
+        cudaFree(d_members);
+        cudaFree(d_moff);
+        if (e == cudaSuccess) e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
     cudaFree(d_vecs);

@@ -103,3 +103,17 @@ def test_small_shapes_and_ties(sg, oracle):
         sg.GpuProductQuantizer.from_centroids(np.zeros((3, 16, 8), F))         # 3 subvectors: not a multiple of 4
     empty.close()
     pq.close()
+
+
+@pytest.mark.skipif(__import__("os").environ.get("SHODH_UNVERIFIED") != "1",
+                    reason="the member-list training path was written after the GPU budget was spent: set SHODH_UNVERIFIED=1")
+def test_member_list_training_path_equals_the_oracle(sg, oracle, monkeypatch):
+    """large training sets (n >= SG_PQ_MEMBERS_MIN_N) take pq_update_members_kernel; forced here on a small set"""
+    monkeypatch.setenv("SG_PQ_MEMBERS_MIN_N", "1")
+    v = np.random.default_rng(9).random((1500, 384), dtype=F)
+    ref = oracle.PQOracle(384, kmeans_iterations=4)
+    orders = ref.shuffled_orders(1500, 2)
+    ref.train(v, orders=orders)
+    pq = sg.GpuProductQuantizer.train(v, orders, kmeans_iterations=4)
+    assert np.array_equal(bits(pq.centroids), bits(ref.centroids))
+    pq.close()
