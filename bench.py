@@ -290,7 +290,7 @@ def run_leg_child(name, local_rank):
     return 0
 
 
-def run_leg(name, local_rank, timeout_s=240):
+def run_leg(name, local_rank, timeout_s=150):
     """parent side: run the leg in its own process on the same GPU"""
     try:
         out = subprocess.run([sys.executable, os.path.abspath(__file__), "--leg", name, "--leg-device", str(local_rank)],
