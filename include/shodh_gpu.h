@@ -49,7 +49,12 @@ typedef enum sg_dtype { SG_DTYPE_F32 = 0, SG_DTYPE_F16 = 1 } sg_dtype;
 /* src/vector_db/vamana.rs:38-54 DistanceMetric, dispatched by VamanaIndex::distance (:755-761).
  * RetrievalEngine only permits NormalizedDotProduct (src/memory/retrieval.rs:188-193); the other
  * two are what a standalone VamanaIndex accepts.  All are scored in the reference's summation order
- * by the exact sweep; only NEG_DOT batches use the tensor-core sweep. */
+ * by the exact sweep; only NEG_DOT batches use the tensor-core sweep.
+ * NaN distances: every NaN is canonicalised to +NaN and sorts LAST (f32::total_cmp order of a positive NaN).
+ * For NEG_DOT that is what x86 produces for the reference (default NaN from arithmetic, negated by `-dot`...
+ * canonicalised the same way in the oracle); for EUCLIDEAN / COSINE the reference's NaN sign follows x86 NaN
+ * propagation through sub/mul/sqrt/div and is NOT reproduced -- rows whose distance is NaN are still returned
+ * after all numbered distances, but their relative order among themselves is by id only. */
 typedef enum sg_metric {
     SG_METRIC_NEG_DOT = 0,    /* normalized_distance_inline (distance_inline.rs:479-481): -dot */
     SG_METRIC_EUCLIDEAN = 1,  /* euclidean_squared_inline (:184-305): |a-b|^2 */
@@ -160,16 +165,32 @@ SG_API int sg_store_search_memory_ids(sg_store *s, const float *queries_f32, uin
 
 /* same, with queries and results resident in device memory and asynchronous on
  * `cuda_stream` (a cudaStream_t; NULL = the CUDA default stream).  This is the
- * form the GPU encoder feeds and the multi-GPU exchange consumes. */
+ * form the GPU encoder feeds and the multi-GPU exchange consumes.
+ * Streams: a store owns ONE set of scratch buffers.  Every call on a store -- asynchronous or not, on any
+ * stream -- first waits (cudaStreamWaitEvent) for the end of the previous asynchronous call if that ran on a
+ * different stream, so calls on one store are serialised on the device in the order they were issued.  Results
+ * of an asynchronous call are valid once `cuda_stream` has passed the call. */
 SG_API int sg_store_search_device(sg_store *s, const float *d_queries_f32, uint32_t b, uint32_t k,
                                   uint32_t *d_ids_out, float *d_dist_out, uint32_t *d_counts_out,
                                   void *cuda_stream);
 
-/* Batched searches (b >= 5, k <= 24, F16 store) run the tensor-core sweep: approximate scores
- * select k+slack candidates, which are re-scored exactly and certified with a rigorous error
- * bound; queries that cannot be certified are re-run on the exact sweep, so results are always
- * the exact ones.  Statistics: queries that took the tensor path / that needed the re-run. */
+/* Batched searches (b >= 5, k <= 128 -- which covers the reference's own request, k = 4 * limit = 120 for a
+ * top-10 recall: retrieval.rs:912-918 x memory/mod.rs:3585 --, F16 store, NormalizedDotProduct) run the
+ * tensor-core sweep: approximate scores select k+slack candidates, which are re-scored exactly in the
+ * reference's summation order and certified with a rigorous error bound (coefficient derived from dim);
+ * queries that cannot be certified are re-run on the exact sweep, so results are always the exact ones.
+ * Statistics: queries that took the tensor path / that needed the re-run. */
 SG_API int sg_store_tc_stats(sg_store *s, uint64_t *queries_out, uint64_t *flagged_out);
+/* mode 0 (default): choose the sweep by shape; mode 1: always the exact sweep (path A) -- what the parity
+ * checks in tests/ and bench.py compare the tensor-core path against. */
+SG_API int sg_store_set_tc_mode(sg_store *s, int mode);
+/* Diagnostics for tests/test_scan_tc_gpu.py (not part of the drop-in surface): raw tensor-core scores and
+ * exact reference-order dots of b queries against rows [first_row, first_row + n_rows) -> out [b, n_rows],
+ * so the accumulation-error coefficient of the certificate can be MEASURED.  F16 stores; b <= 256 for tc. */
+SG_API int sg_debug_tc_scores(sg_store *s, const float *queries_f32, uint32_t b, uint64_t first_row, uint64_t n_rows,
+                              float *out);
+SG_API int sg_debug_exact_scores(sg_store *s, const float *queries_f32, uint32_t b, uint64_t first_row,
+                                 uint64_t n_rows, float *out);
 
 /* k-way merge of per-shard results: lists [b, n_lists, k] of (id, dist)
  * already sorted by (dist, id) -> the global top-k per query, same order rule.
@@ -196,6 +217,15 @@ SG_API int sg_exchange_merge_topk_device(int device, const uint64_t *peer_buffer
                                          uint32_t epoch, const uint32_t *d_ids, const float *d_dist, uint32_t b,
                                          uint32_t k, uint32_t *d_ids_out, float *d_dist_out, uint32_t *d_counts_out,
                                          void *cuda_stream);
+/* The whole multi-GPU recall step of one rank: search this shard (sg_store_search_device) and
+ * exchange + merge, with the push folded into the kernels that produce each query's final local result
+ * (the re-score/certify kernel of the tensor-core path, the merge kernel of the exact path): a query's k
+ * results travel to every peer the moment they exist, and the only extra launch is the wait + merge kernel.
+ * Same buffers, epoch rule and (b, k) agreement as sg_exchange_merge_topk_device.  Outputs: the GLOBAL top-k. */
+SG_API int sg_store_search_sharded_device(sg_store *s, const float *d_queries_f32, uint32_t b, uint32_t k,
+                                          const uint64_t *peer_buffers, uint32_t rank, uint32_t world, uint32_t epoch,
+                                          uint32_t *d_ids_out, float *d_dist_out, uint32_t *d_counts_out,
+                                          void *cuda_stream);
 
 /* ---- Vamana graph index: the reference's DEFAULT search arm -------------------------
  * src/vector_db/vamana.rs: build :200-284, search :779-807 -> greedy_search :576-657, add_vector :853-973.

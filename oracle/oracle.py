@@ -258,6 +258,45 @@ def brute_force_search_batch(corpus, queries, k, deleted=None, metric=METRIC_NEG
     return ids, dist, counts, used
 
 
+def order_keys(dist: np.ndarray, ids: np.ndarray) -> np.ndarray:
+    """u64 keys whose unsigned order is (dist f32::total_cmp asc, id asc) (vamana.rs:1184)."""
+    b = np.ascontiguousarray(dist, np.float32).view(np.uint32).astype(np.uint64)
+    k32 = np.where(b >> np.uint64(31), (~b) & np.uint64(0xFFFFFFFF), b | np.uint64(0x80000000))
+    return (k32 << np.uint64(32)) | np.ascontiguousarray(ids, np.uint32).astype(np.uint64)
+
+
+def brute_force_search_synth(seed, n_total, queries, k, deleted=None, dim=384, chunk=1_000_000,
+                             variant=VARIANT_SCALAR, threads=0):
+    """brute_force_search over the synthetic f16-rounded corpus rows [0, n_total) WITHOUT holding it in memory:
+    the corpus is generated chunk by chunk, each chunk's top-k (global ids) is taken with so_brute_force_search_batch
+    and the per-chunk lists are merged with the same (dist total_cmp, id) rule -- identical to sorting all rows at
+    once, because the order is total.  -> (ids [b,k] u32, dist [b,k] f32, counts [b])."""
+    queries = _f32(queries)
+    b = queries.shape[0]
+    dele = sorted(deleted or [])
+    keys = [[] for _ in range(b)]
+    for lo in range(0, n_total, chunk):
+        m = min(chunk, n_total - lo)
+        c = synth_corpus(seed, lo, m, dim, f16_round=True)
+        dl = [d - lo for d in dele if lo <= d < lo + m]
+        ids, dist, cnt, _ = brute_force_search_batch(c, queries, k, deleted=dl or None, variant=variant, threads=threads)
+        for q in range(b):
+            r = int(cnt[q])
+            keys[q].append(order_keys(dist[q, :r], ids[q, :r].astype(np.uint64) + lo))
+        del c
+    out_ids = np.full((b, k), 0xFFFFFFFF, np.uint32)
+    out_dist = np.full((b, k), np.inf, np.float32)
+    counts = np.zeros(b, np.uint32)
+    for q in range(b):
+        kk = np.sort(np.concatenate(keys[q]))[:k]
+        counts[q] = kk.size
+        out_ids[q, :kk.size] = (kk & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        k32 = (kk >> np.uint64(32)).astype(np.uint32)
+        bits = np.where(k32 & np.uint32(0x80000000), k32 ^ np.uint32(0x80000000), ~k32)
+        out_dist[q, :kk.size] = bits.astype(np.uint32).view(np.float32)
+    return out_ids, out_dist, counts
+
+
 def score_rows(corpus, query, ids, metric=METRIC_NEG_DOT, variant=VARIANT_SCALAR) -> np.ndarray:
     corpus, query = _f32(corpus), _f32(query)
     ids = np.ascontiguousarray(ids, dtype=np.uint32)

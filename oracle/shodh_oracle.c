@@ -358,7 +358,9 @@ SO_EXPORT int so_brute_force_search_batch(const float *corpus, uint64_t n, uint3
 {
     int used = 1;
 #ifdef _OPENMP
-    int maxt = omp_get_max_threads();
+    /* an explicit thread count is honoured up to the processor count: torchrun exports OMP_NUM_THREADS=1, which
+     * would otherwise silently turn the all-cores baseline into a single-thread one */
+    int maxt = threads > 0 ? omp_get_num_procs() : omp_get_max_threads();
     if (threads <= 0 || threads > maxt) threads = maxt;
     if ((uint32_t)threads > b) threads = (int)b;
     if (threads < 1) threads = 1;
@@ -757,7 +759,7 @@ SO_EXPORT void so_synth_corpus(uint64_t seed, uint64_t first_row, uint64_t n, ui
                                int f16_round, float *out)
 {
 #ifdef _OPENMP
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(omp_get_num_procs())
 #endif
     for (uint64_t i = 0; i < n; ++i) {
         float *r = out + i * dim;

@@ -9,8 +9,8 @@ mkdir -p gpurun_out
 SHODH_UNVERIFIED=1 timeout 420 python -m pytest tests -q -x --tb=short -m gpu -p no:cacheprovider > gpurun_out/gpu_tests.log 2>&1
 echo "gpu tests exit $?" >> gpurun_out/gpu_tests.log
 tail -c 1500 gpurun_out/gpu_tests.log
-timeout 420 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
-echo "bench exit $?"
+true # bench skipped in this call
+
 python - <<'PY'
 import json
 try:

@@ -104,6 +104,11 @@ def lib() -> C.CDLL:
     L.sg_exchange_merge_topk_device.argtypes = [C.c_int, u64p, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32,
                                                 C.c_uint32, vp, vp, vp, vp]
     L.sg_store_tc_stats.argtypes = [vp, u64p, u64p]
+    L.sg_store_set_tc_mode.argtypes = [vp, C.c_int]
+    L.sg_debug_tc_scores.argtypes = [vp, f32p, C.c_uint32, C.c_uint64, C.c_uint64, f32p]
+    L.sg_debug_exact_scores.argtypes = [vp, f32p, C.c_uint32, C.c_uint64, C.c_uint64, f32p]
+    L.sg_store_search_sharded_device.argtypes = [vp, vp, C.c_uint32, C.c_uint32, u64p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                 vp, vp, vp, vp]
     L.sg_store_metric.argtypes = [vp, C.POINTER(C.c_int)]
     L.sg_store_enable_graph.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_float]
     L.sg_store_build_graph.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_float, C.c_uint64]

@@ -428,14 +428,17 @@ int sg_store_search_ann_device(sg_store *s, const float *d_q, uint32_t b, uint32
     uint32_t K = 0;
     int rc = ann_beam(s, k, &K);
     if (rc != SG_OK) return rc;
+    if ((rc = chain_begin(s, st)) != SG_OK) return rc;         // the visited tables are per-store scratch
     if (s->n == 0) {                                           // Ok(vec![]) (:766-768)
         SG_CUDA_TRY(launch_merge_keys(nullptr, b, 0, k, s->id_base, nullptr, d_ids, d_dist, d_counts, st));
         if (d_flags) SG_CUDA_TRY(cudaMemsetAsync(d_flags, 0, (size_t)b * 4, st));
-        return SG_OK;
+        return chain_end(s, st);
     }
     s->ann_searches += b;
-    return ann_launch(s, d_q, nullptr, b, K, k, true, s->id_base, s->n, s->graph_len, default_table_size(K), d_ids, d_dist,
-                      d_counts, d_flags, nullptr, st);
+    rc = ann_launch(s, d_q, nullptr, b, K, k, true, s->id_base, s->n, s->graph_len, default_table_size(K), d_ids, d_dist,
+                    d_counts, d_flags, nullptr, st);
+    const int rc2 = chain_end(s, st);
+    return rc != SG_OK ? rc : rc2;
 }
 
 int sg_store_search_ann(sg_store *s, const float *queries, uint32_t b, uint32_t k, uint32_t *ids_out, float *dist_out,
@@ -458,6 +461,7 @@ int sg_store_search_ann(sg_store *s, const float *queries, uint32_t b, uint32_t 
         return SG_OK;
     }
     const size_t qbytes = (size_t)b * s->dim * 4, rbytes = (size_t)b * k * 4, cbytes = (size_t)b * 4, sbytes = (size_t)b * 16;
+    if ((rc = chain_begin(s, s->stream)) != SG_OK) return rc;
     if ((rc = grow_pinned(s, qbytes + 2 * rbytes + 2 * cbytes + sbytes)) != SG_OK) return rc;
     if ((rc = grow(s->d_queries, s->q_cap, (size_t)b * s->dim)) != SG_OK) return rc;
     if ((size_t)b * k > s->res_cap) {

@@ -5,39 +5,51 @@
 // it needs ~2 PFLOP/s to keep up with HBM, which only tcgen05 can deliver.  The tensor cores
 // see fp16(query) x fp16(row) with f32 accumulation, i.e. APPROXIMATE scores; exactness is
 // restored by over-selection + exact re-scoring:
-//   K1 (this file, scan_tc_kernel): one sweep; per query keep the KK = k + slack best
-//       approximate scores (a GPU-wide shared threshold keeps the candidate traffic tiny);
-//   K2 (finalize_tc_kernel): per query take the global top-KK approximate candidates,
+//   K1 (scan_tc_kernel / scan_tc2_kernel): ONE sweep.  Every CTA (pair) first scores one sample
+//       tile, the grid meets at a device-side barrier and derives a valid starting threshold per
+//       query from the sample maxima; from then on every score at or above the query's threshold
+//       is APPENDED to the (query, CTA) candidate region and counted in a per-query score
+//       histogram shared by the whole GPU.  "kk rows have been appended at or above bucket edge e"
+//       makes e a valid threshold, so the threshold follows the running kk-th best score of ALL
+//       rows seen so far by ALL CTAs -- no pre-pass launch, no sorted lists, no atomics that return;
+//   K2 (finalize_tc_kernel): per query take the kk = k + slack best approximate candidates,
 //       re-score them in EXACTLY the reference's summation order (distance_inline.rs:157-173 /
 //       :67-111), sort by (dist, id), and certify with a rigorous error bound E that no row
 //       outside the candidate set can reach the top k:  kth_exact_sim > weakest_kept_approx + E.
-//       Queries that cannot be certified are flagged and re-run on the exact path A.
+//       Queries that cannot be certified are flagged and re-run on the exact path A.  Certified
+//       results can be pushed straight into the peers' exchange buffers (multi-GPU, sg_push.cuh).
 // So the result is bit-identical to path A / the CPU oracle, or the query is flagged.
 //
-// B200 mapping (one CTA per SM, 256 threads, persistent over 128-row corpus tiles):
+// B200 mapping (one CTA per SM, 256 threads, persistent over corpus tiles):
 //   warp 0   TMA producer: the fp16 query block (A operand, 128 x dim, resident for the whole
 //            sweep) and a ring of K-blocks of corpus tiles (B operand, 128 rows x 64 elems,
 //            SWIZZLE_128B, K-major -- the same boxes path A streams);
-//   warp 1   MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128 (queries) x N=128 (rows),
-//            K=16 per instruction, accumulators in TMEM (4 stages x 128 columns);
+//   warp 1   MMA issuer: tcgen05.mma kind::f16, M=128 (queries) x N=128 rows (1 CTA) or
+//            cta_group::2 with M=256 x N=256 (CTA pair), K=16 per instruction, accumulators in TMEM;
 //   warp 2   TMEM allocator;
 //   warps 4-7 epilogue: thread t owns query t = TMEM lane t; tcgen05.ld 32 columns at a time,
-//            compares against its threshold, inserts the (rare) hits into its sorted list in
-//            shared memory.
-// HBM-bound: algorithmic bytes per sweep = n_rows * dim * 2; the MMA work per row is
-// 12 cycles against ~33 cycles of HBM time per row per SM.
+//            one max-tree + one vote per chunk; hits (rare) are appended by the owning lane.
+// Algorithmic bytes per sweep = n_rows * dim * 2; 1-CTA form: HBM-bound (12 MMA cycles per row
+// per SM against ~33 cycles of HBM time); pair form at 256 queries: tensor-bound.
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <mutex>
+
 #include "sg_internal.h"
+#include "sg_push.cuh"
 #include "sg_tc.cuh"
 
 namespace sg {
 namespace {
 
-constexpr uint32_t TC_M = 128;          // queries per sweep (TMEM lanes)
-constexpr uint32_t TC_N = 128;          // corpus rows per tile (TMEM columns per accumulator)
+constexpr uint32_t TC_M = 128;          // queries per CTA (TMEM lanes)
+constexpr uint32_t TC_N = 128;          // corpus rows per CTA tile
 constexpr uint32_t TC_KB = 64;          // fp16 elements per K-block (one 128B swizzle row)
 constexpr uint32_t TC_STAGE_BYTES = TC_N * 128;   // 16 KB
-constexpr uint32_t TC_ACC_STAGES = 4;   // 4 x 128 = 512 TMEM columns
+constexpr uint32_t TC_ACC_STAGES = 4;   // 4 x 128 = 512 TMEM columns (1-CTA form)
 constexpr uint32_t TC_THREADS = 256;
+constexpr float TC_NEG_INF = -__builtin_huge_valf();
 
 SG_DEVICE_INLINE uint32_t ld_relaxed_u32(const uint32_t *p)
 {
@@ -45,139 +57,265 @@ SG_DEVICE_INLINE uint32_t ld_relaxed_u32(const uint32_t *p)
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+SG_DEVICE_INLINE uint32_t ld_acquire_gpu_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+SG_DEVICE_INLINE void epi_bar_sync()      // the 128 epilogue threads only (named barrier 1)
+{
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+}
 
+// tile handled in iteration `it` of a CTA (pair): iteration 0 is the sample pass over the list's first
+// tile (maxima only); iterations 1..my_tiles are the sweep proper, which scores that tile again (it is
+// still in L2) together with all the others.
+SG_DEVICE_INLINE uint64_t tile_of_iter(uint64_t tile0, uint64_t stride, uint64_t it)
+{
+    return tile0 + (it ? it - 1 : 0) * stride;
+}
 
 // ---- the epilogue shared by the 1-CTA and the CTA-pair kernels -------------------------------------
-// thread t (0..127 of the 4 epilogue warps) <-> query q_base + t <-> TMEM lane t.  Each query's
-// candidate list (32 sorted keys) lives in shared memory as one row of 32 entries.  The common case
-// per 32-column chunk is "no score reaches any threshold": one max-tree per lane and one vote.  A hit
-// is re-read with tcgen05.ld.x1 and inserted by the WHOLE warp (lane i holds entry i; one ballot
-// finds the position, one shuffle shifts the tail) -- no dependent shared-memory chain.
+// thread t (0..127 of the 4 epilogue warps) <-> query q_base + t <-> TMEM lane t.
 // NCOLS = corpus rows (TMEM columns) per accumulator stage.  tempty_cluster_addr is the
 // shared::cluster address of the accumulator-empty barriers (the leader CTA's in pair mode).
-template <uint32_t NCOLS>
-SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint64_t *lists, uint32_t tmem_base, uint64_t *tfull_bar,
+//
+// Threshold validity.  tau_f never exceeds the kk-th best approximate score over the whole corpus:
+//   * seed: the sample contributes n_lists * J maxima of DISTINCT 32-row chunks; when at least kk of
+//     them are finite, their minimum has kk distinct rows at or above it;
+//   * histogram: every appended row increments exactly one bucket, bucket(s) = min(31, floor((s - tau0) / w)).
+//     If the buckets >= idx hold kk rows then kk rows have s >= tau0 + (idx - 1) * w: the edge ONE bucket
+//     below absorbs every rounding in bucket() and in the edge (w > 1e-5 * scale >> 2^-23 * scale);
+//   * gtau: the best threshold any CTA derived, shared with atomicMin on its order key.
+// A row that is not appended therefore has a score strictly below the final kk-th best.
+template <uint32_t NCOLS, bool DUMP>
+SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tmem_base, uint64_t *tfull_bar,
                                   uint32_t tempty_cluster_addr, uint64_t my_tiles, uint64_t tile0, uint64_t tile_stride,
                                   uint32_t q_base, uint32_t nq_local, uint32_t list_idx, uint32_t n_lists,
                                   uint32_t acc_stages)
 {
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t warp = threadIdx.x >> 5;
     const uint32_t t = threadIdx.x - 128;
     const uint32_t wq = (warp & 3) * 32;             // first query of this warp
-    uint64_t *wlists = lists + (size_t)wq * 32;      // [32 queries][32 entries]
-    for (uint32_t i = lane; i < 32 * 32; i += 32) wlists[i] = KEY_SENTINEL;
-    __syncwarp();
     const bool active = t < nq_local;
-    const uint32_t KKE = a.kk;                       // candidates kept per query and list (<= 32)
-    const float NEG_INF = -__uint_as_float(0x7F800000u);
-    float tau_f = active ? NEG_INF : -NEG_INF;       // similarity threshold: -inf / never
-    float mx_all = NEG_INF;                          // pre-pass: best live score seen by this lane
+    const uint32_t q = q_base + t;
+    const uint32_t lane_base = wq << 16;
+    float tau_f = active ? TC_NEG_INF : -TC_NEG_INF; // similarity threshold: -inf (everything) / +inf (never)
+    float tau0 = TC_NEG_INF, w = 0.0f, inv_w = 0.0f;
+    bool use_hist = false;
+    uint32_t my_cnt = 0;                             // entries this thread appended to ITS (query, list) region
     uint32_t tau_pub = 0xFFFFFFFFu;                  // last threshold key this lane shared
-    uint32_t *gtau = a.gtau + (size_t)q_base + t;
-    const uint32_t lane_base = (wq) << 16;
+    uint64_t *my_cand = a.cand + ((size_t)q * n_lists + list_idx) * a.cap_l;
+    uint32_t *my_hist = a.hist + (size_t)q * TC_HIST;
+    uint32_t *gtau = a.gtau + q;
 
-    for (uint64_t it = 0; it < my_tiles; ++it) {
-        const uint64_t tile = tile0 + it * tile_stride;
-        const uint32_t acc = (uint32_t)(it % acc_stages);
-        const uint32_t acc_ph = (uint32_t)((it / acc_stages) & 1);
-        if (active && a.mode == 0) {
-            const uint32_t g = ld_relaxed_u32(gtau);
-            if (g != 0xFFFFFFFFu) tau_f = fmaxf(tau_f, -key32_to_dist(g));
+    auto dead_mask = [&](uint64_t row0) -> uint32_t {
+        uint32_t dead = 0;
+        if (a.deleted && row0 < a.n_rows) dead = __ldg(a.deleted + (row0 >> 5));
+        if (row0 + 32 > a.n_rows) dead |= row0 >= a.n_rows ? 0xFFFFFFFFu : ~((1u << (uint32_t)(a.n_rows - row0)) - 1u);
+        return dead;
+    };
+    auto chunk_max = [&](const uint32_t (&r)[32]) -> float {
+        float m0 = fmaxf(fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3])));
+        float m1 = fmaxf(fmaxf(__uint_as_float(r[4]), __uint_as_float(r[5])), fmaxf(__uint_as_float(r[6]), __uint_as_float(r[7])));
+        float m2 = fmaxf(fmaxf(__uint_as_float(r[8]), __uint_as_float(r[9])), fmaxf(__uint_as_float(r[10]), __uint_as_float(r[11])));
+        float m3 = fmaxf(fmaxf(__uint_as_float(r[12]), __uint_as_float(r[13])), fmaxf(__uint_as_float(r[14]), __uint_as_float(r[15])));
+        float m4 = fmaxf(fmaxf(__uint_as_float(r[16]), __uint_as_float(r[17])), fmaxf(__uint_as_float(r[18]), __uint_as_float(r[19])));
+        float m5 = fmaxf(fmaxf(__uint_as_float(r[20]), __uint_as_float(r[21])), fmaxf(__uint_as_float(r[22]), __uint_as_float(r[23])));
+        float m6 = fmaxf(fmaxf(__uint_as_float(r[24]), __uint_as_float(r[25])), fmaxf(__uint_as_float(r[26]), __uint_as_float(r[27])));
+        float m7 = fmaxf(fmaxf(__uint_as_float(r[28]), __uint_as_float(r[29])), fmaxf(__uint_as_float(r[30]), __uint_as_float(r[31])));
+        return fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
+    };
+
+    uint64_t it = 0;
+    if constexpr (!DUMP) {
+        // ===== sample pass (iteration 0): the J best chunk maxima of this list's first tile =====
+        float m[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = TC_NEG_INF;
+        if (my_tiles) {
+            mbar_wait(smem_u32(tfull_bar), 0);
+            tc_fence_after();
+#pragma unroll 1
+            for (uint32_t c = 0; c < NCOLS / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + lane_base + c * 32, r);
+                tmem_ld_wait();
+                const uint32_t dead = dead_mask(tile0 * NCOLS + c * 32);
+                if (dead) {
+#pragma unroll
+                    for (uint32_t j = 0; j < 32; ++j)
+                        if ((dead >> j) & 1u) r[j] = __float_as_uint(TC_NEG_INF);
+                }
+                float mx = chunk_max(r);
+                if (!(mx == mx)) mx = TC_NEG_INF;        // an all-NaN chunk must not enter (it would duplicate entries)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {            // insert into the descending list
+                    const float hi = fmaxf(m[i], mx);
+                    mx = fminf(m[i], mx);
+                    m[i] = hi;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(tempty_cluster_addr);        // accumulator stage 0 is free again
         }
-        mbar_wait(smem_u32(tfull_bar + acc), acc_ph);
+        it = 1;
+        if (active) {
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j)
+                if (j < a.J) a.maxima[((size_t)list_idx * a.J + j) * a.b_pad + q] = m[j];
+        }
+        // device-wide meeting point: every CTA of the grid publishes its sample, then reads all of them
+        __threadfence();
+        epi_bar_sync();
+        if (t == 0) {
+            atomicAdd(a.arrive + a.q_tile, 1u);
+            const long long t0 = clock64();
+            uint32_t ok = 1;
+            while (ld_acquire_gpu_u32(a.arrive + a.q_tile) < gridDim.x) {
+                if (clock64() - t0 > 2000000000ll) {         // ~1 s: the grid is not co-resident (should not happen:
+                    ok = 0;                                  // cooperative launch); degrade to "no threshold" -> the
+                    break;                                   // queries overflow, get flagged and re-run on path A
+                }
+            }
+            s_ctl[0] = ok;
+        }
+        epi_bar_sync();
+        __threadfence();
+        if (active && s_ctl[0]) {
+            float mn = -TC_NEG_INF, sum = 0.0f;
+            uint32_t nfin = 0;
+            const uint32_t nv = n_lists * a.J;
+            const float *mp = a.maxima + q;
+            for (uint32_t i = 0; i < nv; ++i) {
+                const float v = __ldcg(mp + (size_t)i * a.b_pad);
+                if (v > TC_NEG_INF) {
+                    ++nfin;
+                    mn = fminf(mn, v);
+                    sum += v;
+                }
+            }
+            if (nfin >= a.kk) {                              // kk distinct rows score >= mn
+                tau0 = mn;
+                tau_f = mn;
+                // histogram range [mn, mn + 4 (mean - mn)]: the final threshold lies well beyond the sample's typical
+                // maximum (the sample is ~1/500 of a 10M-row corpus), and the MEAN, unlike the largest maximum, is not
+                // dragged away by one near-duplicate of the query that happens to sit in the sample (that stretched the
+                // buckets until a single one covered the whole useful range).  Scores beyond the range land in the last
+                // bucket: the threshold then stops one bucket short of them, which only costs a few extra candidates.
+                const float top = mn + 4.0f * (sum / (float)nfin - mn);
+                w = (top - mn) * (1.0f / TC_HIST);
+                if (w > 1.0e-5f * fmaxf(fabsf(mn), fabsf(top)) && w < -TC_NEG_INF) {
+                    inv_w = 1.0f / w;
+                    use_hist = true;
+                }
+            }
+        }
+    } else {
+        it = 1;
+    }
+
+    // ===== the sweep proper =====
+    for (; it <= my_tiles; ++it) {
+        const uint64_t tile = tile_of_iter(tile0, tile_stride, it);
+        const uint32_t accn = (uint32_t)((DUMP ? it - 1 : it) % acc_stages);
+        const uint32_t acc_ph = (uint32_t)(((DUMP ? it - 1 : it) / acc_stages) & 1);
+        if constexpr (!DUMP) {
+            if (active) {
+                if (use_hist && ((it + list_idx) & 3) == 0) {
+                    // refresh from the shared histogram: highest bucket idx whose tail holds kk rows
+                    const uint4 *hp = reinterpret_cast<const uint4 *>(my_hist);
+                    uint4 h[TC_HIST / 4];
+#pragma unroll
+                    for (uint32_t i = 0; i < TC_HIST / 4; ++i) h[i] = __ldcg(hp + i);
+                    uint32_t cum = 0;
+                    int idx = -1;
+#pragma unroll
+                    for (int i = TC_HIST / 4 - 1; i >= 0; --i) {
+                        cum += h[i].w; if (idx < 0 && cum >= a.kk) idx = 4 * i + 3;
+                        cum += h[i].z; if (idx < 0 && cum >= a.kk) idx = 4 * i + 2;
+                        cum += h[i].y; if (idx < 0 && cum >= a.kk) idx = 4 * i + 1;
+                        cum += h[i].x; if (idx < 0 && cum >= a.kk) idx = 4 * i;
+                    }
+                    if (idx >= 2) tau_f = fmaxf(tau_f, tau0 + (float)(idx - 1) * w);
+                }
+                const uint32_t g = ld_relaxed_u32(gtau);
+                if (g != 0xFFFFFFFFu) tau_f = fmaxf(tau_f, -key32_to_dist(g));
+            }
+        }
+        mbar_wait(smem_u32(tfull_bar + accn), acc_ph);
         tc_fence_after();
 #pragma unroll 1
         for (uint32_t c = 0; c < NCOLS / 32; ++c) {
             uint32_t r[32];
-            const uint32_t taddr = tmem_base + lane_base + acc * NCOLS + c * 32;
-            tmem_ld32(taddr, r);
+            tmem_ld32(tmem_base + lane_base + accn * NCOLS + c * 32, r);
             tmem_ld_wait();
             const uint64_t row0 = tile * NCOLS + c * 32;     // 32-aligned: one bitmap word
-            uint32_t dead = 0;
-            if (a.deleted && row0 < a.n_rows) dead = __ldg(a.deleted + (row0 >> 5));
-            if (row0 + 32 > a.n_rows) dead |= row0 >= a.n_rows ? 0xFFFFFFFFu : ~((1u << (uint32_t)(a.n_rows - row0)) - 1u);
+            if constexpr (DUMP) {
+                if (active) {
+#pragma unroll
+                    for (uint32_t j = 0; j < 32; ++j) {
+                        const uint64_t row = row0 + j;
+                        if (row >= a.dump_row0 && row < a.dump_row0 + a.dump_rows && row < a.n_rows)
+                            a.dump[(size_t)q * a.dump_rows + (row - a.dump_row0)] = __uint_as_float(r[j]);
+                    }
+                }
+                continue;
+            }
+            const uint32_t dead = dead_mask(row0);
             if (dead) {                                      // rare: neutralise dead columns
 #pragma unroll
                 for (uint32_t j = 0; j < 32; ++j)
-                    if ((dead >> j) & 1u) r[j] = __float_as_uint(NEG_INF);
+                    if ((dead >> j) & 1u) r[j] = __float_as_uint(TC_NEG_INF);
             }
-            float m0 = fmaxf(fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3])));
-            float m1 = fmaxf(fmaxf(__uint_as_float(r[4]), __uint_as_float(r[5])), fmaxf(__uint_as_float(r[6]), __uint_as_float(r[7])));
-            float m2 = fmaxf(fmaxf(__uint_as_float(r[8]), __uint_as_float(r[9])), fmaxf(__uint_as_float(r[10]), __uint_as_float(r[11])));
-            float m3 = fmaxf(fmaxf(__uint_as_float(r[12]), __uint_as_float(r[13])), fmaxf(__uint_as_float(r[14]), __uint_as_float(r[15])));
-            float m4 = fmaxf(fmaxf(__uint_as_float(r[16]), __uint_as_float(r[17])), fmaxf(__uint_as_float(r[18]), __uint_as_float(r[19])));
-            float m5 = fmaxf(fmaxf(__uint_as_float(r[20]), __uint_as_float(r[21])), fmaxf(__uint_as_float(r[22]), __uint_as_float(r[23])));
-            float m6 = fmaxf(fmaxf(__uint_as_float(r[24]), __uint_as_float(r[25])), fmaxf(__uint_as_float(r[26]), __uint_as_float(r[27])));
-            float m7 = fmaxf(fmaxf(__uint_as_float(r[28]), __uint_as_float(r[29])), fmaxf(__uint_as_float(r[30]), __uint_as_float(r[31])));
-            const float mx = fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
-            if (a.mode == 1) {                               // pre-pass: only the running maximum
-                mx_all = fmaxf(mx_all, mx);
-                continue;
-            }
+            const float mx = chunk_max(r);
             if (__any_sync(0xFFFFFFFFu, mx >= tau_f)) {
-                // slow path, cost proportional to the number of hits
+                // slow path: the owning lane appends its hits (cost ~ number of 8-column groups with a hit)
                 uint32_t mask = 0;
 #pragma unroll
                 for (uint32_t j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) >= tau_f) ? (1u << j) : 0u;
                 mask &= ~dead;                               // (-inf >= -inf) would let dead columns through
-                uint32_t lanes = __ballot_sync(0xFFFFFFFFu, mask != 0);
-                while (lanes) {
-                    const uint32_t L = __ffs(lanes) - 1;
-                    lanes &= lanes - 1;
-                    uint32_t mL = __shfl_sync(0xFFFFFFFFu, mask, L);
-                    uint64_t *ql = wlists + (size_t)L * 32;
-                    while (mL) {
-                        const uint32_t j = __ffs(mL) - 1;
-                        mL &= mL - 1;
-                        uint32_t v;
-                        tmem_ld1(taddr + j, v);              // column j for every lane; lane L's is the hit
-                        tmem_ld_wait();
-                        const float sc = __uint_as_float(__shfl_sync(0xFFFFFFFFu, v, L));
-                        const float tauL = __shfl_sync(0xFFFFFFFFu, tau_f, L);
-                        if (!(sc >= tauL)) continue;         // the threshold moved since the mask was taken
-                        const uint64_t key = make_key(order_key32(-sc), (uint32_t)(row0 + j));
-                        const uint64_t e = ql[lane];
-                        const uint32_t p = __popc(__ballot_sync(0xFFFFFFFFu, e < key));
-                        if (p < KKE) {                       // lanes >= KKE always hold KEY_SENTINEL
-                            const uint32_t e_lo = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)e, 1);
-                            const uint32_t e_hi = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)(e >> 32), 1);
-                            uint64_t ne = lane < p ? e : (lane == p ? key : (((uint64_t)e_hi << 32) | e_lo));
-                            if (lane >= KKE) ne = KEY_SENTINEL;
-                            ql[lane] = ne;
-                            const uint32_t last = __shfl_sync(0xFFFFFFFFu, (uint32_t)(ne >> 32), KKE - 1);
-                            if (lane == L && last != 0xFFFFFFFFu) tau_f = -key32_to_dist(last);
+#pragma unroll
+                for (uint32_t g8 = 0; g8 < 4; ++g8) {
+                    if ((mask >> (8 * g8)) & 0xFFu) {
+#pragma unroll
+                        for (uint32_t jj = 0; jj < 8; ++jj) {
+                            const uint32_t j = 8 * g8 + jj;
+                            if ((mask >> j) & 1u) {
+                                const float sc = __uint_as_float(r[j]);
+                                if (my_cnt < a.cap_l) my_cand[my_cnt] = make_key(order_key32(-sc), (uint32_t)(row0 + j));
+                                ++my_cnt;
+                                if (use_hist) {
+                                    const float fb = (sc - tau0) * inv_w;
+                                    const uint32_t bi = fb >= (float)(TC_HIST - 1) ? TC_HIST - 1 : (uint32_t)fb;
+                                    atomicAdd(my_hist + bi, 1u);     // result unused: a fire-and-forget RED
+                                }
+                            }
                         }
-                        __syncwarp();
                     }
                 }
             }
         }
         tc_fence_before();
-        mbar_arrive_cluster(tempty_cluster_addr + 8 * acc);  // all epilogue threads release the accumulator
-        if (a.mode == 0 && active && tau_f > NEG_INF) {      // share the threshold GPU-wide when it moved
-            const uint32_t k32 = order_key32(-tau_f);
-            if (k32 < tau_pub) {
-                tau_pub = k32;
-                atomicMin(gtau, k32);
+        mbar_arrive_cluster(tempty_cluster_addr + 8 * accn);  // all epilogue threads release the accumulator
+        if constexpr (!DUMP) {
+            if (active && tau_f > TC_NEG_INF) {              // share the threshold GPU-wide when it moved
+                const uint32_t k32 = order_key32(-tau_f);
+                if (k32 < tau_pub) {
+                    tau_pub = k32;
+                    atomicMin(gtau, k32);
+                }
             }
         }
     }
-
-    __syncwarp();
-    if (a.mode == 1) {
-        // pre-pass result: this CTA's (pair's) best live score per query -- a distinct row per list
-        if (active) a.maxima[((size_t)q_base + t) * n_lists + list_idx] = mx_all;
-    } else {
-        // publish the sorted list of every query of the warp (KEY_SENTINEL padded)
-        for (uint32_t qi = 0; qi < 32; ++qi) {
-            const uint32_t qt = wq + qi;
-            if (qt >= nq_local) break;
-            a.lists[((size_t)(q_base + qt) * n_lists + list_idx) * 32 + lane] = wlists[(size_t)qi * 32 + lane];
-        }
+    if constexpr (!DUMP) {
+        if (active) a.cnts[(size_t)q * n_lists + list_idx] = my_cnt;
     }
 }
 
-// ---- K1: the sweep -----------------------------------------------------------------------------
+// ---- K1: the sweep, one CTA per SM (128 queries per sweep) ------------------------------------------
+template <bool DUMP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
                const TcArgs a)
@@ -187,17 +325,17 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
     const uint32_t nkb = a.dim / TC_KB;          // K-blocks per row
     const uint32_t S = a.stages;
 
-    // carve-up: A block | B ring | per-query lists | barriers | tmem ptr
+    // carve-up: A block | B ring | barriers | control word | tmem ptr
     uint8_t *a_base = smem;                                         // nkb x (128 x 128 B)
     uint8_t *b_base = a_base + (size_t)nkb * TC_M * 128;            // S x 16 KB
-    uint64_t *lists = reinterpret_cast<uint64_t *>(b_base + (size_t)S * TC_STAGE_BYTES);  // [128 queries][32]
-    uint64_t *bars = lists + (size_t)32 * TC_M;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(b_base + (size_t)S * TC_STAGE_BYTES);
     uint64_t *full_bar = bars;                       // [S]
     uint64_t *empty_bar = bars + S;                  // [S]
     uint64_t *tfull_bar = bars + 2 * S;              // [TC_ACC_STAGES]
     uint64_t *tempty_bar = tfull_bar + TC_ACC_STAGES;  // [TC_ACC_STAGES]
     uint64_t *a_bar = tempty_bar + TC_ACC_STAGES;    // [1]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_bar + 1);
+    uint32_t *s_ctl = tmem_slot + 1;
 
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < S; ++i) {
@@ -220,8 +358,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
     const uint32_t tmem_base = *tmem_slot;
 
     const uint64_t n_tiles = (a.n_rows + TC_N - 1) / TC_N;
-    uint64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    if (a.tile_limit && my_tiles > a.tile_limit) my_tiles = a.tile_limit;   // pre-pass: a prefix of this CTA's tiles
+    const uint64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint64_t it0 = (DUMP || my_tiles == 0) ? 1 : 0;   // iteration 0 = the sample pass
+    const uint64_t sh = DUMP ? 1 : 0;                       // accumulator-stage numbering starts at the first iteration run
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -231,8 +370,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
                 tma_load_2d(smem_u32(a_base + (size_t)kb * TC_M * 128), &tmap_q, smem_u32(a_bar), (int32_t)(kb * TC_KB),
                             (int32_t)(a.q_tile * TC_M));
             uint32_t st = 0, ph = 0;
-            for (uint64_t it = 0; it < my_tiles; ++it) {
-                const uint64_t tile = blockIdx.x + it * gridDim.x;
+            for (uint64_t it = it0; it <= my_tiles; ++it) {
+                const uint64_t tile = tile_of_iter(blockIdx.x, gridDim.x, it);
                 for (uint32_t kb = 0; kb < nkb; ++kb) {
                     mbar_wait(smem_u32(empty_bar + st), ph ^ 1);
                     mbar_arrive_expect_tx(smem_u32(full_bar + st), TC_STAGE_BYTES);
@@ -249,9 +388,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
             mbar_wait(smem_u32(a_bar), 0);
             tc_fence_after();
             uint32_t st = 0, ph = 0;
-            for (uint64_t it = 0; it < my_tiles; ++it) {
-                const uint32_t acc = (uint32_t)(it % TC_ACC_STAGES);
-                const uint32_t acc_ph = (uint32_t)((it / TC_ACC_STAGES) & 1);
+            for (uint64_t it = it0; it <= my_tiles; ++it) {
+                const uint32_t acc = (uint32_t)((it - sh) % TC_ACC_STAGES);
+                const uint32_t acc_ph = (uint32_t)(((it - sh) / TC_ACC_STAGES) & 1);
                 mbar_wait(smem_u32(tempty_bar + acc), acc_ph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * TC_N;
@@ -271,9 +410,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
         }
     } else if (warp >= 4) {
         // ===== epilogue: thread t <-> query t <-> TMEM lane t =====
-        tc_epilogue<TC_N>(a, lists, tmem_base, tfull_bar, smem_u32(tempty_bar), my_tiles, /*tile0=*/blockIdx.x,
-                          /*tile_stride=*/gridDim.x, /*q_base=*/a.q_tile * TC_M, /*nq_local=*/a.nq,
-                          /*list_idx=*/blockIdx.x, /*n_lists=*/gridDim.x, TC_ACC_STAGES);
+        tc_epilogue<TC_N, DUMP>(a, s_ctl, tmem_base, tfull_bar, smem_u32(tempty_bar), my_tiles, /*tile0=*/blockIdx.x,
+                                /*tile_stride=*/gridDim.x, /*q_base=*/a.q_tile * TC_M, /*nq_local=*/a.nq,
+                                /*list_idx=*/blockIdx.x, /*n_lists=*/gridDim.x, TC_ACC_STAGES);
     }
 
     tc_fence_before();
@@ -296,6 +435,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
 //             arrive; both CTAs' cta_group::2 TMA loads credit their bytes to it;
 //   empty[s]  per CTA; the leader's tcgen05.commit multicasts the arrival to both;
 //   tfull[a]  per CTA, same multicast commit;  tempty[a] leader's only, 256 epilogue arrivals.
+template <bool DUMP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
                 const TcArgs a)
@@ -311,14 +451,14 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_cons
 
     uint8_t *a_base = smem;                                         // this CTA's 128 queries
     uint8_t *b_base = a_base + (size_t)nkb * TC_M * 128;            // S x 16 KB: this CTA's half of each tile
-    uint64_t *lists = reinterpret_cast<uint64_t *>(b_base + (size_t)S * TC_STAGE_BYTES);
-    uint64_t *bars = lists + (size_t)32 * TC_M;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(b_base + (size_t)S * TC_STAGE_BYTES);
     uint64_t *full_bar = bars;
     uint64_t *empty_bar = bars + S;
     uint64_t *tfull_bar = bars + 2 * S;
-    uint64_t *tempty_bar = tfull_bar + ACC2;
-    uint64_t *a_bar = tempty_bar + ACC2;
+    uint64_t *tempty_bar = tfull_bar + TC_ACC_STAGES;               // same carve-up as the 1-CTA form (ACC2 used)
+    uint64_t *a_bar = tempty_bar + TC_ACC_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_bar + 1);
+    uint32_t *s_ctl = tmem_slot + 1;
 
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < S; ++i) {
@@ -343,8 +483,9 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_cons
 
     const uint32_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const uint64_t n_tiles = (a.n_rows + N2 - 1) / N2;
-    uint64_t my_tiles = cluster_id < n_tiles ? (n_tiles - cluster_id + n_clusters - 1) / n_clusters : 0;
-    if (a.tile_limit && my_tiles > a.tile_limit) my_tiles = a.tile_limit;
+    const uint64_t my_tiles = cluster_id < n_tiles ? (n_tiles - cluster_id + n_clusters - 1) / n_clusters : 0;
+    const uint64_t it0 = (DUMP || my_tiles == 0) ? 1 : 0;
+    const uint64_t sh = DUMP ? 1 : 0;
 
     // resident A operand: this CTA's 128 queries.  Everyone waits, then the pair synchronises so the
     // leader's MMA thread may read the peer's A through the pair datapath.
@@ -361,8 +502,8 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_cons
         // ===== TMA producer (both CTAs): my half of every tile =====
         if (lane == 0) {
             uint32_t st = 0, ph = 0;
-            for (uint64_t it = 0; it < my_tiles; ++it) {
-                const uint64_t tile = cluster_id + it * n_clusters;
+            for (uint64_t it = it0; it <= my_tiles; ++it) {
+                const uint64_t tile = tile_of_iter(cluster_id, n_clusters, it);
                 for (uint32_t kb = 0; kb < nkb; ++kb) {
                     mbar_wait(smem_u32(empty_bar + st), ph ^ 1);
                     const uint32_t lfull = mapa_u32(smem_u32(full_bar + st), 0);
@@ -379,9 +520,9 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_cons
         if (leader && lane == 0) {
             constexpr uint32_t idesc = make_idesc_f16(256, N2);
             uint32_t st = 0, ph = 0;
-            for (uint64_t it = 0; it < my_tiles; ++it) {
-                const uint32_t acc = (uint32_t)(it % ACC2);
-                const uint32_t acc_ph = (uint32_t)((it / ACC2) & 1);
+            for (uint64_t it = it0; it <= my_tiles; ++it) {
+                const uint32_t acc = (uint32_t)((it - sh) % ACC2);
+                const uint32_t acc_ph = (uint32_t)(((it - sh) / ACC2) & 1);
                 mbar_wait(smem_u32(tempty_bar + acc), acc_ph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * N2;
@@ -400,10 +541,10 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_cons
             }
         }
     } else if (warp >= 4) {
-        tc_epilogue<N2>(a, lists, tmem_base, tfull_bar, mapa_u32(smem_u32(tempty_bar), 0), my_tiles, /*tile0=*/cluster_id,
-                        /*tile_stride=*/n_clusters, /*q_base=*/a.q_tile * 256 + rank * TC_M,
-                        /*nq_local=*/a.nq > rank * TC_M ? (a.nq - rank * TC_M < TC_M ? a.nq - rank * TC_M : TC_M) : 0,
-                        /*list_idx=*/cluster_id, /*n_lists=*/n_clusters, ACC2);
+        tc_epilogue<N2, DUMP>(a, s_ctl, tmem_base, tfull_bar, mapa_u32(smem_u32(tempty_bar), 0), my_tiles,
+                              /*tile0=*/cluster_id, /*tile_stride=*/n_clusters, /*q_base=*/a.q_tile * 256 + rank * TC_M,
+                              /*nq_local=*/a.nq > rank * TC_M ? (a.nq - rank * TC_M < TC_M ? a.nq - rank * TC_M : TC_M) : 0,
+                              /*list_idx=*/cluster_id, /*n_lists=*/n_clusters, ACC2);
     }
 
     tc_fence_before();
@@ -415,11 +556,13 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_cons
 }
 
 // ---- query preparation: fp16 rounding + the rigorous error bound -------------------------------
-// qh[q] = fp16(q) (zero rows for q >= b up to the 128-padded count); err[q] = |q - fp16(q)|_2,
-// qnorm[q] = |q|_2 (both rounded up a little by computing in f64).
-__global__ void prep_queries_kernel(const float *__restrict__ q, uint32_t b, uint32_t b_pad, uint32_t dim,
+// qh[q] = fp16(q) (zero rows for q >= b up to the padded count); err[q] = |q - fp16(q)|_2,
+// qnorm[q] = |q|_2 (both rounded up a little by computing in f64).  Also resets the per-search
+// device state of the sweep (thresholds, histograms, sample-phase arrival counters, flag counter).
+__global__ void prep_queries_kernel(const float *__restrict__ q, uint32_t b, uint32_t dim,
                                     __half *__restrict__ qh, float *__restrict__ err, float *__restrict__ qnorm,
-                                    uint32_t *__restrict__ gtau, uint32_t *__restrict__ flags)
+                                    uint32_t *__restrict__ gtau, uint32_t *__restrict__ flags, uint32_t *__restrict__ hist,
+                                    uint32_t *__restrict__ arrive, uint32_t n_qtiles, uint32_t *__restrict__ nflag)
 {
     const uint32_t row = blockIdx.x;
     __shared__ double s_e[32], s_n[32];
@@ -431,6 +574,11 @@ __global__ void prep_queries_kernel(const float *__restrict__ q, uint32_t b, uin
         double d = (double)v - (double)__half2float(h);
         e += d * d;
         n2 += (double)v * (double)v;
+    }
+    if (threadIdx.x < TC_HIST) hist[(size_t)row * TC_HIST + threadIdx.x] = 0;
+    if (row == 0) {
+        for (uint32_t i = threadIdx.x; i < n_qtiles; i += blockDim.x) arrive[i] = 0;
+        if (threadIdx.x == 0) *nflag = 0;
     }
     for (int o = 16; o > 0; o >>= 1) {
         e += __shfl_down_sync(0xFFFFFFFFu, e, o);
@@ -450,42 +598,16 @@ __global__ void prep_queries_kernel(const float *__restrict__ q, uint32_t b, uin
         if (row < b) {
             err[row] = (float)(sqrt(te) * 1.000001);
             qnorm[row] = (float)(sqrt(tn) * 1.000001);
+            flags[row] = 0;
         }
         gtau[row] = 0xFFFFFFFFu;
-        if (row < b) flags[row] = 0;
-        (void)b_pad;
-    }
-}
-
-// ---- threshold seeding from the pre-pass -------------------------------------------------------
-// maxima[q][cta] = best live approximate score CTA `cta` saw for query q over its first tiles.  The
-// kk-th largest of them is a valid lower bound on the global kk-th best (kk distinct rows reach it).
-__global__ void __launch_bounds__(256)
-tau_init_kernel(const float *__restrict__ maxima, uint32_t n_cta, uint32_t kk, uint32_t *__restrict__ gtau)
-{
-    __shared__ uint64_t keys[256];
-    const uint32_t q = blockIdx.x;
-    const uint32_t M = next_pow2(n_cta < 2 ? 2 : n_cta);
-    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) {
-        uint64_t key = KEY_SENTINEL;
-        if (i < n_cta) {
-            const float m = maxima[(size_t)q * n_cta + i];
-            if (m > -__uint_as_float(0x7F800000u)) key = make_key(order_key32(-m), i);
-        }
-        keys[i] = key;
-    }
-    __syncthreads();
-    block_bitonic_sort(keys, M);
-    if (threadIdx.x == 0) {
-        const uint64_t kth = n_cta >= kk ? keys[kk - 1] : KEY_SENTINEL;
-        gtau[q] = kth == KEY_SENTINEL ? 0xFFFFFFFFu : (uint32_t)(kth >> 32);
     }
 }
 
 // ---- K2: exact re-score + certification ---------------------------------------------------------
 // exact -dot in the reference's order for one (query,row): one thread, sequential chain
-template <int ORDER>
-SG_DEVICE_INLINE float exact_dot(const float *__restrict__ q, const __half *__restrict__ row, uint32_t dim)
+template <int ORDER, typename QP>
+SG_DEVICE_INLINE float exact_dot(QP q, const __half *__restrict__ row, uint32_t dim)
 {
     if constexpr (ORDER == SG_ORDER_SCALAR) {
         float sum = 0.0f;
@@ -509,81 +631,90 @@ SG_DEVICE_INLINE float exact_dot(const float *__restrict__ q, const __half *__re
 
 // one CTA (256 threads) per query
 __global__ void __launch_bounds__(256)
-finalize_tc_kernel(const FinalizeArgs f)
+finalize_tc_kernel(const __grid_constant__ FinalizeArgs f)
 {
-    __shared__ uint64_t keys[TC_CAND_CAP];      // heads, then surviving approx keys, then exact keys
-    __shared__ float q_s[2048];
+    __shared__ uint64_t keys[TC_FIN_NC];        // surviving approximate keys, sorted
+    __shared__ uint64_t ekeys[TC_KK_MAX];       // exact keys of the kk best
     __shared__ uint32_t s_flag, s_n;
+    extern __shared__ __align__(16) uint8_t fin_dyn[];
+    float *q_s = reinterpret_cast<float *>(fin_dyn);                     // [dim]
+    uint32_t *rows_s = reinterpret_cast<uint32_t *>(q_s + f.dim);        // [rc][dim/2 + 1]
     const uint32_t q = blockIdx.x;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t L = f.n_lists;
-    const uint64_t *ql = f.lists + (size_t)q * L * 32;   // every list is 32 slots, the first f.kk are used
     for (uint32_t i = threadIdx.x; i < f.dim; i += blockDim.x) q_s[i] = f.queries[(size_t)q * f.dim + i];
-    // (1) threshold from the list heads: at least kk candidates (kk distinct heads) have key <= T0,
-    //     so every member of the global top-kk has key <= T0.
-    const uint32_t MH = next_pow2(L < 2 ? 2 : L);
-    for (uint32_t i = threadIdx.x; i < MH; i += blockDim.x) keys[i] = i < L ? ql[(size_t)i * 32] : KEY_SENTINEL;
     if (threadIdx.x == 0) {
         s_flag = 0;
         s_n = 0;
     }
     __syncthreads();
-    block_bitonic_sort(keys, MH);
-    const uint64_t T0 = L >= f.kk ? keys[f.kk - 1] : KEY_SENTINEL;
-    __syncthreads();
-    // (2) gather every entry with key <= T0 -- all threads, coalesced over the [L][32] list block
-    for (uint32_t e = threadIdx.x; e < L * 32; e += blockDim.x) {
-        if ((e & 31) >= f.kk) continue;
-        const uint64_t key = ql[e];
-        if (key != KEY_SENTINEL && key <= T0) {
-            const uint32_t slot = atomicAdd(&s_n, 1u);
-            if (slot < TC_CAND_CAP) keys[slot] = key;
+    // (1) gather every candidate at or above the final shared threshold (a valid bound on the kk-th best, so at
+    //     least kk survive whenever a threshold was ever published) -- one warp per (query, list) region
+    const uint32_t gt = f.gtau[q];
+    for (uint32_t l = warp; l < L; l += blockDim.x / 32) {
+        uint32_t c = f.cnts[(size_t)q * L + l];
+        if (c > f.cap_l) {                       // the region overflowed: candidates were lost
+            if (lane == 0) s_flag = 1u;
+            c = f.cap_l;
+        }
+        const uint64_t *src = f.cand + ((size_t)q * L + l) * f.cap_l;
+        for (uint32_t e = lane; e < c; e += 32) {
+            const uint64_t key = src[e];
+            if ((uint32_t)(key >> 32) <= gt) {
+                const uint32_t slot = atomicAdd(&s_n, 1u);
+                if (slot < TC_FIN_NC) keys[slot] = key;
+            }
         }
     }
     __syncthreads();
     uint32_t n = s_n;
-    const bool overflow = n > TC_CAND_CAP;
-    if (overflow) n = TC_CAND_CAP;
+    if (n > TC_FIN_NC) {
+        n = TC_FIN_NC;
+        if (threadIdx.x == 0) s_flag = 1u;
+    }
     const uint32_t M = next_pow2(n < 2 ? 2 : n);
     for (uint32_t i = n + threadIdx.x; i < M; i += blockDim.x) keys[i] = KEY_SENTINEL;
-    if (threadIdx.x == 0 && overflow) s_flag = 1u;
     __syncthreads();
     block_bitonic_sort(keys, M);                 // ascending approx key: best approximate first
-    const uint32_t kk = n < f.kk ? n : f.kk;     // the global top-KK by approximate score
+    const uint32_t kk = n < f.kk ? n : f.kk;     // the global top-kk by approximate score
     // weakest approximate similarity that was kept == bound on everything that was dropped
-    const bool dropped_any = (f.n_live > kk);
     const float weakest_approx_sim = kk ? -key32_to_dist((uint32_t)(keys[kk - 1] >> 32)) : 0.0f;
-    __syncthreads();
-    // exact re-score: stage the kk candidate rows in shared memory (coalesced), then one thread per
-    // candidate walks the reference's sequential chain.  Row pitch dim/2 + 1 words: conflict-free.
-    extern __shared__ __align__(16) uint8_t rows_raw[];
-    uint32_t *rows_s = reinterpret_cast<uint32_t *>(rows_raw);
-    const uint32_t pitch = f.dim / 2 + 1;
-    for (uint32_t c = 0; c < kk; ++c) {
-        const uint32_t row = (uint32_t)(keys[c] & 0xFFFFFFFFu);
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(reinterpret_cast<const __half *>(f.rows) + (size_t)row * f.dim);
-        for (uint32_t w = threadIdx.x; w < f.dim / 2; w += blockDim.x) rows_s[(size_t)c * pitch + w] = src[w];
+    // (2) exact re-score, rc candidates per round: rows staged in shared memory with 16-byte loads (all in
+    //     flight at once), then one thread per candidate walks the reference's sequential chain.  Row pitch
+    //     dim/2 + 1 words: conflict-free.
+    const uint32_t pitch = f.dim / 2 + 1, vec_per_row = f.dim / 8;
+    for (uint32_t c0 = 0; c0 < kk; c0 += f.rc) {
+        const uint32_t nc = kk - c0 < f.rc ? kk - c0 : f.rc;
+        for (uint32_t i = threadIdx.x; i < nc * vec_per_row; i += blockDim.x) {
+            const uint32_t c = i / vec_per_row, v = i - c * vec_per_row;
+            const uint32_t row = (uint32_t)(keys[c0 + c] & 0xFFFFFFFFu);
+            const uint4 x = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(f.rows) + (size_t)row * f.dim) + v);
+            uint32_t *dst = rows_s + (size_t)c * pitch + 4 * v;
+            dst[0] = x.x; dst[1] = x.y; dst[2] = x.z; dst[3] = x.w;
+        }
+        __syncthreads();
+        if (threadIdx.x < nc) {
+            const uint32_t row = (uint32_t)(keys[c0 + threadIdx.x] & 0xFFFFFFFFu);
+            const __half *rp = reinterpret_cast<const __half *>(rows_s + (size_t)threadIdx.x * pitch);
+            const float dot = f.order == SG_ORDER_AVX2 ? exact_dot<SG_ORDER_AVX2>(q_s, rp, f.dim)
+                                                       : exact_dot<SG_ORDER_SCALAR>(q_s, rp, f.dim);
+            ekeys[c0 + threadIdx.x] = make_key(order_key32(neg_dot_to_dist(dot)), row);
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    uint64_t exact_key = KEY_SENTINEL;
-    if (threadIdx.x < kk) {
-        const uint32_t row = (uint32_t)(keys[threadIdx.x] & 0xFFFFFFFFu);
-        const __half *rp = reinterpret_cast<const __half *>(rows_s + (size_t)threadIdx.x * pitch);
-        float dot = f.order == SG_ORDER_AVX2 ? exact_dot<SG_ORDER_AVX2>(q_s, rp, f.dim)
-                                             : exact_dot<SG_ORDER_SCALAR>(q_s, rp, f.dim);
-        exact_key = make_key(order_key32(neg_dot_to_dist(dot)), row);
-    }
-    __syncthreads();
     const uint32_t M2 = next_pow2(kk < 2 ? 2 : kk);
-    if (threadIdx.x < M2) keys[threadIdx.x] = exact_key;
+    for (uint32_t i = kk + threadIdx.x; i < M2; i += blockDim.x) ekeys[i] = KEY_SENTINEL;
     __syncthreads();
-    block_bitonic_sort(keys, M2);
+    block_bitonic_sort(ekeys, M2);
     const uint32_t out_n = kk < f.k ? kk : f.k;
-    // certification: every dropped row has approx sim <= weakest_approx_sim, hence exact sim <=
-    // weakest_approx_sim + E; it cannot enter (or tie into) the top k if kth_exact_sim is larger.
-    if (threadIdx.x == 0 && dropped_any) {
+    // (3) certification.  Rows that were not re-scored have approx sim <= weakest_approx_sim (survivors past
+    //     the kk-th by the sort; everything else was below a threshold that never exceeded the kk-th best),
+    //     hence exact sim <= weakest_approx_sim + E; none can enter (or tie into) the top k if kth_exact_sim
+    //     is larger.  Fewer than kk candidates with more live rows around (NaN scores, no threshold) -> flag.
+    if (threadIdx.x == 0 && f.n_live > kk) {
         bool ok = false;
-        if (out_n == f.k) {
-            const float kth_exact_sim = -key32_to_dist((uint32_t)(keys[f.k - 1] >> 32));
+        if (kk == f.kk && out_n == f.k) {
+            const float kth_exact_sim = -key32_to_dist((uint32_t)(ekeys[f.k - 1] >> 32));
             const float R = *f.max_row_norm;
             const float E = f.err[q] * R + f.c_acc * f.qnorm[q] * R;
             ok = kth_exact_sim > weakest_approx_sim + E;     // NaN compares false -> flagged
@@ -591,39 +722,118 @@ finalize_tc_kernel(const FinalizeArgs f)
         if (!ok) s_flag = 1u;
     }
     __syncthreads();
+    const bool flagged = s_flag != 0;
     for (uint32_t i = threadIdx.x; i < f.k; i += blockDim.x) {
         const bool valid = i < out_n;
-        const uint64_t key = valid ? keys[i] : KEY_SENTINEL;
+        const uint64_t key = valid ? ekeys[i] : KEY_SENTINEL;
         f.ids_out[(size_t)q * f.k + i] = valid ? (uint32_t)(key & 0xFFFFFFFFu) + f.id_base : 0xFFFFFFFFu;
         f.dist_out[(size_t)q * f.k + i] = valid ? key32_to_dist((uint32_t)(key >> 32)) : __uint_as_float(0x7F800000u);
     }
     if (threadIdx.x == 0) {
         f.counts_out[q] = out_n;
-        f.flags[q] = s_flag;
-        if (s_flag) {
+        f.flags[q] = flagged;
+        if (flagged) {
             const uint32_t slot = atomicAdd(f.n_flagged, 1u);   // arrival order is irrelevant: slots are independent
             f.flag_list[slot] = q;
             atomicAdd(f.flag_total, 1ull);
         }
     }
+    // multi-GPU: a certified result is final -- push it to the peers now (flagged ones are pushed by the re-run's merge)
+    if (!flagged) push_query(f.push, q, f.ids_out + (size_t)q * f.k, f.dist_out + (size_t)q * f.k);
+}
+
+// ---- diagnostics: exact score of every (query, row) pair ------------------------------------------------
+__global__ void __launch_bounds__(256)
+exact_scores_kernel(const float *__restrict__ q, uint32_t b, const __half *__restrict__ rows, uint32_t dim, uint64_t row0,
+                    uint64_t n, int order, float *__restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const __half *rp = rows + (row0 + i) * dim;
+    for (uint32_t qi = 0; qi < b; ++qi) {
+        const float *qp = q + (size_t)qi * dim;
+        const float dot = order == SG_ORDER_AVX2 ? exact_dot<SG_ORDER_AVX2>(qp, rp, dim) : exact_dot<SG_ORDER_SCALAR>(qp, rp, dim);
+        out[(size_t)qi * n + i] = dot;
+    }
+}
+
+struct DevAttr {           // "dynamic shared memory limit already raised to" per (kernel, device); process-wide
+    std::mutex mu;
+    size_t set[64] = {0};
+};
+template <typename K>
+cudaError_t ensure_smem(K kern, DevAttr &da, size_t smem)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> g(da.mu);
+    size_t &cur = da.set[dev & 63];
+    if (smem > cur) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        cur = smem;
+    }
+    return cudaSuccess;
+}
+
+// The sweep's sample phase ends in a device-wide meeting point, so the whole grid must be co-resident:
+// launch cooperatively (the runtime then guarantees it); SG_TC_COOP=0 or a refusal falls back to a plain
+// launch (the kernel's own time-out keeps that safe, at worst slow).
+template <typename K>
+cudaError_t launch_sweep(K kern, const CUtensorMap &tmap_rows, const CUtensorMap &tmap_q, const TcArgs &a, uint32_t grid,
+                         size_t smem, cudaStream_t st)
+{
+    static const int coop = [] {
+        const char *v = getenv("SG_TC_COOP");
+        return (v && *v) ? atoi(v) : 1;
+    }();
+    if (coop) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap_rows, tmap_q, a);
+        if (e == cudaSuccess) return e;
+        cudaGetLastError();                      // clear; fall through to the plain launch
+    }
+    kern<<<grid, TC_THREADS, smem, st>>>(tmap_rows, tmap_q, a);
+    return cudaGetLastError();
 }
 
 }  // namespace
 
-size_t tc_smem_bytes(uint32_t dim, uint32_t stages, uint32_t kk)
+size_t tc_smem_bytes(uint32_t dim, uint32_t stages)
 {
     size_t s = (size_t)(dim / TC_KB) * TC_M * 128;          // A
     s += (size_t)stages * TC_STAGE_BYTES;                    // B ring
-    (void)kk;
-    s += (size_t)32 * TC_M * 8;                              // lists: 32 slots per query
     s += (size_t)(2 * stages + 2 * TC_ACC_STAGES + 1) * 8 + 16;
     return s;
 }
 
-cudaError_t launch_prep_queries(const float *d_q, uint32_t b, uint32_t b_pad, uint32_t dim, __half *d_qh, float *d_err,
-                                float *d_qnorm, uint32_t *d_gtau, uint32_t *d_flags, cudaStream_t st)
+// Accumulation-error coefficient of the certificate: |tensor-core dot - reference-order dot| <= c_acc * |q| * |row|
+// for the same fp16 operands.  Tensor core: products exact in f32, <= dim accumulation steps of <= 1 ulp each
+// (truncation allowed): dim * 2^-23 * sum|a_i b_i|.  Reference chain: dim/4 + 3 round-to-nearest additions of at
+// most sum|a_i b_i| plus one rounding per product: (dim/4 + 4) * 2^-24.  sum|a_i b_i| <= |fp16(q)| |row| <=
+// (1 + 2^-11) |q| |row|; the factor 1.25 covers that and the rounding of the bound itself.
+// tests/test_scan_tc_gpu.py::test_accumulation_error_bound measures the real maximum against it.
+float tc_c_acc(uint32_t dim)
 {
-    prep_queries_kernel<<<b_pad, 128, 0, st>>>(d_q, b, b_pad, dim, d_qh, d_err, d_qnorm, d_gtau, d_flags);
+    return 1.25f * ((float)dim * 1.1920929e-7f + (float)(dim / 4 + 4) * 5.9604645e-8f);
+}
+
+cudaError_t launch_prep_queries(const float *d_q, uint32_t b, uint32_t b_pad, uint32_t dim, __half *d_qh, float *d_err,
+                                float *d_qnorm, uint32_t *d_gtau, uint32_t *d_flags, uint32_t *d_hist, uint32_t *d_arrive,
+                                uint32_t n_qtiles, uint32_t *d_nflag, cudaStream_t st)
+{
+    prep_queries_kernel<<<b_pad, 128, 0, st>>>(d_q, b, dim, d_qh, d_err, d_qnorm, d_gtau, d_flags, d_hist, d_arrive,
+                                               n_qtiles, d_nflag);
     count_launch();
     return cudaGetLastError();
 }
@@ -631,54 +841,56 @@ cudaError_t launch_prep_queries(const float *d_q, uint32_t b, uint32_t b_pad, ui
 cudaError_t launch_scan_tc(const CUtensorMap &tmap_rows, const CUtensorMap &tmap_q, const TcArgs &a, uint32_t grid,
                            size_t smem, cudaStream_t st)
 {
-    static size_t smem_set_dev[64] = {0};
-    int dev_ = 0;
-    cudaGetDevice(&dev_);
-    size_t &smem_set = smem_set_dev[dev_ & 63];
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        smem_set = smem;
+    static DevAttr da, da_dump;
+    cudaError_t e;
+    if (a.dump) {
+        if ((e = ensure_smem(scan_tc_kernel<true>, da_dump, smem)) != cudaSuccess) return e;
+        scan_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(tmap_rows, tmap_q, a);
+        e = cudaGetLastError();
+    } else {
+        if ((e = ensure_smem(scan_tc_kernel<false>, da, smem)) != cudaSuccess) return e;
+        e = launch_sweep(scan_tc_kernel<false>, tmap_rows, tmap_q, a, grid, smem, st);
     }
-    scan_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmap_rows, tmap_q, a);
     count_launch();
-    return cudaGetLastError();
+    return e;
 }
 
 cudaError_t launch_scan_tc2(const CUtensorMap &tmap_rows, const CUtensorMap &tmap_q, const TcArgs &a, uint32_t grid,
                             size_t smem, cudaStream_t st)
 {
-    static size_t smem_set_dev[64] = {0};
-    int dev_ = 0;
-    cudaGetDevice(&dev_);
-    size_t &smem_set = smem_set_dev[dev_ & 63];
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(scan_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        smem_set = smem;
+    static DevAttr da, da_dump;
+    cudaError_t e;
+    if (a.dump) {
+        if ((e = ensure_smem(scan_tc2_kernel<true>, da_dump, smem)) != cudaSuccess) return e;
+        scan_tc2_kernel<true><<<grid, TC_THREADS, smem, st>>>(tmap_rows, tmap_q, a);   // __cluster_dims__(2,1,1): grid must be even
+        e = cudaGetLastError();
+    } else {
+        if ((e = ensure_smem(scan_tc2_kernel<false>, da, smem)) != cudaSuccess) return e;
+        e = launch_sweep(scan_tc2_kernel<false>, tmap_rows, tmap_q, a, grid, smem, st);
     }
-    scan_tc2_kernel<<<grid, TC_THREADS, smem, st>>>(tmap_rows, tmap_q, a);   // __cluster_dims__(2,1,1): grid must be even
     count_launch();
-    return cudaGetLastError();
-}
-
-cudaError_t launch_tau_init(const float *d_maxima, uint32_t b_pad, uint32_t n_cta, uint32_t kk, uint32_t *d_gtau,
-                            cudaStream_t st)
-{
-    if (n_cta > 256) return cudaErrorInvalidValue;
-    tau_init_kernel<<<b_pad, 256, 0, st>>>(d_maxima, n_cta, kk, d_gtau);
-    count_launch();
-    return cudaGetLastError();
+    return e;
 }
 
 cudaError_t launch_finalize_tc(const FinalizeArgs &f, uint32_t b, cudaStream_t st)
 {
-    const size_t smem = (size_t)f.kk * (f.dim / 2 + 1) * 4;
-    if (smem > 32 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(finalize_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (size_t)f.dim * 4 + (size_t)f.rc * (f.dim / 2 + 1) * 4;
+    static DevAttr da;
+    if (smem > 48 * 1024) {
+        cudaError_t e = ensure_smem(finalize_tc_kernel, da, smem);
         if (e != cudaSuccess) return e;
     }
     finalize_tc_kernel<<<b, 256, smem, st>>>(f);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_exact_scores(const float *d_q, uint32_t b, const void *rows, uint32_t dim, uint64_t row0, uint64_t n,
+                                int order, float *d_out, cudaStream_t st)
+{
+    if (n == 0 || b == 0) return cudaSuccess;
+    exact_scores_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_q, b, reinterpret_cast<const __half *>(rows), dim, row0,
+                                                                     n, order, d_out);
     count_launch();
     return cudaGetLastError();
 }

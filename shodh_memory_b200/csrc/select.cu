@@ -5,7 +5,10 @@
 // survivors of the sweep, and serves as the k-way merge of per-shard results
 // (SURVEY.md 8e).  All ordering is on 64-bit integer keys (order_key32(dist) << 32 | id),
 // whose unsigned order IS (dist total_cmp asc, id asc): no float compare, no ties.
+#include <mutex>
+
 #include "sg_internal.h"
+#include "sg_push.cuh"
 
 namespace sg {
 namespace {
@@ -22,7 +25,7 @@ merge_kernel(const uint64_t *__restrict__ lists, const uint32_t *__restrict__ id
              uint32_t k, uint32_t id_base, uint64_t list_stride, uint64_t query_stride,
              uint64_t *__restrict__ keys_out, uint32_t *__restrict__ ids_out, float *__restrict__ dist_out,
              uint32_t *__restrict__ counts, const uint32_t *__restrict__ slot_count,
-             const uint32_t *__restrict__ slot_to_query)
+             const uint32_t *__restrict__ slot_to_query, const __grid_constant__ PushArgs push)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint64_t *buf = reinterpret_cast<uint64_t *>(smem_raw);
@@ -135,6 +138,8 @@ merge_kernel(const uint64_t *__restrict__ lists, const uint32_t *__restrict__ id
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(&s_cnt, local);
     __syncthreads();
     if (threadIdx.x == 0) counts[q_out] = s_cnt;
+    // multi-GPU: this is the query's final local result -- hand it to the peers right away
+    push_query(push, q_out, ids_out + (size_t)q_out * k, dist_out + (size_t)q_out * k);
 }
 
 template <bool PAIRS>
@@ -142,7 +147,7 @@ cudaError_t launch(const uint64_t *lists, const uint32_t *ids_in, const float *d
                    uint32_t n_per_query, uint32_t group_keys, uint32_t n_groups, uint32_t k, uint32_t id_base,
                    uint64_t list_stride, uint64_t query_stride, uint64_t *keys_out, uint32_t *ids, float *dist,
                    uint32_t *counts, cudaStream_t st, const uint32_t *slot_count = nullptr,
-                   const uint32_t *slot_to_query = nullptr)
+                   const uint32_t *slot_to_query = nullptr, const PushArgs *push = nullptr)
 {
     if (b == 0) return cudaSuccess;
     const uint32_t per_cta = n_groups > 1 ? group_keys : n_per_query;
@@ -151,18 +156,24 @@ cudaError_t launch(const uint64_t *lists, const uint32_t *ids_in, const float *d
     size_t smem = (size_t)need * 8;
     uint32_t threads = need / 2 < 1024 ? (need / 2 < 32 ? 32 : need / 2) : 1024;
     auto kern = merge_kernel<PAIRS>;
-    static bool attr_set_dev[64] = {false};
-    int dev_ = 0;
-    cudaGetDevice(&dev_);
-    bool &attr_set = attr_set_dev[dev_ & 63];
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SORT_MAX * 8));
-        if (e != cudaSuccess) return e;
-        attr_set = true;
+    {
+        static std::mutex mu;                    // process-wide: two stores on two threads may get here together
+        static bool attr_set_dev[64] = {false};
+        int dev_ = 0;
+        cudaGetDevice(&dev_);
+        std::lock_guard<std::mutex> g(mu);
+        bool &attr_set = attr_set_dev[dev_ & 63];
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SORT_MAX * 8));
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
     }
+    PushArgs pa{};
+    if (push && n_groups == 1) pa = *push;       // only the stage that writes the final (ids, dist) pushes
     kern<<<b * n_groups, threads, smem, st>>>(lists, ids_in, dist_in, n_per_query, group_keys, n_groups, k, id_base,
                                               list_stride, query_stride, keys_out, ids, dist, counts, slot_count,
-                                              slot_to_query);
+                                              slot_to_query, pa);
     count_launch();
     return cudaGetLastError();
 }
@@ -183,7 +194,7 @@ uint32_t merge_groups(uint32_t n_lists, uint32_t k)
 
 cudaError_t launch_merge_keys(const uint64_t *d_lists, uint32_t b, uint32_t n_lists, uint32_t k, uint32_t id_base,
                               uint64_t *d_scratch, uint32_t *d_ids, float *d_dist, uint32_t *d_counts,
-                              cudaStream_t st)
+                              cudaStream_t st, const PushArgs *push)
 {
     const uint32_t groups = d_scratch ? merge_groups(n_lists, k) : 1;
     if (groups > 1) {
@@ -192,18 +203,18 @@ cudaError_t launch_merge_keys(const uint64_t *d_lists, uint32_t b, uint32_t n_li
                                       d_scratch, nullptr, nullptr, nullptr, st);
         if (e != cudaSuccess) return e;
         return launch<false>(d_scratch, nullptr, nullptr, b, groups * k, groups * k, 1, k, id_base, 0, 0, nullptr,
-                             d_ids, d_dist, d_counts, st);
+                             d_ids, d_dist, d_counts, st, nullptr, nullptr, push);
     }
     return launch<false>(d_lists, nullptr, nullptr, b, n_lists * k, n_lists * k, 1, k, id_base, 0, 0, nullptr, d_ids,
-                         d_dist, d_counts, st);
+                         d_dist, d_counts, st, nullptr, nullptr, push);
 }
 
 cudaError_t launch_merge_keys_flagged(const uint64_t *d_lists, uint32_t b, uint32_t n_lists, uint32_t k, uint32_t id_base,
                                       const uint32_t *d_slot_count, const uint32_t *d_slot_to_query, uint32_t *d_ids,
-                                      float *d_dist, uint32_t *d_counts, cudaStream_t st)
+                                      float *d_dist, uint32_t *d_counts, cudaStream_t st, const PushArgs *push)
 {
     return launch<false>(d_lists, nullptr, nullptr, b, n_lists * k, n_lists * k, 1, k, id_base, 0, 0, nullptr, d_ids,
-                         d_dist, d_counts, st, d_slot_count, d_slot_to_query);
+                         d_dist, d_counts, st, d_slot_count, d_slot_to_query, push);
 }
 
 cudaError_t launch_merge_pairs(const uint32_t *d_ids_in, const float *d_dist_in, uint32_t b, uint32_t n_lists,

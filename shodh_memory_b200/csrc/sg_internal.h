@@ -23,48 +23,73 @@ size_t scan_smem_bytes(uint32_t W, uint32_t ring, uint32_t qb, uint32_t dim, uin
 cudaError_t launch_scan_exact(const CUtensorMap &tmap, const ScanArgs &a, int qb, bool f16, int order, int metric,
                               uint32_t grid, uint32_t W, size_t smem, cudaStream_t st);
 
+// ---- peer push of final results (exchange.cu) ----
+// Kernels that write a query's FINAL (ids, dist)[k] can also push it straight into every rank's exchange buffer
+// over NVLink peer memory and publish the per-(rank, query) flag, so the multi-GPU step needs no separate
+// push / all-gather launch.  world == 0 disables it.  Buffer layout: see exchange.cu.
+struct PushArgs {
+    uint32_t *peer[8];        // base of every rank's symmetric buffer (peer[rank] is local)
+    uint32_t rank, world, epoch, b, k;
+    uint32_t q0;              // index of the calling kernel's query 0 within the exchange's b queries
+};
+
 // ---- scan_tc.cu (tensor-core sweep) ----
-constexpr uint32_t TC_CAND_CAP = 1024;  // candidates at or above the heads threshold (overflow -> exact re-run)
+constexpr uint32_t TC_HIST = 32;        // buckets of the per-query score histogram that tightens the threshold
+constexpr uint32_t TC_FIN_NC = 2048;    // survivors one finalize CTA can sort (more -> exact re-run)
+constexpr uint32_t TC_KK_MAX = 256;     // candidates re-scored per query (k + slack)
 struct TcArgs {
     uint64_t n_rows;
     uint32_t dim;
     uint32_t nq;              // live queries in this query tile (128 per tile; 256 in pair mode)
     uint32_t q_tile;          // which query tile
     uint32_t stages;          // B ring depth
-    uint32_t kk;              // candidates kept per query (k + slack)
+    uint32_t kk;              // candidates wanted per query (k + slack)
+    uint32_t b_pad;           // padded query count: stride of the [value][query] sample array
+    uint32_t J;               // sample maxima each list contributes (n_lists * J >= kk)
+    uint32_t cap_l;           // entries per (query, list) candidate region
     const uint32_t *deleted;
-    uint32_t *gtau;           // [b_pad] shared threshold per query (best CTA-local kk-th distance key so far)
-    uint64_t *lists;          // [b_pad][gridDim.x][kk] each CTA's sorted approximate candidates
-    uint32_t mode;            // 0 = sweep; 1 = pre-pass (per-CTA maxima only, seeds the thresholds)
-    uint32_t tile_limit;      // pre-pass: tiles per CTA (0 = all)
-    float *maxima;            // [b_pad][gridDim.x] pre-pass output
+    uint32_t *gtau;           // [b_pad] best threshold key published so far (0xFFFFFFFF = none)
+    float *maxima;            // [n_lists * J][b_pad] sample maxima
+    uint32_t *arrive;         // [query tiles] CTAs that finished the sample phase (zeroed by prep)
+    uint32_t *hist;           // [b_pad][TC_HIST] appended candidates per score bucket
+    uint64_t *cand;           // [b_pad][n_lists][cap_l] unsorted approximate candidates
+    uint32_t *cnts;           // [b_pad][n_lists] entries appended (may exceed cap_l: overflow)
+    float *dump;              // diagnostics only: raw accumulators [nq][dump_rows] (null in production)
+    uint64_t dump_row0, dump_rows;
 };
 struct FinalizeArgs {
     const float *queries;     // [b][dim] f32 (the exact operands)
     const void *rows;         // fp16 corpus
     uint32_t dim, k, kk, order, id_base;
     uint64_t n_live;
-    const uint64_t *lists;    // [b][n_lists][kk]
-    uint32_t n_lists;
+    const uint64_t *cand;     // [b][n_lists][cap_l]
+    const uint32_t *cnts;     // [b][n_lists]
+    uint32_t n_lists, cap_l;
+    const uint32_t *gtau;     // [b] final shared threshold key: candidates beyond it cannot be in the top kk
     const float *err, *qnorm; // per-query |q - fp16(q)|, |q|
     const float *max_row_norm; // device scalar: upper bound on |row|_2 over the store
-    float c_acc;              // accumulation-error coefficient of the bound
+    float c_acc;              // accumulation-error coefficient of the bound (derived from dim)
+    uint32_t rc;              // candidates re-scored per round (rows staged in shared memory)
     uint32_t *ids_out; float *dist_out; uint32_t *counts_out;
     uint32_t *flags;          // [b] 1 = could not be certified
     uint32_t *n_flagged;      // device counter (reset per search)
     uint32_t *flag_list;      // [b] indices of the uncertified queries, in arrival order
     unsigned long long *flag_total;  // cumulative statistics
+    PushArgs push;            // certified queries are pushed to the peers right here
 };
-size_t tc_smem_bytes(uint32_t dim, uint32_t stages, uint32_t kk);
+size_t tc_smem_bytes(uint32_t dim, uint32_t stages);
+float tc_c_acc(uint32_t dim);
 cudaError_t launch_prep_queries(const float *d_q, uint32_t b, uint32_t b_pad, uint32_t dim, __half *d_qh, float *d_err,
-                                float *d_qnorm, uint32_t *d_gtau, uint32_t *d_flags, cudaStream_t st);
+                                float *d_qnorm, uint32_t *d_gtau, uint32_t *d_flags, uint32_t *d_hist, uint32_t *d_arrive,
+                                uint32_t n_qtiles, uint32_t *d_nflag, cudaStream_t st);
 cudaError_t launch_scan_tc(const CUtensorMap &tmap_rows, const CUtensorMap &tmap_q, const TcArgs &a, uint32_t grid,
                            size_t smem, cudaStream_t st);
 cudaError_t launch_scan_tc2(const CUtensorMap &tmap_rows, const CUtensorMap &tmap_q, const TcArgs &a, uint32_t grid,
                             size_t smem, cudaStream_t st);
-cudaError_t launch_tau_init(const float *d_maxima, uint32_t b_pad, uint32_t n_cta, uint32_t kk, uint32_t *d_gtau,
-                            cudaStream_t st);
 cudaError_t launch_finalize_tc(const FinalizeArgs &f, uint32_t b, cudaStream_t st);
+// diagnostics: exact -dot of every (query, row) pair in the reference's order -> out [b][n_rows_range]
+cudaError_t launch_exact_scores(const float *d_q, uint32_t b, const void *rows, uint32_t dim, uint64_t row0, uint64_t n,
+                                int order, float *d_out, cudaStream_t st);
 
 // ---- select.cu ----
 // lists [b][n_lists][k] u64 keys (sentinel padded) -> top-k per query.  d_scratch (may be null) holds
@@ -72,11 +97,11 @@ cudaError_t launch_finalize_tc(const FinalizeArgs &f, uint32_t b, cudaStream_t s
 uint32_t merge_groups(uint32_t n_lists, uint32_t k);
 cudaError_t launch_merge_keys(const uint64_t *d_lists, uint32_t b, uint32_t n_lists, uint32_t k, uint32_t id_base,
                               uint64_t *d_scratch, uint32_t *d_ids, float *d_dist, uint32_t *d_counts,
-                              cudaStream_t st);
+                              cudaStream_t st, const PushArgs *push = nullptr);
 // flagged form: CTA i handles slot i of d_lists iff i < *d_slot_count and writes query d_slot_to_query[i]
 cudaError_t launch_merge_keys_flagged(const uint64_t *d_lists, uint32_t b, uint32_t n_lists, uint32_t k, uint32_t id_base,
                                       const uint32_t *d_slot_count, const uint32_t *d_slot_to_query, uint32_t *d_ids,
-                                      float *d_dist, uint32_t *d_counts, cudaStream_t st);
+                                      float *d_dist, uint32_t *d_counts, cudaStream_t st, const PushArgs *push = nullptr);
 // lists as (ids, dist) pairs [b][n_per_query]; id 0xFFFFFFFF marks an empty slot
 cudaError_t launch_merge_pairs(const uint32_t *d_ids_in, const float *d_dist_in, uint32_t b, uint32_t n_lists,
                                uint32_t k, uint64_t list_stride, uint64_t query_stride, uint32_t *d_ids,

@@ -42,10 +42,16 @@ struct sg_store {
     __half *d_qh = nullptr; size_t qh_cap = 0;             // fp16 queries, 128-row padded
     float *d_qerr = nullptr; size_t qmeta_cap = 0;         // [b_pad] |q - fp16(q)|
     float *d_qnorm = nullptr;                              // [b_pad]
-    float *d_maxima = nullptr; size_t maxima_cap = 0;      // [b_pad][grid] pre-pass maxima
+    float *d_maxima = nullptr; size_t maxima_cap = 0;      // [n_lists * J][b_pad] sample maxima
     uint32_t *d_gtau = nullptr, *d_flags = nullptr, *d_nflag = nullptr, *d_flag_list = nullptr;
+    uint32_t *d_hist = nullptr;                            // [b_pad][32] per-query score histogram of the sweep in flight
+    uint32_t *d_arrive = nullptr; size_t arrive_cap = 0;   // sample-phase arrival counter per query tile
+    uint32_t *d_cnts = nullptr; size_t cnts_cap = 0;       // [b_pad][n_lists] candidates appended per region
+    int tc_mode = 0;                                       // 0 = automatic, 1 = never use the tensor-core path
+    cudaEvent_t ev_chain = nullptr;                        // end of the last asynchronous call
+    cudaStream_t chain_stream = nullptr; bool chain_pending = false;
     unsigned long long *d_flag_total = nullptr;            // cumulative count of uncertified queries
-    uint64_t *d_cand = nullptr; size_t cand_cap_q = 0;     // [b_pad][grid][kk] per-CTA candidate lists
+    uint64_t *d_cand = nullptr; size_t cand_cap_q = 0;     // [b_pad][n_lists][cap_l] candidate regions
     uint64_t tc_searches = 0, tc_flagged = 0;              // statistics (sg_store_tc_stats)
 
     // vector id -> MemoryId table (IdMapping of RetrievalEngine, retrieval.rs:64-140) + search_ids scratch
@@ -80,7 +86,15 @@ int grow_pinned(sg_store *s, size_t bytes);
 int ensure_rows(sg_store *s, uint64_t need_rows);
 // exact path A; all pointers are device pointers; asynchronous on st.  use_deleted = false scores every row.
 int search_exact_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint32_t *d_ids, float *d_dist,
-                        uint32_t *d_counts, cudaStream_t st, bool record, bool use_deleted = true);
+                        uint32_t *d_counts, cudaStream_t st, bool record, bool use_deleted = true,
+                        const PushArgs *push = nullptr);
+// exchange.cu: wait for every rank's pushed lists and merge them (one launch)
+int exchange_wait_merge(int device, const PushArgs &p, uint32_t *d_ids_out, float *d_dist_out, uint32_t *d_counts_out,
+                        cudaStream_t st);
+// Every call that launches work for a store goes through these two: an asynchronous call on stream A followed by a
+// call on stream B shares the store's scratch buffers, so B first waits for the event A recorded at its end.
+int chain_begin(sg_store *s, cudaStream_t st);
+int chain_end(sg_store *s, cudaStream_t st);
 // graph_api.cu: link rows [first, first+n) into the graph one by one (VamanaIndex::add_vector); no-op without a graph
 int graph_append_locked(sg_store *s, uint64_t first, uint64_t n);
 void graph_free(sg_store *s);

@@ -232,10 +232,10 @@ namespace sg {
 
 // exact path A.  all pointers are device pointers; runs asynchronously on st
 int search_exact_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint32_t *d_ids, float *d_dist,
-                        uint32_t *d_counts, cudaStream_t st, bool record, bool use_deleted)
+                        uint32_t *d_counts, cudaStream_t st, bool record, bool use_deleted, const PushArgs *push)
 {
     if (s->n == 0) {  // VamanaIndex::search on an empty index: Ok(vec![]) (vamana.rs:766-768)
-        SG_CUDA_TRY(launch_merge_keys(nullptr, b, 0, k, s->id_base, nullptr, d_ids, d_dist, d_counts, st));
+        SG_CUDA_TRY(launch_merge_keys(nullptr, b, 0, k, s->id_base, nullptr, d_ids, d_dist, d_counts, st, push));
         return SG_OK;
     }
     // one plan for the widest sweep; narrower sweeps reuse W/ring/grid (their smem is smaller)
@@ -289,7 +289,22 @@ int search_exact_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, u
         ++s->ev_count;
     }
     SG_CUDA_TRY(launch_merge_keys(s->d_lists, b, L, k, s->id_base, groups > 1 ? s->d_lists2 : nullptr, d_ids, d_dist,
-                                  d_counts, st));
+                                  d_counts, st, push));
+    return SG_OK;
+}
+
+// see sg_store_internal.h
+int chain_begin(sg_store *s, cudaStream_t st)
+{
+    if (s->chain_pending && s->chain_stream != st) SG_CUDA_TRY(cudaStreamWaitEvent(st, s->ev_chain, 0));
+    return SG_OK;
+}
+int chain_end(sg_store *s, cudaStream_t st)
+{
+    if (!s->ev_chain) SG_CUDA_TRY(cudaEventCreateWithFlags(&s->ev_chain, cudaEventDisableTiming));
+    SG_CUDA_TRY(cudaEventRecord(s->ev_chain, st));
+    s->chain_stream = st;
+    s->chain_pending = true;
     return SG_OK;
 }
 
@@ -299,106 +314,120 @@ namespace {
 
 
 // tensor-core path B: approximate sweep + exact re-score + certification; uncertified queries are
-// re-run on path A.  Returns SG_ERR_UNSUPPORTED (without side effects) if the shape does not fit.
-bool tc_eligible(const sg_store *s, uint32_t b, uint32_t k, uint32_t *kk_out, uint32_t *stages_out)
+// re-run on path A.
+struct TcPlan {
+    uint32_t kk, stages, n_lists, grid, J, cap_l, qtile;
+    bool pair;
+};
+
+// candidates re-scored per query = k + slack; fewer => fewer appends and a cheaper finalize, more slack =>
+// fewer exact re-runs on tie-heavy corpora.  The reference's own call shape is k = 4 * limit with
+// limit = 3 * max_results (retrieval.rs:912-918, memory/mod.rs:3585): k = 120 for a top-10 recall.
+uint32_t tc_kk(uint32_t k)
+{
+    if (k <= 10) return 16;
+    if (k <= 24) return 32;
+    return (k + 32 + 7) / 8 * 8;
+}
+
+bool tc_plan(const sg_store *s, uint32_t b, uint32_t k, TcPlan *p)
 {
     if (s->dtype != SG_DTYPE_F16 || s->dim % 64 != 0 || s->metric != SG_METRIC_NEG_DOT) return false;
-    if (env_u32("SG_TC_DISABLE", 0)) return false;
+    if (s->tc_mode == 1 || env_u32("SG_TC_DISABLE", 0)) return false;
     if (b < (uint32_t)env_u32("SG_TC_MIN_B", 5)) return false;
-    if (k > 24 || s->n < 4096) return false;
-    // candidates kept per query and list = k + slack; fewer candidates => a tighter seeded threshold and
-    // fewer list insertions, more slack => fewer exact re-runs on tie-heavy corpora
-    uint32_t kk = k <= 10 ? 16 : 32;
+    if (k > 128 || s->n < 4096) return false;
+    p->kk = tc_kk(k);
     const uint32_t kk_env = (uint32_t)env_u32("SG_TC_KK", 0);
-    if (kk_env >= k + 2 && kk_env <= 32) kk = kk_env;
+    if (kk_env >= k + 2 && kk_env <= TC_KK_MAX) p->kk = kk_env;
+    // CTA-pair form (256 queries per sweep) for b > 128; 1-CTA form (128 per sweep) otherwise
+    const int pair_env = env_u32("SG_TC_PAIR", 1);
+    p->pair = pair_env == 2 || (pair_env == 1 && b > 128);
+    p->qtile = p->pair ? 256 : 128;
+    const uint32_t rows_tile = p->pair ? 256 : 128;
+    const uint64_t n_tiles = (s->n + rows_tile - 1) / rows_tile;
+    const uint32_t units_max = p->pair ? (uint32_t)s->sm_count / 2 : (uint32_t)s->sm_count;   // clusters or CTAs
+    p->n_lists = (uint32_t)(n_tiles < units_max ? n_tiles : units_max);
+    p->grid = p->pair ? 2 * p->n_lists : p->n_lists;
+    // the sample: every list contributes the J best 32-row-chunk maxima of its first tile; kk distinct rows are needed
+    p->J = (p->kk + p->n_lists - 1) / p->n_lists;
+    if (p->J > rows_tile / 32) return false;
+    p->cap_l = p->kk <= 32 ? 64 : 256;
+    const uint32_t cap_env = (uint32_t)env_u32("SG_TC_CAP", 0);
+    if (cap_env >= 8 && cap_env <= 4096) p->cap_l = cap_env;
     const uint32_t st_max = (uint32_t)env_u32("SG_TC_STAGES", 8);
     for (uint32_t stages = st_max < 3 ? 3 : (st_max > 8 ? 8 : st_max); stages >= 3; --stages) {
-        if (tc_smem_bytes(s->dim, stages, kk) <= 227 * 1024) {
-            *kk_out = kk;
-            *stages_out = stages;
+        if (tc_smem_bytes(s->dim, stages) <= 227 * 1024) {
+            p->stages = stages;
             return true;
         }
     }
     return false;
 }
 
-int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint32_t kk, uint32_t stages,
-                     uint32_t *d_ids, float *d_dist, uint32_t *d_counts, cudaStream_t st)
+constexpr uint32_t TC_B_CHUNK = 1024;    // queries per pipeline pass (bounds the candidate scratch)
+
+int search_tc_chunk(sg_store *s, const TcPlan &pl, const float *d_q, uint32_t b, uint32_t k, uint32_t *d_ids,
+                    float *d_dist, uint32_t *d_counts, cudaStream_t st, const PushArgs *push)
 {
-    // CTA-pair form (256 queries per sweep) for b > 128; 1-CTA form (128 per sweep) otherwise
-    const int pair_env = env_u32("SG_TC_PAIR", 1);
-    const bool pair = pair_env == 2 || (pair_env == 1 && b > 128);
-    const uint32_t qtile = pair ? 256 : 128;          // queries per sweep
-    const uint32_t rows_tile = pair ? 256 : 128;      // corpus rows per (pair) tile
+    const uint32_t qtile = pl.qtile, n_lists = pl.n_lists, kk = pl.kk;
     const uint32_t b_pad = (b + qtile - 1) / qtile * qtile;
+    const uint32_t n_qtiles = b_pad / qtile;
     int rc;
     if ((rc = grow(s->d_qh, s->qh_cap, (size_t)b_pad * s->dim)) != SG_OK) return rc;
     if (b_pad > s->qmeta_cap) {
-        size_t c[5] = {s->qmeta_cap, s->qmeta_cap, s->qmeta_cap, s->qmeta_cap, s->qmeta_cap};
+        size_t c[6] = {s->qmeta_cap, s->qmeta_cap, s->qmeta_cap, s->qmeta_cap, s->qmeta_cap, s->qmeta_cap * TC_HIST};
         if ((rc = grow(s->d_flag_list, c[4], b_pad)) != SG_OK) return rc;
         if ((rc = grow(s->d_qerr, c[0], b_pad)) != SG_OK) return rc;
         if ((rc = grow(s->d_qnorm, c[1], b_pad)) != SG_OK) return rc;
         if ((rc = grow(s->d_gtau, c[2], b_pad)) != SG_OK) return rc;
         if ((rc = grow(s->d_flags, c[3], b_pad)) != SG_OK) return rc;
+        if ((rc = grow(s->d_hist, c[5], (size_t)c[0] * TC_HIST)) != SG_OK) return rc;
         s->qmeta_cap = c[0];
     }
-    const uint64_t n_tiles = (s->n + rows_tile - 1) / rows_tile;
-    const uint32_t units_max = pair ? (uint32_t)s->sm_count / 2 : (uint32_t)s->sm_count;   // clusters or CTAs
-    const uint32_t n_lists = (uint32_t)(n_tiles < units_max ? n_tiles : units_max);
-    const uint32_t grid = pair ? 2 * n_lists : n_lists;
-    if ((rc = grow(s->d_cand, s->cand_cap_q, (size_t)b_pad * n_lists * 32)) != SG_OK) return rc;
+    if ((rc = grow(s->d_arrive, s->arrive_cap, (size_t)n_qtiles)) != SG_OK) return rc;
+    if ((rc = grow(s->d_cand, s->cand_cap_q, (size_t)b_pad * n_lists * pl.cap_l)) != SG_OK) return rc;
+    if ((rc = grow(s->d_cnts, s->cnts_cap, (size_t)b_pad * n_lists)) != SG_OK) return rc;
+    if ((rc = grow(s->d_maxima, s->maxima_cap, (size_t)b_pad * n_lists * pl.J)) != SG_OK) return rc;
     CUtensorMap tmap_rows, tmap_q;
     if ((rc = encode_corpus_tmap(&tmap_rows, s->d_rows, true, s->dim, s->n, 128)) != SG_OK) return rc;
     if ((rc = encode_corpus_tmap(&tmap_q, s->d_qh, true, s->dim, b_pad, 128)) != SG_OK) return rc;
 
-    SG_CUDA_TRY(cudaMemsetAsync(s->d_nflag, 0, 4, st));
-    SG_CUDA_TRY(launch_prep_queries(d_q, b, b_pad, s->dim, s->d_qh, s->d_qerr, s->d_qnorm, s->d_gtau, s->d_flags, st));
-    const size_t smem = tc_smem_bytes(s->dim, stages, kk);
+    SG_CUDA_TRY(launch_prep_queries(d_q, b, b_pad, s->dim, s->d_qh, s->d_qerr, s->d_qnorm, s->d_gtau, s->d_flags, s->d_hist,
+                                    s->d_arrive, n_qtiles, s->d_nflag, st));
+    const size_t smem = tc_smem_bytes(s->dim, pl.stages);
     const bool prof = s->profiling && 2 * (size_t)(s->ev_count + 1) <= s->ev.size();
     if (prof) SG_CUDA_TRY(cudaEventRecord(s->ev[2 * s->ev_count], st));
-    // pre-pass (large corpora): every CTA (pair) scores its first few tiles and keeps only its best live
-    // score per query; the kk-th largest of those maxima seeds a valid GPU-wide threshold, so the sweep
-    // does far fewer list insertions than with CTA-local thresholds alone.
-    // tiles of the pre-pass per list: ~1/16 of a list's tiles at most (the pre-pass rows are scanned twice),
-    // 16 (pair) / 4 (1-CTA) on large corpora
-    const uint64_t tiles_per_list = n_tiles / n_lists;
-    uint32_t pre_tiles = pair ? 16 : 4;
-    if (tiles_per_list / 16 < pre_tiles) pre_tiles = (uint32_t)(tiles_per_list / 16);
-    if (pre_tiles == 0 && tiles_per_list >= 8) pre_tiles = 1;
-    const int pre_env = env_u32("SG_TC_PRE_TILES", -1);
-    if (pre_env >= 0) pre_tiles = (uint32_t)pre_env;
-    const bool prepass = pre_tiles > 0 && n_lists >= kk;
-    if (prepass && (rc = grow(s->d_maxima, s->maxima_cap, (size_t)b_pad * n_lists)) != SG_OK) return rc;
-    for (int pass = prepass ? 1 : 0; pass >= 0; --pass) {
-        for (uint32_t qt = 0; qt < b_pad / qtile; ++qt) {
-            TcArgs a;
-            a.n_rows = s->n;
-            a.dim = s->dim;
-            a.nq = b - qt * qtile < qtile ? b - qt * qtile : qtile;
-            a.q_tile = qt;
-            a.stages = stages;
-            a.kk = kk;
-            a.deleted = s->n_deleted ? s->d_deleted : nullptr;
-            a.gtau = s->d_gtau;
-            a.lists = s->d_cand;
-            a.mode = (uint32_t)pass;
-            a.tile_limit = pass ? pre_tiles : 0;
-            a.maxima = s->d_maxima;
-            cudaError_t e = pair ? launch_scan_tc2(tmap_rows, tmap_q, a, grid, smem, st)
-                                 : launch_scan_tc(tmap_rows, tmap_q, a, grid, smem, st);
-            if (e != cudaSuccess) {
-                set_error("tensor-core scan launch failed: %s", cudaGetErrorString(e));
-                return SG_ERR_CUDA;
-            }
-            if (!pass) ++s->last_scan_launches;
+    for (uint32_t qt = 0; qt < n_qtiles; ++qt) {
+        TcArgs a{};
+        a.n_rows = s->n;
+        a.dim = s->dim;
+        a.nq = b - qt * qtile < qtile ? b - qt * qtile : qtile;
+        a.q_tile = qt;
+        a.stages = pl.stages;
+        a.kk = kk;
+        a.b_pad = b_pad;
+        a.J = pl.J;
+        a.cap_l = pl.cap_l;
+        a.deleted = s->n_deleted ? s->d_deleted : nullptr;
+        a.gtau = s->d_gtau;
+        a.maxima = s->d_maxima;
+        a.arrive = s->d_arrive;
+        a.hist = s->d_hist;
+        a.cand = s->d_cand;
+        a.cnts = s->d_cnts;
+        cudaError_t e = pl.pair ? launch_scan_tc2(tmap_rows, tmap_q, a, pl.grid, smem, st)
+                                : launch_scan_tc(tmap_rows, tmap_q, a, pl.grid, smem, st);
+        if (e != cudaSuccess) {
+            set_error("tensor-core scan launch failed: %s", cudaGetErrorString(e));
+            return SG_ERR_CUDA;
         }
-        if (pass) SG_CUDA_TRY(launch_tau_init(s->d_maxima, b, n_lists, kk, s->d_gtau, st));
+        ++s->last_scan_launches;
     }
     if (prof) {
         SG_CUDA_TRY(cudaEventRecord(s->ev[2 * s->ev_count + 1], st));
         ++s->ev_count;
     }
-    FinalizeArgs f;
+    FinalizeArgs f{};
     f.queries = d_q;
     f.rows = s->d_rows;
     f.dim = s->dim;
@@ -407,12 +436,20 @@ int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint
     f.order = (uint32_t)s->order;
     f.id_base = s->id_base;
     f.n_live = s->n - s->n_deleted;
-    f.lists = s->d_cand;
+    f.cand = s->d_cand;
+    f.cnts = s->d_cnts;
     f.n_lists = n_lists;
+    f.cap_l = pl.cap_l;
+    f.gtau = s->d_gtau;
     f.err = s->d_qerr;
     f.qnorm = s->d_qnorm;
     f.max_row_norm = s->d_max_norm;
-    f.c_acc = 1.0e-4f;
+    f.c_acc = tc_c_acc(s->dim);
+    {   // rows staged per re-score round: keep q + rows within 44 KB of dynamic shared memory
+        const size_t row_b = (size_t)(s->dim / 2 + 1) * 4, q_b = (size_t)s->dim * 4;
+        size_t rcn = (44 * 1024 - q_b) / row_b;
+        f.rc = (uint32_t)(rcn > 32 ? 32 : (rcn < 1 ? 1 : rcn));
+    }
     f.ids_out = d_ids;
     f.dist_out = d_dist;
     f.counts_out = d_counts;
@@ -420,12 +457,14 @@ int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint
     f.n_flagged = s->d_nflag;
     f.flag_list = s->d_flag_list;
     f.flag_total = s->d_flag_total;
+    if (push) f.push = *push;
     SG_CUDA_TRY(launch_finalize_tc(f, b, st));
 
     // Certification outcome, handled ON THE DEVICE (no host round trip, the call stays asynchronous):
     // the exact sweep is launched in "flagged" mode -- it reads the number and indices of uncertified
     // queries from device memory, exits at once when there are none (the normal case, ~3 us), and
-    // otherwise re-runs them 4 per sweep; the flagged merge then overwrites exactly those result rows.
+    // otherwise re-runs them 4 per sweep; the flagged merge then overwrites exactly those result rows
+    // (and, multi-GPU, pushes them to the peers: finalize only pushed the certified ones).
     s->tc_searches += b;
     ScanPlan plan;
     if ((rc = plan_scan(s, k, 4, &plan)) != SG_OK) return rc;
@@ -453,13 +492,13 @@ int search_tc_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint
         return SG_ERR_CUDA;
     }
     SG_CUDA_TRY(launch_merge_keys_flagged(s->d_lists, b, LA, k, s->id_base, s->d_nflag, s->d_flag_list, d_ids, d_dist,
-                                          d_counts, st));
+                                          d_counts, st, push));
     return SG_OK;
 }
 
-// all pointers are device pointers
+// all pointers are device pointers.  push (multi-GPU) = hand every query's final local result to the peers
 int search_device_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint32_t *d_ids, float *d_dist,
-                         uint32_t *d_counts, cudaStream_t st)
+                         uint32_t *d_counts, cudaStream_t st, const PushArgs *push = nullptr)
 {
     if (b == 0) return SG_OK;
     if (k == 0 || k > 1024) {
@@ -467,9 +506,20 @@ int search_device_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, 
         return k == 0 ? SG_ERR_INVALID : SG_ERR_UNSUPPORTED;
     }
     s->last_scan_launches = 0;
-    uint32_t kk = 0, stages = 0;
-    if (tc_eligible(s, b, k, &kk, &stages)) return search_tc_locked(s, d_q, b, k, kk, stages, d_ids, d_dist, d_counts, st);
-    return search_exact_locked(s, d_q, b, k, d_ids, d_dist, d_counts, st, true);
+    TcPlan pl;
+    if (!tc_plan(s, b, k, &pl)) return search_exact_locked(s, d_q, b, k, d_ids, d_dist, d_counts, st, true, true, push);
+    for (uint32_t off = 0; off < b; off += TC_B_CHUNK) {
+        const uint32_t bb = b - off < TC_B_CHUNK ? b - off : TC_B_CHUNK;
+        PushArgs pc{};
+        if (push) {
+            pc = *push;
+            pc.q0 = push->q0 + off;
+        }
+        int rc = search_tc_chunk(s, pl, d_q + (size_t)off * s->dim, bb, k, d_ids + (size_t)off * k, d_dist + (size_t)off * k,
+                                 d_counts + off, st, push ? &pc : nullptr);
+        if (rc != SG_OK) return rc;
+    }
+    return SG_OK;
 }
 
 }  // namespace
@@ -570,6 +620,10 @@ void sg_store_destroy(sg_store *s)
     cudaFree(s->d_flag_list);
     cudaFree(s->d_flag_total);
     cudaFree(s->d_cand);
+    cudaFree(s->d_hist);
+    cudaFree(s->d_arrive);
+    cudaFree(s->d_cnts);
+    if (s->ev_chain) cudaEventDestroy(s->ev_chain);
     graph_free(s);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
@@ -582,6 +636,7 @@ int sg_store_reserve(sg_store *s, uint64_t n_rows)
     if (!s) return SG_ERR_INVALID;
     std::lock_guard<std::mutex> g(s->mu);
     SG_CUDA_TRY(cudaSetDevice(s->device));
+    { int rc_ = chain_begin(s, s->stream); if (rc_ != SG_OK) return rc_; }
     return ensure_rows(s, n_rows);
 }
 
@@ -590,6 +645,7 @@ int sg_store_append(sg_store *s, const float *rows, uint64_t n, uint32_t *first_
     if (!s || (!rows && n)) return SG_ERR_INVALID;
     std::lock_guard<std::mutex> g(s->mu);
     SG_CUDA_TRY(cudaSetDevice(s->device));
+    { int rc_ = chain_begin(s, s->stream); if (rc_ != SG_OK) return rc_; }
     if (first_id_out) *first_id_out = (uint32_t)s->n;
     if (n == 0) return SG_OK;
     int rc = ensure_rows(s, s->n + n);
@@ -632,6 +688,7 @@ int sg_store_append_device(sg_store *s, const float *d_rows, uint64_t n, uint32_
     int rc = ensure_rows(s, s->n + n);
     if (rc != SG_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    if ((rc = chain_begin(s, st)) != SG_OK) return rc;
     const size_t elems = (size_t)n * s->dim;
     uint8_t *dst = static_cast<uint8_t *>(s->d_rows) + s->n * (size_t)s->dim * s->esize;
     if (s->dtype == SG_DTYPE_F16) {
@@ -651,6 +708,7 @@ int sg_store_append_synthetic(sg_store *s, uint64_t seed, uint64_t first_row, ui
     if (!s) return SG_ERR_INVALID;
     std::lock_guard<std::mutex> g(s->mu);
     SG_CUDA_TRY(cudaSetDevice(s->device));
+    { int rc_ = chain_begin(s, s->stream); if (rc_ != SG_OK) return rc_; }
     int rc = ensure_rows(s, s->n + n);
     if (rc != SG_OK) return rc;
     uint8_t *dst = static_cast<uint8_t *>(s->d_rows) + s->n * (size_t)s->dim * s->esize;
@@ -671,6 +729,7 @@ int sg_store_mark_deleted(sg_store *s, uint32_t id, int *ok_out)
         return SG_OK;
     }
     SG_CUDA_TRY(cudaSetDevice(s->device));
+    { int rc_ = chain_begin(s, s->stream); if (rc_ != SG_OK) return rc_; }
     uint32_t &w = s->h_deleted[id >> 5];
     const uint32_t bit = 1u << (id & 31);
     if (!(w & bit)) {
@@ -697,6 +756,7 @@ int sg_store_clear_deleted(sg_store *s)
     std::lock_guard<std::mutex> g(s->mu);
     if (!s->d_deleted) return SG_OK;
     SG_CUDA_TRY(cudaSetDevice(s->device));
+    { int rc_ = chain_begin(s, s->stream); if (rc_ != SG_OK) return rc_; }
     std::fill(s->h_deleted.begin(), s->h_deleted.end(), 0u);
     s->n_deleted = 0;
     SG_CUDA_TRY(cudaMemsetAsync(s->d_deleted, 0, s->h_deleted.size() * 4, s->stream));
@@ -745,6 +805,7 @@ int sg_store_get_vectors(sg_store *s, uint64_t first, uint64_t n, float *out)
     }
     if (n == 0) return SG_OK;
     SG_CUDA_TRY(cudaSetDevice(s->device));
+    { int rc_ = chain_begin(s, s->stream); if (rc_ != SG_OK) return rc_; }
     const size_t chunk_rows = (size_t)(16u << 20) / ((size_t)s->dim * 4) ? (size_t)(16u << 20) / ((size_t)s->dim * 4) : 1;
     int rc = grow_pinned(s, chunk_rows * s->dim * 4);
     if (rc != SG_OK) return rc;
@@ -855,7 +916,143 @@ int sg_store_search_device(sg_store *s, const float *d_q, uint32_t b, uint32_t k
     std::lock_guard<std::mutex> g(s->mu);
     SG_CUDA_TRY(cudaSetDevice(s->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);  // NULL = the CUDA (legacy) default stream
-    return search_device_locked(s, d_q, b, k, d_ids, d_dist, d_counts, st);
+    int rc = chain_begin(s, st);
+    if (rc != SG_OK) return rc;
+    rc = search_device_locked(s, d_q, b, k, d_ids, d_dist, d_counts, st);
+    const int rc2 = chain_end(s, st);
+    return rc != SG_OK ? rc : rc2;
+}
+
+int sg_store_search_sharded_device(sg_store *s, const float *d_q, uint32_t b, uint32_t k, const uint64_t *peer_buffers,
+                                   uint32_t rank, uint32_t world, uint32_t epoch, uint32_t *d_ids_out, float *d_dist_out,
+                                   uint32_t *d_counts_out, void *cuda_stream)
+{
+    if (!s || !peer_buffers || world == 0 || world > 8 || rank >= world || epoch == 0) {
+        set_error("sg_store_search_sharded_device: bad arguments (world 1..8, rank < world, epoch >= 1)");
+        return SG_ERR_INVALID;
+    }
+    if (b && (!d_q || !d_ids_out || !d_dist_out || !d_counts_out)) return SG_ERR_INVALID;
+    if (b == 0) return SG_OK;
+    if (k == 0 || k > 1024) {
+        set_error("k=%u outside the supported range 1..1024", k);
+        return k == 0 ? SG_ERR_INVALID : SG_ERR_UNSUPPORTED;
+    }
+    std::lock_guard<std::mutex> g(s->mu);
+    SG_CUDA_TRY(cudaSetDevice(s->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    int rc = chain_begin(s, st);
+    if (rc != SG_OK) return rc;
+    // this shard's own (ids, dist)[b,k]: the store's result scratch
+    if ((size_t)b * k > s->res_cap) {
+        size_t c1 = s->res_cap, c2 = s->res_cap;
+        if ((rc = grow(s->d_ids, c1, (size_t)b * k)) != SG_OK) return rc;
+        if ((rc = grow(s->d_dist, c2, (size_t)b * k)) != SG_OK) return rc;
+        s->res_cap = c1 < c2 ? c1 : c2;
+    }
+    if ((rc = grow(s->d_counts, s->cnt_cap, (size_t)b)) != SG_OK) return rc;
+    PushArgs p{};
+    for (uint32_t r = 0; r < world; ++r) p.peer[r] = reinterpret_cast<uint32_t *>(peer_buffers[r]);
+    p.rank = rank; p.world = world; p.epoch = epoch; p.b = b; p.k = k; p.q0 = 0;
+    rc = search_device_locked(s, d_q, b, k, s->d_ids, s->d_dist, s->d_counts, st, &p);
+    if (rc == SG_OK) rc = exchange_wait_merge(s->device, p, d_ids_out, d_dist_out, d_counts_out, st);
+    const int rc2 = chain_end(s, st);
+    return rc != SG_OK ? rc : rc2;
+}
+
+int sg_store_set_tc_mode(sg_store *s, int mode)
+{
+    if (!s || mode < 0 || mode > 1) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    s->tc_mode = mode;
+    return SG_OK;
+}
+
+// ---- diagnostics (tests only): raw tensor-core scores and exact scores of a row range -----------------
+int sg_debug_tc_scores(sg_store *s, const float *queries, uint32_t b, uint64_t first_row, uint64_t n_rows, float *out)
+{
+    if (!s || !queries || !out || b == 0 || b > 256 || n_rows == 0) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    SG_CUDA_TRY(cudaSetDevice(s->device));
+    if (s->dtype != SG_DTYPE_F16 || s->dim % 64 != 0 || first_row + n_rows > s->n) {
+        set_error("sg_debug_tc_scores: needs an f16 store, dim %% 64 == 0 and a row range inside the store");
+        return SG_ERR_UNSUPPORTED;
+    }
+    int rc = chain_begin(s, s->stream);
+    if (rc != SG_OK) return rc;
+    const bool pair = b > 128;
+    const uint32_t qtile = pair ? 256 : 128, b_pad = qtile;
+    float *d_q = nullptr, *d_out = nullptr;
+    __half *d_qh = nullptr;
+    float *d_e = nullptr;
+    uint32_t *d_u = nullptr;
+    cudaError_t e = cudaMalloc(&d_q, (size_t)b * s->dim * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)b * n_rows * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_qh, (size_t)b_pad * s->dim * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&d_e, (size_t)b_pad * 2 * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_u, ((size_t)b_pad * (2 + TC_HIST) + 8) * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_q, queries, (size_t)b * s->dim * 4, cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess)
+        e = launch_prep_queries(d_q, b, b_pad, s->dim, d_qh, d_e, d_e + b_pad, d_u, d_u + b_pad, d_u + 2 * b_pad,
+                                d_u + (size_t)b_pad * (2 + TC_HIST), 1, d_u + (size_t)b_pad * (2 + TC_HIST) + 4, s->stream);
+    rc = SG_OK;
+    if (e == cudaSuccess) {
+        const uint32_t rows_tile = pair ? 256 : 128;
+        const uint64_t n_tiles = (s->n + rows_tile - 1) / rows_tile;
+        const uint32_t units = pair ? (uint32_t)s->sm_count / 2 : (uint32_t)s->sm_count;
+        const uint32_t n_lists = (uint32_t)(n_tiles < units ? n_tiles : units);
+        uint32_t stages = 8;
+        while (stages > 3 && tc_smem_bytes(s->dim, stages) > 227 * 1024) --stages;
+        CUtensorMap tmap_rows, tmap_q;
+        rc = encode_corpus_tmap(&tmap_rows, s->d_rows, true, s->dim, s->n, 128);
+        if (rc == SG_OK) rc = encode_corpus_tmap(&tmap_q, d_qh, true, s->dim, b_pad, 128);
+        if (rc == SG_OK) {
+            TcArgs a{};
+            a.n_rows = s->n;
+            a.dim = s->dim;
+            a.nq = b;
+            a.stages = stages;
+            a.b_pad = b_pad;
+            a.dump = d_out;
+            a.dump_row0 = first_row;
+            a.dump_rows = n_rows;
+            e = pair ? launch_scan_tc2(tmap_rows, tmap_q, a, 2 * n_lists, tc_smem_bytes(s->dim, stages), s->stream)
+                     : launch_scan_tc(tmap_rows, tmap_q, a, n_lists, tc_smem_bytes(s->dim, stages), s->stream);
+        }
+    }
+    if (rc == SG_OK && e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)b * n_rows * 4, cudaMemcpyDeviceToHost, s->stream);
+    if (rc == SG_OK && e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_q); cudaFree(d_out); cudaFree(d_qh); cudaFree(d_e); cudaFree(d_u);
+    if (rc == SG_OK && e != cudaSuccess) {
+        set_error("sg_debug_tc_scores: %s", cudaGetErrorString(e));
+        rc = SG_ERR_CUDA;
+    }
+    return rc;
+}
+
+int sg_debug_exact_scores(sg_store *s, const float *queries, uint32_t b, uint64_t first_row, uint64_t n_rows, float *out)
+{
+    if (!s || !queries || !out || b == 0 || n_rows == 0) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    SG_CUDA_TRY(cudaSetDevice(s->device));
+    if (s->dtype != SG_DTYPE_F16 || first_row + n_rows > s->n) {
+        set_error("sg_debug_exact_scores: needs an f16 store and a row range inside the store");
+        return SG_ERR_UNSUPPORTED;
+    }
+    int rc = chain_begin(s, s->stream);
+    if (rc != SG_OK) return rc;
+    float *d_q = nullptr, *d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_q, (size_t)b * s->dim * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)b * n_rows * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_q, queries, (size_t)b * s->dim * 4, cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess) e = launch_exact_scores(d_q, b, s->d_rows, s->dim, first_row, n_rows, s->order, d_out, s->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)b * n_rows * 4, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_q); cudaFree(d_out);
+    if (e != cudaSuccess) {
+        set_error("sg_debug_exact_scores: %s", cudaGetErrorString(e));
+        return SG_ERR_CUDA;
+    }
+    return SG_OK;
 }
 
 int sg_store_search(sg_store *s, const float *queries, uint32_t b, uint32_t k, uint32_t *ids_out, float *dist_out,
@@ -883,6 +1080,7 @@ int sg_store_search(sg_store *s, const float *queries, uint32_t b, uint32_t k, u
 
     uint8_t *hp = static_cast<uint8_t *>(s->h_pinned);
     memcpy(hp, queries, qbytes);
+    if ((rc = chain_begin(s, s->stream)) != SG_OK) return rc;
     SG_CUDA_TRY(cudaMemcpyAsync(s->d_queries, hp, qbytes, cudaMemcpyHostToDevice, s->stream));
     rc = search_device_locked(s, s->d_queries, b, k, s->d_ids, s->d_dist, s->d_counts, s->stream);
     if (rc != SG_OK) return rc;
@@ -981,6 +1179,7 @@ int sg_store_search_memory_ids(sg_store *s, const float *queries, uint32_t b, ui
     if ((rc = grow(s->d_memcnt, s->postc_cap, (size_t)b)) != SG_OK) return rc;
     uint8_t *hp = static_cast<uint8_t *>(s->h_pinned);
     memcpy(hp, queries, qbytes);
+    if ((rc = chain_begin(s, s->stream)) != SG_OK) return rc;
     SG_CUDA_TRY(cudaMemcpyAsync(s->d_queries, hp, qbytes, cudaMemcpyHostToDevice, s->stream));
     rc = search_device_locked(s, s->d_queries, b, k, s->d_ids, s->d_dist, s->d_counts, s->stream);
     if (rc != SG_OK) return rc;

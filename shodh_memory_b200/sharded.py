@@ -2,9 +2,12 @@
 
 One process per GPU (torch.distributed).  GPU g holds the contiguous row block
 [g*N/W, (g+1)*N/W) and reports global ids (id_base).  A search is: local exact sweep ->
-ONE all-gather of the per-shard (id, dist)[b,k] lists (b*k*8 bytes per rank, pure latency on
-NVLink/NVSwitch) -> k-way merge on every rank with the same (dist, id) rule, straight out of
-the all-gather receive buffer (strided merge, no repack).
+ONE exchange of the per-shard (id, dist)[b,k] lists (b*k*8 bytes per rank, pure latency on
+NVLink/NVSwitch) -> k-way merge on every rank with the same (dist, id) rule.  Product form
+("p2p"): sg_store_search_sharded_device -- the kernels that produce a query's final local
+result push it into every peer's symmetric buffer themselves, then one wait + merge kernel.
+Baseline form ("nccl"): one all_gather_into_tensor + a strided merge straight out of the
+receive buffer.
 
 torch is plumbing here (device buffers, streams, the process group); the sweep and the
 merge are this package's CUDA kernels.  The packing / layout logic is backend-agnostic so the
@@ -74,6 +77,7 @@ class ShardedGpuStore:
         self.local.set_id_base(self.lo)
         self._bufs = {}
         self.peer = None
+        self.last_ann_flags = None
         self.exchange_mode = "nccl"
         if world > 1 and exchange in ("auto", "p2p") and world <= 8:
             try:
@@ -106,6 +110,7 @@ class ShardedGpuStore:
             self._bufs[key] = dict(
                 pack=torch.empty((2, b, k), dtype=torch.int32, device=dev),
                 cnt=torch.empty(b, dtype=torch.int32, device=dev),
+                ann_flags=torch.zeros(b, dtype=torch.int32, device=dev),
                 out_ids=torch.empty((b, k), dtype=torch.int32, device=dev),
                 out_dist=torch.empty((b, k), dtype=torch.float32, device=dev),
                 out_cnt=torch.empty(b, dtype=torch.int32, device=dev))
@@ -124,9 +129,20 @@ class ShardedGpuStore:
         bufs = self._buffers(b, k)
         stream = torch.cuda.current_stream().cuda_stream
         pack = bufs["pack"]
+        if not ann and self.world > 1 and self.peer is not None:
+            # product path: search + push (inside the result kernels) + wait/merge, one C-ABI call
+            x = self.peer.get(b, k)
+            x["epoch"] += 1
+            self.local.search_sharded_device(d_queries.data_ptr(), b, k, x["ptrs"], self.rank, self.world, x["epoch"],
+                                             bufs["out_ids"].data_ptr(), bufs["out_dist"].data_ptr(),
+                                             bufs["out_cnt"].data_ptr(), stream)
+            return bufs["out_ids"], bufs["out_dist"], bufs["out_cnt"]
         if ann:
+            # flags: bit 0 = a shard's visited table filled up (its list may be incomplete); kept per call in
+            # self.last_ann_flags so the caller can re-run those queries through the host form, which retries
             self.local.search_ann_device(d_queries.data_ptr(), b, k, pack[0].data_ptr(), pack[1].data_ptr(),
-                                         bufs["cnt"].data_ptr(), 0, stream)
+                                         bufs["cnt"].data_ptr(), bufs["ann_flags"].data_ptr(), stream)
+            self.last_ann_flags = bufs["ann_flags"]
         else:
             self.local.search_device(d_queries.data_ptr(), b, k, pack[0].data_ptr(), pack[1].data_ptr(),
                                      bufs["cnt"].data_ptr(), stream)
@@ -165,6 +181,16 @@ class ShardedGpuStore:
         hb["h_cnt"].copy_(cnt, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return hb["h_ids"], hb["h_dist"], hb["h_cnt"]
+
+    def ann_incomplete(self) -> torch.Tensor | None:
+        """After search_device(..., ann=True): bool [b], True where ANY shard flagged its result incomplete
+        (visited table full) -- all ranks get the same answer (one all-reduce of b ints)."""
+        if self.last_ann_flags is None:
+            return None
+        f = (self.last_ann_flags & 1).clone()
+        if self.world > 1:
+            dist.all_reduce(f, op=dist.ReduceOp.MAX, group=self.group)
+        return f > 0
 
     def close(self) -> None:
         self.local.close()

@@ -228,6 +228,27 @@ class GpuVectorStore:
         """Raw device pointers (ints), asynchronous on `stream` (a cudaStream_t value)."""
         capi.check(capi.lib().sg_store_search_device(self._h, d_queries, b, k, d_ids, d_dist, d_counts, stream))
 
+    def search_sharded_device(self, d_queries: int, b: int, k: int, peer_ptrs, rank: int, world: int, epoch: int,
+                              d_ids: int, d_dist: int, d_counts: int, stream: int = 0) -> None:
+        """One rank's whole multi-GPU recall step: local search with the push folded into the result kernels,
+        then the wait + merge kernel (sg_store_search_sharded_device).  Outputs hold the GLOBAL top-k."""
+        capi.check(capi.lib().sg_store_search_sharded_device(self._h, d_queries, b, k, peer_ptrs, rank, world, epoch,
+                                                             d_ids, d_dist, d_counts, stream))
+
+    def set_tc_mode(self, mode: str) -> None:
+        """"auto": pick the sweep by shape; "exact": always path A (the comparator of the parity checks)."""
+        capi.check(capi.lib().sg_store_set_tc_mode(self._h, {"auto": 0, "exact": 1}[mode]))
+
+    def debug_scores(self, queries, first_row: int, n_rows: int):
+        """diagnostics -> (tensor-core scores [b,n_rows], exact reference-order dots [b,n_rows])"""
+        q = np.ascontiguousarray(queries, np.float32)
+        b = q.shape[0]
+        tc = np.empty((b, n_rows), np.float32)
+        ex = np.empty((b, n_rows), np.float32)
+        capi.check(capi.lib().sg_debug_tc_scores(self._h, _ptr(q, C.c_float), b, first_row, n_rows, _ptr(tc, C.c_float)))
+        capi.check(capi.lib().sg_debug_exact_scores(self._h, _ptr(q, C.c_float), b, first_row, n_rows, _ptr(ex, C.c_float)))
+        return tc, ex
+
     # -- profiling hooks for bench.py -----------------------------------------------------
     def set_profiling(self, on: bool) -> None:
         capi.check(capi.lib().sg_store_set_profiling(self._h, int(on)))

@@ -11,7 +11,6 @@ import os
 import numpy as np
 import pytest
 
-from helpers import not_yet_run_on_gpu
 
 pytestmark = pytest.mark.gpu
 COS_TOL, ABS_TOL = 0.999, 6e-3
@@ -131,7 +130,6 @@ def test_encoder_feeds_the_store_on_device(model_and_encoder, sg, oracle):
     st.close()
 
 
-@not_yet_run_on_gpu
 def test_batched_document_ingest_stays_on_the_device(model_and_encoder, sg):
     """SURVEY 8f-4 batched ingest (retrieval.rs:668-676 -> minilm.rs:996): encode_batch output goes straight into
     the store (sg_encoder_encode_device -> sg_store_append_device), no host round trip for the embeddings."""

@@ -6,7 +6,6 @@ import os
 import numpy as np
 import pytest
 
-from helpers import not_yet_run_on_gpu
 
 G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "index_golden_v1.npz"))
 F = np.float32
@@ -63,7 +62,6 @@ def test_oracle_reproduces_pq_and_spann_golden(oracle):
 # ------------------------------------------------------------------ GPU: the device against the committed bytes
 @pytest.mark.gpu
 @pytest.mark.parametrize("order", ["scalar", "avx2"])
-@not_yet_run_on_gpu
 def test_gpu_reproduces_metric_golden(sg, order):
     rows, qs = G["m_rows"], G["m_queries"]
     for metric in ("euclidean", "cosine"):
@@ -80,7 +78,6 @@ def test_gpu_reproduces_metric_golden(sg, order):
 
 
 @pytest.mark.gpu
-@not_yet_run_on_gpu
 def test_gpu_reproduces_graph_golden(sg):
     st = sg.GpuVectorStore(64, "f32")
     st.add_vectors(G["g_rows"])
@@ -94,7 +91,6 @@ def test_gpu_reproduces_graph_golden(sg):
 
 
 @pytest.mark.gpu
-@not_yet_run_on_gpu
 def test_gpu_reproduces_pq_and_spann_golden(sg):
     pq = sg.GpuProductQuantizer.train(G["p_train"], G["p_orders"], num_centroids=32, kmeans_iterations=3)
     assert np.array_equal(bits(pq.centroids), G["p_centroid_bits"])

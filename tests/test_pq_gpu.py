@@ -4,7 +4,6 @@ bit (codes, table entries, distances, ids).  Everything goes through the C ABI (
 import numpy as np
 import pytest
 
-from helpers import not_yet_run_on_gpu
 
 pytestmark = pytest.mark.gpu
 F = np.float32
@@ -107,7 +106,6 @@ def test_small_shapes_and_ties(sg, oracle):
     pq.close()
 
 
-@not_yet_run_on_gpu
 def test_member_list_training_path_equals_the_oracle(sg, oracle, monkeypatch):
     """large training sets (n >= SG_PQ_MEMBERS_MIN_N) take pq_update_members_kernel; forced here on a small set"""
     monkeypatch.setenv("SG_PQ_MEMBERS_MIN_N", "1")

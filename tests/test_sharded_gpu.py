@@ -6,7 +6,6 @@ import sys
 
 import pytest
 
-from helpers import not_yet_run_on_gpu
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -100,7 +99,6 @@ dist.destroy_process_group()
 '''
 
 
-@not_yet_run_on_gpu
 def test_two_gpu_sharded_graph_search(tmp_path):
     """one graph per shard, per-shard beam search, then the same exchange + merge as the exact path"""
     import torch

@@ -6,7 +6,6 @@ import struct
 import numpy as np
 import pytest
 
-from helpers import not_yet_run_on_gpu
 
 F = np.float32
 
@@ -117,7 +116,6 @@ def test_corruption_and_unsupported_files_are_errors(sg, tmp_path):
 
 
 @pytest.mark.gpu
-@not_yet_run_on_gpu
 def test_load_search_save_round_trip(sg, oracle, tmp_path):
     """spann.rs:1153-1183 test_spann_save_and_load: save, verify, load, search the loaded index"""
     v = np.random.default_rng(0).random((500, 384), dtype=F)
