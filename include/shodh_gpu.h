@@ -174,7 +174,7 @@ SG_API int sg_store_search_device(sg_store *s, const float *d_queries_f32, uint3
                                   uint32_t *d_ids_out, float *d_dist_out, uint32_t *d_counts_out,
                                   void *cuda_stream);
 
-/* Batched searches (b >= 5, k <= 128 -- which covers the reference's own request, k = 4 * limit = 120 for a
+/* Batched searches (b >= 3, k <= 128 -- which covers the reference's own request, k = 4 * limit = 120 for a
  * top-10 recall: retrieval.rs:912-918 x memory/mod.rs:3585 --, F16 store, NormalizedDotProduct) run the
  * tensor-core sweep: approximate scores select k+slack candidates, which are re-scored exactly in the
  * reference's summation order and certified with a rigorous error bound (coefficient derived from dim);
@@ -429,6 +429,13 @@ SG_API int sg_encoder_encode(sg_encoder *e, const int64_t *input_ids, const int6
  * sg_store_search_device without leaving the GPU (BASELINE config 5). */
 SG_API int sg_encoder_encode_device(sg_encoder *e, const int64_t *d_input_ids, const int64_t *d_attention_mask,
                                     uint32_t b, uint32_t L, float *d_emb_out, void *cuda_stream);
+
+/* The pooling tail of generate_embedding_onnx on its own (minilm.rs:959-978 masked mean-pool: pooled[d] += h[s][d]
+ * for s ascending over mask == 1, / mask_sum; :846-878 finalize_pooled: NaN/Inf -> 0, norm = sqrt(sum x^2) folded
+ * left to right, divide when norm > f32::EPSILON): hidden [b,L,H] f32 + attention_mask [b,L] i64 -> out [b,H],
+ * bit-identical to the CPU path.  Host buffers; what sg_encoder_encode runs after its last layer. */
+SG_API int sg_pool_finalize(int device, const float *hidden_f32, const int64_t *attention_mask, uint32_t b, uint32_t L,
+                            uint32_t H, float *out);
 
 #ifdef __cplusplus
 }

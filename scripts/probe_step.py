@@ -13,7 +13,10 @@ for n in [int(x) for x in os.environ.get("NS", "10000000,1250000").split(",")]:
     st = sg.GpuVectorStore(384, "f16")
     st.append_synthetic(23821, 0, n)
     st.set_profiling(True)
-    for b, k in [(256, 10), (256, 120), (128, 10), (64, 120), (8, 10), (4, 10), (1, 100)]:
+    cases = [(256, 10), (256, 120), (128, 10), (64, 120), (8, 10), (4, 10), (1, 100)]
+    if os.environ.get("CASES"):
+        cases = [tuple(int(v) for v in c.split("x")) for c in os.environ["CASES"].split(",")]
+    for b, k in cases:
         ids = torch.empty((b, k), dtype=torch.int32, device="cuda"); dist = torch.empty((b, k), device="cuda")
         cnt = torch.empty(b, dtype=torch.int32, device="cuda")
         for _ in range(3):

@@ -5,7 +5,7 @@ host-side mirror of the reference's VamanaIndex / relevance surface for tests an
 Importing the package loads lib/libshodh_gpu.so and fails loudly if it is missing."""
 from . import capi
 from .capi import SgError
-from .encoder import GpuMiniLM, export_bert_weights, random_minilm_state_dict
+from .encoder import GpuMiniLM, export_bert_weights, pool_finalize, random_minilm_state_dict
 from .pq import GpuProductQuantizer
 from .relevance import fuse_topk, RRFusion
 from .spann import GpuSpannIndex, spann_file_inspect, spann_file_read, spann_file_write

@@ -157,6 +157,7 @@ def lib() -> C.CDLL:
     L.sg_encoder_dim.argtypes = [vp, u32p]
     L.sg_encoder_encode.argtypes = [vp, i64p, i64p, C.c_uint32, C.c_uint32, f32p]
     L.sg_encoder_encode_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp]
+    L.sg_pool_finalize.argtypes = [C.c_int, f32p, i64p, C.c_uint32, C.c_uint32, C.c_uint32, f32p]
     L.sg_fuse_default_weights.argtypes = [C.POINTER(FuseWeights)]
     L.sg_fuse_default_weights.restype = None
     L.sg_fuse_default_config.argtypes = [C.POINTER(FuseConfig)]

@@ -1391,6 +1391,41 @@ void sg_encoder_destroy(sg_encoder *e)
     delete e;
 }
 
+// The tail of generate_embedding_onnx on its own (minilm.rs:959-978 masked mean-pool, :846-878 finalize_pooled):
+// f32 hidden states in, pooled + L2-normalised embeddings out, in the reference's summation order (pool_norm_kernel).
+int sg_pool_finalize(int device, const float *hidden, const int64_t *mask, uint32_t b, uint32_t L, uint32_t H, float *out)
+{
+    if (b == 0) return SG_OK;
+    if (!hidden || !mask || !out || L == 0 || H == 0 || H > 8192) return SG_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device available; libshodh_gpu has no CPU fallback");
+        return SG_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) return SG_ERR_INVALID;
+    SG_CUDA_TRY(cudaSetDevice(device));
+    float *d_h = nullptr, *d_o = nullptr;
+    int64_t *d_m = nullptr;
+    const size_t hb = (size_t)b * L * H * 4, mb = (size_t)b * L * 8, ob = (size_t)b * H * 4;
+    cudaError_t e = cudaMalloc(&d_h, hb);
+    if (e == cudaSuccess) e = cudaMalloc(&d_m, mb);
+    if (e == cudaSuccess) e = cudaMalloc(&d_o, ob);
+    if (e == cudaSuccess) e = cudaMemcpy(d_h, hidden, hb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_m, mask, mb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        pool_norm_kernel<<<b, H < 384 ? (H + 31) / 32 * 32 : 384, H * 4>>>(d_h, d_m, L, H, d_o);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_o, ob, cudaMemcpyDeviceToHost);
+    cudaFree(d_h); cudaFree(d_m); cudaFree(d_o);
+    if (e != cudaSuccess) {
+        set_error("sg_pool_finalize: %s", cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? SG_ERR_OOM : SG_ERR_CUDA;
+    }
+    return SG_OK;
+}
+
 int sg_encoder_dim(const sg_encoder *e, uint32_t *dim_out)
 {
     if (!e || !dim_out) return SG_ERR_INVALID;

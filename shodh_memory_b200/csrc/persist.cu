@@ -15,7 +15,7 @@
 #include <cstring>
 #include <vector>
 
-#include "sg_internal.h"
+#include "sg_store_internal.h"
 
 namespace {
 
@@ -57,6 +57,17 @@ int vama_parse(FILE *f, VamaInfo &vi, std::vector<uint32_t> *deleted, int verify
     if (off > vi.file_size) {
         sg::set_error("VAMA file truncated in the deleted-ids section");
         return SG_ERR_INVALID;
+    }
+    // plausibility BEFORE any allocation sized by header fields (a corrupt header must give SG_ERR_INVALID, not a
+    // std::bad_alloc thrown through the C ABI): every node costs >= 2 bytes of graph and dimension * 4 bytes of vector
+    {
+        const uint64_t rest = vi.file_size - off;
+        const unsigned __int128 need_bytes = (unsigned __int128)vi.num_vectors * (2ull + (uint64_t)vi.dimension * 4ull);
+        if (vi.dimension == 0 || vi.num_vectors > 0xFFFFFFFEull || need_bytes > (unsigned __int128)rest) {
+            sg::set_error("VAMA header implausible for a %llu-byte file: %llu vectors x dim %u", (unsigned long long)vi.file_size,
+                          (unsigned long long)vi.num_vectors, vi.dimension);
+            return SG_ERR_INVALID;
+        }
     }
     if (deleted) {
         deleted->resize(vi.deleted_count);
@@ -145,7 +156,19 @@ int vama_parse(FILE *f, VamaInfo &vi, std::vector<uint32_t> *deleted, int verify
 
 extern "C" {
 
+static int vama_inspect_impl(const char *path, int verify_checksum, uint64_t *num_vectors_out, uint32_t *dimension_out,
+                             uint32_t *deleted_count_out, uint32_t *metric_out, uint64_t *vectors_offset_out);
+
 int sg_vama_inspect(const char *path, int verify_checksum, uint64_t *num_vectors_out, uint32_t *dimension_out,
+                    uint32_t *deleted_count_out, uint32_t *metric_out, uint64_t *vectors_offset_out)
+{
+    return sg::abi_guard("sg_vama_inspect", [&] {
+        return vama_inspect_impl(path, verify_checksum, num_vectors_out, dimension_out, deleted_count_out, metric_out,
+                                 vectors_offset_out);
+    });
+}
+
+static int vama_inspect_impl(const char *path, int verify_checksum, uint64_t *num_vectors_out, uint32_t *dimension_out,
                     uint32_t *deleted_count_out, uint32_t *metric_out, uint64_t *vectors_offset_out)
 {
     if (!path) return SG_ERR_INVALID;
@@ -166,6 +189,8 @@ int sg_vama_inspect(const char *path, int verify_checksum, uint64_t *num_vectors
     return SG_OK;
 }
 
+static int load_vama_impl(sg_store *s, const char *path, int verify_checksum);
+
 int sg_store_load_vama(sg_store *s, const char *path, int verify_checksum)
 {
     if (!s || !path) return SG_ERR_INVALID;
@@ -176,6 +201,18 @@ int sg_store_load_vama(sg_store *s, const char *path, int verify_checksum)
         sg::set_error("sg_store_load_vama needs an empty store (ids must equal the file's row numbers)");
         return SG_ERR_INVALID;
     }
+    rc = sg::abi_guard("sg_store_load_vama", [&] { return load_vama_impl(s, path, verify_checksum); });
+    if (rc != SG_OK && sg_store_len(s, &have) == SG_OK && have != 0) {
+        // a failure part-way must not leave the (formerly empty) store half populated; the error message stays
+        std::lock_guard<std::mutex> g(s->mu);
+        sg::store_truncate_locked(s);
+    }
+    return rc;
+}
+
+static int load_vama_impl(sg_store *s, const char *path, int verify_checksum)
+{
+    int rc = SG_OK;
     FILE *f = fopen(path, "rb");
     if (!f) {
         sg::set_error("cannot open %s", path);

@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <new>
 #include <vector>
 
 #include "sg_internal.h"
@@ -298,6 +299,106 @@ pq_scan_kernel(const PqScanArgs a)
     }
 }
 
+// Four queries per sweep with an INTERLEAVED table: lut4[(s * k + code)] is a float4 holding the entry of all
+// four queries, so ONE 16-byte shared-memory gather serves four look-ups (the scan is bound by shared-memory
+// gathers, not by HBM: 48 x QB look-ups per 52 bytes streamed -- see DESIGN.md 3.5d).  Each query still adds its
+// 48 terms in subvector order (`total += table[m][code[m]]`, pq.rs:358-369): bit-identical to the CPU path.
+// 16-byte gathers also conflict less than 4-byte ones (a quarter-warp of 8 lanes shares 8 bank groups).
+__global__ void __launch_bounds__(512, 1)
+pq_scan4_kernel(const PqScanArgs a)
+{
+    constexpr int QB = 4;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const uint32_t m = a.m, k = a.k, C = a.cap;
+    float4 *lut4 = reinterpret_cast<float4 *>(smem);                                 // [m*k]; later the CTA's merge buffer
+    uint64_t *cand = reinterpret_cast<uint64_t *>(smem + pq_region0_bytes(QB, m, k, W, a.topk));   // [W][QB][C]
+    uint32_t *cnt_s = reinterpret_cast<uint32_t *>(cand + (size_t)W * QB * C);      // [W][QB]
+    for (uint32_t i = threadIdx.x; i < m * k; i += blockDim.x) {
+        float4 v;
+        v.x = a.table[i];
+        v.y = a.nq > 1 ? a.table[(size_t)m * k + i] : 0.0f;
+        v.z = a.nq > 2 ? a.table[(size_t)2 * m * k + i] : 0.0f;
+        v.w = a.nq > 3 ? a.table[(size_t)3 * m * k + i] : 0.0f;
+        lut4[i] = v;
+    }
+    __syncthreads();
+
+    uint32_t cnt[QB], tau[QB];
+#pragma unroll
+    for (int q = 0; q < QB; ++q) {
+        cnt[q] = 0;
+        tau[q] = 0xFFFFFFFFu;
+    }
+    uint64_t *my_cand = cand + (size_t)warp * QB * C;
+    const uint64_t n_tiles = (a.n + 31) / 32;
+    const uint64_t G = (uint64_t)gridDim.x * W;
+    const uint32_t words = m / 4;
+    const uint32_t *codes32 = reinterpret_cast<const uint32_t *>(a.codes);
+    for (uint64_t tile = (uint64_t)blockIdx.x * W + warp; tile < n_tiles; tile += G) {
+        const uint64_t row = tile * 32 + lane;
+        const bool live = row < a.n;
+        float total[QB] = {0.0f, 0.0f, 0.0f, 0.0f};
+        bool bad = false;
+        uint32_t id = 0;
+        if (live) {
+            id = a.ids[row];
+            const uint32_t *cw = codes32 + row * words;
+#pragma unroll 4
+            for (uint32_t w = 0; w < words; ++w) {
+                const uint32_t four = __ldg(cw + w);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const uint32_t code = (four >> (8 * t)) & 0xFFu;
+                    const uint32_t s = w * 4 + t;
+                    bad |= code >= k;
+                    const float4 v = lut4[s * k + (code < k ? code : 0)];
+                    total[0] = __fadd_rn(total[0], v.x);
+                    total[1] = __fadd_rn(total[1], v.y);
+                    total[2] = __fadd_rn(total[2], v.z);
+                    total[3] = __fadd_rn(total[3], v.w);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < QB; ++q) {
+            const float d = bad ? 3.402823466e+38f : total[q];             // distance_with_table: f32::MAX on a corrupt code
+            const uint32_t key32 = order_key32(d != d ? __uint_as_float(0x7FC00000u) : d);
+            uint64_t *buf = my_cand + (size_t)q * C;
+            if (cnt[q] + 32 > C) pq_compact(buf, cnt[q], tau[q], a.topk, lane);
+            const bool hit = live && (q < (int)a.nq) && key32 <= tau[q];
+            const uint32_t mk = __ballot_sync(FULL, hit);
+            if (mk) {
+                if (hit) buf[cnt[q] + __popc(mk & ((1u << lane) - 1))] = make_key(key32, id);
+                cnt[q] += __popc(mk);
+                __syncwarp();
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < QB; ++q) {
+        pq_compact(my_cand + (size_t)q * C, cnt[q], tau[q], a.topk, lane);
+        if (lane == 0) cnt_s[warp * QB + q] = cnt[q];
+    }
+    __syncthreads();
+    uint64_t *mbuf = reinterpret_cast<uint64_t *>(lut4);       // the table is no longer needed: merge in its place
+    const uint32_t topk = a.topk;
+    const uint32_t M = next_pow2(W * topk < 2 ? 2 : W * topk);
+    for (uint32_t q = 0; q < a.nq; ++q) {
+        for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) {
+            const uint32_t w = i / topk, r = i - w * topk;
+            uint64_t key = KEY_SENTINEL;
+            if (w < W && r < cnt_s[w * QB + q]) key = cand[((size_t)w * QB + q) * C + r];
+            mbuf[i] = key;
+        }
+        __syncthreads();
+        block_bitonic_sort(mbuf, M);
+        uint64_t *out = a.out_lists + ((size_t)q * gridDim.x + blockIdx.x) * topk;
+        for (uint32_t i = threadIdx.x; i < topk; i += blockDim.x) out[i] = mbuf[i];
+        __syncthreads();
+    }
+}
+
 size_t pq_scan_smem(uint32_t qb, uint32_t m, uint32_t k, uint32_t W, uint32_t cap, uint32_t topk)
 {
     return pq_region0_bytes(qb, m, k, W, topk) + (size_t)W * qb * cap * 8 + (size_t)W * qb * 4 + 16;
@@ -467,10 +568,14 @@ int sg_pq_train(sg_pq **out, int device, uint32_t dim, uint32_t subvec_dim, uint
         if (use_members) {
             e = cudaMalloc(&d_members, (size_t)m * n * 4);
             if (e == cudaSuccess) e = cudaMalloc(&d_moff, (size_t)m * (k + 1) * 8);
-            h_assign.resize((size_t)m * n);
-            h_members.resize((size_t)m * n);
-            h_moff.resize((size_t)m * (k + 1));
-            cur.resize(k);
+            try {                                  // no exception may cross the C ABI (and the device buffers must be freed)
+                h_assign.resize((size_t)m * n);
+                h_members.resize((size_t)m * n);
+                h_moff.resize((size_t)m * (k + 1));
+                cur.resize(k);
+            } catch (const std::bad_alloc &) {
+                e = cudaErrorMemoryAllocation;
+            }
         }
         for (uint32_t it = 0; it < iterations && e == cudaSuccess; ++it) {
             dim3 grid((unsigned)((n + 255) / 256), m);
@@ -652,6 +757,18 @@ int sg_pq_search(sg_pq *p, const float *queries, uint32_t b, uint32_t topk, uint
     const uint32_t cap = 2 * kp;
     uint32_t W = 8, QB = b >= 2 ? 2 : 1;
     auto fits = [&](uint32_t qb, uint32_t w) { return pq_scan_smem(qb, m, k, w, cap, topk) <= 220 * 1024; };
+    // three or more queries: four per sweep with the interleaved table (one 16-byte gather = four look-ups), as many
+    // warps as fit beside the 16*m*k-byte table
+    const char *q4 = getenv("SG_PQ_QB4");
+    if (b >= 3 && !(q4 && atoi(q4) == 0)) {
+        for (uint32_t w4 : {16u, 12u, 8u, 4u}) {
+            if (fits(4, w4)) {
+                QB = 4;
+                W = w4;
+                break;
+            }
+        }
+    }
     while (!fits(QB, W)) {
         if (W > 1) W >>= 1;
         else if (QB > 1) { QB = 1; W = 8; }
@@ -698,7 +815,13 @@ int sg_pq_search(sg_pq *p, const float *queries, uint32_t b, uint32_t topk, uint
             a.topk = topk;
             a.cap = cap;
             a.out_lists = p->d_lists + (size_t)done * grid * topk;
-            if (QB == 2) {
+            if (QB == 4) {
+                if (smem > smem_set[0]) {
+                    SG_CUDA_TRY(cudaFuncSetAttribute(pq_scan4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    smem_set[0] = smem;
+                }
+                pq_scan4_kernel<<<grid, W * 32, smem, st>>>(a);
+            } else if (QB == 2) {
                 if (smem > smem_set[2]) {
                     SG_CUDA_TRY(cudaFuncSetAttribute(pq_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     smem_set[2] = smem;

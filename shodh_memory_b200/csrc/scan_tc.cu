@@ -1,6 +1,6 @@
 // scan_tc.cu -- the tensor-core corpus sweep ("path B") for batched queries.
 //
-// For b >= 5 queries the row loop of VamanaIndex::brute_force_search (reference
+// For b >= 3 queries the row loop of VamanaIndex::brute_force_search (reference
 // src/vector_db/vamana.rs:1167-1188) is a [b x dim] . [dim x n_rows] contraction: at b = 256
 // it needs ~2 PFLOP/s to keep up with HBM, which only tcgen05 can deliver.  The tensor cores
 // see fp16(query) x fp16(row) with f32 accumulation, i.e. APPROXIMATE scores; exactness is
@@ -48,7 +48,8 @@ constexpr uint32_t TC_N = 128;          // corpus rows per CTA tile
 constexpr uint32_t TC_KB = 64;          // fp16 elements per K-block (one 128B swizzle row)
 constexpr uint32_t TC_STAGE_BYTES = TC_N * 128;   // 16 KB
 constexpr uint32_t TC_ACC_STAGES = 4;   // 4 x 128 = 512 TMEM columns (1-CTA form)
-constexpr uint32_t TC_THREADS = 256;
+constexpr uint32_t TC_THREADS = 384;     // warps 0-3: TMA producer, MMA issuer, TMEM allocator, spare; warps 4-11: epilogue
+constexpr uint32_t TC_EPI_THREADS = 256;
 constexpr float TC_NEG_INF = -__builtin_huge_valf();
 
 SG_DEVICE_INLINE uint32_t ld_relaxed_u32(const uint32_t *p)
@@ -63,9 +64,9 @@ SG_DEVICE_INLINE uint32_t ld_acquire_gpu_u32(const uint32_t *p)
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-SG_DEVICE_INLINE void epi_bar_sync()      // the 128 epilogue threads only (named barrier 1)
+SG_DEVICE_INLINE void epi_bar_sync()      // the 256 epilogue threads only (named barrier 1)
 {
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
 // tile handled in iteration `it` of a CTA (pair): iteration 0 is the sample pass over the list's first
@@ -77,9 +78,13 @@ SG_DEVICE_INLINE uint64_t tile_of_iter(uint64_t tile0, uint64_t stride, uint64_t
 }
 
 // ---- the epilogue shared by the 1-CTA and the CTA-pair kernels -------------------------------------
-// thread t (0..127 of the 4 epilogue warps) <-> query q_base + t <-> TMEM lane t.
-// NCOLS = corpus rows (TMEM columns) per accumulator stage.  tempty_cluster_addr is the
-// shared::cluster address of the accumulator-empty barriers (the leader CTA's in pair mode).
+// EIGHT epilogue warps: two per TMEM lane quarter.  Thread (grp, t) <-> query q_base + t <-> TMEM lane t; group
+// grp = 0/1 scans the even/odd 32-column chunks of every accumulator, so a tile's scan time is halved and two
+// warps per scheduler hide each other's TMEM-load latency -- the scan must stay well ahead of the MMA pipe (a
+// 256-row pair tile is ~3000 tensor cycles).  Each (query, list, grp) owns its own candidate region, so nothing is
+// shared between the two threads of a query except the read-only thresholds.
+// NCOLS = corpus rows (TMEM columns) per accumulator stage.  tempty_cluster_addr is the shared::cluster address of
+// the accumulator-empty barriers (the leader CTA's in pair mode).  n_lists counts REGIONS (2 per CTA / CTA pair).
 //
 // Threshold validity.  tau_f never exceeds the kk-th best approximate score over the whole corpus:
 //   * seed: the sample contributes n_lists * J maxima of DISTINCT 32-row chunks; when at least kk of
@@ -92,19 +97,21 @@ SG_DEVICE_INLINE uint64_t tile_of_iter(uint64_t tile0, uint64_t stride, uint64_t
 template <uint32_t NCOLS, bool DUMP>
 SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tmem_base, uint64_t *tfull_bar,
                                   uint32_t tempty_cluster_addr, uint64_t my_tiles, uint64_t tile0, uint64_t tile_stride,
-                                  uint32_t q_base, uint32_t nq_local, uint32_t list_idx, uint32_t n_lists,
+                                  uint32_t q_base, uint32_t nq_local, uint32_t unit_idx, uint32_t n_lists,
                                   uint32_t acc_stages)
 {
-    const uint32_t warp = threadIdx.x >> 5;
-    const uint32_t t = threadIdx.x - 128;
-    const uint32_t wq = (warp & 3) * 32;             // first query of this warp
+    constexpr uint32_t NCH = NCOLS / 32;             // chunks per accumulator; this thread scans grp, grp + 2, ...
+    const uint32_t e = threadIdx.x - 128;            // 0..255 over the eight epilogue warps
+    const uint32_t grp = e >> 7, t = e & 127;
+    const uint32_t wq = ((threadIdx.x >> 5) & 3) * 32;   // first TMEM lane of this warp's quarter
     const bool active = t < nq_local;
     const uint32_t q = q_base + t;
+    const uint32_t list_idx = 2 * unit_idx + grp;    // this thread's region among the query's n_lists regions
     const uint32_t lane_base = wq << 16;
     float tau_f = active ? TC_NEG_INF : -TC_NEG_INF; // similarity threshold: -inf (everything) / +inf (never)
     float tau0 = TC_NEG_INF, w = 0.0f, inv_w = 0.0f;
     bool use_hist = false;
-    uint32_t my_cnt = 0;                             // entries this thread appended to ITS (query, list) region
+    uint32_t my_cnt = 0;                             // entries this thread appended to ITS region
     uint32_t tau_pub = 0xFFFFFFFFu;                  // last threshold key this lane shared
     uint64_t *my_cand = a.cand + ((size_t)q * n_lists + list_idx) * a.cap_l;
     uint32_t *my_hist = a.hist + (size_t)q * TC_HIST;
@@ -128,17 +135,17 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
         return fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
     };
 
-    uint64_t it = 0;
+    uint64_t it = 1;
     if constexpr (!DUMP) {
-        // ===== sample pass (iteration 0): the J best chunk maxima of this list's first tile =====
-        float m[8];
+        // ===== sample pass (iteration 0): the J best chunk maxima of this thread's chunks of the unit's first tile =====
+        float m[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) m[i] = TC_NEG_INF;
+        for (int i = 0; i < 4; ++i) m[i] = TC_NEG_INF;
         if (my_tiles) {
             mbar_wait(smem_u32(tfull_bar), 0);
             tc_fence_after();
 #pragma unroll 1
-            for (uint32_t c = 0; c < NCOLS / 32; ++c) {
+            for (uint32_t c = grp; c < NCH; c += 2) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + lane_base + c * 32, r);
                 tmem_ld_wait();
@@ -151,7 +158,7 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
                 float mx = chunk_max(r);
                 if (!(mx == mx)) mx = TC_NEG_INF;        // an all-NaN chunk must not enter (it would duplicate entries)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {            // insert into the descending list
+                for (int i = 0; i < 4; ++i) {            // insert into the descending list
                     const float hi = fmaxf(m[i], mx);
                     mx = fminf(m[i], mx);
                     m[i] = hi;
@@ -160,16 +167,15 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
             tc_fence_before();
             mbar_arrive_cluster(tempty_cluster_addr);        // accumulator stage 0 is free again
         }
-        it = 1;
         if (active) {
 #pragma unroll
-            for (uint32_t j = 0; j < 8; ++j)
-                if (j < a.J) a.maxima[((size_t)list_idx * a.J + j) * a.b_pad + q] = m[j];
+            for (uint32_t j = 0; j < 4; ++j)
+                if (j < a.J) a.maxima[(size_t)q * a.nv_pad + list_idx * a.J + j] = m[j];
         }
         // device-wide meeting point: every CTA of the grid publishes its sample, then reads all of them
         __threadfence();
         epi_bar_sync();
-        if (t == 0) {
+        if (e == 0) {
             atomicAdd(a.arrive + a.q_tile, 1u);
             const long long t0 = clock64();
             uint32_t ok = 1;
@@ -184,72 +190,107 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
         epi_bar_sync();
         __threadfence();
         if (active && s_ctl[0]) {
+            // this query's sample values are contiguous ([query][value], padded with -inf to a multiple of 4): 16-byte
+            // loads, all independent -- a scalar, strided walk of ~300 values was a 60 us latency chain at kernel start
             float mn = -TC_NEG_INF, sum = 0.0f;
             uint32_t nfin = 0;
-            const uint32_t nv = n_lists * a.J;
-            const float *mp = a.maxima + q;
-            for (uint32_t i = 0; i < nv; ++i) {
-                const float v = __ldcg(mp + (size_t)i * a.b_pad);
-                if (v > TC_NEG_INF) {
-                    ++nfin;
-                    mn = fminf(mn, v);
-                    sum += v;
+            const uint32_t nv4 = a.nv_pad / 4;
+            const float4 *mp4 = reinterpret_cast<const float4 *>(a.maxima + (size_t)q * a.nv_pad);
+#pragma unroll 8
+            for (uint32_t i = 0; i < nv4; ++i) {
+                const float4 v4 = __ldcg(mp4 + i);
+                const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (vv[c] > TC_NEG_INF) {
+                        ++nfin;
+                        mn = fminf(mn, vv[c]);
+                        sum += vv[c];
+                    }
                 }
             }
             if (nfin >= a.kk) {                              // kk distinct rows score >= mn
+                // a better seed than the minimum: the largest of 7 candidate levels mn + j * (mean - mn) / 2 that still
+                // has kk sample values at or above it (each value is the maximum of a DISTINCT 32-row chunk, so that
+                // many distinct rows reach it).  The levels hang off the MEAN of the sample maxima, which -- unlike the
+                // largest one -- is not dragged away by a near-duplicate of the query that happens to sit in the sample.
+                const float mean = sum / (float)nfin, step = 0.5f * (mean - mn);
+                float lv[7];
+                uint32_t cn[7];
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {
+                    lv[j] = mn + (float)(j + 1) * step;
+                    cn[j] = 0;
+                }
+#pragma unroll 8
+                for (uint32_t i = 0; i < nv4; ++i) {
+                    const float4 v4 = __ldcg(mp4 + i);
+#pragma unroll
+                    for (int j = 0; j < 7; ++j)              // -inf / NaN compare false
+                        cn[j] += (v4.x >= lv[j] ? 1u : 0u) + (v4.y >= lv[j] ? 1u : 0u) + (v4.z >= lv[j] ? 1u : 0u) +
+                                 (v4.w >= lv[j] ? 1u : 0u);
+                }
                 tau0 = mn;
-                tau_f = mn;
-                // histogram range [mn, mn + 4 (mean - mn)]: the final threshold lies well beyond the sample's typical
-                // maximum (the sample is ~1/500 of a 10M-row corpus), and the MEAN, unlike the largest maximum, is not
-                // dragged away by one near-duplicate of the query that happens to sit in the sample (that stretched the
-                // buckets until a single one covered the whole useful range).  Scores beyond the range land in the last
+#pragma unroll
+                for (int j = 0; j < 7; ++j)
+                    if (cn[j] >= a.kk) tau0 = lv[j];         // levels ascend: the last one that qualifies wins
+                tau_f = tau0;
+                // histogram over [tau0, tau0 + 3 (mean - mn)]: the final threshold lies well beyond the sample's
+                // typical maximum (the sample is ~1/500 of a 10M-row corpus).  Scores beyond the range land in the last
                 // bucket: the threshold then stops one bucket short of them, which only costs a few extra candidates.
-                const float top = mn + 4.0f * (sum / (float)nfin - mn);
-                w = (top - mn) * (1.0f / TC_HIST);
-                if (w > 1.0e-5f * fmaxf(fabsf(mn), fabsf(top)) && w < -TC_NEG_INF) {
+                const float range = 3.0f * (mean - mn);
+                w = range * (1.0f / TC_HIST);
+                if (w > 1.0e-5f * fmaxf(fabsf(tau0), fabsf(tau0 + range)) && w < -TC_NEG_INF) {
                     inv_w = 1.0f / w;
                     use_hist = true;
                 }
             }
         }
-    } else {
-        it = 1;
     }
 
     // ===== the sweep proper =====
+    //  * the threshold inputs (shared key, every 4th tile the histogram) are requested ONE TILE AHEAD and consumed
+    //    at the top of the next iteration: their L2 latency never sits between "accumulator ready" and the scan;
+    //  * dead / out-of-range columns are NOT neutralised on the fast path: they can at worst trigger the slow
+    //    path, which masks them out -- the fast path is one 3-input max tree and one vote per 32 columns.
+    uint32_t accn = (uint32_t)((DUMP ? it - 1 : it) % acc_stages), acc_ph = (uint32_t)(((DUMP ? it - 1 : it) / acc_stages) & 1);
+    uint32_t g_pend = 0xFFFFFFFFu;
+    uint4 h_pend[TC_HIST / 4];
+    bool h_valid = false;
     for (; it <= my_tiles; ++it) {
         const uint64_t tile = tile_of_iter(tile0, tile_stride, it);
-        const uint32_t accn = (uint32_t)((DUMP ? it - 1 : it) % acc_stages);
-        const uint32_t acc_ph = (uint32_t)(((DUMP ? it - 1 : it) / acc_stages) & 1);
         if constexpr (!DUMP) {
-            if (active) {
-                if (use_hist && ((it + list_idx) & 3) == 0) {
-                    // refresh from the shared histogram: highest bucket idx whose tail holds kk rows
-                    const uint4 *hp = reinterpret_cast<const uint4 *>(my_hist);
-                    uint4 h[TC_HIST / 4];
+            if (h_valid) {
+                // highest bucket idx whose tail holds kk rows
+                uint32_t cum = 0;
+                int idx = -1;
 #pragma unroll
-                    for (uint32_t i = 0; i < TC_HIST / 4; ++i) h[i] = __ldcg(hp + i);
-                    uint32_t cum = 0;
-                    int idx = -1;
-#pragma unroll
-                    for (int i = TC_HIST / 4 - 1; i >= 0; --i) {
-                        cum += h[i].w; if (idx < 0 && cum >= a.kk) idx = 4 * i + 3;
-                        cum += h[i].z; if (idx < 0 && cum >= a.kk) idx = 4 * i + 2;
-                        cum += h[i].y; if (idx < 0 && cum >= a.kk) idx = 4 * i + 1;
-                        cum += h[i].x; if (idx < 0 && cum >= a.kk) idx = 4 * i;
-                    }
-                    if (idx >= 2) tau_f = fmaxf(tau_f, tau0 + (float)(idx - 1) * w);
+                for (int i = TC_HIST / 4 - 1; i >= 0; --i) {
+                    cum += h_pend[i].w; if (idx < 0 && cum >= a.kk) idx = 4 * i + 3;
+                    cum += h_pend[i].z; if (idx < 0 && cum >= a.kk) idx = 4 * i + 2;
+                    cum += h_pend[i].y; if (idx < 0 && cum >= a.kk) idx = 4 * i + 1;
+                    cum += h_pend[i].x; if (idx < 0 && cum >= a.kk) idx = 4 * i;
                 }
-                const uint32_t g = ld_relaxed_u32(gtau);
-                if (g != 0xFFFFFFFFu) tau_f = fmaxf(tau_f, -key32_to_dist(g));
+                if (idx >= 2) tau_f = fmaxf(tau_f, tau0 + (float)(idx - 1) * w);
             }
+            if (g_pend != 0xFFFFFFFFu) tau_f = fmaxf(tau_f, -key32_to_dist(g_pend));
         }
         mbar_wait(smem_u32(tfull_bar + accn), acc_ph);
         tc_fence_after();
+        if constexpr (!DUMP) {
+            if (active) g_pend = ld_relaxed_u32(gtau);       // for the NEXT tile
+            h_valid = active && use_hist && (((uint32_t)it + 1 + list_idx) & 3u) == 0;
+            if (h_valid) {
+                const uint4 *hp = reinterpret_cast<const uint4 *>(my_hist);
+#pragma unroll
+                for (uint32_t i = 0; i < TC_HIST / 4; ++i) h_pend[i] = __ldcg(hp + i);
+            }
+        }
+        const uint32_t tbase = tmem_base + lane_base + accn * NCOLS;
 #pragma unroll 1
-        for (uint32_t c = 0; c < NCOLS / 32; ++c) {
+        for (uint32_t c = grp; c < NCH; c += 2) {
             uint32_t r[32];
-            tmem_ld32(tmem_base + lane_base + accn * NCOLS + c * 32, r);
+            tmem_ld32(tbase + c * 32, r);
             tmem_ld_wait();
             const uint64_t row0 = tile * NCOLS + c * 32;     // 32-aligned: one bitmap word
             if constexpr (DUMP) {
@@ -263,19 +304,14 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
                 }
                 continue;
             }
-            const uint32_t dead = dead_mask(row0);
-            if (dead) {                                      // rare: neutralise dead columns
-#pragma unroll
-                for (uint32_t j = 0; j < 32; ++j)
-                    if ((dead >> j) & 1u) r[j] = __float_as_uint(TC_NEG_INF);
-            }
             const float mx = chunk_max(r);
             if (__any_sync(0xFFFFFFFFu, mx >= tau_f)) {
                 // slow path: the owning lane appends its hits (cost ~ number of 8-column groups with a hit)
+                const uint32_t dead = dead_mask(row0);
                 uint32_t mask = 0;
 #pragma unroll
                 for (uint32_t j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) >= tau_f) ? (1u << j) : 0u;
-                mask &= ~dead;                               // (-inf >= -inf) would let dead columns through
+                mask &= ~dead;
 #pragma unroll
                 for (uint32_t g8 = 0; g8 < 4; ++g8) {
                     if ((mask >> (8 * g8)) & 0xFFu) {
@@ -299,6 +335,10 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
         }
         tc_fence_before();
         mbar_arrive_cluster(tempty_cluster_addr + 8 * accn);  // all epilogue threads release the accumulator
+        if (++accn == acc_stages) {
+            accn = 0;
+            acc_ph ^= 1;
+        }
         if constexpr (!DUMP) {
             if (active && tau_f > TC_NEG_INF) {              // share the threshold GPU-wide when it moved
                 const uint32_t k32 = order_key32(-tau_f);
@@ -328,7 +368,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
     // carve-up: A block | B ring | barriers | control word | tmem ptr
     uint8_t *a_base = smem;                                         // nkb x (128 x 128 B)
     uint8_t *b_base = a_base + (size_t)nkb * TC_M * 128;            // S x 16 KB
-    uint64_t *bars = reinterpret_cast<uint64_t *>(b_base + (size_t)S * TC_STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(b_base + (size_t)S * a.kbs * TC_STAGE_BYTES);
     uint64_t *full_bar = bars;                       // [S]
     uint64_t *empty_bar = bars + S;                  // [S]
     uint64_t *tfull_bar = bars + 2 * S;              // [TC_ACC_STAGES]
@@ -344,7 +384,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
         }
         for (uint32_t i = 0; i < TC_ACC_STAGES; ++i) {
             mbar_init(smem_u32(tfull_bar + i), 1);
-            mbar_init(smem_u32(tempty_bar + i), 128);
+            mbar_init(smem_u32(tempty_bar + i), TC_EPI_THREADS);
         }
         mbar_init(smem_u32(a_bar), 1);
         mbar_fence_init();
@@ -360,59 +400,76 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
     const uint64_t n_tiles = (a.n_rows + TC_N - 1) / TC_N;
     const uint64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const uint64_t it0 = (DUMP || my_tiles == 0) ? 1 : 0;   // iteration 0 = the sample pass
-    const uint64_t sh = DUMP ? 1 : 0;                       // accumulator-stage numbering starts at the first iteration run
 
+    // A ring stage holds KBS consecutive K-blocks of one tile (KBS = 2 when the row has an even number of them): one
+    // barrier round trip, one election and one commit per stage instead of per K-block.  The MMA issue loop is a
+    // single thread's dependent instruction chain; per K-block it cost more than the 4 MMAs it issues take to
+    // execute (measured: 630-750 cycles against 512 / 256), i.e. the issue loop, not HBM or the tensor pipe, set the
+    // pace.  Halving its trips per tile puts it back under the MMA time.
+    const uint32_t KBS = a.kbs, n_grp = nkb / KBS, stage_bytes = KBS * TC_STAGE_BYTES;
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
+        // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
+        if (elect_one_sync()) {
             mbar_arrive_expect_tx(smem_u32(a_bar), nkb * TC_M * 128);
             for (uint32_t kb = 0; kb < nkb; ++kb)
                 tma_load_2d(smem_u32(a_base + (size_t)kb * TC_M * 128), &tmap_q, smem_u32(a_bar), (int32_t)(kb * TC_KB),
                             (int32_t)(a.q_tile * TC_M));
-            uint32_t st = 0, ph = 0;
-            for (uint64_t it = it0; it <= my_tiles; ++it) {
-                const uint64_t tile = tile_of_iter(blockIdx.x, gridDim.x, it);
-                for (uint32_t kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(smem_u32(empty_bar + st), ph ^ 1);
-                    mbar_arrive_expect_tx(smem_u32(full_bar + st), TC_STAGE_BYTES);
-                    tma_load_2d(smem_u32(b_base + (size_t)st * TC_STAGE_BYTES), &tmap_rows, smem_u32(full_bar + st),
-                                (int32_t)(kb * TC_KB), (int32_t)(tile * TC_N));
-                    if (++st == S) { st = 0; ph ^= 1; }
+        }
+        __syncwarp();
+        uint32_t st = 0, ph = 0;
+        for (uint64_t it = it0; it <= my_tiles; ++it) {
+            const uint64_t tile = tile_of_iter(blockIdx.x, gridDim.x, it);
+            for (uint32_t g = 0; g < n_grp; ++g) {
+                mbar_wait(smem_u32(empty_bar + st), ph ^ 1);
+                if (elect_one_sync()) {
+                    const uint32_t fb = smem_u32(full_bar + st), dst = smem_u32(b_base) + st * stage_bytes;
+                    mbar_arrive_expect_tx(fb, stage_bytes);
+                    for (uint32_t j = 0; j < KBS; ++j)
+                        tma_load_2d(dst + j * TC_STAGE_BYTES, &tmap_rows, fb, (int32_t)((g * KBS + j) * TC_KB),
+                                    (int32_t)(tile * TC_N));
                 }
+                __syncwarp();
+                if (++st == S) { st = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(TC_M, TC_N);
-            mbar_wait(smem_u32(a_bar), 0);
+        // ===== MMA issuer: the whole warp walks the (uniform) loop, one elected lane issues =====
+        constexpr uint32_t idesc = make_idesc_f16(TC_M, TC_N);
+        mbar_wait(smem_u32(a_bar), 0);
+        tc_fence_after();
+        uint32_t st = 0, ph = 0;
+        uint32_t acc = 0, acc_ph = 0;
+        // descriptors differ only in their low word (address >> 4): keep that as a running integer
+        const uint64_t desc_hi = make_sw128_desc(0);
+        const uint32_t a_lo = smem_u32(a_base) >> 4, b_lo = smem_u32(b_base) >> 4;
+        for (uint64_t it = it0; it <= my_tiles; ++it) {
+            mbar_wait(smem_u32(tempty_bar + acc), acc_ph ^ 1);
             tc_fence_after();
-            uint32_t st = 0, ph = 0;
-            for (uint64_t it = it0; it <= my_tiles; ++it) {
-                const uint32_t acc = (uint32_t)((it - sh) % TC_ACC_STAGES);
-                const uint32_t acc_ph = (uint32_t)(((it - sh) / TC_ACC_STAGES) & 1);
-                mbar_wait(smem_u32(tempty_bar + acc), acc_ph ^ 1);
+            const uint32_t d_tmem = tmem_base + acc * TC_N;
+            for (uint32_t g = 0; g < n_grp; ++g) {
+                mbar_wait(smem_u32(full_bar + st), ph);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * TC_N;
-                for (uint32_t kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(smem_u32(full_bar + st), ph);
-                    tc_fence_after();
-                    const uint64_t da = make_sw128_desc(smem_u32(a_base + (size_t)kb * TC_M * 128));
-                    const uint64_t db = make_sw128_desc(smem_u32(b_base + (size_t)st * TC_STAGE_BYTES));
+                if (elect_one_sync()) {
+                    for (uint32_t j = 0; j < KBS; ++j) {
+                        const uint64_t da = desc_hi | (uint64_t)(a_lo + (g * KBS + j) * (TC_M * 128 / 16));
+                        const uint64_t db = desc_hi | (uint64_t)(b_lo + (st * stage_bytes + j * TC_STAGE_BYTES) / 16);
 #pragma unroll
-                    for (uint32_t k = 0; k < TC_KB / 16; ++k)   // advance 32 B (= 16 fp16) inside the swizzle row
-                        umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                    umma_commit(smem_u32(empty_bar + st));     // frees the B slot when these MMAs retire
-                    if (++st == S) { st = 0; ph ^= 1; }
+                        for (uint32_t k = 0; k < TC_KB / 16; ++k)   // advance 32 B (= 16 fp16) inside the swizzle row
+                            umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (g | j | k) ? 1u : 0u);
+                    }
+                    umma_commit(smem_u32(empty_bar + st));     // frees the stage when these MMAs retire
+                    if (g + 1 == n_grp) umma_commit(smem_u32(tfull_bar + acc));   // accumulator complete -> epilogue
                 }
-                umma_commit(smem_u32(tfull_bar + acc));        // accumulator complete -> epilogue
+                __syncwarp();
+                if (++st == S) { st = 0; ph ^= 1; }
             }
+            if (++acc == TC_ACC_STAGES) { acc = 0; acc_ph ^= 1; }
         }
     } else if (warp >= 4) {
         // ===== epilogue: thread t <-> query t <-> TMEM lane t =====
         tc_epilogue<TC_N, DUMP>(a, s_ctl, tmem_base, tfull_bar, smem_u32(tempty_bar), my_tiles, /*tile0=*/blockIdx.x,
                                 /*tile_stride=*/gridDim.x, /*q_base=*/a.q_tile * TC_M, /*nq_local=*/a.nq,
-                                /*list_idx=*/blockIdx.x, /*n_lists=*/gridDim.x, TC_ACC_STAGES);
+                                /*unit_idx=*/blockIdx.x, /*n_lists=*/2 * gridDim.x, TC_ACC_STAGES);
     }
 
     tc_fence_before();
@@ -451,7 +508,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_cons
 
     uint8_t *a_base = smem;                                         // this CTA's 128 queries
     uint8_t *b_base = a_base + (size_t)nkb * TC_M * 128;            // S x 16 KB: this CTA's half of each tile
-    uint64_t *bars = reinterpret_cast<uint64_t *>(b_base + (size_t)S * TC_STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(b_base + (size_t)S * a.kbs * TC_STAGE_BYTES);
     uint64_t *full_bar = bars;
     uint64_t *empty_bar = bars + S;
     uint64_t *tfull_bar = bars + 2 * S;
@@ -467,7 +524,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_cons
         }
         for (uint32_t i = 0; i < ACC2; ++i) {
             mbar_init(smem_u32(tfull_bar + i), 1);
-            mbar_init(smem_u32(tempty_bar + i), 256);
+            mbar_init(smem_u32(tempty_bar + i), 2 * TC_EPI_THREADS);
         }
         mbar_init(smem_u32(a_bar), 1);
         mbar_fence_init();
@@ -485,7 +542,6 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_cons
     const uint64_t n_tiles = (a.n_rows + N2 - 1) / N2;
     const uint64_t my_tiles = cluster_id < n_tiles ? (n_tiles - cluster_id + n_clusters - 1) / n_clusters : 0;
     const uint64_t it0 = (DUMP || my_tiles == 0) ? 1 : 0;
-    const uint64_t sh = DUMP ? 1 : 0;
 
     // resident A operand: this CTA's 128 queries.  Everyone waits, then the pair synchronises so the
     // leader's MMA thread may read the peer's A through the pair datapath.
@@ -498,53 +554,63 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_cons
     mbar_wait(smem_u32(a_bar), 0);
     cluster_sync_all();
 
+    const uint32_t KBS = a.kbs, n_grp = nkb / KBS, stage_bytes = KBS * TC_STAGE_BYTES;   // see scan_tc_kernel
     if (warp == 0) {
-        // ===== TMA producer (both CTAs): my half of every tile =====
-        if (lane == 0) {
-            uint32_t st = 0, ph = 0;
-            for (uint64_t it = it0; it <= my_tiles; ++it) {
-                const uint64_t tile = tile_of_iter(cluster_id, n_clusters, it);
-                for (uint32_t kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(smem_u32(empty_bar + st), ph ^ 1);
-                    const uint32_t lfull = mapa_u32(smem_u32(full_bar + st), 0);
-                    if (leader) mbar_arrive_expect_tx(smem_u32(full_bar + st), 2 * TC_STAGE_BYTES);
+        // ===== TMA producer (both CTAs): my half of every tile; warp-uniform loop, one elected lane issues =====
+        uint32_t st = 0, ph = 0;
+        for (uint64_t it = it0; it <= my_tiles; ++it) {
+            const uint64_t tile = tile_of_iter(cluster_id, n_clusters, it);
+            for (uint32_t g = 0; g < n_grp; ++g) {
+                mbar_wait(smem_u32(empty_bar + st), ph ^ 1);
+                if (elect_one_sync()) {
+                    const uint32_t lfull = mapa_u32(smem_u32(full_bar + st), 0), dst = smem_u32(b_base) + st * stage_bytes;
+                    if (leader) mbar_arrive_expect_tx(smem_u32(full_bar + st), 2 * stage_bytes);
                     else mbar_arrive_cluster(lfull);
-                    tma_load_2d_2cta(smem_u32(b_base + (size_t)st * TC_STAGE_BYTES), &tmap_rows, lfull,
-                                     (int32_t)(kb * TC_KB), (int32_t)(tile * N2 + rank * TC_M));
-                    if (++st == S) { st = 0; ph ^= 1; }
+                    for (uint32_t j = 0; j < KBS; ++j)
+                        tma_load_2d_2cta(dst + j * TC_STAGE_BYTES, &tmap_rows, lfull, (int32_t)((g * KBS + j) * TC_KB),
+                                         (int32_t)(tile * N2 + rank * TC_M));
                 }
+                __syncwarp();
+                if (++st == S) { st = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: the leader's single thread drives the pair =====
-        if (leader && lane == 0) {
+        // ===== MMA issuer: the leader's warp walks the (uniform) loop, one elected lane drives the pair =====
+        if (leader) {
             constexpr uint32_t idesc = make_idesc_f16(256, N2);
             uint32_t st = 0, ph = 0;
+            uint32_t acc = 0, acc_ph = 0;
+            const uint64_t desc_hi = make_sw128_desc(0);
+            const uint32_t a_lo = smem_u32(a_base) >> 4, b_lo = smem_u32(b_base) >> 4;
             for (uint64_t it = it0; it <= my_tiles; ++it) {
-                const uint32_t acc = (uint32_t)((it - sh) % ACC2);
-                const uint32_t acc_ph = (uint32_t)(((it - sh) / ACC2) & 1);
                 mbar_wait(smem_u32(tempty_bar + acc), acc_ph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * N2;
-                for (uint32_t kb = 0; kb < nkb; ++kb) {
+                for (uint32_t g = 0; g < n_grp; ++g) {
                     mbar_wait(smem_u32(full_bar + st), ph);
                     tc_fence_after();
-                    const uint64_t da = make_sw128_desc(smem_u32(a_base + (size_t)kb * TC_M * 128));
-                    const uint64_t db = make_sw128_desc(smem_u32(b_base + (size_t)st * TC_STAGE_BYTES));
+                    if (elect_one_sync()) {
+                        for (uint32_t j = 0; j < KBS; ++j) {
+                            const uint64_t da = desc_hi | (uint64_t)(a_lo + (g * KBS + j) * (TC_M * 128 / 16));
+                            const uint64_t db = desc_hi | (uint64_t)(b_lo + (st * stage_bytes + j * TC_STAGE_BYTES) / 16);
 #pragma unroll
-                    for (uint32_t k = 0; k < TC_KB / 16; ++k)
-                        umma_f16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                    umma_commit_2cta(smem_u32(empty_bar + st), 3);     // frees the slot in BOTH CTAs
+                            for (uint32_t k = 0; k < TC_KB / 16; ++k)
+                                umma_f16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (g | j | k) ? 1u : 0u);
+                        }
+                        umma_commit_2cta(smem_u32(empty_bar + st), 3);     // frees the stage in BOTH CTAs
+                        if (g + 1 == n_grp) umma_commit_2cta(smem_u32(tfull_bar + acc), 3);   // accumulators ready in BOTH CTAs
+                    }
+                    __syncwarp();
                     if (++st == S) { st = 0; ph ^= 1; }
                 }
-                umma_commit_2cta(smem_u32(tfull_bar + acc), 3);        // accumulators ready in BOTH CTAs
+                if (++acc == ACC2) { acc = 0; acc_ph ^= 1; }
             }
         }
     } else if (warp >= 4) {
         tc_epilogue<N2, DUMP>(a, s_ctl, tmem_base, tfull_bar, mapa_u32(smem_u32(tempty_bar), 0), my_tiles,
                               /*tile0=*/cluster_id, /*tile_stride=*/n_clusters, /*q_base=*/a.q_tile * 256 + rank * TC_M,
                               /*nq_local=*/a.nq > rank * TC_M ? (a.nq - rank * TC_M < TC_M ? a.nq - rank * TC_M : TC_M) : 0,
-                              /*list_idx=*/cluster_id, /*n_lists=*/n_clusters, ACC2);
+                              /*unit_idx=*/cluster_id, /*n_lists=*/2 * n_clusters, ACC2);
     }
 
     tc_fence_before();
@@ -562,7 +628,8 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_cons
 __global__ void prep_queries_kernel(const float *__restrict__ q, uint32_t b, uint32_t dim,
                                     __half *__restrict__ qh, float *__restrict__ err, float *__restrict__ qnorm,
                                     uint32_t *__restrict__ gtau, uint32_t *__restrict__ flags, uint32_t *__restrict__ hist,
-                                    uint32_t *__restrict__ arrive, uint32_t n_qtiles, uint32_t *__restrict__ nflag)
+                                    uint32_t *__restrict__ arrive, uint32_t n_qtiles, uint32_t *__restrict__ nflag,
+                                    float *__restrict__ maxima, uint32_t nv, uint32_t nv_pad)
 {
     const uint32_t row = blockIdx.x;
     __shared__ double s_e[32], s_n[32];
@@ -576,6 +643,7 @@ __global__ void prep_queries_kernel(const float *__restrict__ q, uint32_t b, uin
         n2 += (double)v * (double)v;
     }
     if (threadIdx.x < TC_HIST) hist[(size_t)row * TC_HIST + threadIdx.x] = 0;
+    if (maxima && nv + threadIdx.x < nv_pad) maxima[(size_t)row * nv_pad + nv + threadIdx.x] = TC_NEG_INF;   // the pad of the sample row
     if (row == 0) {
         for (uint32_t i = threadIdx.x; i < n_qtiles; i += blockDim.x) arrive[i] = 0;
         if (threadIdx.x == 0) *nflag = 0;
@@ -649,21 +717,46 @@ finalize_tc_kernel(const __grid_constant__ FinalizeArgs f)
     }
     __syncthreads();
     // (1) gather every candidate at or above the final shared threshold (a valid bound on the kk-th best, so at
-    //     least kk survive whenever a threshold was ever published) -- one warp per (query, list) region
+    //     least kk survive whenever a threshold was ever published).  The region counts are read first and
+    //     prefix-summed, then ALL threads walk the flat entry index: two dependent global round trips in total,
+    //     not two per region.
     const uint32_t gt = f.gtau[q];
-    for (uint32_t l = warp; l < L; l += blockDim.x / 32) {
+    uint32_t *pre = reinterpret_cast<uint32_t *>(ekeys);          // [L + 1] prefix of min(count, cap_l); ekeys is free until (2)
+    for (uint32_t l = threadIdx.x; l < L; l += blockDim.x) {
         uint32_t c = f.cnts[(size_t)q * L + l];
         if (c > f.cap_l) {                       // the region overflowed: candidates were lost
-            if (lane == 0) s_flag = 1u;
+            s_flag = 1u;
             c = f.cap_l;
         }
-        const uint64_t *src = f.cand + ((size_t)q * L + l) * f.cap_l;
-        for (uint32_t e = lane; e < c; e += 32) {
-            const uint64_t key = src[e];
-            if ((uint32_t)(key >> 32) <= gt) {
-                const uint32_t slot = atomicAdd(&s_n, 1u);
-                if (slot < TC_FIN_NC) keys[slot] = key;
+        pre[l + 1] = c;
+    }
+    if (threadIdx.x == 0) pre[0] = 0;
+    __syncthreads();
+    if (warp == 0) {                             // inclusive scan of pre[1..L] by one warp (L <= 148 ... 512)
+        uint32_t carry = 0;
+        for (uint32_t base = 1; base <= L; base += 32) {
+            const uint32_t i = base + lane;
+            uint32_t v = i <= L ? pre[i] : 0;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+                if ((int)lane >= o) v += t;
             }
+            if (i <= L) pre[i] = v + carry;
+            carry += __shfl_sync(0xFFFFFFFFu, v, 31);
+        }
+    }
+    __syncthreads();
+    const uint32_t total = pre[L];
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+        uint32_t lo = 0, hi = L;                 // region l with pre[l] <= i < pre[l + 1]
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (pre[mid] <= i) lo = mid; else hi = mid;
+        }
+        const uint64_t key = f.cand[((size_t)q * L + lo) * f.cap_l + (i - pre[lo])];
+        if ((uint32_t)(key >> 32) <= gt) {
+            const uint32_t slot = atomicAdd(&s_n, 1u);
+            if (slot < TC_FIN_NC) keys[slot] = key;
         }
     }
     __syncthreads();
@@ -809,10 +902,10 @@ cudaError_t launch_sweep(K kern, const CUtensorMap &tmap_rows, const CUtensorMap
 
 }  // namespace
 
-size_t tc_smem_bytes(uint32_t dim, uint32_t stages)
+size_t tc_smem_bytes(uint32_t dim, uint32_t stages, uint32_t kbs)
 {
     size_t s = (size_t)(dim / TC_KB) * TC_M * 128;          // A
-    s += (size_t)stages * TC_STAGE_BYTES;                    // B ring
+    s += (size_t)stages * kbs * TC_STAGE_BYTES;              // B ring: stages of kbs K-blocks
     s += (size_t)(2 * stages + 2 * TC_ACC_STAGES + 1) * 8 + 16;
     return s;
 }
@@ -830,10 +923,10 @@ float tc_c_acc(uint32_t dim)
 
 cudaError_t launch_prep_queries(const float *d_q, uint32_t b, uint32_t b_pad, uint32_t dim, __half *d_qh, float *d_err,
                                 float *d_qnorm, uint32_t *d_gtau, uint32_t *d_flags, uint32_t *d_hist, uint32_t *d_arrive,
-                                uint32_t n_qtiles, uint32_t *d_nflag, cudaStream_t st)
+                                uint32_t n_qtiles, uint32_t *d_nflag, float *d_maxima, uint32_t nv, uint32_t nv_pad, cudaStream_t st)
 {
     prep_queries_kernel<<<b_pad, 128, 0, st>>>(d_q, b, dim, d_qh, d_err, d_qnorm, d_gtau, d_flags, d_hist, d_arrive,
-                                               n_qtiles, d_nflag);
+                                               n_qtiles, d_nflag, d_maxima, nv, nv_pad);
     count_launch();
     return cudaGetLastError();
 }

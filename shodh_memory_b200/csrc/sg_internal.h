@@ -42,14 +42,16 @@ struct TcArgs {
     uint32_t dim;
     uint32_t nq;              // live queries in this query tile (128 per tile; 256 in pair mode)
     uint32_t q_tile;          // which query tile
-    uint32_t stages;          // B ring depth
+    uint32_t stages;          // B ring depth (stages of kbs K-blocks each)
     uint32_t kk;              // candidates wanted per query (k + slack)
     uint32_t b_pad;           // padded query count: stride of the [value][query] sample array
-    uint32_t J;               // sample maxima each list contributes (n_lists * J >= kk)
+    uint32_t J;               // sample maxima each region contributes (n_lists * J >= kk, J <= 4)
     uint32_t cap_l;           // entries per (query, list) candidate region
+    uint32_t kbs;             // K-blocks per ring stage (1 or 2; divides dim / 64)
     const uint32_t *deleted;
     uint32_t *gtau;           // [b_pad] best threshold key published so far (0xFFFFFFFF = none)
-    float *maxima;            // [n_lists * J][b_pad] sample maxima
+    float *maxima;            // [b_pad][nv_pad] sample maxima (-inf padded); nv_pad = n_lists * J rounded up to 4
+    uint32_t nv_pad;
     uint32_t *arrive;         // [query tiles] CTAs that finished the sample phase (zeroed by prep)
     uint32_t *hist;           // [b_pad][TC_HIST] appended candidates per score bucket
     uint64_t *cand;           // [b_pad][n_lists][cap_l] unsorted approximate candidates
@@ -77,11 +79,12 @@ struct FinalizeArgs {
     unsigned long long *flag_total;  // cumulative statistics
     PushArgs push;            // certified queries are pushed to the peers right here
 };
-size_t tc_smem_bytes(uint32_t dim, uint32_t stages);
+size_t tc_smem_bytes(uint32_t dim, uint32_t stages, uint32_t kbs);
 float tc_c_acc(uint32_t dim);
 cudaError_t launch_prep_queries(const float *d_q, uint32_t b, uint32_t b_pad, uint32_t dim, __half *d_qh, float *d_err,
                                 float *d_qnorm, uint32_t *d_gtau, uint32_t *d_flags, uint32_t *d_hist, uint32_t *d_arrive,
-                                uint32_t n_qtiles, uint32_t *d_nflag, cudaStream_t st);
+                                uint32_t n_qtiles, uint32_t *d_nflag, float *d_maxima, uint32_t nv, uint32_t nv_pad,
+                                cudaStream_t st);
 cudaError_t launch_scan_tc(const CUtensorMap &tmap_rows, const CUtensorMap &tmap_q, const TcArgs &a, uint32_t grid,
                            size_t smem, cudaStream_t st);
 cudaError_t launch_scan_tc2(const CUtensorMap &tmap_rows, const CUtensorMap &tmap_q, const TcArgs &a, uint32_t grid,

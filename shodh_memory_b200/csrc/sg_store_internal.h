@@ -1,6 +1,8 @@
 // sg_store_internal.h -- the store object and the host helpers shared by store.cu and graph_api.cu.
 #pragma once
+#include <exception>
 #include <mutex>
+#include <new>
 #include <vector>
 
 #include "sg_internal.h"
@@ -81,6 +83,26 @@ struct sg_store {
 
 namespace sg {
 
+// C ABI bodies that allocate host memory run inside this: a C++ exception must never cross the extern "C" boundary
+template <typename F>
+int abi_guard(const char *what, F &&body)
+{
+    try {
+        return body();
+    } catch (const std::bad_alloc &) {
+        set_error("%s: out of host memory", what);
+        return SG_ERR_OOM;
+    } catch (const std::exception &e) {
+        set_error("%s: %s", what, e.what());
+        return SG_ERR_INVALID;
+    } catch (...) {
+        set_error("%s: unexpected exception", what);
+        return SG_ERR_INVALID;
+    }
+}
+
+// forget every row, deleted flag and graph edge (capacity is kept): roll-back of a failed load
+int store_truncate_locked(sg_store *s);
 int check_device(int device, int *sm_count);
 int grow_pinned(sg_store *s, size_t bytes);
 int ensure_rows(sg_store *s, uint64_t need_rows);

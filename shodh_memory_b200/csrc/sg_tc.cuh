@@ -5,6 +5,19 @@
 
 namespace sg {
 
+// one lane of a CONVERGED warp (the loop around it stays warp-uniform, so descriptors live in uniform registers;
+// an `if (lane == 0)` loop instead makes every tcgen05.mma operand a per-thread value that has to be re-broadcast)
+SG_DEVICE_INLINE bool elect_one_sync()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- tcgen05 wrappers ---------------------------------------------------------------------
 SG_DEVICE_INLINE void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 SG_DEVICE_INLINE void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -44,6 +57,22 @@ SG_DEVICE_INLINE void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+// same, with a fake read-modify-write of `dep`: code that consumes `dep` cannot be scheduled ABOVE this load, which
+// keeps the load of the NEXT chunk in front of the arithmetic on the current one (software double buffering)
+SG_DEVICE_INLINE void tmem_ld32_before(uint32_t taddr, uint32_t (&r)[32], uint32_t &dep)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%33];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+          "+r"(dep)
         : "r"(taddr)
         : "memory");
 }

@@ -14,7 +14,7 @@
 #include <cstring>
 #include <vector>
 
-#include "sg_internal.h"
+#include "sg_store_internal.h"
 
 namespace {
 
@@ -69,8 +69,11 @@ int span_parse_header(FILE *f, SpanInfo &si, int verify)
         sg::set_error("SPAN file without PQ: posting lists store only PQ codes, such an index cannot be searched (spann.rs:369-379)");
         return SG_ERR_UNSUPPORTED;
     }
-    if (si.centroids_off + (uint64_t)si.n_part * si.dim * 4 > si.file_size || si.codebook_off + 12 > si.file_size ||
-        si.index_off + (uint64_t)si.n_part * 12 > si.file_size || si.data_off > si.file_size) {
+    // every section must lie inside the file; products are formed in 128 bits so a hostile header cannot wrap them
+    auto fits = [&](uint64_t off, unsigned __int128 bytes) { return off <= si.file_size && bytes <= (unsigned __int128)(si.file_size - off); };
+    if (!fits(si.centroids_off, (unsigned __int128)si.n_part * si.dim * 4) || !fits(si.codebook_off, 12) ||
+        !fits(si.index_off, (unsigned __int128)si.n_part * 12) || si.data_off > si.file_size || si.n_part > (1u << 24) ||
+        si.dim == 0 || si.dim > 65536) {
         sg::set_error("SPAN file truncated (section offsets beyond %llu bytes)", (unsigned long long)si.file_size);
         return SG_ERR_INVALID;
     }
@@ -81,7 +84,9 @@ int span_parse_header(FILE *f, SpanInfo &si, int verify)
     si.kc = rd32(cb + 4);
     si.ds = rd32(cb + 8);
     if (si.m == 0 || si.ds == 0 || si.kc == 0 || si.kc > 256 || (uint64_t)si.m * si.ds != si.dim ||
-        si.codebook_off + 12 + (uint64_t)si.m * si.kc * si.ds * 4 > si.file_size) {
+        !fits(si.codebook_off + 12, (unsigned __int128)si.m * si.kc * si.ds * 4) ||
+        // a posting entry is a 4-byte id + m code bytes: num_vectors of them must fit behind data_off
+        !fits(si.data_off, (unsigned __int128)si.num_vectors * (4ull + si.m)) || si.num_vectors > 0xFFFFFFFEull) {
         sg::set_error("SPAN codebook section is inconsistent (%u subvectors x %u centroids x %u dims for dimension %u)", si.m,
                       si.kc, si.ds, si.dim);
         return SG_ERR_INVALID;
@@ -104,7 +109,17 @@ int span_parse_header(FILE *f, SpanInfo &si, int verify)
 
 extern "C" {
 
+static int sg_spann_file_inspect_impl(const char *path, int verify_checksum, uint64_t *num_vectors_out, uint32_t *num_partitions_out,
+                          uint32_t *dimension_out, uint32_t *num_subvectors_out, uint32_t *num_centroids_out,
+                          uint32_t *subvec_dim_out, uint32_t *metric_out);
 int sg_spann_file_inspect(const char *path, int verify_checksum, uint64_t *num_vectors_out, uint32_t *num_partitions_out,
+                          uint32_t *dimension_out, uint32_t *num_subvectors_out, uint32_t *num_centroids_out,
+                          uint32_t *subvec_dim_out, uint32_t *metric_out)
+{
+    return sg::abi_guard("sg_spann_file_inspect", [&] { return sg_spann_file_inspect_impl(path, verify_checksum, num_vectors_out, num_partitions_out, dimension_out, num_subvectors_out, num_centroids_out, subvec_dim_out, metric_out); });
+}
+
+static int sg_spann_file_inspect_impl(const char *path, int verify_checksum, uint64_t *num_vectors_out, uint32_t *num_partitions_out,
                           uint32_t *dimension_out, uint32_t *num_subvectors_out, uint32_t *num_centroids_out,
                           uint32_t *subvec_dim_out, uint32_t *metric_out)
 {
@@ -128,7 +143,15 @@ int sg_spann_file_inspect(const char *path, int verify_checksum, uint64_t *num_v
     return SG_OK;
 }
 
+static int sg_spann_file_read_impl(const char *path, float *centroids_out, float *pq_centroids_out, uint64_t *part_off_out, uint32_t *ids_out,
+                       uint8_t *codes_out);
 int sg_spann_file_read(const char *path, float *centroids_out, float *pq_centroids_out, uint64_t *part_off_out, uint32_t *ids_out,
+                       uint8_t *codes_out)
+{
+    return sg::abi_guard("sg_spann_file_read", [&] { return sg_spann_file_read_impl(path, centroids_out, pq_centroids_out, part_off_out, ids_out, codes_out); });
+}
+
+static int sg_spann_file_read_impl(const char *path, float *centroids_out, float *pq_centroids_out, uint64_t *part_off_out, uint32_t *ids_out,
                        uint8_t *codes_out)
 {
     if (!path || !centroids_out || !pq_centroids_out || !part_off_out) return SG_ERR_INVALID;
@@ -187,7 +210,17 @@ int sg_spann_file_read(const char *path, float *centroids_out, float *pq_centroi
     return SG_OK;
 }
 
+static int sg_spann_file_write_impl(const char *path, uint32_t dim, uint32_t num_partitions, uint32_t metric, const float *centroids,
+                        uint32_t num_subvectors, uint32_t num_centroids, uint32_t subvec_dim, const float *pq_centroids,
+                        const uint64_t *part_off, const uint32_t *ids, const uint8_t *codes);
 int sg_spann_file_write(const char *path, uint32_t dim, uint32_t num_partitions, uint32_t metric, const float *centroids,
+                        uint32_t num_subvectors, uint32_t num_centroids, uint32_t subvec_dim, const float *pq_centroids,
+                        const uint64_t *part_off, const uint32_t *ids, const uint8_t *codes)
+{
+    return sg::abi_guard("sg_spann_file_write", [&] { return sg_spann_file_write_impl(path, dim, num_partitions, metric, centroids, num_subvectors, num_centroids, subvec_dim, pq_centroids, part_off, ids, codes); });
+}
+
+static int sg_spann_file_write_impl(const char *path, uint32_t dim, uint32_t num_partitions, uint32_t metric, const float *centroids,
                         uint32_t num_subvectors, uint32_t num_centroids, uint32_t subvec_dim, const float *pq_centroids,
                         const uint64_t *part_off, const uint32_t *ids, const uint8_t *codes)
 {
@@ -278,7 +311,13 @@ int sg_spann_file_write(const char *path, uint32_t dim, uint32_t num_partitions,
     return SG_OK;
 }
 
+static int sg_spann_load_file_impl(sg_spann **out, int device, const char *path, uint32_t num_probes, int verify_checksum);
 int sg_spann_load_file(sg_spann **out, int device, const char *path, uint32_t num_probes, int verify_checksum)
+{
+    return sg::abi_guard("sg_spann_load_file", [&] { return sg_spann_load_file_impl(out, device, path, num_probes, verify_checksum); });
+}
+
+static int sg_spann_load_file_impl(sg_spann **out, int device, const char *path, uint32_t num_probes, int verify_checksum)
 {
     if (!out || !path) return SG_ERR_INVALID;
     *out = nullptr;
@@ -295,7 +334,13 @@ int sg_spann_load_file(sg_spann **out, int device, const char *path, uint32_t nu
                            off.data(), ids.data(), codes.data());
 }
 
+static int sg_spann_save_file_impl(sg_spann *s, const char *path);
 int sg_spann_save_file(sg_spann *s, const char *path)
+{
+    return sg::abi_guard("sg_spann_save_file", [&] { return sg_spann_save_file_impl(s, path); });
+}
+
+static int sg_spann_save_file_impl(sg_spann *s, const char *path)
 {
     if (!s || !path) return SG_ERR_INVALID;
     uint32_t P = 0;

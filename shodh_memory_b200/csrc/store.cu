@@ -293,6 +293,20 @@ int search_exact_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, u
     return SG_OK;
 }
 
+int store_truncate_locked(sg_store *s)
+{
+    SG_CUDA_TRY(cudaSetDevice(s->device));
+    SG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->n = 0;
+    s->n_deleted = 0;
+    s->graph_len = 0;
+    std::fill(s->h_deleted.begin(), s->h_deleted.end(), 0u);
+    if (s->d_deleted) SG_CUDA_TRY(cudaMemsetAsync(s->d_deleted, 0, s->h_deleted.size() * 4, s->stream));
+    SG_CUDA_TRY(cudaMemsetAsync(s->d_max_norm, 0, sizeof(float), s->stream));
+    SG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return SG_OK;
+}
+
 // see sg_store_internal.h
 int chain_begin(sg_store *s, cudaStream_t st)
 {
@@ -316,7 +330,7 @@ namespace {
 // tensor-core path B: approximate sweep + exact re-score + certification; uncertified queries are
 // re-run on path A.
 struct TcPlan {
-    uint32_t kk, stages, n_lists, grid, J, cap_l, qtile;
+    uint32_t kk, stages, kbs, units, n_lists, grid, J, cap_l, qtile;
     bool pair;
 };
 
@@ -334,7 +348,7 @@ bool tc_plan(const sg_store *s, uint32_t b, uint32_t k, TcPlan *p)
 {
     if (s->dtype != SG_DTYPE_F16 || s->dim % 64 != 0 || s->metric != SG_METRIC_NEG_DOT) return false;
     if (s->tc_mode == 1 || env_u32("SG_TC_DISABLE", 0)) return false;
-    if (b < (uint32_t)env_u32("SG_TC_MIN_B", 5)) return false;
+    if (b < (uint32_t)env_u32("SG_TC_MIN_B", 3)) return false;    // b = 3, 4: one tensor-core sweep (1.24 ms at 10M) beats the 4-query exact sweep (1.79 ms)
     if (k > 128 || s->n < 4096) return false;
     p->kk = tc_kk(k);
     const uint32_t kk_env = (uint32_t)env_u32("SG_TC_KK", 0);
@@ -346,17 +360,22 @@ bool tc_plan(const sg_store *s, uint32_t b, uint32_t k, TcPlan *p)
     const uint32_t rows_tile = p->pair ? 256 : 128;
     const uint64_t n_tiles = (s->n + rows_tile - 1) / rows_tile;
     const uint32_t units_max = p->pair ? (uint32_t)s->sm_count / 2 : (uint32_t)s->sm_count;   // clusters or CTAs
-    p->n_lists = (uint32_t)(n_tiles < units_max ? n_tiles : units_max);
-    p->grid = p->pair ? 2 * p->n_lists : p->n_lists;
-    // the sample: every list contributes the J best 32-row-chunk maxima of its first tile; kk distinct rows are needed
+    p->units = (uint32_t)(n_tiles < units_max ? n_tiles : units_max);
+    p->grid = p->pair ? 2 * p->units : p->units;
+    // every CTA (pair) keeps TWO candidate regions per query (one per epilogue warp group, each scanning every other
+    // 32-row chunk).  The sample: a region contributes the J best chunk maxima of its half of the unit's first tile.
+    p->n_lists = 2 * p->units;
     p->J = (p->kk + p->n_lists - 1) / p->n_lists;
-    if (p->J > rows_tile / 32) return false;
-    p->cap_l = p->kk <= 32 ? 64 : 256;
+    if (p->J > rows_tile / 64) return false;
+    p->cap_l = p->kk <= 32 ? 48 : 128;
     const uint32_t cap_env = (uint32_t)env_u32("SG_TC_CAP", 0);
     if (cap_env >= 8 && cap_env <= 4096) p->cap_l = cap_env;
-    const uint32_t st_max = (uint32_t)env_u32("SG_TC_STAGES", 8);
-    for (uint32_t stages = st_max < 3 ? 3 : (st_max > 8 ? 8 : st_max); stages >= 3; --stages) {
-        if (tc_smem_bytes(s->dim, stages) <= 227 * 1024) {
+    // ring: stages of kbs K-blocks (2 when the row has an even number of 64-element K-blocks), as many as fit
+    p->kbs = ((s->dim / 64) % 2 == 0 && env_u32("SG_TC_KBS", 2) >= 2) ? 2 : 1;
+    const uint32_t st_max = (uint32_t)env_u32("SG_TC_STAGES", 8) / p->kbs;
+    for (uint32_t stages = st_max < 2 ? 2 : (st_max > 8 ? 8 : st_max); stages >= 2; --stages) {
+        if (stages * p->kbs < 3) break;
+        if (tc_smem_bytes(s->dim, stages, p->kbs) <= 227 * 1024) {
             p->stages = stages;
             return true;
         }
@@ -387,14 +406,15 @@ int search_tc_chunk(sg_store *s, const TcPlan &pl, const float *d_q, uint32_t b,
     if ((rc = grow(s->d_arrive, s->arrive_cap, (size_t)n_qtiles)) != SG_OK) return rc;
     if ((rc = grow(s->d_cand, s->cand_cap_q, (size_t)b_pad * n_lists * pl.cap_l)) != SG_OK) return rc;
     if ((rc = grow(s->d_cnts, s->cnts_cap, (size_t)b_pad * n_lists)) != SG_OK) return rc;
-    if ((rc = grow(s->d_maxima, s->maxima_cap, (size_t)b_pad * n_lists * pl.J)) != SG_OK) return rc;
+    const uint32_t nv_pad = (n_lists * pl.J + 3) / 4 * 4;
+    if ((rc = grow(s->d_maxima, s->maxima_cap, (size_t)b_pad * nv_pad)) != SG_OK) return rc;
     CUtensorMap tmap_rows, tmap_q;
     if ((rc = encode_corpus_tmap(&tmap_rows, s->d_rows, true, s->dim, s->n, 128)) != SG_OK) return rc;
     if ((rc = encode_corpus_tmap(&tmap_q, s->d_qh, true, s->dim, b_pad, 128)) != SG_OK) return rc;
 
     SG_CUDA_TRY(launch_prep_queries(d_q, b, b_pad, s->dim, s->d_qh, s->d_qerr, s->d_qnorm, s->d_gtau, s->d_flags, s->d_hist,
-                                    s->d_arrive, n_qtiles, s->d_nflag, st));
-    const size_t smem = tc_smem_bytes(s->dim, pl.stages);
+                                    s->d_arrive, n_qtiles, s->d_nflag, s->d_maxima, n_lists * pl.J, nv_pad, st));
+    const size_t smem = tc_smem_bytes(s->dim, pl.stages, pl.kbs);
     const bool prof = s->profiling && 2 * (size_t)(s->ev_count + 1) <= s->ev.size();
     if (prof) SG_CUDA_TRY(cudaEventRecord(s->ev[2 * s->ev_count], st));
     for (uint32_t qt = 0; qt < n_qtiles; ++qt) {
@@ -408,9 +428,11 @@ int search_tc_chunk(sg_store *s, const TcPlan &pl, const float *d_q, uint32_t b,
         a.b_pad = b_pad;
         a.J = pl.J;
         a.cap_l = pl.cap_l;
+        a.kbs = pl.kbs;
         a.deleted = s->n_deleted ? s->d_deleted : nullptr;
         a.gtau = s->d_gtau;
         a.maxima = s->d_maxima;
+        a.nv_pad = nv_pad;
         a.arrive = s->d_arrive;
         a.hist = s->d_hist;
         a.cand = s->d_cand;
@@ -445,9 +467,9 @@ int search_tc_chunk(sg_store *s, const TcPlan &pl, const float *d_q, uint32_t b,
     f.qnorm = s->d_qnorm;
     f.max_row_norm = s->d_max_norm;
     f.c_acc = tc_c_acc(s->dim);
-    {   // rows staged per re-score round: keep q + rows within 44 KB of dynamic shared memory
+    {   // rows staged per re-score round: q + rows within 28 KB of dynamic shared memory (18.5 KB more are static)
         const size_t row_b = (size_t)(s->dim / 2 + 1) * 4, q_b = (size_t)s->dim * 4;
-        size_t rcn = (44 * 1024 - q_b) / row_b;
+        size_t rcn = (28 * 1024 - q_b) / row_b;
         f.rc = (uint32_t)(rcn > 32 ? 32 : (rcn < 1 ? 1 : rcn));
     }
     f.ids_out = d_ids;
@@ -973,8 +995,9 @@ int sg_debug_tc_scores(sg_store *s, const float *queries, uint32_t b, uint64_t f
     if (!s || !queries || !out || b == 0 || b > 256 || n_rows == 0) return SG_ERR_INVALID;
     std::lock_guard<std::mutex> g(s->mu);
     SG_CUDA_TRY(cudaSetDevice(s->device));
-    if (s->dtype != SG_DTYPE_F16 || s->dim % 64 != 0 || first_row + n_rows > s->n) {
-        set_error("sg_debug_tc_scores: needs an f16 store, dim %% 64 == 0 and a row range inside the store");
+    if (s->dtype != SG_DTYPE_F16 || s->dim % 64 != 0 || first_row + n_rows > s->n || tc_smem_bytes(s->dim, 3, 1) > 227 * 1024) {
+        set_error("sg_debug_tc_scores: needs an f16 store, dim %% 64 == 0, the query block within shared memory (dim <= 704) and a "
+                  "row range inside the store");
         return SG_ERR_UNSUPPORTED;
     }
     int rc = chain_begin(s, s->stream);
@@ -993,7 +1016,8 @@ int sg_debug_tc_scores(sg_store *s, const float *queries, uint32_t b, uint64_t f
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_q, queries, (size_t)b * s->dim * 4, cudaMemcpyHostToDevice, s->stream);
     if (e == cudaSuccess)
         e = launch_prep_queries(d_q, b, b_pad, s->dim, d_qh, d_e, d_e + b_pad, d_u, d_u + b_pad, d_u + 2 * b_pad,
-                                d_u + (size_t)b_pad * (2 + TC_HIST), 1, d_u + (size_t)b_pad * (2 + TC_HIST) + 4, s->stream);
+                                d_u + (size_t)b_pad * (2 + TC_HIST), 1, d_u + (size_t)b_pad * (2 + TC_HIST) + 4, nullptr, 0, 0,
+                                s->stream);
     rc = SG_OK;
     if (e == cudaSuccess) {
         const uint32_t rows_tile = pair ? 256 : 128;
@@ -1001,7 +1025,7 @@ int sg_debug_tc_scores(sg_store *s, const float *queries, uint32_t b, uint64_t f
         const uint32_t units = pair ? (uint32_t)s->sm_count / 2 : (uint32_t)s->sm_count;
         const uint32_t n_lists = (uint32_t)(n_tiles < units ? n_tiles : units);
         uint32_t stages = 8;
-        while (stages > 3 && tc_smem_bytes(s->dim, stages) > 227 * 1024) --stages;
+        while (stages > 3 && tc_smem_bytes(s->dim, stages, 1) > 227 * 1024) --stages;
         CUtensorMap tmap_rows, tmap_q;
         rc = encode_corpus_tmap(&tmap_rows, s->d_rows, true, s->dim, s->n, 128);
         if (rc == SG_OK) rc = encode_corpus_tmap(&tmap_q, d_qh, true, s->dim, b_pad, 128);
@@ -1011,12 +1035,13 @@ int sg_debug_tc_scores(sg_store *s, const float *queries, uint32_t b, uint64_t f
             a.dim = s->dim;
             a.nq = b;
             a.stages = stages;
+            a.kbs = 1;
             a.b_pad = b_pad;
             a.dump = d_out;
             a.dump_row0 = first_row;
             a.dump_rows = n_rows;
-            e = pair ? launch_scan_tc2(tmap_rows, tmap_q, a, 2 * n_lists, tc_smem_bytes(s->dim, stages), s->stream)
-                     : launch_scan_tc(tmap_rows, tmap_q, a, n_lists, tc_smem_bytes(s->dim, stages), s->stream);
+            e = pair ? launch_scan_tc2(tmap_rows, tmap_q, a, 2 * n_lists, tc_smem_bytes(s->dim, stages, 1), s->stream)
+                     : launch_scan_tc(tmap_rows, tmap_q, a, n_lists, tc_smem_bytes(s->dim, stages, 1), s->stream);
         }
     }
     if (rc == SG_OK && e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)b * n_rows * 4, cudaMemcpyDeviceToHost, s->stream);

@@ -53,6 +53,21 @@ def random_minilm_state_dict(seed: int = 0, layers: int = 6, hidden: int = 384, 
     return sd
 
 
+def pool_finalize(hidden_states, attention_mask, device: int = 0) -> np.ndarray:
+    """The tail of generate_embedding_onnx on the device (minilm.rs:959-978 masked mean-pool + :846-878 finalize_pooled):
+    hidden_states [b,L,H] f32, attention_mask [b,L] -> [b,H], bit-identical to the CPU path (sg_pool_finalize)."""
+    h = np.ascontiguousarray(hidden_states, np.float32)
+    m = np.ascontiguousarray(attention_mask, np.int64)
+    if h.ndim != 3 or m.shape != h.shape[:2]:
+        raise capi.SgError(capi.SG_ERR_DIM, f"expected [b,L,H] hidden states and a [b,L] mask, got {h.shape} / {m.shape}")
+    b, L, H = h.shape
+    out = np.empty((b, H), np.float32)
+    capi.check(capi.lib().sg_pool_finalize(device, h.ctypes.data_as(C.POINTER(C.c_float)),
+                                           m.ctypes.data_as(C.POINTER(C.c_int64)), b, L, H,
+                                           out.ctypes.data_as(C.POINTER(C.c_float))))
+    return out
+
+
 class GpuMiniLM:
     """`impl Embedder` on token ids: dimension(), encode_ids() (= encode / encode_batch after tokenising)."""
 

@@ -149,3 +149,31 @@ def test_batched_document_ingest_stays_on_the_device(model_and_encoder, sg):
     for i in (0, 17, 47):                                              # every document finds itself
         assert st.search(got[i], 1)[0][0] == i
     st.close()
+
+
+def test_pool_finalize_is_bit_identical_incl_scrub_and_epsilon_branches(sg, oracle):
+    """a3/a4 in isolation: f32 hidden states -> pool_norm_kernel vs oracle so_pool_finalize
+    (minilm.rs:959-978, :846-878), bit for bit, including the NaN/Inf scrub and the `norm > f32::EPSILON` divide."""
+    rng = np.random.default_rng(7)
+    b, L, H = 9, 23, 384
+    h = rng.standard_normal((b, L, H)).astype(np.float32)
+    mask = (rng.random((b, L)) < 0.7).astype(np.int64)
+    mask[:, 0] = 1
+    mask[1] = 0                                   # all-masked row: mask_sum == 0 -> zeros (empty text, minilm.rs:1123-1125)
+    h[2, 3, 10] = np.nan                          # NaN in a live position -> that component scrubbed to 0
+    h[3, 5, 20] = np.inf                          # +Inf -> scrubbed
+    h[3, 6, 21] = -np.inf
+    h[4, 2, 30], h[4, 4, 30] = np.inf, -np.inf    # Inf - Inf = NaN in the running sum -> scrubbed
+    h[5] *= 1e-12                                 # norm far below f32::EPSILON: no divide, values returned as pooled
+    h[6] *= np.float32(3e-9)                      # norm just around 1.19e-7
+    h[7] *= 1e30                                  # squares overflow: norm = +Inf -> divide gives 0 (and Inf/Inf never: values finite)
+    mask[8] = 1
+    mask[8, 7] = 2                                # only `== 1` counts (minilm.rs:962-966)
+    out = sg.pool_finalize(h, mask)
+    for i in range(b):
+        ref = oracle.pool_finalize(h[i], mask[i])
+        assert np.array_equal(out[i].view(np.uint32), ref.view(np.uint32)), i
+    assert not out[1].any()
+    n5 = float(np.linalg.norm(out[5].astype(np.float64)))
+    assert n5 < 1.2e-7                            # the EPSILON branch really was taken
+    assert abs(float(np.linalg.norm(out[0].astype(np.float64))) - 1.0) < 1e-5

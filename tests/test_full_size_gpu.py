@@ -62,7 +62,7 @@ def test_10m_reference_call_shape_k120(sg, oracle, big_store):
     """k = 120 (what search_ids asks for a top-10 recall): tensor-core path == exact sweep at 10M rows."""
     st = big_store
     b, k = 32, 120
-    queries, _ = oracle.synth_queries(SEED + 1, N, b, 384)
+    queries = oracle.synth_queries(SEED, N, 256 + b, 384)[0][256:]          # fresh queries of the same generator
     before = st.tc_stats()
     tc = st.search_batch(queries, k)
     after = st.tc_stats()
@@ -79,8 +79,9 @@ def test_10m_reference_call_shape_k120(sg, oracle, big_store):
 def test_10m_batch1_top100_equals_oracle(sg, oracle, big_store):
     """configs[2]: batch-1 top-100 (exact sweep, single query) at full size."""
     st = big_store
-    queries, near = oracle.synth_queries(SEED + 2, N, 2, 384)
-    ids, dist, cnt = st.search_batch(queries[1:2], 100)
-    rid, rdist, _ = oracle.brute_force_search_synth(SEED, N, queries[1:2], 100)
-    assert cnt[0] == 100 and ids[0, 0] == near[1]
+    queries, near = oracle.synth_queries(SEED, N, 400, 384)
+    q = queries[399:400]                                                     # odd index: planted next to row near[399]
+    ids, dist, cnt = st.search_batch(q, 100)
+    rid, rdist, _ = oracle.brute_force_search_synth(SEED, N, q, 100)
+    assert cnt[0] == 100 and ids[0, 0] == near[399]
     assert np.array_equal(ids, rid) and np.array_equal(dist.view(np.uint32), rdist.view(np.uint32))

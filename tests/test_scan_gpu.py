@@ -288,6 +288,7 @@ def test_search_device_pointers_and_profiling(sg, oracle):
     dist = torch.empty((4, 10), dtype=torch.float32, device="cuda")
     cnt = torch.empty(4, dtype=torch.int32, device="cuda")
     st.set_profiling(True)
+    st.set_tc_mode("exact")                            # 3 and 4 queries would take the tensor-core sweep by default
     before = sg.kernel_launch_count()
     st.search_device(dq.data_ptr(), 4, 10, ids.data_ptr(), dist.data_ptr(), cnt.data_ptr(),
                      torch.cuda.current_stream().cuda_stream)
@@ -302,7 +303,7 @@ def test_search_device_pointers_and_profiling(sg, oracle):
 
 
 def test_k_1024_and_large_k_batches(sg, oracle):
-    """Documented limit k <= 1024; k > 24 with b >= 5 takes the exact sweep in groups of 4 queries."""
+    """Documented limit k <= 1024; k > 128 (any b) takes the exact sweep in groups of 4 queries."""
     n = 6000
     corpus = oracle.synth_corpus(SEED, 0, n, 384)
     seen = oracle.round_f16(corpus)

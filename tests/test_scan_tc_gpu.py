@@ -244,7 +244,7 @@ def c_acc(dim):
     return 1.25 * (dim * 2.0 ** -23 + (dim // 4 + 4) * 2.0 ** -24)
 
 
-@pytest.mark.parametrize("dim,n,b", [(384, 400_000, 256), (2048, 24_000, 64)])
+@pytest.mark.parametrize("dim,n,b", [(384, 400_000, 256), (640, 24_000, 64)])
 def test_accumulation_error_bound(sg, oracle, dim, n, b):
     """MEASURE max |tensor-core score - reference-order dot| over >= 1e8 (query, row) pairs (dim 384) and
     compare it with the bound the certificate assumes, c_acc(dim) * |q| * |row|.  Queries are fp16-representable,
@@ -287,9 +287,10 @@ def test_accumulation_error_bound(sg, oracle, dim, n, b):
 
 
 def test_large_dim_tensor_path(sg, oracle):
-    """dim = 2048: the certificate coefficient grows with dim; results stay exact."""
+    """dim = 640 (the largest query block that leaves room for a 3-stage row ring; wider stores take the exact
+    sweep): the certificate coefficient is derived from dim; results stay exact."""
     rng = np.random.default_rng(2)
-    n, dim, b = 8192, 2048, 24
+    n, dim, b = 8192, 640, 24
     corpus = rng.standard_normal((n, dim)).astype(F)
     corpus /= np.linalg.norm(corpus, axis=1, keepdims=True)
     st = sg.GpuVectorStore(dim, "f16")
@@ -298,4 +299,17 @@ def test_large_dim_tensor_path(sg, oracle):
     before = st.tc_stats()[0]
     check_batch(oracle, st, oracle.round_f16(corpus), queries, 10)
     assert st.tc_stats()[0] - before == b
+    st.close()
+
+
+def test_wide_rows_fall_back_to_the_exact_sweep(sg, oracle):
+    """dim = 2048: the resident query block does not fit shared memory -> path A, still exact."""
+    rng = np.random.default_rng(3)
+    n, dim, b = 4096, 2048, 8
+    corpus = rng.standard_normal((n, dim)).astype(F)
+    st = sg.GpuVectorStore(dim, "f16")
+    st.add_vectors(corpus)
+    queries = rng.standard_normal((b, dim)).astype(F)
+    check_batch(oracle, st, oracle.round_f16(corpus), queries, 10)
+    assert st.tc_stats()[0] == 0
     st.close()

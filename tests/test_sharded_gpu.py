@@ -1,5 +1,6 @@
-"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): two ranks, row-sharded store, one NCCL
-all-gather of per-shard top-k, strided merge -- must equal the single-store result bit for bit."""
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): two ranks, row-sharded store, per-shard top-k exchanged
+(p2p: pushed by the result kernels + wait/merge kernel; nccl: all-gather + strided merge) -- the merged result must
+equal the CPU ORACLE's brute_force_search over the whole corpus bit for bit (ids, f32 distance bits, counts)."""
 import os
 import subprocess
 import sys
@@ -18,25 +19,30 @@ rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
 import shodh_memory_b200 as sg
-N, B, K, SEED = 300_000, 48, 10, 23821
+N, B, K, SEED = 300_000, 256, 10, 23821
 mode = os.environ.get("SG_TEST_EXCHANGE", "p2p")
 st = sg.ShardedGpuStore(N, 384, "f16", rank, world, rank, exchange=mode)
 assert st.exchange_mode == mode, st.exchange_mode
 st.fill_synthetic(SEED)
-g = torch.Generator().manual_seed(5)
-q = torch.nn.functional.normalize(torch.randn(B, 384, generator=g), dim=1)
+from oracle import oracle as o                         # the checker: CPU restatement of brute_force_search
+q_np, near = o.synth_queries(SEED, N, B, 384)
+q = torch.from_numpy(q_np)
 dq = q.cuda()
-for b, k in ((B, K), (1, 100), (3, 10), (B, K), (B, K)):     # repeats exercise the epoch / double buffering
+deleted = [int(near[1]), int(near[3]), 0, N // 2 - 1, N // 2, N - 1]   # both shards, incl. the shard boundary
+for d in deleted:
+    if st.lo <= d < st.hi:
+        st.local.mark_deleted(d - st.lo)
+seen = o.synth_corpus(SEED, 0, N, 384, f16_round=True) if rank == 0 else None
+# (b, k): tensor-core pair / 1-CTA sweeps, the reference's k = 120, exact-sweep shapes; repeats exercise the
+# epoch / double buffering of the exchange
+for b, k in ((B, K), (48, K), (1, 100), (3, 10), (B, 120), (B, K), (B, K), (200, 64)):
     ids, dst, cnt = st.search_device(dq[:b], k)
     torch.cuda.synchronize()
     if rank == 0:
-        ref = sg.GpuVectorStore(384, "f16", 0)
-        ref.append_synthetic(SEED, 0, N)
-        rid, rdist, rcnt = ref.search_batch(q[:b].numpy(), k)
+        rid, rdist, rcnt, _ = o.brute_force_search_batch(seen, q_np[:b], k, deleted=deleted, threads=len(os.sched_getaffinity(0)))
         assert np.array_equal(ids.cpu().numpy().view(np.uint32), rid), (b, k)
         assert np.array_equal(dst.cpu().numpy().view(np.uint32), rdist.view(np.uint32)), (b, k)
         assert np.array_equal(cnt.cpu().numpy().view(np.uint32), rcnt)
-        ref.close()
 h_ids, h_dist, h_cnt = st.search(q.pin_memory(), K)       # end-to-end host form (collective: all ranks)
 h_ids = h_ids.clone()
 ids, dst, cnt = st.search_device(dq, K); torch.cuda.synchronize()
