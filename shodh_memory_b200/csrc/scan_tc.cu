@@ -710,16 +710,15 @@ finalize_tc_kernel(const __grid_constant__ FinalizeArgs f)
     const uint32_t q = blockIdx.x;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t L = f.n_lists;
-    for (uint32_t i = threadIdx.x; i < f.dim; i += blockDim.x) q_s[i] = f.queries[(size_t)q * f.dim + i];
     if (threadIdx.x == 0) {
         s_flag = 0;
         s_n = 0;
     }
     __syncthreads();
     // (1) gather every candidate at or above the final shared threshold (a valid bound on the kk-th best, so at
-    //     least kk survive whenever a threshold was ever published).  The region counts are read first and
-    //     prefix-summed, then ALL threads walk the flat entry index: two dependent global round trips in total,
-    //     not two per region.
+    //     least kk survive whenever a threshold was ever published).  The region counts are read first (together
+    //     with the query: one global round trip) and prefix-summed, then ALL threads walk the flat entry index:
+    //     two dependent round trips in total, not two per region.
     const uint32_t gt = f.gtau[q];
     uint32_t *pre = reinterpret_cast<uint32_t *>(ekeys);          // [L + 1] prefix of min(count, cap_l); ekeys is free until (2)
     for (uint32_t l = threadIdx.x; l < L; l += blockDim.x) {
@@ -730,9 +729,10 @@ finalize_tc_kernel(const __grid_constant__ FinalizeArgs f)
         }
         pre[l + 1] = c;
     }
+    for (uint32_t i = threadIdx.x; i < f.dim; i += blockDim.x) q_s[i] = f.queries[(size_t)q * f.dim + i];
     if (threadIdx.x == 0) pre[0] = 0;
     __syncthreads();
-    if (warp == 0) {                             // inclusive scan of pre[1..L] by one warp (L <= 148 ... 512)
+    if (warp == 0) {                             // inclusive scan of pre[1..L] by one warp (L <= 296)
         uint32_t carry = 0;
         for (uint32_t base = 1; base <= L; base += 32) {
             const uint32_t i = base + lane;
@@ -765,13 +765,28 @@ finalize_tc_kernel(const __grid_constant__ FinalizeArgs f)
         n = TC_FIN_NC;
         if (threadIdx.x == 0) s_flag = 1u;
     }
-    const uint32_t M = next_pow2(n < 2 ? 2 : n);
-    for (uint32_t i = n + threadIdx.x; i < M; i += blockDim.x) keys[i] = KEY_SENTINEL;
-    __syncthreads();
-    block_bitonic_sort(keys, M);                 // ascending approx key: best approximate first
+    // sort the survivors ascending by approximate key (best first).  The usual case is a few dozen keys: a rank
+    // sort (every key counts the keys below it -- all distinct, ids are -- and goes to that slot of the upper half
+    // of the buffer) costs ONE barrier; the bitonic network with its log^2 barriers is kept for big sets.
+    uint64_t *sorted = keys;
+    if (n <= 512) {
+        sorted = keys + TC_FIN_NC / 2;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint64_t mine = keys[i];
+            uint32_t r = 0;
+            for (uint32_t j2 = 0; j2 < n; ++j2) r += keys[j2] < mine;
+            sorted[r] = mine;
+        }
+        __syncthreads();
+    } else {
+        const uint32_t M = next_pow2(n);
+        for (uint32_t i = n + threadIdx.x; i < M; i += blockDim.x) keys[i] = KEY_SENTINEL;
+        __syncthreads();
+        block_bitonic_sort(keys, M);
+    }
     const uint32_t kk = n < f.kk ? n : f.kk;     // the global top-kk by approximate score
     // weakest approximate similarity that was kept == bound on everything that was dropped
-    const float weakest_approx_sim = kk ? -key32_to_dist((uint32_t)(keys[kk - 1] >> 32)) : 0.0f;
+    const float weakest_approx_sim = kk ? -key32_to_dist((uint32_t)(sorted[kk - 1] >> 32)) : 0.0f;
     // (2) exact re-score, rc candidates per round: rows staged in shared memory with 16-byte loads (all in
     //     flight at once), then one thread per candidate walks the reference's sequential chain.  Row pitch
     //     dim/2 + 1 words: conflict-free.
@@ -780,14 +795,14 @@ finalize_tc_kernel(const __grid_constant__ FinalizeArgs f)
         const uint32_t nc = kk - c0 < f.rc ? kk - c0 : f.rc;
         for (uint32_t i = threadIdx.x; i < nc * vec_per_row; i += blockDim.x) {
             const uint32_t c = i / vec_per_row, v = i - c * vec_per_row;
-            const uint32_t row = (uint32_t)(keys[c0 + c] & 0xFFFFFFFFu);
+            const uint32_t row = (uint32_t)(sorted[c0 + c] & 0xFFFFFFFFu);
             const uint4 x = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(f.rows) + (size_t)row * f.dim) + v);
             uint32_t *dst = rows_s + (size_t)c * pitch + 4 * v;
             dst[0] = x.x; dst[1] = x.y; dst[2] = x.z; dst[3] = x.w;
         }
         __syncthreads();
         if (threadIdx.x < nc) {
-            const uint32_t row = (uint32_t)(keys[c0 + threadIdx.x] & 0xFFFFFFFFu);
+            const uint32_t row = (uint32_t)(sorted[c0 + threadIdx.x] & 0xFFFFFFFFu);
             const __half *rp = reinterpret_cast<const __half *>(rows_s + (size_t)threadIdx.x * pitch);
             const float dot = f.order == SG_ORDER_AVX2 ? exact_dot<SG_ORDER_AVX2>(q_s, rp, f.dim)
                                                        : exact_dot<SG_ORDER_SCALAR>(q_s, rp, f.dim);
@@ -795,10 +810,15 @@ finalize_tc_kernel(const __grid_constant__ FinalizeArgs f)
         }
         __syncthreads();
     }
-    const uint32_t M2 = next_pow2(kk < 2 ? 2 : kk);
-    for (uint32_t i = kk + threadIdx.x; i < M2; i += blockDim.x) ekeys[i] = KEY_SENTINEL;
+    // exact keys -> ascending (dist, id): rank sort into the lower half of `keys` (the approximate list is done with)
+    if (threadIdx.x < kk) {
+        const uint64_t mine = ekeys[threadIdx.x];
+        uint32_t r = 0;
+        for (uint32_t j2 = 0; j2 < kk; ++j2) r += ekeys[j2] < mine;
+        keys[r] = mine;
+    }
     __syncthreads();
-    block_bitonic_sort(ekeys, M2);
+    const uint64_t *fin = keys;
     const uint32_t out_n = kk < f.k ? kk : f.k;
     // (3) certification.  Rows that were not re-scored have approx sim <= weakest_approx_sim (survivors past
     //     the kk-th by the sort; everything else was below a threshold that never exceeded the kk-th best),
@@ -807,7 +827,7 @@ finalize_tc_kernel(const __grid_constant__ FinalizeArgs f)
     if (threadIdx.x == 0 && f.n_live > kk) {
         bool ok = false;
         if (kk == f.kk && out_n == f.k) {
-            const float kth_exact_sim = -key32_to_dist((uint32_t)(ekeys[f.k - 1] >> 32));
+            const float kth_exact_sim = -key32_to_dist((uint32_t)(fin[f.k - 1] >> 32));
             const float R = *f.max_row_norm;
             const float E = f.err[q] * R + f.c_acc * f.qnorm[q] * R;
             ok = kth_exact_sim > weakest_approx_sim + E;     // NaN compares false -> flagged
@@ -818,7 +838,7 @@ finalize_tc_kernel(const __grid_constant__ FinalizeArgs f)
     const bool flagged = s_flag != 0;
     for (uint32_t i = threadIdx.x; i < f.k; i += blockDim.x) {
         const bool valid = i < out_n;
-        const uint64_t key = valid ? ekeys[i] : KEY_SENTINEL;
+        const uint64_t key = valid ? fin[i] : KEY_SENTINEL;
         f.ids_out[(size_t)q * f.k + i] = valid ? (uint32_t)(key & 0xFFFFFFFFu) + f.id_base : 0xFFFFFFFFu;
         f.dist_out[(size_t)q * f.k + i] = valid ? key32_to_dist((uint32_t)(key >> 32)) : __uint_as_float(0x7F800000u);
     }
