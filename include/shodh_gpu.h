@@ -185,8 +185,10 @@ SG_API int sg_store_tc_stats(sg_store *s, uint64_t *queries_out, uint64_t *flagg
  * checks in tests/ and bench.py compare the tensor-core path against. */
 SG_API int sg_store_set_tc_mode(sg_store *s, int mode);
 /* Diagnostics for tests/test_scan_tc_gpu.py (not part of the drop-in surface): raw tensor-core scores and
- * exact reference-order dots of b queries against rows [first_row, first_row + n_rows) -> out [b, n_rows],
- * so the accumulation-error coefficient of the certificate can be MEASURED.  F16 stores; b <= 256 for tc. */
+ * exact reference-order dots of b queries against rows [first_row, first_row + n_rows), so the accumulation-error
+ * coefficient of the certificate can be MEASURED.  sg_debug_tc_scores writes out[n_rows][b] (row-major by corpus
+ * row: the layout the sweep's epilogue can store coalesced), sg_debug_exact_scores out[b][n_rows].  F16 stores;
+ * b <= 256 and dim <= 704 for the tensor-core form. */
 SG_API int sg_debug_tc_scores(sg_store *s, const float *queries_f32, uint32_t b, uint64_t first_row, uint64_t n_rows,
                               float *out);
 SG_API int sg_debug_exact_scores(sg_store *s, const float *queries_f32, uint32_t b, uint64_t first_row,

@@ -109,11 +109,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
 
+    // Producer and MMA issuer: the WHOLE warp walks the (uniform) loop and one elected lane issues, so the smem
+    // descriptors and barrier addresses live in uniform registers.  An `if (lane == 0)` loop makes them per-thread
+    // values that are re-broadcast for every tcgen05.mma: ~700 cycles of issue per K-block against the 256 cycles the
+    // four MMAs take -- the GEMMs of this encoder were issue-bound, not tensor-bound (measured on the corpus sweep).
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t st = 0, ph = 0;
-            for (uint32_t kb = 0; kb < nkb; ++kb) {
-                mbar_wait(smem_u32(empty_bar + st), ph ^ 1);
+        uint32_t st = 0, ph = 0;
+        for (uint32_t kb = 0; kb < nkb; ++kb) {
+            mbar_wait(smem_u32(empty_bar + st), ph ^ 1);
+            if (elect_one_sync()) {
                 mbar_arrive_expect_tx(smem_u32(full_bar + st), STAGE);
                 const uint32_t sa = smem_u32(smem + (size_t)st * STAGE);
                 tma_load_2d(sa, &tmap_a, smem_u32(full_bar + st), (int32_t)(kb * 64), (int32_t)m0);
@@ -121,16 +125,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 for (uint32_t h = 0; h < NSPLIT; ++h)
                     tma_load_2d(sa + A_BYTES + h * MMA_N * 128, &tmap_w, smem_u32(full_bar + st), (int32_t)(kb * 64),
                                 (int32_t)(n0 + h * MMA_N));
-                if (++st == S) { st = 0; ph ^= 1; }
             }
+            __syncwarp();
+            if (++st == S) { st = 0; ph ^= 1; }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(128, MMA_N);
-            uint32_t st = 0, ph = 0;
-            for (uint32_t kb = 0; kb < nkb; ++kb) {
-                mbar_wait(smem_u32(full_bar + st), ph);
-                tc_fence_after();
+        constexpr uint32_t idesc = make_idesc_f16(128, MMA_N);
+        uint32_t st = 0, ph = 0;
+        for (uint32_t kb = 0; kb < nkb; ++kb) {
+            mbar_wait(smem_u32(full_bar + st), ph);
+            tc_fence_after();
+            if (elect_one_sync()) {
                 const uint32_t sa = smem_u32(smem + (size_t)st * STAGE);
                 const uint64_t da = make_sw128_desc(sa);
 #pragma unroll
@@ -141,9 +146,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         umma_f16(tmem_base + h * MMA_N, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
                 }
                 umma_commit(smem_u32(empty_bar + st));
-                if (++st == S) { st = 0; ph ^= 1; }
+                if (kb + 1 == nkb) umma_commit(smem_u32(done_bar));
             }
-            umma_commit(smem_u32(done_bar));
+            __syncwarp();
+            if (++st == S) { st = 0; ph ^= 1; }
         }
     } else if (warp >= 4) {
         // epilogue: thread t <-> output row m0 + t <-> TMEM lane t
@@ -297,33 +303,35 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t m0 = (blockIdx.x / 3) * 128, n0 = crank * BN;
 
-    if (warp == 0) {
-        if (lane == 0) {
-            uint32_t st = 0, ph = 0;
-            for (uint32_t kb = 0; kb < nkb; ++kb) {
-                mbar_wait(smem_u32(empty_bar + st), ph ^ 1);
+    if (warp == 0) {                                      // warp-uniform loops, one elected lane issues (see gemm_tc_kernel)
+        uint32_t st = 0, ph = 0;
+        for (uint32_t kb = 0; kb < nkb; ++kb) {
+            mbar_wait(smem_u32(empty_bar + st), ph ^ 1);
+            if (elect_one_sync()) {
                 mbar_arrive_expect_tx(smem_u32(full_bar + st), STAGE);
                 const uint32_t sa = smem_u32(smem + (size_t)st * STAGE);
                 tma_load_2d(sa, &tmap_a, smem_u32(full_bar + st), (int32_t)(kb * 64), (int32_t)m0);
                 tma_load_2d(sa + A_BYTES, &tmap_w, smem_u32(full_bar + st), (int32_t)(kb * 64), (int32_t)n0);
-                if (++st == S) { st = 0; ph ^= 1; }
             }
+            __syncwarp();
+            if (++st == S) { st = 0; ph ^= 1; }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(128, BN);
-            uint32_t st = 0, ph = 0;
-            for (uint32_t kb = 0; kb < nkb; ++kb) {
-                mbar_wait(smem_u32(full_bar + st), ph);
-                tc_fence_after();
+        constexpr uint32_t idesc = make_idesc_f16(128, BN);
+        uint32_t st = 0, ph = 0;
+        for (uint32_t kb = 0; kb < nkb; ++kb) {
+            mbar_wait(smem_u32(full_bar + st), ph);
+            tc_fence_after();
+            if (elect_one_sync()) {
                 const uint32_t sa = smem_u32(smem + (size_t)st * STAGE);
                 const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + A_BYTES);
 #pragma unroll
                 for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
                 umma_commit(smem_u32(empty_bar + st));
-                if (++st == S) { st = 0; ph ^= 1; }
+                if (kb + 1 == nkb) umma_commit(smem_u32(done_bar));
             }
-            umma_commit(smem_u32(done_bar));
+            __syncwarp();
+            if (++st == S) { st = 0; ph ^= 1; }
         }
     }
     float sum = 0.0f, sq = 0.0f;
@@ -465,41 +473,43 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     const uint32_t total = m_tiles * n_tiles;
     const uint32_t my_tiles = blockIdx.x < total ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    if (warp == 0) {
-        if (lane == 0) {
-            uint32_t st = 0, ph = 0;
-            for (uint32_t i = 0; i < my_tiles; ++i) {
-                const uint32_t tile = blockIdx.x + i * gridDim.x, m0 = (tile / n_tiles) * 128, n0 = (tile % n_tiles) * BN;
-                for (uint32_t kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(smem_u32(empty_bar + st), ph ^ 1);
+    if (warp == 0) {                                      // warp-uniform loops, one elected lane issues (see gemm_tc_kernel)
+        uint32_t st = 0, ph = 0;
+        for (uint32_t i = 0; i < my_tiles; ++i) {
+            const uint32_t tile = blockIdx.x + i * gridDim.x, m0 = (tile / n_tiles) * 128, n0 = (tile % n_tiles) * BN;
+            for (uint32_t kb = 0; kb < nkb; ++kb) {
+                mbar_wait(smem_u32(empty_bar + st), ph ^ 1);
+                if (elect_one_sync()) {
                     mbar_arrive_expect_tx(smem_u32(full_bar + st), STAGE);
                     const uint32_t sa = smem_u32(smem + (size_t)st * STAGE);
                     tma_load_2d(sa, &tmap_a, smem_u32(full_bar + st), (int32_t)(kb * 64), (int32_t)m0);
                     tma_load_2d(sa + A_BYTES, &tmap_w, smem_u32(full_bar + st), (int32_t)(kb * 64), (int32_t)n0);
-                    if (++st == S) { st = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                if (++st == S) { st = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(128, BN);
-            uint32_t st = 0, ph = 0;
-            for (uint32_t i = 0; i < my_tiles; ++i) {
-                const uint32_t acc = i & 1, acc_ph = (i >> 1) & 1;
-                mbar_wait(smem_u32(tempty_bar + acc), acc_ph ^ 1);
+        constexpr uint32_t idesc = make_idesc_f16(128, BN);
+        uint32_t st = 0, ph = 0;
+        for (uint32_t i = 0; i < my_tiles; ++i) {
+            const uint32_t acc = i & 1, acc_ph = (i >> 1) & 1;
+            mbar_wait(smem_u32(tempty_bar + acc), acc_ph ^ 1);
+            tc_fence_after();
+            for (uint32_t kb = 0; kb < nkb; ++kb) {
+                mbar_wait(smem_u32(full_bar + st), ph);
                 tc_fence_after();
-                for (uint32_t kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(smem_u32(full_bar + st), ph);
-                    tc_fence_after();
+                if (elect_one_sync()) {
                     const uint32_t sa = smem_u32(smem + (size_t)st * STAGE);
                     const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + A_BYTES);
 #pragma unroll
                     for (uint32_t k = 0; k < 4; ++k)
                         umma_f16(tmem_base + acc * BN, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
                     umma_commit(smem_u32(empty_bar + st));
-                    if (++st == S) { st = 0; ph ^= 1; }
+                    if (kb + 1 == nkb) umma_commit(smem_u32(tfull_bar + acc));
                 }
-                umma_commit(smem_u32(tfull_bar + acc));
+                __syncwarp();
+                if (++st == S) { st = 0; ph ^= 1; }
             }
         }
     } else if (warp >= 4) {
@@ -1037,6 +1047,20 @@ struct sg_encoder {
     size_t cap_b = 0;
     void *h_pinned = nullptr;
     size_t pinned_cap = 0;
+    // CUDA graphs of whole forwards for small batches (the single-query recall path is ~30 tiny launches:
+    // launch gaps, not kernels, set its latency).  Keyed by shape AND buffer addresses; dropped when buffers regrow.
+    struct Graph {
+        uint32_t b = 0, L = 0;
+        const void *ids = nullptr, *mask = nullptr;
+        void *out = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        uint32_t launches = 0;
+        bool failed = false;
+        uint64_t last_use = 0;
+    };
+    std::vector<Graph> graphs;
+    uint64_t graph_clock = 0;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;   // fence the caller's legacy default stream around a graph launch
 };
 
 namespace {
@@ -1297,6 +1321,97 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
     return SG_OK;
 }
 
+// small batches: replay a captured graph of the whole forward (first call of a shape runs plainly and grows the
+// buffers, the second captures, later ones replay)
+int encode_device_graphed(sg_encoder *e, const int64_t *d_ids, const int64_t *d_mask, uint32_t b, uint32_t L, float *d_out,
+                          cudaStream_t caller)
+{
+    static const bool enabled = [] {
+        const char *v = getenv("SG_ENC_GRAPH");
+        return !(v && *v && atoi(v) == 0);
+    }();
+    const uint32_t T_pad = (b * L + 127) / 128 * 128;
+    if (!enabled || T_pad > 2048) return encode_device_locked(e, d_ids, d_mask, b, L, d_out, caller);
+    // the legacy default stream cannot be captured: graphs for such callers live on the encoder's own stream,
+    // fenced by two events so the call keeps its in-order meaning on the caller's stream
+    const bool legacy = caller == nullptr || caller == cudaStreamLegacy || caller == cudaStreamPerThread;
+    cudaStream_t st = legacy ? e->stream : caller;
+    if (legacy && !e->ev_in) {
+        SG_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
+        SG_CUDA_TRY(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
+    }
+    const size_t cap_before = e->cap_tokens;
+    sg_encoder::Graph *hit = nullptr;
+    for (auto &g : e->graphs)
+        if (g.b == b && g.L == L && g.ids == d_ids && g.mask == d_mask && g.out == d_out) hit = &g;
+    auto launch = [&](cudaGraphExec_t exec) -> int {
+        if (legacy) {
+            SG_CUDA_TRY(cudaEventRecord(e->ev_in, caller));
+            SG_CUDA_TRY(cudaStreamWaitEvent(st, e->ev_in, 0));
+        }
+        SG_CUDA_TRY(cudaGraphLaunch(exec, st));
+        if (legacy) {
+            SG_CUDA_TRY(cudaEventRecord(e->ev_out, st));
+            SG_CUDA_TRY(cudaStreamWaitEvent(caller, e->ev_out, 0));
+        }
+        return SG_OK;
+    };
+    if (hit && hit->exec) {
+        hit->last_use = ++e->graph_clock;
+        count_launch(hit->launches);
+        return launch(hit->exec);
+    }
+    if (!hit || hit->failed || T_pad > e->cap_tokens) {
+        const int rc = encode_device_locked(e, d_ids, d_mask, b, L, d_out, caller);
+        if (e->cap_tokens != cap_before) {           // activations moved: every captured graph points at freed memory
+            for (auto &g : e->graphs)
+                if (g.exec) cudaGraphExecDestroy(g.exec);
+            e->graphs.clear();
+            hit = nullptr;
+        }
+        if (rc == SG_OK && !hit) {
+            if (e->graphs.size() >= 8) {             // evict the least recently used
+                size_t lru = 0;
+                for (size_t i = 1; i < e->graphs.size(); ++i)
+                    if (e->graphs[i].last_use < e->graphs[lru].last_use) lru = i;
+                if (e->graphs[lru].exec) cudaGraphExecDestroy(e->graphs[lru].exec);
+                e->graphs.erase(e->graphs.begin() + lru);
+            }
+            sg_encoder::Graph g;
+            g.b = b; g.L = L; g.ids = d_ids; g.mask = d_mask; g.out = d_out;
+            g.last_use = ++e->graph_clock;
+            e->graphs.push_back(g);
+        }
+        return rc;
+    }
+    // second sighting of this (shape, buffers): capture
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+        hit->failed = true;                          // the caller is capturing itself: stay out of its way
+        cudaGetLastError();
+        return encode_device_locked(e, d_ids, d_mask, b, L, d_out, caller);
+    }
+    const uint64_t l0 = sg_kernel_launch_count();
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    int rc = SG_OK;
+    if (ce == cudaSuccess) {
+        rc = encode_device_locked(e, d_ids, d_mask, b, L, d_out, st);
+        ce = cudaStreamEndCapture(st, &graph);
+    }
+    if (ce == cudaSuccess && rc == SG_OK && graph) ce = cudaGraphInstantiate(&hit->exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (ce != cudaSuccess || rc != SG_OK || !hit->exec) {
+        cudaGetLastError();
+        hit->exec = nullptr;
+        hit->failed = true;
+        return encode_device_locked(e, d_ids, d_mask, b, L, d_out, caller);
+    }
+    hit->launches = (uint32_t)(sg_kernel_launch_count() - l0);
+    hit->last_use = ++e->graph_clock;
+    return launch(hit->exec);
+}
+
 }  // namespace
 
 extern "C" {
@@ -1383,6 +1498,10 @@ void sg_encoder_destroy(sg_encoder *e)
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    for (auto &g : e->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (e->ev_in) cudaEventDestroy(e->ev_in);
+    if (e->ev_out) cudaEventDestroy(e->ev_out);
     for (void *p : e->allocs) cudaFree(p);
     cudaFree(e->h0); cudaFree(e->h1); cudaFree(e->qkv); cudaFree(e->ctx); cudaFree(e->mid); cudaFree(e->hf32);
     cudaFree(e->d_ids); cudaFree(e->d_mask); cudaFree(e->d_emb);
@@ -1444,7 +1563,7 @@ int sg_encoder_encode_device(sg_encoder *e, const int64_t *d_ids, const int64_t 
     }
     std::lock_guard<std::mutex> g(e->mu);
     SG_CUDA_TRY(cudaSetDevice(e->device));
-    return encode_device_locked(e, d_ids, d_mask, b, L, d_emb_out, static_cast<cudaStream_t>(cuda_stream));
+    return encode_device_graphed(e, d_ids, d_mask, b, L, d_emb_out, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int sg_encoder_encode(sg_encoder *e, const int64_t *ids, const int64_t *mask, uint32_t b, uint32_t L, float *emb_out)
@@ -1478,7 +1597,7 @@ int sg_encoder_encode(sg_encoder *e, const int64_t *ids, const int64_t *mask, ui
     memcpy(hp + n * 8, mask, n * 8);
     SG_CUDA_TRY(cudaMemcpyAsync(e->d_ids, hp, n * 8, cudaMemcpyHostToDevice, e->stream));
     SG_CUDA_TRY(cudaMemcpyAsync(e->d_mask, hp + n * 8, n * 8, cudaMemcpyHostToDevice, e->stream));
-    int rc = encode_device_locked(e, e->d_ids, e->d_mask, b, L, e->d_emb, e->stream);
+    int rc = encode_device_graphed(e, e->d_ids, e->d_mask, b, L, e->d_emb, e->stream);
     if (rc != SG_OK) return rc;
     SG_CUDA_TRY(cudaMemcpyAsync(hp + 2 * n * 8, e->d_emb, ob, cudaMemcpyDeviceToHost, e->stream));
     SG_CUDA_TRY(cudaStreamSynchronize(e->stream));

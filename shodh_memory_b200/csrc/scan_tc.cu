@@ -64,6 +64,12 @@ SG_DEVICE_INLINE uint32_t ld_acquire_gpu_u32(const uint32_t *p)
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+SG_DEVICE_INLINE unsigned long long gtimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 SG_DEVICE_INLINE void epi_bar_sync()      // the 256 epilogue threads only (named barrier 1)
 {
     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -135,6 +141,9 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
         return fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
     };
 
+    const bool tr = a.trace != nullptr && e == 0;
+    unsigned long long *trp = a.trace + (size_t)blockIdx.x * 8;
+    if (tr) trp[0] = gtimer();                       // epilogue entered (prologue: barriers, TMEM, query block)
     uint64_t it = 1;
     if constexpr (!DUMP) {
         // ===== sample pass (iteration 0): the J best chunk maxima of this thread's chunks of the unit's first tile =====
@@ -144,6 +153,7 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
         if (my_tiles) {
             mbar_wait(smem_u32(tfull_bar), 0);
             tc_fence_after();
+            if (tr) trp[1] = gtimer();               // sample tile's accumulator ready
 #pragma unroll 1
             for (uint32_t c = grp; c < NCH; c += 2) {
                 uint32_t r[32];
@@ -167,12 +177,31 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
             tc_fence_before();
             mbar_arrive_cluster(tempty_cluster_addr);        // accumulator stage 0 is free again
         }
-        if (active) {
+        // the unit's sample = the 4 best chunk maxima over BOTH groups' chunks: group 1 hands its list to group 0
+        float4 *xchg = reinterpret_cast<float4 *>(s_ctl + 4);            // [128] float4, shared by the two groups
+        if (grp == 1) xchg[t] = make_float4(m[0], m[1], m[2], m[3]);
+        epi_bar_sync();
+        if (grp == 0) {
+            const float4 o = xchg[t];
+            const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-            for (uint32_t j = 0; j < 4; ++j)
-                if (j < a.J) a.maxima[(size_t)q * a.nv_pad + list_idx * a.J + j] = m[j];
+            for (int jj = 0; jj < 4; ++jj) {
+                float mx = ov[jj];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float hi = fmaxf(m[i], mx);
+                    mx = fminf(m[i], mx);
+                    m[i] = hi;
+                }
+            }
+            if (active) {
+#pragma unroll
+                for (uint32_t j = 0; j < 4; ++j)
+                    if (j < a.J) a.maxima[(size_t)q * a.nv_pad + unit_idx * a.J + j] = m[j];
+            }
         }
         // device-wide meeting point: every CTA of the grid publishes its sample, then reads all of them
+        if (tr) trp[2] = gtimer();                   // sample scanned
         __threadfence();
         epi_bar_sync();
         if (e == 0) {
@@ -189,7 +218,8 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
         }
         epi_bar_sync();
         __threadfence();
-        if (active && s_ctl[0]) {
+        if (tr) trp[3] = gtimer();                   // every CTA has arrived
+        if (grp == 0 && active && s_ctl[0]) {
             // this query's sample values are contiguous ([query][value], padded with -inf to a multiple of 4): 16-byte
             // loads, all independent -- a scalar, strided walk of ~300 values was a 60 us latency chain at kernel start
             float mn = -TC_NEG_INF, sum = 0.0f;
@@ -246,6 +276,14 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
                 }
             }
         }
+        // group 0 computed the query's seed; group 1 takes it over (identical thresholds and bucket mapping)
+        if (grp == 0) xchg[t] = make_float4(tau0, w, inv_w, use_hist ? 1.0f : 0.0f);
+        epi_bar_sync();
+        if (grp == 1 && active) {
+            const float4 sd = xchg[t];
+            tau0 = sd.x; w = sd.y; inv_w = sd.z; use_hist = sd.w != 0.0f;
+            tau_f = tau0;
+        }
     }
 
     // ===== the sweep proper =====
@@ -257,6 +295,7 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
     uint32_t g_pend = 0xFFFFFFFFu;
     uint4 h_pend[TC_HIST / 4];
     bool h_valid = false;
+    if (tr) trp[4] = gtimer();                       // seeds computed
     for (; it <= my_tiles; ++it) {
         const uint64_t tile = tile_of_iter(tile0, tile_stride, it);
         if constexpr (!DUMP) {
@@ -299,7 +338,7 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
                     for (uint32_t j = 0; j < 32; ++j) {
                         const uint64_t row = row0 + j;
                         if (row >= a.dump_row0 && row < a.dump_row0 + a.dump_rows && row < a.n_rows)
-                            a.dump[(size_t)q * a.dump_rows + (row - a.dump_row0)] = __uint_as_float(r[j]);
+                            a.dump[(size_t)(row - a.dump_row0) * a.nq + q] = __uint_as_float(r[j]);   // [row][query]: coalesced
                     }
                 }
                 continue;
@@ -335,6 +374,7 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
         }
         tc_fence_before();
         mbar_arrive_cluster(tempty_cluster_addr + 8 * accn);  // all epilogue threads release the accumulator
+        if (tr && it <= 2) trp[4 + it] = gtimer();   // first two tiles of the sweep scanned
         if (++accn == acc_stages) {
             accn = 0;
             acc_ph ^= 1;
@@ -352,6 +392,7 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
     if constexpr (!DUMP) {
         if (active) a.cnts[(size_t)q * n_lists + list_idx] = my_cnt;
     }
+    if (tr) trp[7] = gtimer();                       // sweep done
 }
 
 // ---- K1: the sweep, one CTA per SM (128 queries per sweep) ------------------------------------------
@@ -375,7 +416,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
     uint64_t *tempty_bar = tfull_bar + TC_ACC_STAGES;  // [TC_ACC_STAGES]
     uint64_t *a_bar = tempty_bar + TC_ACC_STAGES;    // [1]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_bar + 1);
-    uint32_t *s_ctl = tmem_slot + 1;
+    uint32_t *s_ctl = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~static_cast<uintptr_t>(15));   // [4] control + [128] float4
 
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < S; ++i) {
@@ -515,7 +556,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_cons
     uint64_t *tempty_bar = tfull_bar + TC_ACC_STAGES;               // same carve-up as the 1-CTA form (ACC2 used)
     uint64_t *a_bar = tempty_bar + TC_ACC_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_bar + 1);
-    uint32_t *s_ctl = tmem_slot + 1;
+    uint32_t *s_ctl = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~static_cast<uintptr_t>(15));   // [4] control + [128] float4
 
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < S; ++i) {
@@ -927,6 +968,7 @@ size_t tc_smem_bytes(uint32_t dim, uint32_t stages, uint32_t kbs)
     size_t s = (size_t)(dim / TC_KB) * TC_M * 128;          // A
     s += (size_t)stages * kbs * TC_STAGE_BYTES;              // B ring: stages of kbs K-blocks
     s += (size_t)(2 * stages + 2 * TC_ACC_STAGES + 1) * 8 + 16;
+    s += 16 + 128 * 16;                                      // control words + the epilogue groups' exchange buffer
     return s;
 }
 

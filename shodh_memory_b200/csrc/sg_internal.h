@@ -56,7 +56,8 @@ struct TcArgs {
     uint32_t *hist;           // [b_pad][TC_HIST] appended candidates per score bucket
     uint64_t *cand;           // [b_pad][n_lists][cap_l] unsorted approximate candidates
     uint32_t *cnts;           // [b_pad][n_lists] entries appended (may exceed cap_l: overflow)
-    float *dump;              // diagnostics only: raw accumulators [nq][dump_rows] (null in production)
+    unsigned long long *trace; // diagnostics only (SG_TC_TRACE=1): [gridDim.x][8] globaltimer stamps of the epilogue's phases
+    float *dump;              // diagnostics only: raw accumulators [dump_rows][nq] (null in production)
     uint64_t dump_row0, dump_rows;
 };
 struct FinalizeArgs {

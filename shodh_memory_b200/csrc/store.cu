@@ -363,10 +363,10 @@ bool tc_plan(const sg_store *s, uint32_t b, uint32_t k, TcPlan *p)
     p->units = (uint32_t)(n_tiles < units_max ? n_tiles : units_max);
     p->grid = p->pair ? 2 * p->units : p->units;
     // every CTA (pair) keeps TWO candidate regions per query (one per epilogue warp group, each scanning every other
-    // 32-row chunk).  The sample: a region contributes the J best chunk maxima of its half of the unit's first tile.
+    // 32-row chunk).  The sample: a unit contributes the J <= 4 best chunk maxima of its first tile.
     p->n_lists = 2 * p->units;
-    p->J = (p->kk + p->n_lists - 1) / p->n_lists;
-    if (p->J > rows_tile / 64) return false;
+    p->J = (p->kk + p->units - 1) / p->units;
+    if (p->J > 4 || p->J > rows_tile / 32) return false;
     p->cap_l = p->kk <= 32 ? 48 : 128;
     const uint32_t cap_env = (uint32_t)env_u32("SG_TC_CAP", 0);
     if (cap_env >= 8 && cap_env <= 4096) p->cap_l = cap_env;
@@ -406,15 +406,21 @@ int search_tc_chunk(sg_store *s, const TcPlan &pl, const float *d_q, uint32_t b,
     if ((rc = grow(s->d_arrive, s->arrive_cap, (size_t)n_qtiles)) != SG_OK) return rc;
     if ((rc = grow(s->d_cand, s->cand_cap_q, (size_t)b_pad * n_lists * pl.cap_l)) != SG_OK) return rc;
     if ((rc = grow(s->d_cnts, s->cnts_cap, (size_t)b_pad * n_lists)) != SG_OK) return rc;
-    const uint32_t nv_pad = (n_lists * pl.J + 3) / 4 * 4;
+    const uint32_t nv_pad = (pl.units * pl.J + 3) / 4 * 4;
     if ((rc = grow(s->d_maxima, s->maxima_cap, (size_t)b_pad * nv_pad)) != SG_OK) return rc;
     CUtensorMap tmap_rows, tmap_q;
     if ((rc = encode_corpus_tmap(&tmap_rows, s->d_rows, true, s->dim, s->n, 128)) != SG_OK) return rc;
     if ((rc = encode_corpus_tmap(&tmap_q, s->d_qh, true, s->dim, b_pad, 128)) != SG_OK) return rc;
 
     SG_CUDA_TRY(launch_prep_queries(d_q, b, b_pad, s->dim, s->d_qh, s->d_qerr, s->d_qnorm, s->d_gtau, s->d_flags, s->d_hist,
-                                    s->d_arrive, n_qtiles, s->d_nflag, s->d_maxima, n_lists * pl.J, nv_pad, st));
+                                    s->d_arrive, n_qtiles, s->d_nflag, s->d_maxima, pl.units * pl.J, nv_pad, st));
     const size_t smem = tc_smem_bytes(s->dim, pl.stages, pl.kbs);
+    unsigned long long *d_trace = nullptr;           // SG_TC_TRACE=1: phase stamps of the sweep, printed to stderr (debug)
+    const bool trace = env_u32("SG_TC_TRACE", 0) != 0;
+    if (trace) {
+        SG_CUDA_TRY(cudaMalloc(&d_trace, (size_t)pl.grid * 8 * 8));
+        SG_CUDA_TRY(cudaMemsetAsync(d_trace, 0, (size_t)pl.grid * 8 * 8, st));
+    }
     const bool prof = s->profiling && 2 * (size_t)(s->ev_count + 1) <= s->ev.size();
     if (prof) SG_CUDA_TRY(cudaEventRecord(s->ev[2 * s->ev_count], st));
     for (uint32_t qt = 0; qt < n_qtiles; ++qt) {
@@ -437,6 +443,7 @@ int search_tc_chunk(sg_store *s, const TcPlan &pl, const float *d_q, uint32_t b,
         a.hist = s->d_hist;
         a.cand = s->d_cand;
         a.cnts = s->d_cnts;
+        a.trace = d_trace;
         cudaError_t e = pl.pair ? launch_scan_tc2(tmap_rows, tmap_q, a, pl.grid, smem, st)
                                 : launch_scan_tc(tmap_rows, tmap_q, a, pl.grid, smem, st);
         if (e != cudaSuccess) {
@@ -448,6 +455,22 @@ int search_tc_chunk(sg_store *s, const TcPlan &pl, const float *d_q, uint32_t b,
     if (prof) {
         SG_CUDA_TRY(cudaEventRecord(s->ev[2 * s->ev_count + 1], st));
         ++s->ev_count;
+    }
+    if (trace) {
+        std::vector<unsigned long long> h((size_t)pl.grid * 8);
+        SG_CUDA_TRY(cudaStreamSynchronize(st));
+        SG_CUDA_TRY(cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost));
+        cudaFree(d_trace);
+        unsigned long long t0 = ~0ull, mx[8] = {0};
+        for (uint32_t c = 0; c < pl.grid; ++c)
+            if (h[(size_t)c * 8] && h[(size_t)c * 8] < t0) t0 = h[(size_t)c * 8];
+        for (uint32_t c = 0; c < pl.grid; ++c)
+            for (int i = 0; i < 8; ++i)
+                if (h[(size_t)c * 8 + i] > mx[i]) mx[i] = h[(size_t)c * 8 + i];
+        fprintf(stderr, "[sg tc trace] us since the first CTA's epilogue start (max over CTAs): enter %.1f | sample acc ready %.1f | "
+                        "sample scanned %.1f | all arrived %.1f | seeds %.1f | tile1 %.1f | tile2 %.1f | done %.1f\n",
+                (mx[0] - t0) / 1e3, (mx[1] - t0) / 1e3, (mx[2] - t0) / 1e3, (mx[3] - t0) / 1e3, (mx[4] - t0) / 1e3,
+                (mx[5] - t0) / 1e3, (mx[6] - t0) / 1e3, (mx[7] - t0) / 1e3);
     }
     FinalizeArgs f{};
     f.queries = d_q;

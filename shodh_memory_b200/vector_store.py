@@ -243,11 +243,11 @@ class GpuVectorStore:
         """diagnostics -> (tensor-core scores [b,n_rows], exact reference-order dots [b,n_rows])"""
         q = np.ascontiguousarray(queries, np.float32)
         b = q.shape[0]
-        tc = np.empty((b, n_rows), np.float32)
+        tc = np.empty((n_rows, b), np.float32)          # the tensor-core dump is row-major by corpus row
         ex = np.empty((b, n_rows), np.float32)
         capi.check(capi.lib().sg_debug_tc_scores(self._h, _ptr(q, C.c_float), b, first_row, n_rows, _ptr(tc, C.c_float)))
         capi.check(capi.lib().sg_debug_exact_scores(self._h, _ptr(q, C.c_float), b, first_row, n_rows, _ptr(ex, C.c_float)))
-        return tc, ex
+        return tc.T, ex
 
     # -- profiling hooks for bench.py -----------------------------------------------------
     def set_profiling(self, on: bool) -> None:
