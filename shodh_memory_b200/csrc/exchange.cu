@@ -78,6 +78,7 @@ exchange_wait_merge_kernel(const __grid_constant__ XArgs a)
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw);
     __shared__ uint32_t s_cnt;
+    pdl_wait();                                  // PDL launch: outputs of earlier searches on this stream are settled
     for (uint32_t q = blockIdx.x; q < a.b; q += gridDim.x) wait_and_merge(a, q, keys, &s_cnt);
 }
 
@@ -91,6 +92,7 @@ exchange_merge_kernel(const __grid_constant__ XArgs a)
     PushArgs p;
     for (uint32_t r = 0; r < 8; ++r) p.peer[r] = a.peer[r];
     p.rank = a.rank; p.world = a.world; p.epoch = a.epoch; p.b = a.b; p.k = a.k; p.q0 = 0;
+    pdl_wait();                                  // PDL launch: the local results this kernel pushes are complete from here on
     for (uint32_t q = blockIdx.x; q < a.b; q += gridDim.x) {
         push_query(p, q, a.ids + (size_t)q * a.k, a.dist + (size_t)q * a.k);   // peer stores over NVLink + flag
         wait_and_merge(a, q, keys, &s_cnt);
@@ -127,9 +129,8 @@ int launch_x(K kern, const XArgs &a, int device, cudaStream_t st)
     int rc = check_device(device, &sms);
     if (rc != SG_OK) return rc;
     const uint32_t grid = a.b < (uint32_t)sms ? a.b : (uint32_t)sms;     // co-resident
-    kern<<<grid, 256, smem, st>>>(a);
+    SG_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(256), smem, st, a));
     count_launch();
-    SG_CUDA_TRY(cudaGetLastError());
     return SG_OK;
 }
 

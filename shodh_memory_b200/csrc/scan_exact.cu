@@ -78,6 +78,7 @@ scan_exact_kernel(const __grid_constant__ CUtensorMap tmap, const ScanArgs a)
     // of queries and their indices live in device memory; with zero flagged queries every CTA exits here.
     uint32_t n_total = a.nq;
     if (a.flag_count) {
+        pdl_wait();                              // flagged launches are PDL launches: wait for the certification results
         n_total = *a.flag_count;
         if (n_total == 0) return;
     }
@@ -281,9 +282,15 @@ cudaError_t launch_t(const CUtensorMap &tmap, const ScanArgs &a, dim3 grid, dim3
         if (e != cudaSuccess) return e;
         smem_set = smem;
     }
-    kern<<<grid, block, smem, st>>>(tmap, a);
+    cudaError_t le;
+    if (a.flag_count) {
+        le = launch_pdl(kern, grid, block, smem, st, tmap, a);
+    } else {
+        kern<<<grid, block, smem, st>>>(tmap, a);
+        le = cudaGetLastError();
+    }
     count_launch();
-    return cudaGetLastError();
+    return le;
 }
 
 }  // namespace

@@ -83,6 +83,32 @@ SG_DEVICE_INLINE uint64_t tile_of_iter(uint64_t tile0, uint64_t stride, uint64_t
     return tile0 + (it ? it - 1 : 0) * stride;
 }
 
+// The A operand: this CTA's 128 query rows, f32 in global memory -> fp16 in shared memory, written directly in the
+// K-major SWIZZLE_128B layout the MMA descriptors expect (K-block kb = 128 rows x 128 B; the 16-byte chunk c of row r
+// sits at chunk c ^ (r & 7)).  Rows past the live count are zero.  All threads of the CTA take part; the caller
+// fences the generic-proxy stores for the async proxy (tcgen05.mma) and synchronises.
+SG_DEVICE_INLINE void stage_queries(const TcArgs &a, uint8_t *a_base, uint32_t q_first, uint32_t nq_local)
+{
+    const uint32_t cpr = a.dim / 8;                      // 16-byte chunks per row
+    const uint32_t a_addr = smem_u32(a_base);
+    for (uint32_t idx = threadIdx.x; idx < TC_M * cpr; idx += blockDim.x) {
+        const uint32_t r = idx / cpr, c8 = idx - r * cpr, kb = c8 >> 3, c = c8 & 7;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (r < nq_local) {
+            const float4 *src = reinterpret_cast<const float4 *>(a.queries + (size_t)(q_first + r) * a.dim + c8 * 8);
+            const float4 f0 = __ldg(src), f1 = __ldg(src + 1);
+            const __half2 h0 = __floats2half2_rn(f0.x, f0.y), h1 = __floats2half2_rn(f0.z, f0.w);
+            const __half2 h2 = __floats2half2_rn(f1.x, f1.y), h3 = __floats2half2_rn(f1.z, f1.w);
+            v.x = *reinterpret_cast<const uint32_t *>(&h0);
+            v.y = *reinterpret_cast<const uint32_t *>(&h1);
+            v.z = *reinterpret_cast<const uint32_t *>(&h2);
+            v.w = *reinterpret_cast<const uint32_t *>(&h3);
+        }
+        const uint32_t dst = a_addr + kb * (TC_M * 128) + r * 128 + ((c ^ (r & 7)) << 4);
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+}
+
 // ---- the epilogue shared by the 1-CTA and the CTA-pair kernels -------------------------------------
 // EIGHT epilogue warps: two per TMEM lane quarter.  Thread (grp, t) <-> query q_base + t <-> TMEM lane t; group
 // grp = 0/1 scans the even/odd 32-column chunks of every accumulator, so a tile's scan time is halved and two
@@ -200,15 +226,27 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
                     if (j < a.J) a.maxima[(size_t)q * a.nv_pad + unit_idx * a.J + j] = m[j];
             }
         }
-        // device-wide meeting point: every CTA of the grid publishes its sample, then reads all of them
+        // CTA 0 resets this query tile's per-search state (there is no separate "prepare" launch): nothing below is
+        // touched by any CTA before the meeting point, and the fence + barrier publish the stores
+        if (blockIdx.x == 0) {
+            const uint32_t q0 = a.q_tile * a.qtile, qn = a.qtile;
+            for (uint32_t i = e; i < qn * TC_HIST; i += TC_EPI_THREADS) a.hist[(size_t)q0 * TC_HIST + i] = 0;
+            for (uint32_t i = e; i < qn; i += TC_EPI_THREADS) {
+                a.gtau[q0 + i] = 0xFFFFFFFFu;
+                for (uint32_t j = a.nv; j < a.nv_pad; ++j) a.maxima[(size_t)(q0 + i) * a.nv_pad + j] = TC_NEG_INF;
+            }
+            if (e == 0 && a.q_tile == 0) *a.nflag = 0;
+        }
+        // device-wide meeting point: every CTA of the grid publishes its sample, then reads all of them.  The arrival
+        // counter is never reset: this launch waits for the value the host computed for it (wrap-safe compare).
         if (tr) trp[2] = gtimer();                   // sample scanned
         __threadfence();
         epi_bar_sync();
         if (e == 0) {
-            atomicAdd(a.arrive + a.q_tile, 1u);
+            atomicAdd(a.arrive, 1u);
             const long long t0 = clock64();
             uint32_t ok = 1;
-            while (ld_acquire_gpu_u32(a.arrive + a.q_tile) < gridDim.x) {
+            while ((int32_t)(ld_acquire_gpu_u32(a.arrive) - a.arrive_target) < 0) {
                 if (clock64() - t0 > 2000000000ll) {         // ~1 s: the grid is not co-resident (should not happen:
                     ok = 0;                                  // cooperative launch); degrade to "no threshold" -> the
                     break;                                   // queries overflow, get flagged and re-run on path A
@@ -318,7 +356,7 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
         tc_fence_after();
         if constexpr (!DUMP) {
             if (active) g_pend = ld_relaxed_u32(gtau);       // for the NEXT tile
-            h_valid = active && use_hist && (((uint32_t)it + 1 + list_idx) & 3u) == 0;
+            h_valid = active && use_hist && (((uint32_t)it + 1 + list_idx) & 3u) == 0;   // (refreshing EVERY early tile was measured slower)
             if (h_valid) {
                 const uint4 *hp = reinterpret_cast<const uint4 *>(my_hist);
 #pragma unroll
@@ -398,8 +436,7 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
 // ---- K1: the sweep, one CTA per SM (128 queries per sweep) ------------------------------------------
 template <bool DUMP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
-               const TcArgs a)
+scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const TcArgs a)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -430,9 +467,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
         mbar_init(smem_u32(a_bar), 1);
         mbar_fence_init();
         tma_prefetch_desc(&tmap_rows);
-        tma_prefetch_desc(&tmap_q);
     }
     if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
+    stage_queries(a, a_base, a.q_tile * TC_M, a.nq);         // the resident A operand (fp16 queries)
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -450,13 +488,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
     const uint32_t KBS = a.kbs, n_grp = nkb / KBS, stage_bytes = KBS * TC_STAGE_BYTES;
     if (warp == 0) {
         // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
-        if (elect_one_sync()) {
-            mbar_arrive_expect_tx(smem_u32(a_bar), nkb * TC_M * 128);
-            for (uint32_t kb = 0; kb < nkb; ++kb)
-                tma_load_2d(smem_u32(a_base + (size_t)kb * TC_M * 128), &tmap_q, smem_u32(a_bar), (int32_t)(kb * TC_KB),
-                            (int32_t)(a.q_tile * TC_M));
-        }
-        __syncwarp();
         uint32_t st = 0, ph = 0;
         for (uint64_t it = it0; it <= my_tiles; ++it) {
             const uint64_t tile = tile_of_iter(blockIdx.x, gridDim.x, it);
@@ -476,8 +507,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
     } else if (warp == 1) {
         // ===== MMA issuer: the whole warp walks the (uniform) loop, one elected lane issues =====
         constexpr uint32_t idesc = make_idesc_f16(TC_M, TC_N);
-        mbar_wait(smem_u32(a_bar), 0);
-        tc_fence_after();
         uint32_t st = 0, ph = 0;
         uint32_t acc = 0, acc_ph = 0;
         // descriptors differ only in their low word (address >> 4): keep that as a running integer
@@ -535,8 +564,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
 //   tfull[a]  per CTA, same multicast commit;  tempty[a] leader's only, 256 epilogue arrivals.
 template <bool DUMP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
-                const TcArgs a)
+scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const TcArgs a)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr uint32_t N2 = 256;                 // corpus rows per pair tile (TMEM columns per stage)
@@ -570,7 +598,6 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_cons
         mbar_init(smem_u32(a_bar), 1);
         mbar_fence_init();
         tma_prefetch_desc(&tmap_rows);
-        tma_prefetch_desc(&tmap_q);
     }
     cluster_sync_all();                                  // both CTAs resident, barriers initialised
     if (warp == 2) tmem_alloc2(smem_u32(tmem_slot), 512);
@@ -584,15 +611,13 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_cons
     const uint64_t my_tiles = cluster_id < n_tiles ? (n_tiles - cluster_id + n_clusters - 1) / n_clusters : 0;
     const uint64_t it0 = (DUMP || my_tiles == 0) ? 1 : 0;
 
-    // resident A operand: this CTA's 128 queries.  Everyone waits, then the pair synchronises so the
-    // leader's MMA thread may read the peer's A through the pair datapath.
-    if (threadIdx.x == 0) {
-        mbar_arrive_expect_tx(smem_u32(a_bar), nkb * TC_M * 128);
-        for (uint32_t kb = 0; kb < nkb; ++kb)
-            tma_load_2d(smem_u32(a_base + (size_t)kb * TC_M * 128), &tmap_q, smem_u32(a_bar), (int32_t)(kb * TC_KB),
-                        (int32_t)(a.q_tile * 256 + rank * TC_M));
+    // resident A operand: this CTA's 128 queries, converted in place; then the pair synchronises so the leader's MMA
+    // thread may read the peer's A through the pair datapath
+    {
+        const uint32_t qf = a.q_tile * 256 + rank * TC_M;
+        stage_queries(a, a_base, qf, a.nq > rank * TC_M ? (a.nq - rank * TC_M < TC_M ? a.nq - rank * TC_M : TC_M) : 0);
+        fence_proxy_async();
     }
-    mbar_wait(smem_u32(a_bar), 0);
     cluster_sync_all();
 
     const uint32_t KBS = a.kbs, n_grp = nkb / KBS, stage_bytes = KBS * TC_STAGE_BYTES;   // see scan_tc_kernel
@@ -662,57 +687,6 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_cons
     }
 }
 
-// ---- query preparation: fp16 rounding + the rigorous error bound -------------------------------
-// qh[q] = fp16(q) (zero rows for q >= b up to the padded count); err[q] = |q - fp16(q)|_2,
-// qnorm[q] = |q|_2 (both rounded up a little by computing in f64).  Also resets the per-search
-// device state of the sweep (thresholds, histograms, sample-phase arrival counters, flag counter).
-__global__ void prep_queries_kernel(const float *__restrict__ q, uint32_t b, uint32_t dim,
-                                    __half *__restrict__ qh, float *__restrict__ err, float *__restrict__ qnorm,
-                                    uint32_t *__restrict__ gtau, uint32_t *__restrict__ flags, uint32_t *__restrict__ hist,
-                                    uint32_t *__restrict__ arrive, uint32_t n_qtiles, uint32_t *__restrict__ nflag,
-                                    float *__restrict__ maxima, uint32_t nv, uint32_t nv_pad)
-{
-    const uint32_t row = blockIdx.x;
-    __shared__ double s_e[32], s_n[32];
-    double e = 0.0, n2 = 0.0;
-    for (uint32_t j = threadIdx.x; j < dim; j += blockDim.x) {
-        float v = row < b ? q[(size_t)row * dim + j] : 0.0f;
-        __half h = __float2half_rn(v);
-        qh[(size_t)row * dim + j] = h;
-        double d = (double)v - (double)__half2float(h);
-        e += d * d;
-        n2 += (double)v * (double)v;
-    }
-    if (threadIdx.x < TC_HIST) hist[(size_t)row * TC_HIST + threadIdx.x] = 0;
-    if (maxima && nv + threadIdx.x < nv_pad) maxima[(size_t)row * nv_pad + nv + threadIdx.x] = TC_NEG_INF;   // the pad of the sample row
-    if (row == 0) {
-        for (uint32_t i = threadIdx.x; i < n_qtiles; i += blockDim.x) arrive[i] = 0;
-        if (threadIdx.x == 0) *nflag = 0;
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        e += __shfl_down_sync(0xFFFFFFFFu, e, o);
-        n2 += __shfl_down_sync(0xFFFFFFFFu, n2, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        s_e[threadIdx.x >> 5] = e;
-        s_n[threadIdx.x >> 5] = n2;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double te = 0, tn = 0;
-        for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) {
-            te += s_e[w];
-            tn += s_n[w];
-        }
-        if (row < b) {
-            err[row] = (float)(sqrt(te) * 1.000001);
-            qnorm[row] = (float)(sqrt(tn) * 1.000001);
-            flags[row] = 0;
-        }
-        gtau[row] = 0xFFFFFFFFu;
-    }
-}
-
 // ---- K2: exact re-score + certification ---------------------------------------------------------
 // exact -dot in the reference's order for one (query,row): one thread, sequential chain
 template <int ORDER, typename QP>
@@ -755,6 +729,7 @@ finalize_tc_kernel(const __grid_constant__ FinalizeArgs f)
         s_flag = 0;
         s_n = 0;
     }
+    pdl_wait();                                  // launched early (PDL): the sweep's candidates are visible from here on
     __syncthreads();
     // (1) gather every candidate at or above the final shared threshold (a valid bound on the kk-th best, so at
     //     least kk survive whenever a threshold was ever published).  The region counts are read first (together
@@ -770,7 +745,27 @@ finalize_tc_kernel(const __grid_constant__ FinalizeArgs f)
         }
         pre[l + 1] = c;
     }
-    for (uint32_t i = threadIdx.x; i < f.dim; i += blockDim.x) q_s[i] = f.queries[(size_t)q * f.dim + i];
+    // the query, and with it the two norms of the certificate: err = |q - fp16(q)|_2 (what the tensor cores did not
+    // see) and |q|_2, both in f64 and rounded up a little
+    __shared__ double s_red[2][8];
+    {
+        double er = 0.0, n2 = 0.0;
+        for (uint32_t i = threadIdx.x; i < f.dim; i += blockDim.x) {
+            const float v = f.queries[(size_t)q * f.dim + i];
+            q_s[i] = v;
+            const double d = (double)v - (double)__half2float(__float2half_rn(v));
+            er += d * d;
+            n2 += (double)v * (double)v;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            er += __shfl_down_sync(0xFFFFFFFFu, er, o);
+            n2 += __shfl_down_sync(0xFFFFFFFFu, n2, o);
+        }
+        if (lane == 0) {
+            s_red[0][warp] = er;
+            s_red[1][warp] = n2;
+        }
+    }
     if (threadIdx.x == 0) pre[0] = 0;
     __syncthreads();
     if (warp == 0) {                             // inclusive scan of pre[1..L] by one warp (L <= 296)
@@ -870,7 +865,13 @@ finalize_tc_kernel(const __grid_constant__ FinalizeArgs f)
         if (kk == f.kk && out_n == f.k) {
             const float kth_exact_sim = -key32_to_dist((uint32_t)(fin[f.k - 1] >> 32));
             const float R = *f.max_row_norm;
-            const float E = f.err[q] * R + f.c_acc * f.qnorm[q] * R;
+            double er = 0.0, n2 = 0.0;
+            for (int wv = 0; wv < 8; ++wv) {
+                er += s_red[0][wv];
+                n2 += s_red[1][wv];
+            }
+            const float err_q = (float)(sqrt(er) * 1.000001), qnorm = (float)(sqrt(n2) * 1.000001);
+            const float E = err_q * R + f.c_acc * qnorm * R;
             ok = kth_exact_sim > weakest_approx_sim + E;     // NaN compares false -> flagged
         }
         if (!ok) s_flag = 1u;
@@ -935,7 +936,7 @@ cudaError_t ensure_smem(K kern, DevAttr &da, size_t smem)
 // launch cooperatively (the runtime then guarantees it); SG_TC_COOP=0 or a refusal falls back to a plain
 // launch (the kernel's own time-out keeps that safe, at worst slow).
 template <typename K>
-cudaError_t launch_sweep(K kern, const CUtensorMap &tmap_rows, const CUtensorMap &tmap_q, const TcArgs &a, uint32_t grid,
+cudaError_t launch_sweep(K kern, const CUtensorMap &tmap_rows, const TcArgs &a, uint32_t grid,
                          size_t smem, cudaStream_t st)
 {
     static const int coop = [] {
@@ -953,11 +954,11 @@ cudaError_t launch_sweep(K kern, const CUtensorMap &tmap_rows, const CUtensorMap
         attr[0].val.cooperative = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap_rows, tmap_q, a);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap_rows, a);
         if (e == cudaSuccess) return e;
         cudaGetLastError();                      // clear; fall through to the plain launch
     }
-    kern<<<grid, TC_THREADS, smem, st>>>(tmap_rows, tmap_q, a);
+    kern<<<grid, TC_THREADS, smem, st>>>(tmap_rows, a);
     return cudaGetLastError();
 }
 
@@ -983,45 +984,33 @@ float tc_c_acc(uint32_t dim)
     return 1.25f * ((float)dim * 1.1920929e-7f + (float)(dim / 4 + 4) * 5.9604645e-8f);
 }
 
-cudaError_t launch_prep_queries(const float *d_q, uint32_t b, uint32_t b_pad, uint32_t dim, __half *d_qh, float *d_err,
-                                float *d_qnorm, uint32_t *d_gtau, uint32_t *d_flags, uint32_t *d_hist, uint32_t *d_arrive,
-                                uint32_t n_qtiles, uint32_t *d_nflag, float *d_maxima, uint32_t nv, uint32_t nv_pad, cudaStream_t st)
-{
-    prep_queries_kernel<<<b_pad, 128, 0, st>>>(d_q, b, dim, d_qh, d_err, d_qnorm, d_gtau, d_flags, d_hist, d_arrive,
-                                               n_qtiles, d_nflag, d_maxima, nv, nv_pad);
-    count_launch();
-    return cudaGetLastError();
-}
-
-cudaError_t launch_scan_tc(const CUtensorMap &tmap_rows, const CUtensorMap &tmap_q, const TcArgs &a, uint32_t grid,
-                           size_t smem, cudaStream_t st)
+cudaError_t launch_scan_tc(const CUtensorMap &tmap_rows, const TcArgs &a, uint32_t grid, size_t smem, cudaStream_t st)
 {
     static DevAttr da, da_dump;
     cudaError_t e;
     if (a.dump) {
         if ((e = ensure_smem(scan_tc_kernel<true>, da_dump, smem)) != cudaSuccess) return e;
-        scan_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(tmap_rows, tmap_q, a);
+        scan_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(tmap_rows, a);
         e = cudaGetLastError();
     } else {
         if ((e = ensure_smem(scan_tc_kernel<false>, da, smem)) != cudaSuccess) return e;
-        e = launch_sweep(scan_tc_kernel<false>, tmap_rows, tmap_q, a, grid, smem, st);
+        e = launch_sweep(scan_tc_kernel<false>, tmap_rows, a, grid, smem, st);
     }
     count_launch();
     return e;
 }
 
-cudaError_t launch_scan_tc2(const CUtensorMap &tmap_rows, const CUtensorMap &tmap_q, const TcArgs &a, uint32_t grid,
-                            size_t smem, cudaStream_t st)
+cudaError_t launch_scan_tc2(const CUtensorMap &tmap_rows, const TcArgs &a, uint32_t grid, size_t smem, cudaStream_t st)
 {
     static DevAttr da, da_dump;
     cudaError_t e;
     if (a.dump) {
         if ((e = ensure_smem(scan_tc2_kernel<true>, da_dump, smem)) != cudaSuccess) return e;
-        scan_tc2_kernel<true><<<grid, TC_THREADS, smem, st>>>(tmap_rows, tmap_q, a);   // __cluster_dims__(2,1,1): grid must be even
+        scan_tc2_kernel<true><<<grid, TC_THREADS, smem, st>>>(tmap_rows, a);   // __cluster_dims__(2,1,1): grid must be even
         e = cudaGetLastError();
     } else {
         if ((e = ensure_smem(scan_tc2_kernel<false>, da, smem)) != cudaSuccess) return e;
-        e = launch_sweep(scan_tc2_kernel<false>, tmap_rows, tmap_q, a, grid, smem, st);
+        e = launch_sweep(scan_tc2_kernel<false>, tmap_rows, a, grid, smem, st);
     }
     count_launch();
     return e;
@@ -1035,9 +1024,9 @@ cudaError_t launch_finalize_tc(const FinalizeArgs &f, uint32_t b, cudaStream_t s
         cudaError_t e = ensure_smem(finalize_tc_kernel, da, smem);
         if (e != cudaSuccess) return e;
     }
-    finalize_tc_kernel<<<b, 256, smem, st>>>(f);
+    cudaError_t e = launch_pdl(finalize_tc_kernel, dim3(b), dim3(256), smem, st, f);
     count_launch();
-    return cudaGetLastError();
+    return e;
 }
 
 cudaError_t launch_exact_scores(const float *d_q, uint32_t b, const void *rows, uint32_t dim, uint64_t row0, uint64_t n,

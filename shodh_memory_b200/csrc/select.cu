@@ -29,6 +29,7 @@ merge_kernel(const uint64_t *__restrict__ lists, const uint32_t *__restrict__ id
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint64_t *buf = reinterpret_cast<uint64_t *>(smem_raw);
+    pdl_wait();                                                   // PDL launch: the producers' lists are visible from here on
     if (slot_count && blockIdx.x >= *slot_count) return;          // flagged form: nothing to do for this slot
     const uint32_t q = blockIdx.x / n_groups, grp = blockIdx.x - q * n_groups;
     const uint32_t q_out = slot_to_query ? slot_to_query[q] : q;  // where the result goes
@@ -171,11 +172,11 @@ cudaError_t launch(const uint64_t *lists, const uint32_t *ids_in, const float *d
     }
     PushArgs pa{};
     if (push && n_groups == 1) pa = *push;       // only the stage that writes the final (ids, dist) pushes
-    kern<<<b * n_groups, threads, smem, st>>>(lists, ids_in, dist_in, n_per_query, group_keys, n_groups, k, id_base,
-                                              list_stride, query_stride, keys_out, ids, dist, counts, slot_count,
-                                              slot_to_query, pa);
+    cudaError_t le = launch_pdl(kern, dim3(b * n_groups), dim3(threads), smem, st, lists, ids_in, dist_in, n_per_query, group_keys,
+                                n_groups, k, id_base, list_stride, query_stride, keys_out, ids, dist, counts, slot_count,
+                                slot_to_query, pa);
     count_launch();
-    return cudaGetLastError();
+    return le;
 }
 
 }  // namespace

@@ -31,6 +31,29 @@ void count_launch(unsigned n = 1);
     } while (0)
 
 // ----------------------------------------------------------------------------------------
+// programmatic dependent launch: the small kernels behind a sweep (re-score, flagged re-run, merges, exchange) are
+// launched with programmatic stream serialization, so their launch latency overlaps the kernel before them; each
+// calls pdl_wait() before it touches anything its predecessor wrote (a no-op under a normal launch).
+// ----------------------------------------------------------------------------------------
+SG_DEVICE_INLINE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename K, typename... Args>
+inline cudaError_t launch_pdl(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+// ----------------------------------------------------------------------------------------
 // keys: (distance, id) -> u64 whose unsigned order is (dist total_cmp asc, id asc)
 // (src/vector_db/vamana.rs:1184, :1664-1673)
 // ----------------------------------------------------------------------------------------

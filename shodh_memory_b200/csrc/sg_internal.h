@@ -52,7 +52,12 @@ struct TcArgs {
     uint32_t *gtau;           // [b_pad] best threshold key published so far (0xFFFFFFFF = none)
     float *maxima;            // [b_pad][nv_pad] sample maxima (-inf padded); nv_pad = n_lists * J rounded up to 4
     uint32_t nv_pad;
-    uint32_t *arrive;         // [query tiles] CTAs that finished the sample phase (zeroed by prep)
+    const float *queries;     // [b][dim] f32: each CTA converts its own 128 rows to the fp16 A operand
+    uint32_t qtile;           // queries per sweep (128 / 256)
+    uint32_t *arrive;         // CTAs that ever reached the sample meeting point (monotonic, never reset)
+    uint32_t arrive_target;   // value of *arrive once every CTA of THIS launch has arrived
+    uint32_t *nflag;          // uncertified-query counter of the search (reset by the first sweep of a search)
+    uint32_t nv;              // live sample values per query (units * J)
     uint32_t *hist;           // [b_pad][TC_HIST] appended candidates per score bucket
     uint64_t *cand;           // [b_pad][n_lists][cap_l] unsorted approximate candidates
     uint32_t *cnts;           // [b_pad][n_lists] entries appended (may exceed cap_l: overflow)
@@ -69,7 +74,6 @@ struct FinalizeArgs {
     const uint32_t *cnts;     // [b][n_lists]
     uint32_t n_lists, cap_l;
     const uint32_t *gtau;     // [b] final shared threshold key: candidates beyond it cannot be in the top kk
-    const float *err, *qnorm; // per-query |q - fp16(q)|, |q|
     const float *max_row_norm; // device scalar: upper bound on |row|_2 over the store
     float c_acc;              // accumulation-error coefficient of the bound (derived from dim)
     uint32_t rc;              // candidates re-scored per round (rows staged in shared memory)
@@ -82,14 +86,8 @@ struct FinalizeArgs {
 };
 size_t tc_smem_bytes(uint32_t dim, uint32_t stages, uint32_t kbs);
 float tc_c_acc(uint32_t dim);
-cudaError_t launch_prep_queries(const float *d_q, uint32_t b, uint32_t b_pad, uint32_t dim, __half *d_qh, float *d_err,
-                                float *d_qnorm, uint32_t *d_gtau, uint32_t *d_flags, uint32_t *d_hist, uint32_t *d_arrive,
-                                uint32_t n_qtiles, uint32_t *d_nflag, float *d_maxima, uint32_t nv, uint32_t nv_pad,
-                                cudaStream_t st);
-cudaError_t launch_scan_tc(const CUtensorMap &tmap_rows, const CUtensorMap &tmap_q, const TcArgs &a, uint32_t grid,
-                           size_t smem, cudaStream_t st);
-cudaError_t launch_scan_tc2(const CUtensorMap &tmap_rows, const CUtensorMap &tmap_q, const TcArgs &a, uint32_t grid,
-                            size_t smem, cudaStream_t st);
+cudaError_t launch_scan_tc(const CUtensorMap &tmap_rows, const TcArgs &a, uint32_t grid, size_t smem, cudaStream_t st);
+cudaError_t launch_scan_tc2(const CUtensorMap &tmap_rows, const TcArgs &a, uint32_t grid, size_t smem, cudaStream_t st);
 cudaError_t launch_finalize_tc(const FinalizeArgs &f, uint32_t b, cudaStream_t st);
 // diagnostics: exact -dot of every (query, row) pair in the reference's order -> out [b][n_rows_range]
 cudaError_t launch_exact_scores(const float *d_q, uint32_t b, const void *rows, uint32_t dim, uint64_t row0, uint64_t n,

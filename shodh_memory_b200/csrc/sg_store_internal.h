@@ -41,13 +41,11 @@ struct sg_store {
 
     // tensor-core path scratch
     float *d_max_norm = nullptr;                           // device scalar: bound on |row|_2 over the store
-    __half *d_qh = nullptr; size_t qh_cap = 0;             // fp16 queries, 128-row padded
-    float *d_qerr = nullptr; size_t qmeta_cap = 0;         // [b_pad] |q - fp16(q)|
-    float *d_qnorm = nullptr;                              // [b_pad]
+    size_t qmeta_cap = 0;                                  // capacity (queries) of gtau / flags / flag_list / hist
     float *d_maxima = nullptr; size_t maxima_cap = 0;      // [n_lists * J][b_pad] sample maxima
     uint32_t *d_gtau = nullptr, *d_flags = nullptr, *d_nflag = nullptr, *d_flag_list = nullptr;
     uint32_t *d_hist = nullptr;                            // [b_pad][32] per-query score histogram of the sweep in flight
-    uint32_t *d_arrive = nullptr; size_t arrive_cap = 0;   // sample-phase arrival counter per query tile
+    uint32_t *d_arrive = nullptr; uint32_t arrive_total = 0; // monotonic arrival counter of the sweeps' meeting point + its host mirror
     uint32_t *d_cnts = nullptr; size_t cnts_cap = 0;       // [b_pad][n_lists] candidates appended per region
     int tc_mode = 0;                                       // 0 = automatic, 1 = never use the tensor-core path
     cudaEvent_t ev_chain = nullptr;                        // end of the last asynchronous call

@@ -392,28 +392,26 @@ int search_tc_chunk(sg_store *s, const TcPlan &pl, const float *d_q, uint32_t b,
     const uint32_t b_pad = (b + qtile - 1) / qtile * qtile;
     const uint32_t n_qtiles = b_pad / qtile;
     int rc;
-    if ((rc = grow(s->d_qh, s->qh_cap, (size_t)b_pad * s->dim)) != SG_OK) return rc;
     if (b_pad > s->qmeta_cap) {
-        size_t c[6] = {s->qmeta_cap, s->qmeta_cap, s->qmeta_cap, s->qmeta_cap, s->qmeta_cap, s->qmeta_cap * TC_HIST};
-        if ((rc = grow(s->d_flag_list, c[4], b_pad)) != SG_OK) return rc;
-        if ((rc = grow(s->d_qerr, c[0], b_pad)) != SG_OK) return rc;
-        if ((rc = grow(s->d_qnorm, c[1], b_pad)) != SG_OK) return rc;
-        if ((rc = grow(s->d_gtau, c[2], b_pad)) != SG_OK) return rc;
-        if ((rc = grow(s->d_flags, c[3], b_pad)) != SG_OK) return rc;
-        if ((rc = grow(s->d_hist, c[5], (size_t)c[0] * TC_HIST)) != SG_OK) return rc;
+        size_t c[4] = {s->qmeta_cap, s->qmeta_cap, s->qmeta_cap, s->qmeta_cap * TC_HIST};
+        if ((rc = grow(s->d_flag_list, c[0], b_pad)) != SG_OK) return rc;
+        if ((rc = grow(s->d_gtau, c[1], b_pad)) != SG_OK) return rc;
+        if ((rc = grow(s->d_flags, c[2], b_pad)) != SG_OK) return rc;
+        if ((rc = grow(s->d_hist, c[3], (size_t)c[0] * TC_HIST)) != SG_OK) return rc;
         s->qmeta_cap = c[0];
     }
-    if ((rc = grow(s->d_arrive, s->arrive_cap, (size_t)n_qtiles)) != SG_OK) return rc;
+    if (!s->d_arrive) {                              // monotonic arrival counter of the sweeps' meeting point
+        SG_CUDA_TRY(cudaMalloc(&s->d_arrive, 4));
+        SG_CUDA_TRY(cudaMemset(s->d_arrive, 0, 4));
+        s->arrive_total = 0;
+    }
     if ((rc = grow(s->d_cand, s->cand_cap_q, (size_t)b_pad * n_lists * pl.cap_l)) != SG_OK) return rc;
     if ((rc = grow(s->d_cnts, s->cnts_cap, (size_t)b_pad * n_lists)) != SG_OK) return rc;
     const uint32_t nv_pad = (pl.units * pl.J + 3) / 4 * 4;
     if ((rc = grow(s->d_maxima, s->maxima_cap, (size_t)b_pad * nv_pad)) != SG_OK) return rc;
-    CUtensorMap tmap_rows, tmap_q;
+    CUtensorMap tmap_rows;
     if ((rc = encode_corpus_tmap(&tmap_rows, s->d_rows, true, s->dim, s->n, 128)) != SG_OK) return rc;
-    if ((rc = encode_corpus_tmap(&tmap_q, s->d_qh, true, s->dim, b_pad, 128)) != SG_OK) return rc;
 
-    SG_CUDA_TRY(launch_prep_queries(d_q, b, b_pad, s->dim, s->d_qh, s->d_qerr, s->d_qnorm, s->d_gtau, s->d_flags, s->d_hist,
-                                    s->d_arrive, n_qtiles, s->d_nflag, s->d_maxima, pl.units * pl.J, nv_pad, st));
     const size_t smem = tc_smem_bytes(s->dim, pl.stages, pl.kbs);
     unsigned long long *d_trace = nullptr;           // SG_TC_TRACE=1: phase stamps of the sweep, printed to stderr (debug)
     const bool trace = env_u32("SG_TC_TRACE", 0) != 0;
@@ -440,12 +438,17 @@ int search_tc_chunk(sg_store *s, const TcPlan &pl, const float *d_q, uint32_t b,
         a.maxima = s->d_maxima;
         a.nv_pad = nv_pad;
         a.arrive = s->d_arrive;
+        s->arrive_total += pl.grid;
+        a.arrive_target = s->arrive_total;
+        a.queries = d_q;
+        a.qtile = qtile;
+        a.nflag = s->d_nflag;
+        a.nv = pl.units * pl.J;
         a.hist = s->d_hist;
         a.cand = s->d_cand;
         a.cnts = s->d_cnts;
         a.trace = d_trace;
-        cudaError_t e = pl.pair ? launch_scan_tc2(tmap_rows, tmap_q, a, pl.grid, smem, st)
-                                : launch_scan_tc(tmap_rows, tmap_q, a, pl.grid, smem, st);
+        cudaError_t e = pl.pair ? launch_scan_tc2(tmap_rows, a, pl.grid, smem, st) : launch_scan_tc(tmap_rows, a, pl.grid, smem, st);
         if (e != cudaSuccess) {
             set_error("tensor-core scan launch failed: %s", cudaGetErrorString(e));
             return SG_ERR_CUDA;
@@ -486,8 +489,6 @@ int search_tc_chunk(sg_store *s, const TcPlan &pl, const float *d_q, uint32_t b,
     f.n_lists = n_lists;
     f.cap_l = pl.cap_l;
     f.gtau = s->d_gtau;
-    f.err = s->d_qerr;
-    f.qnorm = s->d_qnorm;
     f.max_row_norm = s->d_max_norm;
     f.c_acc = tc_c_acc(s->dim);
     {   // rows staged per re-score round: q + rows within 28 KB of dynamic shared memory (18.5 KB more are static)
@@ -655,9 +656,6 @@ void sg_store_destroy(sg_store *s)
     cudaFree(s->d_sim_out);
     cudaFree(s->d_memcnt);
     cudaFree(s->d_max_norm);
-    cudaFree(s->d_qh);
-    cudaFree(s->d_qerr);
-    cudaFree(s->d_qnorm);
     cudaFree(s->d_maxima);
     cudaFree(s->d_gtau);
     cudaFree(s->d_flags);
@@ -1026,21 +1024,11 @@ int sg_debug_tc_scores(sg_store *s, const float *queries, uint32_t b, uint64_t f
     int rc = chain_begin(s, s->stream);
     if (rc != SG_OK) return rc;
     const bool pair = b > 128;
-    const uint32_t qtile = pair ? 256 : 128, b_pad = qtile;
+    const uint32_t qtile = pair ? 256 : 128;
     float *d_q = nullptr, *d_out = nullptr;
-    __half *d_qh = nullptr;
-    float *d_e = nullptr;
-    uint32_t *d_u = nullptr;
     cudaError_t e = cudaMalloc(&d_q, (size_t)b * s->dim * 4);
     if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)b * n_rows * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&d_qh, (size_t)b_pad * s->dim * 2);
-    if (e == cudaSuccess) e = cudaMalloc(&d_e, (size_t)b_pad * 2 * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&d_u, ((size_t)b_pad * (2 + TC_HIST) + 8) * 4);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_q, queries, (size_t)b * s->dim * 4, cudaMemcpyHostToDevice, s->stream);
-    if (e == cudaSuccess)
-        e = launch_prep_queries(d_q, b, b_pad, s->dim, d_qh, d_e, d_e + b_pad, d_u, d_u + b_pad, d_u + 2 * b_pad,
-                                d_u + (size_t)b_pad * (2 + TC_HIST), 1, d_u + (size_t)b_pad * (2 + TC_HIST) + 4, nullptr, 0, 0,
-                                s->stream);
     rc = SG_OK;
     if (e == cudaSuccess) {
         const uint32_t rows_tile = pair ? 256 : 128;
@@ -1049,9 +1037,8 @@ int sg_debug_tc_scores(sg_store *s, const float *queries, uint32_t b, uint64_t f
         const uint32_t n_lists = (uint32_t)(n_tiles < units ? n_tiles : units);
         uint32_t stages = 8;
         while (stages > 3 && tc_smem_bytes(s->dim, stages, 1) > 227 * 1024) --stages;
-        CUtensorMap tmap_rows, tmap_q;
+        CUtensorMap tmap_rows;
         rc = encode_corpus_tmap(&tmap_rows, s->d_rows, true, s->dim, s->n, 128);
-        if (rc == SG_OK) rc = encode_corpus_tmap(&tmap_q, d_qh, true, s->dim, b_pad, 128);
         if (rc == SG_OK) {
             TcArgs a{};
             a.n_rows = s->n;
@@ -1059,17 +1046,18 @@ int sg_debug_tc_scores(sg_store *s, const float *queries, uint32_t b, uint64_t f
             a.nq = b;
             a.stages = stages;
             a.kbs = 1;
-            a.b_pad = b_pad;
+            a.queries = d_q;
+            a.qtile = qtile;
             a.dump = d_out;
             a.dump_row0 = first_row;
             a.dump_rows = n_rows;
-            e = pair ? launch_scan_tc2(tmap_rows, tmap_q, a, 2 * n_lists, tc_smem_bytes(s->dim, stages, 1), s->stream)
-                     : launch_scan_tc(tmap_rows, tmap_q, a, n_lists, tc_smem_bytes(s->dim, stages, 1), s->stream);
+            e = pair ? launch_scan_tc2(tmap_rows, a, 2 * n_lists, tc_smem_bytes(s->dim, stages, 1), s->stream)
+                     : launch_scan_tc(tmap_rows, a, n_lists, tc_smem_bytes(s->dim, stages, 1), s->stream);
         }
     }
     if (rc == SG_OK && e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)b * n_rows * 4, cudaMemcpyDeviceToHost, s->stream);
     if (rc == SG_OK && e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-    cudaFree(d_q); cudaFree(d_out); cudaFree(d_qh); cudaFree(d_e); cudaFree(d_u);
+    cudaFree(d_q); cudaFree(d_out);
     if (rc == SG_OK && e != cudaSuccess) {
         set_error("sg_debug_tc_scores: %s", cudaGetErrorString(e));
         rc = SG_ERR_CUDA;
