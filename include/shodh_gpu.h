@@ -90,6 +90,12 @@ SG_API void sg_store_destroy(sg_store *s);
 
 /* pre-size device memory for n_rows (amortises add_vector growth) */
 SG_API int sg_store_reserve(sg_store *s, uint64_t n_rows);
+/* How the row matrix is held.  in_place_out = 1: it lives in a reserved virtual range and grows by mapping physical
+ * chunks at its end (no second copy of the corpus while growing, no device-to-device copy, base address fixed);
+ * 0: the allocate-x1.5-and-copy fallback (driver without virtual memory management, or SG_STORE_VMM=0).
+ * capacity_rows_out = rows that fit without growing, bytes_out = device bytes held for rows, chunks_out = mapped chunks. */
+SG_API int sg_store_memory_info(sg_store *s, int *in_place_out, uint64_t *capacity_rows_out, uint64_t *bytes_out,
+                                uint32_t *chunks_out);
 
 /* VamanaIndex::add_vector (vamana.rs:853-974) / build (:200-284) /
  * rebuild_from_vectors: append n row-major f32 rows (rounded to the store dtype

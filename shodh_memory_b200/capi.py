@@ -80,6 +80,7 @@ def lib() -> C.CDLL:
     L.sg_store_is_deleted.argtypes = [vp, C.c_uint32, C.POINTER(C.c_int)]
     L.sg_store_clear_deleted.argtypes = [vp]
     L.sg_store_len.argtypes = [vp, u64p]
+    L.sg_store_memory_info.argtypes = [vp, C.POINTER(C.c_int), u64p, u64p, u32p]
     L.sg_store_deleted_count.argtypes = [vp, u64p]
     L.sg_store_dim.argtypes = [vp, u32p]
     L.sg_store_get_vectors.argtypes = [vp, C.c_uint64, C.c_uint64, f32p]

@@ -811,8 +811,7 @@ int sg_pq_search(sg_pq *p, const float *queries, uint32_t b, uint32_t topk, uint
         SG_CUDA_TRY(launch_merge_keys(nullptr, b, 0, topk, 0, nullptr, p->d_rids, p->d_rdist, p->d_rcnt, st));
     } else {
         const size_t smem = pq_scan_smem(QB, m, k, W, cap, topk);
-        static size_t smem_set_dev[64][3] = {};
-        size_t *smem_set = smem_set_dev[p->device & 63];
+        static DevAttr da4, da2, da1;
         for (uint32_t done = 0; done < b; done += QB) {
             PqScanArgs a;
             a.codes = p->d_codes;
@@ -826,22 +825,13 @@ int sg_pq_search(sg_pq *p, const float *queries, uint32_t b, uint32_t topk, uint
             a.cap = cap;
             a.out_lists = p->d_lists + (size_t)done * grid * topk;
             if (QB == 4) {
-                if (smem > smem_set[0]) {
-                    SG_CUDA_TRY(cudaFuncSetAttribute(pq_scan4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    smem_set[0] = smem;
-                }
+                SG_CUDA_TRY(ensure_smem(pq_scan4_kernel, da4, smem));
                 pq_scan4_kernel<<<grid, W * 32, smem, st>>>(a);
             } else if (QB == 2) {
-                if (smem > smem_set[2]) {
-                    SG_CUDA_TRY(cudaFuncSetAttribute(pq_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    smem_set[2] = smem;
-                }
+                SG_CUDA_TRY(ensure_smem(pq_scan_kernel<2>, da2, smem));
                 pq_scan_kernel<2><<<grid, W * 32, smem, st>>>(a);
             } else {
-                if (smem > smem_set[1]) {
-                    SG_CUDA_TRY(cudaFuncSetAttribute(pq_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    smem_set[1] = smem;
-                }
+                SG_CUDA_TRY(ensure_smem(pq_scan_kernel<1>, da1, smem));
                 pq_scan_kernel<1><<<grid, W * 32, smem, st>>>(a);
             }
             count_launch();

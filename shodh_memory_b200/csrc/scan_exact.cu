@@ -273,14 +273,10 @@ cudaError_t launch_t(const CUtensorMap &tmap, const ScanArgs &a, dim3 grid, dim3
                      cudaStream_t st)
 {
     auto kern = scan_exact_kernel<QB, F16, ORDER, METRIC>;
-    static size_t smem_set_dev[64] = {0};     // per instantiation and device: raise the opt-in limit only when it grows
-    int dev_ = 0;
-    cudaGetDevice(&dev_);
-    size_t &smem_set = smem_set_dev[dev_ & 63];
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static DevAttr da;                        // per instantiation: raise the opt-in limit only when it grows
+    {
+        cudaError_t e = ensure_smem(kern, da, smem);
         if (e != cudaSuccess) return e;
-        smem_set = smem;
     }
     cudaError_t le;
     if (a.flag_count) {

@@ -912,26 +912,6 @@ exact_scores_kernel(const float *__restrict__ q, uint32_t b, const __half *__res
     }
 }
 
-struct DevAttr {           // "dynamic shared memory limit already raised to" per (kernel, device); process-wide
-    std::mutex mu;
-    size_t set[64] = {0};
-};
-template <typename K>
-cudaError_t ensure_smem(K kern, DevAttr &da, size_t smem)
-{
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    std::lock_guard<std::mutex> g(da.mu);
-    size_t &cur = da.set[dev & 63];
-    if (smem > cur) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        cur = smem;
-    }
-    return cudaSuccess;
-}
-
 // The sweep's sample phase ends in a device-wide meeting point, so the whole grid must be co-resident:
 // launch cooperatively (the runtime then guarantees it); SG_TC_COOP=0 or a refusal falls back to a plain
 // launch (the kernel's own time-out keeps that safe, at worst slow).

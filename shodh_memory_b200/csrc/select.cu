@@ -158,17 +158,9 @@ cudaError_t launch(const uint64_t *lists, const uint32_t *ids_in, const float *d
     uint32_t threads = need / 2 < 1024 ? (need / 2 < 32 ? 32 : need / 2) : 1024;
     auto kern = merge_kernel<PAIRS>;
     {
-        static std::mutex mu;                    // process-wide: two stores on two threads may get here together
-        static bool attr_set_dev[64] = {false};
-        int dev_ = 0;
-        cudaGetDevice(&dev_);
-        std::lock_guard<std::mutex> g(mu);
-        bool &attr_set = attr_set_dev[dev_ & 63];
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SORT_MAX * 8));
-            if (e != cudaSuccess) return e;
-            attr_set = true;
-        }
+        static DevAttr da;                       // process-wide table: two stores on two threads may get here together
+        cudaError_t e = ensure_smem(kern, da, (size_t)SORT_MAX * 8);
+        if (e != cudaSuccess) return e;
     }
     PushArgs pa{};
     if (push && n_groups == 1) pa = *push;       // only the stage that writes the final (ids, dist) pushes

@@ -1,8 +1,32 @@
 // sg_internal.h -- declarations shared between the translation units of libshodh_gpu.
 #pragma once
+#include <mutex>
+
 #include "sg_common.cuh"
 
 namespace sg {
+
+// "dynamic shared memory opt-in already raised to" per (kernel, device): a process-wide table that two stores on two
+// host threads may reach together, hence the lock.  One DevAttr per kernel instantiation.
+struct DevAttr {
+    std::mutex mu;
+    size_t set[64] = {0};
+};
+template <typename K>
+inline cudaError_t ensure_smem(K kern, DevAttr &da, size_t smem)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> g(da.mu);
+    size_t &cur = da.set[dev & 63];
+    if (smem > cur) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        cur = smem;
+    }
+    return cudaSuccess;
+}
 
 // ---- scan_exact.cu ----
 struct ScanArgs {

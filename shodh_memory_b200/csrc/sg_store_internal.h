@@ -24,6 +24,12 @@ struct sg_store {
 
     void *d_rows = nullptr;
     uint64_t n = 0, cap = 0;
+    // in-place growth (CUDA virtual memory management): d_rows is a reserved VA range, physical chunks are mapped at
+    // its end as the store grows -- no second copy of the corpus, no D2D copy, the base address never changes
+    bool vmm = false;
+    uint64_t va_bytes = 0, mapped_bytes = 0;
+    std::vector<unsigned long long> vmm_handles;   // CUmemGenericAllocationHandle of every mapped chunk
+    std::vector<uint64_t> vmm_sizes;
     uint32_t *d_deleted = nullptr;       // bitmap, cap/32 (+pad) words
     std::vector<uint32_t> h_deleted;     // host mirror
     uint64_t n_deleted = 0;
@@ -104,6 +110,7 @@ int store_truncate_locked(sg_store *s);
 int check_device(int device, int *sm_count);
 int grow_pinned(sg_store *s, size_t bytes);
 int ensure_rows(sg_store *s, uint64_t need_rows);
+void vmm_release(sg_store *s);
 // exact path A; all pointers are device pointers; asynchronous on st.  use_deleted = false scores every row.
 int search_exact_locked(sg_store *s, const float *d_q, uint32_t b, uint32_t k, uint32_t *d_ids, float *d_dist,
                         uint32_t *d_counts, cudaStream_t st, bool record, bool use_deleted = true,

@@ -740,11 +740,8 @@ int sg_spann_search(sg_spann *s, const float *queries, uint32_t b, uint32_t topk
     SG_CUDA_TRY(cudaMemcpyAsync(s->d_q, queries, (size_t)b * s->dim * 4, cudaMemcpyHostToDevice, st));
     {   // partition ranking of the whole batch
         const size_t rsm = ((size_t)SP_CT * (s->dim + 1) + (size_t)SP_QG * s->dim) * 4;
-        static size_t rank_set[64] = {0};
-        if (rsm > 48 * 1024 && rsm > rank_set[s->device & 63]) {
-            SG_CUDA_TRY(cudaFuncSetAttribute(spann_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
-            rank_set[s->device & 63] = rsm;
-        }
+        static DevAttr da_rank;
+        if (rsm > 48 * 1024) SG_CUDA_TRY(ensure_smem(spann_rank_kernel, da_rank, rsm));
         spann_rank_kernel<<<(s->n_part + SP_CT - 1) / SP_CT, 256, rsm, st>>>(s->d_q, b, s->dim, s->d_centroids, s->n_part, p_pow2,
                                                                             s->metric, s->d_pkeys);
         count_launch();
@@ -770,11 +767,8 @@ int sg_spann_search(sg_spann *s, const float *queries, uint32_t b, uint32_t topk
     a.ids_out = s->d_rids;
     a.dist_out = s->d_rdist;
     a.counts_out = s->d_rcnt;
-    static size_t smem_set[64] = {0};
-    if (smem > smem_set[s->device & 63]) {
-        SG_CUDA_TRY(cudaFuncSetAttribute(spann_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set[s->device & 63] = smem;
-    }
+    static DevAttr da_search;
+    SG_CUDA_TRY(ensure_smem(spann_search_kernel, da_search, smem));
     spann_search_kernel<<<b, W * 32, smem, st>>>(a);
     count_launch();
     SG_CUDA_TRY(cudaGetLastError());

@@ -140,6 +140,127 @@ int grow_pinned(sg_store *s, size_t bytes)
     return SG_OK;
 }
 
+// ---- CUDA virtual memory management through the runtime's driver entry points (no -lcuda) ----
+namespace {
+struct VmmApi {
+    CUresult (*reserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*addr_free)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*create)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
+    CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*unmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*set_access)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
+    CUresult (*granularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) = nullptr;
+    bool ok = false;
+};
+const VmmApi &vmm_api()
+{
+    static VmmApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        auto get = [](const char *name, void **fn) {
+            cudaDriverEntryPointQueryResult q;
+            return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+        };
+        api.ok = get("cuMemAddressReserve", reinterpret_cast<void **>(&api.reserve)) &&
+                 get("cuMemAddressFree", reinterpret_cast<void **>(&api.addr_free)) &&
+                 get("cuMemCreate", reinterpret_cast<void **>(&api.create)) &&
+                 get("cuMemRelease", reinterpret_cast<void **>(&api.release)) &&
+                 get("cuMemMap", reinterpret_cast<void **>(&api.map)) &&
+                 get("cuMemUnmap", reinterpret_cast<void **>(&api.unmap)) &&
+                 get("cuMemSetAccess", reinterpret_cast<void **>(&api.set_access)) &&
+                 get("cuMemGetAllocationGranularity", reinterpret_cast<void **>(&api.granularity));
+        const char *v = getenv("SG_STORE_VMM");
+        if (v && *v && atoi(v) == 0) api.ok = false;
+    });
+    return api;
+}
+CUmemAllocationProp vmm_prop(int device)
+{
+    CUmemAllocationProp p = {};
+    p.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    p.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    p.location.id = device;
+    return p;
+}
+}  // namespace
+
+void vmm_release(sg_store *s)
+{
+    if (!s->vmm) return;
+    const VmmApi &api = vmm_api();
+    if (s->mapped_bytes) api.unmap((CUdeviceptr)s->d_rows, s->mapped_bytes);
+    for (unsigned long long h : s->vmm_handles) api.release((CUmemGenericAllocationHandle)h);
+    if (s->d_rows) api.addr_free((CUdeviceptr)s->d_rows, s->va_bytes);
+    s->vmm_handles.clear();
+    s->vmm_sizes.clear();
+    s->d_rows = nullptr;
+    s->mapped_bytes = s->va_bytes = 0;
+    s->vmm = false;
+}
+
+// Row storage that grows IN PLACE: a virtual range for the largest store this device could hold is reserved once,
+// physical chunks are mapped at its end as rows arrive.  A live 10M-row store that grows needs no second buffer and
+// no device-to-device copy, searches in flight keep reading valid memory, and the base address (tensor maps, graph
+// kernels) never changes.  Returns false (caller falls back to allocate-and-copy) if VMM is unavailable.
+static bool vmm_ensure(sg_store *s, uint64_t need_bytes, int *rc_out)
+{
+    const VmmApi &api = vmm_api();
+    *rc_out = SG_OK;
+    if (!api.ok || (s->d_rows && !s->vmm)) return false;
+    const CUmemAllocationProp prop = vmm_prop(s->device);
+    size_t gran = 0;
+    if (api.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0) return false;
+    if (!s->d_rows) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
+        const uint64_t row_bytes = (uint64_t)s->dim * s->esize;
+        uint64_t va = 0xFFFFFFFEull * row_bytes;                       // ids are u32
+        if (va > (uint64_t)total_b) va = total_b;
+        va = (va + gran - 1) / gran * gran;
+        CUdeviceptr base = 0;
+        if (api.reserve(&base, va, 0, 0, 0) != CUDA_SUCCESS) return false;
+        s->d_rows = reinterpret_cast<void *>(base);
+        s->va_bytes = va;
+        s->mapped_bytes = 0;
+        s->vmm = true;
+    }
+    if (need_bytes <= s->mapped_bytes) return true;
+    if (need_bytes > s->va_bytes) {
+        set_error("store would exceed the device's memory (%llu bytes of rows)", (unsigned long long)need_bytes);
+        *rc_out = SG_ERR_OOM;
+        return true;
+    }
+    // grow by at least 1/8 of what is mapped (amortises the map calls), in whole granules
+    uint64_t want = need_bytes - s->mapped_bytes;
+    if (want < s->mapped_bytes / 8) want = s->mapped_bytes / 8;
+    want = (want + gran - 1) / gran * gran;
+    if (s->mapped_bytes + want > s->va_bytes) want = s->va_bytes - s->mapped_bytes;
+    CUmemGenericAllocationHandle h = 0;
+    if (api.create(&h, want, &prop, 0) != CUDA_SUCCESS) {
+        want = (need_bytes - s->mapped_bytes + gran - 1) / gran * gran;   // retry with the bare minimum
+        if (api.create(&h, want, &prop, 0) != CUDA_SUCCESS) {
+            set_error("out of device memory growing the store by %llu bytes", (unsigned long long)want);
+            *rc_out = SG_ERR_OOM;
+            return true;
+        }
+    }
+    const CUdeviceptr at = (CUdeviceptr)s->d_rows + s->mapped_bytes;
+    CUmemAccessDesc acc = {};
+    acc.location = prop.location;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if (api.map(at, want, 0, h, 0) != CUDA_SUCCESS || api.set_access(at, want, &acc, 1) != CUDA_SUCCESS) {
+        api.release(h);
+        set_error("mapping %llu bytes of row storage failed", (unsigned long long)want);
+        *rc_out = SG_ERR_CUDA;
+        return true;
+    }
+    s->vmm_handles.push_back((unsigned long long)h);
+    s->vmm_sizes.push_back(want);
+    s->mapped_bytes += want;
+    return true;
+}
+
 int ensure_rows(sg_store *s, uint64_t need_rows)
 {
     if (need_rows <= s->cap) return SG_OK;
@@ -147,39 +268,60 @@ int ensure_rows(sg_store *s, uint64_t need_rows)
         set_error("store is limited to 2^32-2 rows (ids are u32)");
         return SG_ERR_UNSUPPORTED;
     }
+    const size_t row_bytes = (size_t)s->dim * s->esize;
+    // the soft-delete bitmap is small (1 bit per row): reallocated + copied, generously sized
+    auto grow_bitmap = [&](uint64_t ncap) -> int {
+        const size_t words = ncap / 32 + 1;
+        if (words <= s->h_deleted.size() && s->d_deleted) return SG_OK;
+        uint32_t *nbm = nullptr;
+        SG_CUDA_TRY(cudaMalloc(&nbm, words * 4));
+        cudaError_t e = cudaMemsetAsync(nbm, 0, words * 4, s->stream);
+        if (e == cudaSuccess && s->n && s->d_deleted)
+            e = cudaMemcpyAsync(nbm, s->d_deleted, (s->n / 32 + 1) * 4, cudaMemcpyDeviceToDevice, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) {
+            cudaFree(nbm);
+            set_error("growing the deleted-row bitmap failed: %s", cudaGetErrorString(e));
+            return SG_ERR_CUDA;
+        }
+        if (s->d_deleted) cudaFree(s->d_deleted);   // synchronises the device: no search in flight still reads it
+        s->d_deleted = nbm;
+        s->h_deleted.resize(words, 0u);
+        return SG_OK;
+    };
+    {   // preferred: grow in place
+        int vrc = SG_OK;
+        if (vmm_ensure(s, need_rows * row_bytes, &vrc)) {
+            if (vrc != SG_OK) return vrc;
+            const uint64_t ncap = s->mapped_bytes / row_bytes;
+            int rc = grow_bitmap(ncap + ncap / 2);
+            if (rc != SG_OK) return rc;
+            s->cap = ncap;
+            return SG_OK;
+        }
+    }
+    // fallback: allocate x1.5, copy, free
     uint64_t ncap = s->cap + s->cap / 2;
     if (ncap < need_rows) ncap = need_rows;
     ncap = (ncap + 1023) & ~1023ull;
     void *nrows = nullptr;
-    const size_t row_bytes = (size_t)s->dim * s->esize;
     SG_CUDA_TRY(cudaMalloc(&nrows, ncap * row_bytes));
-    uint32_t *nbm = nullptr;
-    const size_t words = ncap / 32 + 1;
-    cudaError_t e = cudaMalloc(&nbm, words * 4);
-    if (e != cudaSuccess) {
-        cudaFree(nrows);
-        set_error("cudaMalloc(bitmap) failed: %s", cudaGetErrorString(e));
-        return SG_ERR_OOM;
-    }
-    e = cudaMemsetAsync(nbm, 0, words * 4, s->stream);
-    if (e == cudaSuccess && s->n) {
-        e = cudaMemcpyAsync(nrows, s->d_rows, s->n * row_bytes, cudaMemcpyDeviceToDevice, s->stream);
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(nbm, s->d_deleted, (s->n / 32 + 1) * 4, cudaMemcpyDeviceToDevice, s->stream);
-    }
+    cudaError_t e = cudaSuccess;
+    if (s->n) e = cudaMemcpyAsync(nrows, s->d_rows, s->n * row_bytes, cudaMemcpyDeviceToDevice, s->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
     if (e != cudaSuccess) {
         cudaFree(nrows);
-        cudaFree(nbm);
         set_error("growing the store failed: %s", cudaGetErrorString(e));
         return SG_ERR_CUDA;
     }
+    int rc = grow_bitmap(ncap);
+    if (rc != SG_OK) {
+        cudaFree(nrows);
+        return rc;
+    }
     if (s->d_rows) cudaFree(s->d_rows);
-    if (s->d_deleted) cudaFree(s->d_deleted);
     s->d_rows = nrows;
-    s->d_deleted = nbm;
     s->cap = ncap;
-    s->h_deleted.resize(words, 0u);
     return SG_OK;
 }
 
@@ -642,7 +784,8 @@ void sg_store_destroy(sg_store *s)
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    cudaFree(s->d_rows);
+    if (s->vmm) vmm_release(s);
+    else cudaFree(s->d_rows);
     cudaFree(s->d_deleted);
     cudaFree(s->d_queries);
     cudaFree(s->d_lists);
@@ -804,6 +947,18 @@ int sg_store_clear_deleted(sg_store *s)
     s->n_deleted = 0;
     SG_CUDA_TRY(cudaMemsetAsync(s->d_deleted, 0, s->h_deleted.size() * 4, s->stream));
     SG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return SG_OK;
+}
+
+int sg_store_memory_info(sg_store *s, int *in_place_out, uint64_t *capacity_rows_out, uint64_t *bytes_out,
+                         uint32_t *chunks_out)
+{
+    if (!s) return SG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(s->mu);
+    if (in_place_out) *in_place_out = s->vmm ? 1 : 0;
+    if (capacity_rows_out) *capacity_rows_out = s->cap;
+    if (bytes_out) *bytes_out = s->vmm ? s->mapped_bytes : s->cap * (uint64_t)s->dim * s->esize;
+    if (chunks_out) *chunks_out = s->vmm ? (uint32_t)s->vmm_handles.size() : (s->d_rows ? 1u : 0u);
     return SG_OK;
 }
 

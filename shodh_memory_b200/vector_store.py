@@ -57,6 +57,12 @@ class GpuVectorStore:
     def reserve(self, n_rows: int) -> None:
         capi.check(capi.lib().sg_store_reserve(self._h, n_rows))
 
+    def memory_info(self) -> dict:
+        """How the row matrix is held: in-place growth (VMM chunks) or the allocate-and-copy fallback."""
+        ip, cap, nb, ch = C.c_int(), C.c_uint64(), C.c_uint64(), C.c_uint32()
+        capi.check(capi.lib().sg_store_memory_info(self._h, C.byref(ip), C.byref(cap), C.byref(nb), C.byref(ch)))
+        return {"in_place": bool(ip.value), "capacity_rows": cap.value, "bytes": nb.value, "chunks": ch.value}
+
     def add_vector(self, vector) -> int:
         """VamanaIndex::add_vector -> the new id."""
         return self.add_vectors(np.asarray(vector, np.float32)[None, :])
