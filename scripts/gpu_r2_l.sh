@@ -7,3 +7,4 @@ timeout 300 python bench.py --leg spann > gpurun_out/l_spann.json 2>/dev/null; p
 import json; d=json.load(open('gpurun_out/l_spann.json')); print('SPANN', d.get('error') or {k:d[k] for k in ('batch256','batch1_host_api_ms','achieved_GBps_batch256')})"
 timeout 200 python __graft_entry__.py smoke 2>&1 | tail -3
 CASES="10000000:256:10,10000000:128:10,10000000:8:10,1250000:256:10" timeout 300 python scripts/probe_step.py 2>&1 | tail -5
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/l_enc_launches.csv python scripts/prof_enc_target.py > /dev/null 2>&1; wc -l gpurun_out/l_enc_launches.csv

@@ -45,7 +45,16 @@ struct GemmArgs {
     float eps;
     __half *out;           // [M_pad, N]
     float *out_f32;        // optional f32 copy (EPI_BIAS_RES_LN)
+    uint32_t rows;         // rows of the activation matrices (M_pad); the pair kernels may be handed a tile beyond it
+    unsigned long long *trace;   // debug (SG_ENC_TRACE): [CTA][8] %globaltimer stamps of the LayerNorm GEMM's phases
 };
+
+SG_DEVICE_INLINE unsigned long long enc_gtimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // erf-GELU, x * Phi(x), in 12 instructions.  Phi(x) = 1 / (1 + exp(-logit Phi(x))) and logit Phi is odd and
 // smooth, so it is fitted by x * P(x^2) (degree-9 odd minimax fit on |x| <= 6, coefficients pre-multiplied by
@@ -86,6 +95,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t S = g.stages;
     const uint32_t nkb = g.K / 64;
+    unsigned long long *trp = (EPI == EPI_BIAS_RES_LN && g.trace && threadIdx.x == 128) ? g.trace + (size_t)blockIdx.x * 8 : nullptr;
+    if (trp) trp[0] = enc_gtimer();                      // kernel entered
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * STAGE);
     uint64_t *full_bar = bars, *empty_bar = bars + S, *done_bar = bars + 2 * S;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
@@ -107,6 +118,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (trp) trp[1] = enc_gtimer();                      // barriers + TMEM ready
+    pdl_wait();                                            // activations come from the previous kernel of the forward
+    pdl_trigger();
+    if (trp) trp[2] = enc_gtimer();                      // previous kernel complete
     const uint32_t m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
 
     // Producer and MMA issuer: the WHOLE warp walks the (uniform) loop and one elected lane issues, so the smem
@@ -177,6 +192,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_T) : "memory");
         mbar_wait(smem_u32(done_bar), 0);
         tc_fence_after();
+        if (trp) trp[3] = enc_gtimer();                  // accumulator complete
         if constexpr (EPI == EPI_BIAS_RES_LN) {
             // BN == N == hidden: the whole row is in this thread's TMEM lane.  Pass 1: v = acc + bias +
             // residual is written BACK into TMEM while sum / sum of squares accumulate; pass 2 reads v from
@@ -212,6 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             part[(qtr * 128 + t) * 2] = sum;
             part[(qtr * 128 + t) * 2 + 1] = sq;
             asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (trp) trp[4] = enc_gtimer();              // pass 1 (bias + residual + statistics) done by all
             sum = (part[t * 2] + part[(128 + t) * 2]) + (part[(256 + t) * 2] + part[(384 + t) * 2]);
             sq = (part[t * 2 + 1] + part[(128 + t) * 2 + 1]) + (part[(256 + t) * 2 + 1] + part[(384 + t) * 2 + 1]);
             const float mean = sum / (float)BN;
@@ -259,8 +276,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
         }
     }
+    if (trp) trp[5] = enc_gtimer();                      // this thread's pass 2 done
     tc_fence_before();
     __syncthreads();
+    if (trp) trp[6] = enc_gtimer();                      // all done
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TCOLS);
@@ -301,6 +320,8 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                            // activations come from the previous kernel of the forward
+    pdl_trigger();
     const uint32_t m0 = (blockIdx.x / 3) * 128, n0 = crank * BN;
 
     if (warp == 0) {                                      // warp-uniform loops, one elected lane issues (see gemm_tc_kernel)
@@ -470,6 +491,8 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                            // activations come from the previous kernel of the forward
+    pdl_trigger();
     const uint32_t total = m_tiles * n_tiles;
     const uint32_t my_tiles = blockIdx.x < total ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
@@ -566,6 +589,349 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     }
 }
 
+// ---- persistent CTA-PAIR GEMM: 256 x BN tiles with tcgen05 cta_group::2 --------------------------------
+// The 128x128-tile kernel above moves 32 KB from L2 per 2.1 MFLOP K-block: at 148 SMs x 15 TFLOP/s that is ~34 TB/s
+// against an L2 that delivers ~12 (measured: QKV ran at 10.2 TB/s of L2->SM traffic, i.e. it was L2-bandwidth-bound at
+// 46 % of the tensor peak).  A CTA pair computes a 256-row x BN-column tile: each CTA stages ITS 128 activation rows and
+// HALF of the BN weight rows (the pair's MMA reads both halves), so the same FLOPs need 1.75x (BN = 192) fewer bytes.
+// One CTA per SM, 6-deep ring (a whole K = 384 tile in flight), two accumulator stages in TMEM (columns 0 and 256),
+// 8 epilogue warps per CTA drain its 128 rows, output through swizzled staging + TMA stores.  N = 1152 and 1536 are
+// both multiples of 192: 384 / 512 pair tiles over 74 pairs.
+template <uint32_t BN, uint32_t EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LN_THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                    const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g, const uint32_t m_pairs,
+                    const uint32_t n_tiles)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr uint32_t A_BYTES = 128 * 128, B_BYTES = (BN / 2) * 128, STAGE = A_BYTES + B_BYTES, ACC = 2, ACC_COLS = 256;
+    constexpr uint32_t BOXES = BN / 64, CH = BN / 64;         // output boxes of 64 columns; 32-column chunks per half
+    static_assert(BN % 64 == 0 && BN <= 256 && STAGE % 1024 == 0, "pair tile shape");
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const uint32_t S = g.stages, nkb = g.K / 64;
+    uint8_t *stage_out = smem + (size_t)S * STAGE;                      // 2 groups x BOXES x 16 KB, 1024-aligned
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage_out + 2 * BOXES * 128 * 128);
+    uint64_t *full_bar = bars, *empty_bar = bars + S, *tfull_bar = bars + 2 * S, *tempty_bar = tfull_bar + ACC;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + ACC);
+    float *bias_s = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~static_cast<uintptr_t>(15));  // [ACC][BN]
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < S; ++i) {
+            mbar_init(smem_u32(full_bar + i), 2);          // leader: its own expect_tx arrive + the peer's arrive
+            mbar_init(smem_u32(empty_bar + i), 1);
+        }
+        for (uint32_t i = 0; i < ACC; ++i) {
+            mbar_init(smem_u32(tfull_bar + i), 1);
+            mbar_init(smem_u32(tempty_bar + i), 2 * 256);  // leader: the epilogue threads of BOTH CTAs
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_out);
+    }
+    cluster_sync_all();                                    // both CTAs resident, barriers initialised
+    if (warp == 2) tmem_alloc2(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const uint32_t total = m_pairs * n_tiles;
+    const uint32_t my_tiles = cluster_id < total ? (total - cluster_id + n_clusters - 1) / n_clusters : 0;
+    pdl_wait();                                            // the activations come from the previous kernel
+    pdl_trigger();
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): my 128 activation rows + my half of the weight rows; credited to the leader =====
+        uint32_t st = 0, ph = 0;
+        for (uint32_t i = 0; i < my_tiles; ++i) {
+            const uint32_t tile = cluster_id + i * n_clusters;
+            const uint32_t m0 = (tile / n_tiles) * 256 + rank * 128, n0 = (tile % n_tiles) * BN + rank * (BN / 2);
+            for (uint32_t kb = 0; kb < nkb; ++kb) {
+                mbar_wait(smem_u32(empty_bar + st), ph ^ 1);
+                if (elect_one_sync()) {
+                    const uint32_t lfull = mapa_u32(smem_u32(full_bar + st), 0);
+                    const uint32_t sa = smem_u32(smem + (size_t)st * STAGE);
+                    if (leader) mbar_arrive_expect_tx(smem_u32(full_bar + st), 2 * STAGE);
+                    else mbar_arrive_cluster(lfull);
+                    tma_load_2d_2cta(sa, &tmap_a, lfull, (int32_t)(kb * 64), (int32_t)m0);
+                    tma_load_2d_2cta(sa + A_BYTES, &tmap_w, lfull, (int32_t)(kb * 64), (int32_t)n0);
+                }
+                __syncwarp();
+                if (++st == S) { st = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: the leader's warp walks the loop, one elected lane drives the pair =====
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc_f16(256, BN);
+            uint32_t st = 0, ph = 0;
+            for (uint32_t i = 0; i < my_tiles; ++i) {
+                const uint32_t acc = i & 1, acc_ph = (i >> 1) & 1;
+                mbar_wait(smem_u32(tempty_bar + acc), acc_ph ^ 1);
+                tc_fence_after();
+                for (uint32_t kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(smem_u32(full_bar + st), ph);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        const uint32_t sa = smem_u32(smem + (size_t)st * STAGE);
+                        const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + A_BYTES);
+#pragma unroll
+                        for (uint32_t k = 0; k < 4; ++k)
+                            umma_f16_2cta(tmem_base + acc * ACC_COLS, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                        umma_commit_2cta(smem_u32(empty_bar + st), 3);                       // frees the stage in BOTH CTAs
+                        if (kb + 1 == nkb) umma_commit_2cta(smem_u32(tfull_bar + acc), 3);   // accumulators ready in BOTH
+                    }
+                    __syncwarp();
+                    if (++st == S) { st = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue (both CTAs): TWO groups of 8 warps, group = accumulator stage = tile parity, each with its own
+        // staging buffer and named barrier -- the bias/GELU/convert code has little ILP, so 4 warps per scheduler instead of
+        // 2 is what keeps the issue slots busy.  In a group, warps w and w+4 share TMEM lane quarter w%4 and own BN/2 columns.
+        const uint32_t grp = (threadIdx.x - 128) >> 8;         // 0/1
+        const uint32_t et = (threadIdx.x - 128) & 255;         // 0..255 within the group
+        const uint32_t t = et & 127;                           // tile row = TMEM lane
+        const uint32_t half = et >> 7;
+        const uint32_t lane_base = ((warp & 3) * 32) << 16;
+        const uint32_t ltempty = mapa_u32(smem_u32(tempty_bar), 0);
+        uint8_t *my_stage = stage_out + (size_t)grp * BOXES * 128 * 128;
+        const uint32_t acc = grp;
+        for (uint32_t i = grp; i < my_tiles; i += 2) {
+            const uint32_t tile = cluster_id + i * n_clusters;
+            const uint32_t m0 = (tile / n_tiles) * 256 + rank * 128, n0 = (tile % n_tiles) * BN;
+            const uint32_t acc_ph = (i >> 1) & 1;
+            if (et < BN) bias_s[acc * BN + et] = g.bias[n0 + et];   // safe: this group's previous tile was fully drained
+            if (et == 0) tma_store_wait_read();               // the group's previous TMA stores have consumed its staging
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");
+            mbar_wait(smem_u32(tfull_bar + acc), acc_ph);
+            tc_fence_after();
+            const uint32_t sw = (t & 7) << 4;
+#pragma unroll 1
+            for (uint32_t c = half * CH; c < half * CH + CH; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + lane_base + acc * ACC_COLS + c * 32, r);
+                tmem_ld_wait();
+                __align__(16) __half o[32];
+#pragma unroll
+                for (uint32_t j = 0; j < 32; ++j) {
+                    float v = __uint_as_float(r[j]) + bias_s[acc * BN + c * 32 + j];
+                    if constexpr (EPI == EPI_BIAS_GELU) v = gelu_erf(v);
+                    o[j] = __float2half_rn(v);
+                }
+                uint8_t *rowp = my_stage + (size_t)(c >> 1) * (128 * 128) + (size_t)t * 128;
+#pragma unroll
+                for (uint32_t q = 0; q < 4; ++q)
+                    *reinterpret_cast<uint4 *>(rowp + ((((c & 1) * 4 + q) << 4) ^ sw)) = reinterpret_cast<const uint4 *>(o)[q];
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(ltempty + 8 * acc);           // accumulator drained (counted in the leader)
+            fence_proxy_async();                              // generic smem writes -> visible to the TMA engine
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");
+            if (et == 0) {
+#pragma unroll
+                for (uint32_t bx = 0; bx < BOXES; ++bx)
+                    tma_store_2d(&tmap_out, smem_u32(my_stage + bx * 128 * 128), (int32_t)(n0 + bx * 64), (int32_t)m0);
+                tma_store_commit();
+            }
+        }
+        if (et == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    cluster_sync_all();              // nobody may still signal or read the peer's barriers / TMEM
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, 512);
+    }
+}
+
+// ---- LayerNorm GEMM on a CTA PAIR: out = LayerNorm(A . W^T + bias + residual), N = 384 ---------------------
+// The one-CTA form above streams the whole weight matrix into EVERY CTA (64 KB per K-block for 6.3 MFLOP): measured,
+// its main loop runs at the L2->SM bandwidth, not at the tensor rate (attention-out: 6.6-9 us for 2.7 us of MMAs), and
+// its second epilogue pass spends 5-6 us in row-strided 16-byte global stores.  Here two CTAs own 256 rows: each stages
+// its 128 activation rows and HALF of the weight rows per K-block (40 KB), the pair's MMAs (2 x N = 192) read both
+// halves, every CTA ends up with its 128 rows x 384 columns in TMEM exactly as before -- and pass 2 writes the fp16 rows
+// into the (now idle) ring as swizzled 64-column boxes that six TMA stores drain.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LN_THREADS, 1)
+gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                    const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr uint32_t BN = 384, A_BYTES = 128 * 128, BH_BYTES = 96 * 128, STAGE = A_BYTES + 2 * BH_BYTES;   // 40 KB
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const uint32_t S = g.stages, nkb = g.K / 64;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * STAGE);
+    uint64_t *full_bar = bars, *empty_bar = bars + S, *done_bar = bars + 2 * S;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
+    float *par_s = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~static_cast<uintptr_t>(15));  // [3][BN]
+    float *part = par_s + 3 * BN;                                                                                      // [4][128][2]
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < S; ++i) {
+            mbar_init(smem_u32(full_bar + i), 2);
+            mbar_init(smem_u32(empty_bar + i), 1);
+        }
+        mbar_init(smem_u32(done_bar), 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_out);
+    }
+    cluster_sync_all();
+    if (warp == 2) tmem_alloc2(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t m0 = (blockIdx.x >> 1) * 256 + rank * 128;
+    pdl_wait();                                            // activations come from the previous kernel of the forward
+    pdl_trigger();
+
+    if (warp == 0) {
+        uint32_t st = 0, ph = 0;
+        for (uint32_t kb = 0; kb < nkb; ++kb) {
+            mbar_wait(smem_u32(empty_bar + st), ph ^ 1);
+            if (elect_one_sync()) {
+                const uint32_t lfull = mapa_u32(smem_u32(full_bar + st), 0);
+                const uint32_t sa = smem_u32(smem + (size_t)st * STAGE);
+                if (leader) mbar_arrive_expect_tx(smem_u32(full_bar + st), 2 * STAGE);
+                else mbar_arrive_cluster(lfull);
+                tma_load_2d_2cta(sa, &tmap_a, lfull, (int32_t)(kb * 64), (int32_t)m0);
+                // my half of the weight rows of each of the two N = 192 MMAs
+                tma_load_2d_2cta(sa + A_BYTES, &tmap_w, lfull, (int32_t)(kb * 64), (int32_t)(rank * 96));
+                tma_load_2d_2cta(sa + A_BYTES + BH_BYTES, &tmap_w, lfull, (int32_t)(kb * 64), (int32_t)(192 + rank * 96));
+            }
+            __syncwarp();
+            if (++st == S) { st = 0; ph ^= 1; }
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc_f16(256, 192);
+            uint32_t st = 0, ph = 0;
+            for (uint32_t kb = 0; kb < nkb; ++kb) {
+                mbar_wait(smem_u32(full_bar + st), ph);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t sa = smem_u32(smem + (size_t)st * STAGE);
+                    const uint64_t da = make_sw128_desc(sa);
+#pragma unroll
+                    for (uint32_t h = 0; h < 2; ++h) {
+                        const uint64_t db = make_sw128_desc(sa + A_BYTES + h * BH_BYTES);
+#pragma unroll
+                        for (uint32_t k = 0; k < 4; ++k)
+                            umma_f16_2cta(tmem_base + h * 192, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    }
+                    umma_commit_2cta(smem_u32(empty_bar + st), 3);
+                    if (kb + 1 == nkb) umma_commit_2cta(smem_u32(done_bar), 3);
+                }
+                __syncwarp();
+                if (++st == S) { st = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // epilogue: thread t <-> output row m0 + t <-> TMEM lane t; warps w, w+4, w+8, w+12 share a lane quarter and own a
+        // quarter of the columns each (three 32-column chunks)
+        const uint32_t et = threadIdx.x - 128;
+        const uint32_t t = et & 127, qtr = et >> 7;
+        const uint32_t row = m0 + t;
+        const uint32_t lane_base = ((warp & 3) * 32) << 16;
+        constexpr uint32_t CH = 3;
+        for (uint32_t i = et; i < BN; i += 512) {
+            par_s[i] = g.bias[i];
+            par_s[BN + i] = g.gamma[i];
+            par_s[2 * BN + i] = g.beta[i];
+        }
+        uint4 rv[12];                                       // this thread's quarter of the residual row, fetched under the main loop
+        {
+            const uint4 *res4 = reinterpret_cast<const uint4 *>(g.residual + (size_t)row * BN) + qtr * 12;
+#pragma unroll
+            for (uint32_t q = 0; q < 12; ++q) rv[q] = row < g.rows ? res4[q] : make_uint4(0, 0, 0, 0);
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        mbar_wait(smem_u32(done_bar), 0);
+        tc_fence_after();
+        const float4 *bias4 = reinterpret_cast<const float4 *>(par_s);
+        const float4 *gam4 = reinterpret_cast<const float4 *>(par_s + BN);
+        const float4 *bet4 = reinterpret_cast<const float4 *>(par_s + 2 * BN);
+        float sum = 0.0f, sq = 0.0f;
+#pragma unroll
+        for (uint32_t ci = 0; ci < CH; ++ci) {
+            const uint32_t c = qtr * CH + ci;
+            uint32_t r[32];
+            tmem_ld32(tmem_base + lane_base + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (uint32_t q = 0; q < 8; ++q) {
+                const float4 bb = bias4[c * 8 + q];
+                const __half2 *hp = reinterpret_cast<const __half2 *>(&rv[ci * 4 + (q >> 1)]) + (q & 1) * 2;
+                const float2 r01 = __half22float2(hp[0]), r23 = __half22float2(hp[1]);
+                const float v0 = __uint_as_float(r[4 * q]) + bb.x + r01.x, v1 = __uint_as_float(r[4 * q + 1]) + bb.y + r01.y;
+                const float v2 = __uint_as_float(r[4 * q + 2]) + bb.z + r23.x, v3 = __uint_as_float(r[4 * q + 3]) + bb.w + r23.y;
+                sum += (v0 + v1) + (v2 + v3);
+                sq += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
+                r[4 * q] = __float_as_uint(v0); r[4 * q + 1] = __float_as_uint(v1);
+                r[4 * q + 2] = __float_as_uint(v2); r[4 * q + 3] = __float_as_uint(v3);
+            }
+            tmem_st32(tmem_base + lane_base + c * 32, r);
+        }
+        tmem_st_wait();
+        part[(qtr * 128 + t) * 2] = sum;
+        part[(qtr * 128 + t) * 2 + 1] = sq;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        sum = (part[t * 2] + part[(128 + t) * 2]) + (part[(256 + t) * 2] + part[(384 + t) * 2]);
+        sq = (part[t * 2 + 1] + part[(128 + t) * 2 + 1]) + (part[(256 + t) * 2 + 1] + part[(384 + t) * 2 + 1]);
+        const float mean = sum / (float)BN;
+        const float var = fmaxf(sq / (float)BN - mean * mean, 0.0f);
+        const float rstd = rsqrtf(var + g.eps);
+        // pass 2: normalise from TMEM into the idle ring as six swizzled 64-column boxes (box = 128 rows x 128 bytes)
+        uint8_t *stage_out = smem;
+        const uint32_t sw = (t & 7) << 4;
+#pragma unroll 1
+        for (uint32_t c = qtr * CH; c < qtr * CH + CH; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + lane_base + c * 32, r);
+            tmem_ld_wait();
+            __align__(16) __half o[32];
+#pragma unroll
+            for (uint32_t q = 0; q < 8; ++q) {
+                const float4 gg = gam4[c * 8 + q], be = bet4[c * 8 + q];
+                float y[4];
+                y[0] = (__uint_as_float(r[4 * q]) - mean) * rstd * gg.x + be.x;
+                y[1] = (__uint_as_float(r[4 * q + 1]) - mean) * rstd * gg.y + be.y;
+                y[2] = (__uint_as_float(r[4 * q + 2]) - mean) * rstd * gg.z + be.z;
+                y[3] = (__uint_as_float(r[4 * q + 3]) - mean) * rstd * gg.w + be.w;
+#pragma unroll
+                for (uint32_t j = 0; j < 4; ++j) o[4 * q + j] = __float2half_rn(y[j]);
+                if (g.out_f32 && row < g.rows)
+                    *reinterpret_cast<float4 *>(g.out_f32 + (size_t)row * BN + c * 32 + 4 * q) = make_float4(y[0], y[1], y[2], y[3]);
+            }
+            uint8_t *rowp = stage_out + (size_t)(c >> 1) * (128 * 128) + (size_t)t * 128;
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4 *>(rowp + ((((c & 1) * 4 + q) << 4) ^ sw)) = reinterpret_cast<const uint4 *>(o)[q];
+        }
+        fence_proxy_async();                                  // generic smem writes -> visible to the TMA engine
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (et == 0) {
+#pragma unroll
+            for (uint32_t bx = 0; bx < 6; ++bx)
+                tma_store_2d(&tmap_out, smem_u32(stage_out + bx * 128 * 128), (int32_t)(bx * 64), (int32_t)m0);
+            tma_store_commit();
+            tma_store_wait_all();
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, 512);
+    }
+}
+
 // ---- embeddings: word + position + token_type(0), LayerNorm -> fp16 ---------------------------------
 // one warp per token; rows >= T (padding up to a multiple of 128) are zeroed.
 __global__ void embed_ln_kernel(const int64_t *__restrict__ ids, uint32_t T, uint32_t T_pad, uint32_t L, uint32_t H,
@@ -574,6 +940,8 @@ __global__ void embed_ln_kernel(const int64_t *__restrict__ ids, uint32_t T, uin
                                 const float *__restrict__ beta, float eps, __half *__restrict__ out)
 {
     const uint32_t tok = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    pdl_wait();
+    pdl_trigger();
     if (tok >= T_pad) return;
     if (tok >= T) {
         for (uint32_t d = lane; d < H; d += 32) out[(size_t)tok * H + d] = __float2half_rn(0.0f);
@@ -611,6 +979,8 @@ attention_kernel(const __half *__restrict__ qkv, const int64_t *__restrict__ mas
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     constexpr uint32_t D = 32;
+    pdl_wait();
+    pdl_trigger();
     const uint32_t b = blockIdx.x / heads, h = blockIdx.x % heads;
     const uint32_t LP = L + 1;
     float *kt = reinterpret_cast<float *>(smem_raw);          // [32][L+1]
@@ -676,6 +1046,8 @@ attention_small_kernel(const __half *__restrict__ qkv, const int64_t *__restrict
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     constexpr uint32_t D = 32, DP = 33, QB = 64;
+    pdl_wait();
+    pdl_trigger();
     const uint32_t b = blockIdx.x / heads, h = blockIdx.x % heads;
     const uint32_t q0 = blockIdx.y * QB;
     const uint32_t L4 = (L + 3) & ~3u, SP = L4 + 1, CS = L4 / 4;
@@ -813,94 +1185,139 @@ SG_DEVICE_INLINE uint32_t pack_half2(float lo, float hi)
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
+SG_DEVICE_INLINE float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+SG_DEVICE_INLINE void ldmatrix_x4(uint32_t (&r)[4], uint32_t smem_addr)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr));
+}
+SG_DEVICE_INLINE void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t smem_addr)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr));
+}
+
+// Q, K and V of one (sequence, head) sit ROW-MAJOR in shared memory ([row][32] halfs at a pitch of 40 halfs = 80 bytes:
+// eight consecutive rows start in eight different 16-byte bank groups, so every ldmatrix phase is conflict-free), copied
+// with one 16-byte load + one 16-byte store per thread and piece.  The fragments come from ldmatrix: Q as the A operand,
+// K rows as the (col-major) B operand of Q K^T, and V through ldmatrix.trans as the B operand of P V -- the first version
+// transposed V with eight scalar 2-byte stores per thread, which was the top line of the kernel's profile.
 template <uint32_t KS>   // KS = L16 / 16: 16-key steps (1..8)
 __global__ void __launch_bounds__(128)
 attention_mma_kernel(const __half *__restrict__ qkv, const int64_t *__restrict__ mask, uint32_t L, uint32_t H,
                      uint32_t heads, __half *__restrict__ ctx)
 {
-    constexpr uint32_t D = 32, L16 = KS * 16, NT = KS * 2, KP = 40, VP = L16 + 8;
-    __shared__ __align__(16) __half Ks[L16 * KP];
-    __shared__ __align__(16) __half Vt[D * VP];
+    constexpr uint32_t D = 32, L16 = KS * 16, NT = KS * 2, P = 40;
+    __shared__ __align__(16) __half Ks[L16 * P];
+    __shared__ __align__(16) __half Vs[L16 * P];
+    __shared__ __align__(16) __half Qs[64 * P];
     __shared__ float mbias[L16];                       // 0 for live keys, -inf for masked / padding
     const uint32_t b = blockIdx.x / heads, h = blockIdx.x % heads;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t g = lane >> 2, tq = lane & 3;       // fragment row group / quad lane
     const size_t row_stride = 3 * (size_t)H;
-    const __half *base = qkv + (size_t)b * L * row_stride;
     const float NEG_INF = -__uint_as_float(0x7F800000u);
-    for (uint32_t i = threadIdx.x; i < L16 * 4; i += blockDim.x) {
-        const uint32_t j = i >> 2, part = i & 3;
-        uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-        if (j < L) {
-            kv = *reinterpret_cast<const uint4 *>(base + j * row_stride + H + h * D + part * 8);
-            vv = *reinterpret_cast<const uint4 *>(base + j * row_stride + 2 * H + h * D + part * 8);
-        }
-        *reinterpret_cast<uint4 *>(Ks + (size_t)j * KP + part * 8) = kv;
-        const __half *vh = reinterpret_cast<const __half *>(&vv);
-#pragma unroll
-        for (uint32_t e = 0; e < 8; ++e) Vt[(size_t)(part * 8 + e) * VP + j] = vh[e];
-    }
     for (uint32_t j = threadIdx.x; j < L16; j += blockDim.x)
         mbias[j] = (j < L && mask[(size_t)b * L + j] == 1) ? 0.0f : NEG_INF;
+    pdl_wait();                                        // qkv comes from the QKV GEMM
+    pdl_trigger();
+    const __half *base = qkv + (size_t)b * L * row_stride + h * D;
+    const uint32_t q_row0 = blockIdx.y * 64;
+    {   // thread -> (row tid/4 + 32 it, 16-byte piece tid%4); all loads of the CTA are issued before the first store
+        const uint32_t part = threadIdx.x & 3, j0 = threadIdx.x >> 2;
+        constexpr uint32_t KIT = L16 / 32 + (L16 % 32 ? 1 : 0);
+        uint4 kv[KIT], vv[KIT], qv[2];
+#pragma unroll
+        for (uint32_t it = 0; it < KIT; ++it) {
+            const uint32_t j = j0 + it * 32;
+            kv[it] = vv[it] = make_uint4(0, 0, 0, 0);
+            if (j < L) {
+                kv[it] = *reinterpret_cast<const uint4 *>(base + j * row_stride + H + part * 8);
+                vv[it] = *reinterpret_cast<const uint4 *>(base + j * row_stride + 2 * H + part * 8);
+            }
+        }
+#pragma unroll
+        for (uint32_t it = 0; it < 2; ++it) {
+            const uint32_t j = j0 + it * 32;
+            qv[it] = make_uint4(0, 0, 0, 0);
+            if (q_row0 + j < L) qv[it] = *reinterpret_cast<const uint4 *>(base + (size_t)(q_row0 + j) * row_stride + part * 8);
+        }
+#pragma unroll
+        for (uint32_t it = 0; it < KIT; ++it) {
+            const uint32_t j = j0 + it * 32;
+            if (j < L16) {
+                *reinterpret_cast<uint4 *>(Ks + (size_t)j * P + part * 8) = kv[it];
+                *reinterpret_cast<uint4 *>(Vs + (size_t)j * P + part * 8) = vv[it];
+            }
+        }
+#pragma unroll
+        for (uint32_t it = 0; it < 2; ++it) *reinterpret_cast<uint4 *>(Qs + (size_t)(j0 + it * 32) * P + part * 8) = qv[it];
+    }
     __syncthreads();
 
-    const uint32_t r0 = blockIdx.y * 64 + warp * 16 + g;     // this thread's rows: r0 and r0 + 8
-    if (blockIdx.y * 64 + warp * 16 >= L) return;
-    // Q fragments for both k-steps (d 0..15, 16..31), straight from global memory
+    const uint32_t r0 = q_row0 + warp * 16 + g;        // this thread's rows: r0 and r0 + 8
+    if (q_row0 + warp * 16 >= L) return;
+    // Q fragments for both k-steps (d 0..15, 16..31): matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15)
     uint32_t qa[2][4];
-#pragma unroll
-    for (uint32_t ks = 0; ks < 2; ++ks) {
-        const uint32_t d0 = ks * 16 + tq * 2;
-        const __half *q0 = base + (size_t)r0 * row_stride + h * D;
-        const __half *q1 = base + (size_t)(r0 + 8) * row_stride + h * D;
-        qa[ks][0] = r0 < L ? *reinterpret_cast<const uint32_t *>(q0 + d0) : 0u;
-        qa[ks][1] = r0 + 8 < L ? *reinterpret_cast<const uint32_t *>(q1 + d0) : 0u;
-        qa[ks][2] = r0 < L ? *reinterpret_cast<const uint32_t *>(q0 + d0 + 8) : 0u;
-        qa[ks][3] = r0 + 8 < L ? *reinterpret_cast<const uint32_t *>(q1 + d0 + 8) : 0u;
+    {
+        const uint32_t qaddr = smem_u32(Qs + (size_t)(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * P + (lane >> 4) * 8);
+        ldmatrix_x4(qa[0], qaddr);
+        ldmatrix_x4(qa[1], qaddr + 32);
     }
-    // S = Q K^T
+    // S = Q K^T: per 8-key tile one ldmatrix.x4 = the B fragments of both k-steps
     float sacc[NT][4];
+    const uint32_t kaddr = smem_u32(Ks + (size_t)(lane & 7) * P + (lane >> 3) * 8);
 #pragma unroll
     for (uint32_t nt = 0; nt < NT; ++nt) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) sacc[nt][e] = 0.0f;
-#pragma unroll
-        for (uint32_t ks = 0; ks < 2; ++ks) {
-            const __half *kp = Ks + (size_t)(nt * 8 + g) * KP + ks * 16 + tq * 2;
-            mma_m16n8k16(sacc[nt], qa[ks], *reinterpret_cast<const uint32_t *>(kp), *reinterpret_cast<const uint32_t *>(kp + 8));
-        }
+        uint32_t kb[4];
+        ldmatrix_x4(kb, kaddr + nt * 8 * P * 2);
+        mma_m16n8k16(sacc[nt], qa[0], kb[0], kb[1]);
+        mma_m16n8k16(sacc[nt], qa[1], kb[2], kb[3]);
     }
-    // masked softmax on the fragments: rows r0 (elements 0,1) and r0+8 (elements 2,3)
-    const float scale = 0.17677669529663687f;
+    // masked softmax on the fragments: rows r0 (elements 0,1) and r0+8 (elements 2,3).  Scores are kept in the log2 domain
+    // (1/sqrt(d) and log2(e) folded into one factor) so that a probability is ONE ex2.approx of a difference; a fully
+    // masked row gets max = 0, and 2^(-inf) = 0 does the rest.
+    const float scale = 0.17677669529663687f * 1.4426950408889634f;
     float mx0 = NEG_INF, mx1 = NEG_INF;
 #pragma unroll
     for (uint32_t nt = 0; nt < NT; ++nt) {
-        const float b0 = mbias[nt * 8 + tq * 2], b1 = mbias[nt * 8 + tq * 2 + 1];
-        sacc[nt][0] = sacc[nt][0] * scale + b0; sacc[nt][1] = sacc[nt][1] * scale + b1;
-        sacc[nt][2] = sacc[nt][2] * scale + b0; sacc[nt][3] = sacc[nt][3] * scale + b1;
+        const float2 bb = *reinterpret_cast<const float2 *>(mbias + nt * 8 + tq * 2);
+        sacc[nt][0] = fmaf(sacc[nt][0], scale, bb.x); sacc[nt][1] = fmaf(sacc[nt][1], scale, bb.y);
+        sacc[nt][2] = fmaf(sacc[nt][2], scale, bb.x); sacc[nt][3] = fmaf(sacc[nt][3], scale, bb.y);
         mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
         mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xFFFFFFFFu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xFFFFFFFFu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xFFFFFFFFu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xFFFFFFFFu, mx1, 2));
+    if (!(mx0 > NEG_INF)) mx0 = 0.0f;
+    if (!(mx1 > NEG_INF)) mx1 = 0.0f;
     float sum0 = 0.0f, sum1 = 0.0f;
 #pragma unroll
     for (uint32_t nt = 0; nt < NT; ++nt) {
-        sacc[nt][0] = mx0 > NEG_INF ? __expf(sacc[nt][0] - mx0) : 0.0f;
-        sacc[nt][1] = mx0 > NEG_INF ? __expf(sacc[nt][1] - mx0) : 0.0f;
-        sacc[nt][2] = mx1 > NEG_INF ? __expf(sacc[nt][2] - mx1) : 0.0f;
-        sacc[nt][3] = mx1 > NEG_INF ? __expf(sacc[nt][3] - mx1) : 0.0f;
+        sacc[nt][0] = ex2_approx(sacc[nt][0] - mx0);
+        sacc[nt][1] = ex2_approx(sacc[nt][1] - mx0);
+        sacc[nt][2] = ex2_approx(sacc[nt][2] - mx1);
+        sacc[nt][3] = ex2_approx(sacc[nt][3] - mx1);
         sum0 += sacc[nt][0] + sacc[nt][1];
         sum1 += sacc[nt][2] + sacc[nt][3];
     }
     sum0 += __shfl_xor_sync(0xFFFFFFFFu, sum0, 1); sum0 += __shfl_xor_sync(0xFFFFFFFFu, sum0, 2);
     sum1 += __shfl_xor_sync(0xFFFFFFFFu, sum1, 1); sum1 += __shfl_xor_sync(0xFFFFFFFFu, sum1, 2);
-    // O = P V : per 16-key step, the P A-fragment is built from two adjacent S tiles
+    // O = P V : per 16-key step, the P A-fragment is built from two adjacent S tiles; V^T fragments by ldmatrix.trans:
+    // matrices (keys 0-7 | 8-15) x (d tile dt | dt + 1)
     float oacc[4][4];
 #pragma unroll
     for (uint32_t dt = 0; dt < 4; ++dt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) oacc[dt][e] = 0.0f;
+    const uint32_t vaddr = smem_u32(Vs + (size_t)((lane & 7) + ((lane >> 3) & 1) * 8) * P + (lane >> 4) * 8);
 #pragma unroll
     for (uint32_t ks = 0; ks < KS; ++ks) {
         uint32_t pa[4];
@@ -909,9 +1326,11 @@ attention_mma_kernel(const __half *__restrict__ qkv, const int64_t *__restrict__
         pa[2] = pack_half2(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1]);
         pa[3] = pack_half2(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3]);
 #pragma unroll
-        for (uint32_t dt = 0; dt < 4; ++dt) {
-            const __half *vp = Vt + (size_t)(dt * 8 + g) * VP + ks * 16 + tq * 2;
-            mma_m16n8k16(oacc[dt], pa, *reinterpret_cast<const uint32_t *>(vp), *reinterpret_cast<const uint32_t *>(vp + 8));
+        for (uint32_t dp = 0; dp < 2; ++dp) {
+            uint32_t vb[4];
+            ldmatrix_x4_trans(vb, vaddr + (ks * 16 * P + dp * 16) * 2);
+            mma_m16n8k16(oacc[2 * dp], pa, vb[0], vb[1]);
+            mma_m16n8k16(oacc[2 * dp + 1], pa, vb[2], vb[3]);
         }
     }
     const float inv0 = sum0 > 0.0f ? 1.0f / sum0 : 0.0f, inv1 = sum1 > 0.0f ? 1.0f / sum1 : 0.0f;
@@ -929,7 +1348,7 @@ template <uint32_t KS>
 void launch_attention_mma(const __half *qkv, const int64_t *mask, uint32_t b, uint32_t L, uint32_t H, uint32_t heads,
                           __half *ctx, cudaStream_t st)
 {
-    attention_mma_kernel<KS><<<dim3(b * heads, (L + 63) / 64), 128, 0, st>>>(qkv, mask, L, H, heads, ctx);
+    launch_pdl(attention_mma_kernel<KS>, dim3(b * heads, (L + 63) / 64), dim3(128), 0, st, qkv, mask, L, H, heads, ctx);
 }
 
 // ---- masked mean-pool + finalize (reference minilm.rs:959-978, :846-878) -----------------------------
@@ -938,18 +1357,37 @@ void launch_attention_mma(const __half *qkv, const int64_t *mask, uint32_t b, ui
 __global__ void pool_norm_kernel(const float *__restrict__ hidden, const int64_t *__restrict__ mask, uint32_t L,
                                  uint32_t H, float *__restrict__ out)
 {
-    extern __shared__ float pooled[];
+    extern __shared__ float pooled[];                  // [H] pooled, then [L] bytes: token is live
     __shared__ float s_norm;
+    uint8_t *live = reinterpret_cast<uint8_t *>(pooled + H);
     const uint32_t b = blockIdx.x;
+    for (uint32_t s = threadIdx.x; s < L; s += blockDim.x) live[s] = mask[(size_t)b * L + s] == 1;
+    pdl_wait();                                        // the hidden states come from the last LayerNorm GEMM
+    pdl_trigger();
+    __syncthreads();
     for (uint32_t d = threadIdx.x; d < H; d += blockDim.x) {
-        float acc = 0.0f, msum = 0.0f;
-        for (uint32_t s = 0; s < L; ++s) {
-            if (mask[(size_t)b * L + s] == 1) {
-                acc = __fadd_rn(acc, hidden[((size_t)b * L + s) * H + d]);
-                msum = __fadd_rn(msum, 1.0f);
-            }
+        // rows are added in token order, masked rows skipped -- the loads of 8 rows are issued together, the adds stay a chain
+        const float *hp = hidden + (size_t)b * L * H + d;
+        float acc = 0.0f;
+        uint32_t cnt = 0, s = 0;
+        for (; s + 8 <= L; s += 8) {
+            float v[8];
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) v[j] = hp[(size_t)(s + j) * H];
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j)
+                if (live[s + j]) {
+                    acc = __fadd_rn(acc, v[j]);
+                    ++cnt;
+                }
         }
-        if (msum > 0.0f) acc = __fdiv_rn(acc, msum);
+        for (; s < L; ++s)
+            if (live[s]) {
+                acc = __fadd_rn(acc, hp[(size_t)s * H]);
+                ++cnt;
+            }
+        // mask_sum is a sum of 1.0f: exact in f32 for any L <= 2^24
+        if (cnt > 0) acc = __fdiv_rn(acc, (float)cnt);
         if (isnan(acc) || isinf(acc)) acc = 0.0f;
         pooled[d] = acc;
     }
@@ -988,9 +1426,9 @@ cudaError_t launch_gemm(const CUtensorMap &ta, const CUtensorMap &tw, const Gemm
     auto kern = gemm_tc_kernel<BN, EPI>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<dim3(m_tiles, g.N / BN), EPI == EPI_BIAS_RES_LN ? LN_THREADS : G_THREADS, smem, st>>>(ta, tw, g);
+    e = launch_pdl(kern, dim3(m_tiles, g.N / BN), dim3(EPI == EPI_BIAS_RES_LN ? LN_THREADS : G_THREADS), smem, st, ta, tw, g);
     count_launch();
-    return cudaGetLastError();
+    return e;
 }
 
 template <uint32_t EPI>
@@ -1003,9 +1441,39 @@ cudaError_t launch_gemm_persist(const CUtensorMap &ta, const CUtensorMap &tw, co
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const uint32_t grid = total < 2 * sm_count ? total : 2 * sm_count;
-    kern<<<grid, P_THREADS, smem, st>>>(ta, tw, tout, g, m_tiles, n_tiles);
+    e = launch_pdl(kern, dim3(grid), dim3(P_THREADS), smem, st, ta, tw, tout, g, m_tiles, n_tiles);
     count_launch();
-    return cudaGetLastError();
+    return e;
+}
+
+template <uint32_t BN, uint32_t EPI>
+cudaError_t launch_gemm_pair(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &tout, const GemmArgs &g,
+                             uint32_t m_tiles, uint32_t sm_count, cudaStream_t st)
+{
+    const uint32_t n_tiles = g.N / BN, m_pairs = (m_tiles + 1) / 2, total = m_pairs * n_tiles;
+    const size_t smem = (size_t)g.stages * (128 * 128 + (BN / 2) * 128) + 2 * (BN / 64) * 128 * 128 + (2 * g.stages + 4) * 8 + 48 +
+                        2 * BN * 4;
+    auto kern = gemm_tc_pair_kernel<BN, EPI>;
+    static DevAttr da;
+    cudaError_t e = ensure_smem(kern, da, smem);
+    if (e != cudaSuccess) return e;
+    const uint32_t pairs = total < sm_count / 2 ? total : sm_count / 2;
+    e = launch_pdl(kern, dim3(2 * pairs), dim3(LN_THREADS), smem, st, ta, tw, tout, g, m_pairs, n_tiles);
+    count_launch();
+    return e;
+}
+
+cudaError_t launch_gemm_ln_pair(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &tout, const GemmArgs &g,
+                                uint32_t m_tiles, cudaStream_t st)
+{
+    const size_t ring = (size_t)g.stages * (128 * 128 + 2 * 96 * 128);
+    const size_t smem = (ring > 6 * 128 * 128 ? ring : 6 * 128 * 128) + (2 * g.stages + 1) * 8 + 48 + 3 * 384 * 4 + 4 * 128 * 2 * 4;
+    static DevAttr da;
+    cudaError_t e = ensure_smem(gemm_ln_pair_kernel, da, smem);
+    if (e != cudaSuccess) return e;
+    e = launch_pdl(gemm_ln_pair_kernel, dim3((m_tiles + 1) / 2 * 2), dim3(LN_THREADS), smem, st, ta, tw, tout, g);
+    count_launch();
+    return e;
 }
 
 cudaError_t launch_gemm_ln_cluster(const CUtensorMap &ta, const CUtensorMap &tw, const GemmArgs &g, uint32_t m_tiles,
@@ -1014,9 +1482,9 @@ cudaError_t launch_gemm_ln_cluster(const CUtensorMap &ta, const CUtensorMap &tw,
     const size_t smem = (size_t)g.stages * (128 * 128 + 128 * 128) + (2 * g.stages + 1) * 8 + 48 + 3 * 128 * 4 + 2 * 128 * 2 * 4;
     cudaError_t e = cudaFuncSetAttribute(gemm_ln_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    gemm_ln_cluster_kernel<<<m_tiles * 3, P_THREADS, smem, st>>>(ta, tw, g);    // __cluster_dims__(3,1,1)
+    e = launch_pdl(gemm_ln_cluster_kernel, dim3(m_tiles * 3), dim3(P_THREADS), smem, st, ta, tw, g);    // __cluster_dims__(3,1,1)
     count_launch();
-    return cudaGetLastError();
+    return e;
 }
 
 struct Layer {
@@ -1233,8 +1701,9 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
     }
     // ctx rows beyond T are never written by attention: keep them finite
     SG_CUDA_TRY(cudaMemsetAsync(e->ctx, 0, (size_t)T_pad * H * 2, st));
-    embed_ln_kernel<<<(T_pad * 32 + 255) / 256, 256, 0, st>>>(d_ids, T, T_pad, L, H, e->vocab, e->word, e->pos, e->type0,
-                                                               e->emb_g, e->emb_b, e->eps, e->h0);
+    SG_CUDA_TRY(launch_pdl(embed_ln_kernel, dim3((T_pad * 32 + 255) / 256), dim3(256), 0, st, d_ids, T, T_pad, L, H, e->vocab,
+                           (const float *)e->word, (const float *)e->pos, (const float *)e->type0, (const float *)e->emb_g,
+                           (const float *)e->emb_b, e->eps, e->h0));
     count_launch();
     CUtensorMap t_h0, t_h1, t_ctx, t_mid, t_qkv_out;
     if ((rc = encode_tmap(&t_h0, e->h0, H, T_pad, 128)) != SG_OK) return rc;
@@ -1250,6 +1719,17 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
     // 1114 vs 935 us at 256 queries)
     const bool ln_cluster = m_tiles * 3 <= 148 && !getenv("SG_ENC_NO_LN_CLUSTER");
     const bool persist = m_tiles * 9 >= 2 * 148 && !getenv("SG_ENC_NO_PERSIST");   // enough tiles to fill 2 CTAs per SM
+    // timing experiments only (results are garbage): bit 0 QKV, 1 attention, 2 attention-out+LN, 3 FFN-up, 4 FFN-down+LN
+    // CTA-pair 256x192 tiles once the batch fills the GPU (L2 traffic per FLOP 1.75x lower than 128x128 tiles)
+    const bool pair = persist && (3 * H) % 192 == 0 && F % 192 == 0 && !getenv("SG_ENC_NO_PAIR");
+    unsigned long long *d_trace = nullptr;             // SG_ENC_TRACE=1: phase stamps of layer 0's two LayerNorm GEMMs (debug)
+    if (getenv("SG_ENC_TRACE") && !ln_cluster) {
+        SG_CUDA_TRY(cudaMalloc(&d_trace, (size_t)2 * m_tiles * 8 * 8));
+        SG_CUDA_TRY(cudaMemsetAsync(d_trace, 0, (size_t)2 * m_tiles * 8 * 8, st));
+    }
+    const bool ln_pair = !ln_cluster && H == 384 && !getenv("SG_ENC_NO_LN_PAIR");
+    const char *skip_env = getenv("SG_ENC_SKIP");
+    const int skip = skip_env ? atoi(skip_env) : 0;
     for (uint32_t l = 0; l < e->layers; ++l) {
         const Layer &ly = e->L[l];
         CUtensorMap t_wqkv, t_wo, t_w1, t_w2;
@@ -1260,12 +1740,19 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
         GemmArgs g{};
         // QKV = h0 . Wqkv^T + b
         g.K = H; g.N = 3 * H; g.stages = 3; g.bias = ly.bqkv; g.out = e->qkv;   // 96 KB: two CTAs per SM
-        if (persist) {
+        if (skip & 1) {
+        } else if (pair) {
+            CUtensorMap t_wqkv_half;
+            if ((rc = encode_tmap(&t_wqkv_half, ly.wqkv, H, 3 * H, 96)) != SG_OK) return rc;
+            g.stages = 4;
+            SG_CUDA_TRY((launch_gemm_pair<192, EPI_BIAS>(t_h0, t_wqkv_half, t_qkv_out, g, m_tiles, 148, st)));
+        } else if (persist) {
             g.stages = 2;
             SG_CUDA_TRY((launch_gemm_persist<EPI_BIAS>(t_h0, t_wqkv, t_qkv_out, g, m_tiles, 148, st)));
         }
         else SG_CUDA_TRY((launch_gemm<128, EPI_BIAS>(t_h0, t_wqkv, g, m_tiles, st)));
-        if (L <= 128 && !getenv("SG_ENC_ATTN_SIMT")) {
+        if (skip & 2) {
+        } else if (L <= 128 && !getenv("SG_ENC_ATTN_SIMT")) {
             switch ((L + 15) / 16) {
             case 1: launch_attention_mma<1>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st); break;
             case 2: launch_attention_mma<2>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st); break;
@@ -1281,25 +1768,40 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
             const size_t sm = ((size_t)2 * L4 * 33 + 64 * 33 + (size_t)64 * (L4 + 1)) * 4;
             if (sm > 48 * 1024)
                 SG_CUDA_TRY(cudaFuncSetAttribute(attention_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            attention_small_kernel<<<dim3(b * e->heads, (L + 63) / 64), 128, sm, st>>>(e->qkv, d_mask, L, H, e->heads, e->ctx);
+            SG_CUDA_TRY(launch_pdl(attention_small_kernel, dim3(b * e->heads, (L + 63) / 64), dim3(128), sm, st, (const __half *)e->qkv,
+                                   d_mask, L, H, e->heads, e->ctx));
         } else {
-            attention_kernel<<<b * e->heads, 128, att_smem, st>>>(e->qkv, d_mask, L, H, e->heads, e->ctx);
+            SG_CUDA_TRY(launch_pdl(attention_kernel, dim3(b * e->heads), dim3(128), att_smem, st, (const __half *)e->qkv, d_mask, L, H,
+                                   e->heads, e->ctx));
         }
         count_launch();
         // h1 = LN(ctx . Wo^T + b + h0)
         g = GemmArgs{};
         g.K = H; g.N = H; g.stages = 3; g.bias = ly.bo; g.residual = e->h0; g.gamma = ly.ln1_g; g.beta = ly.ln1_b;
         g.eps = e->eps; g.out = e->h1;
-        if (ln_cluster) {
+        if (skip & 4) {
+        } else if (ln_cluster) {
             g.stages = 6;
             SG_CUDA_TRY(launch_gemm_ln_cluster(t_ctx, t_wo, g, m_tiles, st));
+        } else if (ln_pair) {
+            CUtensorMap t_wo_half;
+            if ((rc = encode_tmap(&t_wo_half, ly.wo, H, H, 96)) != SG_OK) return rc;
+            g.stages = 4; g.rows = T_pad;
+            SG_CUDA_TRY(launch_gemm_ln_pair(t_ctx, t_wo_half, t_h1, g, m_tiles, st));
         } else {
+            g.trace = l == 0 ? d_trace : nullptr;
             SG_CUDA_TRY((launch_gemm<384, EPI_BIAS_RES_LN>(t_ctx, t_wo, g, m_tiles, st)));
         }
         // mid = gelu(h1 . W1^T + b)
         g = GemmArgs{};
         g.K = H; g.N = F; g.stages = 3; g.bias = ly.b1; g.out = e->mid;
-        if (persist) {
+        if (skip & 8) {
+        } else if (pair) {
+            CUtensorMap t_w1_half;
+            if ((rc = encode_tmap(&t_w1_half, ly.w1, H, F, 96)) != SG_OK) return rc;
+            g.stages = 4;
+            SG_CUDA_TRY((launch_gemm_pair<192, EPI_BIAS_GELU>(t_h1, t_w1_half, t_mid, g, m_tiles, 148, st)));
+        } else if (persist) {
             g.stages = 2;
             SG_CUDA_TRY((launch_gemm_persist<EPI_BIAS_GELU>(t_h1, t_w1, t_mid, g, m_tiles, 148, st)));
         }
@@ -1308,16 +1810,48 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
         g = GemmArgs{};
         g.K = F; g.N = H; g.stages = 3; g.bias = ly.b2; g.residual = e->h1; g.gamma = ly.ln2_g; g.beta = ly.ln2_b;
         g.eps = e->eps; g.out = e->h0; g.out_f32 = (l + 1 == e->layers) ? e->hf32 : nullptr;
-        if (ln_cluster) {
+        if (skip & 16) {
+        } else if (ln_cluster) {
             g.stages = 6;
             SG_CUDA_TRY(launch_gemm_ln_cluster(t_mid, t_w2, g, m_tiles, st));
+        } else if (ln_pair) {
+            CUtensorMap t_w2_half;
+            if ((rc = encode_tmap(&t_w2_half, ly.w2, F, H, 96)) != SG_OK) return rc;
+            g.stages = 4; g.rows = T_pad;
+            SG_CUDA_TRY(launch_gemm_ln_pair(t_mid, t_w2_half, t_h0, g, m_tiles, st));
         } else {
+            g.trace = (l == 0 && d_trace) ? d_trace + (size_t)m_tiles * 8 : nullptr;
             SG_CUDA_TRY((launch_gemm<384, EPI_BIAS_RES_LN>(t_mid, t_w2, g, m_tiles, st)));
         }
     }
-    pool_norm_kernel<<<b, 384, H * 4, st>>>(e->hf32, d_mask, L, H, d_out);
+    SG_CUDA_TRY(launch_pdl(pool_norm_kernel, dim3(b), dim3(384), (size_t)H * 4 + L, st, (const float *)e->hf32, d_mask, L, H, d_out));
     count_launch();
     SG_CUDA_TRY(cudaGetLastError());
+    if (d_trace) {
+        std::vector<unsigned long long> h((size_t)2 * m_tiles * 8);
+        SG_CUDA_TRY(cudaStreamSynchronize(st));
+        SG_CUDA_TRY(cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost));
+        cudaFree(d_trace);
+        static const char *names[7] = {"enter", "prologue done", "previous kernel complete", "accumulator complete", "pass 1 done",
+                                       "pass 2 done", "all done"};
+        for (int k = 0; k < 2; ++k) {
+            const unsigned long long *t = h.data() + (size_t)k * m_tiles * 8;
+            unsigned long long t0 = ~0ull;
+            for (uint32_t c = 0; c < m_tiles; ++c)
+                if (t[c * 8] && t[c * 8] < t0) t0 = t[c * 8];
+            fprintf(stderr, "[sg enc trace] %s + LayerNorm, %u CTAs, us since the first CTA entered (min / max over CTAs):", k ? "FFN-down" : "attention-out", m_tiles);
+            for (int i = 0; i < 7; ++i) {
+                unsigned long long mn = ~0ull, mx = 0;
+                for (uint32_t c = 0; c < m_tiles; ++c) {
+                    const unsigned long long v = t[c * 8 + i];
+                    if (v && v < mn) mn = v;
+                    if (v > mx) mx = v;
+                }
+                fprintf(stderr, " %s %.1f/%.1f |", names[i], mn >= t0 && mn != ~0ull ? (mn - t0) / 1e3 : -1.0, mx >= t0 ? (mx - t0) / 1e3 : -1.0);
+            }
+            fprintf(stderr, "\n");
+        }
+    }
     return SG_OK;
 }
 
@@ -1515,7 +2049,7 @@ void sg_encoder_destroy(sg_encoder *e)
 int sg_pool_finalize(int device, const float *hidden, const int64_t *mask, uint32_t b, uint32_t L, uint32_t H, float *out)
 {
     if (b == 0) return SG_OK;
-    if (!hidden || !mask || !out || L == 0 || H == 0 || H > 8192) return SG_ERR_INVALID;
+    if (!hidden || !mask || !out || L == 0 || H == 0 || H > 8192 || L > 8192) return SG_ERR_INVALID;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         set_error("no CUDA device available; libshodh_gpu has no CPU fallback");
@@ -1532,7 +2066,7 @@ int sg_pool_finalize(int device, const float *hidden, const int64_t *mask, uint3
     if (e == cudaSuccess) e = cudaMemcpy(d_h, hidden, hb, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_m, mask, mb, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-        pool_norm_kernel<<<b, H < 384 ? (H + 31) / 32 * 32 : 384, H * 4>>>(d_h, d_m, L, H, d_o);
+        pool_norm_kernel<<<b, H < 384 ? (H + 31) / 32 * 32 : 384, (size_t)H * 4 + L>>>(d_h, d_m, L, H, d_o);
         count_launch();
         e = cudaGetLastError();
     }

@@ -168,7 +168,7 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
     };
 
     const bool tr = a.trace != nullptr && e == 0;
-    unsigned long long *trp = a.trace + (size_t)blockIdx.x * 8;
+    unsigned long long *trp = a.trace + (size_t)blockIdx.x * 16;
     if (tr) trp[0] = gtimer();                       // epilogue entered (prologue: barriers, TMEM, query block)
     uint64_t it = 1;
     if constexpr (!DUMP) {
@@ -412,7 +412,7 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
         }
         tc_fence_before();
         mbar_arrive_cluster(tempty_cluster_addr + 8 * accn);  // all epilogue threads release the accumulator
-        if (tr && it <= 2) trp[4 + it] = gtimer();   // first two tiles of the sweep scanned
+        if (tr && it <= 32 && (it & (it - 1)) == 0) trp[5 + (31 - __clz(it))] = gtimer();   // tiles 1,2,4,8,16,32 scanned
         if (++accn == acc_stages) {
             accn = 0;
             acc_ph ^= 1;
@@ -430,7 +430,7 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
     if constexpr (!DUMP) {
         if (active) a.cnts[(size_t)q * n_lists + list_idx] = my_cnt;
     }
-    if (tr) trp[7] = gtimer();                       // sweep done
+    if (tr) trp[11] = gtimer();                      // sweep done
 }
 
 // ---- K1: the sweep, one CTA per SM (128 queries per sweep) ------------------------------------------

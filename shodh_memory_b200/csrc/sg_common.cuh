@@ -36,6 +36,9 @@ void count_launch(unsigned n = 1);
 // calls pdl_wait() before it touches anything its predecessor wrote (a no-op under a normal launch).
 // ----------------------------------------------------------------------------------------
 SG_DEVICE_INLINE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// lets the NEXT kernel of the stream start its prologue now (it still blocks in its own pdl_wait() until this grid has
+// completed and flushed); fires once every CTA of this grid has called it or exited
+SG_DEVICE_INLINE void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 template <typename K, typename... Args>
 inline cudaError_t launch_pdl(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)

@@ -42,6 +42,7 @@ struct sg_store {
     uint64_t *d_lists = nullptr; size_t lists_cap = 0;  // keys
     uint64_t *d_lists2 = nullptr; size_t lists2_cap = 0; // first-level merge output
     uint32_t *d_ids = nullptr; float *d_dist = nullptr; uint32_t *d_counts = nullptr; size_t res_cap = 0, cnt_cap = 0;
+    uint32_t *d_resblk = nullptr; size_t resblk_cap = 0;   // sg_store_search: ids | distances | counts in one block
     void *h_pinned = nullptr; size_t pinned_cap = 0;
     float *d_stage = nullptr; size_t stage_cap = 0;     // floats, append staging
 

@@ -558,8 +558,8 @@ int search_tc_chunk(sg_store *s, const TcPlan &pl, const float *d_q, uint32_t b,
     unsigned long long *d_trace = nullptr;           // SG_TC_TRACE=1: phase stamps of the sweep, printed to stderr (debug)
     const bool trace = env_u32("SG_TC_TRACE", 0) != 0;
     if (trace) {
-        SG_CUDA_TRY(cudaMalloc(&d_trace, (size_t)pl.grid * 8 * 8));
-        SG_CUDA_TRY(cudaMemsetAsync(d_trace, 0, (size_t)pl.grid * 8 * 8, st));
+        SG_CUDA_TRY(cudaMalloc(&d_trace, (size_t)pl.grid * 16 * 8));
+        SG_CUDA_TRY(cudaMemsetAsync(d_trace, 0, (size_t)pl.grid * 16 * 8, st));
     }
     const bool prof = s->profiling && 2 * (size_t)(s->ev_count + 1) <= s->ev.size();
     if (prof) SG_CUDA_TRY(cudaEventRecord(s->ev[2 * s->ev_count], st));
@@ -602,20 +602,24 @@ int search_tc_chunk(sg_store *s, const TcPlan &pl, const float *d_q, uint32_t b,
         ++s->ev_count;
     }
     if (trace) {
-        std::vector<unsigned long long> h((size_t)pl.grid * 8);
+        std::vector<unsigned long long> h((size_t)pl.grid * 16);
         SG_CUDA_TRY(cudaStreamSynchronize(st));
         SG_CUDA_TRY(cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost));
         cudaFree(d_trace);
-        unsigned long long t0 = ~0ull, mx[8] = {0};
+        unsigned long long t0 = ~0ull, mx[12] = {0}, mn_done = ~0ull;
         for (uint32_t c = 0; c < pl.grid; ++c)
-            if (h[(size_t)c * 8] && h[(size_t)c * 8] < t0) t0 = h[(size_t)c * 8];
-        for (uint32_t c = 0; c < pl.grid; ++c)
-            for (int i = 0; i < 8; ++i)
-                if (h[(size_t)c * 8 + i] > mx[i]) mx[i] = h[(size_t)c * 8 + i];
+            if (h[(size_t)c * 16] && h[(size_t)c * 16] < t0) t0 = h[(size_t)c * 16];
+        for (uint32_t c = 0; c < pl.grid; ++c) {
+            for (int i = 0; i < 12; ++i)
+                if (h[(size_t)c * 16 + i] > mx[i]) mx[i] = h[(size_t)c * 16 + i];
+            if (h[(size_t)c * 16 + 11] && h[(size_t)c * 16 + 11] < mn_done) mn_done = h[(size_t)c * 16 + 11];
+        }
+        auto us = [&](unsigned long long t) { return t >= t0 ? (t - t0) / 1e3 : -1.0; };
         fprintf(stderr, "[sg tc trace] us since the first CTA's epilogue start (max over CTAs): enter %.1f | sample acc ready %.1f | "
-                        "sample scanned %.1f | all arrived %.1f | seeds %.1f | tile1 %.1f | tile2 %.1f | done %.1f\n",
-                (mx[0] - t0) / 1e3, (mx[1] - t0) / 1e3, (mx[2] - t0) / 1e3, (mx[3] - t0) / 1e3, (mx[4] - t0) / 1e3,
-                (mx[5] - t0) / 1e3, (mx[6] - t0) / 1e3, (mx[7] - t0) / 1e3);
+                        "sample scanned %.1f | all arrived %.1f | seeds %.1f | tile 1 %.1f | 2 %.1f | 4 %.1f | 8 %.1f | 16 %.1f | "
+                        "32 %.1f | done %.1f (first CTA done %.1f)\n",
+                us(mx[0]), us(mx[1]), us(mx[2]), us(mx[3]), us(mx[4]), us(mx[5]), us(mx[6]), us(mx[7]), us(mx[8]), us(mx[9]),
+                us(mx[10]), us(mx[11]), us(mn_done));
     }
     FinalizeArgs f{};
     f.queries = d_q;
@@ -790,6 +794,7 @@ void sg_store_destroy(sg_store *s)
     cudaFree(s->d_queries);
     cudaFree(s->d_lists);
     cudaFree(s->d_lists2);
+    cudaFree(s->d_resblk);
     cudaFree(s->d_ids);
     cudaFree(s->d_dist);
     cudaFree(s->d_counts);
@@ -1261,23 +1266,20 @@ int sg_store_search(sg_store *s, const float *queries, uint32_t b, uint32_t k, u
     int rc = grow_pinned(s, qbytes + 2 * rbytes + cbytes);
     if (rc != SG_OK) return rc;
     if ((rc = grow(s->d_queries, s->q_cap, (size_t)b * s->dim)) != SG_OK) return rc;
-    if ((size_t)b * k > s->res_cap) {
-        size_t c1 = s->res_cap, c2 = s->res_cap;
-        if ((rc = grow(s->d_ids, c1, (size_t)b * k)) != SG_OK) return rc;
-        if ((rc = grow(s->d_dist, c2, (size_t)b * k)) != SG_OK) return rc;
-        s->res_cap = c1 < c2 ? c1 : c2;
-    }
-    if ((rc = grow(s->d_counts, s->cnt_cap, (size_t)b)) != SG_OK) return rc;
+    // ids | distances | counts in ONE device block -> one device-to-host copy per search
+    const size_t rwords = (size_t)b * k;
+    if ((rc = grow(s->d_resblk, s->resblk_cap, 2 * rwords + b)) != SG_OK) return rc;
+    uint32_t *d_ids = s->d_resblk;
+    float *d_dist = reinterpret_cast<float *>(s->d_resblk + rwords);
+    uint32_t *d_counts = s->d_resblk + 2 * rwords;
 
     uint8_t *hp = static_cast<uint8_t *>(s->h_pinned);
     memcpy(hp, queries, qbytes);
     if ((rc = chain_begin(s, s->stream)) != SG_OK) return rc;
     SG_CUDA_TRY(cudaMemcpyAsync(s->d_queries, hp, qbytes, cudaMemcpyHostToDevice, s->stream));
-    rc = search_device_locked(s, s->d_queries, b, k, s->d_ids, s->d_dist, s->d_counts, s->stream);
+    rc = search_device_locked(s, s->d_queries, b, k, d_ids, d_dist, d_counts, s->stream);
     if (rc != SG_OK) return rc;
-    SG_CUDA_TRY(cudaMemcpyAsync(hp + qbytes, s->d_ids, rbytes, cudaMemcpyDeviceToHost, s->stream));
-    SG_CUDA_TRY(cudaMemcpyAsync(hp + qbytes + rbytes, s->d_dist, rbytes, cudaMemcpyDeviceToHost, s->stream));
-    SG_CUDA_TRY(cudaMemcpyAsync(hp + qbytes + 2 * rbytes, s->d_counts, cbytes, cudaMemcpyDeviceToHost, s->stream));
+    SG_CUDA_TRY(cudaMemcpyAsync(hp + qbytes, s->d_resblk, 2 * rbytes + cbytes, cudaMemcpyDeviceToHost, s->stream));
     SG_CUDA_TRY(cudaStreamSynchronize(s->stream));
     memcpy(ids_out, hp + qbytes, rbytes);
     memcpy(dist_out, hp + qbytes + rbytes, rbytes);
