@@ -56,7 +56,7 @@ SG_DEVICE_INLINE unsigned long long enc_gtimer()
     return t;
 }
 
-// erf-GELU, x * Phi(x), in 12 instructions.  Phi(x) = 1 / (1 + exp(-logit Phi(x))) and logit Phi is odd and
+// erf-GELU, x * Phi(x), in 11 instructions.  Phi(x) = 1 / (1 + exp(-logit Phi(x))) and logit Phi is odd and
 // smooth, so it is fitted by x * P(x^2) (degree-9 odd minimax fit on |x| <= 6, coefficients pre-multiplied by
 // -log2 e): max |error| of the GELU value 3.0e-6 over the whole real line -- two orders below the fp16
 // rounding of the output -- with one ex2.approx and one rcp.approx and no slow-path branches.  (The ncu
@@ -64,14 +64,13 @@ SG_DEVICE_INLINE unsigned long long enc_gtimer()
 // FFN-up epilogue issue-bound at 32 instructions per element: profiles/r01_encoder_ncu.md.)
 SG_DEVICE_INLINE float gelu_erf(float x)
 {
-    const float xc = fminf(fmaxf(x, -6.0f), 6.0f);
-    const float x2 = xc * xc;
+    const float x2 = fminf(x * x, 36.0f);             // beyond |x| = 6 the logit keeps growing linearly: Phi is 0 or 1 there anyway
     float p = fmaf(x2, -3.2290400e-06f, 8.8239125e-05f);
     p = fmaf(x2, p, 3.6026838e-04f);
     p = fmaf(x2, p, -1.0522668e-01f);
     p = fmaf(x2, p, -2.3020454e+00f);
     float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xc * p));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * p));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
     return x * r;
 }
@@ -1202,145 +1201,173 @@ SG_DEVICE_INLINE void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t smem_addr)
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr));
 }
 
+SG_DEVICE_INLINE void cp_async16(uint32_t dst_smem, const void *src, bool valid)
+{
+    const uint32_t n = valid ? 16u : 0u;               // src-size 0: the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(n) : "memory");
+}
+SG_DEVICE_INLINE void cp_async8(uint32_t dst_smem, const void *src, bool valid)
+{
+    const uint32_t n = valid ? 8u : 0u;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst_smem), "l"(src), "r"(n) : "memory");
+}
+SG_DEVICE_INLINE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+SG_DEVICE_INLINE void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // Q, K and V of one (sequence, head) sit ROW-MAJOR in shared memory ([row][32] halfs at a pitch of 40 halfs = 80 bytes:
-// eight consecutive rows start in eight different 16-byte bank groups, so every ldmatrix phase is conflict-free), copied
-// with one 16-byte load + one 16-byte store per thread and piece.  The fragments come from ldmatrix: Q as the A operand,
-// K rows as the (col-major) B operand of Q K^T, and V through ldmatrix.trans as the B operand of P V -- the first version
-// transposed V with eight scalar 2-byte stores per thread, which was the top line of the kernel's profile.
+// eight consecutive rows start in eight different 16-byte bank groups, so every ldmatrix phase is conflict-free).  The
+// fragments come from ldmatrix: Q as the A operand, K rows as the (col-major) B operand of Q K^T, and V through
+// ldmatrix.trans as the B operand of P V -- the first version transposed V with eight scalar 2-byte stores per thread.
+// PERSISTENT: a CTA walks work items (sequence, head, 64-query block) and copies the NEXT item's Q/K/V/mask with
+// cp.async into the other half of a double buffer while the tensor cores work on the current one -- a one-item CTA
+// spends most of its life waiting for its own loads (profile: the top stall was the first shared-memory store).
 template <uint32_t KS>   // KS = L16 / 16: 16-key steps (1..8)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, KS <= 4 ? 7 : 3)
 attention_mma_kernel(const __half *__restrict__ qkv, const int64_t *__restrict__ mask, uint32_t L, uint32_t H,
-                     uint32_t heads, __half *__restrict__ ctx)
+                     uint32_t heads, uint32_t n_items, uint32_t q_blocks, __half *__restrict__ ctx)
 {
     constexpr uint32_t D = 32, L16 = KS * 16, NT = KS * 2, P = 40;
-    __shared__ __align__(16) __half Ks[L16 * P];
-    __shared__ __align__(16) __half Vs[L16 * P];
-    __shared__ __align__(16) __half Qs[64 * P];
-    __shared__ float mbias[L16];                       // 0 for live keys, -inf for masked / padding
-    const uint32_t b = blockIdx.x / heads, h = blockIdx.x % heads;
+    constexpr uint32_t KIT = L16 / 32 + (L16 % 32 ? 1 : 0);
+    struct Buf {
+        __align__(16) __half Ks[L16 * P];
+        __align__(16) __half Vs[L16 * P];
+        __align__(16) __half Qs[64 * P];
+        __align__(16) int64_t mk[L16];                  // raw attention mask of the sequence (0 beyond L)
+    };
+    extern __shared__ __align__(16) uint8_t att_smem_raw[];
+    Buf *bufs = reinterpret_cast<Buf *>(att_smem_raw);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t g = lane >> 2, tq = lane & 3;       // fragment row group / quad lane
     const size_t row_stride = 3 * (size_t)H;
     const float NEG_INF = -__uint_as_float(0x7F800000u);
-    for (uint32_t j = threadIdx.x; j < L16; j += blockDim.x)
-        mbias[j] = (j < L && mask[(size_t)b * L + j] == 1) ? 0.0f : NEG_INF;
-    pdl_wait();                                        // qkv comes from the QKV GEMM
-    pdl_trigger();
-    const __half *base = qkv + (size_t)b * L * row_stride + h * D;
-    const uint32_t q_row0 = blockIdx.y * 64;
-    {   // thread -> (row tid/4 + 32 it, 16-byte piece tid%4); all loads of the CTA are issued before the first store
-        const uint32_t part = threadIdx.x & 3, j0 = threadIdx.x >> 2;
-        constexpr uint32_t KIT = L16 / 32 + (L16 % 32 ? 1 : 0);
-        uint4 kv[KIT], vv[KIT], qv[2];
-#pragma unroll
-        for (uint32_t it = 0; it < KIT; ++it) {
-            const uint32_t j = j0 + it * 32;
-            kv[it] = vv[it] = make_uint4(0, 0, 0, 0);
-            if (j < L) {
-                kv[it] = *reinterpret_cast<const uint4 *>(base + j * row_stride + H + part * 8);
-                vv[it] = *reinterpret_cast<const uint4 *>(base + j * row_stride + 2 * H + part * 8);
-            }
-        }
-#pragma unroll
-        for (uint32_t it = 0; it < 2; ++it) {
-            const uint32_t j = j0 + it * 32;
-            qv[it] = make_uint4(0, 0, 0, 0);
-            if (q_row0 + j < L) qv[it] = *reinterpret_cast<const uint4 *>(base + (size_t)(q_row0 + j) * row_stride + part * 8);
-        }
+    const uint32_t part = threadIdx.x & 3, j0 = threadIdx.x >> 2;
+
+    auto prefetch = [&](uint32_t item, Buf &bf) {
+        const uint32_t qb = item % q_blocks, bh = item / q_blocks, b = bh / heads, h = bh % heads;
+        const __half *base = qkv + (size_t)b * L * row_stride + h * D;
 #pragma unroll
         for (uint32_t it = 0; it < KIT; ++it) {
             const uint32_t j = j0 + it * 32;
             if (j < L16) {
-                *reinterpret_cast<uint4 *>(Ks + (size_t)j * P + part * 8) = kv[it];
-                *reinterpret_cast<uint4 *>(Vs + (size_t)j * P + part * 8) = vv[it];
+                const uint32_t jc = j < L ? j : 0;
+                cp_async16(smem_u32(bf.Ks + (size_t)j * P + part * 8), base + jc * row_stride + H + part * 8, j < L);
+                cp_async16(smem_u32(bf.Vs + (size_t)j * P + part * 8), base + jc * row_stride + 2 * H + part * 8, j < L);
             }
         }
 #pragma unroll
-        for (uint32_t it = 0; it < 2; ++it) *reinterpret_cast<uint4 *>(Qs + (size_t)(j0 + it * 32) * P + part * 8) = qv[it];
-    }
-    __syncthreads();
-
-    const uint32_t r0 = q_row0 + warp * 16 + g;        // this thread's rows: r0 and r0 + 8
-    if (q_row0 + warp * 16 >= L) return;
-    // Q fragments for both k-steps (d 0..15, 16..31): matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15)
-    uint32_t qa[2][4];
-    {
-        const uint32_t qaddr = smem_u32(Qs + (size_t)(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * P + (lane >> 4) * 8);
-        ldmatrix_x4(qa[0], qaddr);
-        ldmatrix_x4(qa[1], qaddr + 32);
-    }
-    // S = Q K^T: per 8-key tile one ldmatrix.x4 = the B fragments of both k-steps
-    float sacc[NT][4];
-    const uint32_t kaddr = smem_u32(Ks + (size_t)(lane & 7) * P + (lane >> 3) * 8);
-#pragma unroll
-    for (uint32_t nt = 0; nt < NT; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) sacc[nt][e] = 0.0f;
-        uint32_t kb[4];
-        ldmatrix_x4(kb, kaddr + nt * 8 * P * 2);
-        mma_m16n8k16(sacc[nt], qa[0], kb[0], kb[1]);
-        mma_m16n8k16(sacc[nt], qa[1], kb[2], kb[3]);
-    }
-    // masked softmax on the fragments: rows r0 (elements 0,1) and r0+8 (elements 2,3).  Scores are kept in the log2 domain
-    // (1/sqrt(d) and log2(e) folded into one factor) so that a probability is ONE ex2.approx of a difference; a fully
-    // masked row gets max = 0, and 2^(-inf) = 0 does the rest.
-    const float scale = 0.17677669529663687f * 1.4426950408889634f;
-    float mx0 = NEG_INF, mx1 = NEG_INF;
-#pragma unroll
-    for (uint32_t nt = 0; nt < NT; ++nt) {
-        const float2 bb = *reinterpret_cast<const float2 *>(mbias + nt * 8 + tq * 2);
-        sacc[nt][0] = fmaf(sacc[nt][0], scale, bb.x); sacc[nt][1] = fmaf(sacc[nt][1], scale, bb.y);
-        sacc[nt][2] = fmaf(sacc[nt][2], scale, bb.x); sacc[nt][3] = fmaf(sacc[nt][3], scale, bb.y);
-        mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
-        mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xFFFFFFFFu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xFFFFFFFFu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xFFFFFFFFu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xFFFFFFFFu, mx1, 2));
-    if (!(mx0 > NEG_INF)) mx0 = 0.0f;
-    if (!(mx1 > NEG_INF)) mx1 = 0.0f;
-    float sum0 = 0.0f, sum1 = 0.0f;
-#pragma unroll
-    for (uint32_t nt = 0; nt < NT; ++nt) {
-        sacc[nt][0] = ex2_approx(sacc[nt][0] - mx0);
-        sacc[nt][1] = ex2_approx(sacc[nt][1] - mx0);
-        sacc[nt][2] = ex2_approx(sacc[nt][2] - mx1);
-        sacc[nt][3] = ex2_approx(sacc[nt][3] - mx1);
-        sum0 += sacc[nt][0] + sacc[nt][1];
-        sum1 += sacc[nt][2] + sacc[nt][3];
-    }
-    sum0 += __shfl_xor_sync(0xFFFFFFFFu, sum0, 1); sum0 += __shfl_xor_sync(0xFFFFFFFFu, sum0, 2);
-    sum1 += __shfl_xor_sync(0xFFFFFFFFu, sum1, 1); sum1 += __shfl_xor_sync(0xFFFFFFFFu, sum1, 2);
-    // O = P V : per 16-key step, the P A-fragment is built from two adjacent S tiles; V^T fragments by ldmatrix.trans:
-    // matrices (keys 0-7 | 8-15) x (d tile dt | dt + 1)
-    float oacc[4][4];
-#pragma unroll
-    for (uint32_t dt = 0; dt < 4; ++dt)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) oacc[dt][e] = 0.0f;
-    const uint32_t vaddr = smem_u32(Vs + (size_t)((lane & 7) + ((lane >> 3) & 1) * 8) * P + (lane >> 4) * 8);
-#pragma unroll
-    for (uint32_t ks = 0; ks < KS; ++ks) {
-        uint32_t pa[4];
-        pa[0] = pack_half2(sacc[2 * ks][0], sacc[2 * ks][1]);
-        pa[1] = pack_half2(sacc[2 * ks][2], sacc[2 * ks][3]);
-        pa[2] = pack_half2(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1]);
-        pa[3] = pack_half2(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3]);
-#pragma unroll
-        for (uint32_t dp = 0; dp < 2; ++dp) {
-            uint32_t vb[4];
-            ldmatrix_x4_trans(vb, vaddr + (ks * 16 * P + dp * 16) * 2);
-            mma_m16n8k16(oacc[2 * dp], pa, vb[0], vb[1]);
-            mma_m16n8k16(oacc[2 * dp + 1], pa, vb[2], vb[3]);
+        for (uint32_t it = 0; it < 2; ++it) {
+            const uint32_t j = qb * 64 + j0 + it * 32, jc = j < L ? j : 0;
+            cp_async16(smem_u32(bf.Qs + (size_t)(j0 + it * 32) * P + part * 8), base + (size_t)jc * row_stride + part * 8, j < L);
         }
-    }
-    const float inv0 = sum0 > 0.0f ? 1.0f / sum0 : 0.0f, inv1 = sum1 > 0.0f ? 1.0f / sum1 : 0.0f;
+        if (threadIdx.x < L16) {
+            const uint32_t j = threadIdx.x, jc = j < L ? j : 0;
+            cp_async8(smem_u32(bf.mk + j), mask + (size_t)b * L + jc, j < L);
+        }
+        cp_async_commit();
+    };
+
+    pdl_wait();                                        // qkv comes from the QKV GEMM
+    pdl_trigger();
+    uint32_t item = blockIdx.x, cur = 0;
+    if (item < n_items) prefetch(item, bufs[0]);
+    for (; item < n_items; item += gridDim.x, cur ^= 1) {
+        const uint32_t next = item + gridDim.x;
+        if (next < n_items) {
+            prefetch(next, bufs[cur ^ 1]);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const Buf &bf = bufs[cur];
+        const uint32_t qb = item % q_blocks, bh = item / q_blocks, b = bh / heads, h = bh % heads;
+        const uint32_t q_row0 = qb * 64;
+        const uint32_t r0 = q_row0 + warp * 16 + g;    // this thread's rows: r0 and r0 + 8
+        if (q_row0 + warp * 16 < L) {
+            // Q fragments for both k-steps (d 0..15, 16..31): matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15)
+            uint32_t qa[2][4];
+            {
+                const uint32_t qaddr = smem_u32(bf.Qs + (size_t)(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * P + (lane >> 4) * 8);
+                ldmatrix_x4(qa[0], qaddr);
+                ldmatrix_x4(qa[1], qaddr + 32);
+            }
+            // S = Q K^T: per 8-key tile one ldmatrix.x4 = the B fragments of both k-steps
+            float sacc[NT][4];
+            const uint32_t kaddr = smem_u32(bf.Ks + (size_t)(lane & 7) * P + (lane >> 3) * 8);
 #pragma unroll
-    for (uint32_t dt = 0; dt < 4; ++dt) {
-        const uint32_t d = dt * 8 + tq * 2;
-        if (r0 < L)
-            *reinterpret_cast<uint32_t *>(ctx + ((size_t)b * L + r0) * H + h * D + d) = pack_half2(oacc[dt][0] * inv0, oacc[dt][1] * inv0);
-        if (r0 + 8 < L)
-            *reinterpret_cast<uint32_t *>(ctx + ((size_t)b * L + r0 + 8) * H + h * D + d) = pack_half2(oacc[dt][2] * inv1, oacc[dt][3] * inv1);
+            for (uint32_t nt = 0; nt < NT; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sacc[nt][e] = 0.0f;
+                uint32_t kb[4];
+                ldmatrix_x4(kb, kaddr + nt * 8 * P * 2);
+                mma_m16n8k16(sacc[nt], qa[0], kb[0], kb[1]);
+                mma_m16n8k16(sacc[nt], qa[1], kb[2], kb[3]);
+            }
+            // masked softmax on the fragments: rows r0 (elements 0,1) and r0+8 (elements 2,3).  Scores are kept in the log2
+            // domain (1/sqrt(d) and log2(e) folded into one factor) so that a probability is ONE ex2.approx of a difference;
+            // a fully masked row gets max = 0, and 2^(-inf) = 0 does the rest.
+            const float scale = 0.17677669529663687f * 1.4426950408889634f;
+            float mx0 = NEG_INF, mx1 = NEG_INF;
+#pragma unroll
+            for (uint32_t nt = 0; nt < NT; ++nt) {
+                const longlong2 mm = *reinterpret_cast<const longlong2 *>(bf.mk + nt * 8 + tq * 2);
+                const float bx = mm.x == 1 ? 0.0f : NEG_INF, by = mm.y == 1 ? 0.0f : NEG_INF;
+                sacc[nt][0] = fmaf(sacc[nt][0], scale, bx); sacc[nt][1] = fmaf(sacc[nt][1], scale, by);
+                sacc[nt][2] = fmaf(sacc[nt][2], scale, bx); sacc[nt][3] = fmaf(sacc[nt][3], scale, by);
+                mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
+                mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
+            }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xFFFFFFFFu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xFFFFFFFFu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xFFFFFFFFu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xFFFFFFFFu, mx1, 2));
+            if (!(mx0 > NEG_INF)) mx0 = 0.0f;
+            if (!(mx1 > NEG_INF)) mx1 = 0.0f;
+            float sum0 = 0.0f, sum1 = 0.0f;
+#pragma unroll
+            for (uint32_t nt = 0; nt < NT; ++nt) {
+                sacc[nt][0] = ex2_approx(sacc[nt][0] - mx0);
+                sacc[nt][1] = ex2_approx(sacc[nt][1] - mx0);
+                sacc[nt][2] = ex2_approx(sacc[nt][2] - mx1);
+                sacc[nt][3] = ex2_approx(sacc[nt][3] - mx1);
+                sum0 += sacc[nt][0] + sacc[nt][1];
+                sum1 += sacc[nt][2] + sacc[nt][3];
+            }
+            sum0 += __shfl_xor_sync(0xFFFFFFFFu, sum0, 1); sum0 += __shfl_xor_sync(0xFFFFFFFFu, sum0, 2);
+            sum1 += __shfl_xor_sync(0xFFFFFFFFu, sum1, 1); sum1 += __shfl_xor_sync(0xFFFFFFFFu, sum1, 2);
+            // O = P V : per 16-key step, the P A-fragment is built from two adjacent S tiles; V^T fragments by
+            // ldmatrix.trans: matrices (keys 0-7 | 8-15) x (d tile dt | dt + 1)
+            float oacc[4][4];
+#pragma unroll
+            for (uint32_t dt = 0; dt < 4; ++dt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) oacc[dt][e] = 0.0f;
+            const uint32_t vaddr = smem_u32(bf.Vs + (size_t)((lane & 7) + ((lane >> 3) & 1) * 8) * P + (lane >> 4) * 8);
+#pragma unroll
+            for (uint32_t ks = 0; ks < KS; ++ks) {
+                uint32_t pa[4];
+                pa[0] = pack_half2(sacc[2 * ks][0], sacc[2 * ks][1]);
+                pa[1] = pack_half2(sacc[2 * ks][2], sacc[2 * ks][3]);
+                pa[2] = pack_half2(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1]);
+                pa[3] = pack_half2(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3]);
+#pragma unroll
+                for (uint32_t dp = 0; dp < 2; ++dp) {
+                    uint32_t vb[4];
+                    ldmatrix_x4_trans(vb, vaddr + (ks * 16 * P + dp * 16) * 2);
+                    mma_m16n8k16(oacc[2 * dp], pa, vb[0], vb[1]);
+                    mma_m16n8k16(oacc[2 * dp + 1], pa, vb[2], vb[3]);
+                }
+            }
+            const float inv0 = sum0 > 0.0f ? 1.0f / sum0 : 0.0f, inv1 = sum1 > 0.0f ? 1.0f / sum1 : 0.0f;
+#pragma unroll
+            for (uint32_t dt = 0; dt < 4; ++dt) {
+                const uint32_t d = dt * 8 + tq * 2;
+                if (r0 < L)
+                    *reinterpret_cast<uint32_t *>(ctx + ((size_t)b * L + r0) * H + h * D + d) = pack_half2(oacc[dt][0] * inv0, oacc[dt][1] * inv0);
+                if (r0 + 8 < L)
+                    *reinterpret_cast<uint32_t *>(ctx + ((size_t)b * L + r0 + 8) * H + h * D + d) = pack_half2(oacc[dt][2] * inv1, oacc[dt][3] * inv1);
+            }
+        }
+        __syncthreads();                               // the next prefetch overwrites this buffer
     }
 }
 
@@ -1348,7 +1375,19 @@ template <uint32_t KS>
 void launch_attention_mma(const __half *qkv, const int64_t *mask, uint32_t b, uint32_t L, uint32_t H, uint32_t heads,
                           __half *ctx, cudaStream_t st)
 {
-    launch_pdl(attention_mma_kernel<KS>, dim3(b * heads, (L + 63) / 64), dim3(128), 0, st, qkv, mask, L, H, heads, ctx);
+    const uint32_t q_blocks = (L + 63) / 64, n_items = b * heads * q_blocks;
+    constexpr uint32_t smem_per_cta = 2 * ((2 * KS * 16 + 64) * 80 + KS * 16 * 8);
+    static DevAttr da;
+    if (ensure_smem(attention_mma_kernel<KS>, da, smem_per_cta) != cudaSuccess) return;
+    static int per_sm_cached = 0;                      // resident CTAs per SM (registers / shared memory), asked once
+    if (per_sm_cached == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, attention_mma_kernel<KS>, 128, smem_per_cta) != cudaSuccess || n < 1) n = 1;
+        per_sm_cached = n;
+    }
+    const uint32_t per_sm = (uint32_t)per_sm_cached;
+    const uint32_t grid = n_items < 148 * per_sm ? n_items : 148 * per_sm;
+    launch_pdl(attention_mma_kernel<KS>, dim3(grid), dim3(128), smem_per_cta, st, qkv, mask, L, H, heads, n_items, q_blocks, ctx);
 }
 
 // ---- masked mean-pool + finalize (reference minilm.rs:959-978, :846-878) -----------------------------
@@ -1698,9 +1737,10 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
         if ((rc = regrow(e->mid, c * F)) != SG_OK) return rc;
         if ((rc = regrow(e->hf32, c * H)) != SG_OK) return rc;
         e->cap_tokens = c;
+        // ctx rows beyond T are never written by attention: they must be finite (zero now; later calls leave finite values
+        // of earlier, larger batches there -- padding rows are computed and discarded)
+        SG_CUDA_TRY(cudaMemsetAsync(e->ctx, 0, c * H * 2, st));
     }
-    // ctx rows beyond T are never written by attention: keep them finite
-    SG_CUDA_TRY(cudaMemsetAsync(e->ctx, 0, (size_t)T_pad * H * 2, st));
     SG_CUDA_TRY(launch_pdl(embed_ln_kernel, dim3((T_pad * 32 + 255) / 256), dim3(256), 0, st, d_ids, T, T_pad, L, H, e->vocab,
                            (const float *)e->word, (const float *)e->pos, (const float *)e->type0, (const float *)e->emb_g,
                            (const float *)e->emb_b, e->eps, e->h0));
