@@ -155,7 +155,8 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
         if (row0 + 32 > a.n_rows) dead |= row0 >= a.n_rows ? 0xFFFFFFFFu : ~((1u << (uint32_t)(a.n_rows - row0)) - 1u);
         return dead;
     };
-    auto chunk_max = [&](const uint32_t (&r)[32]) -> float {
+    // maximum of a 32-column chunk; g8[i] = maximum of columns 8i..8i+7 (by-products of the same tree)
+    auto chunk_max = [&](const uint32_t (&r)[32], float (&g8)[4]) -> float {
         float m0 = fmaxf(fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3])));
         float m1 = fmaxf(fmaxf(__uint_as_float(r[4]), __uint_as_float(r[5])), fmaxf(__uint_as_float(r[6]), __uint_as_float(r[7])));
         float m2 = fmaxf(fmaxf(__uint_as_float(r[8]), __uint_as_float(r[9])), fmaxf(__uint_as_float(r[10]), __uint_as_float(r[11])));
@@ -164,7 +165,8 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
         float m5 = fmaxf(fmaxf(__uint_as_float(r[20]), __uint_as_float(r[21])), fmaxf(__uint_as_float(r[22]), __uint_as_float(r[23])));
         float m6 = fmaxf(fmaxf(__uint_as_float(r[24]), __uint_as_float(r[25])), fmaxf(__uint_as_float(r[26]), __uint_as_float(r[27])));
         float m7 = fmaxf(fmaxf(__uint_as_float(r[28]), __uint_as_float(r[29])), fmaxf(__uint_as_float(r[30]), __uint_as_float(r[31])));
-        return fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
+        g8[0] = fmaxf(m0, m1); g8[1] = fmaxf(m2, m3); g8[2] = fmaxf(m4, m5); g8[3] = fmaxf(m6, m7);
+        return fmaxf(fmaxf(g8[0], g8[1]), fmaxf(g8[2], g8[3]));
     };
 
     const bool tr = a.trace != nullptr && e == 0;
@@ -191,7 +193,8 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
                     for (uint32_t j = 0; j < 32; ++j)
                         if ((dead >> j) & 1u) r[j] = __float_as_uint(TC_NEG_INF);
                 }
-                float mx = chunk_max(r);
+                float g8s[4];
+                float mx = chunk_max(r, g8s);
                 if (!(mx == mx)) mx = TC_NEG_INF;        // an all-NaN chunk must not enter (it would duplicate entries)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {            // insert into the descending list
@@ -240,9 +243,9 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
         // device-wide meeting point: every CTA of the grid publishes its sample, then reads all of them.  The arrival
         // counter is never reset: this launch waits for the value the host computed for it (wrap-safe compare).
         if (tr) trp[2] = gtimer();                   // sample scanned
-        __threadfence();
-        epi_bar_sync();
+        epi_bar_sync();                              // the CTA's stores are ordered before thread 0's fence + arrival
         if (e == 0) {
+            __threadfence();
             atomicAdd(a.arrive, 1u);
             const long long t0 = clock64();
             uint32_t ok = 1;
@@ -252,75 +255,142 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
                     break;                                   // queries overflow, get flagged and re-run on path A
                 }
             }
+            __threadfence();
             s_ctl[0] = ok;
         }
-        epi_bar_sync();
-        __threadfence();
+        epi_bar_sync();                              // (the sample values are read with ld.global.cg: L2, never a stale L1 line)
         if (tr) trp[3] = gtimer();                   // every CTA has arrived
-        if (grp == 0 && active && s_ctl[0]) {
-            // this query's sample values are contiguous ([query][value], padded with -inf to a multiple of 4): 16-byte
-            // loads, all independent -- a scalar, strided walk of ~300 values was a 60 us latency chain at kernel start
-            float mn = -TC_NEG_INF, sum = 0.0f;
-            uint32_t nfin = 0;
-            const uint32_t nv4 = a.nv_pad / 4;
-            const float4 *mp4 = reinterpret_cast<const float4 *>(a.maxima + (size_t)q * a.nv_pad);
-#pragma unroll 8
-            for (uint32_t i = 0; i < nv4; ++i) {
-                const float4 v4 = __ldcg(mp4 + i);
-                const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+        // ===== seed threshold: the best PROVABLE lower bound on the kk-th best score this sample gives =====
+        // Each sample value is the maximum of a DISTINCT 32-row chunk, so "c values >= x" means c distinct rows score >= x.
+        // Seven levels mn + j (mean - mn) / 2 are counted, the highest with kk values wins, and seven sub-levels refine
+        // inside the winning interval (the first tiles of a sweep run under this seed alone, and every chunk that reaches
+        // it takes the slow path).  The levels hang off the MEAN of the sample, which -- unlike its maximum -- is not dragged
+        // away by a near-duplicate of the query that happens to sit in the sample.
+        const uint32_t nv4 = a.nv_pad / 4;
+        const float4 *mp4 = reinterpret_cast<const float4 *>(a.maxima + (size_t)q * a.nv_pad);
+        const bool seed_on = active && s_ctl[0];
+        float mn = -TC_NEG_INF, sum = 0.0f, mean = 0.0f, mn0 = 0.0f;
+        uint32_t nfin = 0;
+        float lv[7];
+        uint32_t cn[7];
+        auto stats = [&](const float4 &v4) {
+            const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (vv[c] > TC_NEG_INF) {
-                        ++nfin;
-                        mn = fminf(mn, vv[c]);
-                        sum += vv[c];
-                    }
+            for (int c = 0; c < 4; ++c) {
+                if (vv[c] > TC_NEG_INF) {
+                    ++nfin;
+                    mn = fminf(mn, vv[c]);
+                    sum += vv[c];
                 }
             }
-            if (nfin >= a.kk) {                              // kk distinct rows score >= mn
-                // a better seed than the minimum: the largest of 7 candidate levels mn + j * (mean - mn) / 2 that still
-                // has kk sample values at or above it (each value is the maximum of a DISTINCT 32-row chunk, so that
-                // many distinct rows reach it).  The levels hang off the MEAN of the sample maxima, which -- unlike the
-                // largest one -- is not dragged away by a near-duplicate of the query that happens to sit in the sample.
-                const float mean = sum / (float)nfin, step = 0.5f * (mean - mn);
-                float lv[7];
-                uint32_t cn[7];
+        };
+        auto set_levels = [&](float base, float step) {
 #pragma unroll
-                for (int j = 0; j < 7; ++j) {
-                    lv[j] = mn + (float)(j + 1) * step;
-                    cn[j] = 0;
-                }
-#pragma unroll 8
-                for (uint32_t i = 0; i < nv4; ++i) {
-                    const float4 v4 = __ldcg(mp4 + i);
+            for (int j = 0; j < 7; ++j) {
+                lv[j] = base + (float)(j + 1) * step;
+                cn[j] = 0;
+            }
+        };
+        auto count = [&](const float4 &v4) {
 #pragma unroll
-                    for (int j = 0; j < 7; ++j)              // -inf / NaN compare false
-                        cn[j] += (v4.x >= lv[j] ? 1u : 0u) + (v4.y >= lv[j] ? 1u : 0u) + (v4.z >= lv[j] ? 1u : 0u) +
-                                 (v4.w >= lv[j] ? 1u : 0u);
-                }
-                tau0 = mn;
+            for (int j = 0; j < 7; ++j)                      // -inf / NaN compare false
+                cn[j] += (v4.x >= lv[j] ? 1u : 0u) + (v4.y >= lv[j] ? 1u : 0u) + (v4.z >= lv[j] ? 1u : 0u) +
+                         (v4.w >= lv[j] ? 1u : 0u);
+        };
+        auto best_level = [&](float base) {                  // levels ascend: the last one that qualifies wins
+            float lo = base;
 #pragma unroll
-                for (int j = 0; j < 7; ++j)
-                    if (cn[j] >= a.kk) tau0 = lv[j];         // levels ascend: the last one that qualifies wins
+            for (int j = 0; j < 7; ++j)
+                if (cn[j] >= a.kk) lo = lv[j];
+            return lo;
+        };
+        constexpr uint32_t NC = 10;                          // float4 per thread held in registers
+        if (nv4 <= 2 * NC) {
+            // The common shape (k <= 24: one value per unit, <= 80 values per query).  BOTH warp groups work on it: thread
+            // (query t, group g) holds half of the query's values in registers -- one round trip to L2 instead of two
+            // passes of dependent loads by one group (measured 7 us of every sweep) -- and the halves are combined through
+            // the exchange slots (.xy = group 0's words, .zw = group 1's).
+            float4 cv[NC];
+#pragma unroll
+            for (uint32_t i = 0; i < NC; ++i) {
+                const uint32_t idx = grp * NC + i;
+                cv[i] = (seed_on && idx < nv4) ? __ldcg(mp4 + idx) : make_float4(TC_NEG_INF, TC_NEG_INF, TC_NEG_INF, TC_NEG_INF);
+            }
+#pragma unroll
+            for (uint32_t i = 0; i < NC; ++i) stats(cv[i]);
+            float2 *slot = reinterpret_cast<float2 *>(xchg + t);                 // [0] group 0, [1] group 1
+            auto swap2 = [&](float x, float y) -> float2 {   // publish two words, return the other group's
+                slot[grp] = make_float2(x, y);
+                epi_bar_sync();
+                const float2 o = slot[grp ^ 1];
+                epi_bar_sync();
+                return o;
+            };
+            {
+                const float2 o = swap2(mn, __uint_as_float(nfin));
+                const float2 o2 = swap2(sum, 0.0f);
+                mn = fminf(mn, o.x);
+                nfin += __float_as_uint(o.y);
+                sum = grp == 0 ? sum + o2.x : o2.x + sum;    // the same operand order in both groups: identical seeds
+            }
+            const bool enough = seed_on && nfin >= a.kk;
+            auto count_all = [&]() {
+#pragma unroll
+                for (uint32_t i = 0; i < NC; ++i) count(cv[i]);
+                // 7 counts <= 80 each: one byte apiece, two words
+                const uint32_t w0 = cn[0] | (cn[1] << 8) | (cn[2] << 16) | (cn[3] << 24), w1 = cn[4] | (cn[5] << 8) | (cn[6] << 16);
+                const float2 o = swap2(__uint_as_float(w0), __uint_as_float(w1));
+                const uint32_t o0 = __float_as_uint(o.x), o1 = __float_as_uint(o.y);
+                cn[0] += o0 & 0xFFu; cn[1] += (o0 >> 8) & 0xFFu; cn[2] += (o0 >> 16) & 0xFFu; cn[3] += o0 >> 24;
+                cn[4] += o1 & 0xFFu; cn[5] += (o1 >> 8) & 0xFFu; cn[6] += (o1 >> 16) & 0xFFu;
+            };
+            mean = nfin ? sum / (float)nfin : 0.0f;
+            set_levels(mn, 0.5f * (mean - mn));
+            count_all();
+            const float lo = best_level(mn);
+            mn0 = mn;
+            set_levels(lo, 0.0625f * (mean - mn));
+            count_all();
+            if (enough) {
+                tau0 = best_level(lo);
                 tau_f = tau0;
-                // histogram over [tau0, tau0 + 3 (mean - mn)]: the final threshold lies well beyond the sample's
-                // typical maximum (the sample is ~1/500 of a 10M-row corpus).  Scores beyond the range land in the last
-                // bucket: the threshold then stops one bucket short of them, which only costs a few extra candidates.
-                const float range = 3.0f * (mean - mn);
-                w = range * (1.0f / TC_HIST);
-                if (w > 1.0e-5f * fmaxf(fabsf(tau0), fabsf(tau0 + range)) && w < -TC_NEG_INF) {
-                    inv_w = 1.0f / w;
-                    use_hist = true;
+            }
+        } else {
+            // many values per query (large k): group 0 alone, two passes of 16-byte loads
+            if (grp == 0 && seed_on) {
+#pragma unroll 8
+                for (uint32_t i = 0; i < nv4; ++i) stats(__ldcg(mp4 + i));
+                if (nfin >= a.kk) {
+                    mean = sum / (float)nfin;
+                    mn0 = mn;
+                    set_levels(mn, 0.5f * (mean - mn));
+#pragma unroll 8
+                    for (uint32_t i = 0; i < nv4; ++i) count(__ldcg(mp4 + i));
+                    tau0 = best_level(mn);
+                    tau_f = tau0;
                 }
             }
         }
-        // group 0 computed the query's seed; group 1 takes it over (identical thresholds and bucket mapping)
-        if (grp == 0) xchg[t] = make_float4(tau0, w, inv_w, use_hist ? 1.0f : 0.0f);
-        epi_bar_sync();
-        if (grp == 1 && active) {
-            const float4 sd = xchg[t];
-            tau0 = sd.x; w = sd.y; inv_w = sd.z; use_hist = sd.w != 0.0f;
-            tau_f = tau0;
+        if (seed_on && nfin >= a.kk && (grp == 0 || nv4 <= 2 * NC)) {
+            // histogram over [tau0, tau0 + 3 (mean - mn)]: the final threshold lies well beyond the sample's typical maximum
+            // (the sample is ~1/500 of a 10M-row corpus).  Scores beyond the range land in the last bucket: the threshold
+            // then stops one bucket short of them, which only costs a few extra candidates.
+            const float range = 3.0f * (mean - mn0);
+            w = range * (1.0f / TC_HIST);
+            if (w > 1.0e-5f * fmaxf(fabsf(tau0), fabsf(tau0 + range)) && w < -TC_NEG_INF) {
+                inv_w = 1.0f / w;
+                use_hist = true;
+            }
+        }
+        if (nv4 > 2 * NC) {
+            // group 0 computed the query's seed; group 1 takes it over (identical thresholds and bucket mapping)
+            if (grp == 0) xchg[t] = make_float4(tau0, w, inv_w, use_hist ? 1.0f : 0.0f);
+            epi_bar_sync();
+            if (grp == 1 && active) {
+                const float4 sd = xchg[t];
+                tau0 = sd.x; w = sd.y; inv_w = sd.z; use_hist = sd.w != 0.0f;
+                tau_f = tau0;
+            }
         }
     }
 
@@ -381,22 +451,21 @@ SG_DEVICE_INLINE void tc_epilogue(const TcArgs &a, uint32_t *s_ctl, uint32_t tme
                 }
                 continue;
             }
-            const float mx = chunk_max(r);
+            float g8[4];
+            const float mx = chunk_max(r, g8);
             if (__any_sync(0xFFFFFFFFu, mx >= tau_f)) {
-                // slow path: the owning lane appends its hits (cost ~ number of 8-column groups with a hit)
+                // slow path: the owning lane appends its hits.  The max tree already holds the maximum of every 8-column
+                // group: only groups that reach the threshold are looked at column by column (under a weak early threshold
+                // most chunks come here, so this path's fixed cost is what the first tiles of a sweep pay)
                 const uint32_t dead = dead_mask(row0);
-                uint32_t mask = 0;
 #pragma unroll
-                for (uint32_t j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) >= tau_f) ? (1u << j) : 0u;
-                mask &= ~dead;
-#pragma unroll
-                for (uint32_t g8 = 0; g8 < 4; ++g8) {
-                    if ((mask >> (8 * g8)) & 0xFFu) {
+                for (uint32_t gi = 0; gi < 4; ++gi) {
+                    if (g8[gi] >= tau_f) {
 #pragma unroll
                         for (uint32_t jj = 0; jj < 8; ++jj) {
-                            const uint32_t j = 8 * g8 + jj;
-                            if ((mask >> j) & 1u) {
-                                const float sc = __uint_as_float(r[j]);
+                            const uint32_t j = 8 * gi + jj;
+                            const float sc = __uint_as_float(r[j]);
+                            if (sc >= tau_f && !((dead >> j) & 1u)) {
                                 if (my_cnt < a.cap_l) my_cand[my_cnt] = make_key(order_key32(-sc), (uint32_t)(row0 + j));
                                 ++my_cnt;
                                 if (use_hist) {

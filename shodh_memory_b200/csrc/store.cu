@@ -495,9 +495,12 @@ bool tc_plan(const sg_store *s, uint32_t b, uint32_t k, TcPlan *p)
     p->kk = tc_kk(k);
     const uint32_t kk_env = (uint32_t)env_u32("SG_TC_KK", 0);
     if (kk_env >= k + 2 && kk_env <= TC_KK_MAX) p->kk = kk_env;
-    // CTA-pair form (256 queries per sweep) for b > 128; 1-CTA form (128 per sweep) otherwise
+    // CTA-pair form (256 queries per sweep, tensor-bound: ~1.56 ms per 10M rows whatever b is) from SG_TC_PAIR_MIN_B
+    // queries; below, the 1-CTA form (128 per sweep).  Measured at 10M rows, b = 128 / 96 / 64: 1.33 / 1.44 / 1.48 ms with
+    // the 1-CTA form against 1.44-1.51 / 1.61 / 1.35 ms with the pair (run-to-run spread ~10 %): no clear winner below
+    // 129, so the pair starts where it is the only form that serves the batch in one sweep.
     const int pair_env = env_u32("SG_TC_PAIR", 1);
-    p->pair = pair_env == 2 || (pair_env == 1 && b > 128);
+    p->pair = pair_env == 2 || (pair_env == 1 && b >= (uint32_t)env_u32("SG_TC_PAIR_MIN_B", 129));
     p->qtile = p->pair ? 256 : 128;
     const uint32_t rows_tile = p->pair ? 256 : 128;
     const uint64_t n_tiles = (s->n + rows_tile - 1) / rows_tile;
