@@ -754,6 +754,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // its 128 activation rows and HALF of the weight rows per K-block (40 KB), the pair's MMAs (2 x N = 192) read both
 // halves, every CTA ends up with its 128 rows x 384 columns in TMEM exactly as before -- and pass 2 writes the fp16 rows
 // into the (now idle) ring as swizzled 64-column boxes that six TMA stores drain.
+// (Tried and dropped: a persistent variant with the COLUMNS split over the cluster -- 128 x 192 per CTA, two accumulator
+// stages, statistics exchanged through distributed shared memory.  It overlaps the epilogue with the next tile's MMAs but
+// loads 40 KB per 3.1 MFLOP K-block: ~105 B/clk against the ~64 B/clk an SM can take from L2 -- 709 vs 651 us per 256 queries.)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LN_THREADS, 1)
 gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g)

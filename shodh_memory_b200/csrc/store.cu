@@ -1277,9 +1277,19 @@ int sg_store_search(sg_store *s, const float *queries, uint32_t b, uint32_t k, u
     uint32_t *d_counts = s->d_resblk + 2 * rwords;
 
     uint8_t *hp = static_cast<uint8_t *>(s->h_pinned);
-    memcpy(hp, queries, qbytes);
+    // a caller that keeps its queries in page-locked memory (cudaHostAlloc / cudaHostRegister / torch pin_memory) is
+    // DMA'd from directly; pageable memory goes through the store's pinned staging buffer first
+    const void *h2d_src = hp;
+    {
+        cudaPointerAttributes pa{};
+        if (cudaPointerGetAttributes(&pa, queries) == cudaSuccess && pa.type == cudaMemoryTypeHost) h2d_src = queries;
+        else {
+            (void)cudaGetLastError();
+            memcpy(hp, queries, qbytes);
+        }
+    }
     if ((rc = chain_begin(s, s->stream)) != SG_OK) return rc;
-    SG_CUDA_TRY(cudaMemcpyAsync(s->d_queries, hp, qbytes, cudaMemcpyHostToDevice, s->stream));
+    SG_CUDA_TRY(cudaMemcpyAsync(s->d_queries, h2d_src, qbytes, cudaMemcpyHostToDevice, s->stream));
     rc = search_device_locked(s, s->d_queries, b, k, d_ids, d_dist, d_counts, s->stream);
     if (rc != SG_OK) return rc;
     SG_CUDA_TRY(cudaMemcpyAsync(hp + qbytes, s->d_resblk, 2 * rbytes + cbytes, cudaMemcpyDeviceToHost, s->stream));

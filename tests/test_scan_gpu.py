@@ -346,3 +346,20 @@ def test_concurrent_callers_serialise_correctly(sg, oracle):
     [t.join() for t in ts]
     assert not errors, errors[:3]
     st.close()
+
+
+def test_page_locked_queries_are_read_in_place(sg, oracle):
+    """sg_store_search DMAs page-locked caller memory directly (no staging copy); same answers as pageable memory."""
+    import torch
+    st = sg.GpuVectorStore(384, "f16")
+    st.append_synthetic(SEED, 0, 30000)
+    corpus = oracle.synth_corpus(SEED, 0, 30000, 384, f16_round=True)
+    rng = np.random.default_rng(11)
+    q = rng.standard_normal((5, 384)).astype(F)
+    pinned = torch.from_numpy(q.copy()).pin_memory()
+    a = st.search_batch(pinned.numpy(), 10)
+    b = st.search_batch(q, 10)
+    for x, y in zip(a, b):
+        assert np.array_equal(np.asarray(x).view(np.uint32), np.asarray(y).view(np.uint32))
+    assert_same(oracle, st, corpus, pinned.numpy(), 10)
+    st.close()
