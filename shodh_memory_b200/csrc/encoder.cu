@@ -291,6 +291,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // SMs in parallel -- what matters for the single-query case, where the whole GEMM is ONE row tile), and
 // exchange per-row (sum, sum of squares) partials through distributed shared memory before normalising.
 // 8 epilogue warps: warps w and w+4 share TMEM lane quarter w%4 and own 64 columns each.
+// (Tried and dropped: a cluster of 6 -- three column slices x two K halves, the upper halves' raw accumulators handed over
+// through distributed shared memory -- so that six SMs stream FFN-down's 1.2 MB of weights: 233.6 vs 226.2 us per single
+// query.  The small-batch forward is bound by its ~26 dependent launches, not by this kernel's weight stream.)
 __global__ void __cluster_dims__(3, 1, 1) __launch_bounds__(P_THREADS, 1)
 gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const GemmArgs g)
 {

@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -1264,6 +1265,15 @@ int sg_store_search(sg_store *s, const float *queries, uint32_t b, uint32_t k, u
         return SG_ERR_INVALID;
     }
     std::lock_guard<std::mutex> g(s->mu);
+    // SG_HOST_TRACE=1: host-clock breakdown of this call, averaged over 64 calls, to stderr (debug)
+    static const bool htrace = env_u32("SG_HOST_TRACE", 0) != 0;
+    static double hacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    static int hn = 0;
+    static cudaEvent_t hev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (htrace && !hev[0])
+        for (auto &e : hev) cudaEventCreate(&e);
+    auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double h0 = htrace ? now() : 0.0;
     SG_CUDA_TRY(cudaSetDevice(s->device));
     const size_t qbytes = (size_t)b * s->dim * 4, rbytes = (size_t)b * k * 4, cbytes = (size_t)b * 4;
     int rc = grow_pinned(s, qbytes + 2 * rbytes + cbytes);
@@ -1288,15 +1298,37 @@ int sg_store_search(sg_store *s, const float *queries, uint32_t b, uint32_t k, u
             memcpy(hp, queries, qbytes);
         }
     }
+    const double h1 = htrace ? now() : 0.0;
     if ((rc = chain_begin(s, s->stream)) != SG_OK) return rc;
+    if (htrace) cudaEventRecord(hev[0], s->stream);
     SG_CUDA_TRY(cudaMemcpyAsync(s->d_queries, h2d_src, qbytes, cudaMemcpyHostToDevice, s->stream));
+    if (htrace) cudaEventRecord(hev[1], s->stream);
+    const double h2 = htrace ? now() : 0.0;
     rc = search_device_locked(s, s->d_queries, b, k, d_ids, d_dist, d_counts, s->stream);
     if (rc != SG_OK) return rc;
+    if (htrace) cudaEventRecord(hev[2], s->stream);
     SG_CUDA_TRY(cudaMemcpyAsync(hp + qbytes, s->d_resblk, 2 * rbytes + cbytes, cudaMemcpyDeviceToHost, s->stream));
+    if (htrace) cudaEventRecord(hev[3], s->stream);
+    const double h3 = htrace ? now() : 0.0;
     SG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    const double h4 = htrace ? now() : 0.0;
     memcpy(ids_out, hp + qbytes, rbytes);
     memcpy(dist_out, hp + qbytes + rbytes, rbytes);
     memcpy(counts_out, hp + qbytes + 2 * rbytes, cbytes);
+    if (htrace) {
+        const double h5 = now();
+        hacc[0] += h1 - h0; hacc[1] += h2 - h1; hacc[2] += h3 - h2; hacc[3] += h4 - h3; hacc[4] += h5 - h4;
+        float g01 = 0, g12 = 0, g23 = 0;
+        cudaEventElapsedTime(&g01, hev[0], hev[1]); cudaEventElapsedTime(&g12, hev[1], hev[2]); cudaEventElapsedTime(&g23, hev[2], hev[3]);
+        hacc[5] += g01 * 1e3; hacc[6] += g12 * 1e3; hacc[7] += g23 * 1e3;
+        if (++hn == 64) {
+            fprintf(stderr, "[sg host trace] sg_store_search b=%u k=%u, us per call: setup+staging %.1f | H2D enqueue %.1f | kernel launches + D2H enqueue %.1f | "
+                            "wait for the GPU %.1f | copy-out %.1f || GPU timeline: H2D %.1f | kernels %.1f | D2H %.1f\n", b, k, hacc[0] / hn,
+                    hacc[1] / hn, hacc[2] / hn, hacc[3] / hn, hacc[4] / hn, hacc[5] / hn, hacc[6] / hn, hacc[7] / hn);
+            hn = 0;
+            for (double &x : hacc) x = 0;
+        }
+    }
     return SG_OK;
 }
 
