@@ -1221,6 +1221,103 @@ SG_DEVICE_INLINE void cp_async_commit() { asm volatile("cp.async.commit_group;" 
 template <int N>
 SG_DEVICE_INLINE void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// One warp's 16 query rows of one (sequence, head): S = Q K^T on mma.sync, masked softmax on the fragments, O = P V.
+// Qw = the warp's 16 rows of Q, Ks / Vs = all keys / values, row-major [row][32] halfs at a pitch of 40 halfs; mk = the
+// sequence's raw attention mask (0 beyond L); row_w0 = sequence position of the warp's first row; ctx_bh = output base of
+// this (sequence, head): row r lands at ctx_bh + r * H.
+template <uint32_t KS>
+SG_DEVICE_INLINE void attend_rows(const __half *Qw, const __half *Ks, const __half *Vs, const int64_t *mk, uint32_t lane,
+                                  uint32_t row_w0, uint32_t L, __half *ctx_bh, uint32_t H)
+{
+    constexpr uint32_t NT = KS * 2, P = 40;
+    const uint32_t g = lane >> 2, tq = lane & 3;       // fragment row group / quad lane
+    const float NEG_INF = -__uint_as_float(0x7F800000u);
+    const uint32_t r0 = row_w0 + g;                    // this thread's rows: r0 and r0 + 8
+    {
+    // Q fragments for both k-steps (d 0..15, 16..31): matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15)
+    uint32_t qa[2][4];
+    {
+        const uint32_t qaddr = smem_u32(Qw + (size_t)((lane & 7) + ((lane >> 3) & 1) * 8) * P + (lane >> 4) * 8);
+        ldmatrix_x4(qa[0], qaddr);
+        ldmatrix_x4(qa[1], qaddr + 32);
+    }
+    // S = Q K^T: per 8-key tile one ldmatrix.x4 = the B fragments of both k-steps
+    float sacc[NT][4];
+    const uint32_t kaddr = smem_u32(Ks + (size_t)(lane & 7) * P + (lane >> 3) * 8);
+#pragma unroll
+    for (uint32_t nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sacc[nt][e] = 0.0f;
+        uint32_t kb[4];
+        ldmatrix_x4(kb, kaddr + nt * 8 * P * 2);
+        mma_m16n8k16(sacc[nt], qa[0], kb[0], kb[1]);
+        mma_m16n8k16(sacc[nt], qa[1], kb[2], kb[3]);
+    }
+    // masked softmax on the fragments: rows r0 (elements 0,1) and r0+8 (elements 2,3).  Scores are kept in the log2
+    // domain (1/sqrt(d) and log2(e) folded into one factor) so that a probability is ONE ex2.approx of a difference;
+    // a fully masked row gets max = 0, and 2^(-inf) = 0 does the rest.
+    const float scale = 0.17677669529663687f * 1.4426950408889634f;
+    float mx0 = NEG_INF, mx1 = NEG_INF;
+#pragma unroll
+    for (uint32_t nt = 0; nt < NT; ++nt) {
+        const longlong2 mm = *reinterpret_cast<const longlong2 *>(mk + nt * 8 + tq * 2);
+        const float bx = mm.x == 1 ? 0.0f : NEG_INF, by = mm.y == 1 ? 0.0f : NEG_INF;
+        sacc[nt][0] = fmaf(sacc[nt][0], scale, bx); sacc[nt][1] = fmaf(sacc[nt][1], scale, by);
+        sacc[nt][2] = fmaf(sacc[nt][2], scale, bx); sacc[nt][3] = fmaf(sacc[nt][3], scale, by);
+        mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xFFFFFFFFu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xFFFFFFFFu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xFFFFFFFFu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xFFFFFFFFu, mx1, 2));
+    if (!(mx0 > NEG_INF)) mx0 = 0.0f;
+    if (!(mx1 > NEG_INF)) mx1 = 0.0f;
+    float sum0 = 0.0f, sum1 = 0.0f;
+#pragma unroll
+    for (uint32_t nt = 0; nt < NT; ++nt) {
+        sacc[nt][0] = ex2_approx(sacc[nt][0] - mx0);
+        sacc[nt][1] = ex2_approx(sacc[nt][1] - mx0);
+        sacc[nt][2] = ex2_approx(sacc[nt][2] - mx1);
+        sacc[nt][3] = ex2_approx(sacc[nt][3] - mx1);
+        sum0 += sacc[nt][0] + sacc[nt][1];
+        sum1 += sacc[nt][2] + sacc[nt][3];
+    }
+    sum0 += __shfl_xor_sync(0xFFFFFFFFu, sum0, 1); sum0 += __shfl_xor_sync(0xFFFFFFFFu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xFFFFFFFFu, sum1, 1); sum1 += __shfl_xor_sync(0xFFFFFFFFu, sum1, 2);
+    // O = P V : per 16-key step, the P A-fragment is built from two adjacent S tiles; V^T fragments by
+    // ldmatrix.trans: matrices (keys 0-7 | 8-15) x (d tile dt | dt + 1)
+    float oacc[4][4];
+#pragma unroll
+    for (uint32_t dt = 0; dt < 4; ++dt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) oacc[dt][e] = 0.0f;
+    const uint32_t vaddr = smem_u32(Vs + (size_t)((lane & 7) + ((lane >> 3) & 1) * 8) * P + (lane >> 4) * 8);
+#pragma unroll
+    for (uint32_t ks = 0; ks < KS; ++ks) {
+        uint32_t pa[4];
+        pa[0] = pack_half2(sacc[2 * ks][0], sacc[2 * ks][1]);
+        pa[1] = pack_half2(sacc[2 * ks][2], sacc[2 * ks][3]);
+        pa[2] = pack_half2(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1]);
+        pa[3] = pack_half2(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3]);
+#pragma unroll
+        for (uint32_t dp = 0; dp < 2; ++dp) {
+            uint32_t vb[4];
+            ldmatrix_x4_trans(vb, vaddr + (ks * 16 * P + dp * 16) * 2);
+            mma_m16n8k16(oacc[2 * dp], pa, vb[0], vb[1]);
+            mma_m16n8k16(oacc[2 * dp + 1], pa, vb[2], vb[3]);
+        }
+    }
+    const float inv0 = sum0 > 0.0f ? 1.0f / sum0 : 0.0f, inv1 = sum1 > 0.0f ? 1.0f / sum1 : 0.0f;
+#pragma unroll
+    for (uint32_t dt = 0; dt < 4; ++dt) {
+        const uint32_t d = dt * 8 + tq * 2;
+        if (r0 < L)
+            *reinterpret_cast<uint32_t *>(ctx_bh + (size_t)r0 * H + d) = pack_half2(oacc[dt][0] * inv0, oacc[dt][1] * inv0);
+        if (r0 + 8 < L)
+            *reinterpret_cast<uint32_t *>(ctx_bh + (size_t)(r0 + 8) * H + d) = pack_half2(oacc[dt][2] * inv1, oacc[dt][3] * inv1);
+    }
+    }
+}
+
 // Q, K and V of one (sequence, head) sit ROW-MAJOR in shared memory ([row][32] halfs at a pitch of 40 halfs = 80 bytes:
 // eight consecutive rows start in eight different 16-byte bank groups, so every ldmatrix phase is conflict-free).  The
 // fragments come from ldmatrix: Q as the A operand, K rows as the (col-major) B operand of Q K^T, and V through
@@ -1290,89 +1387,9 @@ attention_mma_kernel(const __half *__restrict__ qkv, const int64_t *__restrict__
         const uint32_t qb = item % q_blocks, bh = item / q_blocks, b = bh / heads, h = bh % heads;
         const uint32_t q_row0 = qb * 64;
         const uint32_t r0 = q_row0 + warp * 16 + g;    // this thread's rows: r0 and r0 + 8
-        if (q_row0 + warp * 16 < L) {
-            // Q fragments for both k-steps (d 0..15, 16..31): matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15)
-            uint32_t qa[2][4];
-            {
-                const uint32_t qaddr = smem_u32(bf.Qs + (size_t)(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * P + (lane >> 4) * 8);
-                ldmatrix_x4(qa[0], qaddr);
-                ldmatrix_x4(qa[1], qaddr + 32);
-            }
-            // S = Q K^T: per 8-key tile one ldmatrix.x4 = the B fragments of both k-steps
-            float sacc[NT][4];
-            const uint32_t kaddr = smem_u32(bf.Ks + (size_t)(lane & 7) * P + (lane >> 3) * 8);
-#pragma unroll
-            for (uint32_t nt = 0; nt < NT; ++nt) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) sacc[nt][e] = 0.0f;
-                uint32_t kb[4];
-                ldmatrix_x4(kb, kaddr + nt * 8 * P * 2);
-                mma_m16n8k16(sacc[nt], qa[0], kb[0], kb[1]);
-                mma_m16n8k16(sacc[nt], qa[1], kb[2], kb[3]);
-            }
-            // masked softmax on the fragments: rows r0 (elements 0,1) and r0+8 (elements 2,3).  Scores are kept in the log2
-            // domain (1/sqrt(d) and log2(e) folded into one factor) so that a probability is ONE ex2.approx of a difference;
-            // a fully masked row gets max = 0, and 2^(-inf) = 0 does the rest.
-            const float scale = 0.17677669529663687f * 1.4426950408889634f;
-            float mx0 = NEG_INF, mx1 = NEG_INF;
-#pragma unroll
-            for (uint32_t nt = 0; nt < NT; ++nt) {
-                const longlong2 mm = *reinterpret_cast<const longlong2 *>(bf.mk + nt * 8 + tq * 2);
-                const float bx = mm.x == 1 ? 0.0f : NEG_INF, by = mm.y == 1 ? 0.0f : NEG_INF;
-                sacc[nt][0] = fmaf(sacc[nt][0], scale, bx); sacc[nt][1] = fmaf(sacc[nt][1], scale, by);
-                sacc[nt][2] = fmaf(sacc[nt][2], scale, bx); sacc[nt][3] = fmaf(sacc[nt][3], scale, by);
-                mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
-                mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
-            }
-            mx0 = fmaxf(mx0, __shfl_xor_sync(0xFFFFFFFFu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xFFFFFFFFu, mx0, 2));
-            mx1 = fmaxf(mx1, __shfl_xor_sync(0xFFFFFFFFu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xFFFFFFFFu, mx1, 2));
-            if (!(mx0 > NEG_INF)) mx0 = 0.0f;
-            if (!(mx1 > NEG_INF)) mx1 = 0.0f;
-            float sum0 = 0.0f, sum1 = 0.0f;
-#pragma unroll
-            for (uint32_t nt = 0; nt < NT; ++nt) {
-                sacc[nt][0] = ex2_approx(sacc[nt][0] - mx0);
-                sacc[nt][1] = ex2_approx(sacc[nt][1] - mx0);
-                sacc[nt][2] = ex2_approx(sacc[nt][2] - mx1);
-                sacc[nt][3] = ex2_approx(sacc[nt][3] - mx1);
-                sum0 += sacc[nt][0] + sacc[nt][1];
-                sum1 += sacc[nt][2] + sacc[nt][3];
-            }
-            sum0 += __shfl_xor_sync(0xFFFFFFFFu, sum0, 1); sum0 += __shfl_xor_sync(0xFFFFFFFFu, sum0, 2);
-            sum1 += __shfl_xor_sync(0xFFFFFFFFu, sum1, 1); sum1 += __shfl_xor_sync(0xFFFFFFFFu, sum1, 2);
-            // O = P V : per 16-key step, the P A-fragment is built from two adjacent S tiles; V^T fragments by
-            // ldmatrix.trans: matrices (keys 0-7 | 8-15) x (d tile dt | dt + 1)
-            float oacc[4][4];
-#pragma unroll
-            for (uint32_t dt = 0; dt < 4; ++dt)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) oacc[dt][e] = 0.0f;
-            const uint32_t vaddr = smem_u32(bf.Vs + (size_t)((lane & 7) + ((lane >> 3) & 1) * 8) * P + (lane >> 4) * 8);
-#pragma unroll
-            for (uint32_t ks = 0; ks < KS; ++ks) {
-                uint32_t pa[4];
-                pa[0] = pack_half2(sacc[2 * ks][0], sacc[2 * ks][1]);
-                pa[1] = pack_half2(sacc[2 * ks][2], sacc[2 * ks][3]);
-                pa[2] = pack_half2(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1]);
-                pa[3] = pack_half2(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3]);
-#pragma unroll
-                for (uint32_t dp = 0; dp < 2; ++dp) {
-                    uint32_t vb[4];
-                    ldmatrix_x4_trans(vb, vaddr + (ks * 16 * P + dp * 16) * 2);
-                    mma_m16n8k16(oacc[2 * dp], pa, vb[0], vb[1]);
-                    mma_m16n8k16(oacc[2 * dp + 1], pa, vb[2], vb[3]);
-                }
-            }
-            const float inv0 = sum0 > 0.0f ? 1.0f / sum0 : 0.0f, inv1 = sum1 > 0.0f ? 1.0f / sum1 : 0.0f;
-#pragma unroll
-            for (uint32_t dt = 0; dt < 4; ++dt) {
-                const uint32_t d = dt * 8 + tq * 2;
-                if (r0 < L)
-                    *reinterpret_cast<uint32_t *>(ctx + ((size_t)b * L + r0) * H + h * D + d) = pack_half2(oacc[dt][0] * inv0, oacc[dt][1] * inv0);
-                if (r0 + 8 < L)
-                    *reinterpret_cast<uint32_t *>(ctx + ((size_t)b * L + r0 + 8) * H + h * D + d) = pack_half2(oacc[dt][2] * inv1, oacc[dt][3] * inv1);
-            }
-        }
+        if (q_row0 + warp * 16 < L)
+            attend_rows<KS>(bf.Qs + (size_t)warp * 16 * P, bf.Ks, bf.Vs, bf.mk, lane, q_row0 + warp * 16, L,
+                            ctx + (size_t)b * L * H + h * D, H);
         __syncthreads();                               // the next prefetch overwrites this buffer
     }
 }
@@ -1394,6 +1411,137 @@ void launch_attention_mma(const __half *qkv, const int64_t *mask, uint32_t b, ui
     const uint32_t per_sm = (uint32_t)per_sm_cached;
     const uint32_t grid = n_items < 148 * per_sm ? n_items : 148 * per_sm;
     launch_pdl(attention_mma_kernel<KS>, dim3(grid), dim3(128), smem_per_cta, st, qkv, mask, L, H, heads, n_items, q_blocks, ctx);
+}
+
+// ---- small batches: QKV projection + attention of one (sequence, head) in ONE CTA -------------------------------
+// The single-query forward is a chain of ~26 dependent launches at ~9 us each; this kernel removes one per layer.  A CTA
+// computes its head's q, k, v columns for the whole sequence on the tensor core -- [128 rows x 384] . [384 x 96]^T, the
+// 96 weight rows being three 32-row boxes of Wqkv (q, k, v of head h), all six K-blocks in flight at once (no ring to
+// recycle; the weight boxes are requested BEFORE the programmatic-dependency wait, they do not depend on the previous
+// kernel) -- drains the accumulator (+bias, -> fp16, the rounding the separate QKV GEMM applied) straight into the
+// row-major shared-memory tiles the attention fragments are read from, and runs attend_rows on them.  L <= 128.
+template <uint32_t KS>
+__global__ void __launch_bounds__(256, 1)
+qkv_attention_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                     const float *__restrict__ bqkv, const int64_t *__restrict__ mask, uint32_t L, uint32_t H, uint32_t heads,
+                     __half *__restrict__ ctx)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr uint32_t D = 32, P = 40, L16 = KS * 16, A_BYTES = 128 * 128, W_BOX = 32 * 128, STAGE = A_BYTES + 3 * W_BOX;   // 28 KB
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t nkb = H / 64;                                   // 6: every K-block has its own stage
+    const uint32_t b = blockIdx.x / heads, h = blockIdx.x % heads;
+    __half *Qs = reinterpret_cast<__half *>(smem + (size_t)nkb * STAGE);        // [128][P]
+    __half *Ks = Qs + 128 * P, *Vs = Ks + 128 * P;
+    int64_t *mk = reinterpret_cast<int64_t *>(Vs + 128 * P);                    // [128]
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(mk + 128), *wfull_bar = full_bar + nkb, *done_bar = wfull_bar + nkb;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < nkb; ++i) {
+            mbar_init(smem_u32(full_bar + i), 1);
+            mbar_init(smem_u32(wfull_bar + i), 1);
+        }
+        mbar_init(smem_u32(done_bar), 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_w);
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp == 0) {
+        // weights first (constant), activations after the previous kernel has completed
+        if (elect_one_sync()) {
+            for (uint32_t kb = 0; kb < nkb; ++kb) {
+                const uint32_t sw = smem_u32(smem + (size_t)kb * STAGE) + A_BYTES;
+                mbar_arrive_expect_tx(smem_u32(wfull_bar + kb), 3 * W_BOX);
+#pragma unroll
+                for (uint32_t m = 0; m < 3; ++m)
+                    tma_load_2d(sw + m * W_BOX, &tmap_w, smem_u32(wfull_bar + kb), (int32_t)(kb * 64), (int32_t)(m * H + h * D));
+            }
+        }
+        __syncwarp();
+        pdl_wait();
+        pdl_trigger();
+        if (elect_one_sync()) {
+            for (uint32_t kb = 0; kb < nkb; ++kb) {
+                mbar_arrive_expect_tx(smem_u32(full_bar + kb), A_BYTES);
+                tma_load_2d(smem_u32(smem + (size_t)kb * STAGE), &tmap_a, smem_u32(full_bar + kb), (int32_t)(kb * 64), (int32_t)(b * L));
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc_f16(128, 96);
+        for (uint32_t kb = 0; kb < nkb; ++kb) {
+            mbar_wait(smem_u32(wfull_bar + kb), 0);
+            mbar_wait(smem_u32(full_bar + kb), 0);
+            tc_fence_after();
+            if (elect_one_sync()) {
+                const uint32_t sa = smem_u32(smem + (size_t)kb * STAGE);
+                const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + A_BYTES);
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k) umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                if (kb + 1 == nkb) umma_commit(smem_u32(done_bar));
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        // thread t <-> sequence position t <-> TMEM lane t: q | k | v of the head = accumulator columns 0-31 | 32-63 | 64-95
+        const uint32_t t = threadIdx.x - 128;
+        const uint32_t lane_base = ((warp & 3) * 32) << 16;
+        pdl_wait();                                                // (mask and bias are inputs / weights; harmless)
+        mk[t] = (t < L) ? mask[(size_t)b * L + t] : 0;
+        mbar_wait(smem_u32(done_bar), 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (uint32_t m = 0; m < 3; ++m) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + lane_base + m * 32, r);
+            tmem_ld_wait();
+            const float4 *bias4 = reinterpret_cast<const float4 *>(bqkv + m * H + h * D);
+            __align__(16) __half o[32];
+#pragma unroll
+            for (uint32_t q4 = 0; q4 < 8; ++q4) {
+                const float4 bb = __ldg(bias4 + q4);
+                o[4 * q4] = __float2half_rn(__uint_as_float(r[4 * q4]) + bb.x);
+                o[4 * q4 + 1] = __float2half_rn(__uint_as_float(r[4 * q4 + 1]) + bb.y);
+                o[4 * q4 + 2] = __float2half_rn(__uint_as_float(r[4 * q4 + 2]) + bb.z);
+                o[4 * q4 + 3] = __float2half_rn(__uint_as_float(r[4 * q4 + 3]) + bb.w);
+            }
+            // rows at or beyond L belong to the next sequence / padding: they must read as zeros (keys are masked anyway)
+            __half *dst = (m == 0 ? Qs : (m == 1 ? Ks : Vs)) + (size_t)t * P;
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q)
+                reinterpret_cast<uint4 *>(dst)[q] = t < L ? reinterpret_cast<const uint4 *>(o)[q] : make_uint4(0, 0, 0, 0);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const uint32_t w = warp - 4;
+        for (uint32_t q_row0 = 0; q_row0 < L; q_row0 += 64)
+            if (q_row0 + w * 16 < L)
+                attend_rows<KS>(Qs + (size_t)(q_row0 + w * 16) * P, Ks, Vs, mk, lane, q_row0 + w * 16, L,
+                                ctx + (size_t)b * L * H + h * D, H);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 128);
+    }
+}
+
+template <uint32_t KS>
+cudaError_t launch_qkv_attention(const CUtensorMap &ta, const CUtensorMap &tw, const float *bqkv, const int64_t *mask, uint32_t b,
+                                 uint32_t L, uint32_t H, uint32_t heads, __half *ctx, cudaStream_t st)
+{
+    const size_t smem = (size_t)(H / 64) * (128 * 128 + 3 * 32 * 128) + 3 * 128 * 40 * 2 + 128 * 8 + (2 * (H / 64) + 1) * 8 + 16;
+    static DevAttr da;
+    cudaError_t e = ensure_smem(qkv_attention_kernel<KS>, da, smem);
+    if (e != cudaSuccess) return e;
+    e = launch_pdl(qkv_attention_kernel<KS>, dim3(b * heads), dim3(256), smem, st, ta, tw, bqkv, mask, L, H, heads, ctx);
+    count_launch();
+    return e;
 }
 
 // ---- masked mean-pool + finalize (reference minilm.rs:959-978, :846-878) -----------------------------
@@ -1438,8 +1586,18 @@ __global__ void pool_norm_kernel(const float *__restrict__ hidden, const int64_t
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        // left-to-right sum of squares (the reference's order): the loads and products run ahead in blocks of 8, only the
+        // adds form the chain
         float ss = 0.0f;
-        for (uint32_t d = 0; d < H; ++d) ss = __fadd_rn(ss, __fmul_rn(pooled[d], pooled[d]));
+        uint32_t d = 0;
+        for (; d + 8 <= H; d += 8) {
+            float p[8];
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) p[j] = __fmul_rn(pooled[d + j], pooled[d + j]);
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) ss = __fadd_rn(ss, p[j]);
+        }
+        for (; d < H; ++d) ss = __fadd_rn(ss, __fmul_rn(pooled[d], pooled[d]));
         s_norm = __fsqrt_rn(ss);
     }
     __syncthreads();
@@ -1775,6 +1933,9 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
     }
     const bool ln_pair = !ln_cluster && H == 384 && !getenv("SG_ENC_NO_LN_PAIR");
     const char *skip_env = getenv("SG_ENC_SKIP");
+    // one (sequence, head) per CTA while that is at most one wave (head dim 32, 12 heads: up to 12 sequences)
+    const bool fused_qkv_attn = L <= 128 && H == e->heads * 32 && H % 64 == 0 && H <= 384 && b * e->heads <= 148 &&
+                                !getenv("SG_ENC_NO_FUSED_QKV") && !getenv("SG_ENC_ATTN_SIMT");
     const int skip = skip_env ? atoi(skip_env) : 0;
     for (uint32_t l = 0; l < e->layers; ++l) {
         const Layer &ly = e->L[l];
@@ -1786,7 +1947,21 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
         GemmArgs g{};
         // QKV = h0 . Wqkv^T + b
         g.K = H; g.N = 3 * H; g.stages = 3; g.bias = ly.bqkv; g.out = e->qkv;   // 96 KB: two CTAs per SM
-        if (skip & 1) {
+        if (fused_qkv_attn) {
+            // small batches: QKV projection + attention per (sequence, head) in one launch
+            CUtensorMap t_wqkv_head;
+            if ((rc = encode_tmap(&t_wqkv_head, ly.wqkv, H, 3 * H, 32)) != SG_OK) return rc;
+            switch ((L + 15) / 16) {
+            case 1: SG_CUDA_TRY(launch_qkv_attention<1>(t_h0, t_wqkv_head, ly.bqkv, d_mask, b, L, H, e->heads, e->ctx, st)); break;
+            case 2: SG_CUDA_TRY(launch_qkv_attention<2>(t_h0, t_wqkv_head, ly.bqkv, d_mask, b, L, H, e->heads, e->ctx, st)); break;
+            case 3: SG_CUDA_TRY(launch_qkv_attention<3>(t_h0, t_wqkv_head, ly.bqkv, d_mask, b, L, H, e->heads, e->ctx, st)); break;
+            case 4: SG_CUDA_TRY(launch_qkv_attention<4>(t_h0, t_wqkv_head, ly.bqkv, d_mask, b, L, H, e->heads, e->ctx, st)); break;
+            case 5: SG_CUDA_TRY(launch_qkv_attention<5>(t_h0, t_wqkv_head, ly.bqkv, d_mask, b, L, H, e->heads, e->ctx, st)); break;
+            case 6: SG_CUDA_TRY(launch_qkv_attention<6>(t_h0, t_wqkv_head, ly.bqkv, d_mask, b, L, H, e->heads, e->ctx, st)); break;
+            case 7: SG_CUDA_TRY(launch_qkv_attention<7>(t_h0, t_wqkv_head, ly.bqkv, d_mask, b, L, H, e->heads, e->ctx, st)); break;
+            default: SG_CUDA_TRY(launch_qkv_attention<8>(t_h0, t_wqkv_head, ly.bqkv, d_mask, b, L, H, e->heads, e->ctx, st)); break;
+            }
+        } else if (skip & 1) {
         } else if (pair) {
             CUtensorMap t_wqkv_half;
             if ((rc = encode_tmap(&t_wqkv_half, ly.wqkv, H, 3 * H, 96)) != SG_OK) return rc;
@@ -1797,7 +1972,7 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
             SG_CUDA_TRY((launch_gemm_persist<EPI_BIAS>(t_h0, t_wqkv, t_qkv_out, g, m_tiles, 148, st)));
         }
         else SG_CUDA_TRY((launch_gemm<128, EPI_BIAS>(t_h0, t_wqkv, g, m_tiles, st)));
-        if (skip & 2) {
+        if (fused_qkv_attn || (skip & 2)) {
         } else if (L <= 128 && !getenv("SG_ENC_ATTN_SIMT")) {
             switch ((L + 15) / 16) {
             case 1: launch_attention_mma<1>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st); break;
