@@ -641,10 +641,14 @@ int search_tc_chunk(sg_store *s, const TcPlan &pl, const float *d_q, uint32_t b,
     f.gtau = s->d_gtau;
     f.max_row_norm = s->d_max_norm;
     f.c_acc = tc_c_acc(s->dim);
-    {   // rows staged per re-score round: q + rows within 28 KB of dynamic shared memory (18.5 KB more are static)
+    {   // rows staged per re-score round: q + rows in dynamic shared memory (18.5 KB more are static).  Up to 32 rows within
+        // 28 KB for the small over-selections (k <= 24: one round, 4 CTAs per SM); up to 64 rows within 52 KB when kk is
+        // large (k = 120 -> kk = 152: 3 rounds instead of 5 -- a round is one global round trip + one sequential 384-step
+        // chain per candidate, the rounds do not overlap)
         const size_t row_b = (size_t)(s->dim / 2 + 1) * 4, q_b = (size_t)s->dim * 4;
-        size_t rcn = (28 * 1024 - q_b) / row_b;
-        f.rc = (uint32_t)(rcn > 32 ? 32 : (rcn < 1 ? 1 : rcn));
+        const size_t budget = kk > 32 ? 52 * 1024 : 28 * 1024, cap = kk > 32 ? 64 : 32;
+        size_t rcn = (budget - q_b) / row_b;
+        f.rc = (uint32_t)(rcn > cap ? cap : (rcn < 1 ? 1 : rcn));
     }
     f.ids_out = d_ids;
     f.dist_out = d_dist;
