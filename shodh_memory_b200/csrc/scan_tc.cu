@@ -852,16 +852,29 @@ finalize_tc_kernel(const __grid_constant__ FinalizeArgs f)
     }
     __syncthreads();
     const uint32_t total = pre[L];
-    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
-        uint32_t lo = 0, hi = L;                 // region l with pre[l] <= i < pre[l + 1]
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (pre[mid] <= i) lo = mid; else hi = mid;
+    // four entries per thread and step: the four candidate loads are in flight together (one global round trip per step
+    // instead of four -- with k = 120 a query gathers a few thousand entries)
+    for (uint32_t i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
+        uint64_t key[4];
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + u * blockDim.x;
+            key[u] = KEY_SENTINEL;
+            if (i < total) {
+                uint32_t lo = 0, hi = L;         // region l with pre[l] <= i < pre[l + 1]
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (pre[mid] <= i) lo = mid; else hi = mid;
+                }
+                key[u] = __ldg(f.cand + ((size_t)q * L + lo) * f.cap_l + (i - pre[lo]));
+            }
         }
-        const uint64_t key = f.cand[((size_t)q * L + lo) * f.cap_l + (i - pre[lo])];
-        if ((uint32_t)(key >> 32) <= gt) {
-            const uint32_t slot = atomicAdd(&s_n, 1u);
-            if (slot < TC_FIN_NC) keys[slot] = key;
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u) {
+            if (i0 + u * blockDim.x < total && (uint32_t)(key[u] >> 32) <= gt) {
+                const uint32_t slot = atomicAdd(&s_n, 1u);
+                if (slot < TC_FIN_NC) keys[slot] = key[u];
+            }
         }
     }
     __syncthreads();
@@ -898,12 +911,29 @@ finalize_tc_kernel(const __grid_constant__ FinalizeArgs f)
     const uint32_t pitch = f.dim / 2 + 1, vec_per_row = f.dim / 8;
     for (uint32_t c0 = 0; c0 < kk; c0 += f.rc) {
         const uint32_t nc = kk - c0 < f.rc ? kk - c0 : f.rc;
-        for (uint32_t i = threadIdx.x; i < nc * vec_per_row; i += blockDim.x) {
-            const uint32_t c = i / vec_per_row, v = i - c * vec_per_row;
-            const uint32_t row = (uint32_t)(sorted[c0 + c] & 0xFFFFFFFFu);
-            const uint4 x = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(f.rows) + (size_t)row * f.dim) + v);
-            uint32_t *dst = rows_s + (size_t)c * pitch + 4 * v;
-            dst[0] = x.x; dst[1] = x.y; dst[2] = x.z; dst[3] = x.w;
+        // six 16-byte pieces per thread and step, all loads issued before the first store (the rows are random 768-byte
+        // reads from HBM: a piece-by-piece loop paid one round trip per piece)
+        const uint32_t pieces = nc * vec_per_row;
+        for (uint32_t i0 = threadIdx.x; i0 < pieces; i0 += 6 * blockDim.x) {
+            uint4 x[6];
+#pragma unroll
+            for (uint32_t u = 0; u < 6; ++u) {
+                const uint32_t i = i0 + u * blockDim.x;
+                if (i < pieces) {
+                    const uint32_t c = i / vec_per_row, v = i - c * vec_per_row;
+                    const uint32_t row = (uint32_t)(sorted[c0 + c] & 0xFFFFFFFFu);
+                    x[u] = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(f.rows) + (size_t)row * f.dim) + v);
+                }
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < 6; ++u) {
+                const uint32_t i = i0 + u * blockDim.x;
+                if (i < pieces) {
+                    const uint32_t c = i / vec_per_row, v = i - c * vec_per_row;
+                    uint32_t *dst = rows_s + (size_t)c * pitch + 4 * v;
+                    dst[0] = x[u].x; dst[1] = x[u].y; dst[2] = x[u].z; dst[3] = x[u].w;
+                }
+            }
         }
         __syncthreads();
         if (threadIdx.x < nc) {
