@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 
 #include "../../include/shodh_gpu.h"
@@ -52,7 +53,8 @@ inline cudaError_t launch_pdl(K kern, dim3 grid, dim3 block, size_t smem, cudaSt
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    static const bool no_pdl = getenv("SG_NO_PDL") != nullptr;      // measurement switch: plain stream-ordered launches
+    cfg.numAttrs = no_pdl ? 0 : 1;
     return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
