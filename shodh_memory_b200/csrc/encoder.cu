@@ -20,6 +20,7 @@
 // kernel is checked against a PyTorch fp32 BertModel with the same weights (tests/test_encoder_gpu.py).
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -1395,22 +1396,23 @@ attention_mma_kernel(const __half *__restrict__ qkv, const int64_t *__restrict__
 }
 
 template <uint32_t KS>
-void launch_attention_mma(const __half *qkv, const int64_t *mask, uint32_t b, uint32_t L, uint32_t H, uint32_t heads,
-                          __half *ctx, cudaStream_t st)
+cudaError_t launch_attention_mma(const __half *qkv, const int64_t *mask, uint32_t b, uint32_t L, uint32_t H, uint32_t heads,
+                                 __half *ctx, cudaStream_t st)
 {
     const uint32_t q_blocks = (L + 63) / 64, n_items = b * heads * q_blocks;
     constexpr uint32_t smem_per_cta = 2 * ((2 * KS * 16 + 64) * 80 + KS * 16 * 8);
     static DevAttr da;
-    if (ensure_smem(attention_mma_kernel<KS>, da, smem_per_cta) != cudaSuccess) return;
-    static int per_sm_cached = 0;                      // resident CTAs per SM (registers / shared memory), asked once
-    if (per_sm_cached == 0) {
+    cudaError_t err = ensure_smem(attention_mma_kernel<KS>, da, smem_per_cta);
+    if (err != cudaSuccess) return err;
+    static std::atomic<int> per_sm_cached{0};                      // resident CTAs per SM (registers / shared memory), asked once
+    if (per_sm_cached.load(std::memory_order_relaxed) == 0) {
         int n = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, attention_mma_kernel<KS>, 128, smem_per_cta) != cudaSuccess || n < 1) n = 1;
-        per_sm_cached = n;
+        per_sm_cached.store(n, std::memory_order_relaxed);
     }
-    const uint32_t per_sm = (uint32_t)per_sm_cached;
+    const uint32_t per_sm = (uint32_t)per_sm_cached.load(std::memory_order_relaxed);
     const uint32_t grid = n_items < 148 * per_sm ? n_items : 148 * per_sm;
-    launch_pdl(attention_mma_kernel<KS>, dim3(grid), dim3(128), smem_per_cta, st, qkv, mask, L, H, heads, n_items, q_blocks, ctx);
+    return launch_pdl(attention_mma_kernel<KS>, dim3(grid), dim3(128), smem_per_cta, st, qkv, mask, L, H, heads, n_items, q_blocks, ctx);
 }
 
 // ---- small batches: QKV projection + attention of one (sequence, head) in ONE CTA -------------------------------
@@ -1975,14 +1977,14 @@ int encode_device_locked(sg_encoder *e, const int64_t *d_ids, const int64_t *d_m
         if (fused_qkv_attn || (skip & 2)) {
         } else if (L <= 128 && !getenv("SG_ENC_ATTN_SIMT")) {
             switch ((L + 15) / 16) {
-            case 1: launch_attention_mma<1>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st); break;
-            case 2: launch_attention_mma<2>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st); break;
-            case 3: launch_attention_mma<3>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st); break;
-            case 4: launch_attention_mma<4>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st); break;
-            case 5: launch_attention_mma<5>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st); break;
-            case 6: launch_attention_mma<6>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st); break;
-            case 7: launch_attention_mma<7>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st); break;
-            default: launch_attention_mma<8>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st); break;
+            case 1: SG_CUDA_TRY(launch_attention_mma<1>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st)); break;
+            case 2: SG_CUDA_TRY(launch_attention_mma<2>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st)); break;
+            case 3: SG_CUDA_TRY(launch_attention_mma<3>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st)); break;
+            case 4: SG_CUDA_TRY(launch_attention_mma<4>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st)); break;
+            case 5: SG_CUDA_TRY(launch_attention_mma<5>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st)); break;
+            case 6: SG_CUDA_TRY(launch_attention_mma<6>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st)); break;
+            case 7: SG_CUDA_TRY(launch_attention_mma<7>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st)); break;
+            default: SG_CUDA_TRY(launch_attention_mma<8>(e->qkv, d_mask, b, L, H, e->heads, e->ctx, st)); break;
             }
         } else if (L <= 128) {
             const uint32_t L4 = (L + 3) & ~3u;
