@@ -212,25 +212,68 @@ static bool vmm_ensure(sg_store *s, uint64_t need_bytes, int *rc_out)
     const CUmemAllocationProp prop = vmm_prop(s->device);
     size_t gran = 0;
     if (api.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0) return false;
-    if (!s->d_rows) {
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
-        const uint64_t row_bytes = (uint64_t)s->dim * s->esize;
-        uint64_t va = 0xFFFFFFFEull * row_bytes;                       // ids are u32
-        if (va > (uint64_t)total_b) va = total_b;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
+    const uint64_t row_bytes = (uint64_t)s->dim * s->esize;
+    uint64_t va_max = 0xFFFFFFFEull * row_bytes;                       // ids are u32
+    if (va_max > (uint64_t)total_b) va_max = total_b;
+    va_max = (va_max + gran - 1) / gran * gran;
+    // The reservation is address space, not memory -- but address space is finite too (one index per user: a process may
+    // hold thousands of stores), so a store starts with 16 GB (22M fp16 rows of 384) and, should it outgrow that, moves
+    // its chunks into a range 8x as large: the physical chunks are re-mapped, nothing is copied.
+    auto reserve = [&](uint64_t want_va, CUdeviceptr *base) -> uint64_t {
+        uint64_t va = want_va > va_max ? va_max : want_va;
         va = (va + gran - 1) / gran * gran;
+        return api.reserve(base, va, 0, 0, 0) == CUDA_SUCCESS ? va : 0;
+    };
+    const uint64_t va0 = (uint64_t)env_u32("SG_STORE_VA_MB", 16384) << 20;
+    if (!s->d_rows) {
         CUdeviceptr base = 0;
-        if (api.reserve(&base, va, 0, 0, 0) != CUDA_SUCCESS) return false;
+        const uint64_t va = reserve(need_bytes * 2 > va0 ? need_bytes * 2 : va0, &base);
+        if (!va) return false;
         s->d_rows = reinterpret_cast<void *>(base);
         s->va_bytes = va;
         s->mapped_bytes = 0;
         s->vmm = true;
     }
     if (need_bytes <= s->mapped_bytes) return true;
-    if (need_bytes > s->va_bytes) {
+    if (need_bytes > va_max) {
         set_error("store would exceed the device's memory (%llu bytes of rows)", (unsigned long long)need_bytes);
         *rc_out = SG_ERR_OOM;
         return true;
+    }
+    if (need_bytes > s->va_bytes) {
+        // move to a larger range: every search in flight must be done with the old addresses first
+        if (cudaDeviceSynchronize() != cudaSuccess) {
+            *rc_out = SG_ERR_CUDA;
+            return true;
+        }
+        CUdeviceptr nbase = 0;
+        uint64_t nva = reserve(s->va_bytes * 8 > need_bytes * 2 ? s->va_bytes * 8 : need_bytes * 2, &nbase);
+        if (!nva) nva = reserve(need_bytes + need_bytes / 8, &nbase);
+        if (!nva) {
+            set_error("no address range of %llu bytes left for the store", (unsigned long long)need_bytes);
+            *rc_out = SG_ERR_OOM;
+            return true;
+        }
+        CUmemAccessDesc acc = {};
+        acc.location = prop.location;
+        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        bool ok = s->mapped_bytes == 0 || api.unmap((CUdeviceptr)s->d_rows, s->mapped_bytes) == CUDA_SUCCESS;
+        uint64_t off = 0;
+        for (size_t i = 0; ok && i < s->vmm_handles.size(); ++i) {
+            ok = api.map(nbase + off, s->vmm_sizes[i], 0, (CUmemGenericAllocationHandle)s->vmm_handles[i], 0) == CUDA_SUCCESS;
+            off += s->vmm_sizes[i];
+        }
+        if (ok && off) ok = api.set_access(nbase, off, &acc, 1) == CUDA_SUCCESS;
+        if (!ok) {
+            set_error("re-mapping the store's %llu bytes into a larger address range failed", (unsigned long long)s->mapped_bytes);
+            *rc_out = SG_ERR_CUDA;                      // the store is unusable: its rows are unmapped
+            return true;
+        }
+        api.addr_free((CUdeviceptr)s->d_rows, s->va_bytes);
+        s->d_rows = reinterpret_cast<void *>(nbase);
+        s->va_bytes = nva;
     }
     // grow by at least 1/8 of what is mapped (amortises the map calls), in whole granules
     uint64_t want = need_bytes - s->mapped_bytes;

@@ -78,8 +78,10 @@ def test_many_small_stores_stay_small(sg):
         st.close()
 
 
-def test_copy_fallback_still_correct(sg, oracle):
-    """SG_STORE_VMM=0 forces the allocate-and-copy path (read once per process -> child process)"""
+@pytest.mark.parametrize("env,in_place", [({"SG_STORE_VMM": "0"}, False), ({"SG_STORE_VA_MB": "8"}, True)])
+def test_growth_modes_in_a_child_process(sg, oracle, env, in_place):
+    """SG_STORE_VMM=0 forces the allocate-and-copy path; SG_STORE_VA_MB=8 makes the store outgrow its address range
+    several times (chunks re-mapped into a larger range, nothing copied).  Both are read once per process -> child."""
     code = r"""
 import numpy as np, sys
 sys.path.insert(0, %r)
@@ -87,17 +89,20 @@ import shodh_memory_b200 as sg
 from oracle import oracle
 st = sg.GpuVectorStore(384, "f16")
 done = 0
-for n in (10, 5000, 60000):
-    st.append_synthetic(7711, done, n - done); done = n
-assert not st.memory_info()["in_place"]
 q = np.random.default_rng(5).standard_normal((4, 384)).astype(np.float32)
+for n in (10, 5000, 60000, 150000):
+    st.append_synthetic(7711, done, n - done); done = n
+    ids, dist, counts = st.search_batch(q, 10)          # searches between growth steps keep working
+assert st.memory_info()["in_place"] == %r, st.memory_info()
 corpus = oracle.synth_corpus(7711, 0, done, 384, f16_round=True)
-ids, dist, counts = st.search_batch(q, 10)
-for i in range(4):
-    rid, rdist = oracle.brute_force_search(corpus, q[i], 10)
-    assert np.array_equal(ids[i], rid) and np.array_equal(dist[i].view(np.uint32), np.asarray(rdist, np.float32).view(np.uint32))
+assert np.array_equal(st.get_vectors(0, done).view(np.uint32), corpus.view(np.uint32))
+for mode in ("exact", "auto"):
+    st.set_tc_mode(mode)
+    ids, dist, counts = st.search_batch(q, 10)
+    for i in range(4):
+        rid, rdist = oracle.brute_force_search(corpus, q[i], 10)
+        assert np.array_equal(ids[i], rid) and np.array_equal(dist[i].view(np.uint32), np.asarray(rdist, np.float32).view(np.uint32))
 print("ok")
-""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, SG_STORE_VMM="0")
-    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), in_place)
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
