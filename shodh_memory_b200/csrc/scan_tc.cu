@@ -36,6 +36,8 @@
 #include <cstdlib>
 #include <mutex>
 
+#include <atomic>
+
 #include "sg_internal.h"
 #include "sg_push.cuh"
 #include "sg_tc.cuh"
@@ -538,6 +540,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const TcArgs a)
         tma_prefetch_desc(&tmap_rows);
     }
     if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
+    pdl_wait();                                              // everything above overlapped the previous step's tail
     stage_queries(a, a_base, a.q_tile * TC_M, a.nq);         // the resident A operand (fp16 queries)
     fence_proxy_async();
     tc_fence_before();
@@ -682,6 +685,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const TcArgs a)
 
     // resident A operand: this CTA's 128 queries, converted in place; then the pair synchronises so the leader's MMA
     // thread may read the peer's A through the pair datapath
+    pdl_wait();                                              // everything above overlapped the previous step's tail
     {
         const uint32_t qf = a.q_tile * 256 + rank * TC_M;
         stage_queries(a, a_base, qf, a.nq > rank * TC_M ? (a.nq - rank * TC_M < TC_M ? a.nq - rank * TC_M : TC_M) : 0);
@@ -1018,27 +1022,40 @@ template <typename K>
 cudaError_t launch_sweep(K kern, const CUtensorMap &tmap_rows, const TcArgs &a, uint32_t grid,
                          size_t smem, cudaStream_t st)
 {
-    static const int coop = [] {
-        const char *v = getenv("SG_TC_COOP");
-        return (v && *v) ? atoi(v) : 1;
-    }();
+    const char *v = getenv("SG_TC_COOP");
+    const int coop = (v && *v) ? atoi(v) : 1;
+    // cooperative (co-residency guaranteed) + programmatic stream serialisation (the prologue -- barrier init, TMEM
+    // allocation, descriptor prefetch -- overlaps the tail of the previous step; the kernel calls pdl_wait() before it
+    // touches global memory).  A driver that refuses the combination gets the cooperative launch alone.
+    static std::atomic<int> both_ok{1};
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
     if (coop) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(TC_THREADS);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeCooperative;
-        attr[0].val.cooperative = 1;
-        cfg.attrs = attr;
+        if (both_ok.load(std::memory_order_relaxed)) {
+            cfg.attrs = attr;
+            cfg.numAttrs = 2;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap_rows, a);
+            if (e == cudaSuccess) return e;
+            cudaGetLastError();
+            both_ok.store(0, std::memory_order_relaxed);
+        }
+        cfg.attrs = attr + 1;
         cfg.numAttrs = 1;
         cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap_rows, a);
         if (e == cudaSuccess) return e;
         cudaGetLastError();                      // clear; fall through to the plain launch
     }
-    kern<<<grid, TC_THREADS, smem, st>>>(tmap_rows, a);
-    return cudaGetLastError();
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, tmap_rows, a);
 }
 
 }  // namespace
