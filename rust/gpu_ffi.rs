@@ -31,6 +31,14 @@ pub struct SgStore {
 pub struct SgEncoder {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct SgPq {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct SgSpann {
+    _private: [u8; 0],
+}
 
 /// LearnedWeights (src/relevance.rs:64-88)
 #[repr(C)]
@@ -122,6 +130,52 @@ extern "C" {
                              emb_out: *mut f32) -> c_int;
     pub fn sg_pool_finalize(device: c_int, hidden: *const f32, attention_mask: *const i64, b: u32, l: u32, h: u32,
                             out: *mut f32) -> c_int;
+
+    // ---- store diagnostics / knobs ----
+    pub fn sg_store_dim(s: *const SgStore, dim_out: *mut u32) -> c_int;
+    pub fn sg_store_metric(s: *const SgStore, metric_out: *mut c_int) -> c_int;
+    /// in_place = 1: rows live in a reserved address range that grows by mapping chunks (no copy of the corpus)
+    pub fn sg_store_memory_info(s: *mut SgStore, in_place: *mut c_int, capacity_rows: *mut u64, bytes: *mut u64,
+                                chunks: *mut u32) -> c_int;
+    /// queries served by the tensor-core sweep / of those, re-run on the exact sweep (results are exact either way)
+    pub fn sg_store_tc_stats(s: *mut SgStore, queries: *mut u64, flagged: *mut u64) -> c_int;
+    /// 0 = automatic (tensor-core sweep for batches), 1 = exact sweep only
+    pub fn sg_store_set_tc_mode(s: *mut SgStore, mode: c_int) -> c_int;
+    pub fn sg_store_set_id_base(s: *mut SgStore, id_base: u32) -> c_int;
+    pub fn sg_store_set_graph(s: *mut SgStore, max_degree: u32, medoid: u32, deg: *const u32, nbr: *const u32,
+                              stride: u32, n_nodes: u64) -> c_int;
+    pub fn sg_store_get_graph(s: *mut SgStore, deg_out: *mut u32, nbr_out: *mut u32, n_nodes: u64) -> c_int;
+    pub fn sg_store_graph_info(s: *mut SgStore, max_degree: *mut u32, medoid: *mut u32, graph_len: *mut u64) -> c_int;
+
+    // ---- pq.rs: ProductQuantizer + CompressedVectorStore (src/vector_db/pq.rs:94-466) ----
+    pub fn sg_pq_create(out: *mut *mut SgPq, device: c_int, dim: u32, subvec_dim: u32, num_centroids: u32,
+                        centroids: *const f32) -> c_int;
+    /// `orders` [dim/subvec_dim][n]: the shuffled index orders `kmeans` draws from `thread_rng` (pq.rs:157-159)
+    pub fn sg_pq_train(out: *mut *mut SgPq, device: c_int, dim: u32, subvec_dim: u32, num_centroids: u32, iterations: u32,
+                       vectors: *const f32, n: u64, orders: *const u32) -> c_int;
+    pub fn sg_pq_destroy(p: *mut SgPq);
+    pub fn sg_pq_info(p: *mut SgPq, dim: *mut u32, num_subvectors: *mut u32, num_centroids: *mut u32, len: *mut u64) -> c_int;
+    pub fn sg_pq_get_centroids(p: *mut SgPq, centroids_out: *mut f32) -> c_int;
+    pub fn sg_pq_encode(p: *mut SgPq, rows: *const f32, n: u64, codes_out: *mut u8) -> c_int;
+    pub fn sg_pq_decode(p: *mut SgPq, codes: *const u8, n: u64, rows_out: *mut f32) -> c_int;
+    pub fn sg_pq_table(p: *mut SgPq, query: *const f32, table_out: *mut f32) -> c_int;
+    pub fn sg_pq_add(p: *mut SgPq, ids: *const u32, rows: *const f32, n: u64) -> c_int;
+    pub fn sg_pq_search(p: *mut SgPq, queries: *const f32, b: u32, k: u32, ids: *mut u32, dist: *mut f32,
+                        counts: *mut u32) -> c_int;
+
+    // ---- spann.rs: SpannIndex (src/vector_db/spann.rs:363-1083) ----
+    pub fn sg_spann_build(out: *mut *mut SgSpann, device: c_int, dim: u32, num_partitions: u32, num_probes: u32,
+                          kmeans_iterations: u32, metric: c_int, vectors: *const f32, n: u64, order: *const u32,
+                          pq_iterations: u32, pq_orders: *const u32) -> c_int;
+    pub fn sg_spann_destroy(s: *mut SgSpann);
+    pub fn sg_spann_info(s: *mut SgSpann, num_partitions: *mut u32, len: *mut u64, num_probes: *mut u32) -> c_int;
+    pub fn sg_spann_set_probes(s: *mut SgSpann, num_probes: u32) -> c_int;
+    pub fn sg_spann_load_file(out: *mut *mut SgSpann, device: c_int, path: *const c_char, num_probes: u32,
+                              verify_checksum: c_int) -> c_int;
+    pub fn sg_spann_save_file(s: *mut SgSpann, path: *const c_char) -> c_int;
+    pub fn sg_spann_insert(s: *mut SgSpann, vector_id: u32, vector: *const f32) -> c_int;
+    pub fn sg_spann_search(s: *mut SgSpann, queries: *const f32, b: u32, k: u32, ids: *mut u32, dist: *mut f32,
+                           counts: *mut u32) -> c_int;
 }
 
 /// negative status -> anyhow error carrying the library's message (never panics, never aborts)
