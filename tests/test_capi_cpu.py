@@ -52,3 +52,27 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_rust_binding_source_matches_the_header(sg):
+    """rust/gpu_ffi.rs is not compiled here (no Rust toolchain): at least every `pub fn sg_*` it declares must be an
+    entry point include/shodh_gpu.h declares (and the library exports), with the same number of parameters."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rs = open(os.path.join(root, "rust", "gpu_ffi.rs")).read()
+    hdr = open(os.path.join(root, "include", "shodh_gpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    declared = set(sg.capi.declared_symbols())
+    c_arity = {}
+    for m in re.finditer(r"SG_API\s+[\w\s\*]+?\b(sg_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).strip()
+        c_arity[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    fns = re.findall(r"pub fn (sg_\w+)\s*\(([^;]*?)\)\s*(?:->\s*[\w\*\s:]+)?;", rs, flags=re.S)
+    assert len(fns) >= 60
+    for name, args in fns:
+        assert name in declared, f"{name} is declared in rust/gpu_ffi.rs but not in include/shodh_gpu.h"
+        n = 0 if not args.strip() else args.count(",") + 1
+        assert n == c_arity[name], f"{name}: {n} parameters in rust/gpu_ffi.rs, {c_arity[name]} in the header"
+    for f in ("gpu_store.rs", "gpu_embedder.rs", "gpu_pq.rs"):       # every call in the wrappers resolves to a declaration
+        for name in set(re.findall(r"\b(sg_\w+)\s*\(", open(os.path.join(root, "rust", f)).read())):
+            assert name in dict(fns) or name == "sg_last_error", (f, name)
