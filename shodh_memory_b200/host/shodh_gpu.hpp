@@ -46,6 +46,14 @@ public:
 
     /// VamanaIndex::len
     size_t len() const { uint64_t n = 0; check(sg_store_len(h_, &n)); return (size_t)n; }
+    /// how the row matrix is held: grows in place (CUDA virtual-memory chunks) or by allocate-and-copy; rows that fit
+    struct MemoryInfo { bool in_place; uint64_t capacity_rows, bytes; uint32_t chunks; };
+    MemoryInfo memory_info() const
+    {
+        int ip = 0; uint64_t cap = 0, by = 0; uint32_t ch = 0;
+        check(sg_store_memory_info(h_, &ip, &cap, &by, &ch));
+        return MemoryInfo{ip != 0, cap, by, ch};
+    }
     bool is_empty() const { return len() == 0; }
     /// VamanaIndex::add_vector -> the new (dense, sequential) id
     uint32_t add_vector(const std::vector<float> &v)

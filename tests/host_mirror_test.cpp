@@ -75,6 +75,32 @@ int main()
             REQUIRE(st.add_vector(test_vector(300, 384)) == 300);  // linked into the graph like add_vector
             REQUIRE(st.search_ann(test_vector(300, 384), 3).size() == 3);
         }
+        // storage: the rows that were appended one by one fit, and the matrix is reported consistently
+        {
+            auto mi = st.memory_info();
+            REQUIRE(mi.capacity_rows >= st.len() && mi.bytes >= st.len() * 384 * 4 && mi.chunks >= 1);
+        }
+        // pq.rs:622-641 (test_encode_decode shape): a quantizer with one centroid per axis point encodes to the nearest
+        // centroid, the compressed store returns (id, distance) ascending
+        {
+            const uint32_t dim = 32, ds = 8, kc = 4, m = dim / ds;
+            std::vector<float> cent((size_t)m * kc * ds);
+            for (uint32_t s2 = 0; s2 < m; ++s2)
+                for (uint32_t c = 0; c < kc; ++c)
+                    for (uint32_t d = 0; d < ds; ++d) cent[((size_t)s2 * kc + c) * ds + d] = (float)c;   // centroid c = (c, c, ..., c)
+            shodh::GpuProductQuantizer pq(cent, dim, ds, kc, 0);
+            std::vector<float> v(dim);
+            for (uint32_t d = 0; d < dim; ++d) v[d] = (float)((d / ds) % kc) + 0.1f;
+            auto codes = pq.encode(v);
+            REQUIRE(codes.size() == m);
+            for (uint32_t s2 = 0; s2 < m; ++s2) REQUIRE(codes[s2] == s2 % kc);
+            pq.add(42, v);
+            std::vector<float> w(dim, 3.0f);
+            pq.add(7, w);
+            REQUIRE(pq.len() == 2);
+            auto r = pq.search(v, 2);
+            REQUIRE(r.size() == 2 && r[0].first == 42 && r[1].first == 7 && r[0].second <= r[1].second);
+        }
         std::printf("HOST_MIRROR_OK\n");
         return 0;
     } catch (const std::exception &e) {
