@@ -956,6 +956,50 @@ __global__ void embed_ln_kernel(const int64_t *__restrict__ ids, uint32_t T, uin
     int64_t id = ids[tok];
     if (id < 0 || id >= (int64_t)vocab) id = 0;
     const uint32_t p = tok % L;
+    // lane owns 4 consecutive dimensions per 128-wide step: 16-byte loads of the three embedding rows (H % 128 == 0 for
+    // the models this kernel serves; otherwise the scalar walk below)
+    if ((H & 127u) == 0 && H <= 512) {
+        const float4 *w4 = reinterpret_cast<const float4 *>(word + (size_t)id * H);
+        const float4 *p4 = reinterpret_cast<const float4 *>(pos + (size_t)p * H);
+        const float4 *t4 = reinterpret_cast<const float4 *>(type0);
+        const float4 *g4 = reinterpret_cast<const float4 *>(gamma), *b4 = reinterpret_cast<const float4 *>(beta);
+        float4 v4[4];
+        const uint32_t steps = H / 128;
+        float sum = 0.0f;
+#pragma unroll
+        for (uint32_t i = 0; i < 4; ++i) {
+            if (i < steps) {
+                const float4 a = __ldg(w4 + i * 32 + lane), b = __ldg(p4 + i * 32 + lane), c = __ldg(t4 + i * 32 + lane);
+                v4[i] = make_float4(a.x + b.x + c.x, a.y + b.y + c.y, a.z + b.z + c.z, a.w + b.w + c.w);
+                sum += (v4[i].x + v4[i].y) + (v4[i].z + v4[i].w);
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+        const float mean = sum / (float)H;
+        float var = 0.0f;
+#pragma unroll
+        for (uint32_t i = 0; i < 4; ++i) {
+            if (i < steps) {
+                const float dx = v4[i].x - mean, dy = v4[i].y - mean, dz = v4[i].z - mean, dw = v4[i].w - mean;
+                var += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xFFFFFFFFu, var, o);
+        const float rstd = rsqrtf(var / (float)H + eps);
+#pragma unroll
+        for (uint32_t i = 0; i < 4; ++i) {
+            if (i < steps) {
+                const float4 gg = __ldg(g4 + i * 32 + lane), bb = __ldg(b4 + i * 32 + lane);
+                const __half2 lo = __floats2half2_rn((v4[i].x - mean) * rstd * gg.x + bb.x, (v4[i].y - mean) * rstd * gg.y + bb.y);
+                const __half2 hi = __floats2half2_rn((v4[i].z - mean) * rstd * gg.z + bb.z, (v4[i].w - mean) * rstd * gg.w + bb.w);
+                uint2 o2;
+                o2.x = *reinterpret_cast<const uint32_t *>(&lo);
+                o2.y = *reinterpret_cast<const uint32_t *>(&hi);
+                *reinterpret_cast<uint2 *>(out + (size_t)tok * H + (i * 32 + lane) * 4) = o2;
+            }
+        }
+        return;
+    }
     float v[16];                                            // H <= 512
     float sum = 0.0f;
     uint32_t n = 0;
@@ -1561,16 +1605,16 @@ __global__ void pool_norm_kernel(const float *__restrict__ hidden, const int64_t
     pdl_trigger();
     __syncthreads();
     for (uint32_t d = threadIdx.x; d < H; d += blockDim.x) {
-        // rows are added in token order, masked rows skipped -- the loads of 8 rows are issued together, the adds stay a chain
+        // rows are added in token order, masked rows skipped -- the loads of 16 rows are issued together, the adds stay a chain
         const float *hp = hidden + (size_t)b * L * H + d;
         float acc = 0.0f;
         uint32_t cnt = 0, s = 0;
-        for (; s + 8 <= L; s += 8) {
-            float v[8];
+        for (; s + 16 <= L; s += 16) {
+            float v[16];
 #pragma unroll
-            for (uint32_t j = 0; j < 8; ++j) v[j] = hp[(size_t)(s + j) * H];
+            for (uint32_t j = 0; j < 16; ++j) v[j] = hp[(size_t)(s + j) * H];
 #pragma unroll
-            for (uint32_t j = 0; j < 8; ++j)
+            for (uint32_t j = 0; j < 16; ++j)
                 if (live[s + j]) {
                     acc = __fadd_rn(acc, v[j]);
                     ++cnt;
