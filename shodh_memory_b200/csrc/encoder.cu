@@ -719,11 +719,17 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 tmem_ld32(tmem_base + lane_base + acc * ACC_COLS + c * 32, r);
                 tmem_ld_wait();
                 __align__(16) __half o[32];
+                const float4 *b4 = reinterpret_cast<const float4 *>(bias_s + acc * BN + c * 32);   // broadcast reads, 16 bytes each
 #pragma unroll
-                for (uint32_t j = 0; j < 32; ++j) {
-                    float v = __uint_as_float(r[j]) + bias_s[acc * BN + c * 32 + j];
-                    if constexpr (EPI == EPI_BIAS_GELU) v = gelu_erf(v);
-                    o[j] = __float2half_rn(v);
+                for (uint32_t q4 = 0; q4 < 8; ++q4) {
+                    const float4 bb = b4[q4];
+                    float v0 = __uint_as_float(r[4 * q4]) + bb.x, v1 = __uint_as_float(r[4 * q4 + 1]) + bb.y;
+                    float v2 = __uint_as_float(r[4 * q4 + 2]) + bb.z, v3 = __uint_as_float(r[4 * q4 + 3]) + bb.w;
+                    if constexpr (EPI == EPI_BIAS_GELU) {
+                        v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3);
+                    }
+                    *reinterpret_cast<__half2 *>(o + 4 * q4) = __floats2half2_rn(v0, v1);
+                    *reinterpret_cast<__half2 *>(o + 4 * q4 + 2) = __floats2half2_rn(v2, v3);
                 }
                 uint8_t *rowp = my_stage + (size_t)(c >> 1) * (128 * 128) + (size_t)t * 128;
 #pragma unroll
